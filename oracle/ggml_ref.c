@@ -1,0 +1,696 @@
+/*
+ * oracle/ggml_ref.c — TEST INFRASTRUCTURE ONLY (see ggml_ref.h for the rules and parity status).
+ *
+ * Restates, on the CPU and in plain C:
+ *   (1) the ggml CPU-backend numerics the reference's graphs execute (ggml is NOT in the
+ *       reference tree: un-vendored, unpinned — README.md:183-198).  Algorithms follow the
+ *       published ggml sources (ggml-quants.c / ggml-cpu ops, generic non-SIMD paths):
+ *         block formats Q4_K / Q8_0 / Q4_0, quantize_row_q8_K / q8_0,
+ *         vec_dot_q4_K_q8_K / q8_0_q8_0 / q4_0_q8_0, rms_norm, soft_max_ext, silu, argmax,
+ *         timestep_embedding, bf16 KV "weights" with bf16-rounded second operand.
+ *   (2) the reference's own graph semantics for the LM decode step:
+ *         src/moshi/models/lm.h:446-690, 778-979; src/moshi/modules/transformer.h:15-23,
+ *         149-249, 449-712, 910-1039, 1217-1289; src/moshi/modules/rope.h:8-128;
+ *         src/moshi/modules/gating.h:12-37; src/torch.h:79-118, 162-237;
+ *         src/moshi/models/lm_utils.h:126-217; src/moshi/utils/sampling.h:46-64.
+ */
+#include "ggml_ref.h"
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <limits.h>
+
+#define QK_K 256
+#define QK8_0 32
+#define QK4_0 32
+
+/* ------------------------------------------------------------------------------------------------
+ * scalar conversions (ggml-impl.h: ggml_compute_fp32_to_bf16, GGML_FP16_TO_FP32)
+ * ---------------------------------------------------------------------------------------------- */
+float orc_fp16_to_fp32(uint16_t h) { _Float16 f; memcpy(&f, &h, 2); return (float)f; }
+uint16_t orc_fp32_to_fp16(float f) { _Float16 h = (_Float16)f; uint16_t u; memcpy(&u, &h, 2); return u; }
+uint16_t orc_fp32_to_bf16(float f) {
+    uint32_t u; memcpy(&u, &f, 4);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 64); /* quiet NaN */
+    return (uint16_t)((u + (0x7fffu + ((u >> 16) & 1u))) >> 16);
+}
+float orc_bf16_to_fp32(uint16_t h) { uint32_t u = (uint32_t)h << 16; float f; memcpy(&f, &u, 4); return f; }
+static inline float bf16_round(float f) { return orc_bf16_to_fp32(orc_fp32_to_bf16(f)); }
+
+/* ggml-quants.c nearest_int(): round-to-nearest-even via the 1.5*2^23 magic constant */
+static inline int nearest_int(float fval) {
+    float val = fval + 12582912.f;
+    int i; memcpy(&i, &val, sizeof(int));
+    return (i & 0x007fffff) - 0x00400000;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * block formats (ggml-common.h block_q4_K / block_q8_0 / block_q4_0; cross-checked with gguf/quants.py)
+ * ---------------------------------------------------------------------------------------------- */
+#pragma pack(push, 1)
+typedef struct { uint16_t d, dmin; uint8_t scales[12]; uint8_t qs[QK_K / 2]; } block_q4_K; /* 144 B */
+typedef struct { uint16_t d; int8_t qs[QK8_0]; } block_q8_0;                               /* 34 B  */
+typedef struct { uint16_t d; uint8_t qs[QK4_0 / 2]; } block_q4_0;                          /* 18 B  */
+#pragma pack(pop)
+
+int64_t orc_row_size(int type, int64_t k) {
+    switch (type) {
+        case ORC_F32: return 4 * k;
+        case ORC_F16: case ORC_BF16: return 2 * k;
+        case ORC_Q4_0: return k / QK4_0 * (int64_t)sizeof(block_q4_0);
+        case ORC_Q8_0: return k / QK8_0 * (int64_t)sizeof(block_q8_0);
+        case ORC_Q4_K: return k / QK_K * (int64_t)sizeof(block_q4_K);
+    }
+    return -1;
+}
+
+/* ggml-quants.c get_scale_min_k4 */
+static inline void get_scale_min_k4(int j, const uint8_t *q, uint8_t *d, uint8_t *m) {
+    if (j < 4) { *d = q[j] & 63; *m = q[j + 4] & 63; }
+    else {
+        *d = (q[j + 4] & 0xF) | ((q[j - 4] >> 6) << 4);
+        *m = (q[j + 4] >> 4) | ((q[j - 0] >> 6) << 4);
+    }
+}
+
+/* dequantize_row_q4_K / q8_0 / q4_0 (ggml-quants.c). Compiled with -ffp-contract=off so that
+ * d1*q - m1 keeps two roundings, like gguf-py's (d*sc)*q - (dmin*m). */
+void orc_dequantize_row(int type, const void *src, float *y, int64_t k) {
+    if (type == ORC_F32) { memcpy(y, src, 4 * k); return; }
+    if (type == ORC_F16) { const uint16_t *s = src; for (int64_t i = 0; i < k; i++) y[i] = orc_fp16_to_fp32(s[i]); return; }
+    if (type == ORC_BF16) { const uint16_t *s = src; for (int64_t i = 0; i < k; i++) y[i] = orc_bf16_to_fp32(s[i]); return; }
+    if (type == ORC_Q8_0) {
+        const block_q8_0 *x = src;
+        for (int64_t i = 0; i < k / QK8_0; i++) {
+            const float d = orc_fp16_to_fp32(x[i].d);
+            for (int j = 0; j < QK8_0; j++) y[i * QK8_0 + j] = x[i].qs[j] * d;
+        }
+        return;
+    }
+    if (type == ORC_Q4_0) {
+        const block_q4_0 *x = src;
+        for (int64_t i = 0; i < k / QK4_0; i++) {
+            const float d = orc_fp16_to_fp32(x[i].d);
+            for (int j = 0; j < QK4_0 / 2; j++) {
+                const int x0 = (x[i].qs[j] & 0x0F) - 8;
+                const int x1 = (x[i].qs[j] >> 4) - 8;
+                y[i * QK4_0 + j] = x0 * d;
+                y[i * QK4_0 + j + QK4_0 / 2] = x1 * d;
+            }
+        }
+        return;
+    }
+    if (type == ORC_Q4_K) {
+        const block_q4_K *x = src;
+        for (int64_t i = 0; i < k / QK_K; i++) {
+            const uint8_t *q = x[i].qs;
+            const float d = orc_fp16_to_fp32(x[i].d);
+            const float min = orc_fp16_to_fp32(x[i].dmin);
+            int is = 0; uint8_t sc, m;
+            for (int j = 0; j < QK_K; j += 64) {
+                get_scale_min_k4(is + 0, x[i].scales, &sc, &m);
+                const float d1 = d * sc; const float m1 = min * m;
+                get_scale_min_k4(is + 1, x[i].scales, &sc, &m);
+                const float d2 = d * sc; const float m2 = min * m;
+                for (int l = 0; l < 32; ++l) *y++ = d1 * (q[l] & 0xF) - m1;
+                for (int l = 0; l < 32; ++l) *y++ = d2 * (q[l] >> 4) - m2;
+                q += 32; is += 2;
+            }
+        }
+        return;
+    }
+    fprintf(stderr, "orc_dequantize_row: unsupported type %d\n", type); abort();
+}
+
+/* quantize_row_q8_0_ref: d = amax/127, q = roundf(x/d), d stored fp16 */
+void orc_quantize_row_q8_0(const float *x, void *dst, int64_t k) {
+    block_q8_0 *y = dst;
+    for (int64_t i = 0; i < k / QK8_0; i++) {
+        float amax = 0.0f;
+        for (int j = 0; j < QK8_0; j++) { const float v = fabsf(x[i * QK8_0 + j]); if (v > amax) amax = v; }
+        const float d = amax / ((1 << 7) - 1);
+        const float id = d ? 1.0f / d : 0.0f;
+        y[i].d = orc_fp32_to_fp16(d);
+        for (int j = 0; j < QK8_0; ++j) y[i].qs[j] = (int8_t)roundf(x[i * QK8_0 + j] * id);
+    }
+}
+
+/* quantize_row_q8_K_ref: iscale = -127/max(|x|-carrier), q = min(127, nearest_int(iscale*x)), d = 1/iscale */
+void orc_quantize_row_q8_K(const float *x, int8_t *qs, float *dout, int16_t *bsums, int64_t k) {
+    for (int64_t i = 0; i < k / QK_K; i++) {
+        float max = 0, amax = 0;
+        for (int j = 0; j < QK_K; ++j) { float ax = fabsf(x[j]); if (ax > amax) { amax = ax; max = x[j]; } }
+        if (!amax) {
+            dout[i] = 0; memset(qs, 0, QK_K); for (int j = 0; j < QK_K / 16; j++) bsums[j] = 0;
+            x += QK_K; qs += QK_K; bsums += QK_K / 16; continue;
+        }
+        const float iscale = -127.f / max;
+        for (int j = 0; j < QK_K; ++j) { int v = nearest_int(iscale * x[j]); qs[j] = (int8_t)(v < 127 ? v : 127); }
+        for (int j = 0; j < QK_K / 16; ++j) { int sum = 0; for (int ii = 0; ii < 16; ++ii) sum += qs[j * 16 + ii]; bsums[j] = (int16_t)sum; }
+        dout[i] = 1 / iscale;
+        x += QK_K; qs += QK_K; bsums += QK_K / 16;
+    }
+}
+
+/* ggml_vec_dot_q4_K_q8_K (generic path): exact integer inner sums, fp32 8-lane partials */
+static float vec_dot_q4_K_q8_K(int64_t n, const block_q4_K *x, const int8_t *yqs, const float *yd, const int16_t *ybsums) {
+    const int nb = (int)(n / QK_K);
+    int8_t aux8[QK_K]; int16_t aux16[8]; float sums[8]; int32_t aux32[8];
+    uint8_t scales[8], mins[8];
+    memset(sums, 0, sizeof(sums));
+    float sumf = 0;
+    for (int i = 0; i < nb; ++i) {
+        const uint8_t *q4 = x[i].qs;
+        const int8_t *q8 = yqs + (int64_t)i * QK_K;
+        const int16_t *bs = ybsums + (int64_t)i * (QK_K / 16);
+        memset(aux32, 0, sizeof(aux32));
+        int8_t *a = aux8;
+        for (int j = 0; j < QK_K / 64; ++j) {
+            for (int l = 0; l < 32; ++l) a[l] = (int8_t)(q4[l] & 0xF);
+            a += 32;
+            for (int l = 0; l < 32; ++l) a[l] = (int8_t)(q4[l] >> 4);
+            a += 32; q4 += 32;
+        }
+        for (int j = 0; j < 8; j++) get_scale_min_k4(j, x[i].scales, &scales[j], &mins[j]);
+        int sumi = 0;
+        for (int j = 0; j < QK_K / 16; ++j) sumi += bs[j] * mins[j / 2];
+        a = aux8;
+        int is = 0;
+        for (int j = 0; j < QK_K / 32; ++j) {
+            int32_t scale = scales[is++];
+            for (int r = 0; r < 4; r++) {
+                for (int l = 0; l < 8; ++l) aux16[l] = (int16_t)(q8[l] * a[l]);
+                for (int l = 0; l < 8; ++l) aux32[l] += scale * aux16[l];
+                q8 += 8; a += 8;
+            }
+        }
+        const float d = orc_fp16_to_fp32(x[i].d) * yd[i];
+        for (int l = 0; l < 8; ++l) sums[l] += d * aux32[l];
+        const float dmin = orc_fp16_to_fp32(x[i].dmin) * yd[i];
+        sumf -= dmin * sumi;
+    }
+    for (int l = 0; l < 8; ++l) sumf += sums[l];
+    return sumf;
+}
+
+/* ggml_vec_dot_q8_0_q8_0 (generic) */
+static float vec_dot_q8_0_q8_0(int64_t n, const block_q8_0 *x, const block_q8_0 *y) {
+    const int nb = (int)(n / QK8_0);
+    float sumf = 0;
+    for (int ib = 0; ib < nb; ++ib) {
+        int sumi = 0;
+        for (int j = 0; j < QK8_0; j++) sumi += x[ib].qs[j] * y[ib].qs[j];
+        sumf += sumi * (orc_fp16_to_fp32(x[ib].d) * orc_fp16_to_fp32(y[ib].d));
+    }
+    return sumf;
+}
+
+/* ggml_vec_dot_q4_0_q8_0 (generic) */
+static float vec_dot_q4_0_q8_0(int64_t n, const block_q4_0 *x, const block_q8_0 *y) {
+    const int nb = (int)(n / QK4_0);
+    float sumf = 0;
+    for (int ib = 0; ib < nb; ++ib) {
+        int sumi0 = 0, sumi1 = 0;
+        for (int j = 0; j < QK4_0 / 2; ++j) {
+            const int v0 = (x[ib].qs[j] & 0x0F) - 8;
+            const int v1 = (x[ib].qs[j] >> 4) - 8;
+            sumi0 += v0 * y[ib].qs[j];
+            sumi1 += v1 * y[ib].qs[j + QK4_0 / 2];
+        }
+        int sumi = sumi0 + sumi1;
+        sumf += sumi * orc_fp16_to_fp32(x[ib].d) * orc_fp16_to_fp32(y[ib].d);
+    }
+    return sumf;
+}
+
+/* ggml_compute_forward_mul_mat for one f32 activation column: src1 is converted to the weight
+ * type's vec_dot_type (Q8_K for Q4_K, Q8_0 for Q8_0/Q4_0, bf16/f16 for bf16/f16), then rows of
+ * src0 are dotted against it. */
+void orc_mul_mat_vec(int type, const void *w, int64_t k, int64_t rows, const float *x, float *y) {
+    const int64_t rs = orc_row_size(type, k);
+    if (type == ORC_Q4_K) {
+        int8_t *qs = malloc(k); float *d = malloc(sizeof(float) * (k / QK_K)); int16_t *bs = malloc(sizeof(int16_t) * (k / 16));
+        orc_quantize_row_q8_K(x, qs, d, bs, k);
+        #pragma omp parallel for schedule(static)
+        for (int64_t r = 0; r < rows; r++)
+            y[r] = vec_dot_q4_K_q8_K(k, (const block_q4_K *)((const char *)w + r * rs), qs, d, bs);
+        free(qs); free(d); free(bs);
+    } else if (type == ORC_Q8_0 || type == ORC_Q4_0) {
+        block_q8_0 *xq = malloc(sizeof(block_q8_0) * (k / QK8_0));
+        orc_quantize_row_q8_0(x, xq, k);
+        #pragma omp parallel for schedule(static)
+        for (int64_t r = 0; r < rows; r++) {
+            const char *wr = (const char *)w + r * rs;
+            y[r] = type == ORC_Q8_0 ? vec_dot_q8_0_q8_0(k, (const block_q8_0 *)wr, xq)
+                                    : vec_dot_q4_0_q8_0(k, (const block_q4_0 *)wr, xq);
+        }
+        free(xq);
+    } else if (type == ORC_F32 || type == ORC_BF16 || type == ORC_F16) {
+        /* f32: plain dot (ggml_vec_dot_f32, ggml_float accumulate); bf16/f16: x rounded to that type */
+        float *xr = malloc(sizeof(float) * k);
+        for (int64_t i = 0; i < k; i++)
+            xr[i] = type == ORC_F32 ? x[i] : type == ORC_BF16 ? bf16_round(x[i]) : orc_fp16_to_fp32(orc_fp32_to_fp16(x[i]));
+        #pragma omp parallel for schedule(static)
+        for (int64_t r = 0; r < rows; r++) {
+            const char *wr = (const char *)w + r * rs;
+            double acc = 0;
+            for (int64_t i = 0; i < k; i++) {
+                float wv = type == ORC_F32 ? ((const float *)wr)[i]
+                         : type == ORC_BF16 ? orc_bf16_to_fp32(((const uint16_t *)wr)[i]) : orc_fp16_to_fp32(((const uint16_t *)wr)[i]);
+                acc += (double)(wv * xr[i]);
+            }
+            y[r] = (float)acc;
+        }
+        free(xr);
+    } else { fprintf(stderr, "orc_mul_mat_vec: unsupported type %d\n", type); abort(); }
+}
+
+/* T2 "ideal": dequantised weights, fp32 activations, double accumulation */
+void orc_mul_mat_vec_ideal(int type, const void *w, int64_t k, int64_t rows, const float *x, float *y) {
+    const int64_t rs = orc_row_size(type, k);
+    #pragma omp parallel
+    {
+        float *row = malloc(sizeof(float) * k);
+        #pragma omp for schedule(static)
+        for (int64_t r = 0; r < rows; r++) {
+            orc_dequantize_row(type, (const char *)w + r * rs, row, k);
+            double acc = 0;
+            for (int64_t i = 0; i < k; i++) acc += (double)row[i] * (double)x[i];
+            y[r] = (float)acc;
+        }
+        free(row);
+    }
+}
+
+/* ggml_compute_forward_rms_norm_f32 then ggml_mul(alpha, y)  (transformer.h:15-23) */
+void orc_rms_norm(const float *x, const float *alpha, float eps, float *y, int64_t n) {
+    double sum = 0.0;
+    for (int64_t i = 0; i < n; i++) sum += (double)(x[i] * x[i]);
+    const float mean = (float)(sum / n);
+    const float scale = 1.0f / sqrtf(mean + eps);
+    for (int64_t i = 0; i < n; i++) { float v = x[i] * scale; y[i] = alpha ? alpha[i] * v : v; }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * model
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct { int type; int64_t ne0, ne1; const void *data; } orc_tensor;
+
+typedef struct {
+    orc_tensor norm1, norm2;
+    orc_tensor *in_proj, *out_proj, *lin_in, *lin_out; /* [n_weights] */
+} orc_layer;
+
+struct orc_model {
+    orc_config cfg;
+    int ideal;
+    int dep_num_weights, dep_cap;
+    orc_tensor text_emb, *emb /*[n_q]*/;
+    orc_layer *layers /*[num_layers]*/;
+    orc_tensor out_norm, text_linear;
+    orc_tensor *dep_in /*[dep_num_weights]*/, dep_text_emb, *dep_emb /*[dep_q-1]*/;
+    orc_layer *dep_layers;
+    orc_tensor *linears /*[dep_q]*/;
+    orc_tensor *extra_heads;
+};
+
+static int dep_num_weights(const orc_config *c) {
+    /* lm_default.h:72-83 */
+    int n = c->dep_q;
+    if (c->schedule_len) { int mx = c->schedule[0]; for (int i = 0; i < c->schedule_len; i++) if (c->schedule[i] > mx) mx = c->schedule[i]; n = mx + 1; }
+    return n;
+}
+
+orc_model *orc_model_new(const orc_config *cfg) {
+    orc_model *m = calloc(1, sizeof(*m));
+    m->cfg = *cfg;
+    const orc_config *c = &m->cfg;
+    m->dep_num_weights = dep_num_weights(c);
+    m->dep_cap = c->dep_context ? c->dep_context : c->schedule_len; /* transformer.h:327, lm_default.h:92 */
+    m->emb = calloc(c->n_q, sizeof(orc_tensor));
+    m->layers = calloc(c->num_layers, sizeof(orc_layer));
+    for (int i = 0; i < c->num_layers; i++) {
+        orc_layer *l = &m->layers[i];
+        l->in_proj = calloc(1, sizeof(orc_tensor)); l->out_proj = calloc(1, sizeof(orc_tensor));
+        l->lin_in = calloc(1, sizeof(orc_tensor)); l->lin_out = calloc(1, sizeof(orc_tensor));
+    }
+    if (c->dep_q > 0) {
+        int nw = m->dep_num_weights;
+        m->dep_in = calloc(nw, sizeof(orc_tensor));
+        m->dep_emb = calloc(c->dep_q > 1 ? c->dep_q - 1 : 1, sizeof(orc_tensor));
+        m->dep_layers = calloc(c->dep_layers, sizeof(orc_layer));
+        for (int i = 0; i < c->dep_layers; i++) {
+            orc_layer *l = &m->dep_layers[i];
+            l->in_proj = calloc(nw, sizeof(orc_tensor)); l->out_proj = calloc(nw, sizeof(orc_tensor));
+            l->lin_in = calloc(nw, sizeof(orc_tensor)); l->lin_out = calloc(nw, sizeof(orc_tensor));
+        }
+        m->linears = calloc(c->dep_q, sizeof(orc_tensor));
+    }
+    if (c->extra_heads > 0) m->extra_heads = calloc(c->extra_heads, sizeof(orc_tensor));
+    return m;
+}
+
+void orc_model_free(orc_model *m) {
+    if (!m) return;
+    const orc_config *c = &m->cfg;
+    for (int i = 0; i < c->num_layers; i++) { orc_layer *l = &m->layers[i]; free(l->in_proj); free(l->out_proj); free(l->lin_in); free(l->lin_out); }
+    if (m->dep_layers) for (int i = 0; i < c->dep_layers; i++) { orc_layer *l = &m->dep_layers[i]; free(l->in_proj); free(l->out_proj); free(l->lin_in); free(l->lin_out); }
+    free(m->emb); free(m->layers); free(m->dep_in); free(m->dep_emb); free(m->dep_layers); free(m->linears); free(m->extra_heads);
+    free(m);
+}
+
+void orc_model_set_ideal(orc_model *m, int ideal) { m->ideal = ideal; }
+
+/* name resolution follows get_weights(): lm.h:370-395, transformer.h:764-779, 1042-1080, gating.h:39-43 */
+static orc_tensor *find_slot(orc_model *m, const char *name) {
+    const orc_config *c = &m->cfg;
+    int a, b; char tail[64];
+    if (!strcmp(name, "lm.text_emb.weight")) return &m->text_emb;
+    if (!strcmp(name, "lm.out_norm.alpha")) return &m->out_norm;
+    if (!strcmp(name, "lm.text_linear.weight")) return &m->text_linear;
+    if (!strcmp(name, "lm.depformer_text_emb.weight")) return c->dep_q > 0 ? &m->dep_text_emb : NULL;
+    if (sscanf(name, "lm.emb.%d.weigh%1[t]", &a, tail) == 2) return a < c->n_q ? &m->emb[a] : NULL;
+    if (sscanf(name, "lm.depformer_in.%d.weigh%1[t]", &a, tail) == 2) return (m->dep_in && a < m->dep_num_weights) ? &m->dep_in[a] : NULL;
+    if (sscanf(name, "lm.depformer_emb.%d.weigh%1[t]", &a, tail) == 2) return (m->dep_emb && a < c->dep_q - 1) ? &m->dep_emb[a] : NULL;
+    if (sscanf(name, "lm.linears.%d.weigh%1[t]", &a, tail) == 2) return (m->linears && a < c->dep_q) ? &m->linears[a] : NULL;
+    if (sscanf(name, "lm.extra_heads.%d.weigh%1[t]", &a, tail) == 2) return (m->extra_heads && a < c->extra_heads) ? &m->extra_heads[a] : NULL;
+    if (sscanf(name, "lm.transformer.layers.%d.%63s", &a, tail) == 2 && a < c->num_layers) {
+        orc_layer *l = &m->layers[a];
+        if (!strcmp(tail, "norm1.alpha")) return &l->norm1;
+        if (!strcmp(tail, "norm2.alpha")) return &l->norm2;
+        if (!strcmp(tail, "self_attn.in_projs.0.weight")) return &l->in_proj[0];
+        if (!strcmp(tail, "self_attn.out_projs.0.weight")) return &l->out_proj[0];
+        if (!strcmp(tail, "gating.linear_in.weight")) return &l->lin_in[0];
+        if (!strcmp(tail, "gating.linear_out.weight")) return &l->lin_out[0];
+        return NULL;
+    }
+    if (m->dep_layers && sscanf(name, "lm.depformer.layers.%d.%63s", &a, tail) == 2 && a < c->dep_layers) {
+        orc_layer *l = &m->dep_layers[a];
+        if (!strcmp(tail, "norm1.alpha")) return &l->norm1;
+        if (!strcmp(tail, "norm2.alpha")) return &l->norm2;
+        if (sscanf(tail, "self_attn.in_projs.%d.weigh%1[t]", &b, tail + 60) == 2) return b < m->dep_num_weights ? &l->in_proj[b] : NULL;
+        if (sscanf(tail, "self_attn.out_projs.%d.weigh%1[t]", &b, tail + 60) == 2) return b < m->dep_num_weights ? &l->out_proj[b] : NULL;
+        if (sscanf(tail, "gating.%d.linear_in.weigh%1[t]", &b, tail + 60) == 2) return b < m->dep_num_weights ? &l->lin_in[b] : NULL;
+        if (sscanf(tail, "gating.%d.linear_out.weigh%1[t]", &b, tail + 60) == 2) return b < m->dep_num_weights ? &l->lin_out[b] : NULL;
+        /* single-weight depformer: "gating.linear_in.weight" (transformer.h:1064-1066) */
+        if (!strcmp(tail, "gating.linear_in.weight")) return &l->lin_in[0];
+        if (!strcmp(tail, "gating.linear_out.weight")) return &l->lin_out[0];
+        return NULL;
+    }
+    return NULL;
+}
+
+int orc_model_set_tensor(orc_model *m, const char *name, int type, int64_t ne0, int64_t ne1, const void *data) {
+    orc_tensor *t = find_slot(m, name);
+    if (!t) return 0;
+    t->type = type; t->ne0 = ne0; t->ne1 = ne1; t->data = data;
+    return 1;
+}
+
+int orc_model_missing(orc_model *m, char *buf, int buflen) {
+    const orc_config *c = &m->cfg; int n = 0; if (buf && buflen) buf[0] = 0;
+#define CHK(t, nm) do { if (!(t).data) { if (!n && buf) snprintf(buf, buflen, "%s", nm); n++; } } while (0)
+    CHK(m->text_emb, "text_emb"); CHK(m->out_norm, "out_norm"); CHK(m->text_linear, "text_linear");
+    for (int i = 0; i < c->n_q; i++) CHK(m->emb[i], "emb");
+    for (int i = 0; i < c->num_layers; i++) { orc_layer *l = &m->layers[i]; CHK(l->norm1, "norm1"); CHK(l->norm2, "norm2"); CHK(l->in_proj[0], "in_proj"); CHK(l->out_proj[0], "out_proj"); CHK(l->lin_in[0], "lin_in"); CHK(l->lin_out[0], "lin_out"); }
+    if (c->dep_q > 0) {
+        CHK(m->dep_text_emb, "dep_text_emb");
+        for (int i = 0; i < m->dep_num_weights; i++) CHK(m->dep_in[i], "dep_in");
+        for (int i = 0; i < c->dep_q - 1; i++) CHK(m->dep_emb[i], "dep_emb");
+        for (int i = 0; i < c->dep_q; i++) CHK(m->linears[i], "linears");
+        for (int i = 0; i < c->dep_layers; i++) { orc_layer *l = &m->dep_layers[i]; CHK(l->norm1, "dnorm1"); CHK(l->norm2, "dnorm2");
+            for (int w = 0; w < m->dep_num_weights; w++) { CHK(l->in_proj[w], "din_proj"); CHK(l->out_proj[w], "dout_proj"); CHK(l->lin_in[w], "dlin_in"); CHK(l->lin_out[w], "dlin_out"); } }
+    }
+    for (int i = 0; i < c->extra_heads; i++) CHK(m->extra_heads[i], "extra_heads");
+#undef CHK
+    return n;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * state (transformer.h:149-172 KV ring, bf16, zero-initialised; lm.h:423-436 transformer_out)
+ * ---------------------------------------------------------------------------------------------- */
+struct orc_state {
+    orc_model *m;
+    int offset;                 /* moshi_streaming_transformer_state_t::offset */
+    uint16_t *k, *v;            /* [L][H][cap][Dh] */
+    uint16_t *dk, *dv;          /* [Ld][Hd][capd][Dhd] */
+    float *transformer_out;     /* [dim] */
+};
+
+static size_t kv_elems(const orc_config *c) { return (size_t)c->num_layers * c->context * c->dim; }
+static size_t dkv_elems(const orc_model *m) { return (size_t)m->cfg.dep_layers * m->dep_cap * m->cfg.dep_dim; }
+
+orc_state *orc_state_new(orc_model *m) {
+    orc_state *s = calloc(1, sizeof(*s));
+    s->m = m;
+    s->k = calloc(kv_elems(&m->cfg), 2); s->v = calloc(kv_elems(&m->cfg), 2);
+    if (m->cfg.dep_q > 0) { s->dk = calloc(dkv_elems(m), 2); s->dv = calloc(dkv_elems(m), 2); }
+    s->transformer_out = calloc(m->cfg.dim, sizeof(float));
+    return s;
+}
+void orc_state_free(orc_state *s) { if (!s) return; free(s->k); free(s->v); free(s->dk); free(s->dv); free(s->transformer_out); free(s); }
+void orc_state_reset(orc_state *s) {
+    s->offset = 0;
+    memset(s->k, 0, kv_elems(&s->m->cfg) * 2); memset(s->v, 0, kv_elems(&s->m->cfg) * 2);
+    if (s->dk) { memset(s->dk, 0, dkv_elems(s->m) * 2); memset(s->dv, 0, dkv_elems(s->m) * 2); }
+    memset(s->transformer_out, 0, sizeof(float) * s->m->cfg.dim);
+}
+int orc_state_offset(orc_state *s) { return s->offset; }
+void orc_state_get_kv(orc_state *s, int layer, int head, int slot, uint16_t *k, uint16_t *v) {
+    const orc_config *c = &s->m->cfg; int Dh = c->dim / c->num_heads;
+    size_t o = (((size_t)layer * c->num_heads + head) * c->context + slot) * Dh;
+    memcpy(k, s->k + o, 2 * Dh); memcpy(v, s->v + o, 2 * Dh);
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * building blocks
+ * ---------------------------------------------------------------------------------------------- */
+static void linear(const orc_model *m, const orc_tensor *w, const float *x, float *y) {
+    /* torch_nn_linear (torch.h:79-87); LM linears carry no bias */
+    if (m->ideal) orc_mul_mat_vec_ideal(w->type, w->data, w->ne0, w->ne1, x, y);
+    else orc_mul_mat_vec(w->type, w->data, w->ne0, w->ne1, x, y);
+}
+
+/* moshi_scaled_embedding_step + get_rows*scale (lm_utils.h:157-182): -1 -> zeros, other negatives -> row 0 */
+static void embed_row(const orc_tensor *t, int token, float *row /*[ne0]*/) {
+    int is_zero = token == -1;
+    if (token < 0) token = 0;
+    orc_dequantize_row(t->type, (const char *)t->data + (int64_t)token * orc_row_size(t->type, t->ne0), row, t->ne0);
+    const float scale = is_zero ? 0.f : 1.f;
+    for (int64_t i = 0; i < t->ne0; i++) row[i] = row[i] * scale;
+}
+
+/* moshi_get_timestep_embedding (rope.h:8-20) = ggml_timestep_embedding on ts = arange(T)+offset:
+ *   freq_j = expf(-logf(max_period) * j / half);  arg = ts * freq_j;  rotr = cos(arg), roti = sin(arg) */
+static void rope_table(float offset_f32, int Dh, int max_period, float *rotr, float *roti) {
+    const int half = Dh / 2;
+    for (int j = 0; j < half; j++) {
+        float freq = (float)expf(-logf((float)max_period) * j / half);
+        float arg = offset_f32 * freq;
+        rotr[j] = cosf(arg); roti[j] = sinf(arg);
+    }
+}
+
+/* moshi_apply_rope (rope.h:33-128): interleaved pairs rotated, output [re half | im half] */
+static void apply_rope(const float *u, float *out, int Dh, const float *rotr, const float *roti) {
+    const int half = Dh / 2;
+    for (int j = 0; j < half; j++) {
+        const float r = u[2 * j], i = u[2 * j + 1];
+        out[j] = r * rotr[j] - i * roti[j];
+        out[half + j] = r * roti[j] + i * rotr[j];
+    }
+}
+
+/* torch_nn_functional_scaled_dot_product_attention_custom (torch.h:225-237) for T=1 on a bf16 ring:
+ *   scores = mul_mat(K_bf16, q)  -> q rounded to bf16; soft_max_ext(scale, bias); mul_mat(V^T_bf16, p) -> p rounded to bf16.
+ *   bias window for T=1: slot i visible iff i <= pos or pos >= cap-1 (torch.h:170-223). */
+static void attention_head(const uint16_t *K, const uint16_t *V /*[cap][Dh]*/, int cap, int Dh, int pos,
+                           const float *q, float *ctx, float *scratch /*[cap]*/, int ideal) {
+    const int n_valid = (pos >= cap - 1) ? cap : pos + 1;
+    const float scale = 1.f / sqrtf((float)Dh);
+    float maxv = -INFINITY;
+    for (int i = 0; i < n_valid; i++) {
+        double acc = 0;
+        for (int d = 0; d < Dh; d++) {
+            float qq = ideal ? q[d] : bf16_round(q[d]);
+            acc += (double)(orc_bf16_to_fp32(K[(size_t)i * Dh + d]) * qq);
+        }
+        float s = (float)acc;
+        s = s * scale + 0.0f;
+        scratch[i] = s; if (s > maxv) maxv = s;
+    }
+    double sum = 0;
+    for (int i = 0; i < n_valid; i++) { float e = expf(scratch[i] - maxv); scratch[i] = e; sum += (double)e; }
+    const float inv = (float)(1.0 / sum);
+    for (int i = 0; i < n_valid; i++) { float p = scratch[i] * inv; scratch[i] = ideal ? p : bf16_round(p); }
+    for (int d = 0; d < Dh; d++) {
+        double acc = 0;
+        for (int i = 0; i < n_valid; i++) acc += (double)(orc_bf16_to_fp32(V[(size_t)i * Dh + d]) * scratch[i]);
+        ctx[d] = (float)acc;
+    }
+}
+
+/* moshi_streaming_transformer_layer (transformer.h:910-1039), T = 1 */
+static void transformer_layer(const orc_model *m, const orc_layer *l, int w, int dim, int H, int cap,
+                              int max_period, int pos, uint16_t *Kc, uint16_t *Vc /*[H][cap][Dh]*/, float *x) {
+    const int Dh = dim / H;
+    const int F = (int)l->lin_out[w].ne0;
+    float *nx = malloc(sizeof(float) * dim), *p = malloc(sizeof(float) * 3 * dim), *ctx = malloc(sizeof(float) * dim);
+    float *upd = malloc(sizeof(float) * dim), *g = malloc(sizeof(float) * 2 * F), *mm = malloc(sizeof(float) * F);
+    float *scratch = malloc(sizeof(float) * cap), *rotr = malloc(sizeof(float) * Dh), *roti = rotr + Dh / 2;
+    float *qr = malloc(sizeof(float) * Dh), *kr = malloc(sizeof(float) * Dh);
+
+    orc_rms_norm(x, (const float *)l->norm1.data, 1e-8f, nx, dim);
+    linear(m, &l->in_proj[w], nx, p);
+    const int slot = pos % cap;
+    if (max_period) rope_table((float)pos, Dh, max_period, rotr, roti);
+    for (int h = 0; h < H; h++) {
+        const float *q = p + h * Dh, *k = p + dim + h * Dh, *v = p + 2 * dim + h * Dh;
+        if (max_period) { apply_rope(q, qr, Dh, rotr, roti); apply_rope(k, kr, Dh, rotr, roti); }
+        else { memcpy(qr, q, sizeof(float) * Dh); memcpy(kr, k, sizeof(float) * Dh); }
+        uint16_t *Kh = Kc + (size_t)h * cap * Dh, *Vh = Vc + (size_t)h * cap * Dh;
+        for (int d = 0; d < Dh; d++) { Kh[(size_t)slot * Dh + d] = orc_fp32_to_bf16(kr[d]); Vh[(size_t)slot * Dh + d] = orc_fp32_to_bf16(v[d]); }
+        attention_head(Kh, Vh, cap, Dh, pos, qr, ctx + h * Dh, scratch, m->ideal);
+    }
+    linear(m, &l->out_proj[w], ctx, upd);
+    for (int i = 0; i < dim; i++) x[i] = x[i] + upd[i];
+
+    orc_rms_norm(x, (const float *)l->norm2.data, 1e-8f, nx, dim);
+    linear(m, &l->lin_in[w], nx, g);
+    /* gating.h:12-37: silu(left) * right; ggml silu = x/(1+expf(-x)) */
+    for (int i = 0; i < F; i++) { float a = g[i]; float s = a / (1.0f + expf(-a)); mm[i] = s * g[F + i]; }
+    linear(m, &l->lin_out[w], mm, upd);
+    for (int i = 0; i < dim; i++) x[i] = x[i] + upd[i];
+
+    free(nx); free(p); free(ctx); free(upd); free(g); free(mm); free(scratch); free(rotr); free(qr); free(kr);
+}
+
+static int argmax_first(const float *v, int n) { int bi = 0; float bv = v[0]; for (int i = 1; i < n; i++) if (v[i] > bv) { bv = v[i]; bi = i; } return bi; }
+
+int orc_step_temporal(orc_model *m, orc_state *s, const int32_t *tokens, float *text_logits, float *transformer_out) {
+    const orc_config *c = &m->cfg; const int dim = c->dim;
+    float *x = malloc(sizeof(float) * dim), *row = malloc(sizeof(float) * dim);
+    /* lm.h:555-584: text emb first, then audio codebooks added left to right */
+    embed_row(&m->text_emb, tokens[0], x);
+    for (int q = 0; q < c->n_q; q++) { embed_row(&m->emb[q], tokens[q + 1], row); for (int i = 0; i < dim; i++) x[i] = x[i] + row[i]; }
+    const int pos = s->offset; s->offset += 1;          /* transformer.h:1269-1270 */
+    const size_t lstride = (size_t)c->context * dim;
+    for (int l = 0; l < c->num_layers; l++)
+        transformer_layer(m, &m->layers[l], 0, dim, c->num_heads, c->context, c->max_period, pos,
+                          s->k + l * lstride, s->v + l * lstride, x);
+    orc_rms_norm(x, (const float *)m->out_norm.data, 1e-8f, s->transformer_out, dim);   /* lm.h:671-672 */
+    float *logits = text_logits ? text_logits : malloc(sizeof(float) * c->text_card);
+    linear(m, &m->text_linear, s->transformer_out, logits);
+    int tok = argmax_first(logits, (int)m->text_linear.ne1);
+    if (transformer_out) memcpy(transformer_out, s->transformer_out, sizeof(float) * dim);
+    if (!text_logits) free(logits);
+    free(x); free(row);
+    return tok;
+}
+
+void orc_step_depformer(orc_model *m, orc_state *s, int text_token, const int32_t *force, int32_t *audio_tokens, float *audio_logits) {
+    const orc_config *c = &m->cfg; const int dd = c->dep_dim;
+    float *y = malloc(sizeof(float) * dd), *e = malloc(sizeof(float) * dd), *logits = malloc(sizeof(float) * c->card);
+    const size_t lstride = (size_t)m->dep_cap * dd;
+    int prev = text_token;
+    for (int k = 0; k < c->dep_q; k++) {
+        int w = c->schedule_len ? c->schedule[k] : k;                 /* lm.h:457-462 */
+        int wl = m->dep_num_weights == 1 ? 0 : w;                     /* transformer.h:74-83 */
+        if (k == 0) embed_row(&m->dep_text_emb, prev, e);              /* lm.h:494-501, scaled (-1 -> 0) */
+        else {                                                         /* chained get_rows, lm_utils.h:209-217 */
+            const orc_tensor *t = &m->dep_emb[k - 1];
+            orc_dequantize_row(t->type, (const char *)t->data + (int64_t)prev * orc_row_size(t->type, t->ne0), e, t->ne0);
+        }
+        linear(m, &m->dep_in[m->dep_num_weights == 1 ? 0 : w], s->transformer_out, y);
+        for (int i = 0; i < dd; i++) y[i] = y[i] + e[i];
+        for (int l = 0; l < c->dep_layers; l++)
+            transformer_layer(m, &m->dep_layers[l], wl, dd, c->dep_heads, m->dep_cap, c->dep_max_period, k,
+                              s->dk + l * lstride, s->dv + l * lstride, y);
+        linear(m, &m->linears[k], y, logits);                          /* lm.h:472, no final norm */
+        int tok = argmax_first(logits, (int)m->linears[k].ne1);
+        audio_tokens[k] = tok;
+        if (audio_logits) memcpy(audio_logits + (size_t)k * c->card, logits, sizeof(float) * c->card);
+        prev = (force && force[k] >= 0) ? force[k] : tok;
+    }
+    free(y); free(e); free(logits);
+}
+
+float orc_vad(orc_model *m, orc_state *s) {
+    if (m->cfg.extra_heads <= 2) return 0.f;
+    const orc_tensor *t = &m->extra_heads[2]; int n = (int)t->ne1;
+    float *l = malloc(sizeof(float) * n); linear(m, t, s->transformer_out, l);
+    float mx = l[0]; for (int i = 1; i < n; i++) if (l[i] > mx) mx = l[i];
+    double sum = 0; for (int i = 0; i < n; i++) { l[i] = expf(l[i] - mx); sum += l[i]; }
+    float r = l[0] * (float)(1.0 / sum); free(l); return r;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * LMGen host logic (lm.h:715-743 state, lm.h:778-979 step). Greedy, no state machine, no prefixes.
+ * ---------------------------------------------------------------------------------------------- */
+struct orc_lmgen {
+    orc_model *m; orc_state *s;
+    int offset, CT, ncb;
+    int32_t *cache;     /* [CT][ncb], init -2 (lm_ungenerated_token_id) */
+    int32_t initial[ORC_MAX_CODEBOOKS];
+    int max_delay;
+};
+
+orc_lmgen *orc_lmgen_new(orc_model *m) {
+    const orc_config *c = &m->cfg;
+    orc_lmgen *g = calloc(1, sizeof(*g));
+    g->m = m; g->s = orc_state_new(m); g->ncb = c->n_q + 1;
+    int md = c->delays[0]; for (int i = 0; i < c->n_delays; i++) if (c->delays[i] > md) md = c->delays[i];
+    g->max_delay = md;
+    g->CT = md + 2 + (c->personaplex ? 1 : 0);
+    g->cache = malloc(sizeof(int32_t) * g->CT * g->ncb);
+    for (int i = 0; i < g->CT * g->ncb; i++) g->cache[i] = -2;
+    g->initial[0] = c->text_card;
+    for (int i = 1; i < g->ncb; i++) g->initial[i] = c->card;
+    return g;
+}
+void orc_lmgen_free(orc_lmgen *g) { if (!g) return; orc_state_free(g->s); free(g->cache); free(g); }
+orc_state *orc_lmgen_state(orc_lmgen *g) { return g->s; }
+int orc_lmgen_offset(orc_lmgen *g) { return g->offset; }
+
+int orc_lmgen_step(orc_lmgen *g, const int32_t *in_tokens, int n_in, int depformer_replace_tokens,
+                   int32_t *out_text, int32_t *out_audio) {
+    orc_model *m = g->m; const orc_config *c = &m->cfg;
+    const int CT = g->CT, ncb = g->ncb;
+    int dep_q = c->dep_q; if (c->personaplex) dep_q = 8;               /* lm.h:802-805 */
+    const int dep_q_1 = dep_q + 1;
+    const int needed = ncb - dep_q - 1;
+    int provided = 0;
+    if (needed > 0) {
+        if (n_in == ncb) {
+            for (int i = 0; i < ncb; i++) g->cache[((g->offset + c->delays[i]) % CT) * ncb + i] = in_tokens[i];
+            provided = 1;
+        } else {
+            for (int i = 0; i < needed; i++) g->cache[((g->offset + c->delays[dep_q_1 + i]) % CT) * ncb + dep_q_1 + i] = in_tokens[i];
+        }
+    }
+    const int pos = g->offset % CT;
+    int32_t input[ORC_MAX_CODEBOOKS];
+    for (int i = 0; i < ncb; i++) input[i] = (g->offset <= c->delays[i]) ? g->initial[i] : g->cache[pos * ncb + i];
+
+    int text_token = orc_step_temporal(m, g->s, input, NULL, NULL);
+
+    int32_t audio[ORC_MAX_STEPS];
+    if (c->dep_q > 0) {
+        if (!depformer_replace_tokens) orc_step_depformer(m, g->s, text_token, NULL, audio, NULL);
+        else for (int i = 0; i < c->dep_q; i++) audio[i] = -1;
+        if (c->delay_steps) for (int q = 0; q < c->dep_q; q++) if (g->offset < c->delays[q + 1] + c->delay_steps) audio[q] = -1;
+    }
+    g->offset++;
+    if (!provided) {
+        const int p = g->offset % CT;
+        g->cache[p * ncb + 0] = text_token;
+        if (c->dep_q > 0) for (int q = 0; q < c->dep_q; q++) g->cache[p * ncb + q + 1] = audio[q];
+    }
+    for (int q = 0; q < c->dep_q; q++) out_audio[q] = audio[q];
+    if (g->offset <= g->max_delay || depformer_replace_tokens) return 0;
+    *out_text = g->cache[((g->offset - g->max_delay + c->delays[0]) % CT) * ncb + 0];
+    for (int i = 1; i < dep_q_1; i++) out_audio[i - 1] = g->cache[((g->offset - g->max_delay + c->delays[i]) % CT) * ncb + i];
+    for (int q = 0; q < c->dep_q; q++) if (out_audio[q] == -1) return 0;
+    return 1;
+}

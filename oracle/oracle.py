@@ -1,0 +1,258 @@
+"""ctypes front-end of the TEST-ONLY CPU oracle (oracle/ggml_ref.c).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this.
+GGUF files are read with gguf-py's GGUFReader (an implementation independent of the product's C++
+GGUF parser), and tensor pointers are handed to the C restatement.
+"""
+from __future__ import annotations
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "libggml_ref.so")
+
+ORC_MAX_CODEBOOKS, ORC_MAX_STEPS = 40, 40
+
+
+class OrcConfig(C.Structure):
+    _fields_ = [
+        ("dim", C.c_int32), ("num_heads", C.c_int32), ("num_layers", C.c_int32), ("context", C.c_int32), ("max_period", C.c_int32),
+        ("n_q", C.c_int32), ("dep_q", C.c_int32), ("card", C.c_int32), ("text_card", C.c_int32),
+        ("dep_dim", C.c_int32), ("dep_heads", C.c_int32), ("dep_layers", C.c_int32), ("dep_context", C.c_int32), ("dep_max_period", C.c_int32),
+        ("n_delays", C.c_int32), ("delays", C.c_int32 * ORC_MAX_CODEBOOKS),
+        ("schedule_len", C.c_int32), ("schedule", C.c_int32 * ORC_MAX_STEPS),
+        ("personaplex", C.c_int32), ("extra_heads", C.c_int32), ("delay_steps", C.c_int32),
+    ]
+
+
+def build(force: bool = False) -> str:
+    src = [os.path.join(_HERE, f) for f in ("ggml_ref.c", "ggml_ref.h", "Makefile")]
+    stale = (not os.path.exists(_SO)) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in src)
+    if force or stale:
+        subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        try:
+            _lib = C.CDLL(build())
+        except OSError:
+            _lib = C.CDLL(build(force=True))
+        L = _lib
+        vp, i32p, fp = C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_float)
+        L.orc_row_size.restype = C.c_int64; L.orc_row_size.argtypes = [C.c_int, C.c_int64]
+        L.orc_dequantize_row.argtypes = [C.c_int, vp, vp, C.c_int64]
+        L.orc_quantize_row_q8_0.argtypes = [vp, vp, C.c_int64]
+        L.orc_quantize_row_q8_K.argtypes = [vp, vp, vp, vp, C.c_int64]
+        L.orc_mul_mat_vec.argtypes = [C.c_int, vp, C.c_int64, C.c_int64, vp, vp]
+        L.orc_mul_mat_vec_ideal.argtypes = [C.c_int, vp, C.c_int64, C.c_int64, vp, vp]
+        L.orc_rms_norm.argtypes = [vp, vp, C.c_float, vp, C.c_int64]
+        L.orc_fp32_to_bf16.restype = C.c_uint16; L.orc_fp32_to_bf16.argtypes = [C.c_float]
+        L.orc_model_new.restype = vp; L.orc_model_new.argtypes = [C.POINTER(OrcConfig)]
+        L.orc_model_free.argtypes = [vp]
+        L.orc_model_set_tensor.restype = C.c_int
+        L.orc_model_set_tensor.argtypes = [vp, C.c_char_p, C.c_int, C.c_int64, C.c_int64, vp]
+        L.orc_model_missing.restype = C.c_int; L.orc_model_missing.argtypes = [vp, C.c_char_p, C.c_int]
+        L.orc_model_set_ideal.argtypes = [vp, C.c_int]
+        L.orc_state_new.restype = vp; L.orc_state_new.argtypes = [vp]
+        L.orc_state_free.argtypes = [vp]; L.orc_state_reset.argtypes = [vp]
+        L.orc_state_offset.restype = C.c_int; L.orc_state_offset.argtypes = [vp]
+        L.orc_step_temporal.restype = C.c_int; L.orc_step_temporal.argtypes = [vp, vp, vp, vp, vp]
+        L.orc_step_depformer.argtypes = [vp, vp, C.c_int, vp, vp, vp]
+        L.orc_vad.restype = C.c_float; L.orc_vad.argtypes = [vp, vp]
+        L.orc_state_get_kv.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp]
+        L.orc_lmgen_new.restype = vp; L.orc_lmgen_new.argtypes = [vp]
+        L.orc_lmgen_free.argtypes = [vp]
+        L.orc_lmgen_step.restype = C.c_int; L.orc_lmgen_step.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp]
+        L.orc_lmgen_state.restype = vp; L.orc_lmgen_state.argtypes = [vp]
+        L.orc_lmgen_offset.restype = C.c_int; L.orc_lmgen_offset.argtypes = [vp]
+    return _lib
+
+
+def _p(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def make_config(cfg: dict, delay_steps: int = 0) -> OrcConfig:
+    c = OrcConfig()
+    c.dim, c.num_heads, c.num_layers, c.context, c.max_period = cfg["dim"], cfg["num_heads"], cfg["num_layers"], cfg["context"], cfg["max_period"]
+    c.n_q, c.dep_q, c.card, c.text_card = cfg["n_q"], cfg["dep_q"], cfg["card"], cfg["text_card"]
+    c.dep_dim, c.dep_heads, c.dep_layers = cfg["depformer_dim"], cfg["depformer_num_heads"], cfg["depformer_num_layers"]
+    c.dep_context, c.dep_max_period = cfg["depformer_context"], cfg["depformer_max_period"]
+    c.n_delays = len(cfg["delays"])
+    for i, d in enumerate(cfg["delays"]):
+        c.delays[i] = d
+    c.schedule_len = len(cfg["schedule"])
+    for i, s in enumerate(cfg["schedule"]):
+        c.schedule[i] = s
+    c.personaplex = 1 if cfg["model_type"] == "personaplex" else 0
+    c.extra_heads = cfg["extra_heads"]
+    c.delay_steps = delay_steps
+    return c
+
+
+# ---- T0 helpers -------------------------------------------------------------------------------
+def dequantize(gtype: int, raw: np.ndarray, k: int) -> np.ndarray:
+    """raw: uint8 [rows, row_bytes] -> float32 [rows, k]"""
+    raw = np.ascontiguousarray(raw)
+    rows = raw.shape[0]
+    out = np.empty((rows, k), dtype=np.float32)
+    rs = lib().orc_row_size(gtype, k)
+    assert raw.shape[1] == rs, (raw.shape, rs)
+    for r in range(rows):
+        lib().orc_dequantize_row(gtype, raw[r].ctypes.data, out[r].ctypes.data, k)
+    return out
+
+
+def quantize_q8_0(x: np.ndarray) -> np.ndarray:
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    out = np.empty(x.size // 32 * 34, dtype=np.uint8)
+    lib().orc_quantize_row_q8_0(_p(x), _p(out), x.size)
+    return out
+
+
+def quantize_q8_K(x: np.ndarray):
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    qs = np.empty(x.size, dtype=np.int8); d = np.empty(x.size // 256, dtype=np.float32); bs = np.empty(x.size // 16, dtype=np.int16)
+    lib().orc_quantize_row_q8_K(_p(x), _p(qs), _p(d), _p(bs), x.size)
+    return qs, d, bs
+
+
+def mul_mat_vec(gtype: int, w_raw: np.ndarray, k: int, x: np.ndarray, ideal: bool = False) -> np.ndarray:
+    w_raw = np.ascontiguousarray(w_raw); x = np.ascontiguousarray(x, dtype=np.float32)
+    rows = w_raw.shape[0]
+    y = np.empty(rows, dtype=np.float32)
+    fn = lib().orc_mul_mat_vec_ideal if ideal else lib().orc_mul_mat_vec
+    fn(gtype, _p(w_raw), k, rows, _p(x), _p(y))
+    return y
+
+
+def rms_norm(x: np.ndarray, alpha: np.ndarray | None, eps: float = 1e-8) -> np.ndarray:
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    y = np.empty_like(x)
+    lib().orc_rms_norm(_p(x), _p(alpha) if alpha is not None else None, eps, _p(y), x.size)
+    return y
+
+
+# ---- model ------------------------------------------------------------------------------------
+class Model:
+    """Oracle model over a GGUF file (tensors stay mmapped by gguf-py)."""
+
+    def __init__(self, gguf_path: str, cfg: dict, delay_steps: int = 0, ideal: bool = False):
+        from gguf import GGUFReader
+        self.cfg = cfg
+        self.reader = GGUFReader(gguf_path)
+        self._ccfg = make_config(cfg, delay_steps)
+        self.h = lib().orc_model_new(C.byref(self._ccfg))
+        self._keep = []
+        for t in self.reader.tensors:
+            shape = [int(s) for s in t.shape]       # ggml order: ne0 fastest
+            ne0 = shape[0]; ne1 = shape[1] if len(shape) > 1 else 1
+            data = t.data
+            self._keep.append(data)
+            ok = lib().orc_model_set_tensor(self.h, t.name.encode(), int(t.tensor_type), ne0, ne1, data.ctypes.data)
+            if not ok:
+                raise KeyError(f"oracle: tensor {t.name} not recognised")
+        buf = C.create_string_buffer(128)
+        n = lib().orc_model_missing(self.h, buf, 128)
+        if n:
+            raise KeyError(f"oracle: {n} tensors missing (first: {buf.value.decode()})")
+        if ideal:
+            lib().orc_model_set_ideal(self.h, 1)
+
+    def tensor_raw(self, name: str):
+        for t in self.reader.tensors:
+            if t.name == name:
+                return t
+        raise KeyError(name)
+
+    def close(self):
+        if self.h:
+            lib().orc_model_free(self.h); self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class State:
+    def __init__(self, model: Model):
+        self.model = model
+        self.h = lib().orc_state_new(model.h)
+        self._own = True
+
+    @property
+    def offset(self):
+        return lib().orc_state_offset(self.h)
+
+    def reset(self):
+        lib().orc_state_reset(self.h)
+
+    def step_temporal(self, tokens):
+        cfg = self.model.cfg
+        tok = np.ascontiguousarray(tokens, dtype=np.int32)
+        assert tok.size == cfg["n_q"] + 1
+        logits = np.empty(cfg["text_card"], dtype=np.float32)
+        tout = np.empty(cfg["dim"], dtype=np.float32)
+        t = lib().orc_step_temporal(self.model.h, self.h, _p(tok), _p(logits), _p(tout))
+        return t, logits, tout
+
+    def step_depformer(self, text_token: int, force=None):
+        cfg = self.model.cfg
+        toks = np.empty(cfg["dep_q"], dtype=np.int32)
+        logits = np.empty((cfg["dep_q"], cfg["card"]), dtype=np.float32)
+        f = np.ascontiguousarray(force, dtype=np.int32) if force is not None else None
+        lib().orc_step_depformer(self.model.h, self.h, int(text_token), _p(f) if f is not None else None, _p(toks), _p(logits))
+        return toks, logits
+
+    def vad(self) -> float:
+        return float(lib().orc_vad(self.model.h, self.h))
+
+    def get_kv(self, layer: int, head: int, slot: int):
+        Dh = self.model.cfg["dim"] // self.model.cfg["num_heads"]
+        k = np.empty(Dh, dtype=np.uint16); v = np.empty(Dh, dtype=np.uint16)
+        lib().orc_state_get_kv(self.h, layer, head, slot, _p(k), _p(v))
+        return k, v
+
+    def __del__(self):
+        try:
+            if self._own and self.h:
+                lib().orc_state_free(self.h); self.h = None
+        except Exception:
+            pass
+
+
+class LMGen:
+    """Greedy LMGen (lm.h:778-979) on the oracle."""
+
+    def __init__(self, model: Model):
+        self.model = model
+        self.h = lib().orc_lmgen_new(model.h)
+
+    @property
+    def offset(self):
+        return lib().orc_lmgen_offset(self.h)
+
+    def step(self, in_tokens, replace: bool = False):
+        cfg = self.model.cfg
+        tok = np.ascontiguousarray(in_tokens, dtype=np.int32)
+        text = C.c_int32(0)
+        audio = np.full(max(1, cfg["dep_q"]), -7, dtype=np.int32)
+        ok = lib().orc_lmgen_step(self.h, _p(tok), tok.size, int(replace), C.byref(text), _p(audio))
+        return ok, int(text.value), audio[: cfg["dep_q"]].copy()
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().orc_lmgen_free(self.h); self.h = None
+        except Exception:
+            pass
