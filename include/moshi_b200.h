@@ -1,0 +1,140 @@
+/*
+ * include/moshi_b200.h — C ABI of the B200-native LM decode step ("msx").
+ *
+ * This is the drop-in boundary for the hot path of Codes4Fun/moshi.cpp: it replaces the ggml op
+ * graphs that the reference builds and runs for one frame of the LM
+ *     temporal graph   src/moshi/models/lm.h:853-875  (moshi_lmmodel_forward_text_build/_step)
+ *     depformer graph  src/moshi/models/lm.h:478-553  (moshi_lmmodel_depformer_step)
+ * together with the runtime objects those graphs live in
+ *     GraphContext / ScratchContext / StateContext   src/context.h:227-780
+ *     WeightLoader (GGUF side)                        src/loader.h:85-99, 235-271
+ * The reference itself has no C ABI (its API is C++ linkage, include/moshi/moshi.h:14-22); the
+ * C++ mirror of that API (moshi.cpp_b200/host/moshi_api.h: moshi_lm_*) is implemented on top of
+ * the entry points below.  Plain pointers and sizes only; no C++/torch types.
+ *
+ * All functions return 0 on success and a negative msx_status on failure; msx_last_error() gives
+ * the message for the calling thread.  There is NO CPU fallback: every compute entry point fails
+ * with MSX_ERR_CUDA when no sm_100 device / kernel image is available.
+ */
+#ifndef MOSHI_B200_H
+#define MOSHI_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSX_API __attribute__((visibility("default")))
+
+#define MSX_MAX_CODEBOOKS 40
+#define MSX_MAX_STEPS 40
+#define MSX_NO_TOKEN INT32_MIN /* "no override" marker for text_override / force[] */
+
+typedef enum msx_status {
+    MSX_OK = 0,
+    MSX_ERR_ARG = -1,     /* bad argument / config */
+    MSX_ERR_IO = -2,      /* file missing / unreadable (reference: NULL from moshi_lm_from_files, moshi.cpp:621-627) */
+    MSX_ERR_FORMAT = -3,  /* not GGUF / unsupported tensor type / shape mismatch / tensor missing */
+    MSX_ERR_CUDA = -4,    /* CUDA runtime error, no device, out of memory */
+    MSX_ERR_STATE = -5,   /* call sequence error */
+} msx_status;
+
+/* LM fields of moshi_config_t (include/moshi/moshi.h:111-156). hidden sizes come from the weights. */
+typedef struct msx_config {
+    int32_t dim, num_heads, num_layers, context, max_period;
+    int32_t n_q, dep_q, card, text_card;
+    int32_t dep_dim, dep_heads, dep_layers, dep_context, dep_max_period; /* 0 = depformer_pos_emb "none" */
+    int32_t n_delays;
+    int32_t delays[MSX_MAX_CODEBOOKS];
+    int32_t schedule_len;
+    int32_t schedule[MSX_MAX_STEPS]; /* depformer_weights_per_step_schedule */
+    int32_t personaplex;             /* model_type == "personaplex" */
+    int32_t extra_heads;             /* extra_heads_num_heads */
+} msx_config;
+
+typedef struct msx_model msx_model;   /* device-resident, repacked weights (one GPU)      */
+typedef struct msx_stream msx_stream; /* one conversation: KV rings, offset, step graphs  */
+typedef struct msx_gen msx_gen;       /* LMGen host state: token delay ring (lm.h:715-743) */
+
+MSX_API const char *msx_last_error(void);
+MSX_API int msx_device_count(void);
+MSX_API const char *msx_version(void);
+
+/* ---- weights: replaces WeightLoader::from_gguf + load_gguf + get_weights("lm.") --------------
+ * (src/loader.h:85-99, 235-271; src/moshi/models/lm.h:370-395).  Tensor names / shapes / types as
+ * the reference resolves them; Q4_K / Q8_0 / Q4_0 linears and Q4_0 / Q8_0 / F32 / F16 / BF16
+ * embedding tables are repacked into device tiles at load. */
+MSX_API int msx_model_load_gguf(const char *path, const msx_config *cfg, int device, msx_model **out);
+MSX_API void msx_model_free(msx_model *m);
+MSX_API int msx_model_config(const msx_model *m, msx_config *out);
+/* bytes of GGUF weight blocks one frame must read (every hot-path linear once; SURVEY.md §8d "W") */
+MSX_API int64_t msx_model_weight_bytes_per_frame(const msx_model *m);
+MSX_API int64_t msx_model_device_bytes(const msx_model *m);
+MSX_API int msx_model_device(const msx_model *m);
+
+/* ---- per-conversation state: replaces StateContext + moshi_lmmodel_states (lm.h:423-444) ------
+ * context_override > 0 shrinks the temporal ring capacity (tools' "-c N", moshi-sts.cpp:254-264). */
+MSX_API int msx_stream_create(msx_model *m, int context_override, msx_stream **out);
+MSX_API void msx_stream_free(msx_stream *s);
+MSX_API int msx_stream_reset(msx_stream *s);   /* offset = 0, KV rings zeroed */
+MSX_API int msx_stream_offset(const msx_stream *s);
+/* bytes of KV cache the NEXT temporal step must read: n_valid * 2 * dim * 2 B * num_layers */
+MSX_API int64_t msx_stream_kv_bytes_next(const msx_stream *s);
+
+/* One temporal-transformer step (lm.h:679-690 + graph compute, lm.h:872-878).
+ * tokens[n_q+1] = {text, audio codebooks}; -1 embeds as zeros, other negatives as row 0
+ * (lm_utils.h:172-182).  Returns the greedy text token (sampling.h:57-63, temp <= 0).
+ * text_logits (host, [text_card]) and transformer_out (host, [dim]) may be NULL. */
+MSX_API int msx_step_temporal(msx_stream *s, const int32_t *tokens, int32_t *text_token,
+                              float *text_logits, float *transformer_out);
+/* Depformer chain for the frame (lm.h:478-553): dep_q serial codebook steps on the device.
+ * force (host, [dep_q]) optionally replaces the token fed to step k+1 (MSX_NO_TOKEN / NULL = greedy).
+ * audio_logits (host, [dep_q][card]) may be NULL. */
+MSX_API int msx_step_depformer(msx_stream *s, int32_t text_token, const int32_t *force,
+                               int32_t *audio_tokens, float *audio_logits);
+/* Fused frame: temporal -> greedy text -> depformer with a single host synchronisation.
+ * out_tokens[1 + dep_q] = {text, audio...}. */
+MSX_API int msx_step(msx_stream *s, const int32_t *tokens, int32_t *out_tokens);
+/* STT VAD head (lm.h:966-976): softmax(extra_heads[2] . transformer_out)[0]; 0 if < 3 extra heads */
+MSX_API int msx_vad(msx_stream *s, float *vad);
+
+/* Device-resident replay for throughput measurement: frames[n_frames][n_q+1] (host) are uploaded
+ * once, then n_steps fused frames run back to back with no host round trip; step i consumes
+ * frames[i % n_frames].  elapsed_ms (may be NULL) is measured with CUDA events on the stream the
+ * kernels run on.  out_tokens (host, [n_steps][1+dep_q]) may be NULL. */
+MSX_API int msx_run_resident(msx_stream *s, const int32_t *frames, int n_frames, int n_steps,
+                             int32_t *out_tokens, float *elapsed_ms);
+/* kernels launched per fused frame (for bench.py "gpu_launches") */
+MSX_API int msx_stream_launches_per_frame(const msx_stream *s);
+/* KV read-back for parity tests: bf16 bits of K and V for (layer, head, slot), Dh values each */
+MSX_API int msx_stream_get_kv(msx_stream *s, int layer, int head, int slot, uint16_t *k, uint16_t *v);
+
+/* ---- LMGen: the reference's per-frame host logic (moshi_lmgen_step, lm.h:778-979) --------------
+ * Token delay ring, initial tokens, delayed emission; greedy sampling; no TTS state machine.
+ * in_tokens: n_in user codes (n_q - dep_q of them, or n_q + 1 when all streams are "provided").
+ * Returns 1 when out_text / out_audio[dep_q] are valid, 0 during warm-up (offset <= max_delay),
+ * negative msx_status on error. */
+MSX_API int msx_gen_create(msx_stream *s, int delay_steps, msx_gen **out);
+MSX_API void msx_gen_free(msx_gen *g);
+MSX_API int msx_gen_step(msx_gen *g, const int32_t *in_tokens, int n_in, int depformer_replace_tokens,
+                         int32_t *out_text, int32_t *out_audio);
+MSX_API int msx_gen_offset(const msx_gen *g);
+MSX_API int msx_gen_max_delay(const msx_gen *g);
+
+/* ---- unit-level entry points (parity tests of single kernels) -----------------------------------
+ * Repack one row-major GGUF tensor [rows][k] of `type` (ggml type id), run y = W.x on the device
+ * with the same fused kernels the step uses.  prologue: 0 = quantise x, 1 = rms_norm(x)*alpha then
+ * quantise.  All pointers are host pointers. */
+MSX_API int msx_test_gemv(int device, int type, const void *w, int64_t k, int64_t rows,
+                          const float *x, const float *alpha, int prologue, float *y);
+/* bit-exact dequantisation through the device embedding-gather path: out[n_rows][k] */
+MSX_API int msx_test_dequant_rows(int device, int type, const void *table, int64_t k, int64_t table_rows,
+                                  const int32_t *row_ids, int n_rows, float *out);
+/* device Q4_K -> f32 of the REPACKED tiles (checks the repack is lossless) */
+MSX_API int msx_test_dequant_repacked(int device, int type, const void *w, int64_t k, int64_t rows, float *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOSHI_B200_H */

@@ -1,0 +1,289 @@
+"""ctypes binding of the C ABI in include/moshi_b200.h (libmoshi_b200.so) + in-tree build helper.
+
+Fails loudly when the shared library is missing or a call returns an error: there is no fallback.
+"""
+from __future__ import annotations
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(_HERE)
+SO_PATH = os.path.join(_HERE, "libmoshi_b200.so")
+HOST_SO_PATH = os.path.join(_HERE, "libmoshi.so")
+CSRC = os.path.join(_HERE, "csrc")
+NVCC_FLAGS = [
+    "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+    "-Xcompiler", "-fPIC,-fvisibility=hidden", "-shared",
+]
+
+MSX_MAX_CODEBOOKS, MSX_MAX_STEPS = 40, 40
+MSX_NO_TOKEN = -(2 ** 31)
+
+
+class MsxError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"msx error {code}: {msg}")
+        self.code = code
+
+
+class MsxConfig(C.Structure):
+    _fields_ = [
+        ("dim", C.c_int32), ("num_heads", C.c_int32), ("num_layers", C.c_int32), ("context", C.c_int32), ("max_period", C.c_int32),
+        ("n_q", C.c_int32), ("dep_q", C.c_int32), ("card", C.c_int32), ("text_card", C.c_int32),
+        ("dep_dim", C.c_int32), ("dep_heads", C.c_int32), ("dep_layers", C.c_int32), ("dep_context", C.c_int32), ("dep_max_period", C.c_int32),
+        ("n_delays", C.c_int32), ("delays", C.c_int32 * MSX_MAX_CODEBOOKS),
+        ("schedule_len", C.c_int32), ("schedule", C.c_int32 * MSX_MAX_STEPS),
+        ("personaplex", C.c_int32), ("extra_heads", C.c_int32),
+    ]
+
+
+def sources():
+    return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))]
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile csrc/ for sm_100a into moshi.cpp_b200/libmoshi_b200.so (in-tree; nvcc cross-compiles without a GPU)."""
+    srcs = sources() + [os.path.join(ROOT, "include", "moshi_b200.h")]
+    stale = (not os.path.exists(SO_PATH)) or any(os.path.getmtime(s) > os.path.getmtime(SO_PATH) for s in srcs)
+    if force or stale:
+        cmd = ["nvcc"] + NVCC_FLAGS + ["-o", SO_PATH, os.path.join(CSRC, "engine.cu"), os.path.join(CSRC, "gguf_file.cpp")]
+        if verbose:
+            print(" ".join(cmd))
+        subprocess.check_call(cmd)
+    return SO_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO_PATH):
+        raise MsxError(-4, f"{SO_PATH} is missing: run __graft_entry__.build() (nvcc, sm_100a). No CPU fallback exists.")
+    L = C.CDLL(SO_PATH)
+    vp, i32p = C.c_void_p, C.POINTER(C.c_int32)
+    L.msx_last_error.restype = C.c_char_p
+    L.msx_version.restype = C.c_char_p
+    L.msx_device_count.restype = C.c_int
+    L.msx_model_load_gguf.argtypes = [C.c_char_p, C.POINTER(MsxConfig), C.c_int, C.POINTER(vp)]
+    L.msx_model_free.argtypes = [vp]
+    L.msx_model_config.argtypes = [vp, C.POINTER(MsxConfig)]
+    L.msx_model_weight_bytes_per_frame.restype = C.c_int64; L.msx_model_weight_bytes_per_frame.argtypes = [vp]
+    L.msx_model_device_bytes.restype = C.c_int64; L.msx_model_device_bytes.argtypes = [vp]
+    L.msx_model_device.argtypes = [vp]
+    L.msx_stream_create.argtypes = [vp, C.c_int, C.POINTER(vp)]
+    L.msx_stream_free.argtypes = [vp]
+    L.msx_stream_reset.argtypes = [vp]
+    L.msx_stream_offset.argtypes = [vp]
+    L.msx_stream_kv_bytes_next.restype = C.c_int64; L.msx_stream_kv_bytes_next.argtypes = [vp]
+    L.msx_step_temporal.argtypes = [vp, vp, i32p, vp, vp]
+    L.msx_step_depformer.argtypes = [vp, C.c_int32, vp, vp, vp]
+    L.msx_step.argtypes = [vp, vp, vp]
+    L.msx_vad.argtypes = [vp, C.POINTER(C.c_float)]
+    L.msx_run_resident.argtypes = [vp, vp, C.c_int, C.c_int, vp, C.POINTER(C.c_float)]
+    L.msx_stream_launches_per_frame.argtypes = [vp]
+    L.msx_stream_get_kv.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp]
+    L.msx_gen_create.argtypes = [vp, C.c_int, C.POINTER(vp)]
+    L.msx_gen_free.argtypes = [vp]
+    L.msx_gen_step.argtypes = [vp, vp, C.c_int, C.c_int, i32p, vp]
+    L.msx_gen_offset.argtypes = [vp]
+    L.msx_gen_max_delay.argtypes = [vp]
+    L.msx_test_gemv.argtypes = [C.c_int, C.c_int, vp, C.c_int64, C.c_int64, vp, vp, C.c_int, vp]
+    L.msx_test_dequant_rows.argtypes = [C.c_int, C.c_int, vp, C.c_int64, C.c_int64, vp, C.c_int, vp]
+    L.msx_test_dequant_repacked.argtypes = [C.c_int, C.c_int, vp, C.c_int64, C.c_int64, vp]
+    _lib = L
+    return L
+
+
+def _check(rc: int):
+    if rc < 0:
+        raise MsxError(rc, lib().msx_last_error().decode(errors="replace"))
+    return rc
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def make_config(cfg: dict) -> MsxConfig:
+    c = MsxConfig()
+    c.dim, c.num_heads, c.num_layers, c.context, c.max_period = cfg["dim"], cfg["num_heads"], cfg["num_layers"], cfg["context"], cfg["max_period"]
+    c.n_q, c.dep_q, c.card, c.text_card = cfg["n_q"], cfg["dep_q"], cfg["card"], cfg["text_card"]
+    c.dep_dim, c.dep_heads, c.dep_layers = cfg["depformer_dim"], cfg["depformer_num_heads"], cfg["depformer_num_layers"]
+    c.dep_context, c.dep_max_period = cfg["depformer_context"], cfg["depformer_max_period"]
+    c.n_delays = len(cfg["delays"])
+    for i, d in enumerate(cfg["delays"]):
+        c.delays[i] = d
+    c.schedule_len = len(cfg["schedule"])
+    for i, s in enumerate(cfg["schedule"]):
+        c.schedule[i] = s
+    c.personaplex = 1 if cfg["model_type"] == "personaplex" else 0
+    c.extra_heads = cfg["extra_heads"]
+    return c
+
+
+class Model:
+    def __init__(self, gguf_path: str, cfg: dict, device: int = 0):
+        self.cfg = cfg
+        self._c = make_config(cfg)
+        h = C.c_void_p()
+        _check(lib().msx_model_load_gguf(gguf_path.encode(), C.byref(self._c), device, C.byref(h)))
+        self.h = h
+
+    @property
+    def weight_bytes_per_frame(self) -> int:
+        return int(lib().msx_model_weight_bytes_per_frame(self.h))
+
+    @property
+    def device_bytes(self) -> int:
+        return int(lib().msx_model_device_bytes(self.h))
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().msx_model_free(self.h); self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Stream:
+    def __init__(self, model: Model, context: int = 0):
+        self.model = model
+        h = C.c_void_p()
+        _check(lib().msx_stream_create(model.h, context, C.byref(h)))
+        self.h = h
+
+    @property
+    def offset(self) -> int:
+        return lib().msx_stream_offset(self.h)
+
+    @property
+    def launches_per_frame(self) -> int:
+        return lib().msx_stream_launches_per_frame(self.h)
+
+    @property
+    def kv_bytes_next(self) -> int:
+        return int(lib().msx_stream_kv_bytes_next(self.h))
+
+    def reset(self):
+        _check(lib().msx_stream_reset(self.h))
+
+    def step_temporal(self, tokens, want_logits=True):
+        cfg = self.model.cfg
+        tok = np.ascontiguousarray(tokens, dtype=np.int32)
+        assert tok.size == cfg["n_q"] + 1
+        t = C.c_int32(0)
+        logits = np.empty(cfg["text_card"], dtype=np.float32) if want_logits else None
+        tout = np.empty(cfg["dim"], dtype=np.float32) if want_logits else None
+        _check(lib().msx_step_temporal(self.h, _p(tok), C.byref(t), _p(logits), _p(tout)))
+        return int(t.value), logits, tout
+
+    def step_depformer(self, text_token: int, force=None, want_logits=True):
+        cfg = self.model.cfg
+        toks = np.empty(cfg["dep_q"], dtype=np.int32)
+        logits = np.empty((cfg["dep_q"], cfg["card"]), dtype=np.float32) if want_logits else None
+        f = np.ascontiguousarray(force, dtype=np.int32) if force is not None else None
+        _check(lib().msx_step_depformer(self.h, int(text_token), _p(f), _p(toks), _p(logits)))
+        return toks, logits
+
+    def step(self, tokens):
+        cfg = self.model.cfg
+        tok = np.ascontiguousarray(tokens, dtype=np.int32)
+        assert tok.size == cfg["n_q"] + 1
+        out = np.empty(1 + cfg["dep_q"], dtype=np.int32)
+        _check(lib().msx_step(self.h, _p(tok), _p(out)))
+        return out
+
+    def vad(self) -> float:
+        v = C.c_float(0)
+        _check(lib().msx_vad(self.h, C.byref(v)))
+        return float(v.value)
+
+    def run_resident(self, frames, n_steps: int, want_tokens: bool = False):
+        cfg = self.model.cfg
+        fr = np.ascontiguousarray(frames, dtype=np.int32).reshape(-1, cfg["n_q"] + 1)
+        out = np.empty((n_steps, 1 + cfg["dep_q"]), dtype=np.int32) if want_tokens else None
+        ms = C.c_float(0)
+        _check(lib().msx_run_resident(self.h, _p(fr), fr.shape[0], n_steps, _p(out), C.byref(ms)))
+        return float(ms.value), out
+
+    def get_kv(self, layer: int, head: int, slot: int):
+        cfg = self.model.cfg
+        dh = cfg["dim"] // cfg["num_heads"]
+        k = np.empty(dh, dtype=np.uint16); v = np.empty(dh, dtype=np.uint16)
+        _check(lib().msx_stream_get_kv(self.h, layer, head, slot, _p(k), _p(v)))
+        return k, v
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().msx_stream_free(self.h); self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Gen:
+    """LMGen over a stream (msx_gen_*): mirrors moshi_lm_send2 / moshi_lm_receive."""
+
+    def __init__(self, stream: Stream, delay_steps: int = 0):
+        self.stream = stream
+        h = C.c_void_p()
+        _check(lib().msx_gen_create(stream.h, delay_steps, C.byref(h)))
+        self.h = h
+
+    @property
+    def offset(self):
+        return lib().msx_gen_offset(self.h)
+
+    def step(self, in_tokens, replace: bool = False):
+        cfg = self.stream.model.cfg
+        tok = np.ascontiguousarray(in_tokens, dtype=np.int32)
+        text = C.c_int32(0)
+        audio = np.full(max(1, cfg["dep_q"]), -7, dtype=np.int32)
+        rc = _check(lib().msx_gen_step(self.h, _p(tok), tok.size, int(replace), C.byref(text), _p(audio)))
+        return rc, int(text.value), audio[: cfg["dep_q"]].copy()
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().msx_gen_free(self.h); self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ---- unit-level helpers -------------------------------------------------------------------------
+def test_gemv(gtype: int, w_raw: np.ndarray, k: int, x: np.ndarray, alpha=None, device: int = 0) -> np.ndarray:
+    w_raw = np.ascontiguousarray(w_raw); x = np.ascontiguousarray(x, dtype=np.float32)
+    rows = w_raw.shape[0]
+    y = np.empty(rows, dtype=np.float32)
+    al = np.ascontiguousarray(alpha, dtype=np.float32) if alpha is not None else None
+    _check(lib().msx_test_gemv(device, gtype, _p(w_raw), k, rows, _p(x), _p(al), 1 if alpha is not None else 0, _p(y)))
+    return y
+
+
+def test_dequant_rows(gtype: int, table_raw: np.ndarray, k: int, ids, device: int = 0) -> np.ndarray:
+    table_raw = np.ascontiguousarray(table_raw)
+    ids = np.ascontiguousarray(ids, dtype=np.int32)
+    out = np.empty((ids.size, k), dtype=np.float32)
+    _check(lib().msx_test_dequant_rows(device, gtype, _p(table_raw), k, table_raw.shape[0], _p(ids), ids.size, _p(out)))
+    return out
+
+
+def test_dequant_repacked(gtype: int, w_raw: np.ndarray, k: int, device: int = 0) -> np.ndarray:
+    w_raw = np.ascontiguousarray(w_raw)
+    out = np.empty((w_raw.shape[0], k), dtype=np.float32)
+    _check(lib().msx_test_dequant_repacked(device, gtype, _p(w_raw), k, w_raw.shape[0], _p(out)))
+    return out

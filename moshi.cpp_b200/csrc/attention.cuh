@@ -1,0 +1,214 @@
+// attention.cuh — RoPE + ring-KV insert + single-query attention over the bf16 ring cache (sm_100a).
+//
+// One launch replaces, per layer, the reference's graph nodes
+//     q/k/v views, cont, reshape, permute                       transformer.h:498-549
+//     moshi_apply_rope (+ timestep embedding)                   src/moshi/modules/rope.h:8-128
+//     moshi_kv_cache_insert_kv (ggml_set_rows f32->bf16)         transformer.h:238-249
+//     bias-pattern window copy                                   torch.h:205-223, transformer.h:1273-1277
+//     SDPA = mul_mat(K,q) -> soft_max_ext -> cont(transpose V) -> mul_mat   src/torch.h:225-237
+// For T = 1 the bias LUT reduces to "slot i visible iff i <= pos or pos >= cap-1" (SURVEY.md §3.4),
+// so only the n_valid = min(pos+1, cap) valid slots are read (the reference reads all `cap` slots and
+// re-copies V every layer).
+//
+// Numerics mirror ggml's CPU path with a bf16 cache: q and the normalised probabilities are rounded
+// to bf16 before the two contractions, K/V are rounded to bf16 on insert, softmax normalises by the
+// full-row sum BEFORE the bf16 rounding — hence the cluster-wide max/sum exchange below instead of
+// an online-softmax merge.
+//
+// Parallelisation: grid (S, H).  The S CTAs of one head form a thread-block cluster and split the
+// valid slots; row max, row sum and the partial context vectors are exchanged through distributed
+// shared memory.
+#pragma once
+#include <cooperative_groups.h>
+#include "common.cuh"
+
+namespace msx {
+namespace cg = cooperative_groups;
+
+struct AttnArgs {
+    const float *qkv = nullptr;     // [3*dim] = q | k | v, each (h d)
+    uint16_t *kc = nullptr;         // this layer's K ring [H][cap][DH] bf16
+    uint16_t *vc = nullptr;
+    float *ctx = nullptr;           // [dim] attention output (h d)
+    const Ctrl *ctrl = nullptr;
+    int32_t pos_const = -1;         // >= 0: baked position (depformer step k), else ctrl->offset
+    int32_t cap = 0;
+    int32_t dim = 0;
+    int32_t max_period = 0;         // 0 = no RoPE
+    const float *rope_freq = nullptr;  // [DH/2] expf(-logf(max_period)*j/half), computed on the host at load
+};
+
+constexpr int kAttnMaxSplit = 8;
+
+// shared-memory layout (bytes): x_sum[8] f64 | red[8] f64 | x_ctx[8][DH] f64 | part[NG][DH] f64 |
+//                               q[DH] f32 | knew,vnew [2*DH] bf16 | x_max[8] f32 | scores[per] f32
+template <int DH>
+__host__ __device__ inline int attn_smem_bytes(int cap, int S) {
+    const int per = (cap + S - 1) / S + 1;
+    const int ng = kThreads / (DH / 8);
+    return (64 + 64 + kAttnMaxSplit * DH * 8 + ng * DH * 8 + DH * 4 + DH * 4 + 32 + per * 4 + 15) / 16 * 16;
+}
+
+template <int DH, bool CLUSTER>
+__global__ void __launch_bounds__(kThreads) attn_kernel(const AttnArgs a) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    constexpr int LPS = DH / 8;             // lanes per slot (8 dims = 16 B of bf16 each)
+    constexpr int NG = kThreads / LPS;      // slots in flight per CTA iteration
+    const int S = gridDim.x, c = blockIdx.x, h = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cap = a.cap;
+    const int pos = a.pos_const >= 0 ? a.pos_const : a.ctrl->offset;
+    const int slot = pos % cap;
+    const int n_valid = (pos >= cap - 1) ? cap : pos + 1;
+    const int per = (cap + S - 1) / S + 1;
+
+    double *x_sum = reinterpret_cast<double *>(smem);                  // [kAttnMaxSplit] cluster exchange: row sums
+    double *dred = x_sum + kAttnMaxSplit;                              // [8] block reduce scratch
+    float *red = reinterpret_cast<float *>(dred);                      // aliases dred (used at different times)
+    double *x_ctx = dred + 8;                                          // [kAttnMaxSplit][DH] cluster exchange: partial contexts
+    double *part = x_ctx + kAttnMaxSplit * DH;                         // [NG][DH]
+    float *q_s = reinterpret_cast<float *>(part + NG * DH);            // [DH] bf16-rounded q'
+    uint16_t *knew = reinterpret_cast<uint16_t *>(q_s + DH);           // [DH]
+    uint16_t *vnew = knew + DH;                                        // [DH]
+    float *x_max = reinterpret_cast<float *>(vnew + DH);               // [kAttnMaxSplit] cluster exchange: row maxima
+    float *sc_s = x_max + kAttnMaxSplit;                               // [per]
+    (void)per;
+
+    // ---- 1. RoPE (interleaved pairs -> [re half | im half]) and the new K/V row -------------------
+    const float *q = a.qkv + h * DH, *k = a.qkv + a.dim + h * DH, *v = a.qkv + 2 * a.dim + h * DH;
+    if (tid < DH / 2) {
+        const int j = tid;
+        float cs = 1.f, sn = 0.f;
+        if (a.max_period) {
+            // ggml_timestep_embedding: freq = expf(-logf(max_period) * j / half); arg = pos * freq.
+            // cos/sin through double: correctly rounded fp32 irrespective of the libm (order-independent parity)
+            const float arg = (float)pos * a.rope_freq[j];
+            cs = (float)cos((double)arg); sn = (float)sin((double)arg);
+        }
+        const float qr = q[2 * j], qi = q[2 * j + 1], kr = k[2 * j], ki = k[2 * j + 1];
+        float qo_r, qo_i, ko_r, ko_i;
+        if (a.max_period) {
+            qo_r = __fsub_rn(__fmul_rn(qr, cs), __fmul_rn(qi, sn)); qo_i = __fadd_rn(__fmul_rn(qr, sn), __fmul_rn(qi, cs));
+            ko_r = __fsub_rn(__fmul_rn(kr, cs), __fmul_rn(ki, sn)); ko_i = __fadd_rn(__fmul_rn(kr, sn), __fmul_rn(ki, cs));
+            q_s[j] = bf16_round(qo_r); q_s[DH / 2 + j] = bf16_round(qo_i);
+            knew[j] = f32_to_bf16_bits(ko_r); knew[DH / 2 + j] = f32_to_bf16_bits(ko_i);
+        } else {
+            q_s[2 * j] = bf16_round(qr); q_s[2 * j + 1] = bf16_round(qi);
+            knew[2 * j] = f32_to_bf16_bits(kr); knew[2 * j + 1] = f32_to_bf16_bits(ki);
+        }
+        vnew[2 * j] = f32_to_bf16_bits(v[2 * j]); vnew[2 * j + 1] = f32_to_bf16_bits(v[2 * j + 1]);
+    }
+    __syncthreads();
+    // ring insert (moshi_kv_cache_insert_kv): DH bf16 = DH/4 8-byte pieces per row
+    if (c == 0 && tid < DH / 4) {
+        const size_t o = ((size_t)h * cap + slot) * DH;
+        reinterpret_cast<uint2 *>(a.kc + o)[tid] = reinterpret_cast<const uint2 *>(knew)[tid];
+    } else if (c == 0 && tid >= 64 && tid < 64 + DH / 4) {
+        const size_t o = ((size_t)h * cap + slot) * DH;
+        reinterpret_cast<uint2 *>(a.vc + o)[tid - 64] = reinterpret_cast<const uint2 *>(vnew)[tid - 64];
+    }
+
+    // ---- 2. scores over this CTA's share of the valid slots ----------------------------------------
+    const int lo = (int)((long long)n_valid * c / S), hi = (int)((long long)n_valid * (c + 1) / S);
+    const int g = tid / LPS, sl = tid % LPS;
+    const float scale = 1.f / sqrtf((float)DH);
+    float qv[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) qv[i] = q_s[sl * 8 + i];
+    float lmax = -INFINITY;
+    for (int i0 = lo; i0 < hi; i0 += NG) {          // warp-uniform trip count (shuffles below)
+        const int i = i0 + g;
+        const bool valid = i < hi;
+        uint4 kk = make_uint4(0, 0, 0, 0);
+        if (valid) {
+            if (i == slot) kk = reinterpret_cast<const uint4 *>(knew)[sl];
+            else kk = *reinterpret_cast<const uint4 *>(a.kc + ((size_t)h * cap + i) * DH + sl * 8);
+        }
+        // bf16 x bf16 products are exact in fp32; they are summed in double (order-independent)
+        double d = 0.0;
+        d += (double)(bf16_bits_to_f32(kk.x & 0xffff) * qv[0]); d += (double)(bf16_bits_to_f32(kk.x >> 16) * qv[1]);
+        d += (double)(bf16_bits_to_f32(kk.y & 0xffff) * qv[2]); d += (double)(bf16_bits_to_f32(kk.y >> 16) * qv[3]);
+        d += (double)(bf16_bits_to_f32(kk.z & 0xffff) * qv[4]); d += (double)(bf16_bits_to_f32(kk.z >> 16) * qv[5]);
+        d += (double)(bf16_bits_to_f32(kk.w & 0xffff) * qv[6]); d += (double)(bf16_bits_to_f32(kk.w >> 16) * qv[7]);
+#pragma unroll
+        for (int o = LPS / 2; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+        const float s = (float)d * scale + 0.0f;
+        if (valid) {
+            if (sl == 0) sc_s[i - lo] = s;
+            lmax = fmaxf(lmax, s);
+        }
+    }
+    lmax = warp_max(lmax);
+    if (lane == 0) red[warp] = lmax;
+    __syncthreads();
+    float cmax = red[0];
+#pragma unroll
+    for (int w = 1; w < kWarps; w++) cmax = fmaxf(cmax, red[w]);
+    __syncthreads();
+
+    float gmax = cmax;
+    if (CLUSTER) {
+        cg::cluster_group cl = cg::this_cluster();
+        cl.sync();      // every CTA of the cluster has started (its shared memory exists) before remote writes
+        if (tid < S) cl.map_shared_rank(x_max, tid)[c] = cmax;     // scatter my max to every CTA of the cluster
+        cl.sync();
+        gmax = x_max[0];
+        for (int r = 1; r < S; r++) gmax = fmaxf(gmax, x_max[r]);
+    }
+
+    // ---- 3. exp and row sum (ggml soft_max: expf(x - max), sum in double, scale by 1/sum) -----------
+    double lsum = 0.0;
+    for (int i = lo + tid; i < hi; i += kThreads) { const float e = (float)exp((double)(sc_s[i - lo] - gmax)); sc_s[i - lo] = e; lsum += (double)e; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
+    if (lane == 0) dred[warp] = lsum;
+    __syncthreads();
+    double csum = 0.0;
+#pragma unroll
+    for (int w = 0; w < kWarps; w++) csum += dred[w];
+    double gsum = csum;
+    if (CLUSTER) {
+        cg::cluster_group cl = cg::this_cluster();
+        if (tid < S) cl.map_shared_rank(x_sum, tid)[c] = csum;
+        cl.sync();
+        gsum = 0.0;
+        for (int r = 0; r < S; r++) gsum += x_sum[r];
+    }
+    const float inv = (float)(1.0 / gsum);
+
+    // ---- 4. context = sum_i bf16(p_i) * V_i over this CTA's slots ------------------------------------
+    double acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc[i] = 0.0;
+    for (int i = lo + g; i < hi; i += NG) {
+        const float p = bf16_round(sc_s[i - lo] * inv);
+        uint4 vv;
+        if (i == slot) vv = reinterpret_cast<const uint4 *>(vnew)[sl];
+        else vv = *reinterpret_cast<const uint4 *>(a.vc + ((size_t)h * cap + i) * DH + sl * 8);
+        acc[0] += (double)(bf16_bits_to_f32(vv.x & 0xffff) * p); acc[1] += (double)(bf16_bits_to_f32(vv.x >> 16) * p);
+        acc[2] += (double)(bf16_bits_to_f32(vv.y & 0xffff) * p); acc[3] += (double)(bf16_bits_to_f32(vv.y >> 16) * p);
+        acc[4] += (double)(bf16_bits_to_f32(vv.z & 0xffff) * p); acc[5] += (double)(bf16_bits_to_f32(vv.z >> 16) * p);
+        acc[6] += (double)(bf16_bits_to_f32(vv.w & 0xffff) * p); acc[7] += (double)(bf16_bits_to_f32(vv.w >> 16) * p);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) part[g * DH + sl * 8 + i] = acc[i];
+    __syncthreads();
+    double tot = 0.0;
+    if (tid < DH) {
+        for (int gg = 0; gg < NG; gg++) tot += part[gg * DH + tid];
+    }
+    if (CLUSTER) {
+        cg::cluster_group cl = cg::this_cluster();
+        if (tid < DH) cl.map_shared_rank(x_ctx, 0)[c * DH + tid] = tot;    // gather partials in rank 0
+        cl.sync();
+        if (c == 0 && tid < DH) {
+            double t = 0.0;
+            for (int r = 0; r < S; r++) t += x_ctx[r * DH + tid];
+            a.ctx[h * DH + tid] = (float)t;
+        }
+    } else {
+        if (tid < DH) a.ctx[h * DH + tid] = (float)tot;
+    }
+}
+
+}  // namespace msx

@@ -1,0 +1,154 @@
+// common.cuh — shared device helpers and argument structs for the msx kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stddef.h>
+
+namespace msx {
+
+constexpr int kThreads = 256;   // every msx kernel runs 8 warps per CTA
+constexpr int kWarps = kThreads / 32;
+
+// ---- control block: per-stream device-resident step parameters --------------------------------
+// CUDA graphs are captured once per stream; everything that changes per frame (position, tokens,
+// overrides) lives here and is read by the kernels, never passed as a kernel argument.
+struct Ctrl {
+    int32_t offset;                 // temporal position of the step being computed
+    int32_t frame;                  // frames run in resident mode (indexes `feed`)
+    int32_t feed_n;                 // 0 = host mode (tokens[] written by the host)
+    int32_t n_in;                   // n_q + 1
+    const int32_t *feed;            // resident mode: [feed_n][n_q+1]
+    int32_t *trace;                 // resident mode: [n_steps][1+dep_q] outputs or null
+    // ---- host-written input block: one H2D copy per call (kCtrlInOffset / kCtrlInBytes) ----
+    int32_t text_override;          // INT32_MIN = use greedy text token
+    int32_t tokens[40];             // inputs of this frame
+    int32_t force[40];              // depformer feed-forward overrides (INT32_MIN = greedy)
+    int32_t pad0_[3];
+    // ---- device-written output block: one D2H copy per call ----
+    int32_t out_tokens[41];         // {text, audio[dep_q]}
+    int32_t pad1_[3];
+    unsigned long long text_key;    // arg-max keys (see argmax_key())
+    unsigned long long audio_key[40];
+};
+constexpr size_t kCtrlInOffset = 32;
+constexpr size_t kCtrlInBytes = 84 * 4;
+constexpr size_t kCtrlOutOffset = kCtrlInOffset + kCtrlInBytes;
+constexpr size_t kCtrlOutBytes = 44 * 4;
+static_assert(offsetof(Ctrl, text_override) == kCtrlInOffset, "Ctrl layout");
+static_assert(offsetof(Ctrl, out_tokens) == kCtrlOutOffset, "Ctrl layout");
+static_assert(offsetof(Ctrl, text_key) == kCtrlOutOffset + kCtrlOutBytes, "Ctrl layout");
+
+// ---- tensor descriptors -------------------------------------------------------------------------
+// Repacked quantised linear [rows][K] (see DESIGN.md "Data layout in HBM").
+//   Q4_K: qs  rows*(K/2) bytes, per row groups of `gs` pairs: [gs first-chunks][gs second-chunks]
+//         sc  rows*(K/64) u32   {sc_lo, sc_hi, m_lo, m_hi} per 64-weight pair
+//         dd  rows*(K/256) u32  {fp16 d, fp16 dmin} per super-block
+//   Q8_0: qs  rows*K int8, per row groups of `gs` blocks: [gs first-halves][gs second-halves]
+//         dd  rows*(K/32) fp16 d
+struct QLinear {
+    const uint8_t *qs = nullptr;
+    const uint32_t *sc = nullptr;
+    const void *dd = nullptr;
+    int32_t type = 0;     // GgmlType
+    int32_t K = 0;
+    int32_t rows = 0;     // stored ("virtual") rows
+    int32_t gs = 32;      // lanes per row group: 32 or 16
+};
+
+// Embedding table kept in its GGUF row format (single rows are gathered, nothing to coalesce).
+struct EmbTable {
+    const uint8_t *data = nullptr;
+    int32_t type = 0;
+    int32_t K = 0;
+    int32_t rows = 0;
+    int32_t row_bytes = 0;
+};
+
+enum Prologue : int { PRO_PLAIN = 0, PRO_RMS = 1 };
+enum Epilogue : int {
+    EPI_STORE = 0,     // out[r] = acc
+    EPI_RESID = 1,     // out[r] += acc                       (residual stream, in place)
+    EPI_GATE = 2,      // out[r/2] = silu(acc[r]) * acc[r+1]  (rows interleaved at repack)
+    EPI_ARGMAX = 3,    // out[r] = acc and atomicMax(key)
+    EPI_ADD_EMB = 4,   // out[r] = acc + emb_table[token][r]  (depformer_in + last-token embedding)
+};
+
+struct GemvArgs {
+    QLinear w;
+    const float *x = nullptr;       // [K] activations (f32)
+    const float *alpha = nullptr;   // PRO_RMS: [K]
+    float eps = 0.f;
+    float *norm_out = nullptr;      // PRO_RMS: CTA 0 also stores rms_norm(x)*alpha here (transformer_out)
+    float *out = nullptr;
+    unsigned long long *key = nullptr;  // EPI_ARGMAX
+    // EPI_ADD_EMB: token = force/override >= 0 ? that : decoded key / out_tokens
+    EmbTable emb;
+    Ctrl *ctrl = nullptr;
+    int32_t emb_step = 0;           // 0: text token (scaled embedding), k>0: audio token of step k-1 (chained)
+};
+
+// ---- small device helpers -------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// fp32 -> bf16 bits, round to nearest even (ggml_compute_fp32_to_bf16)
+__device__ __forceinline__ uint16_t f32_to_bf16_bits(float f) {
+    uint32_t u = __float_as_uint(f);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 64);
+    return (uint16_t)((u + (0x7fffu + ((u >> 16) & 1u))) >> 16);
+}
+__device__ __forceinline__ float bf16_bits_to_f32(uint32_t h) { return __uint_as_float(h << 16); }
+__device__ __forceinline__ float bf16_round(float f) { return bf16_bits_to_f32(f32_to_bf16_bits(f)); }
+
+// 128-bit streaming load (weights are read exactly once per step: do not allocate in L1)
+__device__ __forceinline__ int4 ldg_stream(const void *p) {
+    int4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+
+// arg-max key: larger value wins, ties -> smaller index (ggml argmax = first maximum)
+__device__ __forceinline__ unsigned long long argmax_key(float v, int idx) {
+    uint32_t u = __float_as_uint(v);
+    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+    return ((unsigned long long)u << 32) | (unsigned long long)(0xffffffffu - (uint32_t)idx);
+}
+__device__ __forceinline__ int argmax_key_index(unsigned long long key) {
+    return (int)(0xffffffffu - (uint32_t)(key & 0xffffffffull));
+}
+
+// one element of a GGUF-format row (Q4_0 / Q8_0 / F32 / F16 / BF16): ggml dequantize_row_* per element
+__device__ __forceinline__ float emb_element(const EmbTable &t, int row, int i) {
+    const uint8_t *r = t.data + (size_t)row * t.row_bytes;
+    switch (t.type) {
+        case 0: return reinterpret_cast<const float *>(r)[i];
+        case 1: return __half2float(reinterpret_cast<const __half *>(r)[i]);
+        case 30: return bf16_bits_to_f32(reinterpret_cast<const uint16_t *>(r)[i]);
+        case 8: {  // Q8_0: 34-byte blocks {fp16 d, int8 qs[32]}
+            const uint8_t *b = r + (size_t)(i >> 5) * 34;
+            float d = __half2float(*reinterpret_cast<const __half *>(b));
+            return (float)((const int8_t *)(b + 2))[i & 31] * d;
+        }
+        case 2: {  // Q4_0: 18-byte blocks {fp16 d, qs[16]}: low nibbles = elems 0..15, high = 16..31
+            const uint8_t *b = r + (size_t)(i >> 5) * 18;
+            float d = __half2float(*reinterpret_cast<const __half *>(b));
+            int j = i & 31;
+            int q = (j < 16) ? (b[2 + j] & 0x0F) : (b[2 + j - 16] >> 4);
+            return (float)(q - 8) * d;
+        }
+    }
+    return 0.f;
+}
+
+}  // namespace msx

@@ -1,0 +1,914 @@
+// engine.cu — model loading/repack, per-stream state, CUDA-graph step orchestration and the C ABI
+// declared in include/moshi_b200.h.  See DESIGN.md for the mapping to the reference.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/moshi_b200.h"
+#include "attention.cuh"
+#include "common.cuh"
+#include "gemv.cuh"
+#include "gguf_file.h"
+#include "misc_kernels.cuh"
+
+using namespace msx;
+
+// -------------------------------------------------------------------------------------------------
+// errors
+// -------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg) { g_err = msg; return code; }
+#define CU(expr)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (expr);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            return fail(MSX_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));               \
+    } while (0)
+
+extern "C" const char *msx_last_error(void) { return g_err.c_str(); }
+extern "C" const char *msx_version(void) { return "moshi_b200 0.1 (sm_100a)"; }
+extern "C" int msx_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+// -------------------------------------------------------------------------------------------------
+// model
+// -------------------------------------------------------------------------------------------------
+struct LayerW {
+    const float *norm1 = nullptr, *norm2 = nullptr;
+    std::vector<QLinear> in_proj, out_proj, lin_in, lin_out;
+};
+
+struct msx_model {
+    msx_config cfg{};
+    int device = 0;
+    int num_sms = 148;
+    int hidden = 0, dep_hidden = 0, dep_cap = 0, dep_nw = 0;
+    std::vector<EmbTable> emb;        // [n_q+1]: text, audio 0..n_q-1
+    EmbTable *d_emb = nullptr;        // device copy of `emb`
+    EmbTable dep_text_emb;
+    std::vector<EmbTable> dep_emb;    // [dep_q-1]
+    std::vector<LayerW> layers, dep_layers;
+    const float *out_norm = nullptr;
+    const float *rope_freq = nullptr, *dep_rope_freq = nullptr;   // [Dh/2] RoPE frequencies (host-computed)
+    QLinear text_linear;
+    std::vector<QLinear> dep_in, linears, extra_heads;
+    std::vector<void *> allocs;
+    int64_t weight_bytes_per_frame = 0;
+    int64_t device_bytes = 0;
+    uint8_t *staging = nullptr;
+    size_t staging_bytes = 0;
+
+    ~msx_model() {
+        cudaSetDevice(device);
+        for (void *p : allocs) cudaFree(p);
+        if (staging) cudaFree(staging);
+    }
+};
+
+namespace {
+
+int dev_alloc(msx_model *m, void **p, size_t bytes) {
+    CU(cudaMalloc(p, std::max<size_t>(bytes, 16)));
+    m->allocs.push_back(*p);
+    m->device_bytes += (int64_t)bytes;
+    return 0;
+}
+
+int ensure_staging(msx_model *m, size_t bytes) {
+    if (bytes <= m->staging_bytes) return 0;
+    if (m->staging) cudaFree(m->staging);
+    m->staging = nullptr; m->staging_bytes = 0;
+    CU(cudaMalloc((void **)&m->staging, bytes));
+    m->staging_bytes = bytes;
+    return 0;
+}
+
+// Upload a GGUF tensor [rows][K] and repack it into device tiles. perm_half: see repack kernels.
+int upload_linear(msx_model *m, const void *host, int type, int64_t K, int64_t rows, int perm_half, QLinear *out) {
+    if (type != T_Q4_K && type != T_Q8_0)
+        return fail(MSX_ERR_FORMAT, std::string("linear weights must be q4_k or q8_0, got ") + ggml_type_name(type));
+    const int64_t rs = ggml_row_size(type, K);
+    if (rs < 0) return fail(MSX_ERR_FORMAT, "K is not a multiple of the block size");
+    const size_t raw = (size_t)rs * rows;
+    if (int e = ensure_staging(m, raw)) return e;
+    CU(cudaMemcpy(m->staging, host, raw, cudaMemcpyHostToDevice));
+    QLinear w;
+    w.type = type; w.K = (int)K; w.rows = (int)rows; w.gs = K >= 4096 ? 32 : 16;
+    void *qs = nullptr, *sc = nullptr, *dd = nullptr;
+    if (type == T_Q4_K) {
+        if (int e = dev_alloc(m, &qs, (size_t)rows * K / 2)) return e;
+        if (int e = dev_alloc(m, &sc, (size_t)rows * (K / 64) * 4)) return e;
+        if (int e = dev_alloc(m, &dd, (size_t)rows * (K / 256) * 4)) return e;
+        const long long n = (long long)rows * (K / 64);
+        repack_q4k_kernel<<<(unsigned)((n + 255) / 256), 256>>>(m->staging, (uint8_t *)qs, (uint32_t *)sc, (uint32_t *)dd,
+                                                                (int)rows, (int)K, w.gs, perm_half);
+    } else {
+        if (int e = dev_alloc(m, &qs, (size_t)rows * K)) return e;
+        if (int e = dev_alloc(m, &dd, (size_t)rows * (K / 32) * 2)) return e;
+        const long long n = (long long)rows * (K / 32);
+        repack_q8_0_kernel<<<(unsigned)((n + 255) / 256), 256>>>(m->staging, (uint8_t *)qs, (uint16_t *)dd, (int)rows, (int)K, w.gs, perm_half);
+    }
+    CU(cudaGetLastError());
+    CU(cudaDeviceSynchronize());
+    w.qs = (const uint8_t *)qs; w.sc = (const uint32_t *)sc; w.dd = dd;
+    *out = w;
+    return 0;
+}
+
+int upload_table(msx_model *m, const void *host, int type, int64_t K, int64_t rows, EmbTable *out) {
+    const int64_t rs = ggml_row_size(type, K);
+    if (rs < 0 || type == T_Q4_K)
+        return fail(MSX_ERR_FORMAT, std::string("embedding table type not supported: ") + ggml_type_name(type));
+    void *d = nullptr;
+    if (int e = dev_alloc(m, &d, (size_t)rs * rows)) return e;
+    CU(cudaMemcpy(d, host, (size_t)rs * rows, cudaMemcpyHostToDevice));
+    out->data = (const uint8_t *)d; out->type = type; out->K = (int)K; out->rows = (int)rows; out->row_bytes = (int)rs;
+    return 0;
+}
+
+struct Loader {
+    msx_model *m;
+    GgufFile &f;
+    int64_t linear_bytes = 0;   // GGUF bytes of the last linear loaded
+
+    const GgufTensor *need(const std::string &name) {
+        const GgufTensor *t = f.find(name);
+        if (!t) { fail(MSX_ERR_FORMAT, "tensor missing in GGUF: " + name); return nullptr; }
+        if (!t->data) { fail(MSX_ERR_FORMAT, "tensor " + name + " has unsupported type " + std::to_string(t->type)); return nullptr; }
+        return t;
+    }
+    int linear(const std::string &name, int64_t K, int64_t rows, QLinear *out, int perm_half = 0) {
+        const GgufTensor *t = need(name);
+        if (!t) return MSX_ERR_FORMAT;
+        if ((K > 0 && t->ne[0] != K) || (rows > 0 && t->ne[1] != rows))
+            return fail(MSX_ERR_FORMAT, "shape mismatch for " + name + ": got [" + std::to_string(t->ne[0]) + "," +
+                                            std::to_string(t->ne[1]) + "], want [" + std::to_string(K) + "," + std::to_string(rows) + "]");
+        linear_bytes = t->nbytes;
+        return upload_linear(m, t->data, t->type, t->ne[0], t->ne[1], perm_half, out);
+    }
+    int table(const std::string &name, int64_t K, int64_t rows, EmbTable *out) {
+        const GgufTensor *t = need(name);
+        if (!t) return MSX_ERR_FORMAT;
+        if (t->ne[0] != K || t->ne[1] != rows)
+            return fail(MSX_ERR_FORMAT, "shape mismatch for " + name);
+        return upload_table(m, t->data, t->type, K, rows, out);
+    }
+    int vec_f32(const std::string &name, int64_t n, const float **out) {
+        const GgufTensor *t = need(name);
+        if (!t) return MSX_ERR_FORMAT;
+        if (t->type != T_F32 || t->ne[0] != n) return fail(MSX_ERR_FORMAT, "norm tensor " + name + " must be f32[" + std::to_string(n) + "]");
+        void *d = nullptr;
+        if (int e = dev_alloc(m, &d, (size_t)n * 4)) return e;
+        CU(cudaMemcpy(d, t->data, (size_t)n * 4, cudaMemcpyHostToDevice));
+        *out = (const float *)d;
+        return 0;
+    }
+};
+
+int check_config(const msx_config *c) {
+    if (!c) return fail(MSX_ERR_ARG, "config is null");
+    if (c->dim <= 0 || c->num_heads <= 0 || c->num_layers <= 0 || c->context <= 0) return fail(MSX_ERR_ARG, "bad temporal dims");
+    if (c->dim % c->num_heads) return fail(MSX_ERR_ARG, "dim % num_heads != 0");
+    const int dh = c->dim / c->num_heads;
+    if (dh != 64 && dh != 128) return fail(MSX_ERR_ARG, "head dim must be 64 or 128");
+    if (c->n_q < 0 || c->n_q + 1 > MSX_MAX_CODEBOOKS || c->dep_q < 0 || c->dep_q > MSX_MAX_STEPS) return fail(MSX_ERR_ARG, "bad codebook counts");
+    if (c->n_delays < c->n_q + 1) return fail(MSX_ERR_ARG, "delays shorter than n_q + 1");
+    if (c->dep_q > 0) {
+        if (c->dep_dim <= 0 || c->dep_heads <= 0 || c->dep_layers <= 0) return fail(MSX_ERR_ARG, "bad depformer dims");
+        const int ddh = c->dep_dim / c->dep_heads;
+        if (c->dep_dim % c->dep_heads || (ddh != 64 && ddh != 128)) return fail(MSX_ERR_ARG, "depformer head dim must be 64 or 128");
+        if (c->dep_context <= 0 && c->schedule_len <= 0) return fail(MSX_ERR_ARG, "depformer needs a context or a schedule");
+        if (c->schedule_len && c->schedule_len < c->dep_q) return fail(MSX_ERR_ARG, "schedule shorter than dep_q");
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int msx_model_load_gguf(const char *path, const msx_config *cfg, int device, msx_model **out) {
+    if (!path || !out) return fail(MSX_ERR_ARG, "null argument");
+    *out = nullptr;
+    if (int e = check_config(cfg)) return e;
+    GgufFile f;
+    std::string err;
+    if (!f.open(path, err)) {
+        const bool io = err.rfind("cannot open", 0) == 0 || err.rfind("cannot stat", 0) == 0;
+        return fail(io ? MSX_ERR_IO : MSX_ERR_FORMAT, err);
+    }
+    int ndev = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(MSX_ERR_CUDA, "no such CUDA device " + std::to_string(device));
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(MSX_ERR_CUDA, std::string("moshi_b200 is built for sm_100a only; device is ") + prop.name);
+
+    std::unique_ptr<msx_model> m(new msx_model);
+    m->cfg = *cfg; m->device = device; m->num_sms = prop.multiProcessorCount;
+    const msx_config &c = m->cfg;
+    Loader L{m.get(), f};
+    const int d = c.dim;
+
+    // embeddings (lm.h:386-391)
+    m->emb.resize(c.n_q + 1);
+    if (int e = L.table("lm.text_emb.weight", d, c.text_card + 1, &m->emb[0])) return e;
+    for (int q = 0; q < c.n_q; q++)
+        if (int e = L.table("lm.emb." + std::to_string(q) + ".weight", d, c.card + 1, &m->emb[q + 1])) return e;
+    {
+        void *p = nullptr;
+        if (int e = dev_alloc(m.get(), &p, sizeof(EmbTable) * m->emb.size())) return e;
+        CU(cudaMemcpy(p, m->emb.data(), sizeof(EmbTable) * m->emb.size(), cudaMemcpyHostToDevice));
+        m->d_emb = (EmbTable *)p;
+    }
+    // temporal transformer (transformer.h:1042-1080)
+    m->layers.resize(c.num_layers);
+    int64_t wb = 0;
+    for (int i = 0; i < c.num_layers; i++) {
+        LayerW &l = m->layers[i];
+        const std::string p = "lm.transformer.layers." + std::to_string(i) + ".";
+        l.in_proj.resize(1); l.out_proj.resize(1); l.lin_in.resize(1); l.lin_out.resize(1);
+        if (int e = L.vec_f32(p + "norm1.alpha", d, &l.norm1)) return e;
+        if (int e = L.vec_f32(p + "norm2.alpha", d, &l.norm2)) return e;
+        if (int e = L.linear(p + "self_attn.in_projs.0.weight", d, 3 * d, &l.in_proj[0])) return e;
+        wb += L.linear_bytes;
+        if (int e = L.linear(p + "self_attn.out_projs.0.weight", d, d, &l.out_proj[0])) return e;
+        wb += L.linear_bytes;
+        const GgufTensor *t = L.need(p + "gating.linear_in.weight");
+        if (!t) return MSX_ERR_FORMAT;
+        const int F = (int)(t->ne[1] / 2);
+        if (i == 0) m->hidden = F;
+        if (F != m->hidden || t->ne[1] != 2 * F) return fail(MSX_ERR_FORMAT, "inconsistent gating hidden size");
+        if (int e = L.linear(p + "gating.linear_in.weight", d, 2 * F, &l.lin_in[0], /*perm_half=*/F)) return e;
+        wb += L.linear_bytes;
+        if (int e = L.linear(p + "gating.linear_out.weight", F, d, &l.lin_out[0])) return e;
+        wb += L.linear_bytes;
+    }
+    if (int e = L.vec_f32("lm.out_norm.alpha", d, &m->out_norm)) return e;
+    if (int e = L.linear("lm.text_linear.weight", d, c.text_card, &m->text_linear)) return e;
+    wb += L.linear_bytes;
+
+    // depformer (lm.h:371-385; lm_default.h:72-83 for the number of per-step weights)
+    if (c.dep_q > 0) {
+        const int dd = c.dep_dim;
+        int nw = c.dep_q;
+        if (c.schedule_len) { nw = 0; for (int i = 0; i < c.schedule_len; i++) nw = std::max(nw, c.schedule[i] + 1); }
+        m->dep_nw = nw;
+        m->dep_cap = c.dep_context ? c.dep_context : c.schedule_len;
+        m->dep_in.resize(nw);
+        std::vector<int64_t> dep_in_bytes(nw), layer_bytes(nw, 0);
+        for (int k = 0; k < nw; k++) {
+            if (int e = L.linear("lm.depformer_in." + std::to_string(k) + ".weight", d, dd, &m->dep_in[k])) return e;
+            dep_in_bytes[k] = L.linear_bytes;
+        }
+        if (int e = L.table("lm.depformer_text_emb.weight", dd, c.text_card + 1, &m->dep_text_emb)) return e;
+        m->dep_emb.resize(c.dep_q - 1);
+        for (int k = 0; k < c.dep_q - 1; k++)
+            if (int e = L.table("lm.depformer_emb." + std::to_string(k) + ".weight", dd, c.card + 1, &m->dep_emb[k])) return e;
+        m->dep_layers.resize(c.dep_layers);
+        for (int i = 0; i < c.dep_layers; i++) {
+            LayerW &l = m->dep_layers[i];
+            const std::string p = "lm.depformer.layers." + std::to_string(i) + ".";
+            if (int e = L.vec_f32(p + "norm1.alpha", dd, &l.norm1)) return e;
+            if (int e = L.vec_f32(p + "norm2.alpha", dd, &l.norm2)) return e;
+            l.in_proj.resize(nw); l.out_proj.resize(nw); l.lin_in.resize(nw); l.lin_out.resize(nw);
+            for (int k = 0; k < nw; k++) {
+                const std::string ks = std::to_string(k);
+                if (int e = L.linear(p + "self_attn.in_projs." + ks + ".weight", dd, 3 * dd, &l.in_proj[k])) return e;
+                layer_bytes[k] += L.linear_bytes;
+                if (int e = L.linear(p + "self_attn.out_projs." + ks + ".weight", dd, dd, &l.out_proj[k])) return e;
+                layer_bytes[k] += L.linear_bytes;
+                // per-step gating names: "gating.{k}.linear_in" (transformer.h:1057-1063); single-weight: "gating.linear_in"
+                std::string gname = p + "gating." + ks + ".linear_in.weight", oname = p + "gating." + ks + ".linear_out.weight";
+                if (nw == 1 && !f.find(gname)) { gname = p + "gating.linear_in.weight"; oname = p + "gating.linear_out.weight"; }
+                const GgufTensor *t = L.need(gname);
+                if (!t) return MSX_ERR_FORMAT;
+                const int Fd = (int)(t->ne[1] / 2);
+                if (i == 0 && k == 0) m->dep_hidden = Fd;
+                if (Fd != m->dep_hidden) return fail(MSX_ERR_FORMAT, "inconsistent depformer hidden size");
+                if (int e = L.linear(gname, dd, 2 * Fd, &l.lin_in[k], Fd)) return e;
+                layer_bytes[k] += L.linear_bytes;
+                if (int e = L.linear(oname, Fd, dd, &l.lin_out[k])) return e;
+                layer_bytes[k] += L.linear_bytes;
+            }
+        }
+        m->linears.resize(c.dep_q);
+        for (int k = 0; k < c.dep_q; k++) {
+            if (int e = L.linear("lm.linears." + std::to_string(k) + ".weight", dd, c.card, &m->linears[k])) return e;
+            const int w = nw == 1 ? 0 : (c.schedule_len ? c.schedule[k] : k);
+            wb += L.linear_bytes + dep_in_bytes[w] + layer_bytes[w];
+        }
+    }
+    m->extra_heads.resize(c.extra_heads);
+    for (int j = 0; j < c.extra_heads; j++)
+        if (int e = L.linear("lm.extra_heads." + std::to_string(j) + ".weight", d, 0, &m->extra_heads[j])) return e;
+    m->weight_bytes_per_frame = wb;
+    // RoPE frequencies exactly as ggml_timestep_embedding computes them on the host CPU:
+    // freq_j = expf(-logf(max_period) * j / half)   (rope.h:8-20)
+    auto make_freq = [&](int dh, int max_period, const float **out) -> int {
+        if (!max_period) return 0;
+        const int half = dh / 2;
+        std::vector<float> fr(half);
+        for (int j = 0; j < half; j++) fr[j] = (float)expf(-logf((float)max_period) * j / half);
+        void *p = nullptr;
+        if (int e = dev_alloc(m.get(), &p, half * 4)) return e;
+        CU(cudaMemcpy(p, fr.data(), half * 4, cudaMemcpyHostToDevice));
+        *out = (const float *)p;
+        return 0;
+    };
+    if (int e = make_freq(c.dim / c.num_heads, c.max_period, &m->rope_freq)) return e;
+    if (c.dep_q > 0)
+        if (int e = make_freq(c.dep_dim / c.dep_heads, c.dep_max_period, &m->dep_rope_freq)) return e;
+    if (m->staging) { cudaFree(m->staging); m->staging = nullptr; m->staging_bytes = 0; }
+    *out = m.release();
+    return 0;
+}
+
+extern "C" void msx_model_free(msx_model *m) { delete m; }
+extern "C" int msx_model_config(const msx_model *m, msx_config *out) {
+    if (!m || !out) return fail(MSX_ERR_ARG, "null argument");
+    *out = m->cfg; return 0;
+}
+extern "C" int64_t msx_model_weight_bytes_per_frame(const msx_model *m) { return m ? m->weight_bytes_per_frame : 0; }
+extern "C" int64_t msx_model_device_bytes(const msx_model *m) { return m ? m->device_bytes : 0; }
+extern "C" int msx_model_device(const msx_model *m) { return m ? m->device : -1; }
+
+// -------------------------------------------------------------------------------------------------
+// kernel launch helpers
+// -------------------------------------------------------------------------------------------------
+namespace {
+
+struct Launcher {
+    cudaStream_t st;
+    int num_sms;
+    int count = 0;
+    cudaError_t err = cudaSuccess;
+    void check() { if (err == cudaSuccess) err = cudaGetLastError(); count++; }
+
+    template <int WT, int LANES>
+    void gemv_dispatch(const GemvArgs &a, int pro, int epi, int grid, int smem) {
+#define MSX_GEMV_CASE(P, E)                                                              \
+        if (pro == P && epi == E) { gemv_kernel<WT, LANES, P, E><<<grid, kThreads, smem, st>>>(a); check(); return; }
+        MSX_GEMV_CASE(PRO_RMS, EPI_STORE)
+        MSX_GEMV_CASE(PRO_RMS, EPI_GATE)
+        MSX_GEMV_CASE(PRO_RMS, EPI_ARGMAX)
+        MSX_GEMV_CASE(PRO_PLAIN, EPI_STORE)
+        MSX_GEMV_CASE(PRO_PLAIN, EPI_RESID)
+        MSX_GEMV_CASE(PRO_PLAIN, EPI_ARGMAX)
+        MSX_GEMV_CASE(PRO_PLAIN, EPI_ADD_EMB)
+#undef MSX_GEMV_CASE
+        err = cudaErrorInvalidValue;
+    }
+
+    void gemv(const GemvArgs &a, int pro, int epi) {
+        const int n_tiles = (a.w.rows + kRowsPerTile - 1) / kRowsPerTile;
+        const int grid = std::max(1, std::min(2 * num_sms, (n_tiles + 1) / 2));
+        const int smem = gemv_smem_bytes(a.w.type, a.w.K);
+        if (a.w.type == T_Q4_K) {
+            if (a.w.gs == 32) gemv_dispatch<12, 32>(a, pro, epi, grid, smem); else gemv_dispatch<12, 16>(a, pro, epi, grid, smem);
+        } else {
+            if (a.w.gs == 32) gemv_dispatch<8, 32>(a, pro, epi, grid, smem); else gemv_dispatch<8, 16>(a, pro, epi, grid, smem);
+        }
+    }
+
+    void attn(const AttnArgs &a, int heads, int dh, int split) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(split, heads, 1);
+        cfg.blockDim = dim3(kThreads, 1, 1);
+        cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = split; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = split > 1 ? 1 : 0;
+        cudaError_t e;
+        if (dh == 128) {
+            cfg.dynamicSmemBytes = attn_smem_bytes<128>(a.cap, split);
+            e = split > 1 ? cudaLaunchKernelEx(&cfg, attn_kernel<128, true>, a) : cudaLaunchKernelEx(&cfg, attn_kernel<128, false>, a);
+        } else {
+            cfg.dynamicSmemBytes = attn_smem_bytes<64>(a.cap, split);
+            e = split > 1 ? cudaLaunchKernelEx(&cfg, attn_kernel<64, true>, a) : cudaLaunchKernelEx(&cfg, attn_kernel<64, false>, a);
+        }
+        if (err == cudaSuccess) err = e;
+        check();
+    }
+};
+
+int attn_split_for(int heads, int cap, int num_sms) {
+    int s = 1;
+    while (s * 2 <= kAttnMaxSplit && heads * s * 2 <= num_sms && cap / (s * 2) >= 1) s *= 2;
+    return s;
+}
+
+}  // namespace
+
+// -------------------------------------------------------------------------------------------------
+// stream
+// -------------------------------------------------------------------------------------------------
+struct msx_stream {
+    msx_model *m = nullptr;
+    int cap = 0;
+    int attn_split = 1;
+    cudaStream_t st = nullptr;
+    Ctrl *ctrl = nullptr;            // device
+    int32_t *h_in = nullptr;         // pinned: text_override, tokens[40], force[40], pad
+    int32_t *h_out = nullptr;        // pinned: out_tokens[41]
+    uint16_t *kc = nullptr, *vc = nullptr, *dkc = nullptr, *dvc = nullptr;
+    float *x = nullptr, *qkv = nullptr, *ctx = nullptr, *gate = nullptr, *tout = nullptr, *text_logits = nullptr;
+    float *dx = nullptr, *dqkv = nullptr, *dctx = nullptr, *dgate = nullptr, *audio_logits = nullptr, *vad_logits = nullptr;
+    cudaGraphExec_t g_temporal = nullptr, g_depformer = nullptr;
+    int launches_temporal = 0, launches_depformer = 0;
+    int host_offset = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<void *> allocs;
+
+    ~msx_stream() {
+        if (m) cudaSetDevice(m->device);
+        if (g_temporal) cudaGraphExecDestroy(g_temporal);
+        if (g_depformer) cudaGraphExecDestroy(g_depformer);
+        for (void *p : allocs) cudaFree(p);
+        if (h_in) cudaFreeHost(h_in);
+        if (h_out) cudaFreeHost(h_out);
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        if (st) cudaStreamDestroy(st);
+    }
+};
+
+namespace {
+
+int salloc(msx_stream *s, void **p, size_t bytes) {
+    CU(cudaMalloc(p, std::max<size_t>(bytes, 16)));
+    CU(cudaMemset(*p, 0, std::max<size_t>(bytes, 16)));
+    s->allocs.push_back(*p);
+    return 0;
+}
+
+size_t kv_elems(const msx_stream *s) { return (size_t)s->m->cfg.num_layers * s->cap * s->m->cfg.dim; }
+size_t dkv_elems(const msx_stream *s) { return (size_t)s->m->cfg.dep_layers * s->m->dep_cap * s->m->cfg.dep_dim; }
+
+// one transformer layer (transformer.h:910-1039) as 5 launches
+void enqueue_layer(Launcher &L, const msx_stream *s, const LayerW &lw, int w, bool temporal, int layer, int pos_const) {
+    const msx_model *m = s->m; const msx_config &c = m->cfg;
+    const int dim = temporal ? c.dim : c.dep_dim, heads = temporal ? c.num_heads : c.dep_heads;
+    const int cap = temporal ? s->cap : m->dep_cap;
+    float *x = temporal ? s->x : s->dx, *qkv = temporal ? s->qkv : s->dqkv, *ctx = temporal ? s->ctx : s->dctx, *gate = temporal ? s->gate : s->dgate;
+    GemvArgs g;
+    g.ctrl = s->ctrl; g.eps = 1e-8f;
+    // x -> rms_norm1 -> in_proj -> qkv
+    g.w = lw.in_proj[w]; g.x = x; g.alpha = lw.norm1; g.out = qkv;
+    L.gemv(g, PRO_RMS, EPI_STORE);
+    // rope + kv insert + attention
+    AttnArgs a;
+    a.qkv = qkv; a.ctx = ctx; a.ctrl = s->ctrl; a.pos_const = pos_const; a.cap = cap; a.dim = dim;
+    a.max_period = temporal ? c.max_period : c.dep_max_period;
+    a.rope_freq = temporal ? m->rope_freq : m->dep_rope_freq;
+    const size_t lstride = (size_t)cap * dim;
+    a.kc = (temporal ? s->kc : s->dkc) + (size_t)layer * lstride;
+    a.vc = (temporal ? s->vc : s->dvc) + (size_t)layer * lstride;
+    L.attn(a, heads, dim / heads, temporal ? s->attn_split : 1);
+    // out_proj + residual
+    g.w = lw.out_proj[w]; g.x = ctx; g.alpha = nullptr; g.out = x;
+    L.gemv(g, PRO_PLAIN, EPI_RESID);
+    // rms_norm2 -> linear_in -> silu gate
+    g.w = lw.lin_in[w]; g.x = x; g.alpha = lw.norm2; g.out = gate;
+    L.gemv(g, PRO_RMS, EPI_GATE);
+    // linear_out + residual
+    g.w = lw.lin_out[w]; g.x = gate; g.alpha = nullptr; g.out = x;
+    L.gemv(g, PRO_PLAIN, EPI_RESID);
+}
+
+void enqueue_temporal(Launcher &L, const msx_stream *s) {
+    const msx_model *m = s->m; const msx_config &c = m->cfg;
+    EmbedArgs e;
+    e.tables = m->d_emb; e.n_tables = c.n_q + 1; e.dim = c.dim; e.ctrl = s->ctrl; e.x = s->x;
+    embed_kernel<<<(c.dim + kThreads - 1) / kThreads, kThreads, 0, L.st>>>(e);
+    L.check();
+    for (int l = 0; l < c.num_layers; l++) enqueue_layer(L, s, m->layers[l], 0, true, l, -1);
+    // out_norm -> transformer_out (kept for depformer / VAD) -> text_linear -> greedy token (lm.h:671-674, 864-868)
+    GemvArgs g;
+    g.ctrl = s->ctrl; g.eps = 1e-8f;
+    g.w = m->text_linear; g.x = s->x; g.alpha = m->out_norm; g.norm_out = s->tout; g.out = s->text_logits;
+    g.key = &s->ctrl->text_key;
+    L.gemv(g, PRO_RMS, EPI_ARGMAX);
+    finalize_temporal_kernel<<<1, 32, 0, L.st>>>(s->ctrl, c.dep_q > 0 ? 1 : 0);
+    L.check();
+}
+
+void enqueue_depformer(Launcher &L, const msx_stream *s) {
+    const msx_model *m = s->m; const msx_config &c = m->cfg;
+    for (int k = 0; k < c.dep_q; k++) {
+        const int wsel = c.schedule_len ? c.schedule[k] : k;            // lm.h:457-462
+        const int w = m->dep_nw == 1 ? 0 : wsel;                        // transformer.h:74-83
+        GemvArgs g;
+        g.ctrl = s->ctrl; g.eps = 1e-8f;
+        // depformer_in[w](transformer_out) + embedding of the previous token (lm.h:464-467, 494-516)
+        g.w = m->dep_in[w]; g.x = s->tout; g.out = s->dx;
+        g.emb = k == 0 ? m->dep_text_emb : m->dep_emb[k - 1];
+        g.emb_step = k;
+        L.gemv(g, PRO_PLAIN, EPI_ADD_EMB);
+        for (int l = 0; l < c.dep_layers; l++) enqueue_layer(L, s, m->dep_layers[l], w, false, l, k);
+        // linears[k] -> logits -> greedy token (no final norm, lm.h:472)
+        GemvArgs h;
+        h.ctrl = s->ctrl;
+        h.w = m->linears[k]; h.x = s->dx; h.out = s->audio_logits + (size_t)k * c.card; h.key = &s->ctrl->audio_key[k];
+        L.gemv(h, PRO_PLAIN, EPI_ARGMAX);
+    }
+    finalize_depformer_kernel<<<1, 64, 0, L.st>>>(s->ctrl, c.dep_q);
+    L.check();
+}
+
+template <typename F>
+int capture(msx_stream *s, F &&body, cudaGraphExec_t *exec, int *launches) {
+    Launcher L{s->st, s->m->num_sms};
+    CU(cudaStreamBeginCapture(s->st, cudaStreamCaptureModeThreadLocal));
+    body(L);
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamEndCapture(s->st, &graph);
+    if (L.err != cudaSuccess) { if (graph) cudaGraphDestroy(graph); return fail(MSX_ERR_CUDA, std::string("kernel launch failed during capture: ") + cudaGetErrorString(L.err)); }
+    if (e != cudaSuccess) return fail(MSX_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+    e = cudaGraphInstantiate(exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) return fail(MSX_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+    *launches = L.count;
+    return 0;
+}
+
+int set_smem_attrs() {
+    // all kernels stay below the 48 KB default except long-context attention with split 1
+    CU(cudaFuncSetAttribute(attn_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    CU(cudaFuncSetAttribute(attn_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    CU(cudaFuncSetAttribute(attn_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    CU(cudaFuncSetAttribute(attn_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int msx_stream_create(msx_model *m, int context_override, msx_stream **out) {
+    if (!m || !out) return fail(MSX_ERR_ARG, "null argument");
+    *out = nullptr;
+    CU(cudaSetDevice(m->device));
+    if (int e = set_smem_attrs()) return e;
+    std::unique_ptr<msx_stream> s(new msx_stream);
+    s->m = m;
+    const msx_config &c = m->cfg;
+    s->cap = context_override > 0 ? std::min(context_override, c.context) : c.context;
+    s->attn_split = attn_split_for(c.num_heads, s->cap, m->num_sms);
+    CU(cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&s->ev0)); CU(cudaEventCreate(&s->ev1));
+    CU(cudaMallocHost((void **)&s->h_in, kCtrlInBytes));
+    CU(cudaMallocHost((void **)&s->h_out, kCtrlOutBytes));
+    if (int e = salloc(s.get(), (void **)&s->ctrl, sizeof(Ctrl))) return e;
+    if (int e = salloc(s.get(), (void **)&s->kc, kv_elems(s.get()) * 2)) return e;
+    if (int e = salloc(s.get(), (void **)&s->vc, kv_elems(s.get()) * 2)) return e;
+    if (int e = salloc(s.get(), (void **)&s->x, (size_t)c.dim * 4)) return e;
+    if (int e = salloc(s.get(), (void **)&s->qkv, (size_t)c.dim * 3 * 4)) return e;
+    if (int e = salloc(s.get(), (void **)&s->ctx, (size_t)c.dim * 4)) return e;
+    if (int e = salloc(s.get(), (void **)&s->gate, (size_t)m->hidden * 4)) return e;
+    if (int e = salloc(s.get(), (void **)&s->tout, (size_t)c.dim * 4)) return e;
+    if (int e = salloc(s.get(), (void **)&s->text_logits, (size_t)c.text_card * 4)) return e;
+    if (c.dep_q > 0) {
+        if (int e = salloc(s.get(), (void **)&s->dkc, dkv_elems(s.get()) * 2)) return e;
+        if (int e = salloc(s.get(), (void **)&s->dvc, dkv_elems(s.get()) * 2)) return e;
+        if (int e = salloc(s.get(), (void **)&s->dx, (size_t)c.dep_dim * 4)) return e;
+        if (int e = salloc(s.get(), (void **)&s->dqkv, (size_t)c.dep_dim * 3 * 4)) return e;
+        if (int e = salloc(s.get(), (void **)&s->dctx, (size_t)c.dep_dim * 4)) return e;
+        if (int e = salloc(s.get(), (void **)&s->dgate, (size_t)m->dep_hidden * 4)) return e;
+        if (int e = salloc(s.get(), (void **)&s->audio_logits, (size_t)c.dep_q * c.card * 4)) return e;
+    }
+    if (c.extra_heads > 0)
+        if (int e = salloc(s.get(), (void **)&s->vad_logits, 64 * 4)) return e;
+    // ctrl: n_in, no overrides
+    Ctrl hc;
+    memset(&hc, 0, sizeof(hc));
+    hc.n_in = c.n_q + 1;
+    hc.text_override = INT32_MIN;
+    for (int i = 0; i < 40; i++) hc.force[i] = INT32_MIN;
+    CU(cudaMemcpy(s->ctrl, &hc, sizeof(hc), cudaMemcpyHostToDevice));
+
+    if (int e = capture(s.get(), [&](Launcher &L) { enqueue_temporal(L, s.get()); }, &s->g_temporal, &s->launches_temporal)) return e;
+    if (c.dep_q > 0)
+        if (int e = capture(s.get(), [&](Launcher &L) { enqueue_depformer(L, s.get()); }, &s->g_depformer, &s->launches_depformer)) return e;
+    CU(cudaStreamSynchronize(s->st));
+    *out = s.release();
+    return 0;
+}
+
+extern "C" void msx_stream_free(msx_stream *s) { delete s; }
+
+extern "C" int msx_stream_reset(msx_stream *s) {
+    if (!s) return fail(MSX_ERR_ARG, "null stream");
+    CU(cudaSetDevice(s->m->device));
+    CU(cudaStreamSynchronize(s->st));
+    CU(cudaMemsetAsync(s->kc, 0, kv_elems(s) * 2, s->st));
+    CU(cudaMemsetAsync(s->vc, 0, kv_elems(s) * 2, s->st));
+    if (s->dkc) { CU(cudaMemsetAsync(s->dkc, 0, dkv_elems(s) * 2, s->st)); CU(cudaMemsetAsync(s->dvc, 0, dkv_elems(s) * 2, s->st)); }
+    CU(cudaMemsetAsync(s->tout, 0, (size_t)s->m->cfg.dim * 4, s->st));
+    CU(cudaMemsetAsync(&s->ctrl->offset, 0, 4, s->st));
+    CU(cudaStreamSynchronize(s->st));
+    s->host_offset = 0;
+    return 0;
+}
+
+extern "C" int msx_stream_offset(const msx_stream *s) { return s ? s->host_offset : -1; }
+extern "C" int64_t msx_stream_kv_bytes_next(const msx_stream *s) {
+    if (!s) return 0;
+    const int n_valid = std::min(s->host_offset + 1, s->cap);
+    return (int64_t)n_valid * 2 * s->m->cfg.dim * 2 * s->m->cfg.num_layers;
+}
+extern "C" int msx_stream_launches_per_frame(const msx_stream *s) { return s ? s->launches_temporal + s->launches_depformer : 0; }
+
+namespace {
+
+int push_inputs(msx_stream *s, const int32_t *tokens, int32_t text_override, const int32_t *force) {
+    const msx_config &c = s->m->cfg;
+    int32_t *h = s->h_in;
+    h[0] = text_override;
+    if (tokens) for (int i = 0; i < c.n_q + 1; i++) h[1 + i] = tokens[i];
+    for (int i = 0; i < 40; i++) h[41 + i] = (force && i < c.dep_q) ? force[i] : INT32_MIN;
+    CU(cudaMemcpyAsync(reinterpret_cast<uint8_t *>(s->ctrl) + kCtrlInOffset, h, kCtrlInBytes, cudaMemcpyHostToDevice, s->st));
+    return 0;
+}
+
+int pull_outputs(msx_stream *s) {
+    CU(cudaMemcpyAsync(s->h_out, reinterpret_cast<uint8_t *>(s->ctrl) + kCtrlOutOffset, kCtrlOutBytes, cudaMemcpyDeviceToHost, s->st));
+    CU(cudaStreamSynchronize(s->st));
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int msx_step_temporal(msx_stream *s, const int32_t *tokens, int32_t *text_token, float *text_logits, float *transformer_out) {
+    if (!s || !tokens) return fail(MSX_ERR_ARG, "null argument");
+    const msx_config &c = s->m->cfg;
+    CU(cudaSetDevice(s->m->device));
+    if (int e = push_inputs(s, tokens, INT32_MIN, nullptr)) return e;
+    CU(cudaGraphLaunch(s->g_temporal, s->st));
+    s->host_offset++;
+    if (int e = pull_outputs(s)) return e;
+    if (text_token) *text_token = s->h_out[0];
+    if (text_logits) CU(cudaMemcpy(text_logits, s->text_logits, (size_t)c.text_card * 4, cudaMemcpyDeviceToHost));
+    if (transformer_out) CU(cudaMemcpy(transformer_out, s->tout, (size_t)c.dim * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int msx_step_depformer(msx_stream *s, int32_t text_token, const int32_t *force, int32_t *audio_tokens, float *audio_logits) {
+    if (!s) return fail(MSX_ERR_ARG, "null stream");
+    const msx_config &c = s->m->cfg;
+    if (c.dep_q <= 0) return fail(MSX_ERR_STATE, "model has no depformer");
+    CU(cudaSetDevice(s->m->device));
+    // tokens[] of the input block are left as they are in h_in (already consumed by the temporal step)
+    if (int e = push_inputs(s, nullptr, text_token, force)) return e;
+    CU(cudaGraphLaunch(s->g_depformer, s->st));
+    if (int e = pull_outputs(s)) return e;
+    if (audio_tokens) for (int k = 0; k < c.dep_q; k++) audio_tokens[k] = s->h_out[1 + k];
+    if (audio_logits) CU(cudaMemcpy(audio_logits, s->audio_logits, (size_t)c.dep_q * c.card * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int msx_step(msx_stream *s, const int32_t *tokens, int32_t *out_tokens) {
+    if (!s || !tokens) return fail(MSX_ERR_ARG, "null argument");
+    const msx_config &c = s->m->cfg;
+    CU(cudaSetDevice(s->m->device));
+    if (int e = push_inputs(s, tokens, INT32_MIN, nullptr)) return e;
+    CU(cudaGraphLaunch(s->g_temporal, s->st));
+    s->host_offset++;
+    if (c.dep_q > 0) CU(cudaGraphLaunch(s->g_depformer, s->st));
+    if (int e = pull_outputs(s)) return e;
+    if (out_tokens) for (int k = 0; k < 1 + c.dep_q; k++) out_tokens[k] = s->h_out[k];
+    return 0;
+}
+
+extern "C" int msx_vad(msx_stream *s, float *vad) {
+    if (!s || !vad) return fail(MSX_ERR_ARG, "null argument");
+    const msx_model *m = s->m;
+    if (m->cfg.extra_heads <= 2) { *vad = 0.f; return 0; }      // lm.h:973-975
+    CU(cudaSetDevice(m->device));
+    const QLinear &w = m->extra_heads[2];
+    if (w.rows > 64) return fail(MSX_ERR_ARG, "extra head wider than 64");
+    Launcher L{s->st, m->num_sms};
+    GemvArgs g;
+    g.ctrl = s->ctrl; g.w = w; g.x = s->tout; g.out = s->vad_logits;
+    L.gemv(g, PRO_PLAIN, EPI_STORE);
+    if (L.err != cudaSuccess) return fail(MSX_ERR_CUDA, cudaGetErrorString(L.err));
+    float h[64];
+    CU(cudaMemcpyAsync(h, s->vad_logits, w.rows * 4, cudaMemcpyDeviceToHost, s->st));
+    CU(cudaStreamSynchronize(s->st));
+    // ggml_soft_max over the head's outputs, element 0 (lm.h:968-971)
+    float mx = h[0];
+    for (int i = 1; i < w.rows; i++) mx = std::max(mx, h[i]);
+    double sum = 0;
+    for (int i = 0; i < w.rows; i++) { h[i] = expf(h[i] - mx); sum += h[i]; }
+    *vad = h[0] * (float)(1.0 / sum);
+    return 0;
+}
+
+extern "C" int msx_run_resident(msx_stream *s, const int32_t *frames, int n_frames, int n_steps, int32_t *out_tokens, float *elapsed_ms) {
+    if (!s || !frames || n_frames <= 0 || n_steps <= 0) return fail(MSX_ERR_ARG, "bad argument");
+    const msx_config &c = s->m->cfg;
+    CU(cudaSetDevice(s->m->device));
+    const int n_in = c.n_q + 1, n_out = 1 + c.dep_q;
+    int32_t *d_feed = nullptr, *d_trace = nullptr;
+    CU(cudaMalloc((void **)&d_feed, (size_t)n_frames * n_in * 4));
+    if (out_tokens) CU(cudaMalloc((void **)&d_trace, (size_t)n_steps * n_out * 4));
+    CU(cudaMemcpy(d_feed, frames, (size_t)n_frames * n_in * 4, cudaMemcpyHostToDevice));
+    if (int e = push_inputs(s, nullptr, INT32_MIN, nullptr)) return e;
+    Ctrl hdr;                       // first 32 bytes: offset, frame, feed_n, n_in, feed, trace
+    memset(&hdr, 0, sizeof(hdr));
+    hdr.offset = s->host_offset; hdr.frame = 0; hdr.feed_n = n_frames; hdr.n_in = n_in; hdr.feed = d_feed; hdr.trace = d_trace;
+    CU(cudaMemcpyAsync(s->ctrl, &hdr, kCtrlInOffset, cudaMemcpyHostToDevice, s->st));
+    CU(cudaStreamSynchronize(s->st));
+    CU(cudaEventRecord(s->ev0, s->st));
+    for (int i = 0; i < n_steps; i++) {
+        CU(cudaGraphLaunch(s->g_temporal, s->st));
+        if (c.dep_q > 0) CU(cudaGraphLaunch(s->g_depformer, s->st));
+    }
+    CU(cudaEventRecord(s->ev1, s->st));
+    CU(cudaStreamSynchronize(s->st));
+    s->host_offset += n_steps;
+    if (elapsed_ms) CU(cudaEventElapsedTime(elapsed_ms, s->ev0, s->ev1));
+    if (out_tokens) CU(cudaMemcpy(out_tokens, d_trace, (size_t)n_steps * n_out * 4, cudaMemcpyDeviceToHost));
+    int32_t zero2[2] = {0, 0};
+    CU(cudaMemcpy(&s->ctrl->frame, zero2, 8, cudaMemcpyHostToDevice));   // frame = 0, feed_n = 0 -> host mode
+    cudaFree(d_feed);
+    if (d_trace) cudaFree(d_trace);
+    return 0;
+}
+
+extern "C" int msx_stream_get_kv(msx_stream *s, int layer, int head, int slot, uint16_t *k, uint16_t *v) {
+    if (!s || !k || !v) return fail(MSX_ERR_ARG, "null argument");
+    const msx_config &c = s->m->cfg;
+    if (layer < 0 || layer >= c.num_layers || head < 0 || head >= c.num_heads || slot < 0 || slot >= s->cap) return fail(MSX_ERR_ARG, "index out of range");
+    CU(cudaSetDevice(s->m->device));
+    const int dh = c.dim / c.num_heads;
+    const size_t o = (((size_t)layer * c.num_heads + head) * s->cap + slot) * dh;
+    CU(cudaMemcpy(k, s->kc + o, dh * 2, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(v, s->vc + o, dh * 2, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// LMGen host logic (reference lm.h:715-743 state, lm.h:778-979 step; greedy, no state machine)
+// -------------------------------------------------------------------------------------------------
+struct msx_gen {
+    msx_stream *s = nullptr;
+    int offset = 0, CT = 0, ncb = 0, max_delay = 0, delay_steps = 0;
+    std::vector<int32_t> cache;       // [CT][ncb], init -2 = lm_ungenerated_token_id
+    std::vector<int32_t> initial;     // {text_card, card, card, ...}
+};
+
+extern "C" int msx_gen_create(msx_stream *s, int delay_steps, msx_gen **out) {
+    if (!s || !out) return fail(MSX_ERR_ARG, "null argument");
+    const msx_config &c = s->m->cfg;
+    auto *g = new msx_gen;
+    g->s = s; g->ncb = c.n_q + 1; g->delay_steps = delay_steps;
+    int md = c.delays[0];
+    for (int i = 0; i < c.n_delays; i++) md = std::max(md, c.delays[i]);     // lm_default.h:177-183
+    g->max_delay = md;
+    g->CT = md + 2 + (c.personaplex ? 1 : 0);                                // lm.h:727-729
+    g->cache.assign((size_t)g->CT * g->ncb, -2);
+    g->initial.assign(g->ncb, c.card);
+    g->initial[0] = c.text_card;
+    *out = g;
+    return 0;
+}
+extern "C" void msx_gen_free(msx_gen *g) { delete g; }
+extern "C" int msx_gen_offset(const msx_gen *g) { return g ? g->offset : -1; }
+extern "C" int msx_gen_max_delay(const msx_gen *g) { return g ? g->max_delay : -1; }
+
+extern "C" int msx_gen_step(msx_gen *g, const int32_t *in_tokens, int n_in, int depformer_replace_tokens, int32_t *out_text, int32_t *out_audio) {
+    if (!g || !out_text || !out_audio) return fail(MSX_ERR_ARG, "null argument");
+    msx_stream *s = g->s;
+    const msx_config &c = s->m->cfg;
+    const int CT = g->CT, ncb = g->ncb;
+    int dep_q = c.dep_q;
+    if (c.personaplex) dep_q = 8;                                             // lm.h:802-805
+    const int dep_q_1 = dep_q + 1;
+    const int needed = ncb - dep_q - 1;
+    bool provided = false;
+    if (needed > 0) {
+        if (!in_tokens || n_in < needed) return fail(MSX_ERR_ARG, "not enough input tokens");   // reference: assert (lm.h:810)
+        if (n_in == ncb) {
+            for (int i = 0; i < ncb; i++) g->cache[(size_t)((g->offset + c.delays[i]) % CT) * ncb + i] = in_tokens[i];
+            provided = true;
+        } else {
+            for (int i = 0; i < needed; i++)
+                g->cache[(size_t)((g->offset + c.delays[dep_q_1 + i]) % CT) * ncb + dep_q_1 + i] = in_tokens[i];
+        }
+    }
+    const int pos = g->offset % CT;
+    int32_t input[MSX_MAX_CODEBOOKS];
+    for (int i = 0; i < ncb; i++) input[i] = (g->offset <= c.delays[i]) ? g->initial[i] : g->cache[(size_t)pos * ncb + i];
+
+    int32_t out[1 + MSX_MAX_STEPS];
+    for (int i = 0; i < 1 + MSX_MAX_STEPS; i++) out[i] = -1;
+    if (c.dep_q > 0 && !depformer_replace_tokens) {
+        if (int e = msx_step(s, input, out)) return e;                        // temporal + depformer, one sync
+    } else {
+        if (int e = msx_step_temporal(s, input, &out[0], nullptr, nullptr)) return e;
+    }
+    const int text_token = out[0];
+    int32_t *audio = out + 1;
+    if (c.dep_q > 0 && g->delay_steps)
+        for (int q = 0; q < c.dep_q; q++)
+            if (g->offset < c.delays[q + 1] + g->delay_steps) audio[q] = -1;  // lm.h:915-921
+    g->offset++;
+    if (!provided) {
+        const int p = g->offset % CT;
+        g->cache[(size_t)p * ncb + 0] = text_token;
+        for (int q = 0; q < c.dep_q; q++) g->cache[(size_t)p * ncb + q + 1] = audio[q];
+    }
+    for (int q = 0; q < c.dep_q; q++) out_audio[q] = audio[q];
+    if (g->offset <= g->max_delay || depformer_replace_tokens) return 0;
+    *out_text = g->cache[(size_t)((g->offset - g->max_delay + c.delays[0]) % CT) * ncb + 0];
+    for (int i = 1; i < dep_q_1; i++)
+        out_audio[i - 1] = g->cache[(size_t)((g->offset - g->max_delay + c.delays[i]) % CT) * ncb + i];
+    for (int q = 0; q < c.dep_q; q++)
+        if (out_audio[q] == -1) return 0;
+    return 1;
+}
+
+// -------------------------------------------------------------------------------------------------
+// unit-level test entry points
+// -------------------------------------------------------------------------------------------------
+namespace {
+int test_setup(int device, std::unique_ptr<msx_model> &m) {
+    int ndev = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(MSX_ERR_CUDA, "no such CUDA device");
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(MSX_ERR_CUDA, "sm_100a device required");
+    m.reset(new msx_model);
+    m->device = device; m->num_sms = prop.multiProcessorCount;
+    return 0;
+}
+}  // namespace
+
+extern "C" int msx_test_gemv(int device, int type, const void *w, int64_t k, int64_t rows, const float *x, const float *alpha, int prologue, float *y) {
+    if (!w || !x || !y) return fail(MSX_ERR_ARG, "null argument");
+    std::unique_ptr<msx_model> m;
+    if (int e = test_setup(device, m)) return e;
+    QLinear ql;
+    if (int e = upload_linear(m.get(), w, type, k, rows, 0, &ql)) return e;
+    float *dx = nullptr, *dy = nullptr, *da = nullptr;
+    if (int e = dev_alloc(m.get(), (void **)&dx, (size_t)k * 4)) return e;
+    if (int e = dev_alloc(m.get(), (void **)&dy, (size_t)rows * 4)) return e;
+    CU(cudaMemcpy(dx, x, (size_t)k * 4, cudaMemcpyHostToDevice));
+    if (prologue == PRO_RMS) {
+        if (!alpha) return fail(MSX_ERR_ARG, "alpha required for the rms prologue");
+        if (int e = dev_alloc(m.get(), (void **)&da, (size_t)k * 4)) return e;
+        CU(cudaMemcpy(da, alpha, (size_t)k * 4, cudaMemcpyHostToDevice));
+    }
+    Launcher L{nullptr, m->num_sms};
+    GemvArgs g;
+    g.w = ql; g.x = dx; g.alpha = da; g.eps = 1e-8f; g.out = dy;
+    L.gemv(g, prologue == PRO_RMS ? PRO_RMS : PRO_PLAIN, EPI_STORE);
+    if (L.err != cudaSuccess) return fail(MSX_ERR_CUDA, std::string("gemv launch: ") + cudaGetErrorString(L.err));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(y, dy, (size_t)rows * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int msx_test_dequant_rows(int device, int type, const void *table, int64_t k, int64_t table_rows, const int32_t *row_ids, int n_rows, float *out) {
+    if (!table || !row_ids || !out) return fail(MSX_ERR_ARG, "null argument");
+    std::unique_ptr<msx_model> m;
+    if (int e = test_setup(device, m)) return e;
+    EmbTable t;
+    if (int e = upload_table(m.get(), table, type, k, table_rows, &t)) return e;
+    int32_t *ids = nullptr; float *o = nullptr;
+    if (int e = dev_alloc(m.get(), (void **)&ids, (size_t)n_rows * 4)) return e;
+    if (int e = dev_alloc(m.get(), (void **)&o, (size_t)n_rows * k * 4)) return e;
+    CU(cudaMemcpy(ids, row_ids, (size_t)n_rows * 4, cudaMemcpyHostToDevice));
+    const long long n = (long long)n_rows * k;
+    dequant_rows_kernel<<<(unsigned)((n + 255) / 256), 256>>>(t, ids, n_rows, o);
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(out, o, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int msx_test_dequant_repacked(int device, int type, const void *w, int64_t k, int64_t rows, float *out) {
+    if (!w || !out) return fail(MSX_ERR_ARG, "null argument");
+    std::unique_ptr<msx_model> m;
+    if (int e = test_setup(device, m)) return e;
+    QLinear ql;
+    if (int e = upload_linear(m.get(), w, type, k, rows, 0, &ql)) return e;
+    float *o = nullptr;
+    const long long n = (long long)rows * k;
+    if (int e = dev_alloc(m.get(), (void **)&o, (size_t)n * 4)) return e;
+    dequant_repacked_kernel<<<(unsigned)((n + 255) / 256), 256>>>(ql, o);
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(out, o, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}

@@ -1,0 +1,144 @@
+// misc_kernels.cuh — embedding sum, frame bookkeeping, load-time repack and test-only dequant kernels.
+#pragma once
+#include "common.cuh"
+
+namespace msx {
+
+// ---- token embedding sum (lm.h:555-584 + lm_utils.h:157-182) --------------------------------------
+// x = E_text(tok[0]) + E_0(tok[1]) + ... + E_{n_q-1}(tok[n_q]), added left to right like the graph.
+// token == -1 -> zeros (scale 0), any other negative -> row 0 (scale 1).
+struct EmbedArgs {
+    const EmbTable *tables = nullptr;   // device array [n_q + 1]
+    int32_t n_tables = 0;
+    int32_t dim = 0;
+    const Ctrl *ctrl = nullptr;
+    float *x = nullptr;
+};
+
+__global__ void __launch_bounds__(kThreads) embed_kernel(const EmbedArgs a) {
+    const Ctrl *c = a.ctrl;
+    const int32_t *toks = c->feed_n ? c->feed + (size_t)(c->frame % c->feed_n) * c->n_in : c->tokens;
+    const int i = blockIdx.x * kThreads + threadIdx.x;
+    if (i >= a.dim) return;
+    float acc = 0.f;
+    for (int t = 0; t < a.n_tables; t++) {
+        const int tok = toks[t];
+        float e = emb_element(a.tables[t], tok < 0 ? 0 : tok, i);
+        e = e * (tok == -1 ? 0.f : 1.f);
+        acc = (t == 0) ? e : acc + e;
+    }
+    a.x[i] = acc;
+}
+
+// ---- frame bookkeeping ------------------------------------------------------------------------------
+// end of the temporal graph: greedy text token out of the arg-max key, position advances
+// (states->offset += T, transformer.h:1269-1270)
+__global__ void finalize_temporal_kernel(Ctrl *c, int has_depformer) {
+    if (threadIdx.x == 0) {
+        c->out_tokens[0] = argmax_key_index(c->text_key);
+        c->text_key = 0ull;
+        c->offset += 1;
+        if (!has_depformer) {
+            if (c->feed_n) { if (c->trace) c->trace[c->frame] = c->out_tokens[0]; c->frame += 1; }
+        }
+    }
+}
+
+// end of the depformer graph: collect the dep_q greedy tokens (lm.h:548-552)
+__global__ void finalize_depformer_kernel(Ctrl *c, int dep_q) {
+    const int k = threadIdx.x;
+    if (k < dep_q) {
+        c->out_tokens[1 + k] = argmax_key_index(c->audio_key[k]);
+        c->audio_key[k] = 0ull;
+    }
+    __syncthreads();
+    if (c->feed_n) {
+        if (c->trace && k <= dep_q) c->trace[(size_t)c->frame * (dep_q + 1) + k] = c->out_tokens[k];
+        __syncthreads();
+        if (k == 0) c->frame += 1;
+    }
+}
+
+// ---- load-time repack (GGUF row-major blocks -> device tiles, see common.cuh QLinear) --------------
+// perm_half > 0 interleaves rows for the gated MLP: stored row v <- source row (v&1 ? perm_half + v/2 : v/2)
+__device__ __forceinline__ int src_row_of(int v, int perm_half) { return perm_half > 0 ? ((v & 1) ? perm_half + (v >> 1) : (v >> 1)) : v; }
+
+__global__ void repack_q4k_kernel(const uint8_t *src, uint8_t *qs, uint32_t *sc, uint32_t *dd,
+                                  int rows, int K, int gs, int perm_half) {
+    const int P = K >> 6, NSB = K >> 8;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // (row, pair)
+    if (idx >= (long long)rows * P) return;
+    const int v = (int)(idx / P), p = (int)(idx % P);
+    const int b = p >> 2, j = p & 3;
+    const uint8_t *blk = src + ((size_t)src_row_of(v, perm_half) * NSB + b) * 144;
+    const uint8_t *s12 = blk + 4;
+    // get_scale_min_k4 for sub-blocks 2j and 2j+1
+    uint32_t scv[2], mv[2];
+#pragma unroll
+    for (int t = 0; t < 2; t++) {
+        const int s = 2 * j + t;
+        if (s < 4) { scv[t] = s12[s] & 63; mv[t] = s12[s + 4] & 63; }
+        else { scv[t] = (s12[s + 4] & 0xF) | ((s12[s - 4] >> 6) << 4); mv[t] = (s12[s + 4] >> 4) | ((s12[s] >> 6) << 4); }
+    }
+    sc[(size_t)v * P + p] = scv[0] | (scv[1] << 8) | (mv[0] << 16) | (mv[1] << 24);
+    if (j == 0) dd[(size_t)v * NSB + b] = (uint32_t)blk[0] | ((uint32_t)blk[1] << 8) | ((uint32_t)blk[2] << 16) | ((uint32_t)blk[3] << 24);
+    const int G = p / gs, q = p % gs, gsz = min(gs, P - G * gs);
+    uint8_t *d0 = qs + (size_t)v * (K >> 1) + (size_t)G * gs * 32 + q * 16;
+    uint8_t *d1 = d0 + gsz * 16;
+    const uint8_t *s0 = blk + 16 + j * 32;
+    *reinterpret_cast<int4 *>(d0) = *reinterpret_cast<const int4 *>(s0);        // 144-byte blocks keep 16 B alignment
+    *reinterpret_cast<int4 *>(d1) = *reinterpret_cast<const int4 *>(s0 + 16);
+}
+
+__global__ void repack_q8_0_kernel(const uint8_t *src, uint8_t *qs, uint16_t *dd, int rows, int K, int gs, int perm_half) {
+    const int P = K >> 5;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // (row, block)
+    if (idx >= (long long)rows * P) return;
+    const int v = (int)(idx / P), p = (int)(idx % P);
+    const uint8_t *blk = src + ((size_t)src_row_of(v, perm_half) * P + p) * 34;
+    dd[(size_t)v * P + p] = (uint16_t)(blk[0] | (blk[1] << 8));
+    const int G = p / gs, q = p % gs, gsz = min(gs, P - G * gs);
+    uint8_t *d0 = qs + (size_t)v * K + (size_t)G * gs * 32 + q * 16;
+    uint8_t *d1 = d0 + gsz * 16;
+    const uint16_t *s16 = reinterpret_cast<const uint16_t *>(blk + 2);           // 34-byte blocks: 2 B alignment only
+    uint16_t *o0 = reinterpret_cast<uint16_t *>(d0), *o1 = reinterpret_cast<uint16_t *>(d1);
+#pragma unroll
+    for (int i = 0; i < 8; i++) { o0[i] = s16[i]; o1[i] = s16[8 + i]; }
+}
+
+// ---- test-only: dequantise the REPACKED tiles back to f32 in source element order -------------------
+__global__ void dequant_repacked_kernel(const QLinear w, float *out) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)w.rows * w.K) return;
+    const int row = (int)(idx / w.K), e = (int)(idx % w.K);
+    if (w.type == 12) {
+        const int P = w.K >> 6, NSB = w.K >> 8;
+        const int p = e >> 6, ee = e & 63, half = ee >> 5, b = ee & 31, chunk = b >> 4;
+        const int G = p / w.gs, q = p % w.gs, gsz = min(w.gs, P - G * w.gs);
+        const uint8_t byte = w.qs[(size_t)row * (w.K >> 1) + (size_t)G * w.gs * 32 + (chunk ? gsz * 16 : 0) + q * 16 + (b & 15)];
+        const int nib = half ? (byte >> 4) : (byte & 15);
+        const uint32_t s = w.sc[(size_t)row * P + p];
+        const uint32_t dd = reinterpret_cast<const uint32_t *>(w.dd)[(size_t)row * NSB + (p >> 2)];
+        const float2 dm = __half22float2(*reinterpret_cast<const __half2 *>(&dd));
+        const float scv = (float)(half ? ((s >> 8) & 0xff) : (s & 0xff));
+        const float mv = (float)(half ? (s >> 24) : ((s >> 16) & 0xff));
+        out[idx] = __fsub_rn(__fmul_rn(__fmul_rn(dm.x, scv), (float)nib), __fmul_rn(dm.y, mv));
+    } else {
+        const int P = w.K >> 5;
+        const int p = e >> 5, b = e & 31, chunk = b >> 4;
+        const int G = p / w.gs, q = p % w.gs, gsz = min(w.gs, P - G * w.gs);
+        const int8_t v = (int8_t)w.qs[(size_t)row * w.K + (size_t)G * w.gs * 32 + (chunk ? gsz * 16 : 0) + q * 16 + (b & 15)];
+        const float d = __half2float(reinterpret_cast<const __half *>(w.dd)[(size_t)row * P + p]);
+        out[idx] = (float)v * d;
+    }
+}
+
+// test-only: gather GGUF-format rows through the embedding path
+__global__ void dequant_rows_kernel(const EmbTable t, const int32_t *ids, int n_rows, float *out) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)n_rows * t.K) return;
+    const int r = (int)(idx / t.K), i = (int)(idx % t.K);
+    out[idx] = emb_element(t, ids[r], i);
+}
+
+}  // namespace msx

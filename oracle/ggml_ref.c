@@ -153,63 +153,55 @@ void orc_quantize_row_q8_K(const float *x, int8_t *qs, float *dout, int16_t *bsu
     }
 }
 
-/* ggml_vec_dot_q4_K_q8_K (generic path): exact integer inner sums, fp32 8-lane partials */
+/* ggml_vec_dot_q4_K_q8_K: integer inner sums exactly as ggml (sub-block dots scaled by the 6-bit scales,
+ * bsums x mins); the per-block fp32 scales d = fp16(d_w)*d_x and dmin = fp16(dmin_w)*d_x are formed in
+ * fp32 like ggml.  ACCUMULATION ORDER: ggml adds the block terms in fp32 in an ISA-dependent order
+ * (generic: 8 lane partials; AVX2/AVX512/NEON: other groupings).  The oracle adds the exact products
+ * d*isum and dmin*imin in double and rounds once, which makes the result independent of summation
+ * order (see DESIGN.md "Order-independent arithmetic"); it differs from any fp32 order by <~1e-6 rel. */
 static float vec_dot_q4_K_q8_K(int64_t n, const block_q4_K *x, const int8_t *yqs, const float *yd, const int16_t *ybsums) {
     const int nb = (int)(n / QK_K);
-    int8_t aux8[QK_K]; int16_t aux16[8]; float sums[8]; int32_t aux32[8];
     uint8_t scales[8], mins[8];
-    memset(sums, 0, sizeof(sums));
-    float sumf = 0;
+    double sumd = 0.0;
     for (int i = 0; i < nb; ++i) {
         const uint8_t *q4 = x[i].qs;
         const int8_t *q8 = yqs + (int64_t)i * QK_K;
         const int16_t *bs = ybsums + (int64_t)i * (QK_K / 16);
-        memset(aux32, 0, sizeof(aux32));
-        int8_t *a = aux8;
-        for (int j = 0; j < QK_K / 64; ++j) {
-            for (int l = 0; l < 32; ++l) a[l] = (int8_t)(q4[l] & 0xF);
-            a += 32;
-            for (int l = 0; l < 32; ++l) a[l] = (int8_t)(q4[l] >> 4);
-            a += 32; q4 += 32;
-        }
         for (int j = 0; j < 8; j++) get_scale_min_k4(j, x[i].scales, &scales[j], &mins[j]);
         int sumi = 0;
         for (int j = 0; j < QK_K / 16; ++j) sumi += bs[j] * mins[j / 2];
-        a = aux8;
-        int is = 0;
-        for (int j = 0; j < QK_K / 32; ++j) {
-            int32_t scale = scales[is++];
-            for (int r = 0; r < 4; r++) {
-                for (int l = 0; l < 8; ++l) aux16[l] = (int16_t)(q8[l] * a[l]);
-                for (int l = 0; l < 8; ++l) aux32[l] += scale * aux16[l];
-                q8 += 8; a += 8;
-            }
+        int32_t isum = 0;
+        for (int j = 0; j < QK_K / 64; ++j) {
+            int32_t lo = 0, hi = 0;
+            for (int l = 0; l < 32; ++l) { lo += (q4[l] & 0xF) * q8[l]; hi += (q4[l] >> 4) * q8[32 + l]; }
+            isum += (int32_t)scales[2 * j] * lo + (int32_t)scales[2 * j + 1] * hi;
+            q4 += 32; q8 += 64;
         }
         const float d = orc_fp16_to_fp32(x[i].d) * yd[i];
-        for (int l = 0; l < 8; ++l) sums[l] += d * aux32[l];
         const float dmin = orc_fp16_to_fp32(x[i].dmin) * yd[i];
-        sumf -= dmin * sumi;
+        sumd += (double)d * (double)isum;
+        sumd -= (double)dmin * (double)sumi;
     }
-    for (int l = 0; l < 8; ++l) sumf += sums[l];
-    return sumf;
+    return (float)sumd;
 }
 
-/* ggml_vec_dot_q8_0_q8_0 (generic) */
+/* ggml_vec_dot_q8_0_q8_0: sumi * (fp16(d_w) * fp16(d_x)) per block; block terms accumulated in double (see above) */
 static float vec_dot_q8_0_q8_0(int64_t n, const block_q8_0 *x, const block_q8_0 *y) {
     const int nb = (int)(n / QK8_0);
-    float sumf = 0;
+    double sumd = 0.0;
     for (int ib = 0; ib < nb; ++ib) {
         int sumi = 0;
         for (int j = 0; j < QK8_0; j++) sumi += x[ib].qs[j] * y[ib].qs[j];
-        sumf += sumi * (orc_fp16_to_fp32(x[ib].d) * orc_fp16_to_fp32(y[ib].d));
+        const float dd = orc_fp16_to_fp32(x[ib].d) * orc_fp16_to_fp32(y[ib].d);
+        sumd += (double)dd * (double)sumi;
     }
-    return sumf;
+    return (float)sumd;
 }
 
-/* ggml_vec_dot_q4_0_q8_0 (generic) */
+/* ggml_vec_dot_q4_0_q8_0 */
 static float vec_dot_q4_0_q8_0(int64_t n, const block_q4_0 *x, const block_q8_0 *y) {
     const int nb = (int)(n / QK4_0);
-    float sumf = 0;
+    double sumd = 0.0;
     for (int ib = 0; ib < nb; ++ib) {
         int sumi0 = 0, sumi1 = 0;
         for (int j = 0; j < QK4_0 / 2; ++j) {
@@ -218,10 +210,10 @@ static float vec_dot_q4_0_q8_0(int64_t n, const block_q4_0 *x, const block_q8_0 
             sumi0 += v0 * y[ib].qs[j];
             sumi1 += v1 * y[ib].qs[j + QK4_0 / 2];
         }
-        int sumi = sumi0 + sumi1;
-        sumf += sumi * orc_fp16_to_fp32(x[ib].d) * orc_fp16_to_fp32(y[ib].d);
+        const float dd = orc_fp16_to_fp32(x[ib].d) * orc_fp16_to_fp32(y[ib].d);
+        sumd += (double)dd * (double)(sumi0 + sumi1);
     }
-    return sumf;
+    return (float)sumd;
 }
 
 /* ggml_compute_forward_mul_mat for one f32 activation column: src1 is converted to the weight
@@ -483,12 +475,14 @@ static void embed_row(const orc_tensor *t, int token, float *row /*[ne0]*/) {
 
 /* moshi_get_timestep_embedding (rope.h:8-20) = ggml_timestep_embedding on ts = arange(T)+offset:
  *   freq_j = expf(-logf(max_period) * j / half);  arg = ts * freq_j;  rotr = cos(arg), roti = sin(arg) */
+/* cos/sin/exp are evaluated in double and rounded to float (= the correctly rounded fp32 value except
+ * with probability ~1e-8), so that the result does not depend on which libm computes it. */
 static void rope_table(float offset_f32, int Dh, int max_period, float *rotr, float *roti) {
     const int half = Dh / 2;
     for (int j = 0; j < half; j++) {
         float freq = (float)expf(-logf((float)max_period) * j / half);
         float arg = offset_f32 * freq;
-        rotr[j] = cosf(arg); roti[j] = sinf(arg);
+        rotr[j] = (float)cos((double)arg); roti[j] = (float)sin((double)arg);
     }
 }
 
@@ -521,7 +515,7 @@ static void attention_head(const uint16_t *K, const uint16_t *V /*[cap][Dh]*/, i
         scratch[i] = s; if (s > maxv) maxv = s;
     }
     double sum = 0;
-    for (int i = 0; i < n_valid; i++) { float e = expf(scratch[i] - maxv); scratch[i] = e; sum += (double)e; }
+    for (int i = 0; i < n_valid; i++) { float e = (float)exp((double)(scratch[i] - maxv)); scratch[i] = e; sum += (double)e; }
     const float inv = (float)(1.0 / sum);
     for (int i = 0; i < n_valid; i++) { float p = scratch[i] * inv; scratch[i] = ideal ? p : bf16_round(p); }
     for (int d = 0; d < Dh; d++) {
@@ -558,8 +552,8 @@ static void transformer_layer(const orc_model *m, const orc_layer *l, int w, int
 
     orc_rms_norm(x, (const float *)l->norm2.data, 1e-8f, nx, dim);
     linear(m, &l->lin_in[w], nx, g);
-    /* gating.h:12-37: silu(left) * right; ggml silu = x/(1+expf(-x)) */
-    for (int i = 0; i < F; i++) { float a = g[i]; float s = a / (1.0f + expf(-a)); mm[i] = s * g[F + i]; }
+    /* gating.h:12-37: silu(left) * right; ggml silu = x/(1+expf(-x)), exp via double (see rope_table) */
+    for (int i = 0; i < F; i++) { float a = g[i]; float s = a / (1.0f + (float)exp((double)(-a))); mm[i] = s * g[F + i]; }
     linear(m, &l->lin_out[w], mm, upd);
     for (int i = 0; i < dim; i++) x[i] = x[i] + upd[i];
 

@@ -1,0 +1,291 @@
+"""GPU parity tests: the CUDA path (through the C ABI, include/moshi_b200.h) against the CPU oracle
+(oracle/ggml_ref.c) on identical random-init GGUF weights and synthetic tokens.
+
+Bars (BASELINE.json north_star): q4_k / q8_0 dequantisation bit-exact; per-step logits within
+max-rel 2e-3; greedy text and audio tokens identical wherever the top-2 margin exceeds that tolerance.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+LOGIT_TOL = 2e-3      # max |gpu - oracle| / max |oracle|   (north_star bar)
+# Both sides accumulate exact block terms in double and round once (DESIGN.md "Order-independent
+# arithmetic"), so the results are expected to be bit-identical; a last-bit difference can only come
+# from a double-rounding coincidence (~1e-8 per output).
+GEMV_TOL = 1e-6
+EXACT_FRACTION = 0.999
+
+
+def assert_bitwise_mostly(a, b, what=""):
+    same = float(np.mean(a.view(np.uint32) == b.view(np.uint32)))
+    assert same >= EXACT_FRACTION, f"{what}: only {same:.5f} of the values are bit-identical"
+
+
+def max_rel(a, b):
+    return float(np.max(np.abs(a.astype(np.float64) - b.astype(np.float64))) / max(1e-30, float(np.max(np.abs(b)))))
+
+
+def top2_margin(logits):
+    s = np.sort(logits.astype(np.float64))
+    return float(s[-1] - s[-2])
+
+
+@pytest.fixture(scope="module")
+def msx():
+    from moshi_cpp_b200 import binding
+    assert binding.lib().msx_device_count() > 0, "no CUDA device: these tests must run on the B200 box"
+    return binding
+
+
+@pytest.fixture(scope="module")
+def orc():
+    import oracle
+    oracle.lib()
+    return oracle
+
+
+# ---------------------------------------------------------------------------------------------------
+# T0: block formats
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("quant,k,rows", [("q4_k", 4096, 64), ("q4_k", 11264, 8), ("q4_k", 1024, 40), ("q4_k", 2816, 24),
+                                          ("q8_0", 4096, 32), ("q8_0", 1024, 48), ("q8_0", 2816, 16), ("q8_0", 96, 8)])
+def test_repacked_dequant_bit_exact(msx, quant, k, rows):
+    from gguf.quants import dequantize
+    from gguf import GGMLQuantizationType as QT
+    from moshi_cpp_b200 import synth
+    rng = np.random.default_rng(7)
+    gt = synth.TYPE_NAMES[quant]
+    raw = synth.random_tensor(rng, gt, rows, k, 0.02)
+    ref = dequantize(raw, QT(gt)).reshape(rows, k)
+    got = msx.test_dequant_repacked(gt, raw, k)
+    assert np.array_equal(ref.view(np.uint32), got.view(np.uint32))
+
+
+@pytest.mark.parametrize("quant", ["q4_0", "q8_0", "f32", "f16", "bf16"])
+def test_embedding_rows_bit_exact(msx, orc, quant):
+    from moshi_cpp_b200 import synth
+    rng = np.random.default_rng(11)
+    gt = synth.TYPE_NAMES[quant]
+    k, rows = 1024, 300
+    raw = synth.random_tensor(rng, gt, rows, k, 0.25)
+    ids = np.array([0, 1, 17, 299, 5, 5], dtype=np.int32)
+    got = msx.test_dequant_rows(gt, raw, k, ids)
+    ref = orc.dequantize(gt, raw[ids], k)
+    assert np.array_equal(ref.view(np.uint32), got.view(np.uint32))
+
+
+# ---------------------------------------------------------------------------------------------------
+# fused GEMV (activation quantisation + dp4a dot + block scales) vs the ggml-CPU-faithful oracle
+# ---------------------------------------------------------------------------------------------------
+GEMV_SHAPES = [(4096, 512), (4096, 12288), (11264, 256), (1024, 3072), (2816, 1024), (1024, 2048), (4096, 6), (512, 10), (768, 512)]
+
+
+@pytest.mark.parametrize("quant", ["q4_k", "q8_0"])
+@pytest.mark.parametrize("k,rows", GEMV_SHAPES)
+@pytest.mark.parametrize("rms", [False, True])
+def test_gemv_vs_oracle(msx, orc, quant, k, rows, rms):
+    from moshi_cpp_b200 import synth
+    if quant == "q4_k" and k % 256:
+        pytest.skip("q4_k needs K % 256 == 0")
+    rng = np.random.default_rng(k * 31 + rows)
+    gt = synth.TYPE_NAMES[quant]
+    raw = synth.random_tensor(rng, gt, rows, k, 1.0 / np.sqrt(k))
+    x = rng.standard_normal(k).astype(np.float32) * 1.7
+    x[3] = 0.0
+    alpha = (1.0 + 0.1 * rng.standard_normal(k)).astype(np.float32) if rms else None
+    xin = orc.rms_norm(x, alpha) if rms else x
+    ref = orc.mul_mat_vec(gt, raw, k, xin)
+    got = msx.test_gemv(gt, raw, k, x, alpha)
+    assert max_rel(got, ref) < GEMV_TOL
+    assert_bitwise_mostly(got, ref, "gemv")
+    # and both sit within quantisation noise of the exact contraction
+    ideal = orc.mul_mat_vec(gt, raw, k, xin, ideal=True)
+    assert max_rel(got, ideal) < 3e-2
+
+
+def test_gemv_zero_and_constant_blocks(msx, orc):
+    """edge cases of quantize_row_q8_K: an all-zero 256-block (d = 0) and ties for the max-|x| carrier"""
+    from moshi_cpp_b200 import synth
+    rng = np.random.default_rng(5)
+    k, rows = 1024, 64
+    raw = synth.random_tensor(rng, synth.GGML_Q4_K, rows, k, 0.03)
+    x = rng.standard_normal(k).astype(np.float32)
+    x[256:512] = 0.0
+    x[512:768] = 0.5
+    x[768] = -2.0; x[900] = 2.0
+    ref = orc.mul_mat_vec(synth.GGML_Q4_K, raw, k, x)
+    got = msx.test_gemv(synth.GGML_Q4_K, raw, k, x)
+    assert max_rel(got, ref) < GEMV_TOL
+
+
+# ---------------------------------------------------------------------------------------------------
+# whole-step parity
+# ---------------------------------------------------------------------------------------------------
+def run_teacher_forced(msx, orc, path, cfg, n_frames, seed=42, check_kv=True):
+    """Drive both implementations with the ORACLE's token history; compare logits every step."""
+    gm = msx.Model(path, cfg); gs = msx.Stream(gm)
+    om = orc.Model(path, cfg); os_ = orc.State(om)
+    rng = np.random.default_rng(seed)
+    n_q, dep_q = cfg["n_q"], cfg["dep_q"]
+    toks = np.array([cfg["text_card"]] + [cfg["card"]] * n_q, dtype=np.int32)
+    worst_text, worst_audio, n_flip = 0.0, 0.0, 0
+    n_exact, n_cmp = 0, 0
+    for f in range(n_frames):
+        t_ref, lg_ref, to_ref = os_.step_temporal(toks)
+        t_gpu, lg_gpu, to_gpu = gs.step_temporal(toks)
+        scale = float(np.max(np.abs(lg_ref)))
+        worst_text = max(worst_text, max_rel(lg_gpu, lg_ref))
+        assert max_rel(lg_gpu, lg_ref) < LOGIT_TOL, f"frame {f}: text logits"
+        assert max_rel(to_gpu, to_ref) < LOGIT_TOL, f"frame {f}: transformer_out"
+        n_cmp += 1; n_exact += int(np.array_equal(lg_gpu.view(np.uint32), lg_ref.view(np.uint32)))
+        if t_gpu != t_ref:
+            n_flip += 1
+            assert top2_margin(lg_ref) <= LOGIT_TOL * scale, f"frame {f}: text token {t_gpu} != {t_ref} with a clear margin"
+        if dep_q > 0:
+            a_ref, al_ref = os_.step_depformer(t_ref)
+            a_gpu, al_gpu = gs.step_depformer(t_ref, force=a_ref)     # feed the oracle's tokens forward
+            for k in range(dep_q):
+                worst_audio = max(worst_audio, max_rel(al_gpu[k], al_ref[k]))
+                assert max_rel(al_gpu[k], al_ref[k]) < LOGIT_TOL, f"frame {f} codebook {k}: audio logits"
+                n_cmp += 1; n_exact += int(np.array_equal(al_gpu[k].view(np.uint32), al_ref[k].view(np.uint32)))
+                if a_gpu[k] != a_ref[k]:
+                    n_flip += 1
+                    assert top2_margin(al_ref[k]) <= LOGIT_TOL * float(np.max(np.abs(al_ref[k]))), f"frame {f} cb {k}: token mismatch with a clear margin"
+            nxt = [t_ref] + list(a_ref)
+        else:
+            nxt = [t_ref]
+        user = list(rng.integers(0, cfg["card"], size=n_q + 1 - len(nxt)))
+        toks = np.array(nxt + user, dtype=np.int32)
+        if f % 7 == 3:
+            toks[1 + (f % n_q)] = -1          # zero embedding
+        if f % 11 == 5:
+            toks[0] = -2                      # "ungenerated" -> row 0
+    if check_kv:
+        # KV rows of the last written slot
+        slot = (n_frames - 1) % cfg["context"]
+        for layer in (0, cfg["num_layers"] - 1):
+            for head in (0, cfg["num_heads"] - 1):
+                kg, vg = gs.get_kv(layer, head, slot); ko, vo = os_.get_kv(layer, head, slot)
+                assert np.array_equal(kg, ko) and np.array_equal(vg, vo), "KV ring rows must be bit-identical"
+    # stronger than the north_star bar: logits are bit-identical step after step
+    assert n_exact >= 0.98 * n_cmp, f"only {n_exact}/{n_cmp} logit vectors bit-identical"
+    return worst_text, worst_audio, n_flip
+
+
+@pytest.mark.parametrize("preset,quant,frames", [("tiny", "q4_k", 80), ("tiny", "q8_0", 60), ("tiny_pplex", "q4_k", 40), ("tiny_stt", "q8_0", 50)])
+def test_step_parity_small(msx, orc, gguf_for, preset, quant, frames):
+    path, cfg = gguf_for(preset, quant)
+    wt, wa, flips = run_teacher_forced(msx, orc, path, cfg, frames)
+    print(f"{preset}/{quant}: worst text max-rel {wt:.2e}, audio {wa:.2e}, margin-excused flips {flips}")
+
+
+@pytest.mark.parametrize("quant", ["q4_k", "q8_0"])
+def test_step_parity_7b_shapes(msx, orc, gguf_for, quant):
+    """Full-size 7B layer / head / depformer shapes (2 temporal layers so the oracle finishes in seconds)."""
+    path, cfg = gguf_for("moshi7b_l2", quant)
+    wt, wa, flips = run_teacher_forced(msx, orc, path, cfg, 4)
+    print(f"moshi7b_l2/{quant}: worst text max-rel {wt:.2e}, audio {wa:.2e}, flips {flips}")
+
+
+def test_greedy_tokens_250_frames(msx, orc, gguf_for):
+    """LMGen end to end (delay ring + step) for 250 frames, free running on both sides."""
+    path, cfg = gguf_for("tiny", "q4_k")
+    gm = msx.Model(path, cfg); gs = msx.Stream(gm); gg = msx.Gen(gs)
+    om = orc.Model(path, cfg); og = orc.LMGen(om)
+    rng = np.random.default_rng(42)
+    n_user = cfg["n_q"] - cfg["dep_q"]
+    emitted = 0
+    for f in range(250):
+        user = rng.integers(0, cfg["card"], size=n_user).astype(np.int32)
+        ok_o, t_o, a_o = og.step(user)
+        ok_g, t_g, a_g = gg.step(user)
+        assert ok_g == ok_o, f"frame {f}: emit flag"
+        assert gg.offset == og.offset
+        if ok_o:
+            emitted += 1
+            assert t_g == t_o and np.array_equal(a_g, a_o), f"frame {f}: tokens differ"
+        else:
+            assert np.array_equal(a_g, a_o)
+    assert emitted == 250 - max(cfg["delays"])
+
+
+def test_gen_provided_and_replace(msx, orc, gguf_for):
+    """all-streams-provided input (prompt replay, lm.h:812-817) and depformer_replace_tokens"""
+    path, cfg = gguf_for("tiny", "q4_k")
+    gm = msx.Model(path, cfg); gs = msx.Stream(gm); gg = msx.Gen(gs, delay_steps=2)
+    ocfg = dict(cfg)
+    om = orc.Model(path, ocfg, delay_steps=2); og = orc.LMGen(om)
+    rng = np.random.default_rng(3)
+    for f in range(12):
+        if f < 4:
+            toks = rng.integers(0, cfg["card"], size=cfg["n_q"] + 1).astype(np.int32)
+        else:
+            toks = rng.integers(0, cfg["card"], size=cfg["n_q"] - cfg["dep_q"]).astype(np.int32)
+        rep = f < 2
+        r_o = og.step(toks, replace=rep); r_g = gg.step(toks, replace=rep)
+        assert r_o[0] == r_g[0] and np.array_equal(r_o[2], r_g[2]), f"frame {f}"
+        if r_o[0]:
+            assert r_o[1] == r_g[1]
+
+
+def test_vad_head(msx, orc, gguf_for):
+    path, cfg = gguf_for("tiny_stt", "q8_0")
+    gm = msx.Model(path, cfg); gs = msx.Stream(gm)
+    om = orc.Model(path, cfg); os_ = orc.State(om)
+    rng = np.random.default_rng(9)
+    for f in range(5):
+        toks = rng.integers(0, cfg["card"], size=cfg["n_q"] + 1).astype(np.int32)
+        os_.step_temporal(toks); gs.step_temporal(toks, want_logits=False)
+        assert abs(gs.vad() - os_.vad()) < 1e-4
+
+
+def test_resident_replay_matches_host_steps(msx, gguf_for):
+    """msx_run_resident (tokens resident in HBM, no host round trips) produces the same tokens as msx_step"""
+    path, cfg = gguf_for("tiny", "q4_k")
+    gm = msx.Model(path, cfg)
+    rng = np.random.default_rng(1)
+    frames = rng.integers(0, cfg["card"], size=(16, cfg["n_q"] + 1)).astype(np.int32)
+    frames[:, 0] = rng.integers(0, cfg["text_card"], size=16)
+    s1 = msx.Stream(gm)
+    host = np.stack([s1.step(frames[i % 16]) for i in range(40)])
+    s2 = msx.Stream(gm)
+    ms, dev = s2.run_resident(frames, 40, want_tokens=True)
+    assert ms > 0 and np.array_equal(host, dev)
+    assert s2.offset == 40
+    # and the stream keeps working in host mode afterwards
+    a = s1.step(frames[3]); b = s2.step(frames[3])
+    assert np.array_equal(a, b)
+
+
+def test_stream_reset_and_context_override(msx, gguf_for):
+    path, cfg = gguf_for("tiny", "q4_k")
+    gm = msx.Model(path, cfg)
+    rng = np.random.default_rng(2)
+    frames = rng.integers(0, cfg["card"], size=(30, cfg["n_q"] + 1)).astype(np.int32)
+    s = msx.Stream(gm)
+    a = np.stack([s.step(f) for f in frames])
+    s.reset()
+    assert s.offset == 0
+    b = np.stack([s.step(f) for f in frames])
+    assert np.array_equal(a, b)
+    # smaller ring (tools' "-c N"): identical until the smaller ring wraps
+    s8 = msx.Stream(gm, context=8)
+    c = np.stack([s8.step(f) for f in frames[:8]])
+    assert np.array_equal(a[:8], c)
+
+
+def test_errors(msx, gguf_for, tmp_path):
+    path, cfg = gguf_for("tiny", "q4_k")
+    with pytest.raises(msx.MsxError) as e:
+        msx.Model(str(tmp_path / "missing.gguf"), cfg)
+    assert e.value.code == -2
+    bad = tmp_path / "bad.gguf"
+    bad.write_bytes(b"NOPE" + b"\0" * 64)
+    with pytest.raises(msx.MsxError) as e:
+        msx.Model(str(bad), cfg)
+    assert e.value.code == -3
+    wrong = dict(cfg); wrong["text_card"] = 999        # embedding table shape no longer matches
+    with pytest.raises(msx.MsxError) as e:
+        msx.Model(path, wrong)
+    assert e.value.code == -3
