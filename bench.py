@@ -1,0 +1,276 @@
+#!/usr/bin/env python
+"""bench.py — frames/s of the per-frame LM decode step (temporal transformer + depformer).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--preset moshi7b] [--quant q4_k]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one frame of one conversation stream (17 input tokens -> text token + dep_q audio tokens).
+N > 1: one process per GPU, each with its own replica of the weights and its own independent stream
+(the path shards by conversation stream; no data-path collective) -> weak scaling, value = N*K / max-over-ranks time.
+
+value   device-resident replay: token frames already in HBM, K fused frames back to back, CUDA events on the
+        launching stream (msx_run_resident).
+e2e     the same metric through the public per-frame API (msx_gen_step = moshi_lm_send2 + moshi_lm_receive):
+        host tokens in, H2D + launch + D2H + host sync every frame, timed with CUDA events on the same stream.
+roofline  the dominant kernel family (gated-MLP linear_in dequant-GEMV) timed per launch inside a real frame
+        (msx_profile_frame: CUDA event after every launch on the launching stream).
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import _pkgload  # noqa: E402
+
+_pkgload.load()
+from moshi_cpp_b200 import configs, synth  # noqa: E402
+
+SEED_MODEL, SEED_TOKENS = 1234, 42
+FRAME_RATE = 12.5
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed regions run."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index, self.lines, self.proc, self.t = gpu_index, [], None, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.gpu_index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            return
+        self.t = threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True)
+        self.t.start()
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=3)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = [s for s in sm if s > 0.5 * max(sm)] or sm
+        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_frames(cfg, n=64):
+    rng = np.random.default_rng(SEED_TOKENS)
+    fr = rng.integers(0, cfg["card"], size=(n, cfg["n_q"] + 1)).astype(np.int32)
+    fr[:, 0] = rng.integers(0, cfg["text_card"], size=n)
+    return fr
+
+
+def ensure_gguf(preset, quant, rank, world, barrier):
+    path = os.path.join(os.environ.get("MSX_CACHE", "/tmp/msx_cache"), f"{preset}-{quant}-s{SEED_MODEL}.gguf")
+    if rank == 0 and not os.path.exists(path):
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        synth.write_gguf(path, configs.get(preset), quant, SEED_MODEL)
+    barrier()
+    return path
+
+
+def cpu_reference_fps(path, cfg, frames, max_frames, budget_s):
+    """The oracle (CPU restatement of the reference's ggml-CPU path) on the host cores, greedy LMGen."""
+    import oracle
+    om = oracle.Model(path, cfg)
+    og = oracle.LMGen(om)
+    n_user = cfg["n_q"] - cfg["dep_q"] if cfg["dep_q"] > 0 else cfg["n_q"]
+    og.step(frames[0][-n_user:])                       # warm-up frame (page-in of the mmapped weights)
+    t0 = time.perf_counter(); n = 0
+    while n < max_frames:
+        og.step(frames[(n + 1) % len(frames)][-n_user:]); n += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return n / dt, n, dt
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--preset", default="moshi7b")
+    ap.add_argument("--quant", default="q4_k")
+    ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cfg = configs.get(args.preset)
+    workload = f"{args.preset} {args.quant} speech-to-speech step (temporal transformer + depformer), single stream per GPU"
+    base_cfg = {"workload": workload, "streams_per_gpu": 1, "sharding": "independent conversation streams (replicas), no data-path collective",
+                "l2": "inputs larger than L2 (each frame streams the full weight set, 4.1 GB >> 126 MB)",
+                "model_seed": SEED_MODEL, "token_seed": SEED_TOKENS, "context": cfg["context"]}
+    frames = make_frames(cfg)
+    ncores = os.cpu_count() or 1
+
+    # ------------------------------------------------------------------------------------------ reference arm
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        path = ensure_gguf(args.preset, args.quant, 0, 1, lambda: None)
+        os.environ.setdefault("OMP_NUM_THREADS", str(ncores))
+        budget = 150.0
+        fps, n, dt = cpu_reference_fps(path, cfg, frames, max(1, args.steps), budget)
+        sample = (f"{n} of the requested {args.steps} frames (capped at {budget:.0f} s of CPU time), greedy LMGen, same GGUF and token seed; "
+                  "CPU restatement of the reference's ggml-CPU path (oracle/ggml_ref.c, OpenMP) — ggml itself is not buildable here")
+        line = {"impl": "reference", "metric": "frames_per_s", "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+                "steps_measured": n, "warmup": 1, "ms_per_step": 1000.0 / fps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "int8 dot / f32", "data": "synthetic", "config": base_cfg,
+                "realtime_factor": fps / FRAME_RATE,
+                "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": ncores, "kind": "port", "sample": sample},
+                "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------------------------------ our arm
+    import torch
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    from moshi_cpp_b200 import binding as msx
+    path = ensure_gguf(args.preset, args.quant, rank, world, barrier)
+    t_load = time.perf_counter()
+    model = msx.Model(path, cfg, device=local_rank)
+    stream = msx.Stream(model)
+    t_load = time.perf_counter() - t_load
+    K, W = args.steps, max(3, args.warmup)
+
+    sampler = ClockSampler(local_rank)
+    # ---- value: device-resident replay ---------------------------------------------------------
+    stream.run_resident(frames, W)
+    kv0 = stream.kv_bytes_next
+    barrier(); torch.cuda.synchronize(local_rank)
+    sampler.start()
+    ms_res, _ = stream.run_resident(frames, K)
+    torch.cuda.synchronize(local_rank); barrier()
+    kv1 = stream.kv_bytes_next
+    # ---- e2e: public per-frame API, host tokens in / out every frame ------------------------------
+    stream.reset()
+    gen = msx.Gen(stream)
+    n_user = cfg["n_q"] - cfg["dep_q"] if cfg["dep_q"] > 0 else cfg["n_q"]
+    for i in range(W):
+        gen.step(frames[i % len(frames)][-n_user:])
+    barrier(); torch.cuda.synchronize(local_rank)
+    stream.timer_start()
+    t0 = time.perf_counter()
+    for i in range(K):
+        gen.step(frames[(W + i) % len(frames)][-n_user:])
+    ms_e2e = stream.timer_stop()
+    wall_e2e = (time.perf_counter() - t0) * 1e3
+    torch.cuda.synchronize(local_rank); barrier()
+    clocks = sampler.stop()
+
+    if dist is not None:
+        t = torch.tensor([ms_res, ms_e2e], device=f"cuda:{local_rank}", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_res, ms_e2e = float(t[0]), float(t[1])
+
+    # ---- roofline of the dominant kernel, timed per launch inside real frames -----------------------
+    fam_ms, fam_n = {}, {}
+    n_prof = 8
+    for i in range(n_prof):
+        _, fam = stream.profile_frame(frames[i % len(frames)])
+        if i < 2:
+            continue                                   # first eager frames: module / clock warm-up
+        for k, (ms, n) in fam.items():
+            fam_ms[k] = fam_ms.get(k, 0.0) + ms; fam_n[k] = fam_n.get(k, 0) + n
+    tot_ms = sum(fam_ms.values())
+    shares = {k: round(v / tot_ms, 4) for k, v in sorted(fam_ms.items(), key=lambda kv: -kv[1])}
+    dom = "linear_in"
+    row_b = synth.row_bytes(synth.TYPE_NAMES[args.quant], cfg["dim"])
+    dom_bytes = row_b * 2 * cfg["hidden"]              # GGUF bytes of one gating.linear_in matrix = algorithmic bytes per launch
+    dom_ms = fam_ms[dom] / fam_n[dom]
+    peaks, peak_src = load_peaks()
+    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "gemv_kernel<Q4_K> gating.linear_in (rms_norm + q8_K quant + dequant-GEMV + silu gate)",
+                "achieved": achieved, "peak": peaks["hbm_gbs"], "peak_source": f"{peak_src} copy bandwidth (MEASURED_PEAKS.json)",
+                "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": None,
+                "bytes_per_launch": dom_bytes, "launch_us": dom_ms * 1e3, "launches_timed": fam_n[dom],
+                "family_time_share": shares}
+
+    fps = world * K / (ms_res * 1e-3)
+    fps_e2e = world * K / (ms_e2e * 1e-3)
+    w_bytes = model.weight_bytes_per_frame
+    kv_avg = 0.5 * (kv0 + kv1)
+    step_gbs = (w_bytes + kv_avg) / (ms_res / K * 1e-3) / 1e9
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        fps_cpu, n, dt = cpu_reference_fps(path, cfg, frames, 64, args.cpu_budget)
+        cpu = {"value": fps_cpu, "unit": "frames/s", "cores": ncores, "kind": "port",
+               "sample": f"{n} frames ({dt:.1f} s) of the same {args.preset} {args.quant} GGUF and token seed through oracle/ggml_ref.c "
+                         "(CPU restatement of the reference's ggml-CPU path, OpenMP on all host cores)"}
+
+    if rank == 0:
+        line = {
+            "metric": "frames_per_s", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_res / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int8 dot (q4_k x q8_K) / f32", "data": "synthetic",
+            "config": base_cfg, "realtime_factor": fps / world / FRAME_RATE,
+            "step_bytes": {"weights": w_bytes, "kv_avg": kv_avg, "gbs": step_gbs, "frac_of_peak": step_gbs / peaks["hbm_gbs"],
+                           "frac_of_8tbs": step_gbs / 8000.0},
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": 336, "d2h_bytes_per_step": 176,
+                    "ms_per_step": ms_e2e / K, "wall_ms_per_step": wall_e2e / K},
+            "gpu_launches": stream.launches_per_frame * K,
+            "launches_per_frame": stream.launches_per_frame,
+            "clocks": clocks, "load_s": t_load,
+        }
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -107,6 +107,16 @@ MSX_API int msx_run_resident(msx_stream *s, const int32_t *frames, int n_frames,
                              int32_t *out_tokens, float *elapsed_ms);
 /* kernels launched per fused frame (for bench.py "gpu_launches") */
 MSX_API int msx_stream_launches_per_frame(const msx_stream *s);
+/* Measurement aid: runs ONE fused frame eagerly (no CUDA graph) with a CUDA event recorded on the
+ * launching stream after every kernel, and returns the summed device time and launch count per
+ * kernel family (msx_family_name(i), i < msx_family_count()).  Results are identical to msx_step. */
+MSX_API int msx_profile_frame(msx_stream *s, const int32_t *tokens, int32_t *out_tokens,
+                              float *family_ms, int32_t *family_launches, int max_families);
+/* CUDA-event stopwatch on the stream's own CUDA stream: start .. stop spans everything enqueued between them */
+MSX_API int msx_timer_start(msx_stream *s);
+MSX_API int msx_timer_stop(msx_stream *s, float *elapsed_ms);
+MSX_API int msx_family_count(void);
+MSX_API const char *msx_family_name(int i);
 /* KV read-back for parity tests: bf16 bits of K and V for (layer, head, slot), Dh values each */
 MSX_API int msx_stream_get_kv(msx_stream *s, int layer, int head, int slot, uint16_t *k, uint16_t *v);
 
@@ -116,6 +126,10 @@ MSX_API int msx_stream_get_kv(msx_stream *s, int layer, int head, int slot, uint
  * Returns 1 when out_text / out_audio[dep_q] are valid, 0 during warm-up (offset <= max_delay),
  * negative msx_status on error. */
 MSX_API int msx_gen_create(msx_stream *s, int delay_steps, msx_gen **out);
+/* Same host logic over a caller-supplied model step (used by the CPU-only host-logic tests):
+ * fn(user, tokens[n_q+1], depformer_replace_tokens, out[1+dep_q]) fills {text, audio...}, returns 0. */
+typedef int (*msx_step_fn)(void *user, const int32_t *tokens, int depformer_replace_tokens, int32_t *out);
+MSX_API int msx_gen_create_with_callback(const msx_config *cfg, int delay_steps, msx_step_fn fn, void *user, msx_gen **out);
 MSX_API void msx_gen_free(msx_gen *g);
 MSX_API int msx_gen_step(msx_gen *g, const int32_t *in_tokens, int n_in, int depformer_replace_tokens,
                          int32_t *out_text, int32_t *out_audio);

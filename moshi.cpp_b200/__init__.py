@@ -4,4 +4,4 @@ The product is the C-ABI shared library built from csrc/ (include/moshi_b200.h) 
 mirror of the reference API in host/.  This Python package is plumbing for tests and bench.py:
 model presets, the random-init GGUF writer and a ctypes binding of the C-ABI.
 """
-from . import configs, synth  # noqa: F401
+from . import configs, parallel, synth  # noqa: F401

@@ -22,6 +22,9 @@ MSX_MAX_CODEBOOKS, MSX_MAX_STEPS = 40, 40
 MSX_NO_TOKEN = -(2 ** 31)
 
 
+STEP_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_int32), C.c_int, C.POINTER(C.c_int32))
+
+
 class MsxError(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"msx error {code}: {msg}")
@@ -86,9 +89,15 @@ def lib():
     L.msx_vad.argtypes = [vp, C.POINTER(C.c_float)]
     L.msx_run_resident.argtypes = [vp, vp, C.c_int, C.c_int, vp, C.POINTER(C.c_float)]
     L.msx_stream_launches_per_frame.argtypes = [vp]
+    L.msx_profile_frame.argtypes = [vp, vp, vp, vp, vp, C.c_int]
+    L.msx_family_count.restype = C.c_int
+    L.msx_timer_start.argtypes = [vp]
+    L.msx_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
+    L.msx_family_name.restype = C.c_char_p; L.msx_family_name.argtypes = [C.c_int]
     L.msx_stream_get_kv.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp]
     L.msx_gen_create.argtypes = [vp, C.c_int, C.POINTER(vp)]
     L.msx_gen_free.argtypes = [vp]
+    L.msx_gen_create_with_callback.argtypes = [C.POINTER(MsxConfig), C.c_int, STEP_FN, vp, C.POINTER(vp)]
     L.msx_gen_step.argtypes = [vp, vp, C.c_int, C.c_int, i32p, vp]
     L.msx_gen_offset.argtypes = [vp]
     L.msx_gen_max_delay.argtypes = [vp]
@@ -214,6 +223,25 @@ class Stream:
         _check(lib().msx_run_resident(self.h, _p(fr), fr.shape[0], n_steps, _p(out), C.byref(ms)))
         return float(ms.value), out
 
+    def profile_frame(self, tokens):
+        """-> (out_tokens, {family: (ms, launches)}) for one eagerly-launched frame"""
+        cfg = self.model.cfg
+        tok = np.ascontiguousarray(tokens, dtype=np.int32)
+        out = np.empty(1 + cfg["dep_q"], dtype=np.int32)
+        n = lib().msx_family_count()
+        ms = np.zeros(n, dtype=np.float32); cnt = np.zeros(n, dtype=np.int32)
+        _check(lib().msx_profile_frame(self.h, _p(tok), _p(out), _p(ms), _p(cnt), n))
+        fam = {lib().msx_family_name(i).decode(): (float(ms[i]), int(cnt[i])) for i in range(n) if cnt[i]}
+        return out, fam
+
+    def timer_start(self):
+        _check(lib().msx_timer_start(self.h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_float(0)
+        _check(lib().msx_timer_stop(self.h, C.byref(ms)))
+        return float(ms.value)
+
     def get_kv(self, layer: int, head: int, slot: int):
         cfg = self.model.cfg
         dh = cfg["dim"] // cfg["num_heads"]
@@ -233,12 +261,27 @@ class Stream:
 
 
 class Gen:
-    """LMGen over a stream (msx_gen_*): mirrors moshi_lm_send2 / moshi_lm_receive."""
+    """LMGen over a stream (msx_gen_*): mirrors moshi_lm_send2 / moshi_lm_receive.
+    With `step_fn(tokens, replace) -> [text, audio...]` instead of a stream, the same host logic runs
+    over a Python model step (CPU-only host-logic tests)."""
 
-    def __init__(self, stream: Stream, delay_steps: int = 0):
+    def __init__(self, stream: "Stream | None", delay_steps: int = 0, cfg: dict | None = None, step_fn=None):
         self.stream = stream
+        self.cfg = stream.model.cfg if stream is not None else cfg
         h = C.c_void_p()
-        _check(lib().msx_gen_create(stream.h, delay_steps, C.byref(h)))
+        if stream is not None:
+            _check(lib().msx_gen_create(stream.h, delay_steps, C.byref(h)))
+        else:
+            n_in, n_out = self.cfg["n_q"] + 1, 1 + self.cfg["dep_q"]
+
+            def _cb(user, tokens, replace, out):
+                res = step_fn([tokens[i] for i in range(n_in)], bool(replace))
+                for i in range(n_out):
+                    out[i] = int(res[i])
+                return 0
+            self._cb = STEP_FN(_cb)
+            self._ccfg = make_config(self.cfg)
+            _check(lib().msx_gen_create_with_callback(C.byref(self._ccfg), delay_steps, self._cb, None, C.byref(h)))
         self.h = h
 
     @property
@@ -246,7 +289,7 @@ class Gen:
         return lib().msx_gen_offset(self.h)
 
     def step(self, in_tokens, replace: bool = False):
-        cfg = self.stream.model.cfg
+        cfg = self.cfg
         tok = np.ascontiguousarray(in_tokens, dtype=np.int32)
         text = C.c_int32(0)
         audio = np.full(max(1, cfg["dep_q"]), -7, dtype=np.int32)

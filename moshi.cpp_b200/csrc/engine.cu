@@ -348,12 +348,33 @@ extern "C" int msx_model_device(const msx_model *m) { return m ? m->device : -1;
 // -------------------------------------------------------------------------------------------------
 namespace {
 
+// kernel families, for msx_profile_frame()
+enum Family : int {
+    FAM_EMBED = 0, FAM_IN_PROJ, FAM_ATTN, FAM_OUT_PROJ, FAM_LIN_IN, FAM_LIN_OUT, FAM_TEXT_HEAD, FAM_FINALIZE,
+    FAM_DEP_IN, FAM_DEP_IN_PROJ, FAM_DEP_ATTN, FAM_DEP_OUT_PROJ, FAM_DEP_LIN_IN, FAM_DEP_LIN_OUT, FAM_DEP_HEAD, FAM_DEP_FINALIZE,
+    FAM_COUNT
+};
+const char *kFamilyNames[FAM_COUNT] = {
+    "embed", "in_proj", "attn", "out_proj", "linear_in", "linear_out", "text_head", "finalize",
+    "dep_in", "dep_in_proj", "dep_attn", "dep_out_proj", "dep_linear_in", "dep_linear_out", "dep_head", "dep_finalize"};
+
 struct Launcher {
     cudaStream_t st;
     int num_sms;
     int count = 0;
     cudaError_t err = cudaSuccess;
-    void check() { if (err == cudaSuccess) err = cudaGetLastError(); count++; }
+    // optional per-launch timing (eager mode only): events[i], events[i+1] bracket launch i
+    std::vector<cudaEvent_t> *events = nullptr;
+    std::vector<int> *families = nullptr;
+    int fam = 0;
+    void begin() {
+        if (events && events->empty()) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); events->push_back(e); }
+    }
+    void check() {
+        if (err == cudaSuccess) err = cudaGetLastError();
+        count++;
+        if (events) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); events->push_back(e); families->push_back(fam); }
+    }
 
     template <int WT, int LANES>
     void gemv_dispatch(const GemvArgs &a, int pro, int epi, int grid, int smem) {
@@ -370,7 +391,8 @@ struct Launcher {
         err = cudaErrorInvalidValue;
     }
 
-    void gemv(const GemvArgs &a, int pro, int epi) {
+    void gemv(const GemvArgs &a, int pro, int epi, int family = 0) {
+        fam = family; begin();
         const int n_tiles = (a.w.rows + kRowsPerTile - 1) / kRowsPerTile;
         const int grid = std::max(1, std::min(2 * num_sms, (n_tiles + 1) / 2));
         const int smem = gemv_smem_bytes(a.w.type, a.w.K);
@@ -381,7 +403,8 @@ struct Launcher {
         }
     }
 
-    void attn(const AttnArgs &a, int heads, int dh, int split) {
+    void attn(const AttnArgs &a, int heads, int dh, int split, int family = 0) {
+        fam = family; begin();
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(split, heads, 1);
         cfg.blockDim = dim3(kThreads, 1, 1);
@@ -466,7 +489,7 @@ void enqueue_layer(Launcher &L, const msx_stream *s, const LayerW &lw, int w, bo
     g.ctrl = s->ctrl; g.eps = 1e-8f;
     // x -> rms_norm1 -> in_proj -> qkv
     g.w = lw.in_proj[w]; g.x = x; g.alpha = lw.norm1; g.out = qkv;
-    L.gemv(g, PRO_RMS, EPI_STORE);
+    L.gemv(g, PRO_RMS, EPI_STORE, temporal ? FAM_IN_PROJ : FAM_DEP_IN_PROJ);
     // rope + kv insert + attention
     AttnArgs a;
     a.qkv = qkv; a.ctx = ctx; a.ctrl = s->ctrl; a.pos_const = pos_const; a.cap = cap; a.dim = dim;
@@ -475,22 +498,23 @@ void enqueue_layer(Launcher &L, const msx_stream *s, const LayerW &lw, int w, bo
     const size_t lstride = (size_t)cap * dim;
     a.kc = (temporal ? s->kc : s->dkc) + (size_t)layer * lstride;
     a.vc = (temporal ? s->vc : s->dvc) + (size_t)layer * lstride;
-    L.attn(a, heads, dim / heads, temporal ? s->attn_split : 1);
+    L.attn(a, heads, dim / heads, temporal ? s->attn_split : 1, temporal ? FAM_ATTN : FAM_DEP_ATTN);
     // out_proj + residual
     g.w = lw.out_proj[w]; g.x = ctx; g.alpha = nullptr; g.out = x;
-    L.gemv(g, PRO_PLAIN, EPI_RESID);
+    L.gemv(g, PRO_PLAIN, EPI_RESID, temporal ? FAM_OUT_PROJ : FAM_DEP_OUT_PROJ);
     // rms_norm2 -> linear_in -> silu gate
     g.w = lw.lin_in[w]; g.x = x; g.alpha = lw.norm2; g.out = gate;
-    L.gemv(g, PRO_RMS, EPI_GATE);
+    L.gemv(g, PRO_RMS, EPI_GATE, temporal ? FAM_LIN_IN : FAM_DEP_LIN_IN);
     // linear_out + residual
     g.w = lw.lin_out[w]; g.x = gate; g.alpha = nullptr; g.out = x;
-    L.gemv(g, PRO_PLAIN, EPI_RESID);
+    L.gemv(g, PRO_PLAIN, EPI_RESID, temporal ? FAM_LIN_OUT : FAM_DEP_LIN_OUT);
 }
 
 void enqueue_temporal(Launcher &L, const msx_stream *s) {
     const msx_model *m = s->m; const msx_config &c = m->cfg;
     EmbedArgs e;
     e.tables = m->d_emb; e.n_tables = c.n_q + 1; e.dim = c.dim; e.ctrl = s->ctrl; e.x = s->x;
+    L.fam = FAM_EMBED; L.begin();
     embed_kernel<<<(c.dim + kThreads - 1) / kThreads, kThreads, 0, L.st>>>(e);
     L.check();
     for (int l = 0; l < c.num_layers; l++) enqueue_layer(L, s, m->layers[l], 0, true, l, -1);
@@ -499,7 +523,8 @@ void enqueue_temporal(Launcher &L, const msx_stream *s) {
     g.ctrl = s->ctrl; g.eps = 1e-8f;
     g.w = m->text_linear; g.x = s->x; g.alpha = m->out_norm; g.norm_out = s->tout; g.out = s->text_logits;
     g.key = &s->ctrl->text_key;
-    L.gemv(g, PRO_RMS, EPI_ARGMAX);
+    L.gemv(g, PRO_RMS, EPI_ARGMAX, FAM_TEXT_HEAD);
+    L.fam = FAM_FINALIZE;
     finalize_temporal_kernel<<<1, 32, 0, L.st>>>(s->ctrl, c.dep_q > 0 ? 1 : 0);
     L.check();
 }
@@ -515,14 +540,15 @@ void enqueue_depformer(Launcher &L, const msx_stream *s) {
         g.w = m->dep_in[w]; g.x = s->tout; g.out = s->dx;
         g.emb = k == 0 ? m->dep_text_emb : m->dep_emb[k - 1];
         g.emb_step = k;
-        L.gemv(g, PRO_PLAIN, EPI_ADD_EMB);
+        L.gemv(g, PRO_PLAIN, EPI_ADD_EMB, FAM_DEP_IN);
         for (int l = 0; l < c.dep_layers; l++) enqueue_layer(L, s, m->dep_layers[l], w, false, l, k);
         // linears[k] -> logits -> greedy token (no final norm, lm.h:472)
         GemvArgs h;
         h.ctrl = s->ctrl;
         h.w = m->linears[k]; h.x = s->dx; h.out = s->audio_logits + (size_t)k * c.card; h.key = &s->ctrl->audio_key[k];
-        L.gemv(h, PRO_PLAIN, EPI_ARGMAX);
+        L.gemv(h, PRO_PLAIN, EPI_ARGMAX, FAM_DEP_HEAD);
     }
+    L.fam = FAM_DEP_FINALIZE;
     finalize_depformer_kernel<<<1, 64, 0, L.st>>>(s->ctrl, c.dep_q);
     L.check();
 }
@@ -745,6 +771,53 @@ extern "C" int msx_run_resident(msx_stream *s, const int32_t *frames, int n_fram
     return 0;
 }
 
+// Eager (non-graph) run of one fused frame with a CUDA event after every launch: per-family kernel time.
+extern "C" int msx_profile_frame(msx_stream *s, const int32_t *tokens, int32_t *out_tokens,
+                                 float *family_ms, int32_t *family_launches, int max_families) {
+    if (!s || !tokens || !family_ms || !family_launches) return fail(MSX_ERR_ARG, "null argument");
+    const msx_config &c = s->m->cfg;
+    CU(cudaSetDevice(s->m->device));
+    for (int i = 0; i < max_families; i++) { family_ms[i] = 0.f; family_launches[i] = 0; }
+    if (int e = push_inputs(s, tokens, INT32_MIN, nullptr)) return e;
+    std::vector<cudaEvent_t> ev;
+    std::vector<int> fam;
+    Launcher L{s->st, s->m->num_sms};
+    L.events = &ev; L.families = &fam;
+    enqueue_temporal(L, s);
+    s->host_offset++;
+    if (c.dep_q > 0) enqueue_depformer(L, s);
+    if (L.err != cudaSuccess) return fail(MSX_ERR_CUDA, std::string("launch failed: ") + cudaGetErrorString(L.err));
+    if (int e = pull_outputs(s)) return e;
+    if (out_tokens) for (int k = 0; k < 1 + c.dep_q; k++) out_tokens[k] = s->h_out[k];
+    for (size_t i = 0; i + 1 < ev.size(); i++) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+        const int f = fam[i];
+        if (f < max_families) { family_ms[f] += ms; family_launches[f] += 1; }
+    }
+    for (cudaEvent_t e : ev) cudaEventDestroy(e);
+    return 0;
+}
+extern "C" int msx_family_count(void) { return FAM_COUNT; }
+extern "C" const char *msx_family_name(int i) { return (i >= 0 && i < FAM_COUNT) ? kFamilyNames[i] : ""; }
+
+// CUDA-event stopwatch on the stream the step kernels and copies run on (bench.py e2e timing)
+extern "C" int msx_timer_start(msx_stream *s) {
+    if (!s) return fail(MSX_ERR_ARG, "null stream");
+    CU(cudaSetDevice(s->m->device));
+    CU(cudaStreamSynchronize(s->st));
+    CU(cudaEventRecord(s->ev0, s->st));
+    return 0;
+}
+extern "C" int msx_timer_stop(msx_stream *s, float *elapsed_ms) {
+    if (!s || !elapsed_ms) return fail(MSX_ERR_ARG, "null argument");
+    CU(cudaSetDevice(s->m->device));
+    CU(cudaEventRecord(s->ev1, s->st));
+    CU(cudaEventSynchronize(s->ev1));
+    CU(cudaEventElapsedTime(elapsed_ms, s->ev0, s->ev1));
+    return 0;
+}
+
 extern "C" int msx_stream_get_kv(msx_stream *s, int layer, int head, int slot, uint16_t *k, uint16_t *v) {
     if (!s || !k || !v) return fail(MSX_ERR_ARG, "null argument");
     const msx_config &c = s->m->cfg;
@@ -762,16 +835,41 @@ extern "C" int msx_stream_get_kv(msx_stream *s, int layer, int head, int slot, u
 // -------------------------------------------------------------------------------------------------
 struct msx_gen {
     msx_stream *s = nullptr;
+    msx_config cfg{};
+    msx_step_fn fn = nullptr;         // host-logic tests: the model step is a caller-supplied callback
+    void *user = nullptr;
     int offset = 0, CT = 0, ncb = 0, max_delay = 0, delay_steps = 0;
     std::vector<int32_t> cache;       // [CT][ncb], init -2 = lm_ungenerated_token_id
     std::vector<int32_t> initial;     // {text_card, card, card, ...}
 };
 
+static void gen_init_impl(msx_gen *g, int delay_steps);
+static void gen_init(msx_gen *g, int delay_steps) { gen_init_impl(g, delay_steps); }
+
 extern "C" int msx_gen_create(msx_stream *s, int delay_steps, msx_gen **out) {
     if (!s || !out) return fail(MSX_ERR_ARG, "null argument");
     const msx_config &c = s->m->cfg;
     auto *g = new msx_gen;
-    g->s = s; g->ncb = c.n_q + 1; g->delay_steps = delay_steps;
+    g->s = s; g->cfg = c;
+    gen_init(g, delay_steps);
+    *out = g;
+    return 0;
+}
+
+extern "C" int msx_gen_create_with_callback(const msx_config *cfg, int delay_steps, msx_step_fn fn, void *user, msx_gen **out) {
+    if (!cfg || !fn || !out) return fail(MSX_ERR_ARG, "null argument");
+    if (cfg->n_q < 0 || cfg->n_q + 1 > MSX_MAX_CODEBOOKS || cfg->dep_q < 0 || cfg->dep_q > MSX_MAX_STEPS || cfg->n_delays < cfg->n_q + 1)
+        return fail(MSX_ERR_ARG, "bad codebook counts / delays");
+    auto *g = new msx_gen;
+    g->cfg = *cfg; g->fn = fn; g->user = user;
+    gen_init(g, delay_steps);
+    *out = g;
+    return 0;
+}
+
+static void gen_init_impl(msx_gen *g, int delay_steps) {
+    const msx_config &c = g->cfg;
+    g->ncb = c.n_q + 1; g->delay_steps = delay_steps;
     int md = c.delays[0];
     for (int i = 0; i < c.n_delays; i++) md = std::max(md, c.delays[i]);     // lm_default.h:177-183
     g->max_delay = md;
@@ -779,8 +877,6 @@ extern "C" int msx_gen_create(msx_stream *s, int delay_steps, msx_gen **out) {
     g->cache.assign((size_t)g->CT * g->ncb, -2);
     g->initial.assign(g->ncb, c.card);
     g->initial[0] = c.text_card;
-    *out = g;
-    return 0;
 }
 extern "C" void msx_gen_free(msx_gen *g) { delete g; }
 extern "C" int msx_gen_offset(const msx_gen *g) { return g ? g->offset : -1; }
@@ -789,7 +885,7 @@ extern "C" int msx_gen_max_delay(const msx_gen *g) { return g ? g->max_delay : -
 extern "C" int msx_gen_step(msx_gen *g, const int32_t *in_tokens, int n_in, int depformer_replace_tokens, int32_t *out_text, int32_t *out_audio) {
     if (!g || !out_text || !out_audio) return fail(MSX_ERR_ARG, "null argument");
     msx_stream *s = g->s;
-    const msx_config &c = s->m->cfg;
+    const msx_config &c = g->cfg;
     const int CT = g->CT, ncb = g->ncb;
     int dep_q = c.dep_q;
     if (c.personaplex) dep_q = 8;                                             // lm.h:802-805
@@ -812,7 +908,10 @@ extern "C" int msx_gen_step(msx_gen *g, const int32_t *in_tokens, int n_in, int 
 
     int32_t out[1 + MSX_MAX_STEPS];
     for (int i = 0; i < 1 + MSX_MAX_STEPS; i++) out[i] = -1;
-    if (c.dep_q > 0 && !depformer_replace_tokens) {
+    if (g->fn) {
+        if (int e = g->fn(g->user, input, depformer_replace_tokens, out)) return fail(MSX_ERR_STATE, "step callback failed: " + std::to_string(e));
+        if (depformer_replace_tokens) for (int q = 0; q < c.dep_q; q++) out[1 + q] = -1;      // lm.h:909-913
+    } else if (c.dep_q > 0 && !depformer_replace_tokens) {
         if (int e = msx_step(s, input, out)) return e;                        // temporal + depformer, one sync
     } else {
         if (int e = msx_step_temporal(s, input, &out[0], nullptr, nullptr)) return e;

@@ -1,0 +1,209 @@
+"""CPU-only tests: the C-ABI library loads and exports every declared symbol, fails loudly without a
+GPU, the GGUF writer round-trips through gguf-py, the LMGen host logic matches a restatement of the
+reference, and the 2-rank (gloo) plumbing of the stream-sharded mode works."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from moshi_cpp_b200 import binding as msx, configs, parallel, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_abi_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "moshi_b200.h")).read()
+    declared = sorted(set(re.findall(r"MSX_API[^;(]*?\b(msx_\w+)\s*\(", hdr)))
+    assert len(declared) >= 30
+    out = subprocess.check_output(["nm", "-D", "--defined-only", msx.SO_PATH], text=True)
+    exported = set(re.findall(r" T (msx_\w+)", out))
+    missing = [d for d in declared if d not in exported]
+    assert not missing, f"declared in include/moshi_b200.h but not exported: {missing}"
+    L = msx.lib()
+    for d in declared:
+        getattr(L, d)
+    assert b"sm_100a" in L.msx_version()
+
+
+def test_no_cpu_fallback(gguf_for):
+    """without a CUDA device every compute entry point fails with MSX_ERR_CUDA (-4) instead of computing on the host"""
+    if msx.lib().msx_device_count() > 0:
+        pytest.skip("a GPU is present")
+    path, cfg = gguf_for("tiny", "q4_k")
+    with pytest.raises(msx.MsxError) as e:
+        msx.Model(path, cfg)            # the GGUF parses fine; device bring-up must fail
+    assert e.value.code == -4
+    rng = np.random.default_rng(0)
+    raw = synth.random_tensor(rng, synth.GGML_Q4_K, 8, 256, 0.05)
+    with pytest.raises(msx.MsxError) as e:
+        msx.test_gemv(synth.GGML_Q4_K, raw, 256, np.zeros(256, np.float32))
+    assert e.value.code == -4
+
+
+def test_loader_errors_before_device(gguf_for, tmp_path):
+    path, cfg = gguf_for("tiny", "q4_k")
+    with pytest.raises(msx.MsxError) as e:
+        msx.Model(str(tmp_path / "nope.gguf"), cfg)
+    assert e.value.code == -2                                   # reference: NULL from moshi_lm_from_files (moshi.cpp:621-627)
+    bad = tmp_path / "bad.gguf"; bad.write_bytes(b"GGUF" + b"\x07\0\0\0" + b"\0" * 32)
+    with pytest.raises(msx.MsxError) as e:
+        msx.Model(str(bad), cfg)
+    assert e.value.code == -3
+    trunc = tmp_path / "trunc.gguf"; trunc.write_bytes(open(path, "rb").read(4096))
+    with pytest.raises(msx.MsxError) as e:
+        msx.Model(str(trunc), cfg)
+    assert e.value.code == -3
+    wrong = dict(cfg); wrong["num_heads"] = 3
+    with pytest.raises(msx.MsxError) as e:
+        msx.Model(path, wrong)
+    assert e.value.code == -1
+
+
+def test_gguf_roundtrip_with_gguf_py(gguf_for):
+    from gguf import GGUFReader
+    path, cfg = gguf_for("tiny", "q8_0")
+    r = GGUFReader(path)
+    man = synth.manifest(cfg, synth.GGML_Q8_0)
+    assert [t.name for t in r.tensors] == [m[0] for m in man]
+    for t, (name, gt, k, rows, _) in zip(r.tensors, man):
+        assert int(t.tensor_type) == gt and int(t.shape[0]) == k
+        assert t.data.nbytes == synth.row_bytes(gt, k) * rows
+    assert len(r.fields) == 3           # GGUF.version / tensor_count / kv_count only: no metadata, like the reference's files
+
+
+def test_weight_bytes_match_survey():
+    """algorithmic bytes per frame: 7B q4_k = 4 148 232 192 B, q8_0 = 7 835 549 696 B"""
+    def w_bytes(cfg, quant):
+        qt = synth.TYPE_NAMES[quant]
+        tot = 0
+        for name, gt, k, rows, _ in synth.manifest(cfg, qt):
+            if "emb" in name or name.endswith("alpha"):
+                continue
+            tot += synth.row_bytes(gt, k) * rows
+        return tot
+    assert w_bytes(configs.get("moshi7b"), "q4_k") == 4_148_232_192
+    assert w_bytes(configs.get("moshi7b"), "q8_0") == 7_835_549_696
+
+
+# ---- LMGen host logic: restatement of moshi_lmgen_step (lm.h:778-979) in Python as the checker -----
+class RefLMGen:
+    def __init__(self, cfg, step_fn, delay_steps=0):
+        self.c, self.step_fn, self.delay_steps = cfg, step_fn, delay_steps
+        self.ncb = cfg["n_q"] + 1
+        self.max_delay = max(cfg["delays"])
+        self.CT = self.max_delay + 2 + (1 if cfg["model_type"] == "personaplex" else 0)
+        self.cache = [[-2] * self.ncb for _ in range(self.CT)]
+        self.initial = [cfg["text_card"]] + [cfg["card"]] * cfg["n_q"]
+        self.offset = 0
+
+    def step(self, toks, replace=False):
+        c, CT, ncb = self.c, self.CT, self.ncb
+        dep_q = 8 if c["model_type"] == "personaplex" else c["dep_q"]
+        needed = ncb - dep_q - 1
+        provided = False
+        if needed > 0:
+            if len(toks) == ncb:
+                for i in range(ncb):
+                    self.cache[(self.offset + c["delays"][i]) % CT][i] = int(toks[i])
+                provided = True
+            else:
+                for i in range(needed):
+                    self.cache[(self.offset + c["delays"][dep_q + 1 + i]) % CT][dep_q + 1 + i] = int(toks[i])
+        pos = self.offset % CT
+        inp = [self.initial[i] if self.offset <= c["delays"][i] else self.cache[pos][i] for i in range(ncb)]
+        out = self.step_fn(inp, replace)
+        text, audio = out[0], list(out[1:1 + c["dep_q"]])
+        if replace:
+            audio = [-1] * c["dep_q"]
+        if c["dep_q"] > 0 and self.delay_steps:
+            for q in range(c["dep_q"]):
+                if self.offset < c["delays"][q + 1] + self.delay_steps:
+                    audio[q] = -1
+        self.offset += 1
+        if not provided:
+            p = self.offset % CT
+            self.cache[p][0] = text
+            for q in range(c["dep_q"]):
+                self.cache[p][q + 1] = audio[q]
+        if self.offset <= self.max_delay or replace:
+            return 0, None, audio
+        t = self.cache[(self.offset - self.max_delay + c["delays"][0]) % CT][0]
+        for i in range(1, dep_q + 1):
+            audio[i - 1] = self.cache[(self.offset - self.max_delay + c["delays"][i]) % CT][i]
+        if any(a == -1 for a in audio):
+            return 0, None, audio
+        return 1, t, audio
+
+
+@pytest.mark.parametrize("preset,delay_steps", [("tiny", 0), ("tiny", 3), ("tiny_pplex", 0), ("tiny_stt", 0)])
+def test_lmgen_host_logic(preset, delay_steps):
+    cfg = configs.get(preset)
+    n_out = 1 + cfg["dep_q"]
+
+    def fake_model(tokens, replace):         # deterministic function of the gathered input row
+        h = 1469598103934665603
+        for t in tokens:
+            h = ((h ^ (int(t) & 0xFFFFFFFF)) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+        return [int((h >> (5 * i)) % (cfg["text_card"] if i == 0 else cfg["card"])) for i in range(n_out)]
+
+    ref = RefLMGen(cfg, fake_model, delay_steps)
+    gen = msx.Gen(None, delay_steps=delay_steps, cfg=cfg, step_fn=fake_model)
+    rng = np.random.default_rng(1)
+    dep_q_eff = 8 if cfg["model_type"] == "personaplex" else cfg["dep_q"]
+    n_user = cfg["n_q"] - dep_q_eff
+    for f in range(40):
+        if f in (0, 1, 17):
+            toks = rng.integers(0, cfg["card"], size=cfg["n_q"] + 1)      # all streams provided (prompt replay)
+        else:
+            toks = rng.integers(0, cfg["card"], size=n_user)
+        rep = f in (2, 3)
+        ok_r, t_r, a_r = ref.step(toks, rep)
+        ok_g, t_g, a_g = gen.step(toks, rep)
+        assert ok_g == ok_r, f"frame {f}"
+        assert list(a_g) == list(a_r), f"frame {f}"
+        if ok_r:
+            assert t_g == t_r
+        assert gen.offset == ref.offset
+
+
+def test_stream_assignment():
+    a = parallel.assign_streams(64, 8)
+    assert all(len(x) == 8 for x in a) and sorted(sum(a, [])) == list(range(64))
+    assert parallel.assign_streams(3, 2) == [[0, 2], [1]]
+    assert parallel.aggregate_throughput([100, 100], [50.0, 100.0]) == pytest.approx(2000.0)
+
+
+_GLOO_WORKER = r"""
+import os, sys
+sys.path.insert(0, sys.argv[1])
+import _pkgload; _pkgload.load()
+import torch.distributed as dist
+from moshi_cpp_b200 import parallel
+dist.init_process_group("gloo")
+r, w = dist.get_rank(), dist.get_world_size()
+mine = parallel.assign_streams(5, w)[r]
+local_ms = 10.0 * (r + 1)                       # pretend device time
+dist.barrier()
+worst = parallel.reduce_max_ms(local_ms, dist)
+assert worst == 10.0 * w, worst
+import torch
+n = torch.tensor([len(mine)]); dist.all_reduce(n)
+assert int(n[0]) == 5
+if r == 0:
+    print("OK", worst, int(n[0]))
+dist.destroy_process_group()
+"""
+
+
+def test_two_rank_gloo_plumbing(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_GLOO_WORKER)
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29541", str(script), ROOT],
+                         capture_output=True, text=True, timeout=240, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "OK 20.0 5" in out.stdout
