@@ -76,6 +76,11 @@ MSX_API int msx_model_device(const msx_model *m);
 /* ---- per-conversation state: replaces StateContext + moshi_lmmodel_states (lm.h:423-444) ------
  * context_override > 0 shrinks the temporal ring capacity (tools' "-c N", moshi-sts.cpp:254-264). */
 MSX_API int msx_stream_create(msx_model *m, int context_override, msx_stream **out);
+/* flags: MSX_STREAM_PERSISTENT_DEPFORMER = run the whole depformer chain as ONE cooperative "phase program"
+ * kernel with grid barriers (164 launches / 7B frame instead of 420).  Results are bit-identical; on B200 the
+ * default PDL-chained launches are currently faster, so this stays opt-in (cross-check + research path). */
+#define MSX_STREAM_PERSISTENT_DEPFORMER 1
+MSX_API int msx_stream_create_ex(msx_model *m, int context_override, int flags, msx_stream **out);
 MSX_API void msx_stream_free(msx_stream *s);
 MSX_API int msx_stream_reset(msx_stream *s);   /* offset = 0, KV rings zeroed */
 MSX_API int msx_stream_offset(const msx_stream *s);
@@ -115,6 +120,9 @@ MSX_API int msx_profile_frame(msx_stream *s, const int32_t *tokens, int32_t *out
 /* CUDA-event stopwatch on the stream's own CUDA stream: start .. stop spans everything enqueued between them */
 MSX_API int msx_timer_start(msx_stream *s);
 MSX_API int msx_timer_stop(msx_stream *s, float *elapsed_ms);
+MSX_API int msx_debug_barrier_timeline(msx_stream *s, int n, long long *stamps, int mode);
+MSX_API int msx_debug_repeat_phase(msx_stream *s, int index, int n, long long *stamps);
+MSX_API int msx_debug_depformer_timeline(msx_stream *s, int32_t text_token, long long *stamps, int max_phases, int *n_phases);
 MSX_API int msx_family_count(void);
 MSX_API const char *msx_family_name(int i);
 /* KV read-back for parity tests: bf16 bits of K and V for (layer, head, slot), Dh values each */
@@ -142,6 +150,9 @@ MSX_API int msx_gen_max_delay(const msx_gen *g);
  * quantise.  All pointers are host pointers. */
 MSX_API int msx_test_gemv(int device, int type, const void *w, int64_t k, int64_t rows,
                           const float *x, const float *alpha, int prologue, float *y);
+/* GEMV micro-benchmark: back-to-back launches over n_mats rotating copies of the matrix; average us per launch */
+MSX_API int msx_bench_gemv(int device, int type, const void *w, int64_t k, int64_t rows, int n_mats, int iters,
+                           int prologue, int epilogue, float *avg_us);
 /* bit-exact dequantisation through the device embedding-gather path: out[n_rows][k] */
 MSX_API int msx_test_dequant_rows(int device, int type, const void *table, int64_t k, int64_t table_rows,
                                   const int32_t *row_ids, int n_rows, float *out);

@@ -79,6 +79,7 @@ def lib():
     L.msx_model_device_bytes.restype = C.c_int64; L.msx_model_device_bytes.argtypes = [vp]
     L.msx_model_device.argtypes = [vp]
     L.msx_stream_create.argtypes = [vp, C.c_int, C.POINTER(vp)]
+    L.msx_stream_create_ex.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp)]
     L.msx_stream_free.argtypes = [vp]
     L.msx_stream_reset.argtypes = [vp]
     L.msx_stream_offset.argtypes = [vp]
@@ -163,10 +164,10 @@ class Model:
 
 
 class Stream:
-    def __init__(self, model: Model, context: int = 0):
+    def __init__(self, model: Model, context: int = 0, persistent_depformer: bool = False):
         self.model = model
         h = C.c_void_p()
-        _check(lib().msx_stream_create(model.h, context, C.byref(h)))
+        _check(lib().msx_stream_create_ex(model.h, context, 1 if persistent_depformer else 0, C.byref(h)))
         self.h = h
 
     @property

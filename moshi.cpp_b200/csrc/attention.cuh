@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(kThreads) attn_kernel(const AttnArgs a) {
     constexpr int LPS = DH / 8;             // lanes per slot (8 dims = 16 B of bf16 each)
     constexpr int NG = kThreads / LPS;      // slots in flight per CTA iteration
     const int S = gridDim.x, c = blockIdx.x, h = blockIdx.y;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = uniform_warp_id();
     const int cap = a.cap;
     const int pos = a.pos_const >= 0 ? a.pos_const : a.ctrl->offset;
     const int slot = pos % cap;
@@ -74,6 +74,8 @@ __global__ void __launch_bounds__(kThreads) attn_kernel(const AttnArgs a) {
     float *sc_s = x_max + kAttnMaxSplit;                               // [per]
     (void)per;
 
+    griddep_launch();
+    griddep_wait();        // qkv comes from the previous kernel (PDL)
     // ---- 1. RoPE (interleaved pairs -> [re half | im half]) and the new K/V row -------------------
     const float *q = a.qkv + h * DH, *k = a.qkv + a.dim + h * DH, *v = a.qkv + 2 * a.dim + h * DH;
     if (tid < DH / 2) {

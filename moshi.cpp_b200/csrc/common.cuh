@@ -31,6 +31,14 @@ struct Ctrl {
     int32_t pad1_[3];
     unsigned long long text_key;    // arg-max keys (see argmax_key())
     unsigned long long audio_key[40];
+    // ---- persistent-kernel grid barrier (megakernel.cuh) ----
+    unsigned long long bar_counter; // monotonic arrival counter (atomics only)
+    unsigned long long pad3_[15];   // keep counter and flag on different 128-byte lines
+    unsigned long long bar_flag;    // last completed barrier target: the only word waiters poll
+    unsigned long long pad4_[15];
+    unsigned long long bar_base;    // counter value at the start of the next launch
+    int32_t error;                  // set by the barrier watchdog
+    int32_t bar_mode;               // 0 = poll the flag word, 1 = poll the counter (measurement only)
 };
 constexpr size_t kCtrlInOffset = 32;
 constexpr size_t kCtrlInBytes = 84 * 4;
@@ -78,9 +86,11 @@ enum Epilogue : int {
 struct GemvArgs {
     QLinear w;
     const float *x = nullptr;       // [K] activations (f32)
+    const double *xparts = nullptr; // alternative input: x = sum of nparts double vectors (split-KV attention partials)
+    int32_t nparts = 0, part_stride = 0;
     const float *alpha = nullptr;   // PRO_RMS: [K]
     float eps = 0.f;
-    float *norm_out = nullptr;      // PRO_RMS: CTA 0 also stores rms_norm(x)*alpha here (transformer_out)
+    float *norm_out = nullptr;      // PRO_RMS: one CTA also stores rms_norm(x)*alpha here (transformer_out)
     float *out = nullptr;
     unsigned long long *key = nullptr;  // EPI_ARGMAX
     // EPI_ADD_EMB: token = force/override >= 0 ? that : decoded key / out_tokens
@@ -88,6 +98,16 @@ struct GemvArgs {
     Ctrl *ctrl = nullptr;
     int32_t emb_step = 0;           // 0: text token (scaled embedding), k>0: audio token of step k-1 (chained)
 };
+
+// warp index broadcast from lane 0: tells the compiler the value is warp-uniform, so loops and branches on it
+// are known to be convergent (no WARPSYNC.COLLECTIVE wrappers around the shuffles inside them)
+__device__ __forceinline__ int uniform_warp_id() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization
+// attribute may start while its predecessor is still running; it must not touch the predecessor's outputs
+// (or overwrite its inputs) before griddep_wait().  griddep_launch() lets the NEXT kernel start early.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ---- small device helpers -------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {

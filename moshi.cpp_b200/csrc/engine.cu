@@ -16,6 +16,7 @@
 #include "common.cuh"
 #include "gemv.cuh"
 #include "gguf_file.h"
+#include "megakernel.cuh"
 #include "misc_kernels.cuh"
 
 using namespace msx;
@@ -352,11 +353,13 @@ namespace {
 enum Family : int {
     FAM_EMBED = 0, FAM_IN_PROJ, FAM_ATTN, FAM_OUT_PROJ, FAM_LIN_IN, FAM_LIN_OUT, FAM_TEXT_HEAD, FAM_FINALIZE,
     FAM_DEP_IN, FAM_DEP_IN_PROJ, FAM_DEP_ATTN, FAM_DEP_OUT_PROJ, FAM_DEP_LIN_IN, FAM_DEP_LIN_OUT, FAM_DEP_HEAD, FAM_DEP_FINALIZE,
+    FAM_DEP_MEGA,
     FAM_COUNT
 };
 const char *kFamilyNames[FAM_COUNT] = {
     "embed", "in_proj", "attn", "out_proj", "linear_in", "linear_out", "text_head", "finalize",
-    "dep_in", "dep_in_proj", "dep_attn", "dep_out_proj", "dep_linear_in", "dep_linear_out", "dep_head", "dep_finalize"};
+    "dep_in", "dep_in_proj", "dep_attn", "dep_out_proj", "dep_linear_in", "dep_linear_out", "dep_head", "dep_finalize",
+    "depformer_persistent"};
 
 struct Launcher {
     cudaStream_t st;
@@ -376,31 +379,35 @@ struct Launcher {
         if (events) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); events->push_back(e); families->push_back(fam); }
     }
 
-    template <int WT, int LANES>
-    void gemv_dispatch(const GemvArgs &a, int pro, int epi, int grid, int smem) {
-#define MSX_GEMV_CASE(P, E)                                                              \
-        if (pro == P && epi == E) { gemv_kernel<WT, LANES, P, E><<<grid, kThreads, smem, st>>>(a); check(); return; }
-        MSX_GEMV_CASE(PRO_RMS, EPI_STORE)
-        MSX_GEMV_CASE(PRO_RMS, EPI_GATE)
-        MSX_GEMV_CASE(PRO_RMS, EPI_ARGMAX)
-        MSX_GEMV_CASE(PRO_PLAIN, EPI_STORE)
-        MSX_GEMV_CASE(PRO_PLAIN, EPI_RESID)
-        MSX_GEMV_CASE(PRO_PLAIN, EPI_ARGMAX)
-        MSX_GEMV_CASE(PRO_PLAIN, EPI_ADD_EMB)
-#undef MSX_GEMV_CASE
-        err = cudaErrorInvalidValue;
+    // cudaLaunchKernelEx with the programmatic-stream-serialization attribute (captured into the graph as a
+    // programmatic dependency edge): the kernel may begin before its predecessor has drained
+    template <typename K, typename... Args>
+    void launch_pdl(K kernel, dim3 grid, dim3 block, size_t smem, Args... args) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, args...);
+        if (err == cudaSuccess) err = e;
     }
+    bool pdl = true;
 
     void gemv(const GemvArgs &a, int pro, int epi, int family = 0) {
         fam = family; begin();
-        const int n_tiles = (a.w.rows + kRowsPerTile - 1) / kRowsPerTile;
-        const int grid = std::max(1, std::min(2 * num_sms, (n_tiles + 1) / 2));
+        const int tr = tile_rows(a.w.gs);
+        const int n_tiles = (a.w.rows + tr - 1) / tr;
+        const int grid = std::max(1, std::min(2 * num_sms, (n_tiles + 3) / 4));
         const int smem = gemv_smem_bytes(a.w.type, a.w.K);
         if (a.w.type == T_Q4_K) {
-            if (a.w.gs == 32) gemv_dispatch<12, 32>(a, pro, epi, grid, smem); else gemv_dispatch<12, 16>(a, pro, epi, grid, smem);
+            if (a.w.gs == 32) launch_pdl(gemv_kernel<12, 32>, dim3(grid), dim3(kThreads), smem, a, pro, epi);
+            else launch_pdl(gemv_kernel<12, 16>, dim3(grid), dim3(kThreads), smem, a, pro, epi);
         } else {
-            if (a.w.gs == 32) gemv_dispatch<8, 32>(a, pro, epi, grid, smem); else gemv_dispatch<8, 16>(a, pro, epi, grid, smem);
+            if (a.w.gs == 32) launch_pdl(gemv_kernel<8, 32>, dim3(grid), dim3(kThreads), smem, a, pro, epi);
+            else launch_pdl(gemv_kernel<8, 16>, dim3(grid), dim3(kThreads), smem, a, pro, epi);
         }
+        check();
     }
 
     void attn(const AttnArgs &a, int heads, int dh, int split, int family = 0) {
@@ -409,10 +416,11 @@ struct Launcher {
         cfg.gridDim = dim3(split, heads, 1);
         cfg.blockDim = dim3(kThreads, 1, 1);
         cfg.stream = st;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = split; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        cfg.attrs = at; cfg.numAttrs = split > 1 ? 1 : 0;
+        cudaLaunchAttribute at[2];
+        int na = 0;
+        if (pdl) { at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[na].val.programmaticStreamSerializationAllowed = 1; na++; }
+        if (split > 1) { at[na].id = cudaLaunchAttributeClusterDimension; at[na].val.clusterDim.x = split; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1; na++; }
+        cfg.attrs = at; cfg.numAttrs = na;
         cudaError_t e;
         if (dh == 128) {
             cfg.dynamicSmemBytes = attn_smem_bytes<128>(a.cap, split);
@@ -445,11 +453,18 @@ struct msx_stream {
     Ctrl *ctrl = nullptr;            // device
     int32_t *h_in = nullptr;         // pinned: text_override, tokens[40], force[40], pad
     int32_t *h_out = nullptr;        // pinned: out_tokens[41]
+    int32_t *h_err = nullptr;        // pinned: Ctrl::error
     uint16_t *kc = nullptr, *vc = nullptr, *dkc = nullptr, *dvc = nullptr;
     float *x = nullptr, *qkv = nullptr, *ctx = nullptr, *gate = nullptr, *tout = nullptr, *text_logits = nullptr;
     float *dx = nullptr, *dqkv = nullptr, *dctx = nullptr, *dgate = nullptr, *audio_logits = nullptr, *vad_logits = nullptr;
     cudaGraphExec_t g_temporal = nullptr, g_depformer = nullptr;
     int launches_temporal = 0, launches_depformer = 0;
+    // persistent phase-program kernel (megakernel.cuh)
+    int flags = 0;
+    Phase *d_dep_prog = nullptr;
+    int n_dep_phases = 0;
+    int mega_smem = 0, mega_gemv_region = 0, mega_local_dim = 0;
+    bool mega_depformer = false;
     int host_offset = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<void *> allocs;
@@ -461,6 +476,7 @@ struct msx_stream {
         for (void *p : allocs) cudaFree(p);
         if (h_in) cudaFreeHost(h_in);
         if (h_out) cudaFreeHost(h_out);
+        if (h_err) cudaFreeHost(h_err);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         if (st) cudaStreamDestroy(st);
@@ -515,7 +531,7 @@ void enqueue_temporal(Launcher &L, const msx_stream *s) {
     EmbedArgs e;
     e.tables = m->d_emb; e.n_tables = c.n_q + 1; e.dim = c.dim; e.ctrl = s->ctrl; e.x = s->x;
     L.fam = FAM_EMBED; L.begin();
-    embed_kernel<<<(c.dim + kThreads - 1) / kThreads, kThreads, 0, L.st>>>(e);
+    L.launch_pdl(embed_kernel, dim3((c.dim + kThreads - 1) / kThreads), dim3(kThreads), 0, e);
     L.check();
     for (int l = 0; l < c.num_layers; l++) enqueue_layer(L, s, m->layers[l], 0, true, l, -1);
     // out_norm -> transformer_out (kept for depformer / VAD) -> text_linear -> greedy token (lm.h:671-674, 864-868)
@@ -525,7 +541,7 @@ void enqueue_temporal(Launcher &L, const msx_stream *s) {
     g.key = &s->ctrl->text_key;
     L.gemv(g, PRO_RMS, EPI_ARGMAX, FAM_TEXT_HEAD);
     L.fam = FAM_FINALIZE;
-    finalize_temporal_kernel<<<1, 32, 0, L.st>>>(s->ctrl, c.dep_q > 0 ? 1 : 0);
+    L.launch_pdl(finalize_temporal_kernel, dim3(1), dim3(32), 0, s->ctrl, c.dep_q > 0 ? 1 : 0);
     L.check();
 }
 
@@ -549,7 +565,75 @@ void enqueue_depformer(Launcher &L, const msx_stream *s) {
         L.gemv(h, PRO_PLAIN, EPI_ARGMAX, FAM_DEP_HEAD);
     }
     L.fam = FAM_DEP_FINALIZE;
-    finalize_depformer_kernel<<<1, 64, 0, L.st>>>(s->ctrl, c.dep_q);
+    L.launch_pdl(finalize_depformer_kernel, dim3(1), dim3(64), 0, s->ctrl, (int)c.dep_q);
+    L.check();
+}
+
+// ---- persistent-kernel program for the depformer chain -------------------------------------------------
+// dep_q x (depformer_in+emb | per layer: in_proj | local attention + out_proj | linear_in+gate | linear_out) | head),
+// then the token collection: 26 phases per codebook step instead of 32 launches.
+std::vector<Phase> build_depformer_program(const msx_stream *s, int *max_gemv_smem) {
+    const msx_model *m = s->m; const msx_config &c = m->cfg;
+    std::vector<Phase> prog;
+    int mx = 0;
+    auto gemv = [&](const GemvArgs &g, int pro, int epi) {
+        Phase ph; ph.type = PH_GEMV; ph.pro = pro; ph.epi = epi; ph.g = g;
+        mx = std::max(mx, gemv_smem_bytes(g.w.type, g.w.K));
+        prog.push_back(ph);
+    };
+    const int dd = c.dep_dim;
+    for (int k = 0; k < c.dep_q; k++) {
+        const int wsel = c.schedule_len ? c.schedule[k] : k;
+        const int w = m->dep_nw == 1 ? 0 : wsel;
+        GemvArgs g;
+        g.ctrl = s->ctrl; g.eps = 1e-8f;
+        g.w = m->dep_in[w]; g.x = s->tout; g.out = s->dx;
+        g.emb = k == 0 ? m->dep_text_emb : m->dep_emb[k - 1];
+        g.emb_step = k;
+        gemv(g, PRO_PLAIN, EPI_ADD_EMB);
+        for (int l = 0; l < c.dep_layers; l++) {
+            const LayerW &lw = m->dep_layers[l];
+            GemvArgs a1;
+            a1.ctrl = s->ctrl; a1.eps = 1e-8f;
+            a1.w = lw.in_proj[w]; a1.x = s->dx; a1.alpha = lw.norm1; a1.out = s->dqkv;
+            gemv(a1, PRO_RMS, EPI_STORE);
+            Phase ph;
+            ph.type = PH_GEMV_LOCAL_ATTN; ph.pro = PRO_PLAIN; ph.epi = EPI_RESID;
+            ph.heads = c.dep_heads; ph.dh = dd / c.dep_heads;
+            ph.a.qkv = s->dqkv; ph.a.ctx = nullptr; ph.a.ctrl = s->ctrl; ph.a.pos_const = k; ph.a.cap = m->dep_cap; ph.a.dim = dd;
+            ph.a.max_period = c.dep_max_period; ph.a.rope_freq = m->dep_rope_freq;
+            const size_t lstride = (size_t)m->dep_cap * dd;
+            ph.a.kc = s->dkc + (size_t)l * lstride; ph.a.vc = s->dvc + (size_t)l * lstride;
+            ph.g.ctrl = s->ctrl; ph.g.w = lw.out_proj[w]; ph.g.x = nullptr; ph.g.out = s->dx;
+            mx = std::max(mx, gemv_smem_bytes(ph.g.w.type, ph.g.w.K));
+            prog.push_back(ph);
+            GemvArgs a3;
+            a3.ctrl = s->ctrl; a3.eps = 1e-8f;
+            a3.w = lw.lin_in[w]; a3.x = s->dx; a3.alpha = lw.norm2; a3.out = s->dgate;
+            gemv(a3, PRO_RMS, EPI_GATE);
+            GemvArgs a4;
+            a4.ctrl = s->ctrl;
+            a4.w = lw.lin_out[w]; a4.x = s->dgate; a4.out = s->dx;
+            gemv(a4, PRO_PLAIN, EPI_RESID);
+        }
+        GemvArgs h;
+        h.ctrl = s->ctrl;
+        h.w = m->linears[k]; h.x = s->dx; h.out = s->audio_logits + (size_t)k * c.card; h.key = &s->ctrl->audio_key[k];
+        gemv(h, PRO_PLAIN, EPI_ARGMAX);
+    }
+    Phase fin; fin.type = PH_FINALIZE_DEPFORMER; fin.dep_q = c.dep_q;
+    prog.push_back(fin);
+    *max_gemv_smem = mx;
+    return prog;
+}
+
+void enqueue_depformer_mega(Launcher &L, const msx_stream *s) {
+    MegaArgs ma; ma.phases = s->d_dep_prog; ma.n_phases = s->n_dep_phases; ma.ctrl = s->ctrl;
+    int region = s->mega_gemv_region, ldim = s->mega_local_dim;
+    void *args[] = {(void *)&ma, (void *)&region, (void *)&ldim};
+    L.fam = FAM_DEP_MEGA; L.begin();
+    cudaError_t e = cudaLaunchCooperativeKernel((const void *)mega_kernel, dim3(s->m->num_sms), dim3(kMegaThreads), args, (size_t)s->mega_smem, L.st);
+    if (L.err == cudaSuccess) L.err = e;
     L.check();
 }
 
@@ -581,12 +665,16 @@ int set_smem_attrs() {
 }  // namespace
 
 extern "C" int msx_stream_create(msx_model *m, int context_override, msx_stream **out) {
+    return msx_stream_create_ex(m, context_override, 0, out);
+}
+
+extern "C" int msx_stream_create_ex(msx_model *m, int context_override, int flags, msx_stream **out) {
     if (!m || !out) return fail(MSX_ERR_ARG, "null argument");
     *out = nullptr;
     CU(cudaSetDevice(m->device));
     if (int e = set_smem_attrs()) return e;
     std::unique_ptr<msx_stream> s(new msx_stream);
-    s->m = m;
+    s->m = m; s->flags = flags;
     const msx_config &c = m->cfg;
     s->cap = context_override > 0 ? std::min(context_override, c.context) : c.context;
     s->attn_split = attn_split_for(c.num_heads, s->cap, m->num_sms);
@@ -594,6 +682,8 @@ extern "C" int msx_stream_create(msx_model *m, int context_override, msx_stream 
     CU(cudaEventCreate(&s->ev0)); CU(cudaEventCreate(&s->ev1));
     CU(cudaMallocHost((void **)&s->h_in, kCtrlInBytes));
     CU(cudaMallocHost((void **)&s->h_out, kCtrlOutBytes));
+    CU(cudaMallocHost((void **)&s->h_err, 4));
+    *s->h_err = 0;
     if (int e = salloc(s.get(), (void **)&s->ctrl, sizeof(Ctrl))) return e;
     if (int e = salloc(s.get(), (void **)&s->kc, kv_elems(s.get()) * 2)) return e;
     if (int e = salloc(s.get(), (void **)&s->vc, kv_elems(s.get()) * 2)) return e;
@@ -623,8 +713,31 @@ extern "C" int msx_stream_create(msx_model *m, int context_override, msx_stream 
     CU(cudaMemcpy(s->ctrl, &hc, sizeof(hc), cudaMemcpyHostToDevice));
 
     if (int e = capture(s.get(), [&](Launcher &L) { enqueue_temporal(L, s.get()); }, &s->g_temporal, &s->launches_temporal)) return e;
-    if (c.dep_q > 0)
-        if (int e = capture(s.get(), [&](Launcher &L) { enqueue_depformer(L, s.get()); }, &s->g_depformer, &s->launches_depformer)) return e;
+    if (c.dep_q > 0) {
+        // persistent phase-program kernel for the depformer chain: opt-in (measured slower than PDL-chained launches on B200)
+        const bool want_mega = (flags & MSX_STREAM_PERSISTENT_DEPFORMER) && m->dep_cap <= 64;
+        if (want_mega) {
+            int mx = 0;
+            std::vector<Phase> prog = build_depformer_program(s.get(), &mx);
+            s->mega_gemv_region = (mx + 15) / 16 * 16;
+            s->mega_local_dim = c.dep_dim;
+            s->mega_smem = mega_smem_bytes(mx, c.dep_dim, c.dep_dim / c.dep_heads);
+            CU(cudaFuncSetAttribute(mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(s->mega_smem, 48 * 1024)));
+            int per_sm = 0;
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mega_kernel, kMegaThreads, s->mega_smem));
+            if (per_sm >= 1) {
+                if (int e = salloc(s.get(), (void **)&s->d_dep_prog, prog.size() * sizeof(Phase))) return e;
+                CU(cudaMemcpy(s->d_dep_prog, prog.data(), prog.size() * sizeof(Phase), cudaMemcpyHostToDevice));
+                s->n_dep_phases = (int)prog.size();
+                s->mega_depformer = true;
+            }
+        }
+        if (s->mega_depformer) {
+            if (int e = capture(s.get(), [&](Launcher &L) { enqueue_depformer_mega(L, s.get()); }, &s->g_depformer, &s->launches_depformer)) return e;
+        } else {
+            if (int e = capture(s.get(), [&](Launcher &L) { enqueue_depformer(L, s.get()); }, &s->g_depformer, &s->launches_depformer)) return e;
+        }
+    }
     CU(cudaStreamSynchronize(s->st));
     *out = s.release();
     return 0;
@@ -668,7 +781,9 @@ int push_inputs(msx_stream *s, const int32_t *tokens, int32_t text_override, con
 
 int pull_outputs(msx_stream *s) {
     CU(cudaMemcpyAsync(s->h_out, reinterpret_cast<uint8_t *>(s->ctrl) + kCtrlOutOffset, kCtrlOutBytes, cudaMemcpyDeviceToHost, s->st));
+    CU(cudaMemcpyAsync(s->h_err, &s->ctrl->error, 4, cudaMemcpyDeviceToHost, s->st));
     CU(cudaStreamSynchronize(s->st));
+    if (*s->h_err) return fail(MSX_ERR_CUDA, "persistent kernel: grid barrier watchdog fired (device-side timeout)");
     return 0;
 }
 
@@ -785,7 +900,7 @@ extern "C" int msx_profile_frame(msx_stream *s, const int32_t *tokens, int32_t *
     L.events = &ev; L.families = &fam;
     enqueue_temporal(L, s);
     s->host_offset++;
-    if (c.dep_q > 0) enqueue_depformer(L, s);
+    if (c.dep_q > 0) { if (s->mega_depformer) enqueue_depformer_mega(L, s); else enqueue_depformer(L, s); }
     if (L.err != cudaSuccess) return fail(MSX_ERR_CUDA, std::string("launch failed: ") + cudaGetErrorString(L.err));
     if (int e = pull_outputs(s)) return e;
     if (out_tokens) for (int k = 0; k < 1 + c.dep_q; k++) out_tokens[k] = s->h_out[k];
@@ -798,6 +913,75 @@ extern "C" int msx_profile_frame(msx_stream *s, const int32_t *tokens, int32_t *
     for (cudaEvent_t e : ev) cudaEventDestroy(e);
     return 0;
 }
+// debug: pure grid-barrier cost — a program of n empty phases, timeline as below
+extern "C" int msx_debug_barrier_timeline(msx_stream *s, int n, long long *stamps, int mode) {
+    if (!s || !stamps || n < 2) return fail(MSX_ERR_ARG, "bad argument");
+    CU(cudaSetDevice(s->m->device));
+    CU(cudaMemcpy(&s->ctrl->bar_mode, &mode, 4, cudaMemcpyHostToDevice));
+    std::vector<Phase> prog(n);
+    for (auto &ph : prog) ph.type = 99;
+    Phase *dp = nullptr; long long *d = nullptr;
+    CU(cudaMalloc((void **)&dp, n * sizeof(Phase)));
+    CU(cudaMemcpy(dp, prog.data(), n * sizeof(Phase), cudaMemcpyHostToDevice));
+    CU(cudaMalloc((void **)&d, (size_t)n * 8 * 8));
+    CU(cudaMemset(d, 0, (size_t)n * 8 * 8));
+    MegaArgs ma; ma.phases = dp; ma.n_phases = n; ma.ctrl = s->ctrl; ma.dbg = d;
+    int region = s->mega_gemv_region, ldim = s->mega_local_dim;
+    void *args[] = {(void *)&ma, (void *)&region, (void *)&ldim};
+    for (int rep = 0; rep < 2; rep++)
+        CU(cudaLaunchCooperativeKernel((const void *)mega_kernel, dim3(s->m->num_sms), dim3(kMegaThreads), args, (size_t)s->mega_smem, s->st));
+    CU(cudaStreamSynchronize(s->st));
+    CU(cudaMemcpy(stamps, d, (size_t)n * 8 * 8, cudaMemcpyDeviceToHost));
+    cudaFree(d); cudaFree(dp);
+    mode = 0;
+    CU(cudaMemcpy(&s->ctrl->bar_mode, &mode, 4, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+// debug: a program made of n copies of phase `index` of the depformer program (steady-state cost of one phase type)
+extern "C" int msx_debug_repeat_phase(msx_stream *s, int index, int n, long long *stamps) {
+    if (!s || !stamps || n < 2 || !s->mega_depformer || index < 0 || index >= s->n_dep_phases) return fail(MSX_ERR_ARG, "bad argument");
+    CU(cudaSetDevice(s->m->device));
+    Phase one;
+    CU(cudaMemcpy(&one, s->d_dep_prog + index, sizeof(Phase), cudaMemcpyDeviceToHost));
+    std::vector<Phase> prog(n, one);
+    Phase *dp = nullptr; long long *d = nullptr;
+    CU(cudaMalloc((void **)&dp, n * sizeof(Phase)));
+    CU(cudaMemcpy(dp, prog.data(), n * sizeof(Phase), cudaMemcpyHostToDevice));
+    CU(cudaMalloc((void **)&d, (size_t)n * 8 * 8));
+    CU(cudaMemset(d, 0, (size_t)n * 8 * 8));
+    MegaArgs ma; ma.phases = dp; ma.n_phases = n; ma.ctrl = s->ctrl; ma.dbg = d;
+    int region = s->mega_gemv_region, ldim = s->mega_local_dim;
+    void *args[] = {(void *)&ma, (void *)&region, (void *)&ldim};
+    for (int rep = 0; rep < 2; rep++)
+        CU(cudaLaunchCooperativeKernel((const void *)mega_kernel, dim3(s->m->num_sms), dim3(kMegaThreads), args, (size_t)s->mega_smem, s->st));
+    CU(cudaStreamSynchronize(s->st));
+    CU(cudaMemcpy(stamps, d, (size_t)n * 8 * 8, cudaMemcpyDeviceToHost));
+    cudaFree(d); cudaFree(dp);
+    return 0;
+}
+
+// debug: run the persistent depformer kernel once with the in-kernel timeline enabled (5 stamps per phase, ns)
+extern "C" int msx_debug_depformer_timeline(msx_stream *s, int32_t text_token, long long *stamps, int max_phases, int *n_phases) {
+    if (!s || !stamps || !n_phases) return fail(MSX_ERR_ARG, "null argument");
+    if (!s->mega_depformer) return fail(MSX_ERR_STATE, "stream does not use the persistent depformer kernel");
+    CU(cudaSetDevice(s->m->device));
+    const int n = std::min(max_phases, s->n_dep_phases);
+    long long *d = nullptr;
+    CU(cudaMalloc((void **)&d, (size_t)s->n_dep_phases * 8 * 8));
+    CU(cudaMemset(d, 0, (size_t)s->n_dep_phases * 8 * 8));
+    if (int e = push_inputs(s, nullptr, text_token, nullptr)) return e;
+    MegaArgs ma; ma.phases = s->d_dep_prog; ma.n_phases = s->n_dep_phases; ma.ctrl = s->ctrl; ma.dbg = d;
+    int region = s->mega_gemv_region, ldim = s->mega_local_dim;
+    void *args[] = {(void *)&ma, (void *)&region, (void *)&ldim};
+    CU(cudaLaunchCooperativeKernel((const void *)mega_kernel, dim3(s->m->num_sms), dim3(kMegaThreads), args, (size_t)s->mega_smem, s->st));
+    if (int e = pull_outputs(s)) return e;
+    CU(cudaMemcpy(stamps, d, (size_t)n * 8 * 8, cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    *n_phases = n;
+    return 0;
+}
+
 extern "C" int msx_family_count(void) { return FAM_COUNT; }
 extern "C" const char *msx_family_name(int i) { return (i >= 0 && i < FAM_COUNT) ? kFamilyNames[i] : ""; }
 
@@ -977,6 +1161,58 @@ extern "C" int msx_test_gemv(int device, int type, const void *w, int64_t k, int
     if (L.err != cudaSuccess) return fail(MSX_ERR_CUDA, std::string("gemv launch: ") + cudaGetErrorString(L.err));
     CU(cudaDeviceSynchronize());
     CU(cudaMemcpy(y, dy, (size_t)rows * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// Micro-benchmark of the fused GEMV kernel: n_mats copies of one random [rows][k] matrix (rotated so every
+// launch streams cold weights from HBM when n_mats * bytes > L2), iters launches timed with CUDA events.
+extern "C" int msx_bench_gemv(int device, int type, const void *w, int64_t k, int64_t rows, int n_mats, int iters,
+                              int prologue, int epilogue, float *avg_us) {
+    if (!w || !avg_us || n_mats < 1 || iters < 1) return fail(MSX_ERR_ARG, "bad argument");
+    std::unique_ptr<msx_model> m;
+    if (int e = test_setup(device, m)) return e;
+    std::vector<QLinear> mats(n_mats);
+    for (int i = 0; i < n_mats; i++)
+        if (int e = upload_linear(m.get(), w, type, k, rows, epilogue == EPI_GATE ? (int)(rows / 2) : 0, &mats[i])) return e;
+    float *dx = nullptr, *dy = nullptr, *da = nullptr;
+    if (int e = dev_alloc(m.get(), (void **)&dx, (size_t)k * 4)) return e;
+    if (int e = dev_alloc(m.get(), (void **)&dy, (size_t)std::max<int64_t>(rows, k) * 4)) return e;
+    if (int e = dev_alloc(m.get(), (void **)&da, (size_t)k * 4)) return e;
+    std::vector<float> hx(k), ha(k, 1.0f);
+    for (int64_t i = 0; i < k; i++) hx[i] = (float)((i * 2654435761u) % 2001) / 1000.f - 1.f;
+    CU(cudaMemcpy(dx, hx.data(), (size_t)k * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(da, ha.data(), (size_t)k * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemset(dy, 0, (size_t)std::max<int64_t>(rows, k) * 4));
+    cudaStream_t st;
+    CU(cudaStreamCreate(&st));
+    Launcher L{st, m->num_sms};
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    unsigned long long *dkey = nullptr;
+    if (int e = dev_alloc(m.get(), (void **)&dkey, 8)) return e;
+    CU(cudaMemset(dkey, 0, 8));
+    // like the real step: the launches are captured into a CUDA graph and replayed
+    cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
+    CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    for (int i = 0; i < iters; i++) {
+        GemvArgs g;
+        g.w = mats[i % n_mats]; g.x = dx; g.alpha = da; g.eps = 1e-8f; g.out = dy; g.key = dkey;
+        L.gemv(g, prologue, epilogue);
+    }
+    CU(cudaStreamEndCapture(st, &graph));
+    if (L.err != cudaSuccess) return fail(MSX_ERR_CUDA, std::string("gemv launch: ") + cudaGetErrorString(L.err));
+    CU(cudaGraphInstantiate(&exec, graph, 0));
+    CU(cudaGraphLaunch(exec, st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaEventRecord(e0, st));
+    CU(cudaGraphLaunch(exec, st));
+    CU(cudaEventRecord(e1, st));
+    CU(cudaStreamSynchronize(st));
+    cudaGraphExecDestroy(exec); cudaGraphDestroy(graph);
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    *avg_us = ms * 1000.f / iters;
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaStreamDestroy(st);
     return 0;
 }
 

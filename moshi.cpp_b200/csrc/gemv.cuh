@@ -27,144 +27,204 @@ __device__ __forceinline__ int dp4a_us(unsigned a, int b, int c) {
     return d;
 }
 
-constexpr int kRowsPerTile = 4;   // rows a warp retires per iteration
+
+// The GEMV body runs either as a whole CTA (standalone kernels, 256 threads) or as the consumer part
+// of the persistent kernel's CTA (480 of 512 threads): geometry comes in at run time and block-level
+// synchronisation uses named barrier 1 over exactly the participating threads.
+struct BlockGeom { int nthr; int nwarps; long long *stamp = nullptr; };
+__device__ __forceinline__ long long global_ns() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ void block_sync(const BlockGeom &bg) { asm volatile("bar.sync 1, %0;" ::"r"(bg.nthr) : "memory"); }
+
+// Activation vectors are produced by other CTAs (previous kernel, or previous phase of the persistent
+// kernel): read them through L2 (ld.global.cg) so a stale L1 line can never be observed.  Generic
+// addresses that point into shared memory (fused attention output) take the plain path.
+__device__ __forceinline__ float4 ld_act4(const float *p) {
+    if (__isShared(p)) return *reinterpret_cast<const float4 *>(p);
+    return __ldcg(reinterpret_cast<const float4 *>(p));
+}
 
 __host__ __device__ inline int gemv_smem_bytes(int type, int K) {
     // Q4_K: x8[K] + bsums int2[K/64] + dx float[K/256];  Q8_0: x8[K] + dx float[K/32]
     int b = (type == 12) ? K + (K / 64) * 8 + (K / 256) * 4 : K + (K / 32) * 4;
-    return (b + 15) / 16 * 16 + 64;   // + block-reduce scratch
+    return (b + 15) / 16 * 16 + 128;  // + block-reduce scratch (16 doubles)
 }
 
 // ---- prologue: (optional RMSNorm) + activation quantisation into shared memory -------------------
-// Σx² is accumulated in double like ggml_compute_forward_rms_norm_f32 (ggml_float), so the fp32
-// `scale` is bit-identical to the CPU path in all but pathological cases.
-template <int PRO>
-__device__ __forceinline__ float rms_scale(const GemvArgs &a, int K, double *red) {
-    if (PRO != PRO_RMS) return 1.f;
-    double ss = 0.0;
-    for (int i = threadIdx.x * 4; i < K; i += kThreads * 4) {
-        float4 v = *reinterpret_cast<const float4 *>(a.x + i);
-        ss += (double)(v.x * v.x); ss += (double)(v.y * v.y); ss += (double)(v.z * v.z); ss += (double)(v.w * v.w);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
-    __syncthreads();
-    double tot = 0.0;
-#pragma unroll
-    for (int w = 0; w < kWarps; w++) tot += red[w];
-    const float mean = (float)(tot / K);
-    return 1.0f / sqrtf(mean + a.eps);
-}
+// One pass over x: every warp owns 256-element blocks (lane = 8 consecutive elements) and keeps up to
+// kKeep of them in registers between the sum-of-squares reduction and the quantisation, so the activation
+// vector is read from L2 exactly once (one dependent round trip instead of two).
+// Σx² is accumulated in double like ggml_compute_forward_rms_norm_f32 (ggml_float).
 
-template <int PRO>
-__device__ __forceinline__ void load8(const GemvArgs &a, int e0, float scale, float (&v)[8]) {
-    float4 p0 = *reinterpret_cast<const float4 *>(a.x + e0);
-    float4 p1 = *reinterpret_cast<const float4 *>(a.x + e0 + 4);
+// 8 consecutive activations starting at e0: plain f32 vector, or the sum of `nparts` double partial vectors
+// (attention context written by the split-KV phase of the persistent kernel)
+__device__ __forceinline__ void load_x8(const GemvArgs &a, const float *xin, int e0, float (&v)[8]) {
+    if (a.xparts) {
+        double s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int c = 0; c < a.nparts; c++) {
+            const double2 *p = reinterpret_cast<const double2 *>(a.xparts + (size_t)c * a.part_stride + e0);
+#pragma unroll
+            for (int i = 0; i < 4; i++) { const double2 t = __ldcg(p + i); s[2 * i] += t.x; s[2 * i + 1] += t.y; }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[i] = (float)s[i];
+        return;
+    }
+    const float4 p0 = ld_act4(xin + e0), p1 = ld_act4(xin + e0 + 4);
     v[0] = p0.x; v[1] = p0.y; v[2] = p0.z; v[3] = p0.w; v[4] = p1.x; v[5] = p1.y; v[6] = p1.z; v[7] = p1.w;
-    if (PRO == PRO_RMS) {
-        float4 a0 = *reinterpret_cast<const float4 *>(a.alpha + e0);
-        float4 a1 = *reinterpret_cast<const float4 *>(a.alpha + e0 + 4);
-        const float al[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-#pragma unroll
-        for (int i = 0; i < 8; i++) v[i] = __fmul_rn(al[i], __fmul_rn(v[i], scale));   // alpha * (x * scale)
-    }
+}
+__device__ __forceinline__ void load_alpha8(const GemvArgs &a, int e0, float (&al)[8]) {
+    const float4 a0 = *reinterpret_cast<const float4 *>(a.alpha + e0), a1 = *reinterpret_cast<const float4 *>(a.alpha + e0 + 4);
+    al[0] = a0.x; al[1] = a0.y; al[2] = a0.z; al[3] = a0.w; al[4] = a1.x; al[5] = a1.y; al[6] = a1.z; al[7] = a1.w;
+}
+__device__ __forceinline__ uint2 pack8(const int (&q)[8]) {
+    uint2 pk;
+    pk.x = (uint32_t)(q[0] & 0xff) | ((uint32_t)(q[1] & 0xff) << 8) | ((uint32_t)(q[2] & 0xff) << 16) | ((uint32_t)(q[3] & 0xff) << 24);
+    pk.y = (uint32_t)(q[4] & 0xff) | ((uint32_t)(q[5] & 0xff) << 8) | ((uint32_t)(q[6] & 0xff) << 16) | ((uint32_t)(q[7] & 0xff) << 24);
+    return pk;
 }
 
-// quantize_row_q8_K: per 256 block, max-|x| carrier, iscale = -127/max, q = min(127, rne(iscale*x)), d = 1/iscale
-template <int PRO>
-__device__ __forceinline__ void quantize_act_q8k(const GemvArgs &a, int K, int8_t *x8, int *bs, float *dx, double *red) {
-    const float scale = rms_scale<PRO>(a, K, red);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int P = K >> 6;
-    for (int b = warp; b < (K >> 8); b += kWarps) {
-        const int e0 = b * 256 + lane * 8;
-        float v[8];
-        load8<PRO>(a, e0, scale, v);
-        if (PRO == PRO_RMS && a.norm_out && blockIdx.x == 0) {
-            *reinterpret_cast<float4 *>(a.norm_out + e0) = make_float4(v[0], v[1], v[2], v[3]);
-            *reinterpret_cast<float4 *>(a.norm_out + e0 + 4) = make_float4(v[4], v[5], v[6], v[7]);
-        }
-        float amax = 0.f, mx = 0.f;
+// quantize_row_q8_K for block b (all 32 lanes participate): max-|x| carrier, iscale = -127/max,
+// q = min(127, rne(iscale*x)), d = 1/iscale; 32-wide sub-block sums for the dmin term
+__device__ __forceinline__ void quantize_block_q8k(int b, int lane, const float (&v)[8], int P, int8_t *x8, int *bs, float *dx) {
+    float amax = 0.f, mx = 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; i++) { float ax = fabsf(v[i]); if (ax > amax) { amax = ax; mx = v[i]; } }
-        const float wmax = warp_max(amax);
-        // carrier = first element (lowest index) attaining the maximum magnitude
-        const unsigned hit = __ballot_sync(0xffffffffu, amax == wmax);
-        const float carrier = __shfl_sync(0xffffffffu, mx, __ffs(hit) - 1);
+    for (int i = 0; i < 8; i++) { float ax = fabsf(v[i]); if (ax > amax) { amax = ax; mx = v[i]; } }
+    const float wmax = warp_max(amax);
+    const unsigned hit = __ballot_sync(0xffffffffu, amax == wmax);          // carrier = first element attaining the max
+    const float carrier = __shfl_sync(0xffffffffu, mx, __ffs(hit) - 1);
+    int q[8];
+    float d = 0.f;
+    if (wmax == 0.f) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) q[i] = 0;
+    } else {
+        const float iscale = -127.f / carrier;
+#pragma unroll
+        for (int i = 0; i < 8; i++) { int t = __float2int_rn(iscale * v[i]); q[i] = t < 127 ? t : 127; }
+        d = 1.f / iscale;
+    }
+    int s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s += q[i];
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    if ((lane & 3) == 0) bs[b * 8 + (lane >> 2)] = s;
+    if (lane == 0) dx[b] = d;
+    // piece-major store: pair p = 4b + lane/8, piece = (lane%8)/2, 8 bytes at (lane&1)*8
+    const int p = 4 * b + (lane >> 3), piece = (lane & 7) >> 1;
+    *reinterpret_cast<uint2 *>(x8 + ((size_t)piece * P + p) * 16 + (lane & 1) * 8) = pack8(q);
+}
+
+// quantize_row_q8_0 for the 8 blocks of 32 inside 256-block b: d = amax/127, q = roundf(x/d), d kept as fp16
+__device__ __forceinline__ void quantize_block_q8_0(int b, int lane, const float (&v)[8], bool act, int P, int8_t *x8, float *dx) {
+    float amax = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; i++) amax = fmaxf(amax, fabsf(v[i]));
+    amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+    amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
+    const float d = amax / 127.f;
+    const float id = d ? 1.0f / d : 0.0f;
+    if (act) {
         int q[8];
-        float d = 0.f;
-        if (wmax == 0.f) {
 #pragma unroll
-            for (int i = 0; i < 8; i++) q[i] = 0;
-        } else {
-            const float iscale = -127.f / carrier;
-#pragma unroll
-            for (int i = 0; i < 8; i++) { int t = __float2int_rn(iscale * v[i]); q[i] = t < 127 ? t : 127; }
-            d = 1.f / iscale;
-        }
-        int s = 0;
-#pragma unroll
-        for (int i = 0; i < 8; i++) s += q[i];
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        s += __shfl_xor_sync(0xffffffffu, s, 2);
-        if ((lane & 3) == 0) bs[b * 8 + (lane >> 2)] = s;     // sum over one 32-wide sub-block
-        if (lane == 0) dx[b] = d;
-        // piece-major store: pair p = 4b + lane/8, piece = (lane%8)/2, 8 bytes at (lane&1)*8
-        const int p = 4 * b + (lane >> 3), piece = (lane & 7) >> 1;
-        uint2 pk;
-        pk.x = (uint32_t)(q[0] & 0xff) | ((uint32_t)(q[1] & 0xff) << 8) | ((uint32_t)(q[2] & 0xff) << 16) | ((uint32_t)(q[3] & 0xff) << 24);
-        pk.y = (uint32_t)(q[4] & 0xff) | ((uint32_t)(q[5] & 0xff) << 8) | ((uint32_t)(q[6] & 0xff) << 16) | ((uint32_t)(q[7] & 0xff) << 24);
-        *reinterpret_cast<uint2 *>(x8 + ((size_t)piece * P + p) * 16 + (lane & 1) * 8) = pk;
+        for (int i = 0; i < 8; i++) q[i] = (int)roundf(v[i] * id);
+        const int blk = b * 8 + (lane >> 2), piece = (lane & 3) >> 1;
+        if ((lane & 3) == 0) dx[blk] = __half2float(__float2half_rn(d));
+        *reinterpret_cast<uint2 *>(x8 + ((size_t)piece * P + blk) * 16 + (lane & 1) * 8) = pack8(q);
     }
 }
 
-// quantize_row_q8_0: per 32 block, d = amax/127, q = roundf(x/d), d kept as fp16
-template <int PRO>
-__device__ __forceinline__ void quantize_act_q8_0(const GemvArgs &a, int K, int8_t *x8, float *dx, double *red) {
-    const float scale = rms_scale<PRO>(a, K, red);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int P = K >> 5;
-    for (int b = warp; b < ((K + 255) >> 8); b += kWarps) {
-        const int e0 = b * 256 + lane * 8;
-        const bool act = e0 < K;                       // K % 32 == 0: groups of 4 lanes are uniform
-        float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        if (act) load8<PRO>(a, e0, scale, v);
-        if (PRO == PRO_RMS && a.norm_out && blockIdx.x == 0 && act) {
-            *reinterpret_cast<float4 *>(a.norm_out + e0) = make_float4(v[0], v[1], v[2], v[3]);
-            *reinterpret_cast<float4 *>(a.norm_out + e0 + 4) = make_float4(v[4], v[5], v[6], v[7]);
+// Latency structure (measured on B200: one L2 round trip for activations written by other SMs costs ~0.7 us):
+// every warp owns the 256-element blocks b = warp, warp + nwarps, ...; they are processed in chunks of kChunk
+// blocks whose loads are ALL issued before the first use, so a chunk costs one round trip.  With RMSNorm,
+// if the warp's blocks fit in one chunk (the common case) x and alpha stay in registers between the
+// sum-of-squares pass and the quantisation pass: the activation vector is read exactly once.
+constexpr int kChunk = 3;
+
+template <int WT>
+__device__ __forceinline__ void gemv_prologue(const GemvArgs &a, const float *xin, const bool norm_out_cta, const int PRO, int K, int8_t *x8,
+                                              int *bs, float *dx, double *red, const BlockGeom &bg) {
+    const int lane = threadIdx.x & 31, warp = uniform_warp_id();
+    const int nblk = (K + 255) >> 8;
+    const int P = WT == 12 ? (K >> 6) : (K >> 5);
+    const int nb_w = warp < nblk ? (nblk - warp + bg.nwarps - 1) / bg.nwarps : 0;    // blocks owned by this warp
+    const bool keep = nb_w <= kChunk;
+    float v[kChunk][8], al[kChunk][8];
+    float scale = 1.f;
+    auto e0_of = [&](int i) { return (warp + i * bg.nwarps) * 256 + lane * 8; };
+    if (PRO == PRO_RMS) {
+        double ss = 0.0;
+#pragma unroll 1
+        for (int c0 = 0; c0 < nb_w; c0 += kChunk) {
+#pragma unroll
+            for (int j = 0; j < kChunk; j++) {
+                const int e0 = e0_of(c0 + j);
+                if (c0 + j < nb_w && e0 < K) { load_x8(a, xin, e0, v[j]); if (keep) load_alpha8(a, e0, al[j]); }
+                else {
+#pragma unroll
+                    for (int i = 0; i < 8; i++) v[j][i] = 0.f;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < kChunk; j++)
+#pragma unroll
+                for (int i = 0; i < 8; i++) ss += (double)(v[j][i] * v[j][i]);
         }
-        float amax = 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; i++) amax = fmaxf(amax, fabsf(v[i]));
-        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
-        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
-        const float d = amax / 127.f;
-        const float id = d ? 1.0f / d : 0.0f;
-        if (act) {
-            int q[8];
+        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        if (lane == 0) red[warp] = ss;
+        block_sync(bg);
+        double tot = 0.0;
+#pragma unroll 1
+        for (int w = 0; w < bg.nwarps; w++) tot += red[w];
+        // sum / K like ggml; for power-of-two K scaling by 2^-log2(K) is the same number
+        const float mean = (K & (K - 1)) == 0 ? (float)scalbn(tot, -(31 - __clz(K))) : (float)(tot / K);
+        scale = 1.0f / sqrtf(mean + a.eps);
+    }
+#pragma unroll 1
+    for (int c0 = 0; c0 < nb_w; c0 += kChunk) {
+        if (!(PRO == PRO_RMS && keep)) {
 #pragma unroll
-            for (int i = 0; i < 8; i++) q[i] = (int)roundf(v[i] * id);
-            const int blk = b * 8 + (lane >> 2), piece = (lane & 3) >> 1;
-            if ((lane & 3) == 0) dx[blk] = __half2float(__float2half_rn(d));
-            uint2 pk;
-            pk.x = (uint32_t)(q[0] & 0xff) | ((uint32_t)(q[1] & 0xff) << 8) | ((uint32_t)(q[2] & 0xff) << 16) | ((uint32_t)(q[3] & 0xff) << 24);
-            pk.y = (uint32_t)(q[4] & 0xff) | ((uint32_t)(q[5] & 0xff) << 8) | ((uint32_t)(q[6] & 0xff) << 16) | ((uint32_t)(q[7] & 0xff) << 24);
-            *reinterpret_cast<uint2 *>(x8 + ((size_t)piece * P + blk) * 16 + (lane & 1) * 8) = pk;
+            for (int j = 0; j < kChunk; j++) {
+                const int e0 = e0_of(c0 + j);
+                if (c0 + j < nb_w && e0 < K) { load_x8(a, xin, e0, v[j]); if (PRO == PRO_RMS) load_alpha8(a, e0, al[j]); }
+                else {
+#pragma unroll
+                    for (int i = 0; i < 8; i++) v[j][i] = 0.f;
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < kChunk; j++) {
+            if (c0 + j < nb_w) {                         // warp-uniform
+                const int b = warp + (c0 + j) * bg.nwarps, e0 = e0_of(c0 + j);
+                const bool act = e0 < K;
+                if (PRO == PRO_RMS && act) {
+#pragma unroll
+                    for (int i = 0; i < 8; i++) v[j][i] = __fmul_rn(al[j][i], __fmul_rn(v[j][i], scale));   // alpha * (x * scale)
+                    if (a.norm_out && norm_out_cta) {
+                        *reinterpret_cast<float4 *>(a.norm_out + e0) = make_float4(v[j][0], v[j][1], v[j][2], v[j][3]);
+                        *reinterpret_cast<float4 *>(a.norm_out + e0 + 4) = make_float4(v[j][4], v[j][5], v[j][6], v[j][7]);
+                    }
+                }
+                if (WT == 12) quantize_block_q8k(b, lane, v[j], P, x8, bs, dx);
+                else quantize_block_q8_0(b, lane, v[j], act, P, x8, dx);
+            }
         }
     }
+    if (bg.stamp && threadIdx.x == 0) bg.stamp[7] = global_ns();
 }
 
 // ---- epilogue ------------------------------------------------------------------------------------
-template <int EPI, int R>
-__device__ __forceinline__ void gemv_epilogue(const GemvArgs &a, int r0, const float (&acc)[R], int emb_token,
+template <int R>
+__device__ __forceinline__ void gemv_epilogue(const GemvArgs &a, const int EPI, int r0, const float (&acc)[R], int emb_token,
                                               unsigned long long &best) {
 #pragma unroll
     for (int r = 0; r < R; r++) {
         const int row = r0 + r;
         if (row >= a.w.rows) break;
         if (EPI == EPI_STORE) a.out[row] = acc[r];
-        else if (EPI == EPI_RESID) a.out[row] = a.out[row] + acc[r];
+        else if (EPI == EPI_RESID) a.out[row] = __ldcg(a.out + row) + acc[r];
         else if (EPI == EPI_GATE) {
             if ((r & 1) == 0) { const float g = acc[r]; a.out[row >> 1] = (g / (1.0f + (float)exp((double)(-g)))) * acc[r + 1]; }
         } else if (EPI == EPI_ARGMAX) {
@@ -186,160 +246,199 @@ __device__ __forceinline__ void gemv_epilogue(const GemvArgs &a, int r0, const f
 
 // token that feeds depformer step `k` (host override > forced > greedy result of the previous step)
 __device__ __forceinline__ int depformer_prev_token(const Ctrl *c, int k) {
-    if (k == 0) return c->text_override != INT32_MIN ? c->text_override : c->out_tokens[0];
-    const int f = c->force[k - 1];
-    return f != INT32_MIN ? f : argmax_key_index(c->audio_key[k - 1]);
+    // read through L2: the keys are written by other CTAs' atomics earlier in the same (persistent) launch
+    if (k == 0) { const int o = __ldcg(&c->text_override); return o != INT32_MIN ? o : __ldcg(&c->out_tokens[0]); }
+    const int f = __ldcg(&c->force[k - 1]);
+    return f != INT32_MIN ? f : argmax_key_index(__ldcg(&c->audio_key[k - 1]));
 }
 
 // ---- the kernel ----------------------------------------------------------------------------------
 // WT: 12 = Q4_K, 8 = Q8_0.  LANES: lanes cooperating on one row (32 or 16).
-template <int WT, int LANES, int PRO, int EPI>
-__global__ void __launch_bounds__(kThreads, 2) gemv_kernel(const GemvArgs a) {
-    extern __shared__ __align__(16) uint8_t smem[];
-    constexpr int R = kRowsPerTile * LANES / 32;        // rows per lane group per iteration
+// ---- main loop building blocks ---------------------------------------------------------------------
+// A "step" is one (tile, it) pair of a warp: R rows x LANES pairs (Q4_K: 64 weights, Q8_0: 32 weights per
+// lane).  The weights of a step live in a WBuf; two WBufs are double-buffered so the loads of step s+1 are
+// in flight while step s is computed, and the very first step is issued BEFORE the activation prologue.
+constexpr int kR = 2;                                    // rows per lane group per step
+__host__ __device__ constexpr int tile_rows(int lanes) { return kR * (32 / lanes); }   // rows a warp retires per tile
+
+template <int WT>
+struct WBuf {
+    int4 w0[kR], w1[kR];
+    uint32_t sc[kR];       // Q4_K: {sc_lo, sc_hi, m_lo, m_hi}
+    uint32_t dd[kR];       // Q4_K: {d, dmin} fp16x2;  Q8_0: fp16 d in the low half
+};
+
+template <int WT, int LANES>
+__device__ __forceinline__ void issue_step(const QLinear &w, WBuf<WT> &b, int r0, int it, int l) {
+    const int P = WT == 12 ? (w.K >> 6) : (w.K >> 5);
+    const int p = it * LANES + l;
+    if (p >= P) return;
+    const int gsz = min(LANES, P - it * LANES);
+    const size_t row_qs = WT == 12 ? (size_t)(w.K >> 1) : (size_t)w.K;
+#pragma unroll
+    for (int r = 0; r < kR; r++) {
+        const int row = min(r0 + r, w.rows - 1);
+        const uint8_t *q = w.qs + (size_t)row * row_qs + (size_t)it * (LANES * 32) + l * 16;
+        b.w0[r] = ldg_stream(q);
+        b.w1[r] = ldg_stream(q + gsz * 16);
+        if (WT == 12) {
+            b.sc[r] = __ldg(w.sc + (size_t)row * P + p);
+            b.dd[r] = __ldg(reinterpret_cast<const uint32_t *>(w.dd) + (size_t)row * (w.K >> 8) + (p >> 2));
+        } else {
+            b.dd[r] = __ldg(reinterpret_cast<const uint16_t *>(w.dd) + (size_t)row * P + p);
+        }
+    }
+}
+
+// acc[r] += exact block terms of this step (double accumulation, see file header)
+template <int WT, int LANES>
+__device__ __forceinline__ void compute_step(const WBuf<WT> &b, int K, int it, int l, const int8_t *x8, const int *bs, const float *dx,
+                                             double (&acc)[kR]) {
+    const int P = WT == 12 ? (K >> 6) : (K >> 5);
+    const int p = it * LANES + l;
+    if (p >= P) return;
+    if (WT == 12) {
+        const int4 xa0 = *reinterpret_cast<const int4 *>(x8 + ((size_t)0 * P + p) * 16);
+        const int4 xa1 = *reinterpret_cast<const int4 *>(x8 + ((size_t)1 * P + p) * 16);
+        const int4 xb0 = *reinterpret_cast<const int4 *>(x8 + ((size_t)2 * P + p) * 16);
+        const int4 xb1 = *reinterpret_cast<const int4 *>(x8 + ((size_t)3 * P + p) * 16);
+        const int2 b2 = *reinterpret_cast<const int2 *>(bs + 2 * p);
+        const float dxv = dx[p >> 2];
+#pragma unroll
+        for (int r = 0; r < kR; r++) {
+            const int4 a0 = b.w0[r], a1 = b.w1[r];
+            int dl = 0, dh = 0;   // dh accumulates 16 * (hi nibble) products: exact multiple of 16
+            dl = __dp4a(a0.x & 0x0F0F0F0F, xa0.x, dl); dh = dp4a_us((unsigned)a0.x & 0xF0F0F0F0u, xb0.x, dh);
+            dl = __dp4a(a0.y & 0x0F0F0F0F, xa0.y, dl); dh = dp4a_us((unsigned)a0.y & 0xF0F0F0F0u, xb0.y, dh);
+            dl = __dp4a(a0.z & 0x0F0F0F0F, xa0.z, dl); dh = dp4a_us((unsigned)a0.z & 0xF0F0F0F0u, xb0.z, dh);
+            dl = __dp4a(a0.w & 0x0F0F0F0F, xa0.w, dl); dh = dp4a_us((unsigned)a0.w & 0xF0F0F0F0u, xb0.w, dh);
+            dl = __dp4a(a1.x & 0x0F0F0F0F, xa1.x, dl); dh = dp4a_us((unsigned)a1.x & 0xF0F0F0F0u, xb1.x, dh);
+            dl = __dp4a(a1.y & 0x0F0F0F0F, xa1.y, dl); dh = dp4a_us((unsigned)a1.y & 0xF0F0F0F0u, xb1.y, dh);
+            dl = __dp4a(a1.z & 0x0F0F0F0F, xa1.z, dl); dh = dp4a_us((unsigned)a1.z & 0xF0F0F0F0u, xb1.z, dh);
+            dl = __dp4a(a1.w & 0x0F0F0F0F, xa1.w, dl); dh = dp4a_us((unsigned)a1.w & 0xF0F0F0F0u, xb1.w, dh);
+            const uint32_t scv = b.sc[r];
+            const int isum = (int)(scv & 0xff) * dl + (int)((scv >> 8) & 0xff) * (dh >> 4);
+            const int imin = (int)((scv >> 16) & 0xff) * b2.x + (int)(scv >> 24) * b2.y;
+            const float2 dm = __half22float2(*reinterpret_cast<const __half2 *>(&b.dd[r]));
+            // exact products (24-bit x <24-bit) accumulated in double: order-independent result
+            acc[r] = fma((double)(dm.x * dxv), (double)isum, acc[r]);
+            acc[r] = fma(-(double)(dm.y * dxv), (double)imin, acc[r]);
+        }
+    } else {
+        const int4 xa = *reinterpret_cast<const int4 *>(x8 + ((size_t)0 * P + p) * 16);
+        const int4 xb = *reinterpret_cast<const int4 *>(x8 + ((size_t)1 * P + p) * 16);
+        const float dxv = dx[p];
+#pragma unroll
+        for (int r = 0; r < kR; r++) {
+            const int4 a0 = b.w0[r], a1 = b.w1[r];
+            int sum = 0;
+            sum = __dp4a(a0.x, xa.x, sum); sum = __dp4a(a0.y, xa.y, sum); sum = __dp4a(a0.z, xa.z, sum); sum = __dp4a(a0.w, xa.w, sum);
+            sum = __dp4a(a1.x, xb.x, sum); sum = __dp4a(a1.y, xb.y, sum); sum = __dp4a(a1.z, xb.z, sum); sum = __dp4a(a1.w, xb.w, sum);
+            const float dw = __half2float(__ushort_as_half((unsigned short)(b.dd[r] & 0xffff)));
+            acc[r] = fma((double)(dw * dxv), (double)sum, acc[r]);
+        }
+    }
+}
+
+// PRO / EPI are run-time (warp-uniform) selectors on purpose: one copy of the main loop per (WT, LANES).
+// `a` may live in kernel-parameter space (standalone kernels) or in shared memory (phase descriptor of the
+// persistent kernel); it is never copied to local memory.  x_over replaces a.x when non-null.
+template <int WT, int LANES, bool PDL = false>
+__device__ __forceinline__ void gemv_body(const GemvArgs &a, const float *x_over, const bool norm_out_cta, const int PRO, const int EPI,
+                                          uint8_t *smem, const int cta, const int n_cta, const BlockGeom bg,
+                                          unsigned long long *progress = nullptr) {
+    const float *xin = x_over ? x_over : a.x;
+    constexpr int TR = tile_rows(LANES);
     const int K = a.w.K;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, warp = uniform_warp_id();
     const int sub = lane / LANES, l = lane % LANES;
+    const int P = WT == 12 ? (K >> 6) : (K >> 5);
+    const int nit = (P + LANES - 1) / LANES;
+
+    const int n_tiles = (a.w.rows + TR - 1) / TR;
+    const int t_begin = (int)((long long)cta * n_tiles / n_cta);
+    const int t_end = (int)((long long)(cta + 1) * n_tiles / n_cta);
+    const int my_tiles = (t_end - t_begin - warp + bg.nwarps - 1) / bg.nwarps;      // tiles t_begin + warp + i * nwarps
+    const int n_steps = my_tiles > 0 ? my_tiles * nit : 0;
+    auto row0_of = [&](int step) { return (t_begin + warp + (step / nit) * bg.nwarps) * TR + sub * kR; };
+
+    // weights do not depend on the activations: get the first step in flight before the prologue
+    // (and, in the standalone kernels, before waiting for the previous kernel: PDL)
+    WBuf<WT> A, B;
+    if (n_steps > 0) issue_step<WT, LANES>(a.w, A, row0_of(0), 0, l);
+    if (PDL) griddep_wait();
 
     int8_t *x8 = reinterpret_cast<int8_t *>(smem);
     int *bs = nullptr; float *dx = nullptr; double *red = nullptr;
     if (WT == 12) {
         bs = reinterpret_cast<int *>(smem + K);
         dx = reinterpret_cast<float *>(smem + K + (K >> 6) * 8);
-        red = reinterpret_cast<double *>(smem + gemv_smem_bytes(12, K) - 64);
-        quantize_act_q8k<PRO>(a, K, x8, bs, dx, red);
+        red = reinterpret_cast<double *>(smem + gemv_smem_bytes(12, K) - 128);
+        gemv_prologue<12>(a, xin, norm_out_cta, PRO, K, x8, bs, dx, red, bg);
     } else {
         dx = reinterpret_cast<float *>(smem + K);
-        red = reinterpret_cast<double *>(smem + gemv_smem_bytes(8, K) - 64);
-        quantize_act_q8_0<PRO>(a, K, x8, dx, red);
+        red = reinterpret_cast<double *>(smem + gemv_smem_bytes(8, K) - 128);
+        gemv_prologue<8>(a, xin, norm_out_cta, PRO, K, x8, nullptr, dx, red, bg);
     }
-    __syncthreads();
+    block_sync(bg);
+    if (bg.stamp && threadIdx.x == 0) bg.stamp[1] = global_ns();
 
     int emb_token = 0;
     if (EPI == EPI_ADD_EMB) emb_token = depformer_prev_token(a.ctrl, a.emb_step);
     unsigned long long best = 0ull;
 
-    const int n_tiles = (a.w.rows + kRowsPerTile - 1) / kRowsPerTile;
-    const int t_begin = (int)((long long)blockIdx.x * n_tiles / gridDim.x);
-    const int t_end = (int)((long long)(blockIdx.x + 1) * n_tiles / gridDim.x);
-
-    if (WT == 12) {
-        const int P = K >> 6, NSB = K >> 8;
-        const int nit = (P + LANES - 1) / LANES;
-        const size_t row_qs = (size_t)(K >> 1);
-        for (int tile = t_begin + warp; tile < t_end; tile += kWarps) {
-            const int r0 = tile * kRowsPerTile + sub * R;
-            double acc[R];
+    double acc[kR];
 #pragma unroll
-            for (int r = 0; r < R; r++) acc[r] = 0.0;
-            for (int it = 0; it < nit; it++) {
-                const int p = it * LANES + l;
-                const int gsz = min(LANES, P - it * LANES);
-                if (p < P) {
-                    int4 w0[R], w1[R]; uint32_t sc[R], dd[R];
+    for (int r = 0; r < kR; r++) acc[r] = 0.0;
+    const unsigned long long tile_bytes = WT == 12 ? (unsigned long long)TR * ((K >> 1) + P * 4 + (K >> 8) * 4)
+                                                   : (unsigned long long)TR * (K + P * 2);
+    // end of a tile: reduce the lane partials, run the epilogue, reset
+    auto finish_tile = [&](int step) {
+        float accf[kR];
 #pragma unroll
-                    for (int r = 0; r < R; r++) {
-                        const int row = min(r0 + r, a.w.rows - 1);
-                        const uint8_t *q = a.w.qs + (size_t)row * row_qs + (size_t)it * (LANES * 32) + l * 16;
-                        w0[r] = ldg_stream(q);
-                        w1[r] = ldg_stream(q + gsz * 16);
-                        sc[r] = __ldg(a.w.sc + (size_t)row * P + p);
-                        dd[r] = __ldg(reinterpret_cast<const uint32_t *>(a.w.dd) + (size_t)row * NSB + (p >> 2));
-                    }
-                    const int4 xa0 = *reinterpret_cast<const int4 *>(x8 + ((size_t)0 * P + p) * 16);
-                    const int4 xa1 = *reinterpret_cast<const int4 *>(x8 + ((size_t)1 * P + p) * 16);
-                    const int4 xb0 = *reinterpret_cast<const int4 *>(x8 + ((size_t)2 * P + p) * 16);
-                    const int4 xb1 = *reinterpret_cast<const int4 *>(x8 + ((size_t)3 * P + p) * 16);
-                    const int2 b2 = *reinterpret_cast<const int2 *>(bs + 2 * p);
-                    const float dxv = dx[p >> 2];
+        for (int r = 0; r < kR; r++) {
 #pragma unroll
-                    for (int r = 0; r < R; r++) {
-                        int dl = 0, dh = 0;   // dh accumulates 16 * (hi nibble) products: exact multiple of 16
-                        dl = __dp4a(w0[r].x & 0x0F0F0F0F, xa0.x, dl); dh = dp4a_us((unsigned)w0[r].x & 0xF0F0F0F0u, xb0.x, dh);
-                        dl = __dp4a(w0[r].y & 0x0F0F0F0F, xa0.y, dl); dh = dp4a_us((unsigned)w0[r].y & 0xF0F0F0F0u, xb0.y, dh);
-                        dl = __dp4a(w0[r].z & 0x0F0F0F0F, xa0.z, dl); dh = dp4a_us((unsigned)w0[r].z & 0xF0F0F0F0u, xb0.z, dh);
-                        dl = __dp4a(w0[r].w & 0x0F0F0F0F, xa0.w, dl); dh = dp4a_us((unsigned)w0[r].w & 0xF0F0F0F0u, xb0.w, dh);
-                        dl = __dp4a(w1[r].x & 0x0F0F0F0F, xa1.x, dl); dh = dp4a_us((unsigned)w1[r].x & 0xF0F0F0F0u, xb1.x, dh);
-                        dl = __dp4a(w1[r].y & 0x0F0F0F0F, xa1.y, dl); dh = dp4a_us((unsigned)w1[r].y & 0xF0F0F0F0u, xb1.y, dh);
-                        dl = __dp4a(w1[r].z & 0x0F0F0F0F, xa1.z, dl); dh = dp4a_us((unsigned)w1[r].z & 0xF0F0F0F0u, xb1.z, dh);
-                        dl = __dp4a(w1[r].w & 0x0F0F0F0F, xa1.w, dl); dh = dp4a_us((unsigned)w1[r].w & 0xF0F0F0F0u, xb1.w, dh);
-                        const int isum = (int)(sc[r] & 0xff) * dl + (int)((sc[r] >> 8) & 0xff) * (dh >> 4);
-                        const int imin = (int)((sc[r] >> 16) & 0xff) * b2.x + (int)(sc[r] >> 24) * b2.y;
-                        const float2 dm = __half22float2(*reinterpret_cast<const __half2 *>(&dd[r]));
-                        // exact products (24-bit x <24-bit) accumulated in double: order-independent result
-                        acc[r] = fma((double)(dm.x * dxv), (double)isum, acc[r]);
-                        acc[r] = fma(-(double)(dm.y * dxv), (double)imin, acc[r]);
-                    }
-                }
-            }
-            float accf[R];
-#pragma unroll
-            for (int r = 0; r < R; r++) {
-#pragma unroll
-                for (int o = LANES / 2; o > 0; o >>= 1) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], o);
-                accf[r] = (float)acc[r];
-            }
-            if (l == 0) gemv_epilogue<EPI, R>(a, r0, accf, emb_token, best);
+            for (int o = LANES / 2; o > 0; o >>= 1) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], o);
+            accf[r] = (float)acc[r];
+            acc[r] = 0.0;
         }
-    } else {   // Q8_0
-        const int P = K >> 5;
-        const int nit = (P + LANES - 1) / LANES;
-        const size_t row_qs = (size_t)K;
-        for (int tile = t_begin + warp; tile < t_end; tile += kWarps) {
-            const int r0 = tile * kRowsPerTile + sub * R;
-            double acc[R];
-#pragma unroll
-            for (int r = 0; r < R; r++) acc[r] = 0.0;
-            for (int it = 0; it < nit; it++) {
-                const int p = it * LANES + l;
-                const int gsz = min(LANES, P - it * LANES);
-                if (p < P) {
-                    int4 w0[R], w1[R]; float dw[R];
-#pragma unroll
-                    for (int r = 0; r < R; r++) {
-                        const int row = min(r0 + r, a.w.rows - 1);
-                        const uint8_t *q = a.w.qs + (size_t)row * row_qs + (size_t)it * (LANES * 32) + l * 16;
-                        w0[r] = ldg_stream(q);
-                        w1[r] = ldg_stream(q + gsz * 16);
-                        dw[r] = __half2float(__ldg(reinterpret_cast<const __half *>(a.w.dd) + (size_t)row * P + p));
-                    }
-                    const int4 xa = *reinterpret_cast<const int4 *>(x8 + ((size_t)0 * P + p) * 16);
-                    const int4 xb = *reinterpret_cast<const int4 *>(x8 + ((size_t)1 * P + p) * 16);
-                    const float dxv = dx[p];
-#pragma unroll
-                    for (int r = 0; r < R; r++) {
-                        int s = 0;
-                        s = __dp4a(w0[r].x, xa.x, s); s = __dp4a(w0[r].y, xa.y, s); s = __dp4a(w0[r].z, xa.z, s); s = __dp4a(w0[r].w, xa.w, s);
-                        s = __dp4a(w1[r].x, xb.x, s); s = __dp4a(w1[r].y, xb.y, s); s = __dp4a(w1[r].z, xb.z, s); s = __dp4a(w1[r].w, xb.w, s);
-                        acc[r] = fma((double)(dw[r] * dxv), (double)s, acc[r]);
-                    }
-                }
-            }
-            float accf[R];
-#pragma unroll
-            for (int r = 0; r < R; r++) {
-#pragma unroll
-                for (int o = LANES / 2; o > 0; o >>= 1) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], o);
-                accf[r] = (float)acc[r];
-            }
-            if (l == 0) gemv_epilogue<EPI, R>(a, r0, accf, emb_token, best);
+        if (l == 0) gemv_epilogue<kR>(a, EPI, row0_of(step), accf, emb_token, best);
+        if (progress && lane == 0) atomicAdd(progress, tile_bytes);
+    };
+#pragma unroll 1
+    for (int s = 0; s < n_steps; s += 2) {
+        if (s + 1 < n_steps) issue_step<WT, LANES>(a.w, B, row0_of(s + 1), (s + 1) % nit, l);
+        compute_step<WT, LANES>(A, K, s % nit, l, x8, bs, dx, acc);
+        if (s % nit == nit - 1) finish_tile(s);
+        if (s + 2 < n_steps) issue_step<WT, LANES>(a.w, A, row0_of(s + 2), (s + 2) % nit, l);
+        if (s + 1 < n_steps) {
+            compute_step<WT, LANES>(B, K, (s + 1) % nit, l, x8, bs, dx, acc);
+            if ((s + 1) % nit == nit - 1) finish_tile(s + 1);
         }
     }
+    if (bg.stamp && threadIdx.x == 0) bg.stamp[2] = global_ns();
 
     if (EPI == EPI_ARGMAX) {
         // CTA-level max, then one atomic per CTA
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { unsigned long long t = __shfl_xor_sync(0xffffffffu, best, o); best = t > best ? t : best; }
-        __shared__ unsigned long long sbest[kWarps];
+        unsigned long long *sbest = reinterpret_cast<unsigned long long *>(red);   // prologue scratch is free by now
+        block_sync(bg);
         if (lane == 0) sbest[warp] = best;
-        __syncthreads();
+        block_sync(bg);
         if (threadIdx.x == 0) {
-            unsigned long long b = 0;
-#pragma unroll
-            for (int w = 0; w < kWarps; w++) b = sbest[w] > b ? sbest[w] : b;
-            if (b) atomicMax(a.key, b);
+            unsigned long long bb = 0;
+            for (int w = 0; w < bg.nwarps; w++) bb = sbest[w] > bb ? sbest[w] : bb;
+            if (bb) atomicMax(a.key, bb);
         }
     }
+}
+
+template <int WT, int LANES>
+__global__ void __launch_bounds__(kThreads, 2) gemv_kernel(const GemvArgs a, const int pro, const int epi) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    griddep_launch();      // the next kernel may start launching: it prefetches its weights and then waits for us
+    gemv_body<WT, LANES, true>(a, nullptr, blockIdx.x == 0, pro, epi, smem, blockIdx.x, gridDim.x, BlockGeom{kThreads, kWarps});
 }
 
 }  // namespace msx

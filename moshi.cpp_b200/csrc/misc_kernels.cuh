@@ -15,25 +15,26 @@ struct EmbedArgs {
     float *x = nullptr;
 };
 
-__global__ void __launch_bounds__(kThreads) embed_kernel(const EmbedArgs a) {
+__device__ __forceinline__ void embed_body(const EmbedArgs &a, int cta, int n_cta, int nthr) {
     const Ctrl *c = a.ctrl;
     const int32_t *toks = c->feed_n ? c->feed + (size_t)(c->frame % c->feed_n) * c->n_in : c->tokens;
-    const int i = blockIdx.x * kThreads + threadIdx.x;
-    if (i >= a.dim) return;
-    float acc = 0.f;
-    for (int t = 0; t < a.n_tables; t++) {
-        const int tok = toks[t];
-        float e = emb_element(a.tables[t], tok < 0 ? 0 : tok, i);
-        e = e * (tok == -1 ? 0.f : 1.f);
-        acc = (t == 0) ? e : acc + e;
+    for (int i = cta * nthr + threadIdx.x; i < a.dim; i += n_cta * nthr) {
+        float acc = 0.f;
+        for (int t = 0; t < a.n_tables; t++) {
+            const int tok = toks[t];
+            float e = emb_element(a.tables[t], tok < 0 ? 0 : tok, i);
+            e = e * (tok == -1 ? 0.f : 1.f);
+            acc = (t == 0) ? e : acc + e;
+        }
+        a.x[i] = acc;
     }
-    a.x[i] = acc;
 }
+__global__ void __launch_bounds__(kThreads) embed_kernel(const EmbedArgs a) { griddep_launch(); griddep_wait(); embed_body(a, blockIdx.x, gridDim.x, kThreads); }
 
 // ---- frame bookkeeping ------------------------------------------------------------------------------
 // end of the temporal graph: greedy text token out of the arg-max key, position advances
 // (states->offset += T, transformer.h:1269-1270)
-__global__ void finalize_temporal_kernel(Ctrl *c, int has_depformer) {
+__device__ __forceinline__ void finalize_temporal_body(Ctrl *c, int has_depformer) {
     if (threadIdx.x == 0) {
         c->out_tokens[0] = argmax_key_index(c->text_key);
         c->text_key = 0ull;
@@ -43,21 +44,24 @@ __global__ void finalize_temporal_kernel(Ctrl *c, int has_depformer) {
         }
     }
 }
+__global__ void finalize_temporal_kernel(Ctrl *c, int has_depformer) { griddep_launch(); griddep_wait(); finalize_temporal_body(c, has_depformer); }
 
 // end of the depformer graph: collect the dep_q greedy tokens (lm.h:548-552)
-__global__ void finalize_depformer_kernel(Ctrl *c, int dep_q) {
-    const int k = threadIdx.x;
-    if (k < dep_q) {
+// single warp does the whole job (dep_q <= 40: two passes of 32 lanes)
+__device__ __forceinline__ void finalize_depformer_body(Ctrl *c, int dep_q) {
+    if (threadIdx.x >= 32) return;
+    for (int k = threadIdx.x; k < dep_q; k += 32) {
         c->out_tokens[1 + k] = argmax_key_index(c->audio_key[k]);
         c->audio_key[k] = 0ull;
     }
-    __syncthreads();
+    __syncwarp();
     if (c->feed_n) {
-        if (c->trace && k <= dep_q) c->trace[(size_t)c->frame * (dep_q + 1) + k] = c->out_tokens[k];
-        __syncthreads();
-        if (k == 0) c->frame += 1;
+        if (c->trace) for (int k = threadIdx.x; k <= dep_q; k += 32) c->trace[(size_t)c->frame * (dep_q + 1) + k] = c->out_tokens[k];
+        __syncwarp();
+        if (threadIdx.x == 0) c->frame += 1;
     }
 }
+__global__ void finalize_depformer_kernel(Ctrl *c, int dep_q) { griddep_launch(); griddep_wait(); finalize_depformer_body(c, dep_q); }
 
 // ---- load-time repack (GGUF row-major blocks -> device tiles, see common.cuh QLinear) --------------
 // perm_half > 0 interleaves rows for the gated MLP: stored row v <- source row (v&1 ? perm_half + v/2 : v/2)

@@ -289,3 +289,21 @@ def test_errors(msx, gguf_for, tmp_path):
     with pytest.raises(msx.MsxError) as e:
         msx.Model(path, wrong)
     assert e.value.code == -3
+
+
+@pytest.mark.parametrize("preset,quant", [("tiny", "q4_k"), ("tiny_pplex", "q8_0"), ("moshi7b_l2", "q4_k")])
+def test_persistent_kernels_match_multi_kernel_path(msx, gguf_for, preset, quant):
+    """The persistent phase-program kernels and the one-launch-per-op path share their arithmetic and
+    accumulate order-independently: logits and tokens must be bit-identical."""
+    path, cfg = gguf_for(preset, quant)
+    gm = msx.Model(path, cfg)
+    a = msx.Stream(gm, persistent_depformer=True); b = msx.Stream(gm)
+    assert a.launches_per_frame < b.launches_per_frame
+    rng = np.random.default_rng(5)
+    for f in range(12 if preset != "moshi7b_l2" else 4):
+        toks = rng.integers(0, cfg["card"], size=cfg["n_q"] + 1).astype(np.int32)
+        ta, la, oa = a.step_temporal(toks); tb, lb, ob = b.step_temporal(toks)
+        assert ta == tb and np.array_equal(la.view(np.uint32), lb.view(np.uint32))
+        xa, xla = a.step_depformer(ta); xb, xlb = b.step_depformer(tb)
+        assert np.array_equal(xa, xb), f"frame {f}"
+        assert np.array_equal(xla.view(np.uint32), xlb.view(np.uint32)), f"frame {f}"
