@@ -398,15 +398,35 @@ struct Launcher {
         fam = family; begin();
         const int tr = tile_rows(a.w.gs);
         const int n_tiles = (a.w.rows + tr - 1) / tr;
-        const int grid = std::max(1, std::min(2 * num_sms, (n_tiles + 3) / 4));
+        const int grid = std::max(1, std::min(num_sms, (n_tiles + 7) / 8));
         const int smem = gemv_smem_bytes(a.w.type, a.w.K);
         if (a.w.type == T_Q4_K) {
-            if (a.w.gs == 32) launch_pdl(gemv_kernel<12, 32>, dim3(grid), dim3(kThreads), smem, a, pro, epi);
-            else launch_pdl(gemv_kernel<12, 16>, dim3(grid), dim3(kThreads), smem, a, pro, epi);
+            if (a.w.gs == 32) launch_pdl(gemv_kernel<12, 32>, dim3(grid), dim3(kGemvThreads), smem, a, pro, epi);
+            else launch_pdl(gemv_kernel<12, 16>, dim3(grid), dim3(kGemvThreads), smem, a, pro, epi);
         } else {
-            if (a.w.gs == 32) launch_pdl(gemv_kernel<8, 32>, dim3(grid), dim3(kThreads), smem, a, pro, epi);
-            else launch_pdl(gemv_kernel<8, 16>, dim3(grid), dim3(kThreads), smem, a, pro, epi);
+            if (a.w.gs == 32) launch_pdl(gemv_kernel<8, 32>, dim3(grid), dim3(kGemvThreads), smem, a, pro, epi);
+            else launch_pdl(gemv_kernel<8, 16>, dim3(grid), dim3(kGemvThreads), smem, a, pro, epi);
         }
+        check();
+    }
+
+    // fused local attention + out_proj (tiny rings)
+    void gemv_local_attn(const GemvArgs &g, const AttnArgs &a, int heads, int dh, int pro, int epi, int family = 0) {
+        fam = family; begin();
+        const int tr = tile_rows(g.w.gs);
+        const int n_tiles = (g.w.rows + tr - 1) / tr;
+        const int grid = std::max(1, std::min(num_sms, (n_tiles + 7) / 8));
+        const int region = (gemv_smem_bytes(g.w.type, g.w.K) + 15) / 16 * 16;
+        const int smem = local_attn_smem_bytes(region, a.dim, dh);
+#define MSX_LA(WT, LN, DH) launch_pdl(gemv_local_attn_kernel<WT, LN, DH>, dim3(grid), dim3(kGemvThreads), smem, g, a, heads, pro, epi, region)
+        if (g.w.type == T_Q4_K) {
+            if (g.w.gs == 32) { if (dh == 64) MSX_LA(12, 32, 64); else MSX_LA(12, 32, 128); }
+            else { if (dh == 64) MSX_LA(12, 16, 64); else MSX_LA(12, 16, 128); }
+        } else {
+            if (g.w.gs == 32) { if (dh == 64) MSX_LA(8, 32, 64); else MSX_LA(8, 32, 128); }
+            else { if (dh == 64) MSX_LA(8, 16, 64); else MSX_LA(8, 16, 128); }
+        }
+#undef MSX_LA
         check();
     }
 
@@ -514,10 +534,16 @@ void enqueue_layer(Launcher &L, const msx_stream *s, const LayerW &lw, int w, bo
     const size_t lstride = (size_t)cap * dim;
     a.kc = (temporal ? s->kc : s->dkc) + (size_t)layer * lstride;
     a.vc = (temporal ? s->vc : s->dvc) + (size_t)layer * lstride;
-    L.attn(a, heads, dim / heads, temporal ? s->attn_split : 1, temporal ? FAM_ATTN : FAM_DEP_ATTN);
-    // out_proj + residual
-    g.w = lw.out_proj[w]; g.x = ctx; g.alpha = nullptr; g.out = x;
-    L.gemv(g, PRO_PLAIN, EPI_RESID, temporal ? FAM_OUT_PROJ : FAM_DEP_OUT_PROJ);
+    if (!temporal && cap <= 64) {
+        // tiny ring: every CTA recomputes the attention of all heads in its prologue -> one launch
+        g.w = lw.out_proj[w]; g.x = nullptr; g.alpha = nullptr; g.out = x;
+        L.gemv_local_attn(g, a, heads, dim / heads, PRO_PLAIN, EPI_RESID, FAM_DEP_OUT_PROJ);
+    } else {
+        L.attn(a, heads, dim / heads, temporal ? s->attn_split : 1, temporal ? FAM_ATTN : FAM_DEP_ATTN);
+        // out_proj + residual
+        g.w = lw.out_proj[w]; g.x = ctx; g.alpha = nullptr; g.out = x;
+        L.gemv(g, PRO_PLAIN, EPI_RESID, temporal ? FAM_OUT_PROJ : FAM_DEP_OUT_PROJ);
+    }
     // rms_norm2 -> linear_in -> silu gate
     g.w = lw.lin_in[w]; g.x = x; g.alpha = lw.norm2; g.out = gate;
     L.gemv(g, PRO_RMS, EPI_GATE, temporal ? FAM_LIN_IN : FAM_DEP_LIN_IN);
@@ -654,6 +680,20 @@ int capture(msx_stream *s, F &&body, cudaGraphExec_t *exec, int *launches) {
 }
 
 int set_smem_attrs() {
+    const int big = 220 * 1024;   // dynamic part; the kernels also have a little static shared memory
+    CU(cudaFuncSetAttribute(gemv_kernel<12, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU(cudaFuncSetAttribute(gemv_kernel<12, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU(cudaFuncSetAttribute(gemv_kernel<8, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU(cudaFuncSetAttribute(gemv_kernel<8, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU(cudaFuncSetAttribute(gemv_local_attn_kernel<12, 32, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU(cudaFuncSetAttribute(gemv_local_attn_kernel<12, 32, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU(cudaFuncSetAttribute(gemv_local_attn_kernel<12, 16, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU(cudaFuncSetAttribute(gemv_local_attn_kernel<12, 16, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU(cudaFuncSetAttribute(gemv_local_attn_kernel<8, 32, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU(cudaFuncSetAttribute(gemv_local_attn_kernel<8, 32, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU(cudaFuncSetAttribute(gemv_local_attn_kernel<8, 16, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU(cudaFuncSetAttribute(gemv_local_attn_kernel<8, 16, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU(cudaFuncSetAttribute(mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     // all kernels stay below the 48 KB default except long-context attention with split 1
     CU(cudaFuncSetAttribute(attn_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     CU(cudaFuncSetAttribute(attn_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
@@ -722,7 +762,6 @@ extern "C" int msx_stream_create_ex(msx_model *m, int context_override, int flag
             s->mega_gemv_region = (mx + 15) / 16 * 16;
             s->mega_local_dim = c.dep_dim;
             s->mega_smem = mega_smem_bytes(mx, c.dep_dim, c.dep_dim / c.dep_heads);
-            CU(cudaFuncSetAttribute(mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(s->mega_smem, 48 * 1024)));
             int per_sm = 0;
             CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mega_kernel, kMegaThreads, s->mega_smem));
             if (per_sm >= 1) {
@@ -1135,7 +1174,7 @@ int test_setup(int device, std::unique_ptr<msx_model> &m) {
     if (prop.major != 10) return fail(MSX_ERR_CUDA, "sm_100a device required");
     m.reset(new msx_model);
     m->device = device; m->num_sms = prop.multiProcessorCount;
-    return 0;
+    return set_smem_attrs();
 }
 }  // namespace
 

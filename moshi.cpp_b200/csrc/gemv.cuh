@@ -43,11 +43,28 @@ __device__ __forceinline__ float4 ld_act4(const float *p) {
     return __ldcg(reinterpret_cast<const float4 *>(p));
 }
 
-__host__ __device__ inline int gemv_smem_bytes(int type, int K) {
+// quantised activations + block-reduce scratch
+__host__ __device__ inline int gemv_q_bytes(int type, int K) {
     // Q4_K: x8[K] + bsums int2[K/64] + dx float[K/256];  Q8_0: x8[K] + dx float[K/32]
     int b = (type == 12) ? K + (K / 64) * 8 + (K / 256) * 4 : K + (K / 32) * 4;
     return (b + 15) / 16 * 16 + 128;  // + block-reduce scratch (16 doubles)
 }
+// Weight ring: every warp owns kStages slots; a slot holds one step of the warp (kR rows x 32 lanes):
+// per lane 2 x 16 B of quants per row + 4 B scales + 4 B d/dmin per row, all lane-private.
+constexpr int kStages = 4;
+constexpr int kR = 2;                                    // rows per lane group per step
+constexpr int kSlotBytes = 32 * kR * (32 + 4 + 4);       // 2560 B
+__host__ __device__ inline int gemv_smem_bytes_n(int type, int K, int nwarps) { return gemv_q_bytes(type, K) + nwarps * kStages * kSlotBytes; }
+__host__ __device__ inline int gemv_smem_bytes(int type, int K) { return gemv_smem_bytes_n(type, K, 16); }
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // ---- prologue: (optional RMSNorm) + activation quantisation into shared memory -------------------
 // One pass over x: every warp owns 256-element blocks (lane = 8 consecutive elements) and keeps up to
@@ -89,7 +106,8 @@ __device__ __forceinline__ void quantize_block_q8k(int b, int lane, const float 
     float amax = 0.f, mx = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; i++) { float ax = fabsf(v[i]); if (ax > amax) { amax = ax; mx = v[i]; } }
-    const float wmax = warp_max(amax);
+    // |x| bit patterns are monotonic as unsigned integers: one REDUX instead of a 5-level shuffle butterfly
+    const float wmax = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(amax)));
     const unsigned hit = __ballot_sync(0xffffffffu, amax == wmax);          // carrier = first element attaining the max
     const float carrier = __shfl_sync(0xffffffffu, mx, __ffs(hit) - 1);
     int q[8];
@@ -255,45 +273,49 @@ __device__ __forceinline__ int depformer_prev_token(const Ctrl *c, int k) {
 // ---- the kernel ----------------------------------------------------------------------------------
 // WT: 12 = Q4_K, 8 = Q8_0.  LANES: lanes cooperating on one row (32 or 16).
 // ---- main loop building blocks ---------------------------------------------------------------------
-// A "step" is one (tile, it) pair of a warp: R rows x LANES pairs (Q4_K: 64 weights, Q8_0: 32 weights per
-// lane).  The weights of a step live in a WBuf; two WBufs are double-buffered so the loads of step s+1 are
-// in flight while step s is computed, and the very first step is issued BEFORE the activation prologue.
-constexpr int kR = 2;                                    // rows per lane group per step
+// A "step" is one (tile, it) pair of a warp: kR rows x LANES pairs (Q4_K: 64 weights, Q8_0: 32 weights per
+// lane).  The weights of a step are copied global -> shared with cp.async into a lane-private part of the
+// warp's ring slot (no registers, no barriers: each lane later reads back exactly what it copied); kStages-1
+// steps are in flight while one is computed, and the first kStages-1 steps are issued BEFORE the PDL wait
+// and the activation prologue, so the HBM stream starts at kernel entry.
 __host__ __device__ constexpr int tile_rows(int lanes) { return kR * (32 / lanes); }   // rows a warp retires per tile
 
-template <int WT>
-struct WBuf {
-    int4 w0[kR], w1[kR];
-    uint32_t sc[kR];       // Q4_K: {sc_lo, sc_hi, m_lo, m_hi}
-    uint32_t dd[kR];       // Q4_K: {d, dmin} fp16x2;  Q8_0: fp16 d in the low half
-};
+// lane-private layout inside a slot: [row r][lane]: w0 at (r*32+lane)*16, w1 at 1024*kR/2.. see offsets below
+__device__ __forceinline__ uint8_t *slot_w0(uint8_t *slot, int r, int lane) { return slot + (r * 32 + lane) * 16; }
+__device__ __forceinline__ uint8_t *slot_w1(uint8_t *slot, int r, int lane) { return slot + 32 * kR * 16 + (r * 32 + lane) * 16; }
+__device__ __forceinline__ uint8_t *slot_sc(uint8_t *slot, int r, int lane) { return slot + 32 * kR * 32 + (r * 32 + lane) * 4; }
+__device__ __forceinline__ uint8_t *slot_dd(uint8_t *slot, int r, int lane) { return slot + 32 * kR * 36 + (r * 32 + lane) * 4; }
 
 template <int WT, int LANES>
-__device__ __forceinline__ void issue_step(const QLinear &w, WBuf<WT> &b, int r0, int it, int l) {
+__device__ __forceinline__ void issue_step(const QLinear &w, uint8_t *slot, int r0, int it, int l, int lane) {
     const int P = WT == 12 ? (w.K >> 6) : (w.K >> 5);
     const int p = it * LANES + l;
-    if (p >= P) return;
-    const int gsz = min(LANES, P - it * LANES);
-    const size_t row_qs = WT == 12 ? (size_t)(w.K >> 1) : (size_t)w.K;
+    if (p < P) {
+        const int gsz = min(LANES, P - it * LANES);
+        const size_t row_qs = WT == 12 ? (size_t)(w.K >> 1) : (size_t)w.K;
 #pragma unroll
-    for (int r = 0; r < kR; r++) {
-        const int row = min(r0 + r, w.rows - 1);
-        const uint8_t *q = w.qs + (size_t)row * row_qs + (size_t)it * (LANES * 32) + l * 16;
-        b.w0[r] = ldg_stream(q);
-        b.w1[r] = ldg_stream(q + gsz * 16);
-        if (WT == 12) {
-            b.sc[r] = __ldg(w.sc + (size_t)row * P + p);
-            b.dd[r] = __ldg(reinterpret_cast<const uint32_t *>(w.dd) + (size_t)row * (w.K >> 8) + (p >> 2));
-        } else {
-            b.dd[r] = __ldg(reinterpret_cast<const uint16_t *>(w.dd) + (size_t)row * P + p);
+        for (int r = 0; r < kR; r++) {
+            const int row = min(r0 + r, w.rows - 1);
+            const uint8_t *q = w.qs + (size_t)row * row_qs + (size_t)it * (LANES * 32) + l * 16;
+            cp_async16(slot_w0(slot, r, lane), q);
+            cp_async16(slot_w1(slot, r, lane), q + gsz * 16);
+            if (WT == 12) {
+                cp_async4(slot_sc(slot, r, lane), w.sc + (size_t)row * P + p);
+                cp_async4(slot_dd(slot, r, lane), reinterpret_cast<const uint32_t *>(w.dd) + (size_t)row * (w.K >> 8) + (p >> 2));
+            } else {
+                // fp16 scale: 4-byte aligned copy of the pair containing it
+                const uint16_t *d = reinterpret_cast<const uint16_t *>(w.dd) + (size_t)row * P + p;
+                cp_async4(slot_dd(slot, r, lane), reinterpret_cast<const void *>(reinterpret_cast<uintptr_t>(d) & ~(uintptr_t)3));
+                *reinterpret_cast<uint32_t *>(slot_sc(slot, r, lane)) = (uint32_t)((reinterpret_cast<uintptr_t>(d) >> 1) & 1);   // which half
+            }
         }
     }
 }
 
 // acc[r] += exact block terms of this step (double accumulation, see file header)
 template <int WT, int LANES>
-__device__ __forceinline__ void compute_step(const WBuf<WT> &b, int K, int it, int l, const int8_t *x8, const int *bs, const float *dx,
-                                             double (&acc)[kR]) {
+__device__ __forceinline__ void compute_step(const uint8_t *slot, int K, int it, int l, int lane, const int8_t *x8, const int *bs,
+                                             const float *dx, double (&acc)[kR]) {
     const int P = WT == 12 ? (K >> 6) : (K >> 5);
     const int p = it * LANES + l;
     if (p >= P) return;
@@ -306,7 +328,10 @@ __device__ __forceinline__ void compute_step(const WBuf<WT> &b, int K, int it, i
         const float dxv = dx[p >> 2];
 #pragma unroll
         for (int r = 0; r < kR; r++) {
-            const int4 a0 = b.w0[r], a1 = b.w1[r];
+            const int4 a0 = *reinterpret_cast<const int4 *>(slot_w0(const_cast<uint8_t *>(slot), r, lane));
+            const int4 a1 = *reinterpret_cast<const int4 *>(slot_w1(const_cast<uint8_t *>(slot), r, lane));
+            const uint32_t scv = *reinterpret_cast<const uint32_t *>(slot_sc(const_cast<uint8_t *>(slot), r, lane));
+            const uint32_t ddv = *reinterpret_cast<const uint32_t *>(slot_dd(const_cast<uint8_t *>(slot), r, lane));
             int dl = 0, dh = 0;   // dh accumulates 16 * (hi nibble) products: exact multiple of 16
             dl = __dp4a(a0.x & 0x0F0F0F0F, xa0.x, dl); dh = dp4a_us((unsigned)a0.x & 0xF0F0F0F0u, xb0.x, dh);
             dl = __dp4a(a0.y & 0x0F0F0F0F, xa0.y, dl); dh = dp4a_us((unsigned)a0.y & 0xF0F0F0F0u, xb0.y, dh);
@@ -316,10 +341,9 @@ __device__ __forceinline__ void compute_step(const WBuf<WT> &b, int K, int it, i
             dl = __dp4a(a1.y & 0x0F0F0F0F, xa1.y, dl); dh = dp4a_us((unsigned)a1.y & 0xF0F0F0F0u, xb1.y, dh);
             dl = __dp4a(a1.z & 0x0F0F0F0F, xa1.z, dl); dh = dp4a_us((unsigned)a1.z & 0xF0F0F0F0u, xb1.z, dh);
             dl = __dp4a(a1.w & 0x0F0F0F0F, xa1.w, dl); dh = dp4a_us((unsigned)a1.w & 0xF0F0F0F0u, xb1.w, dh);
-            const uint32_t scv = b.sc[r];
             const int isum = (int)(scv & 0xff) * dl + (int)((scv >> 8) & 0xff) * (dh >> 4);
             const int imin = (int)((scv >> 16) & 0xff) * b2.x + (int)(scv >> 24) * b2.y;
-            const float2 dm = __half22float2(*reinterpret_cast<const __half2 *>(&b.dd[r]));
+            const float2 dm = __half22float2(*reinterpret_cast<const __half2 *>(&ddv));
             // exact products (24-bit x <24-bit) accumulated in double: order-independent result
             acc[r] = fma((double)(dm.x * dxv), (double)isum, acc[r]);
             acc[r] = fma(-(double)(dm.y * dxv), (double)imin, acc[r]);
@@ -330,11 +354,14 @@ __device__ __forceinline__ void compute_step(const WBuf<WT> &b, int K, int it, i
         const float dxv = dx[p];
 #pragma unroll
         for (int r = 0; r < kR; r++) {
-            const int4 a0 = b.w0[r], a1 = b.w1[r];
+            const int4 a0 = *reinterpret_cast<const int4 *>(slot_w0(const_cast<uint8_t *>(slot), r, lane));
+            const int4 a1 = *reinterpret_cast<const int4 *>(slot_w1(const_cast<uint8_t *>(slot), r, lane));
+            const uint32_t half_sel = *reinterpret_cast<const uint32_t *>(slot_sc(const_cast<uint8_t *>(slot), r, lane));
+            const uint32_t ddv = *reinterpret_cast<const uint32_t *>(slot_dd(const_cast<uint8_t *>(slot), r, lane));
             int sum = 0;
             sum = __dp4a(a0.x, xa.x, sum); sum = __dp4a(a0.y, xa.y, sum); sum = __dp4a(a0.z, xa.z, sum); sum = __dp4a(a0.w, xa.w, sum);
             sum = __dp4a(a1.x, xb.x, sum); sum = __dp4a(a1.y, xb.y, sum); sum = __dp4a(a1.z, xb.z, sum); sum = __dp4a(a1.w, xb.w, sum);
-            const float dw = __half2float(__ushort_as_half((unsigned short)(b.dd[r] & 0xffff)));
+            const float dw = __half2float(__ushort_as_half((unsigned short)((half_sel ? (ddv >> 16) : ddv) & 0xffff)));
             acc[r] = fma((double)(dw * dxv), (double)sum, acc[r]);
         }
     }
@@ -362,22 +389,25 @@ __device__ __forceinline__ void gemv_body(const GemvArgs &a, const float *x_over
     const int n_steps = my_tiles > 0 ? my_tiles * nit : 0;
     auto row0_of = [&](int step) { return (t_begin + warp + (step / nit) * bg.nwarps) * TR + sub * kR; };
 
-    // weights do not depend on the activations: get the first step in flight before the prologue
+    // weights do not depend on the activations: get the first kStages-1 steps in flight before the prologue
     // (and, in the standalone kernels, before waiting for the previous kernel: PDL)
-    WBuf<WT> A, B;
-    if (n_steps > 0) issue_step<WT, LANES>(a.w, A, row0_of(0), 0, l);
+    uint8_t *ring = smem + gemv_q_bytes(WT, K) + (size_t)warp * kStages * kSlotBytes;
+#pragma unroll
+    for (int i = 0; i < kStages - 1; i++) {
+        if (i < n_steps) issue_step<WT, LANES>(a.w, ring + i * kSlotBytes, row0_of(i), i % nit, l, lane);
+        cp_async_commit();
+    }
     if (PDL) griddep_wait();
-
     int8_t *x8 = reinterpret_cast<int8_t *>(smem);
     int *bs = nullptr; float *dx = nullptr; double *red = nullptr;
     if (WT == 12) {
         bs = reinterpret_cast<int *>(smem + K);
         dx = reinterpret_cast<float *>(smem + K + (K >> 6) * 8);
-        red = reinterpret_cast<double *>(smem + gemv_smem_bytes(12, K) - 128);
+        red = reinterpret_cast<double *>(smem + gemv_q_bytes(12, K) - 128);
         gemv_prologue<12>(a, xin, norm_out_cta, PRO, K, x8, bs, dx, red, bg);
     } else {
         dx = reinterpret_cast<float *>(smem + K);
-        red = reinterpret_cast<double *>(smem + gemv_smem_bytes(8, K) - 128);
+        red = reinterpret_cast<double *>(smem + gemv_q_bytes(8, K) - 128);
         gemv_prologue<8>(a, xin, norm_out_cta, PRO, K, x8, nullptr, dx, red, bg);
     }
     block_sync(bg);
@@ -390,6 +420,15 @@ __device__ __forceinline__ void gemv_body(const GemvArgs &a, const float *x_over
     double acc[kR];
 #pragma unroll
     for (int r = 0; r < kR; r++) acc[r] = 0.0;
+    // residual epilogue: the old x[row] values of a tile are fetched when the tile STARTS, so the L2 round
+    // trip (~0.7 us) hides under the tile's dot products instead of stalling the warp at every tile end
+    float resid[kR] = {0.f, 0.f};
+    auto fetch_resid = [&](int step) {
+        if (EPI == EPI_RESID && l == 0) {
+#pragma unroll
+            for (int r = 0; r < kR; r++) { const int row = row0_of(step) + r; if (row < a.w.rows) resid[r] = __ldcg(a.out + row); }
+        }
+    };
     const unsigned long long tile_bytes = WT == 12 ? (unsigned long long)TR * ((K >> 1) + P * 4 + (K >> 8) * 4)
                                                    : (unsigned long long)TR * (K + P * 2);
     // end of a tile: reduce the lane partials, run the epilogue, reset
@@ -402,19 +441,24 @@ __device__ __forceinline__ void gemv_body(const GemvArgs &a, const float *x_over
             accf[r] = (float)acc[r];
             acc[r] = 0.0;
         }
-        if (l == 0) gemv_epilogue<kR>(a, EPI, row0_of(step), accf, emb_token, best);
+        if (l == 0) {
+            if (EPI == EPI_RESID) {                        // residual already in registers
+#pragma unroll
+                for (int r = 0; r < kR; r++) { const int row = row0_of(step) + r; if (row < a.w.rows) a.out[row] = resid[r] + accf[r]; }
+            } else gemv_epilogue<kR>(a, EPI, row0_of(step), accf, emb_token, best);
+        }
         if (progress && lane == 0) atomicAdd(progress, tile_bytes);
     };
 #pragma unroll 1
-    for (int s = 0; s < n_steps; s += 2) {
-        if (s + 1 < n_steps) issue_step<WT, LANES>(a.w, B, row0_of(s + 1), (s + 1) % nit, l);
-        compute_step<WT, LANES>(A, K, s % nit, l, x8, bs, dx, acc);
+    for (int s = 0; s < n_steps; s++) {
+        cp_async_wait<kStages - 2>();            // the group of step s has landed (this lane's own copies)
+        if (s % nit == 0) fetch_resid(s);
+        compute_step<WT, LANES>(ring + (s % kStages) * kSlotBytes, K, s % nit, l, lane, x8, bs, dx, acc);
+        // refill the slot consumed one step ago with step s + kStages - 1
+        const int nx = s + kStages - 1;
+        if (nx < n_steps) issue_step<WT, LANES>(a.w, ring + (nx % kStages) * kSlotBytes, row0_of(nx), nx % nit, l, lane);
+        cp_async_commit();
         if (s % nit == nit - 1) finish_tile(s);
-        if (s + 2 < n_steps) issue_step<WT, LANES>(a.w, A, row0_of(s + 2), (s + 2) % nit, l);
-        if (s + 1 < n_steps) {
-            compute_step<WT, LANES>(B, K, (s + 1) % nit, l, x8, bs, dx, acc);
-            if ((s + 1) % nit == nit - 1) finish_tile(s + 1);
-        }
     }
     if (bg.stamp && threadIdx.x == 0) bg.stamp[2] = global_ns();
 
@@ -434,11 +478,14 @@ __device__ __forceinline__ void gemv_body(const GemvArgs &a, const float *x_over
     }
 }
 
+// 512 threads, one CTA per SM: half as many CTAs repeat the activation prologue, and each prologue has 16
+// warps to spread its 256-element blocks over (K = 11264: 3 block iterations per warp instead of 6)
+constexpr int kGemvThreads = 512;
 template <int WT, int LANES>
-__global__ void __launch_bounds__(kThreads, 2) gemv_kernel(const GemvArgs a, const int pro, const int epi) {
+__global__ void __launch_bounds__(kGemvThreads, 1) gemv_kernel(const GemvArgs a, const int pro, const int epi) {
     extern __shared__ __align__(16) uint8_t smem[];
     griddep_launch();      // the next kernel may start launching: it prefetches its weights and then waits for us
-    gemv_body<WT, LANES, true>(a, nullptr, blockIdx.x == 0, pro, epi, smem, blockIdx.x, gridDim.x, BlockGeom{kThreads, kWarps});
+    gemv_body<WT, LANES, true>(a, nullptr, blockIdx.x == 0, pro, epi, smem, blockIdx.x, gridDim.x, BlockGeom{kGemvThreads, kGemvThreads / 32});
 }
 
 }  // namespace msx

@@ -193,6 +193,26 @@ __device__ __forceinline__ void attn_local(const AttnArgs &a, int heads, float *
     }
 }
 
+// ---- standalone fused kernel: local ring attention (all heads, every CTA) + out_proj GEMV -----------------
+// Used by the PDL-chained path for transformers whose ring is tiny (depformer: <= 64 slots): one launch
+// instead of attention + out_proj.  smem: [gemv region][ctx_s dim floats][attn scratch]
+template <int WT, int LANES, int DH>
+__global__ void __launch_bounds__(kGemvThreads, 1) gemv_local_attn_kernel(const GemvArgs g, const AttnArgs a, const int heads, const int pro,
+                                                                          const int epi, const int gemv_region) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    griddep_launch();
+    const BlockGeom bg{kGemvThreads, kGemvThreads / 32};
+    float *ctx_s = reinterpret_cast<float *>(smem + gemv_region);
+    float *scratch = ctx_s + a.dim;
+    griddep_wait();                                  // qkv comes from the previous kernel
+    attn_local<DH>(a, heads, ctx_s, scratch, blockIdx.x == 0, bg.nwarps);
+    block_sync(bg);
+    gemv_body<WT, LANES, false>(g, ctx_s, false, pro, epi, smem, blockIdx.x, gridDim.x, bg);
+}
+__host__ __device__ inline int local_attn_smem_bytes(int gemv_bytes, int dim, int dh) {
+    return (gemv_bytes + 15) / 16 * 16 + dim * 4 + (kGemvThreads / 32) * (2 * dh + 64) * 4 + 64;
+}
+
 // ---- phase dispatch -------------------------------------------------------------------------------------
 __device__ __noinline__ void gemv_phase(const GemvArgs &g, const float *x_over, bool norm_out_cta, int pro, int epi, uint8_t *smem,
                                         int cta, int n_cta, const BlockGeom bg, unsigned long long *progress) {
