@@ -58,6 +58,22 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return SO_PATH
 
 
+HOST_DIR = os.path.join(_HERE, "host")
+STS_BENCH = os.path.join(_HERE, "moshi-sts-bench")
+
+
+def build_host(force: bool = False) -> str:
+    """g++: the C++ mirror of the reference's moshi_lm_* API (libmoshi.so) and the moshi-sts --bench style tool."""
+    srcs = [os.path.join(HOST_DIR, f) for f in ("moshi_api.cpp", "moshi_api.h", "moshi_sts_bench.cpp")]
+    stale = (not os.path.exists(HOST_SO_PATH)) or (not os.path.exists(STS_BENCH)) or any(
+        os.path.getmtime(s) > min(os.path.getmtime(HOST_SO_PATH), os.path.getmtime(STS_BENCH)) for s in srcs)
+    if force or stale:
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", "-DMOSHI_BUILD", "-o", HOST_SO_PATH,
+                               srcs[0], "-L" + _HERE, "-lmoshi_b200", "-Wl,-rpath,$ORIGIN"])
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", STS_BENCH, srcs[2], "-L" + _HERE, "-lmoshi", "-lmoshi_b200", "-Wl,-rpath,$ORIGIN"])
+    return HOST_SO_PATH
+
+
 _lib = None
 
 

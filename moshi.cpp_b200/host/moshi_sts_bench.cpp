@@ -1,0 +1,59 @@
+// moshi_sts_bench.cpp — the `--bench` entry point of the reference's speech-to-speech tools
+// (tools/moshi-sts.cpp:731-808, tools/personaplex.cpp) reduced to the LM path: the Mimi encoder/decoder and
+// SDL/FFmpeg I/O are out of scope, so user audio codes are synthetic (seeded LCG) instead of encoded silence.
+//   moshi-sts-bench <model.gguf> <config.json> [frames=125] [device=0] [--print-tokens]
+// Uses only the moshi_lm_* API (host/moshi_api.h), exactly like the reference tool uses include/moshi/moshi.h.
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "moshi_api.h"
+
+int main(int argc, char **argv) {
+    if (argc < 3) { fprintf(stderr, "usage: %s model.gguf config.json [frames] [device] [--print-tokens]\n", argv[0]); return 2; }
+    const int frames = argc > 3 ? atoi(argv[3]) : 125;
+    const int device = argc > 4 ? atoi(argv[4]) : 0;
+    bool print_tokens = false;
+    for (int i = 3; i < argc; i++) if (!strcmp(argv[i], "--print-tokens")) print_tokens = true;
+
+    moshi_config_t config;
+    if (moshi_get_config(&config, argv[2]) != 0) return 1;
+    moshi_context_t *moshi = moshi_alloc_b200(device);
+    moshi_lm_t *lm = moshi_lm_from_files(moshi, &config, argv[1]);
+    if (!lm) { fprintf(stderr, "error: could not open %s\n", argv[1]); return 1; }
+    if (moshi_lm_load(lm) != 0) { fprintf(stderr, "error: %s\n", moshi_b200_last_error()); return 1; }
+    moshi_lm_gen_t *gen = moshi_lm_generator(lm);
+    if (config.model_type == "personaplex") {
+        std::deque<std::vector<int16_t>> voice;                      // 4 frames of synthetic voice-prompt codes
+        for (int f = 0; f < 4; f++) { std::vector<int16_t> c(8); for (int j = 0; j < 8; j++) c[j] = (int16_t)((f * 131 + j * 17) % config.card); voice.push_back(c); }
+        moshi_lm_personaplex_audio_prompt(gen, voice);
+        moshi_lm_personaplex_system_prompt_tokens(gen, {5, 17, 99, 250});
+    }
+    moshi_lm_start(moshi, gen, 0.f, 0.f);                            // temperature 0 = greedy
+
+    const int n_user = (int)(config.n_q - (config.model_type == "personaplex" ? 8 : config.dep_q));
+    std::vector<int16_t> user(n_user), audio;
+    uint32_t lcg = 42;
+    int text = -1, emitted = 0;
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int f = 0; f < frames; f++) {
+        for (int j = 0; j < n_user; j++) { lcg = lcg * 1664525u + 1013904223u; user[j] = (int16_t)((lcg >> 8) % config.card); }
+        moshi_lm_send2(gen, user);
+        if (config.dep_q > 0) {
+            const int ok = moshi_lm_receive(gen, text, audio);
+            if (ok) emitted++;
+            if (print_tokens) { printf("%d %d %d", f, ok, ok ? text : -1); if (ok) for (int16_t a : audio) printf(" %d", (int)a); printf("\n"); }
+        } else {
+            float vad = 0.f;
+            moshi_lm_receive2(gen, text, vad);
+            if (print_tokens) printf("%d %d %.6f\n", f, text, vad);
+        }
+    }
+    const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    fprintf(stderr, "frames %d emitted %d  %.2f frames/s (%.1fx real time at 12.5 Hz)\n", frames, emitted, frames / sec, frames / sec / 12.5);
+    unref(gen); unref(lm); unref(moshi);
+    return 0;
+}

@@ -1,0 +1,85 @@
+"""The C++ mirror of the reference's moshi_lm_* API (moshi.cpp_b200/host) exercised through the
+moshi-sts --bench style tool, which only uses that API (like tools/moshi-sts.cpp uses include/moshi/moshi.h)."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from moshi_cpp_b200 import binding as msx, configs
+
+PROMPT_TOKENS = [3, 948, 243, 1178, 546, 1736, 1030, 1978, 2008, 430, 1268, 381, 1611, 1095, 1495, 56, 472]   # lm.h:983-987
+
+
+@pytest.fixture(scope="module")
+def tool():
+    msx.build_host()
+    assert os.path.exists(msx.STS_BENCH)
+    return msx.STS_BENCH
+
+
+def write_config(path, cfg):
+    with open(path, "w") as f:
+        json.dump(configs.to_config_json(cfg), f)
+
+
+def lcg_user_codes(n_frames, n_user, card):
+    lcg, out = 42, []
+    for _ in range(n_frames):
+        row = []
+        for _ in range(n_user):
+            lcg = (lcg * 1664525 + 1013904223) & 0xFFFFFFFF
+            row.append((lcg >> 8) % card)
+        out.append(row)
+    return out
+
+
+def test_tool_error_paths(tool, gguf_for, tmp_path):
+    path, cfg = gguf_for("tiny", "q4_k")
+    cj = tmp_path / "config.json"; write_config(cj, cfg)
+    r = subprocess.run([tool, str(tmp_path / "missing.gguf"), str(cj)], capture_output=True, text=True)
+    assert r.returncode == 1 and "could not open" in r.stderr          # reference: moshi_lm_from_files -> NULL
+    r = subprocess.run([tool, path, str(tmp_path / "missing.json")], capture_output=True, text=True)
+    assert r.returncode == 1 and "failed to open" in r.stderr           # reference message (config.h:160-163)
+    if msx.lib().msx_device_count() == 0:
+        r = subprocess.run([tool, path, str(cj), "4"], capture_output=True, text=True)
+        assert r.returncode == 1 and "error:" in r.stderr               # no CPU fallback
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("preset", ["tiny", "tiny_pplex", "tiny_stt"])
+def test_cpp_api_matches_c_abi(tool, gguf_for, tmp_path, preset):
+    quant = "q8_0" if preset == "tiny_stt" else "q4_k"
+    path, cfg = gguf_for(preset, quant)
+    cj = tmp_path / "config.json"; write_config(cj, cfg)
+    frames = 40
+    r = subprocess.run([tool, path, str(cj), str(frames), "0", "--print-tokens"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    lines = [l.split() for l in r.stdout.strip().splitlines()]
+    assert len(lines) == frames
+    # the same thing through the C ABI from python
+    gm = msx.Model(path, cfg); gs = msx.Stream(gm); gg = msx.Gen(gs)
+    pplex = cfg["model_type"] == "personaplex"
+    if pplex:   # moshi_lmgen_step_system_prompts (lm.h:1120-1134): voice codes, 6 silence, text prompt, 6 silence
+        def row(text=None, codes=None):
+            t = list(PROMPT_TOKENS)
+            if text is not None: t[0] = text
+            if codes is not None: t[1:9] = codes
+            return t
+        for f in range(4):
+            gg.step(row(codes=[(f * 131 + j * 17) % cfg["card"] for j in range(8)]))
+        for _ in range(6): gg.step(row())
+        for tok in (5, 17, 99, 250): gg.step(row(text=tok))
+        for _ in range(6): gg.step(row())
+    n_user = cfg["n_q"] - (8 if pplex else cfg["dep_q"])
+    users = lcg_user_codes(frames, n_user, cfg["card"])
+    for f in range(frames):
+        ok, text, audio = gg.step(users[f])
+        if cfg["dep_q"] > 0:
+            assert int(lines[f][1]) == ok, f"frame {f}"
+            if ok:
+                assert int(lines[f][2]) == text and [int(v) for v in lines[f][3:]] == list(audio), f"frame {f}"
+        else:
+            if ok: assert int(lines[f][1]) == text
+            assert abs(float(lines[f][2]) - gs.vad()) < 1e-5
