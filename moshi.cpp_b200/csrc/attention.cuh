@@ -35,7 +35,9 @@ struct AttnArgs {
     int32_t cap = 0;
     int32_t dim = 0;
     int32_t max_period = 0;         // 0 = no RoPE
+    int32_t small_ctx = 0;          // n_valid <= small_ctx: rank 0 of the cluster handles the head alone
     const float *rope_freq = nullptr;  // [DH/2] expf(-logf(max_period)*j/half), computed on the host at load
+    const float *rope_cs = nullptr;    // optional [DH]: cos | sin of this step's position, written once per frame by the embed kernel
 };
 
 constexpr int kAttnMaxSplit = 8;
@@ -54,13 +56,20 @@ __global__ void __launch_bounds__(kThreads) attn_kernel(const AttnArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
     constexpr int LPS = DH / 8;             // lanes per slot (8 dims = 16 B of bf16 each)
     constexpr int NG = kThreads / LPS;      // slots in flight per CTA iteration
-    const int S = gridDim.x, c = blockIdx.x, h = blockIdx.y;
+    griddep_launch();
+    griddep_wait();        // qkv comes from the previous kernel (PDL)
+    int S = gridDim.x, c = blockIdx.x;
+    const int h = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = uniform_warp_id();
     const int cap = a.cap;
     const int pos = a.pos_const >= 0 ? a.pos_const : a.ctrl->offset;
     const int slot = pos % cap;
     const int n_valid = (pos >= cap - 1) ? cap : pos + 1;
     const int per = (cap + S - 1) / S + 1;
+    // short context: the split is not worth three cluster barriers — rank 0 handles the head alone
+    // (uniform decision across the cluster, so nobody waits at a barrier)
+    const bool use_cluster = CLUSTER && n_valid > min(a.small_ctx, per - 1);
+    if (CLUSTER && !use_cluster) { if (c != 0) return; S = 1; c = 0; }
 
     double *x_sum = reinterpret_cast<double *>(smem);                  // [kAttnMaxSplit] cluster exchange: row sums
     double *dred = x_sum + kAttnMaxSplit;                              // [8] block reduce scratch
@@ -74,8 +83,6 @@ __global__ void __launch_bounds__(kThreads) attn_kernel(const AttnArgs a) {
     float *sc_s = x_max + kAttnMaxSplit;                               // [per]
     (void)per;
 
-    griddep_launch();
-    griddep_wait();        // qkv comes from the previous kernel (PDL)
     // ---- 1. RoPE (interleaved pairs -> [re half | im half]) and the new K/V row -------------------
     const float *q = a.qkv + h * DH, *k = a.qkv + a.dim + h * DH, *v = a.qkv + 2 * a.dim + h * DH;
     if (tid < DH / 2) {
@@ -84,8 +91,11 @@ __global__ void __launch_bounds__(kThreads) attn_kernel(const AttnArgs a) {
         if (a.max_period) {
             // ggml_timestep_embedding: freq = expf(-logf(max_period) * j / half); arg = pos * freq.
             // cos/sin through double: correctly rounded fp32 irrespective of the libm (order-independent parity)
-            const float arg = (float)pos * a.rope_freq[j];
-            cs = (float)cos((double)arg); sn = (float)sin((double)arg);
+            if (a.rope_cs) { cs = __ldcg(a.rope_cs + j); sn = __ldcg(a.rope_cs + DH / 2 + j); }
+            else {
+                const float arg = (float)pos * a.rope_freq[j];
+                cs = (float)cos((double)arg); sn = (float)sin((double)arg);
+            }
         }
         const float qr = q[2 * j], qi = q[2 * j + 1], kr = k[2 * j], ki = k[2 * j + 1];
         float qo_r, qo_i, ko_r, ko_i;
@@ -149,7 +159,7 @@ __global__ void __launch_bounds__(kThreads) attn_kernel(const AttnArgs a) {
     __syncthreads();
 
     float gmax = cmax;
-    if (CLUSTER) {
+    if (use_cluster) {
         cg::cluster_group cl = cg::this_cluster();
         cl.sync();      // every CTA of the cluster has started (its shared memory exists) before remote writes
         if (tid < S) cl.map_shared_rank(x_max, tid)[c] = cmax;     // scatter my max to every CTA of the cluster
@@ -169,7 +179,7 @@ __global__ void __launch_bounds__(kThreads) attn_kernel(const AttnArgs a) {
 #pragma unroll
     for (int w = 0; w < kWarps; w++) csum += dred[w];
     double gsum = csum;
-    if (CLUSTER) {
+    if (use_cluster) {
         cg::cluster_group cl = cg::this_cluster();
         if (tid < S) cl.map_shared_rank(x_sum, tid)[c] = csum;
         cl.sync();
@@ -199,7 +209,7 @@ __global__ void __launch_bounds__(kThreads) attn_kernel(const AttnArgs a) {
     if (tid < DH) {
         for (int gg = 0; gg < NG; gg++) tot += part[gg * DH + tid];
     }
-    if (CLUSTER) {
+    if (use_cluster) {
         cg::cluster_group cl = cg::this_cluster();
         if (tid < DH) cl.map_shared_rank(x_ctx, 0)[c * DH + tid] = tot;    // gather partials in rank 0
         cl.sync();

@@ -6,6 +6,7 @@
 #include <climits>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -477,6 +478,7 @@ struct msx_stream {
     uint16_t *kc = nullptr, *vc = nullptr, *dkc = nullptr, *dvc = nullptr;
     float *x = nullptr, *qkv = nullptr, *ctx = nullptr, *gate = nullptr, *tout = nullptr, *text_logits = nullptr;
     float *dx = nullptr, *dqkv = nullptr, *dctx = nullptr, *dgate = nullptr, *audio_logits = nullptr, *vad_logits = nullptr;
+    float *rope_cs = nullptr;        // [Dh] cos | sin of the current temporal position
     cudaGraphExec_t g_temporal = nullptr, g_depformer = nullptr;
     int launches_temporal = 0, launches_depformer = 0;
     // persistent phase-program kernel (megakernel.cuh)
@@ -531,6 +533,8 @@ void enqueue_layer(Launcher &L, const msx_stream *s, const LayerW &lw, int w, bo
     a.qkv = qkv; a.ctx = ctx; a.ctrl = s->ctrl; a.pos_const = pos_const; a.cap = cap; a.dim = dim;
     a.max_period = temporal ? c.max_period : c.dep_max_period;
     a.rope_freq = temporal ? m->rope_freq : m->dep_rope_freq;
+    a.rope_cs = (temporal && c.max_period) ? s->rope_cs : nullptr;
+    { const char *e = getenv("MSX_ATTN_SMALL"); a.small_ctx = e ? atoi(e) : 32; }
     const size_t lstride = (size_t)cap * dim;
     a.kc = (temporal ? s->kc : s->dkc) + (size_t)layer * lstride;
     a.vc = (temporal ? s->vc : s->dvc) + (size_t)layer * lstride;
@@ -556,6 +560,7 @@ void enqueue_temporal(Launcher &L, const msx_stream *s) {
     const msx_model *m = s->m; const msx_config &c = m->cfg;
     EmbedArgs e;
     e.tables = m->d_emb; e.n_tables = c.n_q + 1; e.dim = c.dim; e.ctrl = s->ctrl; e.x = s->x;
+    if (c.max_period) { e.rope_cs = s->rope_cs; e.rope_freq = m->rope_freq; e.dh = c.dim / c.num_heads; }
     L.fam = FAM_EMBED; L.begin();
     L.launch_pdl(embed_kernel, dim3((c.dim + kThreads - 1) / kThreads), dim3(kThreads), 0, e);
     L.check();
@@ -733,6 +738,7 @@ extern "C" int msx_stream_create_ex(msx_model *m, int context_override, int flag
     if (int e = salloc(s.get(), (void **)&s->gate, (size_t)m->hidden * 4)) return e;
     if (int e = salloc(s.get(), (void **)&s->tout, (size_t)c.dim * 4)) return e;
     if (int e = salloc(s.get(), (void **)&s->text_logits, (size_t)c.text_card * 4)) return e;
+    if (int e = salloc(s.get(), (void **)&s->rope_cs, (size_t)(c.dim / c.num_heads) * 4)) return e;
     if (c.dep_q > 0) {
         if (int e = salloc(s.get(), (void **)&s->dkc, dkv_elems(s.get()) * 2)) return e;
         if (int e = salloc(s.get(), (void **)&s->dvc, dkv_elems(s.get()) * 2)) return e;

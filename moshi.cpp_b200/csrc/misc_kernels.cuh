@@ -13,11 +13,21 @@ struct EmbedArgs {
     int32_t dim = 0;
     const Ctrl *ctrl = nullptr;
     float *x = nullptr;
+    // RoPE table of this step (cos | sin, [dh]) computed once per frame instead of once per attention CTA
+    float *rope_cs = nullptr;
+    const float *rope_freq = nullptr;
+    int32_t dh = 0;
 };
 
 __device__ __forceinline__ void embed_body(const EmbedArgs &a, int cta, int n_cta, int nthr) {
     const Ctrl *c = a.ctrl;
     const int32_t *toks = c->feed_n ? c->feed + (size_t)(c->frame % c->feed_n) * c->n_in : c->tokens;
+    if (cta == 0 && a.rope_cs && (int)threadIdx.x < a.dh / 2) {
+        // ggml_timestep_embedding on the f32 position; cos/sin through double (see attention.cuh)
+        const float arg = (float)c->offset * a.rope_freq[threadIdx.x];
+        a.rope_cs[threadIdx.x] = (float)cos((double)arg);
+        a.rope_cs[a.dh / 2 + threadIdx.x] = (float)sin((double)arg);
+    }
     for (int i = cta * nthr + threadIdx.x; i < a.dim; i += n_cta * nthr) {
         float acc = 0.f;
         for (int t = 0; t < a.n_tables; t++) {
