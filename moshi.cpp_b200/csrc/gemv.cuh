@@ -286,26 +286,45 @@ __device__ __forceinline__ uint8_t *slot_w1(uint8_t *slot, int r, int lane) { re
 __device__ __forceinline__ uint8_t *slot_sc(uint8_t *slot, int r, int lane) { return slot + 32 * kR * 32 + (r * 32 + lane) * 4; }
 __device__ __forceinline__ uint8_t *slot_dd(uint8_t *slot, int r, int lane) { return slot + 32 * kR * 36 + (r * 32 + lane) * 4; }
 
+// position of a step inside the warp's work list, advanced incrementally (no div/mod in the loop)
+struct StepPos {
+    int it;            // K-iteration inside the tile
+    int row0;          // first row of the lane group's rows in this tile
+};
+template <int LANES>
+__device__ __forceinline__ void advance(StepPos &sp, int nit, int row_stride) {
+    if (++sp.it == nit) { sp.it = 0; sp.row0 += row_stride; }
+}
+
+__device__ __forceinline__ void cp_async16_s(unsigned smem_addr, const void *gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async4_s(unsigned smem_addr, const void *gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr), "l"(gsrc) : "memory");
+}
+
+// slot_u32: shared-space address of the slot; lane-private offsets: w0 at (r*32+lane)*16, w1 at +1024,
+// sc at 2048 + (r*32+lane)*4, dd at 2304 + (r*32+lane)*4
 template <int WT, int LANES>
-__device__ __forceinline__ void issue_step(const QLinear &w, uint8_t *slot, int r0, int it, int l, int lane) {
-    const int P = WT == 12 ? (w.K >> 6) : (w.K >> 5);
-    const int p = it * LANES + l;
+__device__ __forceinline__ void issue_step(const QLinear &w, unsigned slot_u32, uint8_t *slot, const StepPos &sp, int l, int lane, int P) {
+    const int p = sp.it * LANES + l;
     if (p < P) {
-        const int gsz = min(LANES, P - it * LANES);
+        const int gsz = min(LANES, P - sp.it * LANES);
         const size_t row_qs = WT == 12 ? (size_t)(w.K >> 1) : (size_t)w.K;
 #pragma unroll
         for (int r = 0; r < kR; r++) {
-            const int row = min(r0 + r, w.rows - 1);
-            const uint8_t *q = w.qs + (size_t)row * row_qs + (size_t)it * (LANES * 32) + l * 16;
-            cp_async16(slot_w0(slot, r, lane), q);
-            cp_async16(slot_w1(slot, r, lane), q + gsz * 16);
+            const int row = min(sp.row0 + r, w.rows - 1);
+            const uint8_t *q = w.qs + (size_t)row * row_qs + (size_t)(sp.it * (LANES * 32) + l * 16);
+            const unsigned o16 = slot_u32 + (r * 32 + lane) * 16, o4 = slot_u32 + 32 * kR * 32 + (r * 32 + lane) * 4;
+            cp_async16_s(o16, q);
+            cp_async16_s(o16 + 32 * kR * 16, q + gsz * 16);
             if (WT == 12) {
-                cp_async4(slot_sc(slot, r, lane), w.sc + (size_t)row * P + p);
-                cp_async4(slot_dd(slot, r, lane), reinterpret_cast<const uint32_t *>(w.dd) + (size_t)row * (w.K >> 8) + (p >> 2));
+                cp_async4_s(o4, w.sc + (size_t)row * P + p);
+                cp_async4_s(o4 + 32 * kR * 4, reinterpret_cast<const uint32_t *>(w.dd) + (size_t)row * (w.K >> 8) + (p >> 2));
             } else {
                 // fp16 scale: 4-byte aligned copy of the pair containing it
                 const uint16_t *d = reinterpret_cast<const uint16_t *>(w.dd) + (size_t)row * P + p;
-                cp_async4(slot_dd(slot, r, lane), reinterpret_cast<const void *>(reinterpret_cast<uintptr_t>(d) & ~(uintptr_t)3));
+                cp_async4_s(o4 + 32 * kR * 4, reinterpret_cast<const void *>(reinterpret_cast<uintptr_t>(d) & ~(uintptr_t)3));
                 *reinterpret_cast<uint32_t *>(slot_sc(slot, r, lane)) = (uint32_t)((reinterpret_cast<uintptr_t>(d) >> 1) & 1);   // which half
             }
         }
@@ -387,17 +406,21 @@ __device__ __forceinline__ void gemv_body(const GemvArgs &a, const float *x_over
     const int t_end = (int)((long long)(cta + 1) * n_tiles / n_cta);
     const int my_tiles = (t_end - t_begin - warp + bg.nwarps - 1) / bg.nwarps;      // tiles t_begin + warp + i * nwarps
     const int n_steps = my_tiles > 0 ? my_tiles * nit : 0;
-    auto row0_of = [&](int step) { return (t_begin + warp + (step / nit) * bg.nwarps) * TR + sub * kR; };
+    const int row_stride = bg.nwarps * TR;                                          // rows between consecutive tiles of this warp
+    StepPos cons{0, (t_begin + warp) * TR + sub * kR};                              // step being computed
+    StepPos prod = cons;                                                            // step being fetched
 
     // weights do not depend on the activations: get the first kStages-1 steps in flight before the prologue
     // (and, in the standalone kernels, before waiting for the previous kernel: PDL)
     uint8_t *ring = smem + gemv_q_bytes(WT, K) + (size_t)warp * kStages * kSlotBytes;
+    const unsigned ring_u32 = (unsigned)__cvta_generic_to_shared(ring);
 #pragma unroll
     for (int i = 0; i < kStages - 1; i++) {
-        if (i < n_steps) issue_step<WT, LANES>(a.w, ring + i * kSlotBytes, row0_of(i), i % nit, l, lane);
+        if (i < n_steps) { issue_step<WT, LANES>(a.w, ring_u32 + i * kSlotBytes, ring + i * kSlotBytes, prod, l, lane, P); advance<LANES>(prod, nit, row_stride); }
         cp_async_commit();
     }
     if (PDL) griddep_wait();
+
     int8_t *x8 = reinterpret_cast<int8_t *>(smem);
     int *bs = nullptr; float *dx = nullptr; double *red = nullptr;
     if (WT == 12) {
@@ -423,16 +446,16 @@ __device__ __forceinline__ void gemv_body(const GemvArgs &a, const float *x_over
     // residual epilogue: the old x[row] values of a tile are fetched when the tile STARTS, so the L2 round
     // trip (~0.7 us) hides under the tile's dot products instead of stalling the warp at every tile end
     float resid[kR] = {0.f, 0.f};
-    auto fetch_resid = [&](int step) {
+    auto fetch_resid = [&]() {
         if (EPI == EPI_RESID && l == 0) {
 #pragma unroll
-            for (int r = 0; r < kR; r++) { const int row = row0_of(step) + r; if (row < a.w.rows) resid[r] = __ldcg(a.out + row); }
+            for (int r = 0; r < kR; r++) { const int row = cons.row0 + r; if (row < a.w.rows) resid[r] = __ldcg(a.out + row); }
         }
     };
     const unsigned long long tile_bytes = WT == 12 ? (unsigned long long)TR * ((K >> 1) + P * 4 + (K >> 8) * 4)
                                                    : (unsigned long long)TR * (K + P * 2);
     // end of a tile: reduce the lane partials, run the epilogue, reset
-    auto finish_tile = [&](int step) {
+    auto finish_tile = [&]() {
         float accf[kR];
 #pragma unroll
         for (int r = 0; r < kR; r++) {
@@ -444,21 +467,25 @@ __device__ __forceinline__ void gemv_body(const GemvArgs &a, const float *x_over
         if (l == 0) {
             if (EPI == EPI_RESID) {                        // residual already in registers
 #pragma unroll
-                for (int r = 0; r < kR; r++) { const int row = row0_of(step) + r; if (row < a.w.rows) a.out[row] = resid[r] + accf[r]; }
-            } else gemv_epilogue<kR>(a, EPI, row0_of(step), accf, emb_token, best);
+                for (int r = 0; r < kR; r++) { const int row = cons.row0 + r; if (row < a.w.rows) a.out[row] = resid[r] + accf[r]; }
+            } else gemv_epilogue<kR>(a, EPI, cons.row0, accf, emb_token, best);
         }
         if (progress && lane == 0) atomicAdd(progress, tile_bytes);
     };
 #pragma unroll 1
     for (int s = 0; s < n_steps; s++) {
         cp_async_wait<kStages - 2>();            // the group of step s has landed (this lane's own copies)
-        if (s % nit == 0) fetch_resid(s);
-        compute_step<WT, LANES>(ring + (s % kStages) * kSlotBytes, K, s % nit, l, lane, x8, bs, dx, acc);
+        if (cons.it == 0) fetch_resid();
+        compute_step<WT, LANES>(ring + (s & (kStages - 1)) * kSlotBytes, K, cons.it, l, lane, x8, bs, dx, acc);
         // refill the slot consumed one step ago with step s + kStages - 1
-        const int nx = s + kStages - 1;
-        if (nx < n_steps) issue_step<WT, LANES>(a.w, ring + (nx % kStages) * kSlotBytes, row0_of(nx), nx % nit, l, lane);
+        if (s + kStages - 1 < n_steps) {
+            const int slot = (s + kStages - 1) & (kStages - 1);
+            issue_step<WT, LANES>(a.w, ring_u32 + slot * kSlotBytes, ring + slot * kSlotBytes, prod, l, lane, P);
+            advance<LANES>(prod, nit, row_stride);
+        }
         cp_async_commit();
-        if (s % nit == nit - 1) finish_tile(s);
+        if (cons.it == nit - 1) finish_tile();
+        advance<LANES>(cons, nit, row_stride);
     }
     if (bg.stamp && threadIdx.x == 0) bg.stamp[2] = global_ns();
 
