@@ -101,6 +101,13 @@ MSX_API int msx_step_depformer(msx_stream *s, int32_t text_token, const int32_t 
 /* Fused frame: temporal -> greedy text -> depformer with a single host synchronisation.
  * out_tokens[1 + dep_q] = {text, audio...}. */
 MSX_API int msx_step(msx_stream *s, const int32_t *tokens, int32_t *out_tokens);
+/* Sampling (moshi_sample_token, sampling.h:46-64).  temp <= 0 = greedy (the default); temp > 0 = softmax(l/temp),
+ * top-k, multinomial by arg-max of p_j / e_j.  The Exp(1) draws e are an INPUT: the reference draws them on the
+ * host with libc rand() (context.h:464-480); msx_gen_step does the same, tests feed fixed numbers.
+ * set_sampling re-captures the stream's graphs; top_k <= 256.  set_noise must precede every sampled step:
+ * noise_text[min(top_k_text, text_card)], noise_audio[dep_q][min(top_k_audio, card)], candidate order = descending p. */
+MSX_API int msx_stream_set_sampling(msx_stream *s, float temp_text, float temp_audio, int top_k_text, int top_k_audio);
+MSX_API int msx_stream_set_noise(msx_stream *s, const float *noise_text, const float *noise_audio);
 /* STT VAD head (lm.h:966-976): softmax(extra_heads[2] . transformer_out)[0]; 0 if < 3 extra heads */
 MSX_API int msx_vad(msx_stream *s, float *vad);
 
@@ -139,6 +146,8 @@ MSX_API int msx_gen_create(msx_stream *s, int delay_steps, msx_gen **out);
 typedef int (*msx_step_fn)(void *user, const int32_t *tokens, int depformer_replace_tokens, int32_t *out);
 MSX_API int msx_gen_create_with_callback(const msx_config *cfg, int delay_steps, msx_step_fn fn, void *user, msx_gen **out);
 MSX_API void msx_gen_free(msx_gen *g);
+/* srand() for the Exp(1) draws of sampled generation (the reference never seeds except in --bench: srand(0)) */
+MSX_API void msx_gen_seed(msx_gen *g, unsigned seed);
 MSX_API int msx_gen_step(msx_gen *g, const int32_t *in_tokens, int n_in, int depformer_replace_tokens,
                          int32_t *out_text, int32_t *out_audio);
 MSX_API int msx_gen_offset(const msx_gen *g);

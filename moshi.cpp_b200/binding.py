@@ -104,6 +104,9 @@ def lib():
     L.msx_step_depformer.argtypes = [vp, C.c_int32, vp, vp, vp]
     L.msx_step.argtypes = [vp, vp, vp]
     L.msx_vad.argtypes = [vp, C.POINTER(C.c_float)]
+    L.msx_stream_set_sampling.argtypes = [vp, C.c_float, C.c_float, C.c_int, C.c_int]
+    L.msx_stream_set_noise.argtypes = [vp, vp, vp]
+    L.msx_gen_seed.argtypes = [vp, C.c_uint]
     L.msx_run_resident.argtypes = [vp, vp, C.c_int, C.c_int, vp, C.POINTER(C.c_float)]
     L.msx_stream_launches_per_frame.argtypes = [vp]
     L.msx_profile_frame.argtypes = [vp, vp, vp, vp, vp, C.c_int]
@@ -226,6 +229,13 @@ class Stream:
         out = np.empty(1 + cfg["dep_q"], dtype=np.int32)
         _check(lib().msx_step(self.h, _p(tok), _p(out)))
         return out
+
+    def set_sampling(self, temp_text, temp_audio, top_k_text=25, top_k_audio=250):
+        _check(lib().msx_stream_set_sampling(self.h, temp_text, temp_audio, top_k_text, top_k_audio))
+
+    def set_noise(self, noise_text, noise_audio):
+        nt = np.ascontiguousarray(noise_text, dtype=np.float32); na = np.ascontiguousarray(noise_audio, dtype=np.float32)
+        _check(lib().msx_stream_set_noise(self.h, _p(nt), _p(na)))
 
     def vad(self) -> float:
         v = C.c_float(0)

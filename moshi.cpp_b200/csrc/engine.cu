@@ -19,6 +19,7 @@
 #include "gguf_file.h"
 #include "megakernel.cuh"
 #include "misc_kernels.cuh"
+#include "sample.cuh"
 
 using namespace msx;
 
@@ -481,6 +482,12 @@ struct msx_stream {
     float *rope_cs = nullptr;        // [Dh] cos | sin of the current temporal position
     cudaGraphExec_t g_temporal = nullptr, g_depformer = nullptr;
     int launches_temporal = 0, launches_depformer = 0;
+    // sampling (sampling.h:46-64): temperature <= 0 = greedy; noise = Exp(1) draws supplied by the host per frame
+    float temp_text = 0.f, temp_audio = 0.f;
+    int top_k_text = 25, top_k_audio = 250;
+    float *d_noise = nullptr, *h_noise = nullptr, *d_probs = nullptr;
+    int noise_floats = 0;
+    bool noise_fresh = false;
     // persistent phase-program kernel (megakernel.cuh)
     int flags = 0;
     Phase *d_dep_prog = nullptr;
@@ -499,6 +506,7 @@ struct msx_stream {
         if (h_in) cudaFreeHost(h_in);
         if (h_out) cudaFreeHost(h_out);
         if (h_err) cudaFreeHost(h_err);
+        if (h_noise) cudaFreeHost(h_noise);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         if (st) cudaStreamDestroy(st);
@@ -571,6 +579,14 @@ void enqueue_temporal(Launcher &L, const msx_stream *s) {
     g.w = m->text_linear; g.x = s->x; g.alpha = m->out_norm; g.norm_out = s->tout; g.out = s->text_logits;
     g.key = &s->ctrl->text_key;
     L.gemv(g, PRO_RMS, EPI_ARGMAX, FAM_TEXT_HEAD);
+    if (s->temp_text > 0.f) {      // moshi_sample_token: softmax(l / temp) -> top-k -> p / Exp(1) -> argmax
+        SampleArgs sa;
+        sa.logits = s->text_logits; sa.n = c.text_card; sa.k = std::min(std::min(s->top_k_text, c.text_card), kSampleMaxK);
+        sa.inv_temp = 1.f / s->temp_text; sa.noise = s->d_noise; sa.key = &s->ctrl->text_key; sa.probs = s->d_probs;
+        L.fam = FAM_TEXT_HEAD; L.begin();
+        L.launch_pdl(sample_kernel, dim3(1), dim3(kSampleThreads), 0, sa);
+        L.check();
+    }
     L.fam = FAM_FINALIZE;
     L.launch_pdl(finalize_temporal_kernel, dim3(1), dim3(32), 0, s->ctrl, c.dep_q > 0 ? 1 : 0);
     L.check();
@@ -594,6 +610,15 @@ void enqueue_depformer(Launcher &L, const msx_stream *s) {
         h.ctrl = s->ctrl;
         h.w = m->linears[k]; h.x = s->dx; h.out = s->audio_logits + (size_t)k * c.card; h.key = &s->ctrl->audio_key[k];
         L.gemv(h, PRO_PLAIN, EPI_ARGMAX, FAM_DEP_HEAD);
+        if (s->temp_audio > 0.f) {
+            const int kk = std::min(std::min(s->top_k_audio, c.card), kSampleMaxK);
+            SampleArgs sa;
+            sa.logits = h.out; sa.n = c.card; sa.k = kk; sa.inv_temp = 1.f / s->temp_audio;
+            sa.noise = s->d_noise + kSampleMaxK + (size_t)k * kSampleMaxK; sa.key = &s->ctrl->audio_key[k]; sa.probs = s->d_probs;
+            L.fam = FAM_DEP_HEAD; L.begin();
+            L.launch_pdl(sample_kernel, dim3(1), dim3(kSampleThreads), 0, sa);
+            L.check();
+        }
     }
     L.fam = FAM_DEP_FINALIZE;
     L.launch_pdl(finalize_depformer_kernel, dim3(1), dim3(64), 0, s->ctrl, (int)c.dep_q);
@@ -709,6 +734,8 @@ int set_smem_attrs() {
 
 }  // namespace
 
+static int build_graphs(msx_stream *sp);
+
 extern "C" int msx_stream_create(msx_model *m, int context_override, msx_stream **out) {
     return msx_stream_create_ex(m, context_override, 0, out);
 }
@@ -750,6 +777,10 @@ extern "C" int msx_stream_create_ex(msx_model *m, int context_override, int flag
     }
     if (c.extra_heads > 0)
         if (int e = salloc(s.get(), (void **)&s->vad_logits, 64 * 4)) return e;
+    s->noise_floats = kSampleMaxK * (1 + MSX_MAX_STEPS);
+    if (int e = salloc(s.get(), (void **)&s->d_noise, (size_t)s->noise_floats * 4)) return e;
+    if (int e = salloc(s.get(), (void **)&s->d_probs, (size_t)std::max(c.text_card, c.card) * 4)) return e;
+    CU(cudaMallocHost((void **)&s->h_noise, (size_t)s->noise_floats * 4));
     // ctrl: n_in, no overrides
     Ctrl hc;
     memset(&hc, 0, sizeof(hc));
@@ -758,10 +789,24 @@ extern "C" int msx_stream_create_ex(msx_model *m, int context_override, int flag
     for (int i = 0; i < 40; i++) hc.force[i] = INT32_MIN;
     CU(cudaMemcpy(s->ctrl, &hc, sizeof(hc), cudaMemcpyHostToDevice));
 
+    if (int e = build_graphs(s.get())) return e;
+    CU(cudaStreamSynchronize(s->st));
+    *out = s.release();
+    return 0;
+}
+
+static int build_graphs(msx_stream *sp) {
+    struct Holder { msx_stream *p; msx_stream *get() const { return p; } msx_stream *operator->() const { return p; } } s{sp};
+    msx_model *m = sp->m;
+    const msx_config &c = m->cfg;
+    const int flags = sp->flags;
+    if (sp->g_temporal) { cudaGraphExecDestroy(sp->g_temporal); sp->g_temporal = nullptr; }
+    if (sp->g_depformer) { cudaGraphExecDestroy(sp->g_depformer); sp->g_depformer = nullptr; }
     if (int e = capture(s.get(), [&](Launcher &L) { enqueue_temporal(L, s.get()); }, &s->g_temporal, &s->launches_temporal)) return e;
     if (c.dep_q > 0) {
         // persistent phase-program kernel for the depformer chain: opt-in (measured slower than PDL-chained launches on B200)
-        const bool want_mega = (flags & MSX_STREAM_PERSISTENT_DEPFORMER) && m->dep_cap <= 64;
+        const bool want_mega = (flags & MSX_STREAM_PERSISTENT_DEPFORMER) && m->dep_cap <= 64 && sp->temp_audio <= 0.f && !sp->d_dep_prog;
+        if (sp->temp_audio > 0.f) sp->mega_depformer = false;
         if (want_mega) {
             int mx = 0;
             std::vector<Phase> prog = build_depformer_program(s.get(), &mx);
@@ -783,8 +828,34 @@ extern "C" int msx_stream_create_ex(msx_model *m, int context_override, int flag
             if (int e = capture(s.get(), [&](Launcher &L) { enqueue_depformer(L, s.get()); }, &s->g_depformer, &s->launches_depformer)) return e;
         }
     }
+    return 0;
+}
+
+extern "C" int msx_stream_set_sampling(msx_stream *s, float temp_text, float temp_audio, int top_k_text, int top_k_audio) {
+    if (!s) return fail(MSX_ERR_ARG, "null stream");
+    if (top_k_text < 1 || top_k_audio < 1) return fail(MSX_ERR_ARG, "top_k must be >= 1");
+    if (std::min(top_k_text, s->m->cfg.text_card) > kSampleMaxK || std::min(top_k_audio, s->m->cfg.card) > kSampleMaxK)
+        return fail(MSX_ERR_ARG, "top_k > 256 is not supported");
+    CU(cudaSetDevice(s->m->device));
     CU(cudaStreamSynchronize(s->st));
-    *out = s.release();
+    s->temp_text = temp_text; s->temp_audio = temp_audio; s->top_k_text = top_k_text; s->top_k_audio = top_k_audio;
+    if (int e = build_graphs(s)) return e;
+    CU(cudaStreamSynchronize(s->st));
+    return 0;
+}
+
+// noise_text[top_k_text], noise_audio[dep_q][top_k_audio]: Exp(1) draws in candidate order (descending probability)
+extern "C" int msx_stream_set_noise(msx_stream *s, const float *noise_text, const float *noise_audio) {
+    if (!s) return fail(MSX_ERR_ARG, "null stream");
+    const msx_config &c = s->m->cfg;
+    CU(cudaSetDevice(s->m->device));
+    CU(cudaStreamSynchronize(s->st));     // the pinned staging buffer may still be in flight
+    const int kt = std::min(std::min(s->top_k_text, c.text_card), kSampleMaxK), ka = std::min(std::min(s->top_k_audio, c.card), kSampleMaxK);
+    for (int i = 0; i < s->noise_floats; i++) s->h_noise[i] = 1.f;
+    if (noise_text) memcpy(s->h_noise, noise_text, (size_t)kt * 4);
+    if (noise_audio) for (int k = 0; k < c.dep_q; k++) memcpy(s->h_noise + kSampleMaxK + (size_t)k * kSampleMaxK, noise_audio + (size_t)k * ka, (size_t)ka * 4);
+    CU(cudaMemcpyAsync(s->d_noise, s->h_noise, (size_t)(kSampleMaxK * (1 + c.dep_q)) * 4, cudaMemcpyHostToDevice, s->st));
+    s->noise_fresh = true;
     return 0;
 }
 
@@ -1108,6 +1179,7 @@ static void gen_init_impl(msx_gen *g, int delay_steps) {
     g->initial[0] = c.text_card;
 }
 extern "C" void msx_gen_free(msx_gen *g) { delete g; }
+extern "C" void msx_gen_seed(msx_gen *, unsigned seed) { srand(seed); }
 extern "C" int msx_gen_offset(const msx_gen *g) { return g ? g->offset : -1; }
 extern "C" int msx_gen_max_delay(const msx_gen *g) { return g ? g->max_delay : -1; }
 
@@ -1137,6 +1209,15 @@ extern "C" int msx_gen_step(msx_gen *g, const int32_t *in_tokens, int n_in, int 
 
     int32_t out[1 + MSX_MAX_STEPS];
     for (int i = 0; i < 1 + MSX_MAX_STEPS; i++) out[i] = -1;
+    if (!g->fn && (s->temp_text > 0.f || s->temp_audio > 0.f)) {
+        // Exp(1) draws exactly like GraphContext::_exponential_compute (context.h:464-480): one libc rand() per
+        // top-k candidate, text graph first, then the depformer codebooks in order
+        const int kt = std::min(std::min(s->top_k_text, c.text_card), kSampleMaxK), ka = std::min(std::min(s->top_k_audio, c.card), kSampleMaxK);
+        std::vector<float> nt(kt), na((size_t)std::max(1, c.dep_q) * ka);
+        if (s->temp_text > 0.f) for (int i = 0; i < kt; i++) nt[i] = -logf(rand() / (float)RAND_MAX);
+        if (s->temp_audio > 0.f && !depformer_replace_tokens) for (size_t i = 0; i < (size_t)c.dep_q * ka; i++) na[i] = -logf(rand() / (float)RAND_MAX);
+        if (int e = msx_stream_set_noise(s, nt.data(), na.data())) return e;
+    }
     if (g->fn) {
         if (int e = g->fn(g->user, input, depformer_replace_tokens, out)) return fail(MSX_ERR_STATE, "step callback failed: " + std::to_string(e));
         if (depformer_replace_tokens) for (int q = 0; q < c.dep_q; q++) out[1 + q] = -1;      // lm.h:909-913

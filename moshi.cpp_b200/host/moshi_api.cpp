@@ -210,12 +210,13 @@ static void personaplex_prompts(moshi_lm_gen_t *gen) {
 }
 
 void moshi_lm_start(moshi_context_t *, moshi_lm_gen_t *gen, float depth_temperature, float text_temperature, bool) {
-    // the reference always samples (top-k 250 / 25, moshi.cpp:862-877) and is greedy only for temperature 0;
-    // this build implements the greedy path (sampling.h:57-63) — temperatures are accepted and ignored for now
-    (void)depth_temperature; (void)text_temperature;
+    // like the reference: use_sampling = true, top_k = 250 (audio) / 25 (text) (moshi.cpp:862-877); a temperature
+    // of 0 selects the greedy path (sampling.h:57-63).  Exp(1) noise comes from libc rand() inside msx_gen_step.
     if (gen->gen) { msx_gen_free(gen->gen); gen->gen = nullptr; }
     if (gen->stream) { msx_stream_free(gen->stream); gen->stream = nullptr; }
     if (msx_stream_create(gen->lm->model, 0, &gen->stream) != 0) { fprintf(stderr, "moshi_b200: %s\n", msx_last_error()); return; }
+    if (depth_temperature > 0.f || text_temperature > 0.f)
+        if (msx_stream_set_sampling(gen->stream, text_temperature, depth_temperature, 25, 250) != 0) { fprintf(stderr, "moshi_b200: %s\n", msx_last_error()); return; }
     if (msx_gen_create(gen->stream, gen->lm->delay_steps, &gen->gen) != 0) { fprintf(stderr, "moshi_b200: %s\n", msx_last_error()); return; }
     gen->audio_tokens.assign(gen->lm->cfg.n_q, 0);
     if (gen->lm->cfg.personaplex) personaplex_prompts(gen);

@@ -428,6 +428,9 @@ struct orc_state {
     uint16_t *k, *v;            /* [L][H][cap][Dh] */
     uint16_t *dk, *dv;          /* [Ld][Hd][capd][Dhd] */
     float *transformer_out;     /* [dim] */
+    /* sampling (sampling.h:46-64): temp <= 0 greedy; noise = Exp(1) draws in candidate order */
+    float temp_text, temp_audio; int top_k_text, top_k_audio;
+    const float *noise_text, *noise_audio;
 };
 
 static size_t kv_elems(const orc_config *c) { return (size_t)c->num_layers * c->context * c->dim; }
@@ -560,6 +563,37 @@ static void transformer_layer(const orc_model *m, const orc_layer *l, int w, int
     free(nx); free(p); free(ctx); free(upd); free(g); free(mm); free(scratch); free(rotr); free(qr); free(kr);
 }
 
+/* moshi_sample_token (sampling.h:4-64) for use_sampling && temp > 0:
+ *   probs = soft_max(logits * (1/temp))  [max, exp(x - max) through double, sum in double, * (float)(1/sum)]
+ *   top-k by descending probability (ties: ascending id), q_j = p_j / e_j, first arg-max -> token */
+typedef struct { float p; int id; } orc_cand;
+static int cand_cmp(const void *a, const void *b) {
+    const orc_cand *x = a, *y = b;
+    if (x->p > y->p) return -1; if (x->p < y->p) return 1;
+    return x->id < y->id ? -1 : (x->id > y->id ? 1 : 0);
+}
+static int sample_top_k(const float *logits, int n, float temp, int k, const float *noise) {
+    const float inv_temp = 1.f / temp;
+    orc_cand *c = malloc(sizeof(orc_cand) * n);
+    float mx = -INFINITY;
+    for (int i = 0; i < n; i++) { float v = logits[i] * inv_temp; if (v > mx) mx = v; }
+    double sum = 0;
+    for (int i = 0; i < n; i++) { float e = (float)exp((double)(logits[i] * inv_temp - mx)); c[i].p = e; c[i].id = i; sum += (double)e; }
+    const float inv = (float)(1.0 / sum);
+    for (int i = 0; i < n; i++) c[i].p = c[i].p * inv;
+    qsort(c, n, sizeof(orc_cand), cand_cmp);
+    if (k > n) k = n;
+    int best = 0; float bq = c[0].p / noise[0];
+    for (int j = 1; j < k; j++) { float q = c[j].p / noise[j]; if (q > bq) { bq = q; best = j; } }
+    int tok = c[best].id;
+    free(c);
+    return tok;
+}
+void orc_state_set_sampling(orc_state *s, float temp_text, float temp_audio, int top_k_text, int top_k_audio) {
+    s->temp_text = temp_text; s->temp_audio = temp_audio; s->top_k_text = top_k_text; s->top_k_audio = top_k_audio;
+}
+void orc_state_set_noise(orc_state *s, const float *noise_text, const float *noise_audio) { s->noise_text = noise_text; s->noise_audio = noise_audio; }
+
 static int argmax_first(const float *v, int n) { int bi = 0; float bv = v[0]; for (int i = 1; i < n; i++) if (v[i] > bv) { bv = v[i]; bi = i; } return bi; }
 
 int orc_step_temporal(orc_model *m, orc_state *s, const int32_t *tokens, float *text_logits, float *transformer_out) {
@@ -576,7 +610,8 @@ int orc_step_temporal(orc_model *m, orc_state *s, const int32_t *tokens, float *
     orc_rms_norm(x, (const float *)m->out_norm.data, 1e-8f, s->transformer_out, dim);   /* lm.h:671-672 */
     float *logits = text_logits ? text_logits : malloc(sizeof(float) * c->text_card);
     linear(m, &m->text_linear, s->transformer_out, logits);
-    int tok = argmax_first(logits, (int)m->text_linear.ne1);
+    int tok = (s->temp_text > 0.f && s->noise_text) ? sample_top_k(logits, (int)m->text_linear.ne1, s->temp_text, s->top_k_text, s->noise_text)
+                                                   : argmax_first(logits, (int)m->text_linear.ne1);
     if (transformer_out) memcpy(transformer_out, s->transformer_out, sizeof(float) * dim);
     if (!text_logits) free(logits);
     free(x); free(row);
@@ -602,7 +637,10 @@ void orc_step_depformer(orc_model *m, orc_state *s, int text_token, const int32_
             transformer_layer(m, &m->dep_layers[l], wl, dd, c->dep_heads, m->dep_cap, c->dep_max_period, k,
                               s->dk + l * lstride, s->dv + l * lstride, y);
         linear(m, &m->linears[k], y, logits);                          /* lm.h:472, no final norm */
-        int tok = argmax_first(logits, (int)m->linears[k].ne1);
+        int tok = (s->temp_audio > 0.f && s->noise_audio)
+                      ? sample_top_k(logits, (int)m->linears[k].ne1, s->temp_audio, s->top_k_audio,
+                                     s->noise_audio + (size_t)k * (s->top_k_audio < c->card ? s->top_k_audio : c->card))
+                      : argmax_first(logits, (int)m->linears[k].ne1);
         audio_tokens[k] = tok;
         if (audio_logits) memcpy(audio_logits + (size_t)k * c->card, logits, sizeof(float) * c->card);
         prev = (force && force[k] >= 0) ? force[k] : tok;

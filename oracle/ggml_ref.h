@@ -80,6 +80,9 @@ int orc_step_temporal(orc_model *m, orc_state *s, const int32_t *tokens,
 /* depformer chain (lm.h:446-553); force[k] >= 0 replaces the greedy choice that feeds step k+1 */
 void orc_step_depformer(orc_model *m, orc_state *s, int text_token, const int32_t *force /*[dep_q] or NULL*/,
                         int32_t *audio_tokens /*[dep_q]*/, float *audio_logits /*[dep_q][card] or NULL*/);
+/* sampling: temp <= 0 keeps greedy; noise_text[top_k_text], noise_audio[dep_q][min(top_k_audio, card)] must outlive the steps */
+void orc_state_set_sampling(orc_state *s, float temp_text, float temp_audio, int top_k_text, int top_k_audio);
+void orc_state_set_noise(orc_state *s, const float *noise_text, const float *noise_audio);
 /* STT VAD head (lm.h:966-976): softmax(extra_heads[2] . transformer_out)[0] */
 float orc_vad(orc_model *m, orc_state *s);
 /* debugging / parity: copy KV row */

@@ -67,6 +67,8 @@ def lib():
         L.orc_step_temporal.restype = C.c_int; L.orc_step_temporal.argtypes = [vp, vp, vp, vp, vp]
         L.orc_step_depformer.argtypes = [vp, vp, C.c_int, vp, vp, vp]
         L.orc_vad.restype = C.c_float; L.orc_vad.argtypes = [vp, vp]
+        L.orc_state_set_sampling.argtypes = [vp, C.c_float, C.c_float, C.c_int, C.c_int]
+        L.orc_state_set_noise.argtypes = [vp, vp, vp]
         L.orc_state_get_kv.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp]
         L.orc_lmgen_new.restype = vp; L.orc_lmgen_new.argtypes = [vp]
         L.orc_lmgen_free.argtypes = [vp]
@@ -216,6 +218,14 @@ class State:
 
     def vad(self) -> float:
         return float(lib().orc_vad(self.model.h, self.h))
+
+    def set_sampling(self, temp_text, temp_audio, top_k_text=25, top_k_audio=250):
+        lib().orc_state_set_sampling(self.h, temp_text, temp_audio, top_k_text, top_k_audio)
+
+    def set_noise(self, noise_text, noise_audio):
+        self._nt = np.ascontiguousarray(noise_text, dtype=np.float32)
+        self._na = np.ascontiguousarray(noise_audio, dtype=np.float32)
+        lib().orc_state_set_noise(self.h, _p(self._nt), _p(self._na))
 
     def get_kv(self, layer: int, head: int, slot: int):
         Dh = self.model.cfg["dim"] // self.model.cfg["num_heads"]

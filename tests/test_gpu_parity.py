@@ -307,3 +307,34 @@ def test_persistent_kernels_match_multi_kernel_path(msx, gguf_for, preset, quant
         xa, xla = a.step_depformer(ta); xb, xlb = b.step_depformer(tb)
         assert np.array_equal(xa, xb), f"frame {f}"
         assert np.array_equal(xla.view(np.uint32), xlb.view(np.uint32)), f"frame {f}"
+
+
+@pytest.mark.parametrize("preset,quant", [("tiny", "q4_k"), ("moshi7b_l2", "q4_k")])
+def test_top_k_sampling_matches_oracle(msx, orc, gguf_for, preset, quant):
+    """temp > 0: softmax(l/temp) -> top-k (25 text / 250 audio) -> arg-max of p/Exp(1) with the SAME host noise
+    on both sides (reference: sampling.h:4-64, context.h:464-480) -> identical tokens, free running."""
+    path, cfg = gguf_for(preset, quant)
+    gm = msx.Model(path, cfg); gs = msx.Stream(gm)
+    om = orc.Model(path, cfg); os_ = orc.State(om)
+    kt, ka = min(25, cfg["text_card"]), min(250, cfg["card"])
+    gs.set_sampling(0.7, 0.8, 25, 250); os_.set_sampling(0.7, 0.8, 25, 250)
+    rng = np.random.default_rng(11)
+    toks = np.array([cfg["text_card"]] + [cfg["card"]] * cfg["n_q"], dtype=np.int32)
+    n_diff_from_greedy = 0
+    for f in range(10 if preset == "tiny" else 3):
+        nt = rng.exponential(size=kt).astype(np.float32); na = rng.exponential(size=(cfg["dep_q"], ka)).astype(np.float32)
+        os_.set_noise(nt, na); gs.set_noise(nt, na)
+        t_ref, lg_ref, _ = os_.step_temporal(toks)
+        a_ref, al_ref = os_.step_depformer(t_ref)
+        t_gpu, lg_gpu, _ = gs.step_temporal(toks)
+        a_gpu, al_gpu = gs.step_depformer(t_gpu)
+        assert t_gpu == t_ref, f"frame {f}: sampled text token"
+        assert np.array_equal(a_gpu, a_ref), f"frame {f}: sampled audio tokens"
+        assert np.array_equal(lg_gpu.view(np.uint32), lg_ref.view(np.uint32))
+        n_diff_from_greedy += int(t_ref != int(np.argmax(lg_ref))) + int(np.sum(a_ref != np.argmax(al_ref, axis=1)))
+        toks = np.array([t_ref] + list(a_ref) + list(rng.integers(0, cfg["card"], size=cfg["n_q"] - cfg["dep_q"])), dtype=np.int32)
+    assert n_diff_from_greedy > 0, "sampling never left the greedy path: the test would not exercise top-k"
+    # back to greedy: graphs are re-captured
+    gs.set_sampling(0.0, 0.0); os_.set_sampling(0.0, 0.0)
+    t_ref, lg_ref, _ = os_.step_temporal(toks); t_gpu, lg_gpu, _ = gs.step_temporal(toks)
+    assert t_gpu == t_ref == int(np.argmax(lg_ref))
