@@ -117,6 +117,9 @@ MSX_API int msx_vad(msx_stream *s, float *vad);
  * kernels run on.  out_tokens (host, [n_steps][1+dep_q]) may be NULL. */
 MSX_API int msx_run_resident(msx_stream *s, const int32_t *frames, int n_frames, int n_steps,
                              int32_t *out_tokens, float *elapsed_ms);
+/* Several streams on ONE GPU: enqueue without waiting, then join.  elapsed_ms = device time of this stream's run. */
+MSX_API int msx_run_resident_async(msx_stream *s, const int32_t *frames, int n_frames, int n_steps);
+MSX_API int msx_stream_wait(msx_stream *s, float *elapsed_ms);
 /* kernels launched per fused frame (for bench.py "gpu_launches") */
 MSX_API int msx_stream_launches_per_frame(const msx_stream *s);
 /* Measurement aid: runs ONE fused frame eagerly (no CUDA graph) with a CUDA event recorded on the

@@ -109,6 +109,8 @@ def lib():
     L.msx_gen_seed.argtypes = [vp, C.c_uint]
     L.msx_run_resident.argtypes = [vp, vp, C.c_int, C.c_int, vp, C.POINTER(C.c_float)]
     L.msx_stream_launches_per_frame.argtypes = [vp]
+    L.msx_run_resident_async.argtypes = [vp, vp, C.c_int, C.c_int]
+    L.msx_stream_wait.argtypes = [vp, C.POINTER(C.c_float)]
     L.msx_profile_frame.argtypes = [vp, vp, vp, vp, vp, C.c_int]
     L.msx_family_count.restype = C.c_int
     L.msx_timer_start.argtypes = [vp]
@@ -267,6 +269,16 @@ class Stream:
     def timer_stop(self) -> float:
         ms = C.c_float(0)
         _check(lib().msx_timer_stop(self.h, C.byref(ms)))
+        return float(ms.value)
+
+    def run_resident_async(self, frames, n_steps: int):
+        cfg = self.model.cfg
+        fr = np.ascontiguousarray(frames, dtype=np.int32).reshape(-1, cfg["n_q"] + 1)
+        _check(lib().msx_run_resident_async(self.h, _p(fr), fr.shape[0], n_steps))
+
+    def wait(self) -> float:
+        ms = C.c_float(0)
+        _check(lib().msx_stream_wait(self.h, C.byref(ms)))
         return float(ms.value)
 
     def get_kv(self, layer: int, head: int, slot: int):

@@ -128,26 +128,36 @@ __global__ void __launch_bounds__(kThreads) attn_kernel(const AttnArgs a) {
 #pragma unroll
     for (int i = 0; i < 8; i++) qv[i] = q_s[sl * 8 + i];
     float lmax = -INFINITY;
-    for (int i0 = lo; i0 < hi; i0 += NG) {          // warp-uniform trip count (shuffles below)
-        const int i = i0 + g;
-        const bool valid = i < hi;
-        uint4 kk = make_uint4(0, 0, 0, 0);
-        if (valid) {
-            if (i == slot) kk = reinterpret_cast<const uint4 *>(knew)[sl];
-            else kk = *reinterpret_cast<const uint4 *>(a.kc + ((size_t)h * cap + i) * DH + sl * 8);
-        }
-        // bf16 x bf16 products are exact in fp32; they are summed in double (order-independent)
-        double d = 0.0;
-        d += (double)(bf16_bits_to_f32(kk.x & 0xffff) * qv[0]); d += (double)(bf16_bits_to_f32(kk.x >> 16) * qv[1]);
-        d += (double)(bf16_bits_to_f32(kk.y & 0xffff) * qv[2]); d += (double)(bf16_bits_to_f32(kk.y >> 16) * qv[3]);
-        d += (double)(bf16_bits_to_f32(kk.z & 0xffff) * qv[4]); d += (double)(bf16_bits_to_f32(kk.z >> 16) * qv[5]);
-        d += (double)(bf16_bits_to_f32(kk.w & 0xffff) * qv[6]); d += (double)(bf16_bits_to_f32(kk.w >> 16) * qv[7]);
+    // U slots per group and iteration: all U key rows are requested before the first is used, so the
+    // (HBM-latency-bound) loop pays one round trip per U slots.  Trip count is warp-uniform (shuffles below).
+    constexpr int U = 8;
+    for (int i0 = lo; i0 < hi; i0 += NG * U) {
+        uint4 kk[U];
 #pragma unroll
-        for (int o = LPS / 2; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-        const float s = (float)d * scale + 0.0f;
-        if (valid) {
-            if (sl == 0) sc_s[i - lo] = s;
-            lmax = fmaxf(lmax, s);
+        for (int u = 0; u < U; u++) {
+            const int i = i0 + u * NG + g;
+            kk[u] = make_uint4(0, 0, 0, 0);
+            if (i < hi) {
+                if (i == slot) kk[u] = reinterpret_cast<const uint4 *>(knew)[sl];
+                else kk[u] = *reinterpret_cast<const uint4 *>(a.kc + ((size_t)h * cap + i) * DH + sl * 8);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int i = i0 + u * NG + g;
+            // bf16 x bf16 products are exact in fp32; they are summed in double (order-independent)
+            double d = 0.0;
+            d += (double)(bf16_bits_to_f32(kk[u].x & 0xffff) * qv[0]); d += (double)(bf16_bits_to_f32(kk[u].x >> 16) * qv[1]);
+            d += (double)(bf16_bits_to_f32(kk[u].y & 0xffff) * qv[2]); d += (double)(bf16_bits_to_f32(kk[u].y >> 16) * qv[3]);
+            d += (double)(bf16_bits_to_f32(kk[u].z & 0xffff) * qv[4]); d += (double)(bf16_bits_to_f32(kk[u].z >> 16) * qv[5]);
+            d += (double)(bf16_bits_to_f32(kk[u].w & 0xffff) * qv[6]); d += (double)(bf16_bits_to_f32(kk[u].w >> 16) * qv[7]);
+#pragma unroll
+            for (int o = LPS / 2; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+            const float sv = (float)d * scale + 0.0f;
+            if (i < hi) {
+                if (sl == 0) sc_s[i - lo] = sv;
+                lmax = fmaxf(lmax, sv);
+            }
         }
     }
     lmax = warp_max(lmax);
@@ -192,15 +202,28 @@ __global__ void __launch_bounds__(kThreads) attn_kernel(const AttnArgs a) {
     double acc[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) acc[i] = 0.0;
-    for (int i = lo + g; i < hi; i += NG) {
-        const float p = bf16_round(sc_s[i - lo] * inv);
-        uint4 vv;
-        if (i == slot) vv = reinterpret_cast<const uint4 *>(vnew)[sl];
-        else vv = *reinterpret_cast<const uint4 *>(a.vc + ((size_t)h * cap + i) * DH + sl * 8);
-        acc[0] += (double)(bf16_bits_to_f32(vv.x & 0xffff) * p); acc[1] += (double)(bf16_bits_to_f32(vv.x >> 16) * p);
-        acc[2] += (double)(bf16_bits_to_f32(vv.y & 0xffff) * p); acc[3] += (double)(bf16_bits_to_f32(vv.y >> 16) * p);
-        acc[4] += (double)(bf16_bits_to_f32(vv.z & 0xffff) * p); acc[5] += (double)(bf16_bits_to_f32(vv.z >> 16) * p);
-        acc[6] += (double)(bf16_bits_to_f32(vv.w & 0xffff) * p); acc[7] += (double)(bf16_bits_to_f32(vv.w >> 16) * p);
+    for (int i0 = lo + g; i0 < hi; i0 += NG * U) {
+        uint4 vv[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int i = i0 + u * NG;
+            vv[u] = make_uint4(0, 0, 0, 0);
+            if (i < hi) {
+                if (i == slot) vv[u] = reinterpret_cast<const uint4 *>(vnew)[sl];
+                else vv[u] = *reinterpret_cast<const uint4 *>(a.vc + ((size_t)h * cap + i) * DH + sl * 8);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int i = i0 + u * NG;
+            if (i < hi) {
+                const float p = bf16_round(sc_s[i - lo] * inv);
+                acc[0] += (double)(bf16_bits_to_f32(vv[u].x & 0xffff) * p); acc[1] += (double)(bf16_bits_to_f32(vv[u].x >> 16) * p);
+                acc[2] += (double)(bf16_bits_to_f32(vv[u].y & 0xffff) * p); acc[3] += (double)(bf16_bits_to_f32(vv[u].y >> 16) * p);
+                acc[4] += (double)(bf16_bits_to_f32(vv[u].z & 0xffff) * p); acc[5] += (double)(bf16_bits_to_f32(vv[u].z >> 16) * p);
+                acc[6] += (double)(bf16_bits_to_f32(vv[u].w & 0xffff) * p); acc[7] += (double)(bf16_bits_to_f32(vv[u].w >> 16) * p);
+            }
+        }
     }
 #pragma unroll
     for (int i = 0; i < 8; i++) part[g * DH + sl * 8 + i] = acc[i];

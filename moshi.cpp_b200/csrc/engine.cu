@@ -457,8 +457,10 @@ struct Launcher {
 };
 
 int attn_split_for(int heads, int cap, int num_sms) {
+    // short rings: at most one CTA per SM; long rings (KV streaming dominates): up to two CTAs per SM
+    const int budget = cap > 1024 ? 2 * num_sms : num_sms;
     int s = 1;
-    while (s * 2 <= kAttnMaxSplit && heads * s * 2 <= num_sms && cap / (s * 2) >= 1) s *= 2;
+    while (s * 2 <= kAttnMaxSplit && heads * s * 2 <= budget && cap / (s * 2) >= 1) s *= 2;
     return s;
 }
 
@@ -480,6 +482,7 @@ struct msx_stream {
     float *x = nullptr, *qkv = nullptr, *ctx = nullptr, *gate = nullptr, *tout = nullptr, *text_logits = nullptr;
     float *dx = nullptr, *dqkv = nullptr, *dctx = nullptr, *dgate = nullptr, *audio_logits = nullptr, *vad_logits = nullptr;
     float *rope_cs = nullptr;        // [Dh] cos | sin of the current temporal position
+    int32_t *d_feed = nullptr;       // msx_run_resident_async
     cudaGraphExec_t g_temporal = nullptr, g_depformer = nullptr;
     int launches_temporal = 0, launches_depformer = 0;
     // sampling (sampling.h:46-64): temperature <= 0 = greedy; noise = Exp(1) draws supplied by the host per frame
@@ -1115,6 +1118,45 @@ extern "C" int msx_timer_stop(msx_stream *s, float *elapsed_ms) {
     CU(cudaEventRecord(s->ev1, s->st));
     CU(cudaEventSynchronize(s->ev1));
     CU(cudaEventElapsedTime(elapsed_ms, s->ev0, s->ev1));
+    return 0;
+}
+
+// Asynchronous variant of msx_run_resident for several streams on one GPU: enqueue n_steps fused frames on the
+// stream's own CUDA stream and return; msx_stream_wait() joins and yields the device time.  feed buffers are owned
+// by the stream until the wait.
+extern "C" int msx_run_resident_async(msx_stream *s, const int32_t *frames, int n_frames, int n_steps) {
+    if (!s || !frames || n_frames <= 0 || n_steps <= 0) return fail(MSX_ERR_ARG, "bad argument");
+    const msx_config &c = s->m->cfg;
+    CU(cudaSetDevice(s->m->device));
+    const int n_in = c.n_q + 1;
+    if (s->d_feed) { cudaFree(s->d_feed); s->d_feed = nullptr; }
+    CU(cudaMalloc((void **)&s->d_feed, (size_t)n_frames * n_in * 4));
+    CU(cudaMemcpy(s->d_feed, frames, (size_t)n_frames * n_in * 4, cudaMemcpyHostToDevice));
+    if (int e = push_inputs(s, nullptr, INT32_MIN, nullptr)) return e;
+    Ctrl hdr;
+    memset(&hdr, 0, sizeof(hdr));
+    hdr.offset = s->host_offset; hdr.frame = 0; hdr.feed_n = n_frames; hdr.n_in = n_in; hdr.feed = s->d_feed; hdr.trace = nullptr;
+    CU(cudaMemcpyAsync(s->ctrl, &hdr, kCtrlInOffset, cudaMemcpyHostToDevice, s->st));
+    CU(cudaStreamSynchronize(s->st));
+    CU(cudaEventRecord(s->ev0, s->st));
+    for (int i = 0; i < n_steps; i++) {
+        CU(cudaGraphLaunch(s->g_temporal, s->st));
+        if (c.dep_q > 0) CU(cudaGraphLaunch(s->g_depformer, s->st));
+    }
+    CU(cudaEventRecord(s->ev1, s->st));
+    s->host_offset += n_steps;
+    return 0;
+}
+extern "C" int msx_stream_wait(msx_stream *s, float *elapsed_ms) {
+    if (!s) return fail(MSX_ERR_ARG, "null stream");
+    CU(cudaSetDevice(s->m->device));
+    CU(cudaStreamSynchronize(s->st));
+    if (elapsed_ms) CU(cudaEventElapsedTime(elapsed_ms, s->ev0, s->ev1));
+    if (s->d_feed) {
+        int32_t zero2[2] = {0, 0};
+        CU(cudaMemcpy(&s->ctrl->frame, zero2, 8, cudaMemcpyHostToDevice));   // back to host mode
+        cudaFree(s->d_feed); s->d_feed = nullptr;
+    }
     return 0;
 }
 
