@@ -160,6 +160,30 @@ MSX_API int msx_gen_max_delay(const msx_gen *g);
  * Repack one row-major GGUF tensor [rows][k] of `type` (ggml type id), run y = W.x on the device
  * with the same fused kernels the step uses.  prologue: 0 = quantise x, 1 = rms_norm(x)*alpha then
  * quantise.  All pointers are host pointers. */
+/* ---- lock-step batch of independent streams (BASELINE.json config 5) ------------------
+ * n_streams (1..8) conversations share every weight read: one activation-quantisation launch and one
+ * tensor-core dequant-GEMM launch per linear layer serve all of them; KV rings, positions and delay state
+ * stay private, so stream i of a batch computes exactly what a single msx_stream would.  q4_k models only. */
+typedef struct msx_batch msx_batch;
+MSX_API int msx_batch_create(msx_model *model, int n_streams, int context_override, msx_batch **out);
+MSX_API void msx_batch_free(msx_batch *b);
+MSX_API int msx_batch_size(const msx_batch *b);
+MSX_API int msx_batch_offset(const msx_batch *b, int stream);
+MSX_API int msx_batch_launches_per_frame(const msx_batch *b);
+MSX_API int64_t msx_batch_kv_bytes_next(const msx_batch *b);
+/* stream < 0: every stream; otherwise restart one stream (KV cleared, position 0) while the others go on */
+MSX_API int msx_batch_reset_stream(msx_batch *b, int stream);
+/* tokens [n][n_q+1] -> out_tokens [n][1+dep_q] (greedy), one fused frame for every stream */
+MSX_API int msx_batch_step(msx_batch *b, const int32_t *tokens, int32_t *out_tokens);
+MSX_API int msx_batch_get_logits(msx_batch *b, int stream, float *text_logits, float *audio_logits);
+/* frames [n][n_frames][n_q+1] copied to the device once, n_steps frames replayed; out_tokens [n][n_steps][1+dep_q] or NULL */
+MSX_API int msx_batch_run_resident(msx_batch *b, const int32_t *frames, int n_frames, int n_steps, int32_t *out_tokens, float *elapsed_ms);
+MSX_API int msx_batch_profile_frame(msx_batch *b, const int32_t *tokens, float *family_ms, int32_t *family_launches, int max_families);
+/* test / measurement hooks of the batched GEMM */
+MSX_API int msx_test_gemm_batch(int device, int type, const void *w, int64_t k, int64_t rows, const float *x, int nb, const float *alpha, float *y);
+MSX_API int msx_bench_gemm_batch(int device, const void *w, int64_t k, int64_t rows, int nb, int n_mats, int iters, int epilogue, int with_quant,
+                                 float *avg_us);
+
 MSX_API int msx_test_gemv(int device, int type, const void *w, int64_t k, int64_t rows,
                           const float *x, const float *alpha, int prologue, float *y);
 /* GEMV micro-benchmark: back-to-back launches over n_mats rotating copies of the matrix; average us per launch */

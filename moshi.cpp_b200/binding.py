@@ -124,6 +124,19 @@ def lib():
     L.msx_gen_offset.argtypes = [vp]
     L.msx_gen_max_delay.argtypes = [vp]
     L.msx_test_gemv.argtypes = [C.c_int, C.c_int, vp, C.c_int64, C.c_int64, vp, vp, C.c_int, vp]
+    L.msx_batch_create.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp)]
+    L.msx_batch_free.argtypes = [vp]
+    L.msx_batch_size.argtypes = [vp]
+    L.msx_batch_offset.argtypes = [vp, C.c_int]
+    L.msx_batch_launches_per_frame.argtypes = [vp]
+    L.msx_batch_kv_bytes_next.restype = C.c_int64; L.msx_batch_kv_bytes_next.argtypes = [vp]
+    L.msx_batch_reset_stream.argtypes = [vp, C.c_int]
+    L.msx_batch_step.argtypes = [vp, vp, vp]
+    L.msx_batch_get_logits.argtypes = [vp, C.c_int, vp, vp]
+    L.msx_batch_run_resident.argtypes = [vp, vp, C.c_int, C.c_int, vp, C.POINTER(C.c_float)]
+    L.msx_batch_profile_frame.argtypes = [vp, vp, vp, vp, C.c_int]
+    L.msx_test_gemm_batch.argtypes = [C.c_int, C.c_int, vp, C.c_int64, C.c_int64, vp, C.c_int, vp, vp]
+    L.msx_bench_gemm_batch.argtypes = [C.c_int, vp, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]
     L.msx_test_dequant_rows.argtypes = [C.c_int, C.c_int, vp, C.c_int64, C.c_int64, vp, C.c_int, vp]
     L.msx_test_dequant_repacked.argtypes = [C.c_int, C.c_int, vp, C.c_int64, C.c_int64, vp]
     _lib = L
@@ -346,6 +359,70 @@ class Gen:
             pass
 
 
+class Batch:
+    """Lock-step batch of independent streams on one GPU (msx_batch_*): weights are read once per frame for all."""
+
+    def __init__(self, model: Model, n_streams: int, context: int = 0):
+        self.model = model
+        self.n = n_streams
+        self.h = C.c_void_p()
+        _check(lib().msx_batch_create(model.h, n_streams, context, C.byref(self.h)))
+
+    @property
+    def launches_per_frame(self) -> int:
+        return lib().msx_batch_launches_per_frame(self.h)
+
+    def offset(self, stream: int) -> int:
+        return lib().msx_batch_offset(self.h, stream)
+
+    def kv_bytes_next(self) -> int:
+        return int(lib().msx_batch_kv_bytes_next(self.h))
+
+    def reset(self, stream: int = -1):
+        _check(lib().msx_batch_reset_stream(self.h, stream))
+
+    def step(self, tokens):
+        cfg = self.model.cfg
+        tok = np.ascontiguousarray(tokens, dtype=np.int32).reshape(self.n, cfg["n_q"] + 1)
+        out = np.empty((self.n, 1 + cfg["dep_q"]), dtype=np.int32)
+        _check(lib().msx_batch_step(self.h, _p(tok), _p(out)))
+        return out
+
+    def logits(self, stream: int):
+        cfg = self.model.cfg
+        tl = np.empty(cfg["text_card"], dtype=np.float32)
+        al = np.empty((cfg["dep_q"], cfg["card"]), dtype=np.float32) if cfg["dep_q"] > 0 else None
+        _check(lib().msx_batch_get_logits(self.h, stream, _p(tl), _p(al)))
+        return tl, al
+
+    def run_resident(self, frames, n_steps: int, want_tokens: bool = False):
+        """frames [n][n_frames][n_q+1] -> (elapsed ms, tokens [n][n_steps][1+dep_q] or None)"""
+        cfg = self.model.cfg
+        fr = np.ascontiguousarray(frames, dtype=np.int32).reshape(self.n, -1, cfg["n_q"] + 1)
+        out = np.empty((self.n, n_steps, 1 + cfg["dep_q"]), dtype=np.int32) if want_tokens else None
+        ms = C.c_float(0)
+        _check(lib().msx_batch_run_resident(self.h, _p(fr), fr.shape[1], n_steps, _p(out), C.byref(ms)))
+        return float(ms.value), out
+
+    def profile_frame(self, tokens):
+        cfg = self.model.cfg
+        tok = np.ascontiguousarray(tokens, dtype=np.int32).reshape(self.n, cfg["n_q"] + 1)
+        n = lib().msx_family_count()
+        ms = np.zeros(n, dtype=np.float32); cnt = np.zeros(n, dtype=np.int32)
+        _check(lib().msx_batch_profile_frame(self.h, _p(tok), _p(ms), _p(cnt), n))
+        return {lib().msx_family_name(i).decode(): (float(ms[i]), int(cnt[i])) for i in range(n) if cnt[i]}
+
+    def close(self):
+        if self.h:
+            lib().msx_batch_free(self.h); self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 # ---- unit-level helpers -------------------------------------------------------------------------
 def test_gemv(gtype: int, w_raw: np.ndarray, k: int, x: np.ndarray, alpha=None, device: int = 0) -> np.ndarray:
     w_raw = np.ascontiguousarray(w_raw); x = np.ascontiguousarray(x, dtype=np.float32)
@@ -369,3 +446,20 @@ def test_dequant_repacked(gtype: int, w_raw: np.ndarray, k: int, device: int = 0
     out = np.empty((w_raw.shape[0], k), dtype=np.float32)
     _check(lib().msx_test_dequant_repacked(device, gtype, _p(w_raw), k, w_raw.shape[0], _p(out)))
     return out
+
+
+def test_gemm_batch(gtype: int, w_raw: np.ndarray, k: int, x: np.ndarray, alpha=None, device: int = 0) -> np.ndarray:
+    """y[nb][rows] through the batched quantise + tensor-core GEMM kernels; x is [nb][k]"""
+    w_raw = np.ascontiguousarray(w_raw); x = np.ascontiguousarray(x, dtype=np.float32).reshape(-1, k)
+    rows = w_raw.shape[0]
+    y = np.empty((x.shape[0], rows), dtype=np.float32)
+    al = np.ascontiguousarray(alpha, dtype=np.float32) if alpha is not None else None
+    _check(lib().msx_test_gemm_batch(device, gtype, _p(w_raw), k, rows, _p(x), x.shape[0], _p(al), _p(y)))
+    return y
+
+
+def bench_gemm_batch(w_raw: np.ndarray, k: int, nb: int, n_mats: int, iters: int, epilogue: int = 0, with_quant: bool = True, device: int = 0) -> float:
+    w_raw = np.ascontiguousarray(w_raw)
+    us = C.c_float(0)
+    _check(lib().msx_bench_gemm_batch(device, _p(w_raw), k, w_raw.shape[0], nb, n_mats, iters, epilogue, 1 if with_quant else 0, C.byref(us)))
+    return float(us.value)

@@ -38,6 +38,9 @@ struct AttnArgs {
     int32_t small_ctx = 0;          // n_valid <= small_ctx: rank 0 of the cluster handles the head alone
     const float *rope_freq = nullptr;  // [DH/2] expf(-logf(max_period)*j/half), computed on the host at load
     const float *rope_cs = nullptr;    // optional [DH]: cos | sin of this step's position, written once per frame by the embed kernel
+    // batched steps: grid.z = stream; per-stream strides in elements (0 for a single stream)
+    int64_t kv_bstride = 0;
+    int32_t qkv_bstride = 0, ctx_bstride = 0;
 };
 
 constexpr int kAttnMaxSplit = 8;
@@ -52,8 +55,15 @@ __host__ __device__ inline int attn_smem_bytes(int cap, int S) {
 }
 
 template <int DH, bool CLUSTER>
-__global__ void __launch_bounds__(kThreads) attn_kernel(const AttnArgs a) {
+__global__ void __launch_bounds__(kThreads) attn_kernel(const AttnArgs a0) {
     extern __shared__ __align__(16) uint8_t smem[];
+    AttnArgs a = a0;
+    {
+        const int b = blockIdx.z;
+        a.qkv += (size_t)b * a.qkv_bstride; a.ctx += (size_t)b * a.ctx_bstride;
+        a.kc += (size_t)b * a.kv_bstride; a.vc += (size_t)b * a.kv_bstride;
+        a.ctrl += b; if (a.rope_cs) a.rope_cs += (size_t)b * DH;
+    }
     constexpr int LPS = DH / 8;             // lanes per slot (8 dims = 16 B of bf16 each)
     constexpr int NG = kThreads / LPS;      // slots in flight per CTA iteration
     griddep_launch();

@@ -1,0 +1,493 @@
+// batch.inl — lock-step batch of independent conversation streams on one GPU (included by engine.cu).
+//
+// SURVEY.md §8e / BASELINE.json config 5: streams are independent (private KV rings, delay state, positions);
+// stepping n of them together lets every weight matrix be read from HBM once per frame for all of them
+// (mma_gemm.cuh).  The step is the single-stream step (enqueue_temporal / enqueue_depformer above) with
+//   * one activation-quantisation launch + one tensor-core GEMM launch per linear layer,
+//   * attention / embedding / bookkeeping kernels launched with one grid slice per stream.
+// Streams may sit at different positions (msx_batch_reset_stream): everything per-frame lives in the
+// stream's own Ctrl block.
+
+struct msx_batch {
+    msx_model *m = nullptr;
+    int n = 0, cap = 0, attn_split = 1;
+    cudaStream_t st = nullptr;
+    Ctrl *ctrl = nullptr;                 // device [n]
+    int32_t *h_in = nullptr, *h_out = nullptr;   // pinned [n][84], [n][44]
+    uint16_t *kc = nullptr, *vc = nullptr, *dkc = nullptr, *dvc = nullptr;
+    float *x = nullptr, *qkv = nullptr, *ctx = nullptr, *gate = nullptr, *tout = nullptr, *text_logits = nullptr, *rope_cs = nullptr;
+    float *dx = nullptr, *dqkv = nullptr, *dctx = nullptr, *dgate = nullptr, *audio_logits = nullptr;
+    uint8_t *img = nullptr;               // activation image of the GEMM being fed
+    uint8_t *img_tout = nullptr;          // image of transformer_out (depformer_in input, reused by every codebook step)
+    cudaGraphExec_t g_temporal = nullptr, g_depformer = nullptr;
+    int launches_temporal = 0, launches_depformer = 0;
+    std::vector<int> host_offset;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<void *> allocs;
+
+    ~msx_batch() {
+        if (m) cudaSetDevice(m->device);
+        if (g_temporal) cudaGraphExecDestroy(g_temporal);
+        if (g_depformer) cudaGraphExecDestroy(g_depformer);
+        for (void *p : allocs) cudaFree(p);
+        if (h_in) cudaFreeHost(h_in);
+        if (h_out) cudaFreeHost(h_out);
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        if (st) cudaStreamDestroy(st);
+    }
+};
+
+namespace {
+
+int balloc(msx_batch *b, void **p, size_t bytes) {
+    CU(cudaMalloc(p, std::max<size_t>(bytes, 16)));
+    CU(cudaMemset(*p, 0, std::max<size_t>(bytes, 16)));
+    b->allocs.push_back(*p);
+    return 0;
+}
+
+// units layout of one linear (created on first use, kept for the life of the model)
+int tiles_of(msx_model *m, const QLinear &w, QTiles *out) {
+    auto it = m->tiles.find(w.qs);
+    if (it != m->tiles.end()) { *out = it->second; return 0; }
+    if (w.type != T_Q4_K) return fail(MSX_ERR_ARG, "batched streams need q4_k linear weights");
+    QTiles t;
+    t.K = w.K; t.rows = w.rows; t.nsb = w.K >> 8; t.n_tiles = (w.rows + 15) / 16;
+    void *u = nullptr;
+    if (int e = dev_alloc(m, &u, (size_t)t.n_tiles * t.nsb * kUnitBytes)) return e;
+    const long long n = (long long)t.n_tiles * t.nsb * 148;
+    tile_q4k_kernel<<<(unsigned)((n + 255) / 256), 256>>>(w, w.gate, (uint8_t *)u, t.n_tiles);
+    CU(cudaGetLastError());
+    t.units = (const uint8_t *)u;
+    m->tiles[w.qs] = t;
+    *out = t;
+    return 0;
+}
+
+int ensure_all_tiles(msx_model *m) {
+    QTiles t;
+    auto all = [&](const std::vector<QLinear> &v) -> int { for (const QLinear &w : v) if (int e = tiles_of(m, w, &t)) return e; return 0; };
+    for (const LayerW &l : m->layers) { if (int e = all(l.in_proj)) return e; if (int e = all(l.out_proj)) return e; if (int e = all(l.lin_in)) return e; if (int e = all(l.lin_out)) return e; }
+    for (const LayerW &l : m->dep_layers) { if (int e = all(l.in_proj)) return e; if (int e = all(l.out_proj)) return e; if (int e = all(l.lin_in)) return e; if (int e = all(l.lin_out)) return e; }
+    if (int e = tiles_of(m, m->text_linear, &t)) return e;
+    if (int e = all(m->dep_in)) return e;
+    if (int e = all(m->linears)) return e;
+    CU(cudaDeviceSynchronize());
+    return 0;
+}
+
+struct BatchLauncher {
+    Launcher &L;
+    msx_batch *b;
+    int err = 0;
+
+    void quant(const float *x, int ld, const float *alpha, float *norm_out, int norm_ld, int K, int family, uint8_t *img = nullptr) {
+        QuantArgs q;
+        q.x = x; q.ld = ld; q.alpha = alpha; q.eps = 1e-8f; q.norm_out = norm_out; q.norm_ld = norm_ld; q.img = img ? img : b->img; q.K = K;
+        L.fam = family; L.begin();
+        L.launch_pdl(quant_q8k_kernel, dim3(b->n), dim3(kGemmThreads), 0, q);
+        L.check();
+    }
+    void gemm(const QLinear &w, float *out, int ld, int epi, int family, int key_index = -1, const EmbTable *emb = nullptr, int emb_step = 0,
+              const uint8_t *img = nullptr) {
+        GemmArgs g;
+        if (int e = tiles_of(b->m, w, &g.w)) { err = e; return; }
+        g.img = img ? img : b->img; g.out = out; g.ld = ld; g.nb = b->n; g.epi = epi; g.ctrl = b->ctrl; g.key_index = key_index; g.emb_step = emb_step;
+        if (emb) g.emb = *emb;
+        g.wpt = gemm_wpt_for(g.w.n_tiles, g.w.nsb, L.num_sms);
+        g.stages = gemm_stages_for(w.K);
+        const int tpr = kGemmWarps / g.wpt;
+        const int n_rounds = (g.w.n_tiles + tpr - 1) / tpr;
+        L.fam = family; L.begin();
+        L.launch_pdl(gemm_q4k_kernel, dim3(std::min(L.num_sms, n_rounds)), dim3(kGemmThreads), (size_t)gemm_smem_bytes(w.K, g.stages), g);
+        L.check();
+    }
+};
+
+void enqueue_layer_b(BatchLauncher &B, const LayerW &lw, int w, bool temporal, int layer, int pos_const) {
+    msx_batch *b = B.b; const msx_model *m = b->m; const msx_config &c = m->cfg;
+    const int dim = temporal ? c.dim : c.dep_dim, heads = temporal ? c.num_heads : c.dep_heads;
+    const int cap = temporal ? b->cap : m->dep_cap;
+    const int hidden = temporal ? m->hidden : m->dep_hidden;
+    float *x = temporal ? b->x : b->dx, *qkv = temporal ? b->qkv : b->dqkv, *ctx = temporal ? b->ctx : b->dctx, *gate = temporal ? b->gate : b->dgate;
+    B.quant(x, dim, lw.norm1, nullptr, 0, dim, temporal ? FAM_IN_PROJ : FAM_DEP_IN_PROJ);
+    B.gemm(lw.in_proj[w], qkv, 3 * dim, EPI_STORE, temporal ? FAM_IN_PROJ : FAM_DEP_IN_PROJ);
+    AttnArgs a;
+    a.qkv = qkv; a.ctx = ctx; a.ctrl = b->ctrl; a.pos_const = pos_const; a.cap = cap; a.dim = dim;
+    a.max_period = temporal ? c.max_period : c.dep_max_period;
+    a.rope_freq = temporal ? m->rope_freq : m->dep_rope_freq;
+    a.rope_cs = (temporal && c.max_period) ? b->rope_cs : nullptr;
+    a.small_ctx = 32;
+    const size_t lstride = (size_t)cap * dim;
+    const int n_layers = temporal ? c.num_layers : c.dep_layers;
+    a.kc = (temporal ? b->kc : b->dkc) + (size_t)layer * lstride;
+    a.vc = (temporal ? b->vc : b->dvc) + (size_t)layer * lstride;
+    a.kv_bstride = (int64_t)n_layers * lstride; a.qkv_bstride = 3 * dim; a.ctx_bstride = dim;
+    B.L.attn(a, heads, dim / heads, temporal ? b->attn_split : 1, temporal ? FAM_ATTN : FAM_DEP_ATTN, b->n);
+    B.quant(ctx, dim, nullptr, nullptr, 0, dim, temporal ? FAM_OUT_PROJ : FAM_DEP_OUT_PROJ);
+    B.gemm(lw.out_proj[w], x, dim, EPI_RESID, temporal ? FAM_OUT_PROJ : FAM_DEP_OUT_PROJ);
+    B.quant(x, dim, lw.norm2, nullptr, 0, dim, temporal ? FAM_LIN_IN : FAM_DEP_LIN_IN);
+    B.gemm(lw.lin_in[w], gate, hidden, EPI_GATE, temporal ? FAM_LIN_IN : FAM_DEP_LIN_IN);
+    B.quant(gate, hidden, nullptr, nullptr, 0, hidden, temporal ? FAM_LIN_OUT : FAM_DEP_LIN_OUT);
+    B.gemm(lw.lin_out[w], x, dim, EPI_RESID, temporal ? FAM_LIN_OUT : FAM_DEP_LIN_OUT);
+}
+
+void enqueue_temporal_b(BatchLauncher &B) {
+    msx_batch *b = B.b; const msx_model *m = b->m; const msx_config &c = m->cfg;
+    Launcher &L = B.L;
+    EmbedArgs e;
+    e.tables = m->d_emb; e.n_tables = c.n_q + 1; e.dim = c.dim; e.ctrl = b->ctrl; e.x = b->x;
+    if (c.max_period) { e.rope_cs = b->rope_cs; e.rope_freq = m->rope_freq; e.dh = c.dim / c.num_heads; }
+    L.fam = FAM_EMBED; L.begin();
+    L.launch_pdl(embed_kernel, dim3((c.dim + kThreads - 1) / kThreads, b->n), dim3(kThreads), 0, e);
+    L.check();
+    for (int l = 0; l < c.num_layers; l++) enqueue_layer_b(B, m->layers[l], 0, true, l, -1);
+    B.quant(b->x, c.dim, m->out_norm, b->tout, c.dim, c.dim, FAM_TEXT_HEAD);
+    B.gemm(m->text_linear, b->text_logits, c.text_card, EPI_ARGMAX, FAM_TEXT_HEAD, -1);
+    L.fam = FAM_FINALIZE; L.begin();
+    L.launch_pdl(finalize_temporal_kernel, dim3(b->n), dim3(32), 0, b->ctrl, c.dep_q > 0 ? 1 : 0);
+    L.check();
+}
+
+void enqueue_depformer_b(BatchLauncher &B) {
+    msx_batch *b = B.b; const msx_model *m = b->m; const msx_config &c = m->cfg;
+    Launcher &L = B.L;
+    for (int k = 0; k < c.dep_q; k++) {
+        const int wsel = c.schedule_len ? c.schedule[k] : k;
+        const int w = m->dep_nw == 1 ? 0 : wsel;
+        // transformer_out is quantised once per frame into its own image and reused by all dep_q depformer_in GEMMs
+        if (k == 0) B.quant(b->tout, c.dim, nullptr, nullptr, 0, c.dim, FAM_DEP_IN, b->img_tout);
+        B.gemm(m->dep_in[w], b->dx, c.dep_dim, EPI_ADD_EMB, FAM_DEP_IN, -1, k == 0 ? &m->dep_text_emb : &m->dep_emb[k - 1], k, b->img_tout);
+        for (int l = 0; l < c.dep_layers; l++) enqueue_layer_b(B, m->dep_layers[l], w, false, l, k);
+        B.quant(b->dx, c.dep_dim, nullptr, nullptr, 0, c.dep_dim, FAM_DEP_HEAD);
+        B.gemm(m->linears[k], b->audio_logits + (size_t)k * c.card, c.dep_q * c.card, EPI_ARGMAX, FAM_DEP_HEAD, k);
+    }
+    L.fam = FAM_DEP_FINALIZE; L.begin();
+    L.launch_pdl(finalize_depformer_kernel, dim3(b->n), dim3(64), 0, b->ctrl, (int)c.dep_q);
+    L.check();
+}
+
+template <typename F>
+int capture_b(msx_batch *b, F &&body, cudaGraphExec_t *exec, int *launches) {
+    Launcher L{b->st, b->m->num_sms};
+    BatchLauncher B{L, b};
+    CU(cudaStreamBeginCapture(b->st, cudaStreamCaptureModeThreadLocal));
+    body(B);
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamEndCapture(b->st, &graph);
+    if (B.err) { if (graph) cudaGraphDestroy(graph); return B.err; }
+    if (L.err != cudaSuccess) { if (graph) cudaGraphDestroy(graph); return fail(MSX_ERR_CUDA, std::string("kernel launch failed during capture: ") + cudaGetErrorString(L.err)); }
+    if (e != cudaSuccess) return fail(MSX_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+    e = cudaGraphInstantiate(exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) return fail(MSX_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+    *launches = L.count;
+    return 0;
+}
+
+int push_inputs_b(msx_batch *b, const int32_t *tokens) {
+    const msx_config &c = b->m->cfg;
+    const int w = (int)(kCtrlInBytes / 4);
+    for (int s = 0; s < b->n; s++) {
+        int32_t *h = b->h_in + (size_t)s * w;
+        h[0] = INT32_MIN;
+        if (tokens) for (int i = 0; i < c.n_q + 1; i++) h[1 + i] = tokens[(size_t)s * (c.n_q + 1) + i];
+        for (int i = 0; i < 40; i++) h[41 + i] = INT32_MIN;
+    }
+    CU(cudaMemcpy2DAsync(reinterpret_cast<uint8_t *>(b->ctrl) + kCtrlInOffset, sizeof(Ctrl), b->h_in, kCtrlInBytes, kCtrlInBytes, b->n,
+                         cudaMemcpyHostToDevice, b->st));
+    return 0;
+}
+
+int pull_outputs_b(msx_batch *b) {
+    CU(cudaMemcpy2DAsync(b->h_out, kCtrlOutBytes, reinterpret_cast<uint8_t *>(b->ctrl) + kCtrlOutOffset, sizeof(Ctrl), kCtrlOutBytes, b->n,
+                         cudaMemcpyDeviceToHost, b->st));
+    CU(cudaStreamSynchronize(b->st));
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int msx_batch_create(msx_model *m, int n_streams, int context_override, msx_batch **out) {
+    if (!m || !out) return fail(MSX_ERR_ARG, "null argument");
+    *out = nullptr;
+    if (n_streams < 1 || n_streams > kMmaCols) return fail(MSX_ERR_ARG, "a batch holds 1..8 streams");
+    CU(cudaSetDevice(m->device));
+    if (int e = set_smem_attrs()) return e;
+    CU(cudaFuncSetAttribute(gemm_q4k_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemMax));
+    if (int e = ensure_all_tiles(m)) return e;
+    std::unique_ptr<msx_batch> b(new msx_batch);
+    b->m = m; b->n = n_streams;
+    const msx_config &c = m->cfg;
+    const size_t n = (size_t)n_streams;
+    b->cap = context_override > 0 ? std::min(context_override, c.context) : c.context;
+    b->attn_split = attn_split_for(c.num_heads * n_streams, b->cap, m->num_sms);
+    b->host_offset.assign(n_streams, 0);
+    CU(cudaStreamCreateWithFlags(&b->st, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&b->ev0)); CU(cudaEventCreate(&b->ev1));
+    CU(cudaMallocHost((void **)&b->h_in, kCtrlInBytes * n));
+    CU(cudaMallocHost((void **)&b->h_out, kCtrlOutBytes * n));
+    if (int e = balloc(b.get(), (void **)&b->ctrl, sizeof(Ctrl) * n)) return e;
+    const size_t kv = (size_t)c.num_layers * b->cap * c.dim;
+    if (int e = balloc(b.get(), (void **)&b->kc, kv * 2 * n)) return e;
+    if (int e = balloc(b.get(), (void **)&b->vc, kv * 2 * n)) return e;
+    if (int e = balloc(b.get(), (void **)&b->x, n * c.dim * 4)) return e;
+    if (int e = balloc(b.get(), (void **)&b->qkv, n * c.dim * 3 * 4)) return e;
+    if (int e = balloc(b.get(), (void **)&b->ctx, n * c.dim * 4)) return e;
+    if (int e = balloc(b.get(), (void **)&b->gate, n * m->hidden * 4)) return e;
+    if (int e = balloc(b.get(), (void **)&b->tout, n * c.dim * 4)) return e;
+    if (int e = balloc(b.get(), (void **)&b->text_logits, n * c.text_card * 4)) return e;
+    if (int e = balloc(b.get(), (void **)&b->rope_cs, n * (c.dim / c.num_heads) * 4)) return e;
+    int maxK = std::max(c.dim, m->hidden);
+    if (c.dep_q > 0) {
+        const size_t dkv = (size_t)c.dep_layers * m->dep_cap * c.dep_dim;
+        if (int e = balloc(b.get(), (void **)&b->dkc, dkv * 2 * n)) return e;
+        if (int e = balloc(b.get(), (void **)&b->dvc, dkv * 2 * n)) return e;
+        if (int e = balloc(b.get(), (void **)&b->dx, n * c.dep_dim * 4)) return e;
+        if (int e = balloc(b.get(), (void **)&b->dqkv, n * c.dep_dim * 3 * 4)) return e;
+        if (int e = balloc(b.get(), (void **)&b->dctx, n * c.dep_dim * 4)) return e;
+        if (int e = balloc(b.get(), (void **)&b->dgate, n * m->dep_hidden * 4)) return e;
+        if (int e = balloc(b.get(), (void **)&b->audio_logits, n * c.dep_q * c.card * 4)) return e;
+        maxK = std::max(maxK, std::max(c.dep_dim, m->dep_hidden));
+    }
+    if (gemm_stages_for(maxK) < 2) return fail(MSX_ERR_ARG, "inner dimension too large for the batched GEMM's shared-memory image");
+    if (int e = balloc(b.get(), (void **)&b->img, (size_t)act_image_bytes(maxK))) return e;
+    if (int e = balloc(b.get(), (void **)&b->img_tout, (size_t)act_image_bytes(c.dim))) return e;
+    std::vector<Ctrl> hc(n_streams);
+    memset(hc.data(), 0, sizeof(Ctrl) * n);
+    for (Ctrl &h : hc) { h.n_in = c.n_q + 1; h.text_override = INT32_MIN; for (int i = 0; i < 40; i++) h.force[i] = INT32_MIN; }
+    CU(cudaMemcpy(b->ctrl, hc.data(), sizeof(Ctrl) * n, cudaMemcpyHostToDevice));
+    if (int e = capture_b(b.get(), [&](BatchLauncher &B) { enqueue_temporal_b(B); }, &b->g_temporal, &b->launches_temporal)) return e;
+    if (c.dep_q > 0)
+        if (int e = capture_b(b.get(), [&](BatchLauncher &B) { enqueue_depformer_b(B); }, &b->g_depformer, &b->launches_depformer)) return e;
+    CU(cudaStreamSynchronize(b->st));
+    *out = b.release();
+    return 0;
+}
+
+extern "C" void msx_batch_free(msx_batch *b) { delete b; }
+extern "C" int msx_batch_size(const msx_batch *b) { return b ? b->n : 0; }
+extern "C" int msx_batch_launches_per_frame(const msx_batch *b) { return b ? b->launches_temporal + b->launches_depformer : 0; }
+extern "C" int msx_batch_offset(const msx_batch *b, int stream) { return (b && stream >= 0 && stream < b->n) ? b->host_offset[stream] : -1; }
+extern "C" int64_t msx_batch_kv_bytes_next(const msx_batch *b) {
+    if (!b) return 0;
+    int64_t t = 0;
+    for (int s = 0; s < b->n; s++) t += (int64_t)std::min(b->host_offset[s] + 1, b->cap) * 2 * b->m->cfg.dim * 2 * b->m->cfg.num_layers;
+    return t;
+}
+
+// stream < 0: all streams.  A stream can be restarted while the others keep their context.
+extern "C" int msx_batch_reset_stream(msx_batch *b, int stream) {
+    if (!b || stream >= b->n) return fail(MSX_ERR_ARG, "bad argument");
+    const msx_config &c = b->m->cfg;
+    CU(cudaSetDevice(b->m->device));
+    CU(cudaStreamSynchronize(b->st));
+    const size_t kv = (size_t)c.num_layers * b->cap * c.dim * 2;
+    const size_t dkv = c.dep_q > 0 ? (size_t)c.dep_layers * b->m->dep_cap * c.dep_dim * 2 : 0;
+    for (int s = (stream < 0 ? 0 : stream); s < (stream < 0 ? b->n : stream + 1); s++) {
+        CU(cudaMemsetAsync(reinterpret_cast<uint8_t *>(b->kc) + kv * s, 0, kv, b->st));
+        CU(cudaMemsetAsync(reinterpret_cast<uint8_t *>(b->vc) + kv * s, 0, kv, b->st));
+        if (dkv) {
+            CU(cudaMemsetAsync(reinterpret_cast<uint8_t *>(b->dkc) + dkv * s, 0, dkv, b->st));
+            CU(cudaMemsetAsync(reinterpret_cast<uint8_t *>(b->dvc) + dkv * s, 0, dkv, b->st));
+        }
+        CU(cudaMemsetAsync(b->tout + (size_t)s * c.dim, 0, (size_t)c.dim * 4, b->st));
+        CU(cudaMemsetAsync(&b->ctrl[s].offset, 0, 4, b->st));
+        b->host_offset[s] = 0;
+    }
+    CU(cudaStreamSynchronize(b->st));
+    return 0;
+}
+
+// tokens [n][n_q+1] -> out_tokens [n][1+dep_q]: one fused frame for every stream of the batch
+extern "C" int msx_batch_step(msx_batch *b, const int32_t *tokens, int32_t *out_tokens) {
+    if (!b || !tokens) return fail(MSX_ERR_ARG, "null argument");
+    const msx_config &c = b->m->cfg;
+    CU(cudaSetDevice(b->m->device));
+    if (int e = push_inputs_b(b, tokens)) return e;
+    CU(cudaGraphLaunch(b->g_temporal, b->st));
+    if (c.dep_q > 0) CU(cudaGraphLaunch(b->g_depformer, b->st));
+    for (int &o : b->host_offset) o++;
+    if (int e = pull_outputs_b(b)) return e;
+    const int w = (int)(kCtrlOutBytes / 4);
+    if (out_tokens)
+        for (int s = 0; s < b->n; s++)
+            for (int k = 0; k < 1 + c.dep_q; k++) out_tokens[(size_t)s * (1 + c.dep_q) + k] = b->h_out[(size_t)s * w + k];
+    return 0;
+}
+
+// logits of the last step of one stream (parity checks)
+extern "C" int msx_batch_get_logits(msx_batch *b, int stream, float *text_logits, float *audio_logits) {
+    if (!b || stream < 0 || stream >= b->n) return fail(MSX_ERR_ARG, "bad argument");
+    const msx_config &c = b->m->cfg;
+    CU(cudaSetDevice(b->m->device));
+    CU(cudaStreamSynchronize(b->st));
+    if (text_logits) CU(cudaMemcpy(text_logits, b->text_logits + (size_t)stream * c.text_card, (size_t)c.text_card * 4, cudaMemcpyDeviceToHost));
+    if (audio_logits && c.dep_q > 0)
+        CU(cudaMemcpy(audio_logits, b->audio_logits + (size_t)stream * c.dep_q * c.card, (size_t)c.dep_q * c.card * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// frames [n][n_frames][n_q+1] resident on the device, n_steps frames replayed back to back for every stream
+extern "C" int msx_batch_run_resident(msx_batch *b, const int32_t *frames, int n_frames, int n_steps, int32_t *out_tokens, float *elapsed_ms) {
+    if (!b || !frames || n_frames <= 0 || n_steps <= 0) return fail(MSX_ERR_ARG, "bad argument");
+    const msx_config &c = b->m->cfg;
+    CU(cudaSetDevice(b->m->device));
+    const int n_in = c.n_q + 1, n_out = 1 + c.dep_q;
+    int32_t *d_feed = nullptr, *d_trace = nullptr;
+    CU(cudaMalloc((void **)&d_feed, (size_t)b->n * n_frames * n_in * 4));
+    if (out_tokens) CU(cudaMalloc((void **)&d_trace, (size_t)b->n * n_steps * n_out * 4));
+    CU(cudaMemcpy(d_feed, frames, (size_t)b->n * n_frames * n_in * 4, cudaMemcpyHostToDevice));
+    if (int e = push_inputs_b(b, nullptr)) return e;
+    for (int s = 0; s < b->n; s++) {
+        Ctrl hdr;
+        memset(&hdr, 0, sizeof(hdr));
+        hdr.offset = b->host_offset[s]; hdr.frame = 0; hdr.feed_n = n_frames; hdr.n_in = n_in;
+        hdr.feed = d_feed + (size_t)s * n_frames * n_in;
+        hdr.trace = d_trace ? d_trace + (size_t)s * n_steps * n_out : nullptr;
+        CU(cudaMemcpyAsync(&b->ctrl[s], &hdr, kCtrlInOffset, cudaMemcpyHostToDevice, b->st));
+        CU(cudaStreamSynchronize(b->st));      // hdr is a stack object
+    }
+    CU(cudaEventRecord(b->ev0, b->st));
+    for (int i = 0; i < n_steps; i++) {
+        CU(cudaGraphLaunch(b->g_temporal, b->st));
+        if (c.dep_q > 0) CU(cudaGraphLaunch(b->g_depformer, b->st));
+    }
+    CU(cudaEventRecord(b->ev1, b->st));
+    CU(cudaStreamSynchronize(b->st));
+    for (int &o : b->host_offset) o += n_steps;
+    if (elapsed_ms) CU(cudaEventElapsedTime(elapsed_ms, b->ev0, b->ev1));
+    if (out_tokens) CU(cudaMemcpy(out_tokens, d_trace, (size_t)b->n * n_steps * n_out * 4, cudaMemcpyDeviceToHost));
+    int32_t zero2[2] = {0, 0};
+    for (int s = 0; s < b->n; s++) CU(cudaMemcpy(&b->ctrl[s].frame, zero2, 8, cudaMemcpyHostToDevice));
+    cudaFree(d_feed);
+    if (d_trace) cudaFree(d_trace);
+    return 0;
+}
+
+// per-family kernel time of one eager batched frame (CUDA event after every launch)
+extern "C" int msx_batch_profile_frame(msx_batch *b, const int32_t *tokens, float *family_ms, int32_t *family_launches, int max_families) {
+    if (!b || !tokens || !family_ms || !family_launches) return fail(MSX_ERR_ARG, "null argument");
+    const msx_config &c = b->m->cfg;
+    CU(cudaSetDevice(b->m->device));
+    for (int i = 0; i < max_families; i++) { family_ms[i] = 0.f; family_launches[i] = 0; }
+    if (int e = push_inputs_b(b, tokens)) return e;
+    std::vector<cudaEvent_t> ev;
+    std::vector<int> fam;
+    Launcher L{b->st, b->m->num_sms};
+    L.events = &ev; L.families = &fam;
+    BatchLauncher B{L, b};
+    enqueue_temporal_b(B);
+    if (c.dep_q > 0) enqueue_depformer_b(B);
+    for (int &o : b->host_offset) o++;
+    if (L.err != cudaSuccess) return fail(MSX_ERR_CUDA, std::string("launch failed: ") + cudaGetErrorString(L.err));
+    if (int e = pull_outputs_b(b)) return e;
+    for (size_t i = 0; i + 1 < ev.size(); i++) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+        const int f = fam[i];
+        if (f < max_families) { family_ms[f] += ms; family_launches[f] += 1; }
+    }
+    for (cudaEvent_t e : ev) cudaEventDestroy(e);
+    return 0;
+}
+
+// test hook: y[nb][rows] = W x[nb][k] through quant_q8k_kernel + gemm_q4k_kernel (EPI_STORE)
+extern "C" int msx_test_gemm_batch(int device, int type, const void *w, int64_t k, int64_t rows, const float *x, int nb, const float *alpha,
+                                   float *y) {
+    if (!w || !x || !y || nb < 1 || nb > kMmaCols) return fail(MSX_ERR_ARG, "bad argument");
+    std::unique_ptr<msx_model> m;
+    if (int e = test_setup(device, m)) return e;
+    CU(cudaFuncSetAttribute(gemm_q4k_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemMax));
+    QLinear ql;
+    if (int e = upload_linear(m.get(), w, type, k, rows, 0, &ql)) return e;
+    QTiles qt;
+    if (int e = tiles_of(m.get(), ql, &qt)) return e;
+    if (gemm_stages_for((int)k) < 2) return fail(MSX_ERR_ARG, "k too large");
+    float *dx = nullptr, *dy = nullptr, *da = nullptr; uint8_t *img = nullptr;
+    if (int e = dev_alloc(m.get(), (void **)&dx, (size_t)nb * k * 4)) return e;
+    if (int e = dev_alloc(m.get(), (void **)&dy, (size_t)nb * rows * 4)) return e;
+    if (int e = dev_alloc(m.get(), (void **)&img, (size_t)act_image_bytes((int)k))) return e;
+    CU(cudaMemset(img, 0xff, (size_t)act_image_bytes((int)k)));      // dead columns hold garbage in production too
+    CU(cudaMemcpy(dx, x, (size_t)nb * k * 4, cudaMemcpyHostToDevice));
+    if (alpha) {
+        if (int e = dev_alloc(m.get(), (void **)&da, (size_t)k * 4)) return e;
+        CU(cudaMemcpy(da, alpha, (size_t)k * 4, cudaMemcpyHostToDevice));
+    }
+    QuantArgs q;
+    q.x = dx; q.ld = (int)k; q.alpha = da; q.eps = 1e-8f; q.img = img; q.K = (int)k;
+    quant_q8k_kernel<<<nb, kGemmThreads>>>(q);
+    GemmArgs g;
+    g.w = qt; g.img = img; g.out = dy; g.ld = (int)rows; g.nb = nb; g.epi = EPI_STORE;
+    g.wpt = gemm_wpt_for(qt.n_tiles, qt.nsb, m->num_sms);
+    g.stages = gemm_stages_for((int)k);
+    const int tpr = kGemmWarps / g.wpt;
+    const int n_rounds = (qt.n_tiles + tpr - 1) / tpr;
+    gemm_q4k_kernel<<<std::min(m->num_sms, n_rounds), kGemmThreads, gemm_smem_bytes((int)k, g.stages)>>>(g);
+    CU(cudaGetLastError());
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(y, dy, (size_t)nb * rows * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// micro-benchmark: quant + GEMM pairs over n_mats rotating copies of one matrix, replayed from a CUDA graph
+extern "C" int msx_bench_gemm_batch(int device, const void *w, int64_t k, int64_t rows, int nb, int n_mats, int iters, int epilogue,
+                                    int with_quant, float *avg_us) {
+    if (!w || !avg_us || n_mats < 1 || iters < 1 || nb < 1 || nb > kMmaCols) return fail(MSX_ERR_ARG, "bad argument");
+    std::unique_ptr<msx_model> m;
+    if (int e = test_setup(device, m)) return e;
+    CU(cudaFuncSetAttribute(gemm_q4k_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemMax));
+    std::vector<QTiles> mats(n_mats);
+    for (int i = 0; i < n_mats; i++) {
+        QLinear ql;
+        if (int e = upload_linear(m.get(), w, T_Q4_K, k, rows, epilogue == EPI_GATE ? (int)(rows / 2) : 0, &ql)) return e;
+        if (int e = tiles_of(m.get(), ql, &mats[i])) return e;
+    }
+    float *dx = nullptr, *dy = nullptr; uint8_t *img = nullptr; Ctrl *ctrl = nullptr;
+    const size_t outn = (size_t)nb * std::max<int64_t>(rows, k);
+    if (int e = dev_alloc(m.get(), (void **)&dx, (size_t)nb * k * 4)) return e;
+    if (int e = dev_alloc(m.get(), (void **)&dy, outn * 4)) return e;
+    if (int e = dev_alloc(m.get(), (void **)&img, (size_t)act_image_bytes((int)k))) return e;
+    if (int e = dev_alloc(m.get(), (void **)&ctrl, sizeof(Ctrl) * nb)) return e;
+    std::vector<float> hx((size_t)nb * k);
+    for (size_t i = 0; i < hx.size(); i++) hx[i] = (float)((i * 2654435761u) % 2001) / 1000.f - 1.f;
+    CU(cudaMemcpy(dx, hx.data(), hx.size() * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemset(dy, 0, outn * 4));
+    CU(cudaMemset(ctrl, 0, sizeof(Ctrl) * nb));
+    CU(cudaMemset(img, 0, (size_t)act_image_bytes((int)k)));
+    cudaStream_t st;
+    CU(cudaStreamCreate(&st));
+    Launcher L{st, m->num_sms};
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
+    CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    for (int i = 0; i < iters; i++) {
+        QuantArgs q;
+        q.x = dx; q.ld = (int)k; q.eps = 1e-8f; q.img = img; q.K = (int)k;
+        if (with_quant || i == 0) L.launch_pdl(quant_q8k_kernel, dim3(nb), dim3(kGemmThreads), 0, q);
+        GemmArgs g;
+        g.w = mats[i % n_mats]; g.img = img; g.out = dy; g.ld = (int)(epilogue == EPI_GATE ? rows / 2 : rows); g.nb = nb; g.epi = epilogue; g.ctrl = ctrl;
+        g.wpt = gemm_wpt_for(g.w.n_tiles, g.w.nsb, m->num_sms);
+        g.stages = gemm_stages_for((int)k);
+        const int tpr = kGemmWarps / g.wpt;
+        const int n_rounds = (g.w.n_tiles + tpr - 1) / tpr;
+        L.launch_pdl(gemm_q4k_kernel, dim3(std::min(m->num_sms, n_rounds)), dim3(kGemmThreads), (size_t)gemm_smem_bytes((int)k, g.stages), g);
+    }
+    CU(cudaStreamEndCapture(st, &graph));
+    if (L.err != cudaSuccess) return fail(MSX_ERR_CUDA, std::string("gemm launch: ") + cudaGetErrorString(L.err));
+    CU(cudaGraphInstantiate(&exec, graph, 0));
+    CU(cudaGraphLaunch(exec, st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaEventRecord(e0, st));
+    CU(cudaGraphLaunch(exec, st));
+    CU(cudaEventRecord(e1, st));
+    CU(cudaStreamSynchronize(st));
+    cudaGraphExecDestroy(exec); cudaGraphDestroy(graph);
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    *avg_us = ms * 1000.f / iters;
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaStreamDestroy(st);
+    return 0;
+}

@@ -63,6 +63,7 @@ struct QLinear {
     int32_t K = 0;
     int32_t rows = 0;     // stored ("virtual") rows
     int32_t gs = 32;      // lanes per row group: 32 or 16
+    int32_t gate = 0;     // rows interleaved (gate j, up j) for the gated MLP
 };
 
 // Embedding table kept in its GGUF row format (single rows are gathered, nothing to coalesce).

@@ -10,6 +10,7 @@
 #include <cstring>
 #include <memory>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/moshi_b200.h"
@@ -19,6 +20,7 @@
 #include "gguf_file.h"
 #include "megakernel.cuh"
 #include "misc_kernels.cuh"
+#include "mma_gemm.cuh"
 #include "sample.cuh"
 
 using namespace msx;
@@ -66,6 +68,7 @@ struct msx_model {
     QLinear text_linear;
     std::vector<QLinear> dep_in, linears, extra_heads;
     std::vector<void *> allocs;
+    std::unordered_map<const void *, QTiles> tiles;   // MMA unit layout of a linear, keyed by its qs plane (batch.inl)
     int64_t weight_bytes_per_frame = 0;
     int64_t device_bytes = 0;
     uint8_t *staging = nullptr;
@@ -106,7 +109,7 @@ int upload_linear(msx_model *m, const void *host, int type, int64_t K, int64_t r
     if (int e = ensure_staging(m, raw)) return e;
     CU(cudaMemcpy(m->staging, host, raw, cudaMemcpyHostToDevice));
     QLinear w;
-    w.type = type; w.K = (int)K; w.rows = (int)rows; w.gs = K >= 4096 ? 32 : 16;
+    w.type = type; w.K = (int)K; w.rows = (int)rows; w.gs = K >= 4096 ? 32 : 16; w.gate = perm_half > 0;
     void *qs = nullptr, *sc = nullptr, *dd = nullptr;
     if (type == T_Q4_K) {
         if (int e = dev_alloc(m, &qs, (size_t)rows * K / 2)) return e;
@@ -432,10 +435,10 @@ struct Launcher {
         check();
     }
 
-    void attn(const AttnArgs &a, int heads, int dh, int split, int family = 0) {
+    void attn(const AttnArgs &a, int heads, int dh, int split, int family = 0, int n_streams = 1) {
         fam = family; begin();
         cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(split, heads, 1);
+        cfg.gridDim = dim3(split, heads, n_streams);
         cfg.blockDim = dim3(kThreads, 1, 1);
         cfg.stream = st;
         cudaLaunchAttribute at[2];
@@ -1415,3 +1418,5 @@ extern "C" int msx_test_dequant_repacked(int device, int type, const void *w, in
     CU(cudaMemcpy(out, o, (size_t)n * 4, cudaMemcpyDeviceToHost));
     return 0;
 }
+
+#include "batch.inl"

@@ -19,7 +19,10 @@ struct EmbedArgs {
     int32_t dh = 0;
 };
 
-__device__ __forceinline__ void embed_body(const EmbedArgs &a, int cta, int n_cta, int nthr) {
+// `b` = stream of a batch (batched steps launch grid.y = streams; per-stream buffers are b * dim / b * dh apart)
+__device__ __forceinline__ void embed_body(const EmbedArgs &a0, int cta, int n_cta, int nthr, int b = 0) {
+    EmbedArgs a = a0;
+    a.ctrl += b; a.x += (size_t)b * a.dim; if (a.rope_cs) a.rope_cs += (size_t)b * a.dh;
     const Ctrl *c = a.ctrl;
     const int32_t *toks = c->feed_n ? c->feed + (size_t)(c->frame % c->feed_n) * c->n_in : c->tokens;
     if (cta == 0 && a.rope_cs && (int)threadIdx.x < a.dh / 2) {
@@ -39,7 +42,7 @@ __device__ __forceinline__ void embed_body(const EmbedArgs &a, int cta, int n_ct
         a.x[i] = acc;
     }
 }
-__global__ void __launch_bounds__(kThreads) embed_kernel(const EmbedArgs a) { griddep_launch(); griddep_wait(); embed_body(a, blockIdx.x, gridDim.x, kThreads); }
+__global__ void __launch_bounds__(kThreads) embed_kernel(const EmbedArgs a) { griddep_launch(); griddep_wait(); embed_body(a, blockIdx.x, gridDim.x, kThreads, blockIdx.y); }
 
 // ---- frame bookkeeping ------------------------------------------------------------------------------
 // end of the temporal graph: greedy text token out of the arg-max key, position advances
@@ -54,7 +57,7 @@ __device__ __forceinline__ void finalize_temporal_body(Ctrl *c, int has_depforme
         }
     }
 }
-__global__ void finalize_temporal_kernel(Ctrl *c, int has_depformer) { griddep_launch(); griddep_wait(); finalize_temporal_body(c, has_depformer); }
+__global__ void finalize_temporal_kernel(Ctrl *c, int has_depformer) { griddep_launch(); griddep_wait(); finalize_temporal_body(c + blockIdx.x, has_depformer); }
 
 // end of the depformer graph: collect the dep_q greedy tokens (lm.h:548-552)
 // single warp does the whole job (dep_q <= 40: two passes of 32 lanes)
@@ -71,7 +74,7 @@ __device__ __forceinline__ void finalize_depformer_body(Ctrl *c, int dep_q) {
         if (threadIdx.x == 0) c->frame += 1;
     }
 }
-__global__ void finalize_depformer_kernel(Ctrl *c, int dep_q) { griddep_launch(); griddep_wait(); finalize_depformer_body(c, dep_q); }
+__global__ void finalize_depformer_kernel(Ctrl *c, int dep_q) { griddep_launch(); griddep_wait(); finalize_depformer_body(c + blockIdx.x, dep_q); }
 
 // ---- load-time repack (GGUF row-major blocks -> device tiles, see common.cuh QLinear) --------------
 // perm_half > 0 interleaves rows for the gated MLP: stored row v <- source row (v&1 ? perm_half + v/2 : v/2)

@@ -338,3 +338,92 @@ def test_top_k_sampling_matches_oracle(msx, orc, gguf_for, preset, quant):
     gs.set_sampling(0.0, 0.0); os_.set_sampling(0.0, 0.0)
     t_ref, lg_ref, _ = os_.step_temporal(toks); t_gpu, lg_gpu, _ = gs.step_temporal(toks)
     assert t_gpu == t_ref == int(np.argmax(lg_ref))
+
+
+# ---------------------------------------------------------------------------------------------------
+# batched streams (SURVEY.md §8e row 1 / BASELINE.json config 5): tensor-core dequant-GEMM, 8 columns
+# ---------------------------------------------------------------------------------------------------
+GEMM_SHAPES = [(4096, 512), (4096, 12288), (11264, 256), (1024, 3072), (2816, 1024), (1024, 2048), (4096, 6), (256, 40), (768, 520)]
+
+
+@pytest.mark.parametrize("k,rows", GEMM_SHAPES)
+@pytest.mark.parametrize("nb,rms", [(8, False), (8, True), (3, True), (1, False)])
+def test_batched_gemm_vs_oracle(msx, orc, k, rows, nb, rms):
+    """every column of the batched quantise + mma GEMM equals the oracle's ggml-faithful mul_mat of that column"""
+    from moshi_cpp_b200 import synth
+    rng = np.random.default_rng(k * 17 + rows + nb)
+    raw = synth.random_tensor(rng, synth.GGML_Q4_K, rows, k, 1.0 / np.sqrt(k))
+    x = rng.standard_normal((nb, k)).astype(np.float32) * 1.3
+    x[0, 5] = 0.0
+    if nb > 1:
+        x[1, :256] = 0.0                                  # an all-zero Q8_K block (d = 0)
+    alpha = (1.0 + 0.1 * rng.standard_normal(k)).astype(np.float32) if rms else None
+    got = msx.test_gemm_batch(synth.GGML_Q4_K, raw, k, x, alpha)
+    for b in range(nb):
+        xin = orc.rms_norm(x[b], alpha) if rms else x[b]
+        ref = orc.mul_mat_vec(synth.GGML_Q4_K, raw, k, xin)
+        assert max_rel(got[b], ref) < GEMV_TOL, f"column {b}"
+        assert_bitwise_mostly(got[b], ref, f"gemm column {b}")
+
+
+@pytest.mark.parametrize("preset,n", [("tiny", 8), ("tiny", 3), ("tiny_pplex", 5), ("moshi7b_l2", 8)])
+def test_batch_equals_independent_streams(msx, gguf_for, preset, n):
+    """n streams stepped as one batch (different inputs, free running) produce the tokens and logits of n
+    single msx_streams: the batched kernels share the single-stream arithmetic (double accumulation of exact
+    block terms), only the summation order of the fp64 partials differs."""
+    path, cfg = gguf_for(preset, "q4_k")
+    gm = msx.Model(path, cfg)
+    batch = msx.Batch(gm, n)
+    singles = [msx.Stream(gm) for _ in range(n)]
+    rng = np.random.default_rng(9)
+    frames = 10 if preset != "moshi7b_l2" else 3
+    for f in range(frames):
+        toks = rng.integers(0, cfg["card"], size=(n, cfg["n_q"] + 1)).astype(np.int32)
+        toks[:, 0] = rng.integers(0, cfg["text_card"], size=n)
+        if f == 0:
+            toks[0, :] = -1                                   # zero embedding rows (lm_utils.h:172-182)
+        out = batch.step(toks)
+        for s in range(n):
+            t, tl, _ = singles[s].step_temporal(toks[s])
+            a, al = singles[s].step_depformer(t)
+            btl, bal = batch.logits(s)
+            assert max_rel(btl, tl) < 2e-3 and max_rel(bal, al) < 2e-3, f"frame {f} stream {s}"
+            assert out[s, 0] == t and np.array_equal(out[s, 1:], a), f"frame {f} stream {s}"
+            assert_bitwise_mostly(btl, tl, f"text logits frame {f} stream {s}")
+
+
+def test_batch_stream_restart_and_resident(msx, gguf_for):
+    """streams of a batch sit at their own positions: restarting one leaves the others untouched; the resident
+    replay gives the tokens of the per-call path"""
+    path, cfg = gguf_for("tiny", "q4_k")
+    gm = msx.Model(path, cfg)
+    n = 4
+    batch = msx.Batch(gm, n); ref = msx.Batch(gm, n)
+    rng = np.random.default_rng(3)
+    frames = rng.integers(0, cfg["card"], size=(n, 12, cfg["n_q"] + 1)).astype(np.int32)
+    outs = [batch.step(frames[:, f]) for f in range(6)]
+    batch.reset(2)
+    assert batch.offset(2) == 0 and batch.offset(1) == 6
+    # stream 2 replays its first frames, the others continue
+    nxt = frames[:, 6:9].copy(); nxt[2] = frames[2, 0:3]
+    outs2 = [batch.step(nxt[:, f]) for f in range(3)]
+    for f in range(3):
+        assert np.array_equal(outs2[f][2], outs[f][2]), "restarted stream repeats its history"
+    ms, tok = ref.run_resident(frames, 9, want_tokens=True)
+    for f in range(6):
+        assert np.array_equal(tok[:, f], outs[f])
+    for f in range(3):
+        for s in (0, 1, 3):
+            assert np.array_equal(tok[s, 6 + f], outs2[f][s])
+
+
+def test_batch_rejects_q8_0_and_bad_sizes(msx, gguf_for):
+    path, cfg = gguf_for("tiny", "q8_0")
+    gm = msx.Model(path, cfg)
+    with pytest.raises(msx.MsxError):
+        msx.Batch(gm, 4)
+    path, cfg = gguf_for("tiny", "q4_k")
+    gm = msx.Model(path, cfg)
+    for n in (0, 9):
+        with pytest.raises(msx.MsxError):
+            msx.Batch(gm, n)
