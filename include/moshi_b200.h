@@ -183,6 +183,9 @@ MSX_API int msx_batch_profile_frame(msx_batch *b, const int32_t *tokens, float *
 MSX_API int msx_test_gemm_batch(int device, int type, const void *w, int64_t k, int64_t rows, const float *x, int nb, const float *alpha, float *y);
 MSX_API int msx_bench_gemm_batch(int device, const void *w, int64_t k, int64_t rows, int nb, int n_mats, int iters, int epilogue, int with_quant,
                                  float *avg_us);
+/* same, plus per-CTA globaltimer stamps [iters][148][8]: entry, ring primed, predecessor done, image landed, main loop done */
+MSX_API int msx_bench_gemm_batch_ex(int device, const void *w, int64_t k, int64_t rows, int nb, int n_mats, int iters, int epilogue, int with_quant,
+                                    float *avg_us, long long *stamps_out);
 
 MSX_API int msx_test_gemv(int device, int type, const void *w, int64_t k, int64_t rows,
                           const float *x, const float *alpha, int prologue, float *y);

@@ -136,6 +136,7 @@ def lib():
     L.msx_batch_run_resident.argtypes = [vp, vp, C.c_int, C.c_int, vp, C.POINTER(C.c_float)]
     L.msx_batch_profile_frame.argtypes = [vp, vp, vp, vp, C.c_int]
     L.msx_test_gemm_batch.argtypes = [C.c_int, C.c_int, vp, C.c_int64, C.c_int64, vp, C.c_int, vp, vp]
+    L.msx_bench_gemm_batch_ex.argtypes = [C.c_int, vp, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), vp]
     L.msx_bench_gemm_batch.argtypes = [C.c_int, vp, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]
     L.msx_test_dequant_rows.argtypes = [C.c_int, C.c_int, vp, C.c_int64, C.c_int64, vp, C.c_int, vp]
     L.msx_test_dequant_repacked.argtypes = [C.c_int, C.c_int, vp, C.c_int64, C.c_int64, vp]
@@ -463,3 +464,11 @@ def bench_gemm_batch(w_raw: np.ndarray, k: int, nb: int, n_mats: int, iters: int
     us = C.c_float(0)
     _check(lib().msx_bench_gemm_batch(device, _p(w_raw), k, w_raw.shape[0], nb, n_mats, iters, epilogue, 1 if with_quant else 0, C.byref(us)))
     return float(us.value)
+
+
+def bench_gemm_batch_stamps(w_raw: np.ndarray, k: int, nb: int, n_mats: int, iters: int, epilogue: int = 0, with_quant: bool = True, device: int = 0):
+    w_raw = np.ascontiguousarray(w_raw)
+    us = C.c_float(0)
+    st = np.zeros((iters, 148, 8), dtype=np.int64)
+    _check(lib().msx_bench_gemm_batch_ex(device, _p(w_raw), k, w_raw.shape[0], nb, n_mats, iters, epilogue, 1 if with_quant else 0, C.byref(us), _p(st)))
+    return float(us.value), st

@@ -86,7 +86,7 @@ struct BatchLauncher {
         QuantArgs q;
         q.x = x; q.ld = ld; q.alpha = alpha; q.eps = 1e-8f; q.norm_out = norm_out; q.norm_ld = norm_ld; q.img = img ? img : b->img; q.K = K;
         L.fam = family; L.begin();
-        L.launch_pdl(quant_q8k_kernel, dim3(b->n), dim3(kGemmThreads), 0, q);
+        L.launch_pdl(quant_q8k_kernel, dim3(b->n, quant_parts_for(K)), dim3(kGemmThreads), 0, q);
         L.check();
     }
     void gemm(const QLinear &w, float *out, int ld, int epi, int family, int key_index = -1, const EmbTable *emb = nullptr, int emb_step = 0,
@@ -95,12 +95,9 @@ struct BatchLauncher {
         if (int e = tiles_of(b->m, w, &g.w)) { err = e; return; }
         g.img = img ? img : b->img; g.out = out; g.ld = ld; g.nb = b->n; g.epi = epi; g.ctrl = b->ctrl; g.key_index = key_index; g.emb_step = emb_step;
         if (emb) g.emb = *emb;
-        g.wpt = gemm_wpt_for(g.w.n_tiles, g.w.nsb, L.num_sms);
         g.stages = gemm_stages_for(w.K);
-        const int tpr = kGemmWarps / g.wpt;
-        const int n_rounds = (g.w.n_tiles + tpr - 1) / tpr;
         L.fam = family; L.begin();
-        L.launch_pdl(gemm_q4k_kernel, dim3(std::min(L.num_sms, n_rounds)), dim3(kGemmThreads), (size_t)gemm_smem_bytes(w.K, g.stages), g);
+        L.launch_pdl(gemm_q4k_kernel, dim3(gemm_grid_for(g.w.n_tiles, L.num_sms)), dim3(kGemmThreads), (size_t)gemm_smem_bytes(w.K, g.stages), g);
         L.check();
     }
 };
@@ -417,14 +414,11 @@ extern "C" int msx_test_gemm_batch(int device, int type, const void *w, int64_t 
     }
     QuantArgs q;
     q.x = dx; q.ld = (int)k; q.alpha = da; q.eps = 1e-8f; q.img = img; q.K = (int)k;
-    quant_q8k_kernel<<<nb, kGemmThreads>>>(q);
+    quant_q8k_kernel<<<dim3(nb, quant_parts_for((int)k)), kGemmThreads>>>(q);
     GemmArgs g;
     g.w = qt; g.img = img; g.out = dy; g.ld = (int)rows; g.nb = nb; g.epi = EPI_STORE;
-    g.wpt = gemm_wpt_for(qt.n_tiles, qt.nsb, m->num_sms);
     g.stages = gemm_stages_for((int)k);
-    const int tpr = kGemmWarps / g.wpt;
-    const int n_rounds = (qt.n_tiles + tpr - 1) / tpr;
-    gemm_q4k_kernel<<<std::min(m->num_sms, n_rounds), kGemmThreads, gemm_smem_bytes((int)k, g.stages)>>>(g);
+    gemm_q4k_kernel<<<gemm_grid_for(qt.n_tiles, m->num_sms), kGemmThreads, gemm_smem_bytes((int)k, g.stages)>>>(g);
     CU(cudaGetLastError());
     CU(cudaDeviceSynchronize());
     CU(cudaMemcpy(y, dy, (size_t)nb * rows * 4, cudaMemcpyDeviceToHost));
@@ -432,8 +426,14 @@ extern "C" int msx_test_gemm_batch(int device, int type, const void *w, int64_t 
 }
 
 // micro-benchmark: quant + GEMM pairs over n_mats rotating copies of one matrix, replayed from a CUDA graph
+extern "C" int msx_bench_gemm_batch_ex(int device, const void *w, int64_t k, int64_t rows, int nb, int n_mats, int iters, int epilogue,
+                                       int with_quant, float *avg_us, long long *stamps_out /* [iters][148][8] or null */);
 extern "C" int msx_bench_gemm_batch(int device, const void *w, int64_t k, int64_t rows, int nb, int n_mats, int iters, int epilogue,
                                     int with_quant, float *avg_us) {
+    return msx_bench_gemm_batch_ex(device, w, k, rows, nb, n_mats, iters, epilogue, with_quant, avg_us, nullptr);
+}
+extern "C" int msx_bench_gemm_batch_ex(int device, const void *w, int64_t k, int64_t rows, int nb, int n_mats, int iters, int epilogue,
+                                       int with_quant, float *avg_us, long long *stamps_out) {
     if (!w || !avg_us || n_mats < 1 || iters < 1 || nb < 1 || nb > kMmaCols) return fail(MSX_ERR_ARG, "bad argument");
     std::unique_ptr<msx_model> m;
     if (int e = test_setup(device, m)) return e;
@@ -456,6 +456,8 @@ extern "C" int msx_bench_gemm_batch(int device, const void *w, int64_t k, int64_
     CU(cudaMemset(dy, 0, outn * 4));
     CU(cudaMemset(ctrl, 0, sizeof(Ctrl) * nb));
     CU(cudaMemset(img, 0, (size_t)act_image_bytes((int)k)));
+    long long *d_stamps = nullptr;
+    if (stamps_out) { if (int e = dev_alloc(m.get(), (void **)&d_stamps, (size_t)iters * 148 * 8 * 8)) return e; CU(cudaMemset(d_stamps, 0, (size_t)iters * 148 * 8 * 8)); }
     cudaStream_t st;
     CU(cudaStreamCreate(&st));
     Launcher L{st, m->num_sms};
@@ -466,14 +468,12 @@ extern "C" int msx_bench_gemm_batch(int device, const void *w, int64_t k, int64_
     for (int i = 0; i < iters; i++) {
         QuantArgs q;
         q.x = dx; q.ld = (int)k; q.eps = 1e-8f; q.img = img; q.K = (int)k;
-        if (with_quant || i == 0) L.launch_pdl(quant_q8k_kernel, dim3(nb), dim3(kGemmThreads), 0, q);
+        if (with_quant || i == 0) L.launch_pdl(quant_q8k_kernel, dim3(nb, quant_parts_for((int)k)), dim3(kGemmThreads), 0, q);
         GemmArgs g;
         g.w = mats[i % n_mats]; g.img = img; g.out = dy; g.ld = (int)(epilogue == EPI_GATE ? rows / 2 : rows); g.nb = nb; g.epi = epilogue; g.ctrl = ctrl;
-        g.wpt = gemm_wpt_for(g.w.n_tiles, g.w.nsb, m->num_sms);
+        if (d_stamps) g.stamps = d_stamps + (size_t)i * 148 * 8;
         g.stages = gemm_stages_for((int)k);
-        const int tpr = kGemmWarps / g.wpt;
-        const int n_rounds = (g.w.n_tiles + tpr - 1) / tpr;
-        L.launch_pdl(gemm_q4k_kernel, dim3(std::min(m->num_sms, n_rounds)), dim3(kGemmThreads), (size_t)gemm_smem_bytes((int)k, g.stages), g);
+        L.launch_pdl(gemm_q4k_kernel, dim3(gemm_grid_for(g.w.n_tiles, m->num_sms)), dim3(kGemmThreads), (size_t)gemm_smem_bytes((int)k, g.stages), g);
     }
     CU(cudaStreamEndCapture(st, &graph));
     if (L.err != cudaSuccess) return fail(MSX_ERR_CUDA, std::string("gemm launch: ") + cudaGetErrorString(L.err));
@@ -488,6 +488,7 @@ extern "C" int msx_bench_gemm_batch(int device, const void *w, int64_t k, int64_
     float ms = 0;
     CU(cudaEventElapsedTime(&ms, e0, e1));
     *avg_us = ms * 1000.f / iters;
+    if (stamps_out) CU(cudaMemcpy(stamps_out, d_stamps, (size_t)iters * 148 * 8 * 8, cudaMemcpyDeviceToHost));
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaStreamDestroy(st);
     return 0;
 }

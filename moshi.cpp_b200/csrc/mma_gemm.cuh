@@ -104,6 +104,8 @@ struct QuantArgs {
 };
 
 constexpr int kQChunk = 3;
+// CTAs per column: every CTA reduces the whole column (RMSNorm) but quantises only every gridDim.y-th block of each warp
+__host__ inline int quant_parts_for(int K) { const int per_warp = ((K >> 8) + kGemmWarps - 1) / kGemmWarps; return per_warp < 1 ? 1 : (per_warp > kQChunk ? kQChunk : per_warp); }
 __global__ void __launch_bounds__(kGemmThreads) quant_q8k_kernel(const QuantArgs a) {
     __shared__ double red[kGemmWarps];
     griddep_launch();
@@ -160,6 +162,7 @@ __global__ void __launch_bounds__(kGemmThreads) quant_q8k_kernel(const QuantArgs
 #pragma unroll
         for (int j = 0; j < kQChunk; j++) {
             if (c0 + j >= nb_w) continue;                    // warp-uniform
+            if ((c0 + j) % (int)gridDim.y != (int)blockIdx.y) continue;   // long columns: the warp's blocks are dealt over gridDim.y CTAs
             const int blk = warp + (c0 + j) * kGemmWarps, e0 = e0_of(c0 + j);
             if (norm) {
 #pragma unroll
@@ -214,12 +217,12 @@ struct GemmArgs {
     float *out = nullptr; int32_t ld = 0;   // out[col * ld + row]
     int32_t nb = 0;                   // live columns (streams)
     int32_t epi = 0;
-    int32_t wpt = 16;                 // warps sharing one tile (power of two, 2..16)
     int32_t stages = 4;
     Ctrl *ctrl = nullptr;             // [nb] control blocks
     int32_t key_index = -1;           // EPI_ARGMAX: -1 = text_key, k = audio_key[k]
     int32_t emb_step = 0;             // EPI_ADD_EMB
     EmbTable emb;
+    long long *stamps = nullptr;      // debug: [grid][8] globaltimer stamps
 };
 
 __device__ __forceinline__ void mbar_init(uint32_t addr, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count) : "memory"); }
@@ -267,8 +270,8 @@ __device__ __forceinline__ void unit_compute(const uint8_t *slot, const uint8_t 
         int c[4], d[4];
         mma_u8s8(c, w.x & 0x0F0F0F0Fu, w.y & 0x0F0F0F0Fu, w.z & 0x0F0F0F0Fu, w.w & 0x0F0F0F0Fu, xb.x, xb.y);
         mma_u8s8(d, w.x & 0xF0F0F0F0u, w.y & 0xF0F0F0F0u, w.z & 0xF0F0F0F0u, w.w & 0xF0F0F0F0u, xb.z, xb.w);   // 16 x the high-nibble dots
-        const int slg = (int)(scg[p] & 0xff), shg = (int)((scg[p] >> 8) & 0xff);
-        const int slh = (int)(sch[p] & 0xff), shh = (int)((sch[p] >> 8) & 0xff);
+        const int slg = (int)__byte_perm(scg[p], 0, 0x4440), shg = (int)__byte_perm(scg[p], 0, 0x4441);
+        const int slh = (int)__byte_perm(sch[p], 0, 0x4440), shh = (int)__byte_perm(sch[p], 0, 0x4441);
         lo[0] += slg * c[0]; lo[1] += slg * c[1]; lo[2] += slh * c[2]; lo[3] += slh * c[3];
         hi[0] += shg * d[0]; hi[1] += shg * d[1]; hi[2] += shh * d[2]; hi[3] += shh * d[3];
         const uint2 bw = *reinterpret_cast<const uint2 *>(bsw + p * 8);
@@ -284,9 +287,33 @@ __device__ __forceinline__ void unit_compute(const uint8_t *slot, const uint8_t 
     acc[3] = fma((double)__fmul_rn(dmh.x, dxv.y), (double)(lo[3] + (hi[3] >> 4)), acc[3]); acc[3] = fma(-(double)__fmul_rn(dmh.y, dxv.y), (double)mn[3], acc[3]);
 }
 
+// Work schedule of one CTA.  The CTA owns a contiguous range of R tiles and walks it in "rounds": a round
+// takes n = the largest power of two <= min(remaining, 8) tiles and gives each of them wpt = 16 / n warps,
+// which split the tile's super-blocks (sb = wq, wq + wpt, ...).  Every round therefore costs each warp
+// nsb * n / 16 units whatever R is (perfect balance inside the CTA), needs one CTA barrier, and its
+// partial accumulators always fill exactly one 16 KB buffer.
+struct WarpRound {
+    int tile0, rem;        // first tile of the round, tiles left including this round
+    int n, lw;             // tiles in this round, log2(warps per tile)
+    int tile, wq, upr;     // this warp: its tile, its first super-block, its units in this round
+};
+__device__ __forceinline__ void round_setup(WarpRound &w, int warp, int nsb) {
+    if (w.rem >= 8) { w.n = 8; w.lw = 1; } else if (w.rem >= 4) { w.n = 4; w.lw = 2; } else if (w.rem >= 2) { w.n = 2; w.lw = 3; } else { w.n = 1; w.lw = 4; }
+    const int wpt = 1 << w.lw;
+    w.tile = w.tile0 + (warp >> w.lw);
+    w.wq = warp & (wpt - 1);
+    w.upr = (w.rem > 0 && w.wq < nsb) ? (nsb - w.wq + wpt - 1) >> w.lw : 0;
+}
+__device__ __forceinline__ void round_next(WarpRound &w, int warp, int nsb) {
+    w.tile0 += w.n; w.rem -= w.n;
+    round_setup(w, warp, nsb);
+}
+
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_q4k_kernel(const GemmArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
     griddep_launch();
+    long long *stamp = a.stamps ? a.stamps + (size_t)blockIdx.x * 8 : nullptr;
+    if (stamp && threadIdx.x == 0) stamp[0] = global_ns();
     const int lane = threadIdx.x & 31, warp = uniform_warp_id();
     const int g = lane >> 2, t = lane & 3;
     const int K = a.w.K, nsb = a.w.nsb, S = a.stages;
@@ -299,14 +326,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_q4k_kernel(const GemmArg
     const uint32_t ring_u32 = (uint32_t)__cvta_generic_to_shared(ring);
     const uint32_t my_bar = bar_u32 + 8 + warp * (kGemmMaxStages * 8);
 
-    const int wpt = a.wpt, tpr = kGemmWarps / wpt;
-    const int n_rounds = (a.w.n_tiles + tpr - 1) / tpr;
-    const int r0 = (int)((long long)blockIdx.x * n_rounds / gridDim.x), r1 = (int)((long long)(blockIdx.x + 1) * n_rounds / gridDim.x);
-    const int tau = warp / wpt, wq = warp % wpt;
-    const int upr = wq < nsb ? (nsb - wq + wpt - 1) / wpt : 0;                         // units of this warp per round
-    const int r_valid_end = tau < a.w.n_tiles ? (a.w.n_tiles - 1 - tau) / tpr + 1 : 0;  // rounds r < r_valid_end have a tile for this warp
-    const int my_rounds = max(0, min(r1, r_valid_end) - r0);
-    const int n_units = my_rounds * upr;
+    const int t_begin = (int)((long long)blockIdx.x * a.w.n_tiles / gridDim.x);
+    const int t_end = (int)((long long)(blockIdx.x + 1) * a.w.n_tiles / gridDim.x);
 
     if (lane == 0) {
         for (int s = 0; s < S; s++) mbar_init(my_bar + s * 8, 1);
@@ -314,91 +335,115 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_q4k_kernel(const GemmArg
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
-    // producer cursor
-    int pr = r0, pi = 0;
-    auto issue = [&](int u) {        // lane 0 only
-        const int s = u % S;
-        const uint8_t *src = a.w.units + ((size_t)(pr * tpr + tau) * nsb + wq + pi * wpt) * kUnitBytes;
-        mbar_expect_tx(my_bar + s * 8, kUnitBytes);
-        bulk_g2s(ring_u32 + s * kUnitBytes, src, kUnitBytes, my_bar + s * 8);
-        if (++pi == upr) { pi = 0; pr++; }
+    // producer cursor (lane 0): walks the same schedule as the consumer, S units ahead
+    WarpRound pc{t_begin, t_end - t_begin};
+    round_setup(pc, warp, nsb);
+    int pi = 0, ps = 0;                 // unit inside the round, ring slot
+    const uint8_t *psrc = a.w.units + ((size_t)pc.tile * nsb + pc.wq) * kUnitBytes;
+    auto issue = [&]() -> bool {       // lane 0 only; false when the warp's work list is exhausted
+        if (pi >= pc.upr) {
+            do { round_next(pc, warp, nsb); } while (pc.rem > 0 && pc.upr == 0);
+            if (pc.rem <= 0) return false;
+            pi = 0;
+            psrc = a.w.units + ((size_t)pc.tile * nsb + pc.wq) * kUnitBytes;
+        }
+        mbar_expect_tx(my_bar + ps * 8, kUnitBytes);
+        bulk_g2s(ring_u32 + ps * kUnitBytes, psrc, kUnitBytes, my_bar + ps * 8);
+        psrc += (size_t)kUnitBytes << pc.lw;
+        pi++;
+        if (++ps == S) ps = 0;
+        return true;
     };
     // weights never depend on the previous kernel: fill the ring before waiting for it (PDL)
-    if (lane == 0) for (int u = 0; u < S && u < n_units; u++) issue(u);
+    if (lane == 0) for (int u = 0; u < S; u++) if (!issue()) break;
     __syncthreads();                  // image barrier initialised
+    if (stamp && threadIdx.x == 0) stamp[1] = global_ns();
     griddep_wait();
-    if (threadIdx.x == 0) {
-        mbar_expect_tx(bar_u32, (uint32_t)img_sz);
-        bulk_g2s((uint32_t)__cvta_generic_to_shared(img), a.img, (uint32_t)img_sz, bar_u32);
+    if (stamp && threadIdx.x == 0) stamp[2] = global_ns();
+    // activation image: 16 bulk copies (one per warp) so the L2 -> shared transfer is requested in parallel
+    if (threadIdx.x == 0) mbar_expect_tx(bar_u32, (uint32_t)img_sz);
+    if (lane == 0) {
+        const int piece = ((img_sz / kGemmWarps) + 15) & ~15;
+        const int off = warp * piece;
+        const int len = min(piece, img_sz - off);
+        if (len > 0) bulk_g2s((uint32_t)__cvta_generic_to_shared(img) + off, a.img + off, (uint32_t)len, bar_u32);
     }
     // per-thread epilogue constants: as reducer this thread owns column 2t + (warp & 1)
     const int col = 2 * t + (warp & 1);
     const bool col_live = col < a.nb;
+    float *const ocol = a.out + (size_t)col * a.ld;
     int emb_token = 0;
     if (a.epi == EPI_ADD_EMB && col_live) emb_token = depformer_prev_token(a.ctrl + col, a.emb_step);
     unsigned long long best = 0ull;
     mbar_wait(bar_u32, 0);
+    if (stamp && threadIdx.x == 0) stamp[3] = global_ns();
 
-    int u = 0;
+    WarpRound cr{t_begin, t_end - t_begin};
+    round_setup(cr, warp, nsb);
+    int cs = 0; uint32_t cphase = 0;    // consumer ring slot and its mbarrier parity
+    int rr = 0;
 #pragma unroll 1
-    for (int r = r0; r < r1; r++) {
-        const int rr = r - r0;
+    for (; cr.rem > 0; round_next(cr, warp, nsb), rr++) {
         double *pbuf = part + (size_t)(rr & 1) * (kGemmWarps * 128);
-        if (r < r_valid_end && upr > 0) {
+        // reducer role of this warp in this round: two rotating warps per tile (parity = column parity)
+        const int idx = (warp - ((rr * 2 * cr.n) & (kGemmWarps - 1))) & (kGemmWarps - 1);
+        const bool reducer = idx < 2 * cr.n && col_live;
+        const int red_tile = cr.tile0 + (idx >> 1), e = idx & 1;
+        float old0 = 0.f, old1 = 0.f;
+        if (reducer && a.epi == EPI_RESID) {      // residual: old values requested now, consumed after the round's dot products
+            const int row0 = red_tile * 16 + g;
+            if (row0 < a.w.rows) old0 = __ldcg(ocol + row0);
+            if (row0 + 8 < a.w.rows) old1 = __ldcg(ocol + row0 + 8);
+        }
+        if (cr.upr > 0) {
             double acc[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll 1
-            for (int i = 0; i < upr; i++, u++) {
-                const int s = u % S;
-                mbar_wait(my_bar + s * 8, (uint32_t)((u / S) & 1));
-                unit_compute(ring + (size_t)s * kUnitBytes, img, K, wq + i * wpt, lane, acc);
+            for (int i = 0; i < cr.upr; i++) {
+                mbar_wait(my_bar + cs * 8, cphase);
+                unit_compute(ring + (size_t)cs * kUnitBytes, img, K, cr.wq + (i << cr.lw), lane, acc);
                 __syncwarp();
-                if (lane == 0 && u + S < n_units) issue(u + S);
+                if (lane == 0) issue();
+                if (++cs == S) { cs = 0; cphase ^= 1; }
             }
             double *pw = pbuf + warp * 128 + lane;
             pw[0] = acc[0]; pw[32] = acc[1]; pw[64] = acc[2]; pw[96] = acc[3];
         }
         __syncthreads();
-        // two rotating warps per tile add the partials in fixed order and run the epilogue
-        const int idx = (warp - ((rr * tpr * 2) & (kGemmWarps - 1))) & (kGemmWarps - 1);
-        if (idx < tpr * 2) {
-            const int tq = idx >> 1, e = idx & 1;          // e == warp & 1
-            const int tile = r * tpr + tq;
-            if (tile < a.w.n_tiles && col_live) {
-                const int nw = min(wpt, nsb);
-                double s0 = 0.0, s1 = 0.0;
-                for (int j = 0; j < nw; j++) {
-                    const double *pj = pbuf + (tq * wpt + j) * 128 + lane;
-                    s0 += pj[e * 32]; s1 += pj[(e + 2) * 32];
-                }
-                const float v0 = (float)s0, v1 = (float)s1;
-                const int row0 = tile * 16 + g, row1 = row0 + 8;
-                float *o = a.out + (size_t)col * a.ld;
-                if (a.epi == EPI_GATE) {
-                    const int h = tile * 8 + g;
-                    if (2 * h < a.w.rows) o[h] = (v0 / (1.0f + (float)exp((double)(-v0)))) * v1;
-                } else {
+        if (reducer) {
+            const int nw = min(1 << cr.lw, nsb);
+            double s0 = 0.0, s1 = 0.0;
+            const double *pj = pbuf + ((idx >> 1) << cr.lw) * 128 + lane;
+            for (int j = 0; j < nw; j++, pj += 128) { s0 += pj[e * 32]; s1 += pj[(e + 2) * 32]; }
+            const float v0 = (float)s0, v1 = (float)s1;
+            const int row0 = red_tile * 16 + g, row1 = row0 + 8;
+            if (a.epi == EPI_GATE) {
+                const int h = red_tile * 8 + g;
+                if (2 * h < a.w.rows) ocol[h] = (v0 / (1.0f + (float)exp((double)(-v0)))) * v1;
+            } else if (a.epi == EPI_RESID) {
+                if (row0 < a.w.rows) ocol[row0] = old0 + v0;
+                if (row1 < a.w.rows) ocol[row1] = old1 + v1;
+            } else {
 #pragma unroll
-                    for (int hh = 0; hh < 2; hh++) {
-                        const int row = hh ? row1 : row0;
-                        const float v = hh ? v1 : v0;
-                        if (row >= a.w.rows) continue;
-                        if (a.epi == EPI_STORE) o[row] = v;
-                        else if (a.epi == EPI_RESID) o[row] = __ldcg(o + row) + v;
-                        else if (a.epi == EPI_ARGMAX) {
-                            o[row] = v;
-                            const unsigned long long k = argmax_key(v, row);
-                            best = k > best ? k : best;
-                        } else if (a.epi == EPI_ADD_EMB) {
-                            float em;
-                            if (a.emb_step == 0) { em = emb_element(a.emb, emb_token < 0 ? 0 : emb_token, row); em = em * (emb_token == -1 ? 0.f : 1.f); }
-                            else em = emb_element(a.emb, emb_token, row);
-                            o[row] = v + em;
-                        }
+                for (int hh = 0; hh < 2; hh++) {
+                    const int row = hh ? row1 : row0;
+                    const float v = hh ? v1 : v0;
+                    if (row >= a.w.rows) continue;
+                    if (a.epi == EPI_STORE) ocol[row] = v;
+                    else if (a.epi == EPI_ARGMAX) {
+                        ocol[row] = v;
+                        const unsigned long long k = argmax_key(v, row);
+                        best = k > best ? k : best;
+                    } else if (a.epi == EPI_ADD_EMB) {
+                        float em;
+                        if (a.emb_step == 0) { em = emb_element(a.emb, emb_token < 0 ? 0 : emb_token, row); em = em * (emb_token == -1 ? 0.f : 1.f); }
+                        else em = emb_element(a.emb, emb_token, row);
+                        ocol[row] = v + em;
                     }
                 }
             }
         }
     }
+    if (stamp && threadIdx.x == 0) stamp[4] = global_ns();
     if (a.epi == EPI_ARGMAX) {
         // best over the 8 row groups of the warp (lanes sharing t), then over the warps of equal parity
 #pragma unroll
@@ -416,12 +461,6 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_q4k_kernel(const GemmArg
     }
 }
 
-__host__ inline int gemm_wpt_for(int n_tiles, int nsb, int num_sms) {
-    int wpt = 2;
-    while (wpt * 2 <= kGemmWarps && wpt * 2 <= nsb) wpt *= 2;
-    // small matrices: spread the tiles over more SMs (idle warps are cheaper than idle SMs)
-    while (wpt < kGemmWarps && (n_tiles + kGemmWarps / wpt - 1) / (kGemmWarps / wpt) < num_sms) wpt *= 2;
-    return wpt;
-}
+__host__ inline int gemm_grid_for(int n_tiles, int num_sms) { return n_tiles < num_sms ? n_tiles : num_sms; }
 
 }  // namespace msx
