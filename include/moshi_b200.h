@@ -51,6 +51,10 @@ typedef struct msx_config {
     int32_t schedule[MSX_MAX_STEPS]; /* depformer_weights_per_step_schedule */
     int32_t personaplex;             /* model_type == "personaplex" */
     int32_t extra_heads;             /* extra_heads_num_heads */
+    /* TTS family (moshi.h:111-156): */
+    int32_t cross_attention;         /* temporal layers carry norm_cross + cross_attention (lm_default.h:18-34) */
+    int32_t demux_second_stream;     /* two-stream text embeddings (lm_utils.h:14-125) */
+    int32_t dep_low_rank;            /* depformer_low_rank_embeddings (0 = none) */
 } msx_config;
 
 typedef struct msx_model msx_model;   /* device-resident, repacked weights (one GPU)      */
@@ -109,6 +113,11 @@ MSX_API int msx_step(msx_stream *s, const int32_t *tokens, int32_t *out_tokens);
 MSX_API int msx_stream_set_sampling(msx_stream *s, float temp_text, float temp_audio, int top_k_text, int top_k_audio);
 MSX_API int msx_stream_set_noise(msx_stream *s, const float *noise_text, const float *noise_audio);
 /* STT VAD head (lm.h:966-976): softmax(extra_heads[2] . transformer_out)[0]; 0 if < 3 extra heads */
+/* TTS conditioning (reference: moshi_lm_start -> init(), moshi.cpp:851-883; transformer.h:343-396; lm.h:575-577).
+ * cond_sum[dim] (or NULL) is added to the embedding sum of every frame; cond_cross[tc][dim] (or NULL) is projected once
+ * through every layer's cross_attention.in_proj rows [dim, 3*dim) into the f32 k_cross / v_cross memory.  The
+ * conditioners that PRODUCE these tensors (src/moshi.cpp:296-366) are outside the per-frame path. */
+MSX_API int msx_stream_set_condition(msx_stream *s, const float *cond_sum, const float *cond_cross, int tc);
 MSX_API int msx_vad(msx_stream *s, float *vad);
 
 /* Device-resident replay for throughput measurement: frames[n_frames][n_q+1] (host) are uploaded

@@ -39,6 +39,7 @@ class MsxConfig(C.Structure):
         ("n_delays", C.c_int32), ("delays", C.c_int32 * MSX_MAX_CODEBOOKS),
         ("schedule_len", C.c_int32), ("schedule", C.c_int32 * MSX_MAX_STEPS),
         ("personaplex", C.c_int32), ("extra_heads", C.c_int32),
+        ("cross_attention", C.c_int32), ("demux_second_stream", C.c_int32), ("dep_low_rank", C.c_int32),
     ]
 
 
@@ -104,6 +105,7 @@ def lib():
     L.msx_step_depformer.argtypes = [vp, C.c_int32, vp, vp, vp]
     L.msx_step.argtypes = [vp, vp, vp]
     L.msx_vad.argtypes = [vp, C.POINTER(C.c_float)]
+    L.msx_stream_set_condition.argtypes = [vp, vp, vp, C.c_int]
     L.msx_stream_set_sampling.argtypes = [vp, C.c_float, C.c_float, C.c_int, C.c_int]
     L.msx_stream_set_noise.argtypes = [vp, vp, vp]
     L.msx_gen_seed.argtypes = [vp, C.c_uint]
@@ -168,6 +170,9 @@ def make_config(cfg: dict) -> MsxConfig:
         c.schedule[i] = s
     c.personaplex = 1 if cfg["model_type"] == "personaplex" else 0
     c.extra_heads = cfg["extra_heads"]
+    c.cross_attention = 1 if cfg.get("cross_attention") else 0
+    c.demux_second_stream = 1 if cfg.get("demux") else 0
+    c.dep_low_rank = int(cfg.get("dep_low_rank") or 0)
     return c
 
 
@@ -252,6 +257,12 @@ class Stream:
     def set_noise(self, noise_text, noise_audio):
         nt = np.ascontiguousarray(noise_text, dtype=np.float32); na = np.ascontiguousarray(noise_audio, dtype=np.float32)
         _check(lib().msx_stream_set_noise(self.h, _p(nt), _p(na)))
+
+    def set_condition(self, cond_sum=None, cond_cross=None):
+        """TTS conditioning: cond_sum [dim] and / or cond_cross [Tc][dim]"""
+        cs = np.ascontiguousarray(cond_sum, dtype=np.float32) if cond_sum is not None else None
+        cc = np.ascontiguousarray(cond_cross, dtype=np.float32) if cond_cross is not None else None
+        _check(lib().msx_stream_set_condition(self.h, _p(cs), _p(cc), 0 if cc is None else cc.shape[0]))
 
     def vad(self) -> float:
         v = C.c_float(0)

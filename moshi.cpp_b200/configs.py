@@ -70,7 +70,39 @@ PRESETS = {
         depformer_dim=0, depformer_num_heads=0, depformer_num_layers=0, depformer_context=0,
         depformer_max_period=0, dep_hidden=0, schedule=[], extra_heads=4, extra_heads_dim=6,
     ),
+    # TTS-like: n_q == dep_q (no user stream), cross-attention to a conditioning memory, demuxed two-stream text
+    # embedding, low-rank (128 -> Q4_0 in a q4_k model) depformer embeddings (moshi.h:111-156)
+    "tiny_tts": dict(
+        name="tiny_tts", model_type="tts",
+        dim=512, num_heads=4, num_layers=2, context=20, max_period=10000,
+        n_q=8, dep_q=8, card=256, text_card=500, delays=[0, 0, 1, 1, 1, 1, 1, 1, 1],
+        hidden=768,
+        depformer_dim=256, depformer_num_heads=4, depformer_num_layers=2, depformer_context=8,
+        depformer_max_period=0, dep_hidden=512, schedule=[], extra_heads=0, extra_heads_dim=0,
+        cross_attention=True, demux=True, dep_low_rank=128,
+    ),
+    # low-rank depformer embeddings without demux (the other moshi_scaled_embedding_t variant)
+    "tiny_lowrank": dict(
+        name="tiny_lowrank", model_type="moshi",
+        dim=512, num_heads=4, num_layers=2, context=24, max_period=10000,
+        n_q=16, dep_q=8, card=256, text_card=1000, delays=_DELAYS_7B,
+        hidden=768,
+        depformer_dim=256, depformer_num_heads=4, depformer_num_layers=2, depformer_context=8,
+        depformer_max_period=0, dep_hidden=512, schedule=[], extra_heads=0, extra_heads_dim=0,
+        dep_low_rank=64,
+    ),
+    "tts1_6b": dict(
+        name="tts1_6b", model_type="tts",
+        dim=2048, num_heads=16, num_layers=16, context=500, max_period=10000,
+        n_q=32, dep_q=32, card=2048, text_card=8000, delays=[0] + [1] * 16 + [2] * 16,
+        hidden=8448,
+        depformer_dim=1024, depformer_num_heads=16, depformer_num_layers=4, depformer_context=32,
+        depformer_max_period=0, dep_hidden=2816, schedule=[], extra_heads=0, extra_heads_dim=0,
+        cross_attention=True, demux=True, dep_low_rank=128,
+    ),
 }
+for _c in PRESETS.values():
+    _c.setdefault("cross_attention", False); _c.setdefault("demux", False); _c.setdefault("dep_low_rank", 0)
 
 
 def get(name: str) -> dict:
@@ -100,6 +132,7 @@ def to_config_json(cfg: dict) -> dict:
         "depformer_gating": "silu", "depformer_pos_emb": "rope" if cfg["depformer_max_period"] else "none",
         "depformer_weights_per_step": True,
         "depformer_weights_per_step_schedule": cfg["schedule"] or None,
-        "conditioners": {}, "cross_attention": False, "model_type": cfg["model_type"],
+        "conditioners": {}, "cross_attention": bool(cfg.get("cross_attention")), "model_type": cfg["model_type"],
+        "demux_second_stream": bool(cfg.get("demux")), "depformer_low_rank_embeddings": cfg.get("dep_low_rank") or None,
         "extra_heads_num_heads": cfg["extra_heads"], "extra_heads_dim": cfg["extra_heads_dim"],
     }

@@ -210,6 +210,8 @@ extern "C" int msx_batch_create(msx_model *m, int n_streams, int context_overrid
     if (!m || !out) return fail(MSX_ERR_ARG, "null argument");
     *out = nullptr;
     if (n_streams < 1 || n_streams > kMmaCols) return fail(MSX_ERR_ARG, "a batch holds 1..8 streams");
+    if (m->cfg.cross_attention || m->cfg.demux_second_stream || m->cfg.dep_low_rank)
+        return fail(MSX_ERR_ARG, "batched streams do not cover the TTS-family layers (cross-attention, demux / low-rank embeddings)");
     CU(cudaSetDevice(m->device));
     if (int e = set_smem_attrs()) return e;
     CU(cudaFuncSetAttribute(gemm_q4k_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemMax));

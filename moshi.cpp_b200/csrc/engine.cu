@@ -22,6 +22,7 @@
 #include "misc_kernels.cuh"
 #include "mma_gemm.cuh"
 #include "sample.cuh"
+#include "tts_kernels.cuh"
 
 using namespace msx;
 
@@ -51,6 +52,9 @@ extern "C" int msx_device_count(void) {
 struct LayerW {
     const float *norm1 = nullptr, *norm2 = nullptr;
     std::vector<QLinear> in_proj, out_proj, lin_in, lin_out;
+    // cross-attention layers (TTS): LayerNorm weight / bias, in_proj [dim -> 3 dim] (q | k | v rows), out_proj
+    const float *norm_cross_w = nullptr, *norm_cross_b = nullptr;
+    QLinear cross_in, cross_out;
 };
 
 struct msx_model {
@@ -67,6 +71,12 @@ struct msx_model {
     const float *rope_freq = nullptr, *dep_rope_freq = nullptr;   // [Dh/2] RoPE frequencies (host-computed)
     QLinear text_linear;
     std::vector<QLinear> dep_in, linears, extra_heads;
+    // TTS family: demuxed text embedding projections (temporal: repacked linears; depformer: GGUF-format rows),
+    // low-rank projections of the depformer embeddings
+    QLinear text_out1, text_out2;
+    EmbTable dep_text_out1, dep_text_out2, dep_text_lr;
+    std::vector<EmbTable> dep_emb_lr;
+    bool dep_small = false;           // depformer embeddings go through small_linear_kernel
     std::vector<void *> allocs;
     std::unordered_map<const void *, QTiles> tiles;   // MMA unit layout of a linear, keyed by its qs plane (batch.inl)
     int64_t weight_bytes_per_frame = 0;
@@ -229,6 +239,10 @@ extern "C" int msx_model_load_gguf(const char *path, const msx_config *cfg, int 
     // embeddings (lm.h:386-391)
     m->emb.resize(c.n_q + 1);
     if (int e = L.table("lm.text_emb.weight", d, c.text_card + 1, &m->emb[0])) return e;
+    if (c.demux_second_stream) {      // lm_utils.h:14-40
+        if (int e = L.linear("lm.text_emb.out1.weight", d, d, &m->text_out1)) return e;
+        if (int e = L.linear("lm.text_emb.out2.weight", d, d, &m->text_out2)) return e;
+    }
     for (int q = 0; q < c.n_q; q++)
         if (int e = L.table("lm.emb." + std::to_string(q) + ".weight", d, c.card + 1, &m->emb[q + 1])) return e;
     {
@@ -250,6 +264,14 @@ extern "C" int msx_model_load_gguf(const char *path, const msx_config *cfg, int 
         wb += L.linear_bytes;
         if (int e = L.linear(p + "self_attn.out_projs.0.weight", d, d, &l.out_proj[0])) return e;
         wb += L.linear_bytes;
+        if (c.cross_attention) {      // transformer.h:1053-1056; bias is optional (torch.h:62-68)
+            if (int e = L.vec_f32(p + "norm_cross.weight", d, &l.norm_cross_w)) return e;
+            if (f.find(p + "norm_cross.bias")) if (int e = L.vec_f32(p + "norm_cross.bias", d, &l.norm_cross_b)) return e;
+            if (int e = L.linear(p + "cross_attention.in_projs.0.weight", d, 3 * d, &l.cross_in)) return e;
+            wb += L.linear_bytes / 3;     // per frame only the q rows are read; k / v rows once per conditioning
+            if (int e = L.linear(p + "cross_attention.out_projs.0.weight", d, d, &l.cross_out)) return e;
+            wb += L.linear_bytes;
+        }
         const GgufTensor *t = L.need(p + "gating.linear_in.weight");
         if (!t) return MSX_ERR_FORMAT;
         const int F = (int)(t->ne[1] / 2);
@@ -277,10 +299,30 @@ extern "C" int msx_model_load_gguf(const char *path, const msx_config *cfg, int 
             if (int e = L.linear("lm.depformer_in." + std::to_string(k) + ".weight", d, dd, &m->dep_in[k])) return e;
             dep_in_bytes[k] = L.linear_bytes;
         }
-        if (int e = L.table("lm.depformer_text_emb.weight", dd, c.text_card + 1, &m->dep_text_emb)) return e;
+        // low-rank / demux depformer embeddings: table rows are [lr] wide and go through a small projection
+        // (lm_utils.h:126-217; lm_default.h:196-214)
+        const int de = c.dep_low_rank ? c.dep_low_rank : dd;
+        m->dep_small = c.dep_low_rank || c.demux_second_stream;
+        if (m->dep_small && (de > kSmallMaxK || de % 32)) return fail(MSX_ERR_FORMAT, "low-rank embedding width must be a multiple of 32, <= 2048");
+        auto small = [&](const std::string &name, EmbTable *out) -> int {
+            const GgufTensor *t = L.need(name);
+            if (!t) return MSX_ERR_FORMAT;
+            if (t->type != T_Q4_0 && t->type != T_Q8_0) return fail(MSX_ERR_FORMAT, name + ": small projections must be q4_0 or q8_0");
+            return L.table(name, de, dd, out);
+        };
+        if (int e = L.table("lm.depformer_text_emb.weight", de, c.text_card + 1, &m->dep_text_emb)) return e;
+        if (c.demux_second_stream) {
+            if (int e = small("lm.depformer_text_emb.out1.weight", &m->dep_text_out1)) return e;
+            if (int e = small("lm.depformer_text_emb.out2.weight", &m->dep_text_out2)) return e;
+        } else if (c.dep_low_rank) {
+            if (int e = small("lm.depformer_text_emb.low_rank.weight", &m->dep_text_lr)) return e;
+        }
         m->dep_emb.resize(c.dep_q - 1);
-        for (int k = 0; k < c.dep_q - 1; k++)
-            if (int e = L.table("lm.depformer_emb." + std::to_string(k) + ".weight", dd, c.card + 1, &m->dep_emb[k])) return e;
+        m->dep_emb_lr.resize(c.dep_low_rank ? c.dep_q - 1 : 0);
+        for (int k = 0; k < c.dep_q - 1; k++) {
+            if (int e = L.table("lm.depformer_emb." + std::to_string(k) + ".weight", de, c.card + 1, &m->dep_emb[k])) return e;
+            if (c.dep_low_rank) if (int e = small("lm.depformer_emb." + std::to_string(k) + ".low_rank.weight", &m->dep_emb_lr[k])) return e;
+        }
         m->dep_layers.resize(c.dep_layers);
         for (int i = 0; i < c.dep_layers; i++) {
             LayerW &l = m->dep_layers[i];
@@ -435,6 +477,24 @@ struct Launcher {
         check();
     }
 
+    void layer_norm(const float *x, const float *w, const float *b, float *y, int n, float eps, int family) {
+        LayerNormArgs a; a.x = x; a.w = w; a.b = b; a.y = y; a.n = n; a.eps = eps;
+        fam = family; begin();
+        launch_pdl(layer_norm_kernel, dim3(1), dim3(kLnThreads), 0, a);
+        check();
+    }
+    void cross_attn(const CrossAttnArgs &a, int heads, int dh, int family) {
+        fam = family; begin();
+        if (dh == 128) launch_pdl(cross_attn_kernel<128>, dim3(heads), dim3(kCrossThreads), (size_t)cross_attn_smem<128>(a.tc), a);
+        else launch_pdl(cross_attn_kernel<64>, dim3(heads), dim3(kCrossThreads), (size_t)cross_attn_smem<64>(a.tc), a);
+        check();
+    }
+    void small_linear(const SmallLinearArgs &a, int family) {
+        fam = family; begin();
+        launch_pdl(small_linear_kernel, dim3((a.w.rows + kSmallThreads - 1) / kSmallThreads), dim3(kSmallThreads), 0, a);
+        check();
+    }
+
     void attn(const AttnArgs &a, int heads, int dh, int split, int family = 0, int n_streams = 1) {
         fam = family; begin();
         cudaLaunchConfig_t cfg{};
@@ -458,6 +518,21 @@ struct Launcher {
         check();
     }
 };
+
+// rows [row0, row0 + rows) of a repacked linear (torch_nn_linear_view, torch.h:103-118)
+QLinear linear_rows(const QLinear &w, int row0, int rows) {
+    QLinear v = w;
+    v.rows = rows;
+    if (w.type == T_Q4_K) {
+        v.qs = w.qs + (size_t)row0 * (w.K >> 1);
+        v.sc = w.sc + (size_t)row0 * (w.K >> 6);
+        v.dd = reinterpret_cast<const uint32_t *>(w.dd) + (size_t)row0 * (w.K >> 8);
+    } else {
+        v.qs = w.qs + (size_t)row0 * w.K;
+        v.dd = reinterpret_cast<const uint16_t *>(w.dd) + (size_t)row0 * (w.K >> 5);
+    }
+    return v;
+}
 
 int attn_split_for(int heads, int cap, int num_sms) {
     // short rings: at most one CTA per SM; long rings (KV streaming dominates): up to two CTAs per SM
@@ -485,6 +560,13 @@ struct msx_stream {
     float *x = nullptr, *qkv = nullptr, *ctx = nullptr, *gate = nullptr, *tout = nullptr, *text_logits = nullptr;
     float *dx = nullptr, *dqkv = nullptr, *dctx = nullptr, *dgate = nullptr, *audio_logits = nullptr, *vad_logits = nullptr;
     float *rope_cs = nullptr;        // [Dh] cos | sin of the current temporal position
+    // TTS family
+    float *cond_sum = nullptr;       // [dim] or null
+    float *kv_cross = nullptr;       // [L][tc][2*dim] f32 cross-attention memory
+    int tc = 0;
+    float *cnx = nullptr, *cq = nullptr, *cctx = nullptr;     // layer-norm output, cross q, cross context [dim]
+    float *demux_l = nullptr, *demux_r = nullptr, *demux_y1 = nullptr, *demux_y2 = nullptr;   // [dim]
+    float *dep_e = nullptr;          // [dep_dim] embedding of the previous token after its low-rank / demux projection
     int32_t *d_feed = nullptr;       // msx_run_resident_async
     cudaGraphExec_t g_temporal = nullptr, g_depformer = nullptr;
     int launches_temporal = 0, launches_depformer = 0;
@@ -562,6 +644,17 @@ void enqueue_layer(Launcher &L, const msx_stream *s, const LayerW &lw, int w, bo
         g.w = lw.out_proj[w]; g.x = ctx; g.alpha = nullptr; g.out = x;
         L.gemv(g, PRO_PLAIN, EPI_RESID, temporal ? FAM_OUT_PROJ : FAM_DEP_OUT_PROJ);
     }
+    if (temporal && lw.cross_in.qs && s->kv_cross && s->tc > 0) {
+        // x += cross_attention(layer_norm(x)) over the conditioning memory (transformer.h:936-943, 714-762)
+        L.layer_norm(x, lw.norm_cross_w, lw.norm_cross_b, s->cnx, dim, 0.0f, FAM_ATTN);
+        g.w = linear_rows(lw.cross_in, 0, dim); g.x = s->cnx; g.alpha = nullptr; g.out = s->cq;
+        L.gemv(g, PRO_PLAIN, EPI_STORE, FAM_IN_PROJ);
+        CrossAttnArgs ca;
+        ca.q = s->cq; ca.kv = s->kv_cross + (size_t)layer * s->tc * 2 * dim; ca.ctx = s->cctx; ca.tc = s->tc; ca.dim = dim;
+        L.cross_attn(ca, heads, dim / heads, FAM_ATTN);
+        g.w = lw.cross_out; g.x = s->cctx; g.alpha = nullptr; g.out = x;
+        L.gemv(g, PRO_PLAIN, EPI_RESID, FAM_OUT_PROJ);
+    }
     // rms_norm2 -> linear_in -> silu gate
     g.w = lw.lin_in[w]; g.x = x; g.alpha = lw.norm2; g.out = gate;
     L.gemv(g, PRO_RMS, EPI_GATE, temporal ? FAM_LIN_IN : FAM_DEP_LIN_IN);
@@ -575,6 +668,21 @@ void enqueue_temporal(Launcher &L, const msx_stream *s) {
     EmbedArgs e;
     e.tables = m->d_emb; e.n_tables = c.n_q + 1; e.dim = c.dim; e.ctrl = s->ctrl; e.x = s->x;
     if (c.max_period) { e.rope_cs = s->rope_cs; e.rope_freq = m->rope_freq; e.dh = c.dim / c.num_heads; }
+    if (c.demux_second_stream) {
+        // text embedding = out1(row[left]) + out2(row[right]) * right_scale (lm_utils.h:42-86)
+        DemuxRowsArgs dr;
+        dr.table = m->emb[0]; dr.ctrl = s->ctrl; dr.num_embeddings = c.text_card + 1; dr.left = s->demux_l; dr.right = s->demux_r;
+        L.fam = FAM_EMBED; L.begin();
+        L.launch_pdl(demux_rows_kernel, dim3((c.dim + 255) / 256), dim3(256), 0, dr);
+        L.check();
+        GemvArgs g1;
+        g1.ctrl = s->ctrl; g1.w = m->text_out1; g1.x = s->demux_l; g1.out = s->demux_y1;
+        L.gemv(g1, PRO_PLAIN, EPI_STORE, FAM_EMBED);
+        g1.w = m->text_out2; g1.x = s->demux_r; g1.out = s->demux_y2;
+        L.gemv(g1, PRO_PLAIN, EPI_STORE, FAM_EMBED);
+        e.text_pre1 = s->demux_y1; e.text_pre2 = s->demux_y2; e.num_embeddings = c.text_card + 1;
+    }
+    e.cond_sum = s->cond_sum;
     L.fam = FAM_EMBED; L.begin();
     L.launch_pdl(embed_kernel, dim3((c.dim + kThreads - 1) / kThreads), dim3(kThreads), 0, e);
     L.check();
@@ -607,9 +715,28 @@ void enqueue_depformer(Launcher &L, const msx_stream *s) {
         g.ctrl = s->ctrl; g.eps = 1e-8f;
         // depformer_in[w](transformer_out) + embedding of the previous token (lm.h:464-467, 494-516)
         g.w = m->dep_in[w]; g.x = s->tout; g.out = s->dx;
-        g.emb = k == 0 ? m->dep_text_emb : m->dep_emb[k - 1];
-        g.emb_step = k;
-        L.gemv(g, PRO_PLAIN, EPI_ADD_EMB, FAM_DEP_IN);
+        if (m->dep_small) {
+            // previous token's embedding through its low-rank / demux projection first (lm_utils.h:42-66, 155-168, 209-217)
+            SmallLinearArgs sl;
+            sl.ctrl = s->ctrl; sl.step = k; sl.out = s->dep_e; sl.num_embeddings = c.text_card + 1;
+            if (k == 0 && c.demux_second_stream) {
+                sl.table = m->dep_text_emb; sl.w = m->dep_text_out1; sl.mode = 2;
+                L.small_linear(sl, FAM_DEP_IN);
+                sl.w = m->dep_text_out2; sl.mode = 3;
+                L.small_linear(sl, FAM_DEP_IN);
+            } else {
+                sl.table = k == 0 ? m->dep_text_emb : m->dep_emb[k - 1];
+                sl.w = k == 0 ? m->dep_text_lr : m->dep_emb_lr[k - 1];
+                sl.mode = k == 0 ? 0 : 1;
+                L.small_linear(sl, FAM_DEP_IN);
+            }
+            g.addvec = s->dep_e;
+            L.gemv(g, PRO_PLAIN, EPI_ADD_VEC, FAM_DEP_IN);
+        } else {
+            g.emb = k == 0 ? m->dep_text_emb : m->dep_emb[k - 1];
+            g.emb_step = k;
+            L.gemv(g, PRO_PLAIN, EPI_ADD_EMB, FAM_DEP_IN);
+        }
         for (int l = 0; l < c.dep_layers; l++) enqueue_layer(L, s, m->dep_layers[l], w, false, l, k);
         // linears[k] -> logits -> greedy token (no final norm, lm.h:472)
         GemvArgs h;
@@ -783,6 +910,19 @@ extern "C" int msx_stream_create_ex(msx_model *m, int context_override, int flag
     }
     if (c.extra_heads > 0)
         if (int e = salloc(s.get(), (void **)&s->vad_logits, 64 * 4)) return e;
+    if (c.cross_attention) {
+        if (int e = salloc(s.get(), (void **)&s->cnx, (size_t)c.dim * 4)) return e;
+        if (int e = salloc(s.get(), (void **)&s->cq, (size_t)c.dim * 4)) return e;
+        if (int e = salloc(s.get(), (void **)&s->cctx, (size_t)c.dim * 4)) return e;
+    }
+    if (c.demux_second_stream) {
+        if (int e = salloc(s.get(), (void **)&s->demux_l, (size_t)c.dim * 4)) return e;
+        if (int e = salloc(s.get(), (void **)&s->demux_r, (size_t)c.dim * 4)) return e;
+        if (int e = salloc(s.get(), (void **)&s->demux_y1, (size_t)c.dim * 4)) return e;
+        if (int e = salloc(s.get(), (void **)&s->demux_y2, (size_t)c.dim * 4)) return e;
+    }
+    if (m->dep_small)
+        if (int e = salloc(s.get(), (void **)&s->dep_e, (size_t)c.dep_dim * 4)) return e;
     s->noise_floats = kSampleMaxK * (1 + MSX_MAX_STEPS);
     if (int e = salloc(s.get(), (void **)&s->d_noise, (size_t)s->noise_floats * 4)) return e;
     if (int e = salloc(s.get(), (void **)&s->d_probs, (size_t)std::max(c.text_card, c.card) * 4)) return e;
@@ -811,7 +951,7 @@ static int build_graphs(msx_stream *sp) {
     if (int e = capture(s.get(), [&](Launcher &L) { enqueue_temporal(L, s.get()); }, &s->g_temporal, &s->launches_temporal)) return e;
     if (c.dep_q > 0) {
         // persistent phase-program kernel for the depformer chain: opt-in (measured slower than PDL-chained launches on B200)
-        const bool want_mega = (flags & MSX_STREAM_PERSISTENT_DEPFORMER) && m->dep_cap <= 64 && sp->temp_audio <= 0.f && !sp->d_dep_prog;
+        const bool want_mega = (flags & MSX_STREAM_PERSISTENT_DEPFORMER) && m->dep_cap <= 64 && sp->temp_audio <= 0.f && !sp->d_dep_prog && !m->dep_small;
         if (sp->temp_audio > 0.f) sp->mega_depformer = false;
         if (want_mega) {
             int mx = 0;
@@ -949,6 +1089,44 @@ extern "C" int msx_step(msx_stream *s, const int32_t *tokens, int32_t *out_token
     if (c.dep_q > 0) CU(cudaGraphLaunch(s->g_depformer, s->st));
     if (int e = pull_outputs(s)) return e;
     if (out_tokens) for (int k = 0; k < 1 + c.dep_q; k++) out_tokens[k] = s->h_out[k];
+    return 0;
+}
+
+extern "C" int msx_stream_set_condition(msx_stream *s, const float *cond_sum, const float *cond_cross, int tc) {
+    if (!s) return fail(MSX_ERR_ARG, "null stream");
+    msx_model *m = s->m; const msx_config &c = m->cfg;
+    if (cond_cross && !c.cross_attention) return fail(MSX_ERR_STATE, "model has no cross-attention layers (moshi_lm_set_voice_condition returns -1 likewise, moshi.cpp:729-731)");
+    if (cond_cross && tc <= 0) return fail(MSX_ERR_ARG, "tc must be positive");
+    CU(cudaSetDevice(m->device));
+    CU(cudaStreamSynchronize(s->st));
+    const int dim = c.dim;
+    if (cond_sum) {
+        if (!s->cond_sum) if (int e = salloc(s, (void **)&s->cond_sum, (size_t)dim * 4)) return e;
+        CU(cudaMemcpy(s->cond_sum, cond_sum, (size_t)dim * 4, cudaMemcpyHostToDevice));
+    } else s->cond_sum = nullptr;       // (allocation stays in the stream's arena)
+    if (cond_cross) {
+        // init(): k | v = in_proj rows [dim, 3 dim) applied to every condition column, kept in f32 (transformer.h:343-396)
+        float *d_cross = nullptr;
+        CU(cudaMalloc((void **)&d_cross, (size_t)tc * dim * 4));
+        CU(cudaMemcpy(d_cross, cond_cross, (size_t)tc * dim * 4, cudaMemcpyHostToDevice));
+        if (tc != s->tc || !s->kv_cross) if (int e = salloc(s, (void **)&s->kv_cross, (size_t)c.num_layers * tc * 2 * dim * 4)) { cudaFree(d_cross); return e; }
+        s->tc = tc;
+        Launcher L{s->st, m->num_sms};
+        L.pdl = false;
+        for (int l = 0; l < c.num_layers; l++) {
+            const QLinear kvw = linear_rows(m->layers[l].cross_in, dim, 2 * dim);
+            for (int i = 0; i < tc; i++) {
+                GemvArgs g;
+                g.ctrl = s->ctrl; g.w = kvw; g.x = d_cross + (size_t)i * dim; g.out = s->kv_cross + ((size_t)l * tc + i) * 2 * dim;
+                L.gemv(g, PRO_PLAIN, EPI_STORE);
+            }
+        }
+        cudaError_t e = cudaStreamSynchronize(s->st);
+        cudaFree(d_cross);
+        if (L.err != cudaSuccess || e != cudaSuccess) return fail(MSX_ERR_CUDA, std::string("cross-attention memory: ") + cudaGetErrorString(L.err != cudaSuccess ? L.err : e));
+    } else { s->tc = 0; }
+    if (int e = build_graphs(s)) return e;     // the graphs bake the conditioning pointers and tc
+    CU(cudaStreamSynchronize(s->st));
     return 0;
 }
 

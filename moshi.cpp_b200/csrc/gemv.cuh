@@ -258,6 +258,8 @@ __device__ __forceinline__ void gemv_epilogue(const GemvArgs &a, const int EPI, 
                 e = emb_element(a.emb, emb_token, row);
             }
             a.out[row] = acc[r] + e;
+        } else if (EPI == EPI_ADD_VEC) {
+            a.out[row] = acc[r] + __ldcg(a.addvec + row);
         }
     }
 }

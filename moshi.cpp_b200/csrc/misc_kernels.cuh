@@ -17,6 +17,11 @@ struct EmbedArgs {
     float *rope_cs = nullptr;
     const float *rope_freq = nullptr;
     int32_t dh = 0;
+    // TTS family: demuxed text embedding = pre1 + pre2 * right_scale(token) (out1 / out2 projections computed by
+    // earlier launches, lm_utils.h:42-66) instead of table 0; cond_sum is added last (lm.h:575-577)
+    const float *text_pre1 = nullptr, *text_pre2 = nullptr;
+    int32_t num_embeddings = 0;
+    const float *cond_sum = nullptr;
 };
 
 // `b` = stream of a batch (batched steps launch grid.y = streams; per-stream buffers are b * dim / b * dh apart)
@@ -35,10 +40,18 @@ __device__ __forceinline__ void embed_body(const EmbedArgs &a0, int cta, int n_c
         float acc = 0.f;
         for (int t = 0; t < a.n_tables; t++) {
             const int tok = toks[t];
-            float e = emb_element(a.tables[t], tok < 0 ? 0 : tok, i);
-            e = e * (tok == -1 ? 0.f : 1.f);
+            float e;
+            if (t == 0 && a.text_pre1) {
+                int tk = tok < 0 ? 0 : tok;
+                const float rs = (tk / a.num_embeddings - 1) < 0 ? 0.f : 1.f;
+                e = __fadd_rn(__ldcg(a.text_pre1 + i), __fmul_rn(__ldcg(a.text_pre2 + i), rs));
+            } else {
+                e = emb_element(a.tables[t], tok < 0 ? 0 : tok, i);
+                e = e * (tok == -1 ? 0.f : 1.f);
+            }
             acc = (t == 0) ? e : acc + e;
         }
+        if (a.cond_sum) acc = a.cond_sum[i] + acc;
         a.x[i] = acc;
     }
 }

@@ -117,7 +117,12 @@ def manifest(cfg: dict, qtype: int):
     lin = lambda name, k, rows: out.append((name, linear_type(qtype, k), k, rows, 1.0 / np.sqrt(k)))
     emb = lambda name, k, rows: out.append((name, emb_type(qtype, k), k, rows, 0.25))
     f32 = lambda name, k: out.append((name, GGML_F32, k, 1, None))
+    bias = lambda name, k: out.append((name, GGML_F32, k, 1, -0.1))        # std < 0: plain N(0, |std|) f32 vector
+    cross, demux, lr = cfg.get("cross_attention"), cfg.get("demux"), cfg.get("dep_low_rank") or 0
     emb("lm.text_emb.weight", d, cfg["text_card"] + 1)
+    if demux:                                                              # lm_utils.h:14-40
+        lin("lm.text_emb.out1.weight", d, d)
+        lin("lm.text_emb.out2.weight", d, d)
     for c in range(cfg["n_q"]):
         emb(f"lm.emb.{c}.weight", d, cfg["card"] + 1)
     for i in range(L):
@@ -125,6 +130,11 @@ def manifest(cfg: dict, qtype: int):
         f32(p + "norm1.alpha", d)
         lin(p + "self_attn.in_projs.0.weight", d, 3 * d)
         lin(p + "self_attn.out_projs.0.weight", d, d)
+        if cross:                                                          # transformer.h:1053-1056
+            f32(p + "norm_cross.weight", d)
+            bias(p + "norm_cross.bias", d)
+            lin(p + "cross_attention.in_projs.0.weight", d, 3 * d)
+            lin(p + "cross_attention.out_projs.0.weight", d, d)
         f32(p + "norm2.alpha", d)
         lin(p + "gating.linear_in.weight", d, 2 * F)
         lin(p + "gating.linear_out.weight", F, d)
@@ -134,9 +144,17 @@ def manifest(cfg: dict, qtype: int):
         dd, Fd, nw = cfg["depformer_dim"], cfg["dep_hidden"], configs.dep_num_weights(cfg)
         for k in range(nw):
             lin(f"lm.depformer_in.{k}.weight", d, dd)
-        emb("lm.depformer_text_emb.weight", dd, cfg["text_card"] + 1)
+        de = lr if lr else dd                                              # low-rank tables are [lr, rows] + a [lr -> dd] linear
+        emb("lm.depformer_text_emb.weight", de, cfg["text_card"] + 1)
+        if demux:
+            lin("lm.depformer_text_emb.out1.weight", de, dd)
+            lin("lm.depformer_text_emb.out2.weight", de, dd)
+        elif lr:
+            lin("lm.depformer_text_emb.low_rank.weight", lr, dd)
         for k in range(cfg["dep_q"] - 1):
-            emb(f"lm.depformer_emb.{k}.weight", dd, cfg["card"] + 1)
+            emb(f"lm.depformer_emb.{k}.weight", de, cfg["card"] + 1)
+            if lr:
+                lin(f"lm.depformer_emb.{k}.low_rank.weight", lr, dd)
         for i in range(cfg["depformer_num_layers"]):
             p = f"lm.depformer.layers.{i}."
             f32(p + "norm1.alpha", dd)
@@ -182,6 +200,8 @@ def write_gguf(path: str, cfg: dict, quant: str = "q4_k", seed: int = 1234) -> d
             if std is None:  # norm alpha: around 1
                 data = (1.0 + 0.1 * rng.standard_normal(size=k)).astype(np.float32).view(np.uint8)
                 f.write(data.tobytes())
+            elif std < 0:    # f32 bias vector
+                f.write((-std * rng.standard_normal(size=k)).astype(np.float32).tobytes())
             else:
                 # generate in row chunks to bound peak memory on the 7B model
                 chunk = max(1, (64 << 20) // max(1, row_bytes(gtype, k)))

@@ -292,6 +292,7 @@ typedef struct { int type; int64_t ne0, ne1; const void *data; } orc_tensor;
 typedef struct {
     orc_tensor norm1, norm2;
     orc_tensor *in_proj, *out_proj, *lin_in, *lin_out; /* [n_weights] */
+    orc_tensor norm_cross_w, norm_cross_b, cross_in, cross_out;   /* cross-attention layers only */
 } orc_layer;
 
 struct orc_model {
@@ -299,6 +300,8 @@ struct orc_model {
     int ideal;
     int dep_num_weights, dep_cap;
     orc_tensor text_emb, *emb /*[n_q]*/;
+    orc_tensor text_out1, text_out2;                  /* demux text embedding (lm_utils.h:14-19) */
+    orc_tensor dep_text_out1, dep_text_out2, dep_text_lr, *dep_emb_lr /*[dep_q-1]*/;
     orc_layer *layers /*[num_layers]*/;
     orc_tensor out_norm, text_linear;
     orc_tensor *dep_in /*[dep_num_weights]*/, dep_text_emb, *dep_emb /*[dep_q-1]*/;
@@ -331,6 +334,7 @@ orc_model *orc_model_new(const orc_config *cfg) {
         int nw = m->dep_num_weights;
         m->dep_in = calloc(nw, sizeof(orc_tensor));
         m->dep_emb = calloc(c->dep_q > 1 ? c->dep_q - 1 : 1, sizeof(orc_tensor));
+        m->dep_emb_lr = calloc(c->dep_q > 1 ? c->dep_q - 1 : 1, sizeof(orc_tensor));
         m->dep_layers = calloc(c->dep_layers, sizeof(orc_layer));
         for (int i = 0; i < c->dep_layers; i++) {
             orc_layer *l = &m->dep_layers[i];
@@ -348,7 +352,7 @@ void orc_model_free(orc_model *m) {
     const orc_config *c = &m->cfg;
     for (int i = 0; i < c->num_layers; i++) { orc_layer *l = &m->layers[i]; free(l->in_proj); free(l->out_proj); free(l->lin_in); free(l->lin_out); }
     if (m->dep_layers) for (int i = 0; i < c->dep_layers; i++) { orc_layer *l = &m->dep_layers[i]; free(l->in_proj); free(l->out_proj); free(l->lin_in); free(l->lin_out); }
-    free(m->emb); free(m->layers); free(m->dep_in); free(m->dep_emb); free(m->dep_layers); free(m->linears); free(m->extra_heads);
+    free(m->emb); free(m->layers); free(m->dep_in); free(m->dep_emb); free(m->dep_emb_lr); free(m->dep_layers); free(m->linears); free(m->extra_heads);
     free(m);
 }
 
@@ -362,6 +366,12 @@ static orc_tensor *find_slot(orc_model *m, const char *name) {
     if (!strcmp(name, "lm.out_norm.alpha")) return &m->out_norm;
     if (!strcmp(name, "lm.text_linear.weight")) return &m->text_linear;
     if (!strcmp(name, "lm.depformer_text_emb.weight")) return c->dep_q > 0 ? &m->dep_text_emb : NULL;
+    if (!strcmp(name, "lm.text_emb.out1.weight")) return c->demux_second_stream ? &m->text_out1 : NULL;
+    if (!strcmp(name, "lm.text_emb.out2.weight")) return c->demux_second_stream ? &m->text_out2 : NULL;
+    if (!strcmp(name, "lm.depformer_text_emb.out1.weight")) return (c->demux_second_stream && c->dep_q > 0) ? &m->dep_text_out1 : NULL;
+    if (!strcmp(name, "lm.depformer_text_emb.out2.weight")) return (c->demux_second_stream && c->dep_q > 0) ? &m->dep_text_out2 : NULL;
+    if (!strcmp(name, "lm.depformer_text_emb.low_rank.weight")) return (c->dep_low_rank && !c->demux_second_stream && c->dep_q > 0) ? &m->dep_text_lr : NULL;
+    if (sscanf(name, "lm.depformer_emb.%d.low_rank.weigh%1[t]", &a, tail) == 2) return (c->dep_low_rank && m->dep_emb_lr && a < c->dep_q - 1) ? &m->dep_emb_lr[a] : NULL;
     if (sscanf(name, "lm.emb.%d.weigh%1[t]", &a, tail) == 2) return a < c->n_q ? &m->emb[a] : NULL;
     if (sscanf(name, "lm.depformer_in.%d.weigh%1[t]", &a, tail) == 2) return (m->dep_in && a < m->dep_num_weights) ? &m->dep_in[a] : NULL;
     if (sscanf(name, "lm.depformer_emb.%d.weigh%1[t]", &a, tail) == 2) return (m->dep_emb && a < c->dep_q - 1) ? &m->dep_emb[a] : NULL;
@@ -375,6 +385,12 @@ static orc_tensor *find_slot(orc_model *m, const char *name) {
         if (!strcmp(tail, "self_attn.out_projs.0.weight")) return &l->out_proj[0];
         if (!strcmp(tail, "gating.linear_in.weight")) return &l->lin_in[0];
         if (!strcmp(tail, "gating.linear_out.weight")) return &l->lin_out[0];
+        if (c->cross_attention) {
+            if (!strcmp(tail, "norm_cross.weight")) return &l->norm_cross_w;
+            if (!strcmp(tail, "norm_cross.bias")) return &l->norm_cross_b;
+            if (!strcmp(tail, "cross_attention.in_projs.0.weight")) return &l->cross_in;
+            if (!strcmp(tail, "cross_attention.out_projs.0.weight")) return &l->cross_out;
+        }
         return NULL;
     }
     if (m->dep_layers && sscanf(name, "lm.depformer.layers.%d.%63s", &a, tail) == 2 && a < c->dep_layers) {
@@ -405,6 +421,10 @@ int orc_model_missing(orc_model *m, char *buf, int buflen) {
 #define CHK(t, nm) do { if (!(t).data) { if (!n && buf) snprintf(buf, buflen, "%s", nm); n++; } } while (0)
     CHK(m->text_emb, "text_emb"); CHK(m->out_norm, "out_norm"); CHK(m->text_linear, "text_linear");
     for (int i = 0; i < c->n_q; i++) CHK(m->emb[i], "emb");
+    if (c->demux_second_stream) { CHK(m->text_out1, "text_emb.out1"); CHK(m->text_out2, "text_emb.out2"); }
+    if (c->cross_attention) for (int i = 0; i < c->num_layers; i++) { orc_layer *l = &m->layers[i]; CHK(l->norm_cross_w, "norm_cross.weight"); CHK(l->cross_in, "cross_attention.in_proj"); CHK(l->cross_out, "cross_attention.out_proj"); }
+    if (c->dep_q > 0 && c->demux_second_stream) { CHK(m->dep_text_out1, "depformer_text_emb.out1"); CHK(m->dep_text_out2, "depformer_text_emb.out2"); }
+    if (c->dep_q > 0 && c->dep_low_rank) { if (!c->demux_second_stream) CHK(m->dep_text_lr, "depformer_text_emb.low_rank"); for (int i = 0; i < c->dep_q - 1; i++) CHK(m->dep_emb_lr[i], "depformer_emb.low_rank"); }
     for (int i = 0; i < c->num_layers; i++) { orc_layer *l = &m->layers[i]; CHK(l->norm1, "norm1"); CHK(l->norm2, "norm2"); CHK(l->in_proj[0], "in_proj"); CHK(l->out_proj[0], "out_proj"); CHK(l->lin_in[0], "lin_in"); CHK(l->lin_out[0], "lin_out"); }
     if (c->dep_q > 0) {
         CHK(m->dep_text_emb, "dep_text_emb");
@@ -428,6 +448,8 @@ struct orc_state {
     uint16_t *k, *v;            /* [L][H][cap][Dh] */
     uint16_t *dk, *dv;          /* [Ld][Hd][capd][Dhd] */
     float *transformer_out;     /* [dim] */
+    float *cond_sum;            /* [dim] or NULL (lm.h:575-577) */
+    float *kv_cross; int tc;    /* [L][tc][2*dim] f32: k | v of the cross-attention memory (transformer.h:343-396) */
     /* sampling (sampling.h:46-64): temp <= 0 greedy; noise = Exp(1) draws in candidate order */
     float temp_text, temp_audio; int top_k_text, top_k_audio;
     const float *noise_text, *noise_audio;
@@ -444,7 +466,7 @@ orc_state *orc_state_new(orc_model *m) {
     s->transformer_out = calloc(m->cfg.dim, sizeof(float));
     return s;
 }
-void orc_state_free(orc_state *s) { if (!s) return; free(s->k); free(s->v); free(s->dk); free(s->dv); free(s->transformer_out); free(s); }
+void orc_state_free(orc_state *s) { if (!s) return; free(s->k); free(s->v); free(s->dk); free(s->dv); free(s->transformer_out); free(s->cond_sum); free(s->kv_cross); free(s); }
 void orc_state_reset(orc_state *s) {
     s->offset = 0;
     memset(s->k, 0, kv_elems(&s->m->cfg) * 2); memset(s->v, 0, kv_elems(&s->m->cfg) * 2);
@@ -465,6 +487,57 @@ static void linear(const orc_model *m, const orc_tensor *w, const float *x, floa
     /* torch_nn_linear (torch.h:79-87); LM linears carry no bias */
     if (m->ideal) orc_mul_mat_vec_ideal(w->type, w->data, w->ne0, w->ne1, x, y);
     else orc_mul_mat_vec(w->type, w->data, w->ne0, w->ne1, x, y);
+}
+
+static void embed_row(const orc_tensor *t, int token, float *row);
+#define embed_row_k embed_row
+/* torch_nn_linear_view (torch.h:103-118): rows [row0, row0 + rows) of w */
+static void linear_rows(const orc_model *m, const orc_tensor *w, int64_t row0, int64_t rows, const float *x, float *y) {
+    const char *d = (const char *)w->data + row0 * orc_row_size(w->type, w->ne0);
+    if (m->ideal) orc_mul_mat_vec_ideal(w->type, d, w->ne0, rows, x, y);
+    else orc_mul_mat_vec(w->type, d, w->ne0, rows, x, y);
+}
+
+/* torch_nn_layer_norm (torch.h:49-60) = ggml_norm (mean, then variance of the centred values, both in double,
+ * scale = 1/sqrtf(var + eps)) * weight (+ bias) */
+static void layer_norm(const float *x, const float *w, const float *b, float eps, float *y, int64_t n) {
+    double sum = 0.0;
+    for (int64_t i = 0; i < n; i++) sum += (double)x[i];
+    const float mean = (float)(sum / n);
+    double sum2 = 0.0;
+    for (int64_t i = 0; i < n; i++) { const float v = x[i] - mean; y[i] = v; sum2 += (double)(v * v); }
+    const float variance = (float)(sum2 / n);
+    const float scale = 1.0f / sqrtf(variance + eps);
+    for (int64_t i = 0; i < n; i++) { float v = y[i] * scale; v = v * w[i]; y[i] = b ? v + b[i] : v; }
+}
+
+/* moshi_scaled_embedding_demux (lm_utils.h:42-125): token -> (left, right) rows of one table, out1(left) + out2(right)*scale */
+static void embed_demux(const orc_model *m, const orc_tensor *table, const orc_tensor *out1, const orc_tensor *out2,
+                        int num_embeddings, int token, float *y /*[out rows]*/) {
+    if (token < 0) token = 0;
+    const int left = token % num_embeddings;
+    int right = token / num_embeddings - 1;
+    const int right_zero = right < 0;
+    if (right < 0) right = 0;
+    const int64_t k = table->ne0, n = out1->ne1;
+    float *rl = malloc(sizeof(float) * k), *rr = malloc(sizeof(float) * k), *yr = malloc(sizeof(float) * n);
+    orc_dequantize_row(table->type, (const char *)table->data + (int64_t)left * orc_row_size(table->type, k), rl, k);
+    orc_dequantize_row(table->type, (const char *)table->data + (int64_t)right * orc_row_size(table->type, k), rr, k);
+    linear(m, out2, rr, yr);
+    linear(m, out1, rl, y);
+    const float sc = right_zero ? 0.f : 1.f;
+    for (int64_t i = 0; i < n; i++) y[i] = y[i] + yr[i] * sc;
+    free(rl); free(rr); free(yr);
+}
+
+/* moshi_scaled_embedding with low_rank (lm_utils.h:155-168, 209-217): y = low_rank(get_rows(w)[*scale]) */
+static void embed_low_rank(const orc_model *m, const orc_tensor *table, const orc_tensor *lr, int token, int scaled, float *y) {
+    const int64_t k = table->ne0;
+    float *row = malloc(sizeof(float) * k);
+    if (scaled) embed_row_k(table, token, row);
+    else orc_dequantize_row(table->type, (const char *)table->data + (int64_t)token * orc_row_size(table->type, k), row, k);
+    linear(m, lr, row, y);
+    free(row);
 }
 
 /* moshi_scaled_embedding_step + get_rows*scale (lm_utils.h:157-182): -1 -> zeros, other negatives -> row 0 */
@@ -529,8 +602,32 @@ static void attention_head(const uint16_t *K, const uint16_t *V /*[cap][Dh]*/, i
 }
 
 /* moshi_streaming_transformer_layer (transformer.h:910-1039), T = 1 */
+/* SDPA over the f32 cross-attention memory, no mask (transformer.h:714-762; torch.h:225-237 with f32 "weights") */
+static void cross_attention_head(const float *kv /*[tc][2*dim]*/, int tc, int dim, int h, int Dh, const float *q, float *ctx, float *scratch) {
+    const float scale = 1.f / sqrtf((float)Dh);
+    float maxv = -INFINITY;
+    for (int i = 0; i < tc; i++) {
+        const float *K = kv + (size_t)i * 2 * dim + h * Dh;
+        double acc = 0;
+        for (int d = 0; d < Dh; d++) acc += (double)(K[d] * q[d]);
+        float s = (float)acc;
+        s = s * scale;
+        scratch[i] = s; if (s > maxv) maxv = s;
+    }
+    double sum = 0;
+    for (int i = 0; i < tc; i++) { float e = (float)exp((double)(scratch[i] - maxv)); scratch[i] = e; sum += (double)e; }
+    const float inv = (float)(1.0 / sum);
+    for (int i = 0; i < tc; i++) scratch[i] = scratch[i] * inv;
+    for (int d = 0; d < Dh; d++) {
+        double acc = 0;
+        for (int i = 0; i < tc; i++) acc += (double)(kv[(size_t)i * 2 * dim + dim + h * Dh + d] * scratch[i]);
+        ctx[d] = (float)acc;
+    }
+}
+
 static void transformer_layer(const orc_model *m, const orc_layer *l, int w, int dim, int H, int cap,
-                              int max_period, int pos, uint16_t *Kc, uint16_t *Vc /*[H][cap][Dh]*/, float *x) {
+                              int max_period, int pos, uint16_t *Kc, uint16_t *Vc /*[H][cap][Dh]*/, float *x,
+                              const float *kv_cross /*[tc][2*dim] or NULL*/, int tc) {
     const int Dh = dim / H;
     const int F = (int)l->lin_out[w].ne0;
     float *nx = malloc(sizeof(float) * dim), *p = malloc(sizeof(float) * 3 * dim), *ctx = malloc(sizeof(float) * dim);
@@ -552,6 +649,17 @@ static void transformer_layer(const orc_model *m, const orc_layer *l, int w, int
     }
     linear(m, &l->out_proj[w], ctx, upd);
     for (int i = 0; i < dim; i++) x[i] = x[i] + upd[i];
+
+    if (l->cross_in.data && kv_cross && tc > 0) {
+        /* transformer.h:936-943: nx = layer_norm(x) (eps 0.0, lm_default.h:34); q = in_proj rows [0, dim) */
+        float *cs = malloc(sizeof(float) * tc);
+        layer_norm(x, (const float *)l->norm_cross_w.data, (const float *)l->norm_cross_b.data, 0.0f, nx, dim);
+        linear_rows(m, &l->cross_in, 0, dim, nx, p);
+        for (int h = 0; h < H; h++) cross_attention_head(kv_cross, tc, dim, h, Dh, p + h * Dh, ctx + h * Dh, cs);
+        linear(m, &l->cross_out, ctx, upd);
+        for (int i = 0; i < dim; i++) x[i] = x[i] + upd[i];
+        free(cs);
+    }
 
     orc_rms_norm(x, (const float *)l->norm2.data, 1e-8f, nx, dim);
     linear(m, &l->lin_in[w], nx, g);
@@ -600,13 +708,16 @@ int orc_step_temporal(orc_model *m, orc_state *s, const int32_t *tokens, float *
     const orc_config *c = &m->cfg; const int dim = c->dim;
     float *x = malloc(sizeof(float) * dim), *row = malloc(sizeof(float) * dim);
     /* lm.h:555-584: text emb first, then audio codebooks added left to right */
-    embed_row(&m->text_emb, tokens[0], x);
+    if (c->demux_second_stream) embed_demux(m, &m->text_emb, &m->text_out1, &m->text_out2, c->text_card + 1, tokens[0], x);
+    else embed_row(&m->text_emb, tokens[0], x);
     for (int q = 0; q < c->n_q; q++) { embed_row(&m->emb[q], tokens[q + 1], row); for (int i = 0; i < dim; i++) x[i] = x[i] + row[i]; }
+    if (s->cond_sum) for (int i = 0; i < dim; i++) x[i] = s->cond_sum[i] + x[i];      /* lm.h:575-577 */
     const int pos = s->offset; s->offset += 1;          /* transformer.h:1269-1270 */
     const size_t lstride = (size_t)c->context * dim;
     for (int l = 0; l < c->num_layers; l++)
         transformer_layer(m, &m->layers[l], 0, dim, c->num_heads, c->context, c->max_period, pos,
-                          s->k + l * lstride, s->v + l * lstride, x);
+                          s->k + l * lstride, s->v + l * lstride, x,
+                          s->kv_cross ? s->kv_cross + (size_t)l * s->tc * 2 * dim : NULL, s->tc);
     orc_rms_norm(x, (const float *)m->out_norm.data, 1e-8f, s->transformer_out, dim);   /* lm.h:671-672 */
     float *logits = text_logits ? text_logits : malloc(sizeof(float) * c->text_card);
     linear(m, &m->text_linear, s->transformer_out, logits);
@@ -626,16 +737,20 @@ void orc_step_depformer(orc_model *m, orc_state *s, int text_token, const int32_
     for (int k = 0; k < c->dep_q; k++) {
         int w = c->schedule_len ? c->schedule[k] : k;                 /* lm.h:457-462 */
         int wl = m->dep_num_weights == 1 ? 0 : w;                     /* transformer.h:74-83 */
-        if (k == 0) embed_row(&m->dep_text_emb, prev, e);              /* lm.h:494-501, scaled (-1 -> 0) */
-        else {                                                         /* chained get_rows, lm_utils.h:209-217 */
+        if (k == 0) {                                                  /* lm.h:494-501, scaled (-1 -> 0) */
+            if (c->demux_second_stream) embed_demux(m, &m->dep_text_emb, &m->dep_text_out1, &m->dep_text_out2, c->text_card + 1, prev, e);
+            else if (m->dep_text_lr.data) embed_low_rank(m, &m->dep_text_emb, &m->dep_text_lr, prev, 1, e);
+            else embed_row(&m->dep_text_emb, prev, e);
+        } else {                                                       /* chained get_rows (+ low_rank), lm_utils.h:209-217 */
             const orc_tensor *t = &m->dep_emb[k - 1];
-            orc_dequantize_row(t->type, (const char *)t->data + (int64_t)prev * orc_row_size(t->type, t->ne0), e, t->ne0);
+            if (m->dep_emb_lr[k - 1].data) embed_low_rank(m, t, &m->dep_emb_lr[k - 1], prev, 0, e);
+            else orc_dequantize_row(t->type, (const char *)t->data + (int64_t)prev * orc_row_size(t->type, t->ne0), e, t->ne0);
         }
         linear(m, &m->dep_in[m->dep_num_weights == 1 ? 0 : w], s->transformer_out, y);
         for (int i = 0; i < dd; i++) y[i] = y[i] + e[i];
         for (int l = 0; l < c->dep_layers; l++)
             transformer_layer(m, &m->dep_layers[l], wl, dd, c->dep_heads, m->dep_cap, c->dep_max_period, k,
-                              s->dk + l * lstride, s->dv + l * lstride, y);
+                              s->dk + l * lstride, s->dv + l * lstride, y, NULL, 0);
         linear(m, &m->linears[k], y, logits);                          /* lm.h:472, no final norm */
         int tok = (s->temp_audio > 0.f && s->noise_audio)
                       ? sample_top_k(logits, (int)m->linears[k].ne1, s->temp_audio, s->top_k_audio,
@@ -646,6 +761,20 @@ void orc_step_depformer(orc_model *m, orc_state *s, int text_token, const int32_
         prev = (force && force[k] >= 0) ? force[k] : tok;
     }
     free(y); free(e); free(logits);
+}
+
+void orc_state_set_condition(orc_state *s, const float *sum, const float *cross, int tc) {
+    orc_model *m = s->m; const orc_config *c = &m->cfg; const int dim = c->dim;
+    free(s->cond_sum); s->cond_sum = NULL; free(s->kv_cross); s->kv_cross = NULL; s->tc = 0;
+    if (sum) { s->cond_sum = malloc(sizeof(float) * dim); memcpy(s->cond_sum, sum, sizeof(float) * dim); }
+    if (cross && tc > 0 && c->cross_attention) {
+        /* init(): kv = in_proj rows [dim, 3*dim) applied to every condition column (transformer.h:343-396) */
+        s->tc = tc;
+        s->kv_cross = malloc(sizeof(float) * (size_t)c->num_layers * tc * 2 * dim);
+        for (int l = 0; l < c->num_layers; l++)
+            for (int i = 0; i < tc; i++)
+                linear_rows(m, &m->layers[l].cross_in, dim, 2 * dim, cross + (size_t)i * dim, s->kv_cross + ((size_t)l * tc + i) * 2 * dim);
+    }
 }
 
 float orc_vad(orc_model *m, orc_state *s) {

@@ -38,6 +38,10 @@ typedef struct orc_config {
     int32_t personaplex;
     int32_t extra_heads;        /* extra_heads_num_heads */
     int32_t delay_steps;        /* moshi_lm_set_delay_steps */
+    /* TTS-family switches (moshi.h:111-156): */
+    int32_t cross_attention;    /* temporal layers carry norm_cross + cross_attention (lm_default.h:18-34) */
+    int32_t demux_second_stream;/* text embeddings are moshi_scaled_embedding_demux_t (lm_default.h:175-184, 205-211) */
+    int32_t dep_low_rank;       /* depformer_low_rank_embeddings: != 0 -> depformer embeddings carry a low_rank linear */
 } orc_config;
 
 typedef struct orc_model orc_model;
@@ -83,6 +87,10 @@ void orc_step_depformer(orc_model *m, orc_state *s, int text_token, const int32_
 /* sampling: temp <= 0 keeps greedy; noise_text[top_k_text], noise_audio[dep_q][min(top_k_audio, card)] must outlive the steps */
 void orc_state_set_sampling(orc_state *s, float temp_text, float temp_audio, int top_k_text, int top_k_audio);
 void orc_state_set_noise(orc_state *s, const float *noise_text, const float *noise_audio);
+/* TTS conditioning (moshi.cpp:851-883, transformer.h:343-396, lm.h:575-577): sum[dim] is added to the embedding sum of
+ * every frame, cross[Tc][dim] is projected ONCE through every layer's cross_attention.in_proj rows [dim, 3*dim) into
+ * f32 k_cross / v_cross.  Either may be NULL. */
+void orc_state_set_condition(orc_state *s, const float *sum, const float *cross, int tc);
 /* STT VAD head (lm.h:966-976): softmax(extra_heads[2] . transformer_out)[0] */
 float orc_vad(orc_model *m, orc_state *s);
 /* debugging / parity: copy KV row */

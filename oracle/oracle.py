@@ -24,6 +24,7 @@ class OrcConfig(C.Structure):
         ("n_delays", C.c_int32), ("delays", C.c_int32 * ORC_MAX_CODEBOOKS),
         ("schedule_len", C.c_int32), ("schedule", C.c_int32 * ORC_MAX_STEPS),
         ("personaplex", C.c_int32), ("extra_heads", C.c_int32), ("delay_steps", C.c_int32),
+        ("cross_attention", C.c_int32), ("demux_second_stream", C.c_int32), ("dep_low_rank", C.c_int32),
     ]
 
 
@@ -67,6 +68,7 @@ def lib():
         L.orc_step_temporal.restype = C.c_int; L.orc_step_temporal.argtypes = [vp, vp, vp, vp, vp]
         L.orc_step_depformer.argtypes = [vp, vp, C.c_int, vp, vp, vp]
         L.orc_vad.restype = C.c_float; L.orc_vad.argtypes = [vp, vp]
+        L.orc_state_set_condition.argtypes = [vp, vp, vp, C.c_int]
         L.orc_state_set_sampling.argtypes = [vp, C.c_float, C.c_float, C.c_int, C.c_int]
         L.orc_state_set_noise.argtypes = [vp, vp, vp]
         L.orc_state_get_kv.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp]
@@ -97,6 +99,9 @@ def make_config(cfg: dict, delay_steps: int = 0) -> OrcConfig:
     c.personaplex = 1 if cfg["model_type"] == "personaplex" else 0
     c.extra_heads = cfg["extra_heads"]
     c.delay_steps = delay_steps
+    c.cross_attention = 1 if cfg.get("cross_attention") else 0
+    c.demux_second_stream = 1 if cfg.get("demux") else 0
+    c.dep_low_rank = int(cfg.get("dep_low_rank") or 0)
     return c
 
 
@@ -218,6 +223,12 @@ class State:
 
     def vad(self) -> float:
         return float(lib().orc_vad(self.model.h, self.h))
+
+    def set_condition(self, cond_sum=None, cond_cross=None):
+        """cond_sum [dim] and / or cond_cross [Tc][dim] (moshi.cpp:851-883)"""
+        s = np.ascontiguousarray(cond_sum, dtype=np.float32) if cond_sum is not None else None
+        c = np.ascontiguousarray(cond_cross, dtype=np.float32) if cond_cross is not None else None
+        lib().orc_state_set_condition(self.h, _p(s) if s is not None else None, _p(c) if c is not None else None, 0 if c is None else c.shape[0])
 
     def set_sampling(self, temp_text, temp_audio, top_k_text=25, top_k_audio=250):
         lib().orc_state_set_sampling(self.h, temp_text, temp_audio, top_k_text, top_k_audio)

@@ -427,3 +427,65 @@ def test_batch_rejects_q8_0_and_bad_sizes(msx, gguf_for):
     for n in (0, 9):
         with pytest.raises(msx.MsxError):
             msx.Batch(gm, n)
+
+
+# ---------------------------------------------------------------------------------------------------
+# TTS family: cross-attention memory, condition_sum, demuxed text
+# embeddings, low-rank depformer embeddings
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("preset,quant,tc", [("tiny_tts", "q4_k", 37), ("tiny_tts", "q8_0", 5), ("tiny_lowrank", "q4_k", 0)])
+def test_tts_family_step_parity(msx, orc, gguf_for, preset, quant, tc):
+    """teacher-forced like run_teacher_forced, with a conditioning memory (cond_cross [Tc][dim] -> per-layer f32 k/v,
+    transformer.h:343-396), condition_sum (lm.h:575-577) and two-stream text tokens (second + 1) * (text_card + 1) + text
+    as StateMachine::process emits them (lm.h:171-188)"""
+    path, cfg = gguf_for(preset, quant)
+    gm = msx.Model(path, cfg); gs = msx.Stream(gm)
+    om = orc.Model(path, cfg); os_ = orc.State(om)
+    rng = np.random.default_rng(17)
+    if tc:
+        cs = (0.2 * rng.standard_normal(cfg["dim"])).astype(np.float32)
+        cc = rng.standard_normal((tc, cfg["dim"])).astype(np.float32)
+        gs.set_condition(cs, cc); os_.set_condition(cs, cc)
+    n_q, dep_q, ne = cfg["n_q"], cfg["dep_q"], cfg["text_card"] + 1
+    toks = np.array([cfg["text_card"]] + [cfg["card"]] * n_q, dtype=np.int32)
+    n_exact = n_cmp = 0
+    for f in range(24):
+        t_ref, lg_ref, to_ref = os_.step_temporal(toks)
+        t_gpu, lg_gpu, to_gpu = gs.step_temporal(toks)
+        assert max_rel(lg_gpu, lg_ref) < LOGIT_TOL and max_rel(to_gpu, to_ref) < LOGIT_TOL, f"frame {f}"
+        n_cmp += 1; n_exact += int(np.array_equal(lg_gpu.view(np.uint32), lg_ref.view(np.uint32)))
+        # the text token the state machine would hand to the depformer: sometimes with a second-stream word
+        text = int(t_ref)
+        if cfg["demux"] and f % 3 != 0:
+            text = (int(rng.integers(0, cfg["text_card"])) + 1) * ne + text
+        if f % 5 == 4:
+            text = -1 if not cfg["demux"] else 0
+        a_ref, al_ref = os_.step_depformer(text)
+        a_gpu, al_gpu = gs.step_depformer(text, force=a_ref)
+        for k in range(dep_q):
+            assert max_rel(al_gpu[k], al_ref[k]) < LOGIT_TOL, f"frame {f} codebook {k}"
+            n_cmp += 1; n_exact += int(np.array_equal(al_gpu[k].view(np.uint32), al_ref[k].view(np.uint32)))
+        user = list(rng.integers(0, cfg["card"], size=n_q - dep_q))
+        toks = np.array([text] + list(a_ref) + user, dtype=np.int32)
+    assert n_exact >= 0.98 * n_cmp, f"only {n_exact}/{n_cmp} logit vectors bit-identical"
+
+
+def test_condition_changes_output_and_can_be_replaced(msx, orc, gguf_for):
+    path, cfg = gguf_for("tiny_tts", "q4_k")
+    gm = msx.Model(path, cfg); gs = msx.Stream(gm)
+    om = orc.Model(path, cfg); os_ = orc.State(om)
+    rng = np.random.default_rng(2)
+    toks = np.array([cfg["text_card"]] + [cfg["card"]] * cfg["n_q"], dtype=np.int32)
+    _, l0, _ = gs.step_temporal(toks)
+    for tc in (3, 64, 9):                                   # memory re-sized between utterances
+        cc = rng.standard_normal((tc, cfg["dim"])).astype(np.float32)
+        gs.reset(); os_.reset()
+        gs.set_condition(None, cc); os_.set_condition(None, cc)
+        _, l1, _ = gs.step_temporal(toks); _, r1, _ = os_.step_temporal(toks)
+        assert max_rel(l1, r1) < LOGIT_TOL
+        assert max_rel(l1, l0) > 1e-3, "the conditioning memory must influence the logits"
+    # a model without cross-attention refuses a memory (reference: moshi_lm_set_voice_condition returns -1)
+    path2, cfg2 = gguf_for("tiny", "q4_k")
+    s2 = msx.Stream(msx.Model(path2, cfg2))
+    with pytest.raises(msx.MsxError):
+        s2.set_condition(None, np.zeros((2, cfg2["dim"]), dtype=np.float32))
