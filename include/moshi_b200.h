@@ -160,6 +160,14 @@ MSX_API int msx_gen_create_with_callback(const msx_config *cfg, int delay_steps,
 MSX_API void msx_gen_free(msx_gen *g);
 /* srand() for the Exp(1) draws of sampled generation (the reference never seeds except in --bench: srand(0)) */
 MSX_API void msx_gen_seed(msx_gen *g, unsigned seed);
+/* TTS hooks of the generator.  text hook: called between the temporal and the depformer graph with the sampled text
+ * token, returns the token to use instead (state machine / text prefix, lm.h:877-899).  audio hook: may overwrite the
+ * dep_q audio tokens of this frame (audio prefix, lm.h:922-931); returns the number of following frames whose output
+ * is to be swallowed (state->skip), or -1 to leave it alone. */
+typedef int32_t (*msx_text_hook)(void *user, int32_t offset, int32_t text_token);
+typedef int (*msx_audio_hook)(void *user, int32_t offset, int32_t *audio_tokens, int n);
+MSX_API int msx_gen_set_text_hook(msx_gen *g, msx_text_hook fn, void *user);
+MSX_API int msx_gen_set_audio_hook(msx_gen *g, msx_audio_hook fn, void *user);
 MSX_API int msx_gen_step(msx_gen *g, const int32_t *in_tokens, int n_in, int depformer_replace_tokens,
                          int32_t *out_text, int32_t *out_audio);
 MSX_API int msx_gen_offset(const msx_gen *g);

@@ -134,5 +134,6 @@ def to_config_json(cfg: dict) -> dict:
         "depformer_weights_per_step_schedule": cfg["schedule"] or None,
         "conditioners": {}, "cross_attention": bool(cfg.get("cross_attention")), "model_type": cfg["model_type"],
         "demux_second_stream": bool(cfg.get("demux")), "depformer_low_rank_embeddings": cfg.get("dep_low_rank") or None,
+        "tts_config": {"audio_delay": 1.28, "second_stream_ahead": 2} if cfg["model_type"] == "tts" else None,
         "extra_heads_num_heads": cfg["extra_heads"], "extra_heads_dim": cfg["extra_heads_dim"],
     }

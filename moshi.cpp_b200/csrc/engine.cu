@@ -1364,6 +1364,10 @@ struct msx_gen {
     int offset = 0, CT = 0, ncb = 0, max_delay = 0, delay_steps = 0;
     std::vector<int32_t> cache;       // [CT][ncb], init -2 = lm_ungenerated_token_id
     std::vector<int32_t> initial;     // {text_card, card, card, ...}
+    // TTS hooks (lm.h:877-899 on_text_hook, 915-931 on_audio_hook) and the frames to swallow after an audio prefix
+    msx_text_hook text_hook = nullptr; void *text_user = nullptr;
+    msx_audio_hook audio_hook = nullptr; void *audio_user = nullptr;
+    int skip = 0;
 };
 
 static void gen_init_impl(msx_gen *g, int delay_steps);
@@ -1406,6 +1410,17 @@ extern "C" void msx_gen_seed(msx_gen *, unsigned seed) { srand(seed); }
 extern "C" int msx_gen_offset(const msx_gen *g) { return g ? g->offset : -1; }
 extern "C" int msx_gen_max_delay(const msx_gen *g) { return g ? g->max_delay : -1; }
 
+extern "C" int msx_gen_set_text_hook(msx_gen *g, msx_text_hook fn, void *user) {
+    if (!g) return fail(MSX_ERR_ARG, "null generator");
+    g->text_hook = fn; g->text_user = user;
+    return 0;
+}
+extern "C" int msx_gen_set_audio_hook(msx_gen *g, msx_audio_hook fn, void *user) {
+    if (!g) return fail(MSX_ERR_ARG, "null generator");
+    g->audio_hook = fn; g->audio_user = user;
+    return 0;
+}
+
 extern "C" int msx_gen_step(msx_gen *g, const int32_t *in_tokens, int n_in, int depformer_replace_tokens, int32_t *out_text, int32_t *out_audio) {
     if (!g || !out_text || !out_audio) return fail(MSX_ERR_ARG, "null argument");
     msx_stream *s = g->s;
@@ -1443,7 +1458,14 @@ extern "C" int msx_gen_step(msx_gen *g, const int32_t *in_tokens, int n_in, int 
     }
     if (g->fn) {
         if (int e = g->fn(g->user, input, depformer_replace_tokens, out)) return fail(MSX_ERR_STATE, "step callback failed: " + std::to_string(e));
+        if (g->text_hook) out[0] = g->text_hook(g->text_user, g->offset, out[0]);               // (callback mode: applied after the fact)
         if (depformer_replace_tokens) for (int q = 0; q < c.dep_q; q++) out[1 + q] = -1;      // lm.h:909-913
+    } else if (g->text_hook) {
+        // the text token is rewritten between the two graphs (state machine / text prefix, lm.h:877-899)
+        if (int e = msx_step_temporal(s, input, &out[0], nullptr, nullptr)) return e;
+        out[0] = g->text_hook(g->text_user, g->offset, out[0]);
+        if (c.dep_q > 0 && !depformer_replace_tokens)
+            if (int e = msx_step_depformer(s, out[0], nullptr, out + 1, nullptr)) return e;
     } else if (c.dep_q > 0 && !depformer_replace_tokens) {
         if (int e = msx_step(s, input, out)) return e;                        // temporal + depformer, one sync
     } else {
@@ -1454,6 +1476,10 @@ extern "C" int msx_gen_step(msx_gen *g, const int32_t *in_tokens, int n_in, int 
     if (c.dep_q > 0 && g->delay_steps)
         for (int q = 0; q < c.dep_q; q++)
             if (g->offset < c.delays[q + 1] + g->delay_steps) audio[q] = -1;  // lm.h:915-921
+    if (c.dep_q > 0 && g->audio_hook) {                                       // audio prefix (lm.h:922-931)
+        const int sk = g->audio_hook(g->audio_user, g->offset, audio, c.dep_q);
+        if (sk >= 0) g->skip = sk;
+    }
     g->offset++;
     if (!provided) {
         const int p = g->offset % CT;
@@ -1461,6 +1487,7 @@ extern "C" int msx_gen_step(msx_gen *g, const int32_t *in_tokens, int n_in, int 
         for (int q = 0; q < c.dep_q; q++) g->cache[(size_t)p * ncb + q + 1] = audio[q];
     }
     for (int q = 0; q < c.dep_q; q++) out_audio[q] = audio[q];
+    if (g->skip > 0) { --g->skip; return 0; }                                 // lm.h:944-947
     if (g->offset <= g->max_delay || depformer_replace_tokens) return 0;
     *out_text = g->cache[(size_t)((g->offset - g->max_delay + c.delays[0]) % CT) * ncb + 0];
     for (int i = 1; i < dep_q_1; i++)

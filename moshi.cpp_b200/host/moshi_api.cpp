@@ -98,6 +98,25 @@ int moshi_get_config(moshi_config_t *c, const char *filename) {
         else if (k == "depformer_weights_per_step_schedule") ok = arr(c->depformer_weights_per_step_schedule);
         else if (k == "model_type") ok = string_or_null(c->model_type); else if (k == "tokenizer_name") ok = string_or_null(c->tokenizer_name);
         else if (k == "mimi_name") ok = string_or_null(c->mimi_name); else if (k == "moshi_name") ok = string_or_null(c->moshi_name);
+        else if (k == "tts_config") {                              // config_tts_parse (config.h:54-70)
+            j.ws();
+            if (j.lit("null")) ok = true;
+            else if (j.p < j.e && *j.p == '{') {
+                j.p++;
+                while (ok) {
+                    j.ws();
+                    if (j.p < j.e && *j.p == '}') { j.p++; break; }
+                    std::string kk;
+                    if (!j.str(kk)) { ok = false; break; }
+                    j.ws(); if (j.p >= j.e || *j.p != ':') { ok = false; break; } j.p++;
+                    if (kk == "second_stream_ahead") ok = i64(c->tts_config.second_stream_ahead);
+                    else if (kk == "audio_delay") { double d = 0; j.ws(); ok = j.num(d); c->tts_config.audio_delay = (float)d; }
+                    else ok = j.skip();
+                    j.ws();
+                    if (j.p < j.e && *j.p == ',') j.p++;
+                }
+            } else ok = false;
+        }
         else ok = j.skip();
         if (!ok) { fprintf(stderr, "error: reading config %s\n", filename); return -1; }
         j.ws();
@@ -115,6 +134,7 @@ struct moshi_lm_t {
     msx_config cfg{};
     msx_model *model = nullptr;
     int delay_steps = 0;
+    int second_stream_ahead = 0;
     std::string want_quant;
 };
 
@@ -132,6 +152,8 @@ static bool to_msx(const moshi_config_t &c, msx_config *m) {
     for (int i = 0; i < m->schedule_len; i++) m->schedule[i] = (int)c.depformer_weights_per_step_schedule[i];
     m->personaplex = c.model_type == "personaplex";
     m->extra_heads = (int)c.extra_heads_num_heads;
+    m->cross_attention = c.cross_attention; m->demux_second_stream = c.demux_second_stream;
+    m->dep_low_rank = (int)c.depformer_low_rank_embeddings;
     return true;
 }
 
@@ -140,12 +162,9 @@ moshi_lm_t *moshi_lm_from_files(moshi_context_t *moshi, moshi_config_t *config, 
     FILE *f = fopen(filepath, "rb");                       // reference: WeightLoader::from_gguf returns NULL (moshi.cpp:621-627)
     if (!f) return nullptr;
     fclose(f);
-    if (config->cross_attention || config->demux_second_stream) {
-        fprintf(stderr, "moshi_b200: cross-attention / demux (TTS) models are not supported yet\n");
-        return nullptr;
-    }
     auto lm = new moshi_lm_t;
     lm->filepath = filepath; lm->device = moshi->device;
+    lm->second_stream_ahead = (int)config->tts_config.second_stream_ahead;      // moshi.cpp:633
     if (!to_msx(*config, &lm->cfg)) { delete lm; return nullptr; }
     return lm;
 }
@@ -166,6 +185,82 @@ int moshi_lm_load(moshi_lm_t *lm) {
     return msx_model_load_gguf(lm->filepath.c_str(), &lm->cfg, lm->device, &lm->model);
 }
 
+// ---- TTS text scheduling: TokenIds / State / StateMachine (src/moshi/models/lm.h:5-194) -------------------------
+// The model proposes PAD or NEW_WORD; the machine decides what is actually fed: queued word tokens, forced
+// padding after a word, at most max_padding pads in a row, the look-ahead word on the second text stream.
+struct moshi_tts_machine_t {
+    static constexpr int kNewWord = 0, kPad = 3, kZero = -1;     // TokenIds (lm.h:5-18)
+    int card, second_stream_ahead, max_padding, initial_padding;
+    int remaining_padding, forced_padding, end_step = -1;
+    std::deque<Entry> entries;
+    std::deque<int> queued, lookahead_queued;
+
+    moshi_tts_machine_t(int text_card, int ahead, int max_pad, int init_pad)
+        : card(text_card), second_stream_ahead(ahead), max_padding(max_pad), initial_padding(init_pad),
+          remaining_padding(init_pad), forced_padding(init_pad) {}
+    void reset() {                                               // reset_state (lm.h:95-102)
+        remaining_padding = initial_padding; forced_padding = initial_padding; end_step = -1;
+        entries.clear(); queued.clear(); lookahead_queued.clear();
+    }
+    bool is_empty() const { return entries.empty() && queued.empty() && lookahead_queued.empty(); }
+    std::vector<int> tokens_ahead(int lookahead) const {         // State::get_tokens_ahead (lm.h:28-39)
+        for (const Entry &e : entries) {
+            if (e.tokens.empty()) continue;
+            if (--lookahead != 0) continue;
+            return e.tokens;
+        }
+        return {};
+    }
+    int process(int step, int token) {                           // StateMachine::process (lm.h:104-193)
+        if (token != kNewWord && token != kPad) token = kPad;
+        if (!queued.empty()) token = kPad;                       // text tokens still to be fed
+        else if (forced_padding > 0) token = kPad;
+        else if (remaining_padding <= 0) token = kNewWord;       // not allowed to pad any longer
+        if (token == kNewWord) {
+            if (!entries.empty()) {
+                Entry entry = entries.front();
+                entries.pop_front();
+                if (!entry.tokens.empty()) {
+                    for (int t : entry.tokens) queued.push_back(t);
+                    if (second_stream_ahead)
+                        for (int t : tokens_ahead(second_stream_ahead)) lookahead_queued.push_back(t);
+                    remaining_padding = max_padding;
+                } else token = kPad;
+                forced_padding = entry.padding;
+            } else {
+                token = kPad;
+                if (second_stream_ahead && end_step < 0) token = kNewWord;
+                if (end_step < 0) end_step = step;               // consumed past the last word
+            }
+        }
+        int output = 0;
+        if (token == kPad) {
+            if (remaining_padding > 0) remaining_padding -= 1;
+            if (forced_padding > 0) forced_padding -= 1;
+            if (!queued.empty()) { output = queued.front(); queued.pop_front(); }
+            else output = kPad;
+        } else if (token == kNewWord) output = kNewWord;
+        else if (token == kZero) output = token;
+        if (second_stream_ahead) {
+            int second = -1;
+            if (output == kNewWord) {
+                second = kNewWord;
+                if (!queued.empty()) { output = queued.front(); queued.pop_front(); }
+                else output = kPad;
+            } else if (!lookahead_queued.empty()) { second = lookahead_queued.front(); lookahead_queued.pop_front(); }
+            output = (second + 1) * card + output;
+        }
+        return output;
+    }
+};
+moshi_tts_machine_t *moshi_tts_machine_new(int text_card, int ahead, int max_padding, int initial_padding) { return new moshi_tts_machine_t(text_card, ahead, max_padding, initial_padding); }
+void moshi_tts_machine_free(moshi_tts_machine_t *m) { delete m; }
+void moshi_tts_machine_push(moshi_tts_machine_t *m, const int *tokens, int n, int padding) { Entry e; e.tokens.assign(tokens, tokens + n); e.padding = padding; m->entries.push_back(e); }
+int moshi_tts_machine_process(moshi_tts_machine_t *m, int step, int token) { return m->process(step, token); }
+int moshi_tts_machine_end_step(moshi_tts_machine_t *m) { return m->end_step; }
+int moshi_tts_machine_is_empty(moshi_tts_machine_t *m) { return m->is_empty() ? 1 : 0; }
+void moshi_tts_machine_reset(moshi_tts_machine_t *m) { m->reset(); }
+
 // ---- generator -----------------------------------------------------------------------------------------
 struct moshi_lm_gen_t {
     moshi_lm_t *lm = nullptr;
@@ -174,9 +269,59 @@ struct moshi_lm_gen_t {
     std::vector<int32_t> audio_tokens;                         // moshi_lm_send2 -> next receive
     std::deque<std::vector<int16_t>> prompt_audio;             // personaplex voice prompt (codes)
     std::vector<int> text_prompt_tokens;                       // personaplex system prompt
+    // TTS (voice_t + machine of the reference's moshi_lm_gen_t, moshi.cpp:586-606)
+    bool has_voice = false;
+    std::vector<float> cond_sum, cond_cross; int tc = 0;
+    std::deque<int> text_prefixes;
+    std::deque<std::vector<int>> audio_prefixes;
+    moshi_tts_machine_t *machine = nullptr;
 };
 moshi_lm_gen_t *moshi_lm_generator(moshi_lm_t *lm) { auto g = new moshi_lm_gen_t; g->lm = lm; return g; }
-void unref(moshi_lm_gen_t *g) { if (g) { msx_gen_free(g->gen); msx_stream_free(g->stream); delete g; } }
+void unref(moshi_lm_gen_t *g) { if (g) { msx_gen_free(g->gen); msx_stream_free(g->stream); delete g->machine; delete g; } }
+
+int moshi_lm_set_condition(moshi_lm_gen_t *gen, const float *cond_sum, const float *cond_cross, int tc) {
+    if (!gen) return -1;
+    const msx_config &c = gen->lm->cfg;
+    if (cond_cross && !c.cross_attention) return -1;           // uses_cross check of moshi_lm_set_voice_condition
+    gen->cond_sum.clear(); gen->cond_cross.clear(); gen->tc = 0;
+    if (cond_sum) gen->cond_sum.assign(cond_sum, cond_sum + c.dim);
+    if (cond_cross && tc > 0) { gen->cond_cross.assign(cond_cross, cond_cross + (size_t)tc * c.dim); gen->tc = tc; }
+    gen->has_voice = true;
+    return 0;
+}
+int moshi_lm_set_voice_condition(moshi_context_t *, moshi_lm_gen_t *gen, const char *) { return gen->lm->cfg.cross_attention ? -2 : -1; }
+int moshi_lm_load_voice_condition(moshi_context_t *, moshi_lm_gen_t *gen) { return gen->lm->cfg.cross_attention ? -2 : -1; }
+int moshi_lm_voice_prefix(moshi_lm_gen_t *gen, std::deque<int> &text_prefix, std::deque<std::vector<int>> &audio_prefix) {
+    gen->text_prefixes.clear(); gen->audio_prefixes.clear();
+    gen->text_prefixes.swap(text_prefix);                      // the reference swaps (steals) both deques (moshi.cpp:768-769)
+    gen->audio_prefixes.swap(audio_prefix);
+    gen->has_voice = true;
+    return 0;
+}
+void moshi_lm_send(moshi_lm_gen_t *gen, Entry *entry) { if (gen->machine && entry) gen->machine->entries.push_back(*entry); }
+int moshi_lm_is_active(moshi_lm_gen_t *gen) {                  // moshi.cpp:940-945
+    if (!gen->machine || !gen->gen) return 0;
+    const int final_padding = 4;
+    const int end_offset = gen->machine->end_step + gen->lm->delay_steps + final_padding;
+    return (msx_gen_offset(gen->gen) < end_offset || gen->machine->end_step == -1) ? 1 : 0;
+}
+int moshi_lm_is_empty(moshi_lm_gen_t *gen) { return (!gen->machine || gen->machine->is_empty()) ? 1 : 0; }
+void moshi_lm_machine_reset(moshi_lm_gen_t *gen) { if (gen->machine) gen->machine->reset(); }
+
+// on_text_hook / on_audio_hook of moshi_lmgen_step (lm.h:877-899, 922-931)
+static int32_t tts_text_hook(void *user, int32_t offset, int32_t text_token) {
+    auto gen = static_cast<moshi_lm_gen_t *>(user);
+    if (!gen->text_prefixes.empty()) { const int t = gen->text_prefixes.front(); gen->text_prefixes.pop_front(); return t; }
+    return gen->machine->process(offset, text_token);
+}
+static int tts_audio_hook(void *user, int32_t, int32_t *audio, int n) {
+    auto gen = static_cast<moshi_lm_gen_t *>(user);
+    if (gen->audio_prefixes.empty()) return -1;
+    const std::vector<int> &codes = gen->audio_prefixes.front();
+    for (int q = 0; q < n && q < (int)codes.size(); q++) if (codes[q] != -2) audio[q] = codes[q];   // lm_ungenerated_token_id
+    gen->audio_prefixes.pop_front();
+    return 2;                                                   // skip_prefix default (lm.h:787)
+}
 
 int moshi_lm_personaplex_audio_prompt(moshi_lm_gen_t *gen, std::deque<std::vector<int16_t>> &audio_prompt) {
     gen->prompt_audio.clear();
@@ -217,7 +362,19 @@ void moshi_lm_start(moshi_context_t *, moshi_lm_gen_t *gen, float depth_temperat
     if (msx_stream_create(gen->lm->model, 0, &gen->stream) != 0) { fprintf(stderr, "moshi_b200: %s\n", msx_last_error()); return; }
     if (depth_temperature > 0.f || text_temperature > 0.f)
         if (msx_stream_set_sampling(gen->stream, text_temperature, depth_temperature, 25, 250) != 0) { fprintf(stderr, "moshi_b200: %s\n", msx_last_error()); return; }
+    if (gen->has_voice && !gen->lm->cfg.personaplex) {
+        // TTS: conditioning memory + state machine (moshi.cpp:857-871: max_padding 8, initial_padding 2)
+        if (!gen->cond_sum.empty() || gen->tc > 0)
+            if (msx_stream_set_condition(gen->stream, gen->cond_sum.empty() ? nullptr : gen->cond_sum.data(),
+                                         gen->tc > 0 ? gen->cond_cross.data() : nullptr, gen->tc) != 0) { fprintf(stderr, "moshi_b200: %s\n", msx_last_error()); return; }
+        delete gen->machine;
+        gen->machine = new moshi_tts_machine_t(gen->lm->cfg.text_card + 1, gen->lm->second_stream_ahead, 8, 2);
+    }
     if (msx_gen_create(gen->stream, gen->lm->delay_steps, &gen->gen) != 0) { fprintf(stderr, "moshi_b200: %s\n", msx_last_error()); return; }
+    if (gen->machine) {
+        msx_gen_set_text_hook(gen->gen, tts_text_hook, gen);
+        msx_gen_set_audio_hook(gen->gen, tts_audio_hook, gen);
+    }
     gen->audio_tokens.assign(gen->lm->cfg.n_q, 0);
     if (gen->lm->cfg.personaplex) personaplex_prompts(gen);
 }

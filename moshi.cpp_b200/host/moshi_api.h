@@ -5,8 +5,11 @@
 //   moshi_lm_get_max_delay, moshi_lm_get_delay_steps, moshi_lm_generator, moshi_lm_start, moshi_lm_send2,
 //   moshi_lm_receive, moshi_lm_receive2, moshi_lm_personaplex_audio_prompt, moshi_lm_personaplex_system_prompt,
 //   unref(...).
-// Out of scope: Mimi codec, tokenizer (sentencepiece), TTS state machine /
-// voice conditioning, quantise-on-load — those entry points are not declared here.
+//   TTS: Entry, moshi_lm_send, moshi_lm_is_active, moshi_lm_is_empty, moshi_lm_machine_reset, moshi_lm_voice_prefix,
+//   and moshi_lm_set_condition (the conditioning TENSORS; the conditioners that compute them from a voice file,
+//   moshi.cpp:296-366, are outside the per-frame path).
+// Out of scope: Mimi codec, tokenizer (sentencepiece), voice-file loading,
+// quantise-on-load — those entry points are not declared here.
 #pragma once
 #include <cstdint>
 #include <deque>
@@ -47,6 +50,7 @@ struct moshi_config_t {
     int64_t extra_heads_num_heads = 0;
     std::vector<int64_t> depformer_weights_per_step_schedule;
     std::string model_type, tokenizer_name, mimi_name, moshi_name = "model.safetensors";
+    struct { float audio_delay = 0.f; int64_t second_stream_ahead = 0; } tts_config;   // config_tts_t (moshi.h:90-97)
 };
 MOSHI_API int moshi_get_config(moshi_config_t *config, const char *filename);   // 0 ok, -1 on error (config.h:148-346)
 
@@ -66,7 +70,38 @@ MOSHI_API int moshi_lm_personaplex_audio_prompt(moshi_lm_gen_t *gen, std::deque<
 // the reference tokenises `prompt` with sentencepiece (moshi.cpp:838-849); without a tokenizer the caller passes ids
 MOSHI_API int moshi_lm_personaplex_system_prompt_tokens(moshi_lm_gen_t *gen, const std::vector<int> &text_tokens);
 MOSHI_API void moshi_lm_start(moshi_context_t *moshi, moshi_lm_gen_t *gen, float depth_temperature, float text_temperature, bool logging = false);
+// TTS word queue entry (moshi.h:63-68)
+struct Entry {
+    std::vector<int> tokens;
+    std::string text;
+    int padding = 0;
+    int64_t time = 0;
+};
+// conditioning tensors of the utterance: cond_sum[dim] (or NULL), cond_cross[tc][dim] (or NULL); call before moshi_lm_start.
+// Marks the generator as a TTS generator (state machine on), like a loaded voice does in the reference (moshi.cpp:857-871).
+MOSHI_API int moshi_lm_set_condition(moshi_lm_gen_t *gen, const float *cond_sum, const float *cond_cross, int tc);
+// reference entry points that need the safetensors loader + conditioners: -1 without cross-attention, -2 otherwise (moshi.cpp:729-760)
+MOSHI_API int moshi_lm_set_voice_condition(moshi_context_t *moshi, moshi_lm_gen_t *gen, const char *filepath);
+MOSHI_API int moshi_lm_load_voice_condition(moshi_context_t *moshi, moshi_lm_gen_t *gen);
+MOSHI_API int moshi_lm_voice_prefix(moshi_lm_gen_t *gen, std::deque<int> &text_prefix, std::deque<std::vector<int>> &audio_prefix);   // steals both deques
+MOSHI_API void moshi_lm_send(moshi_lm_gen_t *gen, Entry *entry);
+MOSHI_API int moshi_lm_is_active(moshi_lm_gen_t *gen);
+MOSHI_API int moshi_lm_is_empty(moshi_lm_gen_t *gen);
+MOSHI_API void moshi_lm_machine_reset(moshi_lm_gen_t *gen);
 MOSHI_API void moshi_lm_send2(moshi_lm_gen_t *gen, std::vector<int16_t> &audio_tokens);
 MOSHI_API int moshi_lm_receive(moshi_lm_gen_t *gen, int &text_token, std::vector<int16_t> &audio_tokens);
 MOSHI_API void moshi_lm_receive2(moshi_lm_gen_t *gen, int &text_token, float &vad);
 MOSHI_API const char *moshi_b200_last_error();
+
+// ---- TTS text scheduling (src/moshi/models/lm.h:5-194), exposed with C linkage so that host-only tests can drive it --
+struct moshi_tts_machine_t;
+extern "C" {
+#define MOSHI_C_API __attribute__((visibility("default")))
+MOSHI_C_API moshi_tts_machine_t *moshi_tts_machine_new(int text_card, int second_stream_ahead, int max_padding, int initial_padding);
+MOSHI_C_API void moshi_tts_machine_free(moshi_tts_machine_t *m);
+MOSHI_C_API void moshi_tts_machine_push(moshi_tts_machine_t *m, const int *tokens, int n_tokens, int padding);
+MOSHI_C_API int moshi_tts_machine_process(moshi_tts_machine_t *m, int step, int token);
+MOSHI_C_API int moshi_tts_machine_end_step(moshi_tts_machine_t *m);
+MOSHI_C_API int moshi_tts_machine_is_empty(moshi_tts_machine_t *m);
+MOSHI_C_API void moshi_tts_machine_reset(moshi_tts_machine_t *m);
+}

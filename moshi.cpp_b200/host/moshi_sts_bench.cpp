@@ -2,6 +2,9 @@
 // (tools/moshi-sts.cpp:731-808, tools/personaplex.cpp) reduced to the LM path: the Mimi encoder/decoder and
 // SDL/FFmpeg I/O are out of scope, so user audio codes are synthetic (seeded LCG) instead of encoded silence.
 //   moshi-sts-bench <model.gguf> <config.json> [frames=125] [device=0] [--print-tokens]
+// For a TTS model (model_type "tts": no user stream, cross-attention conditioning) it runs the moshi-tts --bench loop
+// instead (tools/moshi-tts.cpp:770-781): a synthetic conditioning memory, a script of LCG "words" sent as Entry
+// objects, receive() while moshi_lm_is_active().
 // Uses only the moshi_lm_* API (host/moshi_api.h), exactly like the reference tool uses include/moshi/moshi.h.
 #include <chrono>
 #include <cstdio>
@@ -26,6 +29,39 @@ int main(int argc, char **argv) {
     if (!lm) { fprintf(stderr, "error: could not open %s\n", argv[1]); return 1; }
     if (moshi_lm_load(lm) != 0) { fprintf(stderr, "error: %s\n", moshi_b200_last_error()); return 1; }
     moshi_lm_gen_t *gen = moshi_lm_generator(lm);
+    if (config.model_type == "tts") {
+        // conditioning tensors the conditioners would produce (moshi.cpp:296-366): seeded, deterministic
+        const int tc = 11, dim = (int)config.dim;
+        std::vector<float> sum(dim), cross((size_t)tc * dim);
+        uint32_t l2 = 7;
+        auto rnd = [&]() { l2 = l2 * 1664525u + 1013904223u; return ((l2 >> 8) % 2001) / 1000.f - 1.f; };
+        for (float &v : sum) v = 0.2f * rnd();
+        for (float &v : cross) v = rnd();
+        if (moshi_lm_set_condition(gen, sum.data(), config.cross_attention ? cross.data() : nullptr, tc) != 0) { fprintf(stderr, "error: set_condition\n"); return 1; }
+        moshi_lm_start(moshi, gen, 0.f, 0.f);
+        uint32_t l3 = 99;
+        for (int w = 0; w < 6; w++) {                                // six "words" of 1-3 tokens, padding 0-1
+            Entry e;
+            l3 = l3 * 1664525u + 1013904223u;
+            const int nt = 1 + (int)((l3 >> 8) % 3);
+            for (int i = 0; i < nt; i++) { l3 = l3 * 1664525u + 1013904223u; e.tokens.push_back(4 + (int)((l3 >> 8) % (config.text_card - 4))); }
+            e.padding = w % 2;
+            moshi_lm_send(gen, &e);
+        }
+        std::vector<int16_t> audio;
+        int text = -1, f = 0, emitted = 0;
+        const auto t0 = std::chrono::steady_clock::now();
+        while (moshi_lm_is_active(gen) && f < frames) {
+            const int ok = moshi_lm_receive(gen, text, audio);
+            if (ok) emitted++;
+            if (print_tokens) { printf("%d %d %d", f, ok, ok ? text : -1); if (ok) for (int16_t a : audio) printf(" %d", (int)a); printf("\n"); }
+            f++;
+        }
+        const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        fprintf(stderr, "tts frames %d emitted %d empty %d  %.2f frames/s\n", f, emitted, moshi_lm_is_empty(gen), f / sec);
+        unref(gen); unref(lm); unref(moshi);
+        return 0;
+    }
     if (config.model_type == "personaplex") {
         std::deque<std::vector<int16_t>> voice;                      // 4 frames of synthetic voice-prompt codes
         for (int f = 0; f < 4; f++) { std::vector<int16_t> c(8); for (int j = 0; j < 8; j++) c[j] = (int16_t)((f * 131 + j * 17) % config.card); voice.push_back(c); }
