@@ -113,6 +113,17 @@ MSX_API int msx_step(msx_stream *s, const int32_t *tokens, int32_t *out_tokens);
 MSX_API int msx_stream_set_sampling(msx_stream *s, float temp_text, float temp_audio, int top_k_text, int top_k_audio);
 MSX_API int msx_stream_set_noise(msx_stream *s, const float *noise_text, const float *noise_audio);
 /* STT VAD head (lm.h:966-976): softmax(extra_heads[2] . transformer_out)[0]; 0 if < 3 extra heads */
+/* ---- tensor parallelism over the temporal transformer (BASELINE.json config 4) -------------
+ * One process per GPU.  Rank r of `world` loads only its shard: the q/k/v rows and KV ring of heads
+ * [r*H/world, (r+1)*H/world), the matching out_proj columns, a hidden slice of the gated MLP; embeddings, text head and
+ * depformer are replicated.  out_proj / linear_out produce partial sums kept in DOUBLE, all-reduced with
+ * ncclAllReduce(sum, f64) inside the captured graph and rounded once into the residual stream, so every rank computes
+ * the single-GPU numbers.  msx_tp_unique_id on one rank, ship the 128 bytes to the others (torch.distributed, MPI, a
+ * file), then msx_stream_create_tp on every rank (collective).  NCCL is bound with dlopen("libnccl.so.2"). */
+MSX_API int msx_model_load_gguf_tp(const char *path, const msx_config *cfg, int device, int tp_rank, int tp_world, msx_model **out);
+MSX_API int msx_tp_unique_id(uint8_t *out128);
+MSX_API int msx_stream_create_tp(msx_model *model, int context_override, const uint8_t *nccl_id128, msx_stream **out);
+
 /* TTS conditioning (reference: moshi_lm_start -> init(), moshi.cpp:851-883; transformer.h:343-396; lm.h:575-577).
  * cond_sum[dim] (or NULL) is added to the embedding sum of every frame; cond_cross[tc][dim] (or NULL) is projected once
  * through every layer's cross_attention.in_proj rows [dim, 3*dim) into the f32 k_cross / v_cross memory.  The

@@ -91,6 +91,9 @@ def lib():
     L.msx_device_count.restype = C.c_int
     L.msx_model_load_gguf.argtypes = [C.c_char_p, C.POINTER(MsxConfig), C.c_int, C.POINTER(vp)]
     L.msx_model_free.argtypes = [vp]
+    L.msx_model_load_gguf_tp.argtypes = [C.c_char_p, C.POINTER(MsxConfig), C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+    L.msx_tp_unique_id.argtypes = [vp]
+    L.msx_stream_create_tp.argtypes = [vp, C.c_int, vp, C.POINTER(vp)]
     L.msx_model_config.argtypes = [vp, C.POINTER(MsxConfig)]
     L.msx_model_weight_bytes_per_frame.restype = C.c_int64; L.msx_model_weight_bytes_per_frame.argtypes = [vp]
     L.msx_model_device_bytes.restype = C.c_int64; L.msx_model_device_bytes.argtypes = [vp]
@@ -176,12 +179,20 @@ def make_config(cfg: dict) -> MsxConfig:
     return c
 
 
+def tp_unique_id() -> bytes:
+    """128-byte NCCL id for one tensor-parallel group: create on one rank, broadcast to the others"""
+    buf = np.zeros(128, dtype=np.uint8)
+    _check(lib().msx_tp_unique_id(_p(buf)))
+    return buf.tobytes()
+
+
 class Model:
-    def __init__(self, gguf_path: str, cfg: dict, device: int = 0):
+    def __init__(self, gguf_path: str, cfg: dict, device: int = 0, tp_rank: int = 0, tp_world: int = 1):
         self.cfg = cfg
         self._c = make_config(cfg)
+        self.tp_rank, self.tp_world = tp_rank, tp_world
         h = C.c_void_p()
-        _check(lib().msx_model_load_gguf(gguf_path.encode(), C.byref(self._c), device, C.byref(h)))
+        _check(lib().msx_model_load_gguf_tp(gguf_path.encode(), C.byref(self._c), device, tp_rank, tp_world, C.byref(h)))
         self.h = h
 
     @property
@@ -204,10 +215,15 @@ class Model:
 
 
 class Stream:
-    def __init__(self, model: Model, context: int = 0, persistent_depformer: bool = False):
+    def __init__(self, model: Model, context: int = 0, persistent_depformer: bool = False, nccl_id: bytes | None = None):
         self.model = model
         h = C.c_void_p()
-        _check(lib().msx_stream_create_ex(model.h, context, 1 if persistent_depformer else 0, C.byref(h)))
+        if nccl_id is not None:
+            idb = np.frombuffer(nccl_id, dtype=np.uint8).copy()
+            assert idb.size == 128
+            _check(lib().msx_stream_create_tp(model.h, context, _p(idb), C.byref(h)))
+        else:
+            _check(lib().msx_stream_create_ex(model.h, context, 1 if persistent_depformer else 0, C.byref(h)))
         self.h = h
 
     @property

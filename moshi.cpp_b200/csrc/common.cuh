@@ -82,6 +82,7 @@ enum Epilogue : int {
     EPI_GATE = 2,      // out[r/2] = silu(acc[r]) * acc[r+1]  (rows interleaved at repack)
     EPI_ARGMAX = 3,    // out[r] = acc and atomicMax(key)
     EPI_ADD_EMB = 4,   // out[r] = acc + emb_table[token][r]  (depformer_in + last-token embedding)
+    EPI_STORE_F64 = 6, // out_f64[r] = the un-rounded double accumulator (tensor-parallel partial sums, all-reduced in double)
     EPI_ADD_VEC = 5,   // out[r] = acc + addvec[r]            (depformer_in + low-rank / demux embedding computed by small_linear_kernel)
 };
 
@@ -100,6 +101,7 @@ struct GemvArgs {
     Ctrl *ctrl = nullptr;
     int32_t emb_step = 0;           // 0: text token (scaled embedding), k>0: audio token of step k-1 (chained)
     const float *addvec = nullptr;  // EPI_ADD_VEC
+    double *out_f64 = nullptr;      // EPI_STORE_F64
 };
 
 // warp index broadcast from lane 0: tells the compiler the value is warp-uniform, so loops and branches on it

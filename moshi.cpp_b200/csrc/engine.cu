@@ -1,6 +1,7 @@
 // engine.cu — model loading/repack, per-stream state, CUDA-graph step orchestration and the C ABI
 // declared in include/moshi_b200.h.  See DESIGN.md for the mapping to the reference.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <climits>
@@ -39,6 +40,41 @@ static int fail(int code, const std::string &msg) { g_err = msg; return code; }
     } while (0)
 
 extern "C" const char *msx_last_error(void) { return g_err.c_str(); }
+
+// ---- NCCL, bound at run time (tensor-parallel streams only) -------------------------------------------
+// dlopen by soname: inside a torch process this resolves to the NCCL torch has already loaded, so one
+// process never holds two NCCL copies; a process that never asks for tensor parallelism never loads it.
+namespace {
+struct Nccl {
+    typedef struct { char internal[128]; } UniqueId;
+    typedef void *Comm;
+    int (*GetUniqueId)(UniqueId *) = nullptr;
+    int (*CommInitRank)(Comm *, int, UniqueId, int) = nullptr;
+    int (*CommDestroy)(Comm) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, Comm, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    bool ok = false;
+    std::string why;
+};
+Nccl &nccl() {
+    static Nccl n;
+    static bool tried = false;
+    if (tried) return n;
+    tried = true;
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) { n.why = std::string("cannot load libnccl: ") + dlerror(); return n; }
+    n.GetUniqueId = (int (*)(Nccl::UniqueId *))dlsym(h, "ncclGetUniqueId");
+    n.CommInitRank = (int (*)(Nccl::Comm *, int, Nccl::UniqueId, int))dlsym(h, "ncclCommInitRank");
+    n.CommDestroy = (int (*)(Nccl::Comm))dlsym(h, "ncclCommDestroy");
+    n.AllReduce = (int (*)(const void *, void *, size_t, int, int, Nccl::Comm, cudaStream_t))dlsym(h, "ncclAllReduce");
+    n.GetErrorString = (const char *(*)(int))dlsym(h, "ncclGetErrorString");
+    n.ok = n.GetUniqueId && n.CommInitRank && n.CommDestroy && n.AllReduce && n.GetErrorString;
+    if (!n.ok) n.why = "libnccl lacks an expected symbol";
+    return n;
+}
+constexpr int kNcclFloat64 = 8, kNcclSum = 0;       // ncclDataType_t / ncclRedOp_t values (nccl.h)
+}  // namespace
 extern "C" const char *msx_version(void) { return "moshi_b200 0.1 (sm_100a)"; }
 extern "C" int msx_device_count(void) {
     int n = 0;
@@ -62,6 +98,10 @@ struct msx_model {
     int device = 0;
     int num_sms = 148;
     int hidden = 0, dep_hidden = 0, dep_cap = 0, dep_nw = 0;
+    // tensor parallelism over the temporal transformer: this rank owns heads [h0, h1) and the
+    // hidden slice [f0, f1); everything else (embeddings, text head, depformer) is replicated
+    int tp_rank = 0, tp_world = 1;
+    int heads_local = 0, adim = 0, h0 = 0, f0 = 0, hidden_local = 0;
     std::vector<EmbTable> emb;        // [n_q+1]: text, audio 0..n_q-1
     EmbTable *d_emb = nullptr;        // device copy of `emb`
     EmbTable dep_text_emb;
@@ -172,6 +212,26 @@ struct Loader {
         linear_bytes = t->nbytes;
         return upload_linear(m, t->data, t->type, t->ne[0], t->ne[1], perm_half, out);
     }
+    // tensor-parallel shard of a linear: the listed row ranges (concatenated) x the K-slice [k0, k1) of every row
+    int linear_slice(const std::string &name, int64_t K, int64_t rows, const std::vector<std::pair<int64_t, int64_t>> &ranges,
+                     int64_t k0, int64_t k1, int perm_half, QLinear *out) {
+        const GgufTensor *t = need(name);
+        if (!t) return MSX_ERR_FORMAT;
+        if (t->ne[0] != K || t->ne[1] != rows) return fail(MSX_ERR_FORMAT, "shape mismatch for " + name);
+        if (t->type != T_Q4_K && t->type != T_Q8_0) return fail(MSX_ERR_FORMAT, name + ": tensor-parallel shards need q4_k or q8_0 weights");
+        const int64_t bw = t->type == T_Q4_K ? 256 : 32, bb = t->type == T_Q4_K ? 144 : 34;
+        if (k0 % bw || k1 % bw || k1 <= k0 || k1 > K) return fail(MSX_ERR_ARG, name + ": K-slice is not block aligned");
+        const int64_t rs = ggml_row_size(t->type, K), srs = (k1 - k0) / bw * bb;
+        int64_t n = 0;
+        for (auto &r : ranges) n += r.second - r.first;
+        std::vector<uint8_t> buf((size_t)n * srs);
+        int64_t i = 0;
+        for (auto &rg : ranges)
+            for (int64_t r = rg.first; r < rg.second; r++, i++)
+                memcpy(buf.data() + (size_t)i * srs, (const uint8_t *)t->data + (size_t)r * rs + (size_t)(k0 / bw) * bb, (size_t)srs);
+        linear_bytes = n * srs;
+        return upload_linear(m, buf.data(), t->type, k1 - k0, n, perm_half, out);
+    }
     int table(const std::string &name, int64_t K, int64_t rows, EmbTable *out) {
         const GgufTensor *t = need(name);
         if (!t) return MSX_ERR_FORMAT;
@@ -212,9 +272,18 @@ int check_config(const msx_config *c) {
 }  // namespace
 
 extern "C" int msx_model_load_gguf(const char *path, const msx_config *cfg, int device, msx_model **out) {
+    return msx_model_load_gguf_tp(path, cfg, device, 0, 1, out);
+}
+
+extern "C" int msx_model_load_gguf_tp(const char *path, const msx_config *cfg, int device, int tp_rank, int tp_world, msx_model **out) {
     if (!path || !out) return fail(MSX_ERR_ARG, "null argument");
     *out = nullptr;
     if (int e = check_config(cfg)) return e;
+    if (tp_world < 1 || tp_rank < 0 || tp_rank >= tp_world) return fail(MSX_ERR_ARG, "bad tensor-parallel rank / world");
+    if (tp_world > 1) {
+        if (cfg->num_heads % tp_world) return fail(MSX_ERR_ARG, "num_heads must be divisible by the tensor-parallel world size");
+        if (cfg->cross_attention) return fail(MSX_ERR_ARG, "tensor parallelism does not cover cross-attention layers");
+    }
     GgufFile f;
     std::string err;
     if (!f.open(path, err)) {
@@ -235,6 +304,9 @@ extern "C" int msx_model_load_gguf(const char *path, const msx_config *cfg, int 
     const msx_config &c = m->cfg;
     Loader L{m.get(), f};
     const int d = c.dim;
+    const int Dh = d / c.num_heads;
+    m->tp_rank = tp_rank; m->tp_world = tp_world;
+    m->heads_local = c.num_heads / tp_world; m->h0 = tp_rank * m->heads_local; m->adim = m->heads_local * Dh;
 
     // embeddings (lm.h:386-391)
     m->emb.resize(c.n_q + 1);
@@ -260,10 +332,19 @@ extern "C" int msx_model_load_gguf(const char *path, const msx_config *cfg, int 
         l.in_proj.resize(1); l.out_proj.resize(1); l.lin_in.resize(1); l.lin_out.resize(1);
         if (int e = L.vec_f32(p + "norm1.alpha", d, &l.norm1)) return e;
         if (int e = L.vec_f32(p + "norm2.alpha", d, &l.norm2)) return e;
-        if (int e = L.linear(p + "self_attn.in_projs.0.weight", d, 3 * d, &l.in_proj[0])) return e;
-        wb += L.linear_bytes;
-        if (int e = L.linear(p + "self_attn.out_projs.0.weight", d, d, &l.out_proj[0])) return e;
-        wb += L.linear_bytes;
+        if (tp_world == 1) {
+            if (int e = L.linear(p + "self_attn.in_projs.0.weight", d, 3 * d, &l.in_proj[0])) return e;
+            wb += L.linear_bytes;
+            if (int e = L.linear(p + "self_attn.out_projs.0.weight", d, d, &l.out_proj[0])) return e;
+            wb += L.linear_bytes;
+        } else {
+            // q | k | v rows of this rank's heads; out_proj columns of the same heads (partial sums, all-reduced)
+            const int64_t r0 = (int64_t)m->h0 * Dh, r1 = r0 + m->adim;
+            if (int e = L.linear_slice(p + "self_attn.in_projs.0.weight", d, 3 * d, {{r0, r1}, {d + r0, d + r1}, {2 * d + r0, 2 * d + r1}}, 0, d, 0, &l.in_proj[0])) return e;
+            wb += L.linear_bytes;
+            if (int e = L.linear_slice(p + "self_attn.out_projs.0.weight", d, d, {{0, d}}, r0, r1, 0, &l.out_proj[0])) return e;
+            wb += L.linear_bytes;
+        }
         if (c.cross_attention) {      // transformer.h:1053-1056; bias is optional (torch.h:62-68)
             if (int e = L.vec_f32(p + "norm_cross.weight", d, &l.norm_cross_w)) return e;
             if (f.find(p + "norm_cross.bias")) if (int e = L.vec_f32(p + "norm_cross.bias", d, &l.norm_cross_b)) return e;
@@ -275,12 +356,27 @@ extern "C" int msx_model_load_gguf(const char *path, const msx_config *cfg, int 
         const GgufTensor *t = L.need(p + "gating.linear_in.weight");
         if (!t) return MSX_ERR_FORMAT;
         const int F = (int)(t->ne[1] / 2);
-        if (i == 0) m->hidden = F;
+        if (i == 0) {
+            m->hidden = F;
+            // hidden slice of this rank, on super-block (256) boundaries when the width allows it, else on 32
+            const int unit = F % 256 == 0 ? 256 : 32, nu = F / unit;
+            m->f0 = (int)((long long)tp_rank * nu / tp_world) * unit;
+            m->hidden_local = (int)((long long)(tp_rank + 1) * nu / tp_world) * unit - m->f0;
+            if (m->hidden_local <= 0) return fail(MSX_ERR_ARG, "hidden size too small for this tensor-parallel world size");
+        }
         if (F != m->hidden || t->ne[1] != 2 * F) return fail(MSX_ERR_FORMAT, "inconsistent gating hidden size");
-        if (int e = L.linear(p + "gating.linear_in.weight", d, 2 * F, &l.lin_in[0], /*perm_half=*/F)) return e;
-        wb += L.linear_bytes;
-        if (int e = L.linear(p + "gating.linear_out.weight", F, d, &l.lin_out[0])) return e;
-        wb += L.linear_bytes;
+        if (tp_world == 1) {
+            if (int e = L.linear(p + "gating.linear_in.weight", d, 2 * F, &l.lin_in[0], /*perm_half=*/F)) return e;
+            wb += L.linear_bytes;
+            if (int e = L.linear(p + "gating.linear_out.weight", F, d, &l.lin_out[0])) return e;
+            wb += L.linear_bytes;
+        } else {
+            const int64_t a0 = m->f0, a1 = m->f0 + m->hidden_local;
+            if (int e = L.linear_slice(p + "gating.linear_in.weight", d, 2 * F, {{a0, a1}, {F + a0, F + a1}}, 0, d, m->hidden_local, &l.lin_in[0])) return e;
+            wb += L.linear_bytes;
+            if (int e = L.linear_slice(p + "gating.linear_out.weight", F, d, {{0, d}}, a0, a1, 0, &l.lin_out[0])) return e;
+            wb += L.linear_bytes;
+        }
     }
     if (int e = L.vec_f32("lm.out_norm.alpha", d, &m->out_norm)) return e;
     if (int e = L.linear("lm.text_linear.weight", d, c.text_card, &m->text_linear)) return e;
@@ -567,6 +663,9 @@ struct msx_stream {
     float *cnx = nullptr, *cq = nullptr, *cctx = nullptr;     // layer-norm output, cross q, cross context [dim]
     float *demux_l = nullptr, *demux_r = nullptr, *demux_y1 = nullptr, *demux_y2 = nullptr;   // [dim]
     float *dep_e = nullptr;          // [dep_dim] embedding of the previous token after its low-rank / demux projection
+    // tensor parallelism: double partial sums of out_proj / linear_out, all-reduced with NCCL inside the graph
+    double *tp_partial = nullptr;    // [dim]
+    void *nccl_comm = nullptr;
     int32_t *d_feed = nullptr;       // msx_run_resident_async
     cudaGraphExec_t g_temporal = nullptr, g_depformer = nullptr;
     int launches_temporal = 0, launches_depformer = 0;
@@ -590,6 +689,7 @@ struct msx_stream {
         if (m) cudaSetDevice(m->device);
         if (g_temporal) cudaGraphExecDestroy(g_temporal);
         if (g_depformer) cudaGraphExecDestroy(g_depformer);
+        if (nccl_comm) nccl().CommDestroy(nccl_comm);
         for (void *p : allocs) cudaFree(p);
         if (h_in) cudaFreeHost(h_in);
         if (h_out) cudaFreeHost(h_out);
@@ -610,15 +710,31 @@ int salloc(msx_stream *s, void **p, size_t bytes) {
     return 0;
 }
 
-size_t kv_elems(const msx_stream *s) { return (size_t)s->m->cfg.num_layers * s->cap * s->m->cfg.dim; }
+size_t kv_elems(const msx_stream *s) { return (size_t)s->m->cfg.num_layers * s->cap * s->m->adim; }
 size_t dkv_elems(const msx_stream *s) { return (size_t)s->m->cfg.dep_layers * s->m->dep_cap * s->m->cfg.dep_dim; }
 
 // one transformer layer (transformer.h:910-1039) as 5 launches
 void enqueue_layer(Launcher &L, const msx_stream *s, const LayerW &lw, int w, bool temporal, int layer, int pos_const) {
     const msx_model *m = s->m; const msx_config &c = m->cfg;
-    const int dim = temporal ? c.dim : c.dep_dim, heads = temporal ? c.num_heads : c.dep_heads;
+    const int dim = temporal ? c.dim : c.dep_dim;
+    // tensor parallelism shards the temporal layers only: this rank's heads / hidden slice (adim == dim for one rank)
+    const bool tp = temporal && m->tp_world > 1;
+    const int heads = temporal ? m->heads_local : c.dep_heads;
+    const int adim = temporal ? m->adim : c.dep_dim;
     const int cap = temporal ? s->cap : m->dep_cap;
     float *x = temporal ? s->x : s->dx, *qkv = temporal ? s->qkv : s->dqkv, *ctx = temporal ? s->ctx : s->dctx, *gate = temporal ? s->gate : s->dgate;
+    // out[dim] += W_shard . in : partial sums in double -> NCCL all-reduce (sum) -> rounded once into the residual stream
+    auto reduce_into_x = [&](GemvArgs &gg, int family) {
+        gg.out_f64 = s->tp_partial; gg.out = nullptr;
+        L.gemv(gg, PRO_PLAIN, EPI_STORE_F64, family);
+        L.fam = family; L.begin();
+        const int rc = nccl().AllReduce(s->tp_partial, s->tp_partial, (size_t)dim, kNcclFloat64, kNcclSum, s->nccl_comm, L.st);
+        if (rc != 0 && L.err == cudaSuccess) L.err = cudaErrorUnknown;
+        L.check();
+        L.fam = family; L.begin();
+        L.launch_pdl(tp_apply_kernel, dim3((dim + 255) / 256), dim3(256), 0, x, (const double *)s->tp_partial, dim);
+        L.check();
+    };
     GemvArgs g;
     g.ctrl = s->ctrl; g.eps = 1e-8f;
     // x -> rms_norm1 -> in_proj -> qkv
@@ -626,23 +742,24 @@ void enqueue_layer(Launcher &L, const msx_stream *s, const LayerW &lw, int w, bo
     L.gemv(g, PRO_RMS, EPI_STORE, temporal ? FAM_IN_PROJ : FAM_DEP_IN_PROJ);
     // rope + kv insert + attention
     AttnArgs a;
-    a.qkv = qkv; a.ctx = ctx; a.ctrl = s->ctrl; a.pos_const = pos_const; a.cap = cap; a.dim = dim;
+    a.qkv = qkv; a.ctx = ctx; a.ctrl = s->ctrl; a.pos_const = pos_const; a.cap = cap; a.dim = adim;
     a.max_period = temporal ? c.max_period : c.dep_max_period;
     a.rope_freq = temporal ? m->rope_freq : m->dep_rope_freq;
     a.rope_cs = (temporal && c.max_period) ? s->rope_cs : nullptr;
     { const char *e = getenv("MSX_ATTN_SMALL"); a.small_ctx = e ? atoi(e) : 32; }
-    const size_t lstride = (size_t)cap * dim;
+    const size_t lstride = (size_t)cap * adim;
     a.kc = (temporal ? s->kc : s->dkc) + (size_t)layer * lstride;
     a.vc = (temporal ? s->vc : s->dvc) + (size_t)layer * lstride;
     if (!temporal && cap <= 64) {
         // tiny ring: every CTA recomputes the attention of all heads in its prologue -> one launch
         g.w = lw.out_proj[w]; g.x = nullptr; g.alpha = nullptr; g.out = x;
-        L.gemv_local_attn(g, a, heads, dim / heads, PRO_PLAIN, EPI_RESID, FAM_DEP_OUT_PROJ);
+        L.gemv_local_attn(g, a, heads, adim / heads, PRO_PLAIN, EPI_RESID, FAM_DEP_OUT_PROJ);
     } else {
-        L.attn(a, heads, dim / heads, temporal ? s->attn_split : 1, temporal ? FAM_ATTN : FAM_DEP_ATTN);
+        L.attn(a, heads, adim / heads, temporal ? s->attn_split : 1, temporal ? FAM_ATTN : FAM_DEP_ATTN);
         // out_proj + residual
         g.w = lw.out_proj[w]; g.x = ctx; g.alpha = nullptr; g.out = x;
-        L.gemv(g, PRO_PLAIN, EPI_RESID, temporal ? FAM_OUT_PROJ : FAM_DEP_OUT_PROJ);
+        if (tp) reduce_into_x(g, FAM_OUT_PROJ);
+        else L.gemv(g, PRO_PLAIN, EPI_RESID, temporal ? FAM_OUT_PROJ : FAM_DEP_OUT_PROJ);
     }
     if (temporal && lw.cross_in.qs && s->kv_cross && s->tc > 0) {
         // x += cross_attention(layer_norm(x)) over the conditioning memory (transformer.h:936-943, 714-762)
@@ -660,7 +777,8 @@ void enqueue_layer(Launcher &L, const msx_stream *s, const LayerW &lw, int w, bo
     L.gemv(g, PRO_RMS, EPI_GATE, temporal ? FAM_LIN_IN : FAM_DEP_LIN_IN);
     // linear_out + residual
     g.w = lw.lin_out[w]; g.x = gate; g.alpha = nullptr; g.out = x;
-    L.gemv(g, PRO_PLAIN, EPI_RESID, temporal ? FAM_LIN_OUT : FAM_DEP_LIN_OUT);
+    if (tp) reduce_into_x(g, FAM_LIN_OUT);
+    else L.gemv(g, PRO_PLAIN, EPI_RESID, temporal ? FAM_LIN_OUT : FAM_DEP_LIN_OUT);
 }
 
 void enqueue_temporal(Launcher &L, const msx_stream *s) {
@@ -873,16 +991,39 @@ extern "C" int msx_stream_create(msx_model *m, int context_override, msx_stream 
     return msx_stream_create_ex(m, context_override, 0, out);
 }
 
+extern "C" int msx_tp_unique_id(uint8_t *out128) {
+    if (!out128) return fail(MSX_ERR_ARG, "null argument");
+    Nccl &n = nccl();
+    if (!n.ok) return fail(MSX_ERR_STATE, n.why);
+    Nccl::UniqueId id;
+    const int rc = n.GetUniqueId(&id);
+    if (rc != 0) return fail(MSX_ERR_CUDA, std::string("ncclGetUniqueId: ") + n.GetErrorString(rc));
+    memcpy(out128, id.internal, 128);
+    return 0;
+}
+
+static int stream_create_impl(msx_model *m, int context_override, int flags, const uint8_t *nccl_id, msx_stream **out);
+
 extern "C" int msx_stream_create_ex(msx_model *m, int context_override, int flags, msx_stream **out) {
+    return stream_create_impl(m, context_override, flags, nullptr, out);
+}
+// tensor-parallel stream: collective over the ranks of the model's tensor-parallel group (every rank calls it with the
+// same 128-byte id obtained from msx_tp_unique_id on one rank)
+extern "C" int msx_stream_create_tp(msx_model *m, int context_override, const uint8_t *nccl_id, msx_stream **out) {
+    return stream_create_impl(m, context_override, 0, nccl_id, out);
+}
+
+static int stream_create_impl(msx_model *m, int context_override, int flags, const uint8_t *nccl_id, msx_stream **out) {
     if (!m || !out) return fail(MSX_ERR_ARG, "null argument");
     *out = nullptr;
+    if (m->tp_world > 1 && !nccl_id) return fail(MSX_ERR_STATE, "tensor-parallel model: create its streams with msx_stream_create_tp");
     CU(cudaSetDevice(m->device));
     if (int e = set_smem_attrs()) return e;
     std::unique_ptr<msx_stream> s(new msx_stream);
     s->m = m; s->flags = flags;
     const msx_config &c = m->cfg;
     s->cap = context_override > 0 ? std::min(context_override, c.context) : c.context;
-    s->attn_split = attn_split_for(c.num_heads, s->cap, m->num_sms);
+    s->attn_split = attn_split_for(m->heads_local, s->cap, m->num_sms);
     CU(cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking));
     CU(cudaEventCreate(&s->ev0)); CU(cudaEventCreate(&s->ev1));
     CU(cudaMallocHost((void **)&s->h_in, kCtrlInBytes));
@@ -893,9 +1034,19 @@ extern "C" int msx_stream_create_ex(msx_model *m, int context_override, int flag
     if (int e = salloc(s.get(), (void **)&s->kc, kv_elems(s.get()) * 2)) return e;
     if (int e = salloc(s.get(), (void **)&s->vc, kv_elems(s.get()) * 2)) return e;
     if (int e = salloc(s.get(), (void **)&s->x, (size_t)c.dim * 4)) return e;
-    if (int e = salloc(s.get(), (void **)&s->qkv, (size_t)c.dim * 3 * 4)) return e;
-    if (int e = salloc(s.get(), (void **)&s->ctx, (size_t)c.dim * 4)) return e;
-    if (int e = salloc(s.get(), (void **)&s->gate, (size_t)m->hidden * 4)) return e;
+    if (int e = salloc(s.get(), (void **)&s->qkv, (size_t)m->adim * 3 * 4)) return e;
+    if (int e = salloc(s.get(), (void **)&s->ctx, (size_t)m->adim * 4)) return e;
+    if (int e = salloc(s.get(), (void **)&s->gate, (size_t)(m->tp_world > 1 ? m->hidden_local : m->hidden) * 4)) return e;
+    if (m->tp_world > 1) {
+        Nccl &n = nccl();
+        if (!n.ok) return fail(MSX_ERR_STATE, n.why);
+        if (int e = salloc(s.get(), (void **)&s->tp_partial, (size_t)c.dim * 8)) return e;
+        Nccl::UniqueId id;
+        memcpy(id.internal, nccl_id, 128);
+        const int rc = n.CommInitRank(&s->nccl_comm, m->tp_world, id, m->tp_rank);
+        if (rc != 0) { s->nccl_comm = nullptr; return fail(MSX_ERR_CUDA, std::string("ncclCommInitRank: ") + n.GetErrorString(rc)); }
+        flags &= ~MSX_STREAM_PERSISTENT_DEPFORMER;
+    }
     if (int e = salloc(s.get(), (void **)&s->tout, (size_t)c.dim * 4)) return e;
     if (int e = salloc(s.get(), (void **)&s->text_logits, (size_t)c.text_card * 4)) return e;
     if (int e = salloc(s.get(), (void **)&s->rope_cs, (size_t)(c.dim / c.num_heads) * 4)) return e;
@@ -1025,7 +1176,7 @@ extern "C" int msx_stream_offset(const msx_stream *s) { return s ? s->host_offse
 extern "C" int64_t msx_stream_kv_bytes_next(const msx_stream *s) {
     if (!s) return 0;
     const int n_valid = std::min(s->host_offset + 1, s->cap);
-    return (int64_t)n_valid * 2 * s->m->cfg.dim * 2 * s->m->cfg.num_layers;
+    return (int64_t)n_valid * 2 * s->m->adim * 2 * s->m->cfg.num_layers;      // this rank's share under tensor parallelism
 }
 extern "C" int msx_stream_launches_per_frame(const msx_stream *s) { return s ? s->launches_temporal + s->launches_depformer : 0; }
 

@@ -463,6 +463,7 @@ __device__ __forceinline__ void gemv_body(const GemvArgs &a, const float *x_over
         for (int r = 0; r < kR; r++) {
 #pragma unroll
             for (int o = LANES / 2; o > 0; o >>= 1) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], o);
+            if (EPI == EPI_STORE_F64 && l == 0 && cons.row0 + r < a.w.rows) a.out_f64[cons.row0 + r] = acc[r];
             accf[r] = (float)acc[r];
             acc[r] = 0.0;
         }
@@ -470,7 +471,7 @@ __device__ __forceinline__ void gemv_body(const GemvArgs &a, const float *x_over
             if (EPI == EPI_RESID) {                        // residual already in registers
 #pragma unroll
                 for (int r = 0; r < kR; r++) { const int row = cons.row0 + r; if (row < a.w.rows) a.out[row] = resid[r] + accf[r]; }
-            } else gemv_epilogue<kR>(a, EPI, cons.row0, accf, emb_token, best);
+            } else if (EPI != EPI_STORE_F64) gemv_epilogue<kR>(a, EPI, cons.row0, accf, emb_token, best);
         }
         if (progress && lane == 0) atomicAdd(progress, tile_bytes);
     };

@@ -89,6 +89,14 @@ __device__ __forceinline__ void finalize_depformer_body(Ctrl *c, int dep_q) {
 }
 __global__ void finalize_depformer_kernel(Ctrl *c, int dep_q) { griddep_launch(); griddep_wait(); finalize_depformer_body(c + blockIdx.x, dep_q); }
 
+// ---- tensor parallelism: residual += all-reduced double partial sums, rounded once (== the single-GPU fp64 accumulate) ---
+__global__ void tp_apply_kernel(float *x, const double *partial, int n) {
+    griddep_launch();
+    griddep_wait();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[i] = __ldcg(x + i) + (float)__ldcg(partial + i);
+}
+
 // ---- load-time repack (GGUF row-major blocks -> device tiles, see common.cuh QLinear) --------------
 // perm_half > 0 interleaves rows for the gated MLP: stored row v <- source row (v&1 ? perm_half + v/2 : v/2)
 __device__ __forceinline__ int src_row_of(int v, int perm_half) { return perm_half > 0 ? ((v & 1) ? perm_half + (v >> 1) : (v >> 1)) : v; }
