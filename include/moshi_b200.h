@@ -100,6 +100,8 @@ MSX_API int msx_step_temporal(msx_stream *s, const int32_t *tokens, int32_t *tex
 /* Depformer chain for the frame (lm.h:478-553): dep_q serial codebook steps on the device.
  * force (host, [dep_q]) optionally replaces the token fed to step k+1 (MSX_NO_TOKEN / NULL = greedy).
  * audio_logits (host, [dep_q][card]) may be NULL. */
+/* PersonaPlex voice-embedding prompt (lm.h:694-709): the temporal step with the embedding sum replaced by x[dim] */
+MSX_API int msx_step_temporal_embedding(msx_stream *s, const float *x, int32_t *text_token, float *text_logits, float *transformer_out);
 MSX_API int msx_step_depformer(msx_stream *s, int32_t text_token, const int32_t *force,
                                int32_t *audio_tokens, float *audio_logits);
 /* Fused frame: temporal -> greedy text -> depformer with a single host synchronisation.
@@ -171,6 +173,12 @@ MSX_API int msx_gen_create_with_callback(const msx_config *cfg, int delay_steps,
 MSX_API void msx_gen_free(msx_gen *g);
 /* srand() for the Exp(1) draws of sampled generation (the reference never seeds except in --bench: srand(0)) */
 MSX_API void msx_gen_seed(msx_gen *g, unsigned seed);
+/* PersonaPlex voice prompt, embedding variant (moshi_lmgen_step_voice_prompt, lm.h:1005-1050): replay one embedding
+ * row (text forced to 3, depformer run, offset++); afterwards install the voice's token ring, cache[CT][n_q+1] with
+ * CT = msx_gen_cache_rows() */
+MSX_API int msx_gen_prompt_embedding(msx_gen *g, const float *row);
+MSX_API int msx_gen_set_cache(msx_gen *g, const int32_t *cache);
+MSX_API int msx_gen_cache_rows(const msx_gen *g);
 /* TTS hooks of the generator.  text hook: called between the temporal and the depformer graph with the sampled text
  * token, returns the token to use instead (state machine / text prefix, lm.h:877-899).  audio hook: may overwrite the
  * dep_q audio tokens of this frame (audio prefix, lm.h:922-931); returns the number of following frames whose output

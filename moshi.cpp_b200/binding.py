@@ -106,6 +106,10 @@ def lib():
     L.msx_stream_kv_bytes_next.restype = C.c_int64; L.msx_stream_kv_bytes_next.argtypes = [vp]
     L.msx_step_temporal.argtypes = [vp, vp, i32p, vp, vp]
     L.msx_step_depformer.argtypes = [vp, C.c_int32, vp, vp, vp]
+    L.msx_step_temporal_embedding.argtypes = [vp, vp, i32p, vp, vp]
+    L.msx_gen_prompt_embedding.argtypes = [vp, vp]
+    L.msx_gen_set_cache.argtypes = [vp, vp]
+    L.msx_gen_cache_rows.argtypes = [vp]
     L.msx_step.argtypes = [vp, vp, vp]
     L.msx_vad.argtypes = [vp, C.POINTER(C.c_float)]
     L.msx_stream_set_condition.argtypes = [vp, vp, vp, C.c_int]
@@ -249,6 +253,16 @@ class Stream:
         logits = np.empty(cfg["text_card"], dtype=np.float32) if want_logits else None
         tout = np.empty(cfg["dim"], dtype=np.float32) if want_logits else None
         _check(lib().msx_step_temporal(self.h, _p(tok), C.byref(t), _p(logits), _p(tout)))
+        return int(t.value), logits, tout
+
+    def step_temporal_embedding(self, x, want_logits=True):
+        cfg = self.model.cfg
+        xx = np.ascontiguousarray(x, dtype=np.float32)
+        assert xx.size == cfg["dim"]
+        t = C.c_int32(0)
+        logits = np.empty(cfg["text_card"], dtype=np.float32) if want_logits else None
+        tout = np.empty(cfg["dim"], dtype=np.float32) if want_logits else None
+        _check(lib().msx_step_temporal_embedding(self.h, _p(xx), C.byref(t), _p(logits), _p(tout)))
         return int(t.value), logits, tout
 
     def step_depformer(self, text_token: int, force=None, want_logits=True):

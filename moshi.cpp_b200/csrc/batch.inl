@@ -191,6 +191,7 @@ int push_inputs_b(msx_batch *b, const int32_t *tokens) {
         h[0] = INT32_MIN;
         if (tokens) for (int i = 0; i < c.n_q + 1; i++) h[1 + i] = tokens[(size_t)s * (c.n_q + 1) + i];
         for (int i = 0; i < 40; i++) h[41 + i] = INT32_MIN;
+        h[81] = h[82] = h[83] = 0;
     }
     CU(cudaMemcpy2DAsync(reinterpret_cast<uint8_t *>(b->ctrl) + kCtrlInOffset, sizeof(Ctrl), b->h_in, kCtrlInBytes, kCtrlInBytes, b->n,
                          cudaMemcpyHostToDevice, b->st));

@@ -25,7 +25,8 @@ struct Ctrl {
     int32_t text_override;          // INT32_MIN = use greedy text token
     int32_t tokens[40];             // inputs of this frame
     int32_t force[40];              // depformer feed-forward overrides (INT32_MIN = greedy)
-    int32_t pad0_[3];
+    int32_t embed_override;         // != 0: the embedding sum is replaced by the stream's embed_in row (voice-embedding prompt)
+    int32_t pad0_[2];
     // ---- device-written output block: one D2H copy per call ----
     int32_t out_tokens[41];         // {text, audio[dep_q]}
     int32_t pad1_[3];

@@ -504,10 +504,16 @@ const char *kFamilyNames[FAM_COUNT] = {
     "dep_in", "dep_in_proj", "dep_attn", "dep_out_proj", "dep_linear_in", "dep_linear_out", "dep_head", "dep_finalize",
     "depformer_persistent"};
 
+int tiles_of(msx_model *m, const QLinear &w, QTiles *out);     // batch.inl
+int ensure_all_tiles(msx_model *m);
+
 struct Launcher {
     cudaStream_t st;
     int num_sms;
     int count = 0;
+    // Q4_K linears through the tensor-core unit kernel (gemm1_q4k_kernel) when the model carries the units layout
+    msx_model *model = nullptr;
+    bool mma = false;
     cudaError_t err = cudaSuccess;
     // optional per-launch timing (eager mode only): events[i], events[i+1] bracket launch i
     std::vector<cudaEvent_t> *events = nullptr;
@@ -539,6 +545,16 @@ struct Launcher {
 
     void gemv(const GemvArgs &a, int pro, int epi, int family = 0) {
         fam = family; begin();
+        if (mma && model && a.w.type == T_Q4_K) {
+            auto it = model->tiles.find(a.w.qs);
+            if (it != model->tiles.end() && a.w.rows == it->second.rows) {
+                const QTiles &wt = it->second;
+                const int S = gemm1_stages_for(wt.K);
+                launch_pdl(gemm1_q4k_kernel, dim3(gemm_grid_for(wt.n_tiles, num_sms)), dim3(kGemmThreads), (size_t)gemm1_smem_bytes(wt.K, S), a, wt, pro, epi, S);
+                check();
+                return;
+            }
+        }
         const int tr = tile_rows(a.w.gs);
         const int n_tiles = (a.w.rows + tr - 1) / tr;
         const int grid = std::max(1, std::min(num_sms, (n_tiles + 7) / 8));
@@ -662,10 +678,13 @@ struct msx_stream {
     int tc = 0;
     float *cnx = nullptr, *cq = nullptr, *cctx = nullptr;     // layer-norm output, cross q, cross context [dim]
     float *demux_l = nullptr, *demux_r = nullptr, *demux_y1 = nullptr, *demux_y2 = nullptr;   // [dim]
+    float *embed_in = nullptr;       // [dim] voice-embedding prompt row (msx_step_temporal_embedding)
     float *dep_e = nullptr;          // [dep_dim] embedding of the previous token after its low-rank / demux projection
     // tensor parallelism: double partial sums of out_proj / linear_out, all-reduced with NCCL inside the graph
     double *tp_partial = nullptr;    // [dim]
     void *nccl_comm = nullptr;
+    bool embed_override_next = false;
+    bool use_mma = false;            // Q4_K linears on the tensor-core unit kernel (MSX_MMA=1)
     int32_t *d_feed = nullptr;       // msx_run_resident_async
     cudaGraphExec_t g_temporal = nullptr, g_depformer = nullptr;
     int launches_temporal = 0, launches_depformer = 0;
@@ -801,6 +820,7 @@ void enqueue_temporal(Launcher &L, const msx_stream *s) {
         e.text_pre1 = s->demux_y1; e.text_pre2 = s->demux_y2; e.num_embeddings = c.text_card + 1;
     }
     e.cond_sum = s->cond_sum;
+    e.embed_in = s->embed_in;
     L.fam = FAM_EMBED; L.begin();
     L.launch_pdl(embed_kernel, dim3((c.dim + kThreads - 1) / kThreads), dim3(kThreads), 0, e);
     L.check();
@@ -947,6 +967,7 @@ void enqueue_depformer_mega(Launcher &L, const msx_stream *s) {
 template <typename F>
 int capture(msx_stream *s, F &&body, cudaGraphExec_t *exec, int *launches) {
     Launcher L{s->st, s->m->num_sms};
+    L.model = s->m; L.mma = s->use_mma;
     CU(cudaStreamBeginCapture(s->st, cudaStreamCaptureModeThreadLocal));
     body(L);
     cudaGraph_t graph = nullptr;
@@ -975,6 +996,7 @@ int set_smem_attrs() {
     CU(cudaFuncSetAttribute(gemv_local_attn_kernel<8, 16, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CU(cudaFuncSetAttribute(gemv_local_attn_kernel<8, 16, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CU(cudaFuncSetAttribute(mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU(cudaFuncSetAttribute(gemm1_q4k_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemMax));
     // all kernels stay below the 48 KB default except long-context attention with split 1
     CU(cudaFuncSetAttribute(attn_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     CU(cudaFuncSetAttribute(attn_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
@@ -1024,6 +1046,11 @@ static int stream_create_impl(msx_model *m, int context_override, int flags, con
     const msx_config &c = m->cfg;
     s->cap = context_override > 0 ? std::min(context_override, c.context) : c.context;
     s->attn_split = attn_split_for(m->heads_local, s->cap, m->num_sms);
+    { const char *e = getenv("MSX_MMA"); s->use_mma = e && atoi(e) != 0; }
+    if (s->use_mma) {
+        bool all_q4k = m->text_linear.type == T_Q4_K;
+        if (all_q4k) { if (int e = ensure_all_tiles(m)) return e; } else s->use_mma = false;
+    }
     CU(cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking));
     CU(cudaEventCreate(&s->ev0)); CU(cudaEventCreate(&s->ev1));
     CU(cudaMallocHost((void **)&s->h_in, kCtrlInBytes));
@@ -1050,6 +1077,7 @@ static int stream_create_impl(msx_model *m, int context_override, int flags, con
     if (int e = salloc(s.get(), (void **)&s->tout, (size_t)c.dim * 4)) return e;
     if (int e = salloc(s.get(), (void **)&s->text_logits, (size_t)c.text_card * 4)) return e;
     if (int e = salloc(s.get(), (void **)&s->rope_cs, (size_t)(c.dim / c.num_heads) * 4)) return e;
+    if (int e = salloc(s.get(), (void **)&s->embed_in, (size_t)c.dim * 4)) return e;
     if (c.dep_q > 0) {
         if (int e = salloc(s.get(), (void **)&s->dkc, dkv_elems(s.get()) * 2)) return e;
         if (int e = salloc(s.get(), (void **)&s->dvc, dkv_elems(s.get()) * 2)) return e;
@@ -1188,6 +1216,8 @@ int push_inputs(msx_stream *s, const int32_t *tokens, int32_t text_override, con
     h[0] = text_override;
     if (tokens) for (int i = 0; i < c.n_q + 1; i++) h[1 + i] = tokens[i];
     for (int i = 0; i < 40; i++) h[41 + i] = (force && i < c.dep_q) ? force[i] : INT32_MIN;
+    h[81] = s->embed_override_next ? 1 : 0;
+    s->embed_override_next = false;
     CU(cudaMemcpyAsync(reinterpret_cast<uint8_t *>(s->ctrl) + kCtrlInOffset, h, kCtrlInBytes, cudaMemcpyHostToDevice, s->st));
     return 0;
 }
@@ -1207,6 +1237,23 @@ extern "C" int msx_step_temporal(msx_stream *s, const int32_t *tokens, int32_t *
     const msx_config &c = s->m->cfg;
     CU(cudaSetDevice(s->m->device));
     if (int e = push_inputs(s, tokens, INT32_MIN, nullptr)) return e;
+    CU(cudaGraphLaunch(s->g_temporal, s->st));
+    s->host_offset++;
+    if (int e = pull_outputs(s)) return e;
+    if (text_token) *text_token = s->h_out[0];
+    if (text_logits) CU(cudaMemcpy(text_logits, s->text_logits, (size_t)c.text_card * 4, cudaMemcpyDeviceToHost));
+    if (transformer_out) CU(cudaMemcpy(transformer_out, s->tout, (size_t)c.dim * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// PersonaPlex voice-embedding prompt (lm.h:694-709, 1005-1036): the temporal step on a given f32 embedding row
+extern "C" int msx_step_temporal_embedding(msx_stream *s, const float *x, int32_t *text_token, float *text_logits, float *transformer_out) {
+    if (!s || !x) return fail(MSX_ERR_ARG, "null argument");
+    const msx_config &c = s->m->cfg;
+    CU(cudaSetDevice(s->m->device));
+    CU(cudaMemcpyAsync(s->embed_in, x, (size_t)c.dim * 4, cudaMemcpyHostToDevice, s->st));
+    s->embed_override_next = true;
+    if (int e = push_inputs(s, nullptr, INT32_MIN, nullptr)) return e;
     CU(cudaGraphLaunch(s->g_temporal, s->st));
     s->host_offset++;
     if (int e = pull_outputs(s)) return e;
@@ -1348,6 +1395,7 @@ extern "C" int msx_profile_frame(msx_stream *s, const int32_t *tokens, int32_t *
     std::vector<cudaEvent_t> ev;
     std::vector<int> fam;
     Launcher L{s->st, s->m->num_sms};
+    L.model = s->m; L.mma = s->use_mma;
     L.events = &ev; L.families = &fam;
     enqueue_temporal(L, s);
     s->host_offset++;
@@ -1561,6 +1609,24 @@ extern "C" void msx_gen_seed(msx_gen *, unsigned seed) { srand(seed); }
 extern "C" int msx_gen_offset(const msx_gen *g) { return g ? g->offset : -1; }
 extern "C" int msx_gen_max_delay(const msx_gen *g) { return g ? g->max_delay : -1; }
 
+// moshi_lmgen_step_voice_prompt, embedding variant (lm.h:1005-1050): one prompt frame = temporal step on the row,
+// text token forced to 3, depformer step (its tokens are dropped), offset++
+extern "C" int msx_gen_prompt_embedding(msx_gen *g, const float *row) {
+    if (!g || !row || !g->s) return fail(MSX_ERR_ARG, "null argument / callback generator");
+    int32_t text = 0, audio[MSX_MAX_STEPS];
+    if (int e = msx_step_temporal_embedding(g->s, row, &text, nullptr, nullptr)) return e;
+    if (g->cfg.dep_q > 0) if (int e = msx_step_depformer(g->s, 3, nullptr, audio, nullptr)) return e;
+    g->offset++;
+    return 0;
+}
+// the token delay ring as stored with the voice ("voice.cache"): cache[CT][n_q+1] row-major here
+extern "C" int msx_gen_set_cache(msx_gen *g, const int32_t *cache) {
+    if (!g || !cache) return fail(MSX_ERR_ARG, "null argument");
+    for (size_t i = 0; i < g->cache.size(); i++) g->cache[i] = cache[i];
+    return 0;
+}
+extern "C" int msx_gen_cache_rows(const msx_gen *g) { return g ? g->CT : -1; }
+
 extern "C" int msx_gen_set_text_hook(msx_gen *g, msx_text_hook fn, void *user) {
     if (!g) return fail(MSX_ERR_ARG, "null generator");
     g->text_hook = fn; g->text_user = user;
@@ -1682,6 +1748,7 @@ extern "C" int msx_test_gemv(int device, int type, const void *w, int64_t k, int
         CU(cudaMemcpy(da, alpha, (size_t)k * 4, cudaMemcpyHostToDevice));
     }
     Launcher L{nullptr, m->num_sms};
+    if (type == T_Q4_K) { const char *e = getenv("MSX_MMA"); if (e && atoi(e)) { QTiles qt; if (int er = tiles_of(m.get(), ql, &qt)) return er; L.model = m.get(); L.mma = true; } }
     GemvArgs g;
     g.w = ql; g.x = dx; g.alpha = da; g.eps = 1e-8f; g.out = dy;
     L.gemv(g, prologue == PRO_RMS ? PRO_RMS : PRO_PLAIN, EPI_STORE);
@@ -1701,6 +1768,9 @@ extern "C" int msx_bench_gemv(int device, int type, const void *w, int64_t k, in
     std::vector<QLinear> mats(n_mats);
     for (int i = 0; i < n_mats; i++)
         if (int e = upload_linear(m.get(), w, type, k, rows, epilogue == EPI_GATE ? (int)(rows / 2) : 0, &mats[i])) return e;
+    bool bench_mma = false;
+    if (type == T_Q4_K) { const char *e = getenv("MSX_MMA"); bench_mma = e && atoi(e); }
+    if (bench_mma) for (int i = 0; i < n_mats; i++) { QTiles qt; if (int e = tiles_of(m.get(), mats[i], &qt)) return e; }
     float *dx = nullptr, *dy = nullptr, *da = nullptr;
     if (int e = dev_alloc(m.get(), (void **)&dx, (size_t)k * 4)) return e;
     if (int e = dev_alloc(m.get(), (void **)&dy, (size_t)std::max<int64_t>(rows, k) * 4)) return e;
@@ -1713,6 +1783,7 @@ extern "C" int msx_bench_gemv(int device, int type, const void *w, int64_t k, in
     cudaStream_t st;
     CU(cudaStreamCreate(&st));
     Launcher L{st, m->num_sms};
+    L.model = m.get(); L.mma = bench_mma;
     cudaEvent_t e0, e1;
     CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
     unsigned long long *dkey = nullptr;

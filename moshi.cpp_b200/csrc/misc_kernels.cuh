@@ -22,6 +22,7 @@ struct EmbedArgs {
     const float *text_pre1 = nullptr, *text_pre2 = nullptr;
     int32_t num_embeddings = 0;
     const float *cond_sum = nullptr;
+    const float *embed_in = nullptr;    // [dim]: used instead of the embedding sum when ctrl->embed_override (lm.h:694-709)
 };
 
 // `b` = stream of a batch (batched steps launch grid.y = streams; per-stream buffers are b * dim / b * dh apart)
@@ -35,6 +36,10 @@ __device__ __forceinline__ void embed_body(const EmbedArgs &a0, int cta, int n_c
         const float arg = (float)c->offset * a.rope_freq[threadIdx.x];
         a.rope_cs[threadIdx.x] = (float)cos((double)arg);
         a.rope_cs[a.dh / 2 + threadIdx.x] = (float)sin((double)arg);
+    }
+    if (a.embed_in && c->embed_override) {
+        for (int i = cta * nthr + threadIdx.x; i < a.dim; i += n_cta * nthr) a.x[i] = __ldcg(a.embed_in + i);
+        return;
     }
     for (int i = cta * nthr + threadIdx.x; i < a.dim; i += n_cta * nthr) {
         float acc = 0.f;

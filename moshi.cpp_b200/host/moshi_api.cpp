@@ -269,6 +269,8 @@ struct moshi_lm_gen_t {
     std::vector<int32_t> audio_tokens;                         // moshi_lm_send2 -> next receive
     std::deque<std::vector<int16_t>> prompt_audio;             // personaplex voice prompt (codes)
     std::vector<int> text_prompt_tokens;                       // personaplex system prompt
+    std::vector<float> prompt_embeddings; int prompt_rows = 0;  // personaplex voice prompt (embedding variant)
+    std::vector<int32_t> prompt_cache; int prompt_cache_rows = 0;
     // TTS (voice_t + machine of the reference's moshi_lm_gen_t, moshi.cpp:586-606)
     bool has_voice = false;
     std::vector<float> cond_sum, cond_cross; int tc = 0;
@@ -328,6 +330,15 @@ int moshi_lm_personaplex_audio_prompt(moshi_lm_gen_t *gen, std::deque<std::vecto
     gen->prompt_audio.swap(audio_prompt);                      // the reference swaps (steals) the caller's deque (moshi.cpp:782)
     return 0;
 }
+int moshi_lm_personaplex_voice_tensors(moshi_lm_gen_t *gen, const float *embeddings, int n_rows, const int32_t *cache, int cache_rows) {
+    if (!gen || !embeddings || n_rows <= 0 || !cache) return -1;
+    const msx_config &c = gen->lm->cfg;
+    gen->prompt_embeddings.assign(embeddings, embeddings + (size_t)n_rows * c.dim);
+    gen->prompt_rows = n_rows;
+    gen->prompt_cache.assign(cache, cache + (size_t)cache_rows * (c.n_q + 1));
+    gen->prompt_cache_rows = cache_rows;
+    return 0;
+}
 int moshi_lm_personaplex_system_prompt_tokens(moshi_lm_gen_t *gen, const std::vector<int> &text_tokens) {
     gen->text_prompt_tokens = text_tokens;
     return 0;
@@ -341,6 +352,10 @@ static void personaplex_prompts(moshi_lm_gen_t *gen) {
     if (ncb != 17) return;                                     // the reference's table has 17 entries
     int32_t row[MSX_MAX_CODEBOOKS], text, audio[MSX_MAX_STEPS];
     auto step = [&]() { msx_gen_step(gen->gen, row, ncb, 0, &text, audio); };
+    if (gen->prompt_rows > 0) {                                // embedding variant (lm.h:1005-1051)
+        for (int i = 0; i < gen->prompt_rows; i++) msx_gen_prompt_embedding(gen->gen, gen->prompt_embeddings.data() + (size_t)i * c.dim);
+        if (gen->prompt_cache_rows == msx_gen_cache_rows(gen->gen)) msx_gen_set_cache(gen->gen, gen->prompt_cache.data());
+    } else
     while (!gen->prompt_audio.empty()) {                       // voice prompt: codes of the 8 moshi codebooks
         for (int i = 0; i < ncb; i++) row[i] = PROMPT_TOKENS[i];
         const auto &codes = gen->prompt_audio.front();

@@ -704,14 +704,8 @@ void orc_state_set_noise(orc_state *s, const float *noise_text, const float *noi
 
 static int argmax_first(const float *v, int n) { int bi = 0; float bv = v[0]; for (int i = 1; i < n; i++) if (v[i] > bv) { bv = v[i]; bi = i; } return bi; }
 
-int orc_step_temporal(orc_model *m, orc_state *s, const int32_t *tokens, float *text_logits, float *transformer_out) {
+static int temporal_from_x(orc_model *m, orc_state *s, float *x, float *text_logits, float *transformer_out) {
     const orc_config *c = &m->cfg; const int dim = c->dim;
-    float *x = malloc(sizeof(float) * dim), *row = malloc(sizeof(float) * dim);
-    /* lm.h:555-584: text emb first, then audio codebooks added left to right */
-    if (c->demux_second_stream) embed_demux(m, &m->text_emb, &m->text_out1, &m->text_out2, c->text_card + 1, tokens[0], x);
-    else embed_row(&m->text_emb, tokens[0], x);
-    for (int q = 0; q < c->n_q; q++) { embed_row(&m->emb[q], tokens[q + 1], row); for (int i = 0; i < dim; i++) x[i] = x[i] + row[i]; }
-    if (s->cond_sum) for (int i = 0; i < dim; i++) x[i] = s->cond_sum[i] + x[i];      /* lm.h:575-577 */
     const int pos = s->offset; s->offset += 1;          /* transformer.h:1269-1270 */
     const size_t lstride = (size_t)c->context * dim;
     for (int l = 0; l < c->num_layers; l++)
@@ -725,7 +719,27 @@ int orc_step_temporal(orc_model *m, orc_state *s, const int32_t *tokens, float *
                                                    : argmax_first(logits, (int)m->text_linear.ne1);
     if (transformer_out) memcpy(transformer_out, s->transformer_out, sizeof(float) * dim);
     if (!text_logits) free(logits);
+    return tok;
+}
+
+int orc_step_temporal(orc_model *m, orc_state *s, const int32_t *tokens, float *text_logits, float *transformer_out) {
+    const orc_config *c = &m->cfg; const int dim = c->dim;
+    float *x = malloc(sizeof(float) * dim), *row = malloc(sizeof(float) * dim);
+    /* lm.h:555-584: text emb first, then audio codebooks added left to right */
+    if (c->demux_second_stream) embed_demux(m, &m->text_emb, &m->text_out1, &m->text_out2, c->text_card + 1, tokens[0], x);
+    else embed_row(&m->text_emb, tokens[0], x);
+    for (int q = 0; q < c->n_q; q++) { embed_row(&m->emb[q], tokens[q + 1], row); for (int i = 0; i < dim; i++) x[i] = x[i] + row[i]; }
+    if (s->cond_sum) for (int i = 0; i < dim; i++) x[i] = s->cond_sum[i] + x[i];      /* lm.h:575-577 */
+    const int tok = temporal_from_x(m, s, x, text_logits, transformer_out);
     free(x); free(row);
+    return tok;
+}
+
+int orc_step_temporal_embedding(orc_model *m, orc_state *s, const float *xin, float *text_logits, float *transformer_out) {
+    float *x = malloc(sizeof(float) * m->cfg.dim);
+    memcpy(x, xin, sizeof(float) * m->cfg.dim);
+    const int tok = temporal_from_x(m, s, x, text_logits, transformer_out);
+    free(x);
     return tok;
 }
 

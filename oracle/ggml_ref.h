@@ -81,6 +81,9 @@ int orc_state_offset(orc_state *s);
 /* one temporal step (lm.h:659-690 + transformer.h:1217-1289): tokens[n_q+1] -> logits, token */
 int orc_step_temporal(orc_model *m, orc_state *s, const int32_t *tokens,
                       float *text_logits /*[text_card] or NULL*/, float *transformer_out /*[dim] or NULL*/);
+/* PersonaPlex voice-embedding prompt (lm.h:694-709, 1005-1036): the same step with the embedding sum REPLACED by a given
+ * f32 row x[dim] (no tokens, no condition_sum) */
+int orc_step_temporal_embedding(orc_model *m, orc_state *s, const float *x, float *text_logits, float *transformer_out);
 /* depformer chain (lm.h:446-553); force[k] >= 0 replaces the greedy choice that feeds step k+1 */
 void orc_step_depformer(orc_model *m, orc_state *s, int text_token, const int32_t *force /*[dep_q] or NULL*/,
                         int32_t *audio_tokens /*[dep_q]*/, float *audio_logits /*[dep_q][card] or NULL*/);

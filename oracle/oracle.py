@@ -67,6 +67,7 @@ def lib():
         L.orc_state_offset.restype = C.c_int; L.orc_state_offset.argtypes = [vp]
         L.orc_step_temporal.restype = C.c_int; L.orc_step_temporal.argtypes = [vp, vp, vp, vp, vp]
         L.orc_step_depformer.argtypes = [vp, vp, C.c_int, vp, vp, vp]
+        L.orc_step_temporal_embedding.restype = C.c_int; L.orc_step_temporal_embedding.argtypes = [vp, vp, vp, vp, vp]
         L.orc_vad.restype = C.c_float; L.orc_vad.argtypes = [vp, vp]
         L.orc_state_set_condition.argtypes = [vp, vp, vp, C.c_int]
         L.orc_state_set_sampling.argtypes = [vp, C.c_float, C.c_float, C.c_int, C.c_int]
@@ -211,6 +212,15 @@ class State:
         logits = np.empty(cfg["text_card"], dtype=np.float32)
         tout = np.empty(cfg["dim"], dtype=np.float32)
         t = lib().orc_step_temporal(self.model.h, self.h, _p(tok), _p(logits), _p(tout))
+        return t, logits, tout
+
+    def step_temporal_embedding(self, x):
+        cfg = self.model.cfg
+        xx = np.ascontiguousarray(x, dtype=np.float32)
+        assert xx.size == cfg["dim"]
+        logits = np.empty(cfg["text_card"], dtype=np.float32)
+        tout = np.empty(cfg["dim"], dtype=np.float32)
+        t = lib().orc_step_temporal_embedding(self.model.h, self.h, _p(xx), _p(logits), _p(tout))
         return t, logits, tout
 
     def step_depformer(self, text_token: int, force=None):

@@ -489,3 +489,29 @@ def test_condition_changes_output_and_can_be_replaced(msx, orc, gguf_for):
     s2 = msx.Stream(msx.Model(path2, cfg2))
     with pytest.raises(msx.MsxError):
         s2.set_condition(None, np.zeros((2, cfg2["dim"]), dtype=np.float32))
+
+
+def test_voice_embedding_prompt_matches_oracle(msx, orc, gguf_for):
+    """PersonaPlex voice-embedding prompt (lm.h:694-709, 1005-1036): f32 rows fed straight into the
+    temporal transformer, text forced to 3, depformer run; then normal token frames continue on the same KV state"""
+    path, cfg = gguf_for("tiny_pplex", "q4_k")
+    gm = msx.Model(path, cfg); gs = msx.Stream(gm)
+    om = orc.Model(path, cfg); os_ = orc.State(om)
+    rng = np.random.default_rng(21)
+    for f in range(5):
+        row = (0.5 * rng.standard_normal(cfg["dim"])).astype(np.float32)
+        t_ref, lg_ref, to_ref = os_.step_temporal_embedding(row)
+        t_gpu, lg_gpu, to_gpu = gs.step_temporal_embedding(row)
+        assert max_rel(lg_gpu, lg_ref) < LOGIT_TOL and max_rel(to_gpu, to_ref) < LOGIT_TOL, f"prompt frame {f}"
+        assert_bitwise_mostly(lg_gpu, lg_ref, f"prompt frame {f}")
+        a_ref, al_ref = os_.step_depformer(3)
+        a_gpu, al_gpu = gs.step_depformer(3, force=a_ref)
+        assert max_rel(al_gpu, al_ref) < LOGIT_TOL
+    toks = np.array([cfg["text_card"]] + [cfg["card"]] * cfg["n_q"], dtype=np.int32)
+    for f in range(6):                                    # token frames attend to the prompt's KV rows
+        t_ref, lg_ref, _ = os_.step_temporal(toks); t_gpu, lg_gpu, _ = gs.step_temporal(toks)
+        assert max_rel(lg_gpu, lg_ref) < LOGIT_TOL and t_gpu == t_ref, f"frame {f}"
+        a_ref, _ = os_.step_depformer(t_ref); a_gpu, _ = gs.step_depformer(t_ref, force=a_ref)
+        assert np.array_equal(a_gpu, a_ref)
+        toks = np.concatenate([[t_ref], a_ref, rng.integers(0, cfg["card"], size=cfg["n_q"] - cfg["dep_q"])]).astype(np.int32)
+    assert gs.offset == 11 and os_.offset == 11
