@@ -247,7 +247,10 @@ def main():
         replay_gbs = dom_bytes / (us.value * 1e-6) / 1e9
     roofline = {"bound": "hbm", "kernel": "gemv_kernel<Q4_K,32> gating.linear_in (rms_norm + q8_K quant + dequant-GEMV + silu gate)",
                 "achieved": achieved, "peak": peaks["hbm_gbs"], "peak_source": f"{peak_src} copy bandwidth (MEASURED_PEAKS.json)",
-                "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": None,
+                "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel / shape from the committed ncu --set full capture
+                # (profiles/r1d_linear_in_ncu_summary.md: 53.44 MB read = the stored 148 B / 256 weights, no re-reads)
+                "traffic": 53_440_000 if (args.quant == "q4_k" and args.preset.startswith(("moshi7b", "personaplex7b"))) else None,
                 "bytes_per_launch": dom_bytes, "launch_us": dom_ms * 1e3, "launches_timed": fam_n[dom],
                 "graph_replay": {"launch_us": us.value, "achieved": replay_gbs, "frac": (replay_gbs or 0) / peaks["hbm_gbs"],
                                  "how": "200 launches of the same kernel/shape in one CUDA graph over 8 rotating matrices (415 MB > L2)"},

@@ -84,7 +84,7 @@ def lib():
         return _lib
     if not os.path.exists(SO_PATH):
         raise MsxError(-4, f"{SO_PATH} is missing: run __graft_entry__.build() (nvcc, sm_100a). No CPU fallback exists.")
-    L = C.CDLL(SO_PATH)
+    L = C.CDLL(os.environ.get("MSX_LIB_EXPERIMENT") or SO_PATH)     # dev: A/B an experimental build of the same ABI
     vp, i32p = C.c_void_p, C.POINTER(C.c_int32)
     L.msx_last_error.restype = C.c_char_p
     L.msx_version.restype = C.c_char_p
