@@ -125,6 +125,13 @@ MSX_API int msx_stream_set_noise(msx_stream *s, const float *noise_text, const f
 MSX_API int msx_model_load_gguf_tp(const char *path, const msx_config *cfg, int device, int tp_rank, int tp_world, msx_model **out);
 MSX_API int msx_tp_unique_id(uint8_t *out128);
 MSX_API int msx_stream_create_tp(msx_model *model, int context_override, const uint8_t *nccl_id128, msx_stream **out);
+/* Fused GEMV -> all-reduce over peer memory (replaces the NCCL launches of a tensor-parallel stream): every rank exports
+ * a 64-byte CUDA-IPC handle of its inbox arena, the handles are exchanged out of band, and msx_stream_tp_connect maps the
+ * peers and re-captures the graphs: out_proj / linear_out push their fp64 partial sums straight into every rank's inbox
+ * over NVLink from the GEMV epilogue, the last CTA publishes an epoch flag (st.release.sys), and the residual kernel
+ * waits for the flags and adds the rows in rank order.  Same numbers as the NCCL path and as one GPU. */
+MSX_API int msx_stream_tp_export(msx_stream *s, uint8_t *handle64);
+MSX_API int msx_stream_tp_connect(msx_stream *s, const uint8_t *handles /* [world][64] */);
 
 /* TTS conditioning (reference: moshi_lm_start -> init(), moshi.cpp:851-883; transformer.h:343-396; lm.h:575-577).
  * cond_sum[dim] (or NULL) is added to the embedding sum of every frame; cond_cross[tc][dim] (or NULL) is projected once

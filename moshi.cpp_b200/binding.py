@@ -94,6 +94,8 @@ def lib():
     L.msx_model_load_gguf_tp.argtypes = [C.c_char_p, C.POINTER(MsxConfig), C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
     L.msx_tp_unique_id.argtypes = [vp]
     L.msx_stream_create_tp.argtypes = [vp, C.c_int, vp, C.POINTER(vp)]
+    L.msx_stream_tp_export.argtypes = [vp, vp]
+    L.msx_stream_tp_connect.argtypes = [vp, vp]
     L.msx_model_config.argtypes = [vp, C.POINTER(MsxConfig)]
     L.msx_model_weight_bytes_per_frame.restype = C.c_int64; L.msx_model_weight_bytes_per_frame.argtypes = [vp]
     L.msx_model_device_bytes.restype = C.c_int64; L.msx_model_device_bytes.argtypes = [vp]
@@ -287,6 +289,16 @@ class Stream:
     def set_noise(self, noise_text, noise_audio):
         nt = np.ascontiguousarray(noise_text, dtype=np.float32); na = np.ascontiguousarray(noise_audio, dtype=np.float32)
         _check(lib().msx_stream_set_noise(self.h, _p(nt), _p(na)))
+
+    def tp_export(self) -> bytes:
+        buf = np.zeros(64, dtype=np.uint8)
+        _check(lib().msx_stream_tp_export(self.h, _p(buf)))
+        return buf.tobytes()
+
+    def tp_connect(self, handles):
+        """handles: list of 64-byte IPC handles in rank order -> fused GEMV + peer-memory all-reduce"""
+        buf = np.frombuffer(b"".join(handles), dtype=np.uint8).copy()
+        _check(lib().msx_stream_tp_connect(self.h, _p(buf)))
 
     def set_condition(self, cond_sum=None, cond_cross=None):
         """TTS conditioning: cond_sum [dim] and / or cond_cross [Tc][dim]"""

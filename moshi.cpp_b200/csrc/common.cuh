@@ -87,6 +87,19 @@ enum Epilogue : int {
     EPI_ADD_VEC = 5,   // out[r] = acc + addvec[r]            (depformer_in + low-rank / demux embedding computed by small_linear_kernel)
 };
 
+// Tensor-parallel peer-memory context (device resident).  Every rank owns an inbox [2 parities][world][dim] of 16-byte
+// entries {value.lo, seq, value.hi, seq} that its peers map through CUDA IPC.  A GEMV with EPI_STORE_F64 pushes every
+// un-rounded fp64 partial sum straight into every rank's inbox from its epilogue (one 16-byte store per row and rank over
+// NVLink); the sequence number travels WITH the data in each 8-byte half (the "LL" idea: no fence, no separate flag, no
+// completion counting), so the consumer (tp_apply_p2p_kernel) just polls the entries it needs and adds them in rank
+// order.  Two parities: a rank can be at most one reduce ahead of its slowest peer.
+struct TpCtx {
+    int32_t rank = 0, world = 1, dim = 0, pad = 0;
+    uint4 *inbox[8] = {};         // inbox base of every rank (own entry = local pointer)
+    uint32_t *epoch = nullptr;    // local: number of completed reduces (seq of the running one = epoch + 1)
+    int32_t *error = nullptr;     // Ctrl::error (spin watchdog)
+};
+
 struct GemvArgs {
     QLinear w;
     const float *x = nullptr;       // [K] activations (f32)
@@ -103,6 +116,7 @@ struct GemvArgs {
     int32_t emb_step = 0;           // 0: text token (scaled embedding), k>0: audio token of step k-1 (chained)
     const float *addvec = nullptr;  // EPI_ADD_VEC
     double *out_f64 = nullptr;      // EPI_STORE_F64
+    const TpCtx *tp = nullptr;      // EPI_STORE_F64: push to the peers' inboxes instead (see TpCtx)
 };
 
 // warp index broadcast from lane 0: tells the compiler the value is warp-uniform, so loops and branches on it
@@ -135,6 +149,10 @@ __device__ __forceinline__ uint16_t f32_to_bf16_bits(float f) {
 }
 __device__ __forceinline__ float bf16_bits_to_f32(uint32_t h) { return __uint_as_float(h << 16); }
 __device__ __forceinline__ float bf16_round(float f) { return bf16_bits_to_f32(f32_to_bf16_bits(f)); }
+
+__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t ld_relaxed_sys(const uint32_t *p) { uint32_t v; asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) { uint32_t v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
 
 // 128-bit streaming load (weights are read exactly once per step: do not allocate in L1)
 __device__ __forceinline__ int4 ldg_stream(const void *p) {

@@ -545,7 +545,7 @@ struct Launcher {
 
     void gemv(const GemvArgs &a, int pro, int epi, int family = 0) {
         fam = family; begin();
-        if (mma && model && a.w.type == T_Q4_K) {
+        if (mma && model && a.w.type == T_Q4_K && !a.tp) {
             auto it = model->tiles.find(a.w.qs);
             if (it != model->tiles.end() && a.w.rows == it->second.rows) {
                 const QTiles &wt = it->second;
@@ -683,6 +683,11 @@ struct msx_stream {
     // tensor parallelism: double partial sums of out_proj / linear_out, all-reduced with NCCL inside the graph
     double *tp_partial = nullptr;    // [dim]
     void *nccl_comm = nullptr;
+    // peer-memory all-reduce (msx_stream_tp_export / _connect): arena mapped by the peers through CUDA IPC
+    uint8_t *tp_arena = nullptr;     // [inbox 2 x world x dim x {lo, seq, hi, seq} | epoch]
+    TpCtx *d_tp = nullptr;           // device copy of the context
+    std::vector<void *> tp_peer_maps;
+    bool tp_p2p = false;
     bool embed_override_next = false;
     bool use_mma = false;            // Q4_K linears on the tensor-core unit kernel (MSX_MMA=1)
     int32_t *d_feed = nullptr;       // msx_run_resident_async
@@ -709,6 +714,7 @@ struct msx_stream {
         if (g_temporal) cudaGraphExecDestroy(g_temporal);
         if (g_depformer) cudaGraphExecDestroy(g_depformer);
         if (nccl_comm) nccl().CommDestroy(nccl_comm);
+        for (void *p : tp_peer_maps) cudaIpcCloseMemHandle(p);
         for (void *p : allocs) cudaFree(p);
         if (h_in) cudaFreeHost(h_in);
         if (h_out) cudaFreeHost(h_out);
@@ -744,6 +750,16 @@ void enqueue_layer(Launcher &L, const msx_stream *s, const LayerW &lw, int w, bo
     float *x = temporal ? s->x : s->dx, *qkv = temporal ? s->qkv : s->dqkv, *ctx = temporal ? s->ctx : s->dctx, *gate = temporal ? s->gate : s->dgate;
     // out[dim] += W_shard . in : partial sums in double -> NCCL all-reduce (sum) -> rounded once into the residual stream
     auto reduce_into_x = [&](GemvArgs &gg, int family) {
+        if (s->tp_p2p) {
+            // GEMV pushes its partial sums into every rank's inbox over NVLink; the consumer waits for the flags
+            gg.out_f64 = nullptr; gg.out = nullptr; gg.tp = s->d_tp;
+            L.gemv(gg, PRO_PLAIN, EPI_STORE_F64, family);
+            gg.tp = nullptr;
+            L.fam = family; L.begin();
+            L.launch_pdl(tp_apply_p2p_kernel, dim3(1), dim3(1024), 0, x, (const TpCtx *)s->d_tp);
+            L.check();
+            return;
+        }
         gg.out_f64 = s->tp_partial; gg.out = nullptr;
         L.gemv(gg, PRO_PLAIN, EPI_STORE_F64, family);
         L.fam = family; L.begin();
@@ -1287,6 +1303,59 @@ extern "C" int msx_step(msx_stream *s, const int32_t *tokens, int32_t *out_token
     if (c.dep_q > 0) CU(cudaGraphLaunch(s->g_depformer, s->st));
     if (int e = pull_outputs(s)) return e;
     if (out_tokens) for (int k = 0; k < 1 + c.dep_q; k++) out_tokens[k] = s->h_out[k];
+    return 0;
+}
+
+// ---- peer-memory all-reduce for tensor-parallel streams ---------------------------------------------------------------
+static size_t tp_arena_bytes(const msx_stream *s) { return (size_t)2 * s->m->tp_world * s->m->cfg.dim * 16 + 64; }
+
+extern "C" int msx_stream_tp_export(msx_stream *s, uint8_t *handle64) {
+    if (!s || !handle64) return fail(MSX_ERR_ARG, "null argument");
+    if (s->m->tp_world < 2) return fail(MSX_ERR_STATE, "not a tensor-parallel stream");
+    if (s->m->tp_world > 8) return fail(MSX_ERR_ARG, "peer-memory all-reduce supports up to 8 ranks");
+    CU(cudaSetDevice(s->m->device));
+    if (!s->tp_arena) {
+        CU(cudaMalloc((void **)&s->tp_arena, tp_arena_bytes(s)));        // plain cudaMalloc: IPC-exportable
+        s->allocs.push_back(s->tp_arena);
+        CU(cudaMemset(s->tp_arena, 0, tp_arena_bytes(s)));
+    }
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, s->tp_arena));
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t");
+    memcpy(handle64, &h, 64);
+    return 0;
+}
+
+// handles[world][64] in rank order (own entry ignored).  Re-captures the graphs with the fused GEMV -> peer push path.
+extern "C" int msx_stream_tp_connect(msx_stream *s, const uint8_t *handles) {
+    if (!s || !handles) return fail(MSX_ERR_ARG, "null argument");
+    msx_model *m = s->m;
+    if (m->tp_world < 2 || !s->tp_arena) return fail(MSX_ERR_STATE, "call msx_stream_tp_export on every rank first");
+    CU(cudaSetDevice(m->device));
+    CU(cudaStreamSynchronize(s->st));
+    TpCtx h;
+    h.rank = m->tp_rank; h.world = m->tp_world; h.dim = m->cfg.dim;
+    if (m->cfg.dim > 1024 * kTpApplyPer) return fail(MSX_ERR_ARG, "peer-memory all-reduce: dim too large for the apply kernel");
+    const size_t inbox_bytes = (size_t)2 * m->tp_world * m->cfg.dim * 16;
+    for (int r = 0; r < m->tp_world; r++) {
+        uint8_t *base = s->tp_arena;
+        if (r != m->tp_rank) {
+            cudaIpcMemHandle_t ih;
+            memcpy(&ih, handles + (size_t)r * 64, 64);
+            void *p = nullptr;
+            CU(cudaIpcOpenMemHandle(&p, ih, cudaIpcMemLazyEnablePeerAccess));
+            s->tp_peer_maps.push_back(p);
+            base = (uint8_t *)p;
+        }
+        h.inbox[r] = reinterpret_cast<uint4 *>(base);
+    }
+    h.epoch = reinterpret_cast<uint32_t *>(s->tp_arena + inbox_bytes);
+    h.error = &s->ctrl->error;
+    if (!s->d_tp) if (int e = salloc(s, (void **)&s->d_tp, sizeof(TpCtx))) return e;
+    CU(cudaMemcpy(s->d_tp, &h, sizeof(h), cudaMemcpyHostToDevice));
+    s->tp_p2p = true;
+    if (int e = build_graphs(s)) return e;
+    CU(cudaStreamSynchronize(s->st));
     return 0;
 }
 

@@ -478,6 +478,8 @@ __device__ __forceinline__ void gemv_body(const GemvArgs &a, const float *x_over
     int emb_token = 0;
     if (EPI == EPI_ADD_EMB) emb_token = depformer_prev_token(a.ctrl, a.emb_step);
     unsigned long long best = 0ull;
+    uint32_t tp_epoch = 0, tp_parity = 0;
+    if (EPI == EPI_STORE_F64 && a.tp) { tp_epoch = __ldcg(a.tp->epoch); tp_parity = tp_epoch & 1u; }
 
     double acc[kR];
 #pragma unroll
@@ -500,7 +502,14 @@ __device__ __forceinline__ void gemv_body(const GemvArgs &a, const float *x_over
         for (int r = 0; r < kR; r++) {
 #pragma unroll
             for (int o = LANES / 2; o > 0; o >>= 1) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], o);
-            if (EPI == EPI_STORE_F64 && l == 0 && cons.row0 + r < a.w.rows) a.out_f64[cons.row0 + r] = acc[r];
+            if (EPI == EPI_STORE_F64 && l == 0 && cons.row0 + r < a.w.rows) {
+                if (a.tp) {      // partial sum + sequence number straight into every rank's inbox (own rank included)
+                    const size_t o = ((size_t)tp_parity * a.tp->world + a.tp->rank) * a.tp->dim + cons.row0 + r;
+                    const unsigned long long bits = (unsigned long long)__double_as_longlong(acc[r]);
+                    const uint4 pk = make_uint4((uint32_t)bits, tp_epoch + 1u, (uint32_t)(bits >> 32), tp_epoch + 1u);
+                    for (int q = 0; q < a.tp->world; q++) a.tp->inbox[q][o] = pk;
+                } else a.out_f64[cons.row0 + r] = acc[r];
+            }
             accf[r] = (float)acc[r];
             acc[r] = 0.0;
         }

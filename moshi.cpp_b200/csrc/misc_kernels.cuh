@@ -102,6 +102,47 @@ __global__ void tp_apply_kernel(float *x, const double *partial, int n) {
     if (i < n) x[i] = __ldcg(x + i) + (float)__ldcg(partial + i);
 }
 
+// peer-memory variant: poll the inbox entries (data and sequence number arrive together), add them in rank order
+// (identical on all ranks).  The epoch (which reduce this is) is only stable once the previous apply kernel has finished:
+// with chained programmatic launches this kernel can become resident several kernels early, so it waits first.
+__device__ __forceinline__ uint4 ld_volatile_v4(const uint4 *p) {
+    uint4 v;
+    asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+constexpr int kTpApplyPer = 4;     // elements per thread (dim <= 4096 with 1024 threads)
+__global__ void __launch_bounds__(1024) tp_apply_p2p_kernel(float *x, const TpCtx *tp) {
+    griddep_launch();
+    griddep_wait();
+    const int world = tp->world, rank = tp->rank, dim = tp->dim;
+    const uint32_t e = *reinterpret_cast<const volatile uint32_t *>(tp->epoch), seq = e + 1u, parity = e & 1u;
+    const uint4 *in = tp->inbox[rank] + (size_t)parity * world * dim;
+    double s[kTpApplyPer];
+    long long t0 = 0; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+#pragma unroll
+    for (int j = 0; j < kTpApplyPer; j++) {
+        s[j] = 0.0;
+        const int i = threadIdx.x + j * blockDim.x;
+        if (i >= dim) continue;
+        for (int r = 0; r < world; r++) {
+            uint4 v = ld_volatile_v4(in + (size_t)r * dim + i);
+            while (v.y != seq || v.w != seq) {
+                long long t1; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+                if (t1 - t0 > 20000000000ll) { *tp->error = 2; break; }     // watchdog: a peer never arrived (20 s)
+                v = ld_volatile_v4(in + (size_t)r * dim + i);
+            }
+            s[j] += __longlong_as_double((long long)(((unsigned long long)v.z << 32) | v.x));
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < kTpApplyPer; j++) {
+        const int i = threadIdx.x + j * blockDim.x;
+        if (i < dim) x[i] = __ldcg(x + i) + (float)s[j];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *tp->epoch = e + 1u;
+}
+
 // ---- load-time repack (GGUF row-major blocks -> device tiles, see common.cuh QLinear) --------------
 // perm_half > 0 interleaves rows for the gated MLP: stored row v <- source row (v&1 ? perm_half + v/2 : v/2)
 __device__ __forceinline__ int src_row_of(int v, int perm_half) { return perm_half > 0 ? ((v & 1) ? perm_half + (v >> 1) : (v >> 1)) : v; }

@@ -25,7 +25,12 @@ def main():
     dist.broadcast_object_list(ids, src=0)
     model = msx.Model(path, cfg, device=local, tp_rank=rank, tp_world=world)
     stream = msx.Stream(model, nccl_id=ids[0])
+    if os.environ.get("TP_P2P", "0") == "1":       # fused GEMV -> peer-memory all-reduce instead of NCCL launches
+        hs = [None] * world
+        dist.all_gather_object(hs, stream.tp_export())
+        stream.tp_connect(hs)
     ref = msx.Stream(msx.Model(path, cfg, device=local)) if (rank == 0 and os.environ.get("CHECK", "1") == "1") else None
+    dist.barrier()
     rng = np.random.default_rng(5)
     n_q, dep_q = cfg["n_q"], cfg["dep_q"]
     toks = np.array([cfg["text_card"]] + [cfg["card"]] * n_q, dtype=np.int32)
@@ -70,7 +75,7 @@ def main():
             ms1, _ = ref.run_resident(fr, 200)
             res["single_gpu_ms_per_frame"] = ms1 / 200
     if rank == 0:
-        out = {"preset": preset, "quant": quant, "tp": world, "frames": frames, "worst_max_rel_vs_single_gpu": worst,
+        out = {"preset": preset, "quant": quant, "tp": world, "allreduce": "peer-memory (fused)" if os.environ.get("TP_P2P", "0") == "1" else "nccl", "frames": frames, "worst_max_rel_vs_single_gpu": worst,
                "logit_vectors_bit_identical": f"{exact}/{cmp_n}", "token_mismatches": tok_bad, "ranks_agree": bool(same), **res}
         print("TP_CHECK " + json.dumps(out), flush=True)
         ok = same and (ref is None or (tok_bad == 0 and worst < 2e-3))
