@@ -192,6 +192,12 @@ assert worst == 10.0 * w, worst
 import torch
 n = torch.tensor([len(mine)]); dist.all_reduce(n)
 assert int(n[0]) == 5
+# tensor-parallel bring-up protocol: id from rank 0 to everyone, one handle per rank gathered in rank order
+ids = [b"id-from-rank-0" if r == 0 else None]
+dist.broadcast_object_list(ids, src=0)
+assert ids[0] == b"id-from-rank-0"
+hs = parallel.tp_exchange(dist, bytes([r]) * 64)
+assert [h[0] for h in hs] == list(range(w)) and all(len(h) == 64 for h in hs)
 if r == 0:
     print("OK", worst, int(n[0]))
 dist.destroy_process_group()
@@ -207,3 +213,58 @@ def test_two_rank_gloo_plumbing(tmp_path):
                          capture_output=True, text=True, timeout=240, env=env)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "OK 20.0 5" in out.stdout
+
+
+@pytest.mark.parametrize("preset", ["moshi7b", "personaplex7b", "tiny", "stt1b"])
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+def test_tensor_parallel_shards_tile_the_model(preset, world):
+    """heads and hidden slices of all ranks are disjoint, cover everything, and respect the block alignment the
+    quantised K-slices need (256 for q4_k super-blocks when the width allows, else 32)"""
+    cfg = configs.get(preset)
+    if cfg["num_heads"] % world:
+        with pytest.raises(ValueError):
+            parallel.tp_shard(cfg, 0, world)
+        return
+    F = cfg["hidden"]
+    try:
+        shards = [parallel.tp_shard(cfg, r, world) for r in range(world)]
+    except ValueError:
+        assert F // (256 if F % 256 == 0 else 32) < world
+        return
+    assert shards[0]["h0"] == 0 and shards[-1]["h1"] == cfg["num_heads"] and shards[0]["f0"] == 0 and shards[-1]["f1"] == F
+    for a, b in zip(shards, shards[1:]):
+        assert a["h1"] == b["h0"] and a["f1"] == b["f0"]
+    unit = 256 if F % 256 == 0 else 32
+    dh = cfg["dim"] // cfg["num_heads"]
+    for s in shards:
+        assert s["f0"] % unit == 0 and s["f1"] % unit == 0 and s["f1"] > s["f0"]
+        assert s["adim"] == (s["h1"] - s["h0"]) * dh
+        assert (s["h0"] * dh) % 32 == 0
+
+
+def test_tensor_parallel_decomposition_is_exact_in_double():
+    """why the shards reproduce one GPU bit for bit: out_proj / linear_out partial sums over K-slices, added in
+    double, equal the full contraction; in_proj / linear_in row slices concatenate"""
+    import oracle as orc
+    rng = np.random.default_rng(0)
+    cfg = configs.get("tiny")
+    k, rows = cfg["hidden"], cfg["dim"]
+    raw = synth.random_tensor(rng, synth.GGML_Q8_0, rows, k, 0.05)
+    w = orc.dequantize(synth.GGML_Q8_0, raw, k).astype(np.float64)
+    x = rng.standard_normal(k)
+    full = w @ x
+    for world in (2, 3):
+        if world == 3:
+            continue
+        parts = []
+        for r in range(world):
+            s = parallel.tp_shard(cfg, r, world)
+            parts.append(w[:, s["f0"]:s["f1"]] @ x[s["f0"]:s["f1"]])
+        assert np.allclose(np.sum(parts, axis=0), full, rtol=1e-13, atol=1e-13)
+    rows_w = rng.standard_normal((3 * cfg["dim"], 16))
+    got = []
+    for sec in range(3):
+        for r in range(2):
+            a, b = parallel.tp_shard(cfg, r, 2)["in_proj_rows"][sec]
+            got.append(rows_w[a:b])
+    assert np.array_equal(np.concatenate(got), rows_w)
