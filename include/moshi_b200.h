@@ -180,6 +180,9 @@ MSX_API int msx_gen_create_with_callback(const msx_config *cfg, int delay_steps,
 MSX_API void msx_gen_free(msx_gen *g);
 /* srand() for the Exp(1) draws of sampled generation (the reference never seeds except in --bench: srand(0)) */
 MSX_API void msx_gen_seed(msx_gen *g, unsigned seed);
+/* T prompt frames with all n_q+1 tokens given (rows [T][n_q+1]) as one batched-T prefill: delay-ring bookkeeping of
+ * moshi_lmgen_step's "provided" branch + msx_stream_prefill; same final state as T msx_gen_step calls with n_in == n_q+1 */
+MSX_API int msx_gen_prefill(msx_gen *g, const int32_t *rows, int n_frames);
 /* PersonaPlex voice prompt, embedding variant (moshi_lmgen_step_voice_prompt, lm.h:1005-1050): replay one embedding
  * row (text forced to 3, depformer run, offset++); afterwards install the voice's token ring, cache[CT][n_q+1] with
  * CT = msx_gen_cache_rows() */
@@ -203,6 +206,12 @@ MSX_API int msx_gen_max_delay(const msx_gen *g);
  * Repack one row-major GGUF tensor [rows][k] of `type` (ggml type id), run y = W.x on the device
  * with the same fused kernels the step uses.  prologue: 0 = quantise x, 1 = rms_norm(x)*alpha then
  * quantise.  All pointers are host pointers. */
+/* Batched-T prompt prefill: T frames whose n_q+1 tokens are all given (PersonaPlex voice / system
+ * prompt rows, lm.h:983-1134) are run 8 positions at a time as the 8 columns of the tensor-core GEMM.  Only the temporal
+ * KV rings and the position advance — exactly what T "provided" steps leave behind (their logits, sampled tokens and
+ * depformer output are discarded, lm.h:933-943).  tokens [T][n_q+1]; offset + T must not exceed the ring; q4_k models. */
+MSX_API int msx_stream_prefill(msx_stream *s, const int32_t *tokens, int n_frames);
+
 /* ---- lock-step batch of independent streams (BASELINE.json config 5) ------------------
  * n_streams (1..8) conversations share every weight read: one activation-quantisation launch and one
  * tensor-core dequant-GEMM launch per linear layer serve all of them; KV rings, positions and delay state

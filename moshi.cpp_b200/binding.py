@@ -95,6 +95,7 @@ def lib():
     L.msx_tp_unique_id.argtypes = [vp]
     L.msx_stream_create_tp.argtypes = [vp, C.c_int, vp, C.POINTER(vp)]
     L.msx_stream_tp_export.argtypes = [vp, vp]
+    L.msx_stream_prefill.argtypes = [vp, vp, C.c_int]
     L.msx_stream_tp_connect.argtypes = [vp, vp]
     L.msx_model_config.argtypes = [vp, C.POINTER(MsxConfig)]
     L.msx_model_weight_bytes_per_frame.restype = C.c_int64; L.msx_model_weight_bytes_per_frame.argtypes = [vp]
@@ -133,6 +134,7 @@ def lib():
     L.msx_gen_create_with_callback.argtypes = [C.POINTER(MsxConfig), C.c_int, STEP_FN, vp, C.POINTER(vp)]
     L.msx_gen_step.argtypes = [vp, vp, C.c_int, C.c_int, i32p, vp]
     L.msx_gen_offset.argtypes = [vp]
+    L.msx_gen_prefill.argtypes = [vp, vp, C.c_int]
     L.msx_gen_max_delay.argtypes = [vp]
     L.msx_test_gemv.argtypes = [C.c_int, C.c_int, vp, C.c_int64, C.c_int64, vp, vp, C.c_int, vp]
     L.msx_batch_create.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp)]
@@ -290,6 +292,11 @@ class Stream:
         nt = np.ascontiguousarray(noise_text, dtype=np.float32); na = np.ascontiguousarray(noise_audio, dtype=np.float32)
         _check(lib().msx_stream_set_noise(self.h, _p(nt), _p(na)))
 
+    def prefill(self, tokens):
+        """tokens [T][n_q+1]: batched-T prompt prefill (KV rings + position only)"""
+        tk = np.ascontiguousarray(tokens, dtype=np.int32).reshape(-1, self.model.cfg["n_q"] + 1)
+        _check(lib().msx_stream_prefill(self.h, _p(tk), tk.shape[0]))
+
     def tp_export(self) -> bytes:
         buf = np.zeros(64, dtype=np.uint8)
         _check(lib().msx_stream_tp_export(self.h, _p(buf)))
@@ -393,6 +400,11 @@ class Gen:
     @property
     def offset(self):
         return lib().msx_gen_offset(self.h)
+
+    def prefill(self, rows):
+        """rows [T][n_q+1] (all tokens given): batched-T prompt prefill with the generator's ring bookkeeping"""
+        r = np.ascontiguousarray(rows, dtype=np.int32).reshape(-1, self.cfg["n_q"] + 1)
+        _check(lib().msx_gen_prefill(self.h, _p(r), r.shape[0]))
 
     def step(self, in_tokens, replace: bool = False):
         cfg = self.cfg

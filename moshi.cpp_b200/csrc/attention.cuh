@@ -41,6 +41,7 @@ struct AttnArgs {
     // batched steps: grid.z = stream; per-stream strides in elements (0 for a single stream)
     int64_t kv_bstride = 0;
     int32_t qkv_bstride = 0, ctx_bstride = 0;
+    int32_t skip_insert = 0;        // the ring rows of this step were written by kv_insert_kernel (batched-T prefill)
 };
 
 constexpr int kAttnMaxSplit = 8;
@@ -52,6 +53,37 @@ __host__ __device__ inline int attn_smem_bytes(int cap, int S) {
     const int per = (cap + S - 1) / S + 1;
     const int ng = kThreads / (DH / 8);
     return (64 + 64 + kAttnMaxSplit * DH * 8 + ng * DH * 8 + DH * 4 + DH * 4 + 32 + per * 4 + 15) / 16 * 16;
+}
+
+// q' (bf16-rounded, RoPE'd), and the bf16 K / V rows of this step for head h; threads tid < DH/2 work
+template <int DH>
+__device__ __forceinline__ void rope_rows(const AttnArgs &a, int h, int pos, int tid, float *q_s, uint16_t *knew, uint16_t *vnew) {
+    const float *q = a.qkv + h * DH, *k = a.qkv + a.dim + h * DH, *v = a.qkv + 2 * a.dim + h * DH;
+    if (tid < DH / 2) {
+        const int j = tid;
+        float cs = 1.f, sn = 0.f;
+        if (a.max_period) {
+            // ggml_timestep_embedding: freq = expf(-logf(max_period) * j / half); arg = pos * freq.
+            // cos/sin through double: correctly rounded fp32 irrespective of the libm (order-independent parity)
+            if (a.rope_cs) { cs = __ldcg(a.rope_cs + j); sn = __ldcg(a.rope_cs + DH / 2 + j); }
+            else {
+                const float arg = (float)pos * a.rope_freq[j];
+                cs = (float)cos((double)arg); sn = (float)sin((double)arg);
+            }
+        }
+        const float qr = q[2 * j], qi = q[2 * j + 1], kr = k[2 * j], ki = k[2 * j + 1];
+        float qo_r, qo_i, ko_r, ko_i;
+        if (a.max_period) {
+            qo_r = __fsub_rn(__fmul_rn(qr, cs), __fmul_rn(qi, sn)); qo_i = __fadd_rn(__fmul_rn(qr, sn), __fmul_rn(qi, cs));
+            ko_r = __fsub_rn(__fmul_rn(kr, cs), __fmul_rn(ki, sn)); ko_i = __fadd_rn(__fmul_rn(kr, sn), __fmul_rn(ki, cs));
+            q_s[j] = bf16_round(qo_r); q_s[DH / 2 + j] = bf16_round(qo_i);
+            knew[j] = f32_to_bf16_bits(ko_r); knew[DH / 2 + j] = f32_to_bf16_bits(ko_i);
+        } else {
+            q_s[2 * j] = bf16_round(qr); q_s[2 * j + 1] = bf16_round(qi);
+            knew[2 * j] = f32_to_bf16_bits(kr); knew[2 * j + 1] = f32_to_bf16_bits(ki);
+        }
+        vnew[2 * j] = f32_to_bf16_bits(v[2 * j]); vnew[2 * j + 1] = f32_to_bf16_bits(v[2 * j + 1]);
+    }
 }
 
 template <int DH, bool CLUSTER>
@@ -94,35 +126,11 @@ __global__ void __launch_bounds__(kThreads) attn_kernel(const AttnArgs a0) {
     (void)per;
 
     // ---- 1. RoPE (interleaved pairs -> [re half | im half]) and the new K/V row -------------------
-    const float *q = a.qkv + h * DH, *k = a.qkv + a.dim + h * DH, *v = a.qkv + 2 * a.dim + h * DH;
-    if (tid < DH / 2) {
-        const int j = tid;
-        float cs = 1.f, sn = 0.f;
-        if (a.max_period) {
-            // ggml_timestep_embedding: freq = expf(-logf(max_period) * j / half); arg = pos * freq.
-            // cos/sin through double: correctly rounded fp32 irrespective of the libm (order-independent parity)
-            if (a.rope_cs) { cs = __ldcg(a.rope_cs + j); sn = __ldcg(a.rope_cs + DH / 2 + j); }
-            else {
-                const float arg = (float)pos * a.rope_freq[j];
-                cs = (float)cos((double)arg); sn = (float)sin((double)arg);
-            }
-        }
-        const float qr = q[2 * j], qi = q[2 * j + 1], kr = k[2 * j], ki = k[2 * j + 1];
-        float qo_r, qo_i, ko_r, ko_i;
-        if (a.max_period) {
-            qo_r = __fsub_rn(__fmul_rn(qr, cs), __fmul_rn(qi, sn)); qo_i = __fadd_rn(__fmul_rn(qr, sn), __fmul_rn(qi, cs));
-            ko_r = __fsub_rn(__fmul_rn(kr, cs), __fmul_rn(ki, sn)); ko_i = __fadd_rn(__fmul_rn(kr, sn), __fmul_rn(ki, cs));
-            q_s[j] = bf16_round(qo_r); q_s[DH / 2 + j] = bf16_round(qo_i);
-            knew[j] = f32_to_bf16_bits(ko_r); knew[DH / 2 + j] = f32_to_bf16_bits(ko_i);
-        } else {
-            q_s[2 * j] = bf16_round(qr); q_s[2 * j + 1] = bf16_round(qi);
-            knew[2 * j] = f32_to_bf16_bits(kr); knew[2 * j + 1] = f32_to_bf16_bits(ki);
-        }
-        vnew[2 * j] = f32_to_bf16_bits(v[2 * j]); vnew[2 * j + 1] = f32_to_bf16_bits(v[2 * j + 1]);
-    }
+    rope_rows<DH>(a, h, pos, tid, q_s, knew, vnew);
     __syncthreads();
     // ring insert (moshi_kv_cache_insert_kv): DH bf16 = DH/4 8-byte pieces per row
-    if (c == 0 && tid < DH / 4) {
+    if (a.skip_insert) {
+    } else if (c == 0 && tid < DH / 4) {
         const size_t o = ((size_t)h * cap + slot) * DH;
         reinterpret_cast<uint2 *>(a.kc + o)[tid] = reinterpret_cast<const uint2 *>(knew)[tid];
     } else if (c == 0 && tid >= 64 && tid < 64 + DH / 4) {
@@ -254,6 +262,25 @@ __global__ void __launch_bounds__(kThreads) attn_kernel(const AttnArgs a0) {
     } else {
         if (tid < DH) a.ctx[h * DH + tid] = (float)tot;
     }
+}
+
+// Batched-T prefill: the K / V rows of ALL columns of a chunk are inserted first (columns = consecutive positions of ONE
+// stream sharing its ring), then attn_kernel runs with skip_insert: column b sees the rows of columns < b.
+template <int DH>
+__global__ void __launch_bounds__(64) kv_insert_kernel(const AttnArgs a0) {
+    __shared__ float q_s[DH];
+    __shared__ __align__(16) uint16_t knew[DH], vnew[DH];
+    AttnArgs a = a0;
+    const int b = blockIdx.y, h = blockIdx.x, tid = threadIdx.x;
+    griddep_launch();
+    griddep_wait();
+    a.qkv += (size_t)b * a.qkv_bstride; a.ctrl += b; if (a.rope_cs) a.rope_cs += (size_t)b * DH;
+    const int pos = a.pos_const >= 0 ? a.pos_const : a.ctrl->offset;
+    rope_rows<DH>(a, h, pos, tid, q_s, knew, vnew);
+    __syncthreads();
+    const size_t o = ((size_t)h * a.cap + (pos % a.cap)) * DH;
+    if (tid < DH / 4) reinterpret_cast<uint2 *>(a.kc + o)[tid] = reinterpret_cast<const uint2 *>(knew)[tid];
+    else if (tid >= 32 && tid < 32 + DH / 4) reinterpret_cast<uint2 *>(a.vc + o)[tid - 32] = reinterpret_cast<const uint2 *>(vnew)[tid - 32];
 }
 
 }  // namespace msx

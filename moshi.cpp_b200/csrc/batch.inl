@@ -24,6 +24,11 @@ struct msx_batch {
     std::vector<int> host_offset;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<void *> allocs;
+    // batched-T prefill of ONE stream: the columns are consecutive positions of `prefill_of`, they
+    // share its KV rings and its CUDA stream; n_active <= n columns are live in the launches being enqueued
+    msx_stream *prefill_of = nullptr;
+    int n_active = 0;
+    uint8_t *h_hdr = nullptr;             // pinned [n][32]: Ctrl headers (position per column)
 
     ~msx_batch() {
         if (m) cudaSetDevice(m->device);
@@ -32,9 +37,10 @@ struct msx_batch {
         for (void *p : allocs) cudaFree(p);
         if (h_in) cudaFreeHost(h_in);
         if (h_out) cudaFreeHost(h_out);
+        if (h_hdr) cudaFreeHost(h_hdr);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
-        if (st) cudaStreamDestroy(st);
+        if (st && !prefill_of) cudaStreamDestroy(st);
     }
 };
 
@@ -86,14 +92,14 @@ struct BatchLauncher {
         QuantArgs q;
         q.x = x; q.ld = ld; q.alpha = alpha; q.eps = 1e-8f; q.norm_out = norm_out; q.norm_ld = norm_ld; q.img = img ? img : b->img; q.K = K;
         L.fam = family; L.begin();
-        L.launch_pdl(quant_q8k_kernel, dim3(b->n, quant_parts_for(K)), dim3(kGemmThreads), 0, q);
+        L.launch_pdl(quant_q8k_kernel, dim3(b->n_active, quant_parts_for(K)), dim3(kGemmThreads), 0, q);
         L.check();
     }
     void gemm(const QLinear &w, float *out, int ld, int epi, int family, int key_index = -1, const EmbTable *emb = nullptr, int emb_step = 0,
               const uint8_t *img = nullptr) {
         GemmArgs g;
         if (int e = tiles_of(b->m, w, &g.w)) { err = e; return; }
-        g.img = img ? img : b->img; g.out = out; g.ld = ld; g.nb = b->n; g.epi = epi; g.ctrl = b->ctrl; g.key_index = key_index; g.emb_step = emb_step;
+        g.img = img ? img : b->img; g.out = out; g.ld = ld; g.nb = b->n_active; g.epi = epi; g.ctrl = b->ctrl; g.key_index = key_index; g.emb_step = emb_step;
         if (emb) g.emb = *emb;
         g.stages = gemm_stages_for(w.K);
         L.fam = family; L.begin();
@@ -121,7 +127,16 @@ void enqueue_layer_b(BatchLauncher &B, const LayerW &lw, int w, bool temporal, i
     a.kc = (temporal ? b->kc : b->dkc) + (size_t)layer * lstride;
     a.vc = (temporal ? b->vc : b->dvc) + (size_t)layer * lstride;
     a.kv_bstride = (int64_t)n_layers * lstride; a.qkv_bstride = 3 * dim; a.ctx_bstride = dim;
-    B.L.attn(a, heads, dim / heads, temporal ? b->attn_split : 1, temporal ? FAM_ATTN : FAM_DEP_ATTN, b->n);
+    if (b->prefill_of) {
+        // columns = consecutive positions of one stream: insert all their K / V rows into ITS ring first, then attend
+        a.kc = b->prefill_of->kc + (size_t)layer * lstride; a.vc = b->prefill_of->vc + (size_t)layer * lstride;
+        a.kv_bstride = 0; a.skip_insert = 1;
+        B.L.fam = FAM_ATTN; B.L.begin();
+        if (dim / heads == 128) B.L.launch_pdl(kv_insert_kernel<128>, dim3(heads, b->n_active), dim3(64), 0, a);
+        else B.L.launch_pdl(kv_insert_kernel<64>, dim3(heads, b->n_active), dim3(64), 0, a);
+        B.L.check();
+    }
+    B.L.attn(a, heads, dim / heads, temporal ? b->attn_split : 1, temporal ? FAM_ATTN : FAM_DEP_ATTN, b->n_active);
     B.quant(ctx, dim, nullptr, nullptr, 0, dim, temporal ? FAM_OUT_PROJ : FAM_DEP_OUT_PROJ);
     B.gemm(lw.out_proj[w], x, dim, EPI_RESID, temporal ? FAM_OUT_PROJ : FAM_DEP_OUT_PROJ);
     B.quant(x, dim, lw.norm2, nullptr, 0, dim, temporal ? FAM_LIN_IN : FAM_DEP_LIN_IN);
@@ -137,13 +152,14 @@ void enqueue_temporal_b(BatchLauncher &B) {
     e.tables = m->d_emb; e.n_tables = c.n_q + 1; e.dim = c.dim; e.ctrl = b->ctrl; e.x = b->x;
     if (c.max_period) { e.rope_cs = b->rope_cs; e.rope_freq = m->rope_freq; e.dh = c.dim / c.num_heads; }
     L.fam = FAM_EMBED; L.begin();
-    L.launch_pdl(embed_kernel, dim3((c.dim + kThreads - 1) / kThreads, b->n), dim3(kThreads), 0, e);
+    L.launch_pdl(embed_kernel, dim3((c.dim + kThreads - 1) / kThreads, b->n_active), dim3(kThreads), 0, e);
     L.check();
     for (int l = 0; l < c.num_layers; l++) enqueue_layer_b(B, m->layers[l], 0, true, l, -1);
+    if (b->prefill_of) return;           // prompt frames only populate the KV rings: no head, no sampling, no depformer
     B.quant(b->x, c.dim, m->out_norm, b->tout, c.dim, c.dim, FAM_TEXT_HEAD);
     B.gemm(m->text_linear, b->text_logits, c.text_card, EPI_ARGMAX, FAM_TEXT_HEAD, -1);
     L.fam = FAM_FINALIZE; L.begin();
-    L.launch_pdl(finalize_temporal_kernel, dim3(b->n), dim3(32), 0, b->ctrl, c.dep_q > 0 ? 1 : 0);
+    L.launch_pdl(finalize_temporal_kernel, dim3(b->n_active), dim3(32), 0, b->ctrl, c.dep_q > 0 ? 1 : 0);
     L.check();
 }
 
@@ -161,7 +177,7 @@ void enqueue_depformer_b(BatchLauncher &B) {
         B.gemm(m->linears[k], b->audio_logits + (size_t)k * c.card, c.dep_q * c.card, EPI_ARGMAX, FAM_DEP_HEAD, k);
     }
     L.fam = FAM_DEP_FINALIZE; L.begin();
-    L.launch_pdl(finalize_depformer_kernel, dim3(b->n), dim3(64), 0, b->ctrl, (int)c.dep_q);
+    L.launch_pdl(finalize_depformer_kernel, dim3(b->n_active), dim3(64), 0, b->ctrl, (int)c.dep_q);
     L.check();
 }
 
@@ -207,7 +223,11 @@ int pull_outputs_b(msx_batch *b) {
 
 }  // namespace
 
+static int batch_create_impl(msx_model *m, int n_streams, int context_override, msx_stream *prefill_of, msx_batch **out);
 extern "C" int msx_batch_create(msx_model *m, int n_streams, int context_override, msx_batch **out) {
+    return batch_create_impl(m, n_streams, context_override, nullptr, out);
+}
+static int batch_create_impl(msx_model *m, int n_streams, int context_override, msx_stream *prefill_of, msx_batch **out) {
     if (!m || !out) return fail(MSX_ERR_ARG, "null argument");
     *out = nullptr;
     if (n_streams < 1 || n_streams > kMmaCols) return fail(MSX_ERR_ARG, "a batch holds 1..8 streams");
@@ -218,20 +238,24 @@ extern "C" int msx_batch_create(msx_model *m, int n_streams, int context_overrid
     CU(cudaFuncSetAttribute(gemm_q4k_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemMax));
     if (int e = ensure_all_tiles(m)) return e;
     std::unique_ptr<msx_batch> b(new msx_batch);
-    b->m = m; b->n = n_streams;
+    b->m = m; b->n = n_streams; b->n_active = n_streams; b->prefill_of = prefill_of;
     const msx_config &c = m->cfg;
     const size_t n = (size_t)n_streams;
     b->cap = context_override > 0 ? std::min(context_override, c.context) : c.context;
     b->attn_split = attn_split_for(c.num_heads * n_streams, b->cap, m->num_sms);
     b->host_offset.assign(n_streams, 0);
-    CU(cudaStreamCreateWithFlags(&b->st, cudaStreamNonBlocking));
+    if (prefill_of) b->st = prefill_of->st;
+    else CU(cudaStreamCreateWithFlags(&b->st, cudaStreamNonBlocking));
     CU(cudaEventCreate(&b->ev0)); CU(cudaEventCreate(&b->ev1));
+    CU(cudaMallocHost((void **)&b->h_hdr, kCtrlInOffset * n));
     CU(cudaMallocHost((void **)&b->h_in, kCtrlInBytes * n));
     CU(cudaMallocHost((void **)&b->h_out, kCtrlOutBytes * n));
     if (int e = balloc(b.get(), (void **)&b->ctrl, sizeof(Ctrl) * n)) return e;
     const size_t kv = (size_t)c.num_layers * b->cap * c.dim;
-    if (int e = balloc(b.get(), (void **)&b->kc, kv * 2 * n)) return e;
-    if (int e = balloc(b.get(), (void **)&b->vc, kv * 2 * n)) return e;
+    if (!prefill_of) {
+        if (int e = balloc(b.get(), (void **)&b->kc, kv * 2 * n)) return e;
+        if (int e = balloc(b.get(), (void **)&b->vc, kv * 2 * n)) return e;
+    }
     if (int e = balloc(b.get(), (void **)&b->x, n * c.dim * 4)) return e;
     if (int e = balloc(b.get(), (void **)&b->qkv, n * c.dim * 3 * 4)) return e;
     if (int e = balloc(b.get(), (void **)&b->ctx, n * c.dim * 4)) return e;
@@ -240,7 +264,7 @@ extern "C" int msx_batch_create(msx_model *m, int n_streams, int context_overrid
     if (int e = balloc(b.get(), (void **)&b->text_logits, n * c.text_card * 4)) return e;
     if (int e = balloc(b.get(), (void **)&b->rope_cs, n * (c.dim / c.num_heads) * 4)) return e;
     int maxK = std::max(c.dim, m->hidden);
-    if (c.dep_q > 0) {
+    if (c.dep_q > 0 && !prefill_of) {
         const size_t dkv = (size_t)c.dep_layers * m->dep_cap * c.dep_dim;
         if (int e = balloc(b.get(), (void **)&b->dkc, dkv * 2 * n)) return e;
         if (int e = balloc(b.get(), (void **)&b->dvc, dkv * 2 * n)) return e;
@@ -259,10 +283,58 @@ extern "C" int msx_batch_create(msx_model *m, int n_streams, int context_overrid
     for (Ctrl &h : hc) { h.n_in = c.n_q + 1; h.text_override = INT32_MIN; for (int i = 0; i < 40; i++) h.force[i] = INT32_MIN; }
     CU(cudaMemcpy(b->ctrl, hc.data(), sizeof(Ctrl) * n, cudaMemcpyHostToDevice));
     if (int e = capture_b(b.get(), [&](BatchLauncher &B) { enqueue_temporal_b(B); }, &b->g_temporal, &b->launches_temporal)) return e;
-    if (c.dep_q > 0)
+    if (c.dep_q > 0 && !prefill_of)
         if (int e = capture_b(b.get(), [&](BatchLauncher &B) { enqueue_depformer_b(B); }, &b->g_depformer, &b->launches_depformer)) return e;
     CU(cudaStreamSynchronize(b->st));
     *out = b.release();
+    return 0;
+}
+
+// ---- batched-T prompt prefill -------------------------------------------------------------------------------------
+// Prompt frames (PersonaPlex voice / system prompt rows, lm.h:983-1134: all n_q+1 tokens given) only populate the
+// temporal KV rings — their logits, sampled tokens and depformer results are discarded by moshi_lmgen_step when the
+// tokens are "provided" (lm.h:933-943).  Eight consecutive positions are therefore run as the eight columns of the
+// tensor-core GEMM: every weight matrix is read once per 8 prompt frames instead of once per frame.
+extern "C" int msx_stream_prefill(msx_stream *s, const int32_t *tokens, int T) {
+    if (!s || !tokens || T <= 0) return fail(MSX_ERR_ARG, "bad argument");
+    msx_model *m = s->m; const msx_config &c = m->cfg;
+    if (m->tp_world > 1 || c.cross_attention || c.demux_second_stream) return fail(MSX_ERR_STATE, "prefill covers plain single-GPU models");
+    if (s->host_offset + T > s->cap) return fail(MSX_ERR_ARG, "prefill must not wrap the KV ring (offset + T <= context)");
+    CU(cudaSetDevice(m->device));
+    if (!s->prefill) {
+        msx_batch *pb = nullptr;
+        if (int e = batch_create_impl(m, kMmaCols, s->cap, s, &pb)) return e;
+        s->prefill = pb;
+    }
+    msx_batch *b = s->prefill;
+    const int n_in = c.n_q + 1;
+    for (int c0 = 0; c0 < T; c0 += b->n) {
+        const int nb = std::min(b->n, T - c0);
+        CU(cudaStreamSynchronize(b->st));            // the pinned staging buffers are reused per chunk
+        for (int j = 0; j < b->n; j++) {
+            Ctrl hdr; memset(&hdr, 0, sizeof(hdr));
+            hdr.offset = s->host_offset + c0 + std::min(j, nb - 1); hdr.n_in = n_in;
+            memcpy(b->h_hdr + (size_t)j * kCtrlInOffset, &hdr, kCtrlInOffset);
+        }
+        CU(cudaMemcpy2DAsync(b->ctrl, sizeof(Ctrl), b->h_hdr, kCtrlInOffset, kCtrlInOffset, b->n, cudaMemcpyHostToDevice, b->st));
+        std::vector<int32_t> tk((size_t)b->n * n_in, 0);
+        memcpy(tk.data(), tokens + (size_t)c0 * n_in, (size_t)nb * n_in * 4);
+        if (int e = push_inputs_b(b, tk.data())) return e;
+        if (nb == b->n) {
+            CU(cudaGraphLaunch(b->g_temporal, b->st));
+        } else {                                       // tail: exactly nb live columns, launched eagerly
+            Launcher L{b->st, m->num_sms};
+            BatchLauncher B{L, b};
+            b->n_active = nb;
+            enqueue_temporal_b(B);
+            b->n_active = b->n;
+            if (B.err) return B.err;
+            if (L.err != cudaSuccess) return fail(MSX_ERR_CUDA, std::string("prefill launch: ") + cudaGetErrorString(L.err));
+        }
+    }
+    s->host_offset += T;
+    CU(cudaMemcpyAsync(&s->ctrl->offset, &s->host_offset, 4, cudaMemcpyHostToDevice, s->st));
+    CU(cudaStreamSynchronize(s->st));
     return 0;
 }
 

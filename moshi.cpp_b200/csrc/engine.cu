@@ -659,6 +659,7 @@ int attn_split_for(int heads, int cap, int num_sms) {
 // -------------------------------------------------------------------------------------------------
 // stream
 // -------------------------------------------------------------------------------------------------
+static void free_prefill(struct msx_batch *b);
 struct msx_stream {
     msx_model *m = nullptr;
     int cap = 0;
@@ -688,6 +689,7 @@ struct msx_stream {
     TpCtx *d_tp = nullptr;           // device copy of the context
     std::vector<void *> tp_peer_maps;
     bool tp_p2p = false;
+    struct msx_batch *prefill = nullptr;   // batched-T prompt prefill context (batch.inl), created on first use
     bool embed_override_next = false;
     bool use_mma = false;            // Q4_K linears on the tensor-core unit kernel (MSX_MMA=1)
     int32_t *d_feed = nullptr;       // msx_run_resident_async
@@ -711,6 +713,7 @@ struct msx_stream {
 
     ~msx_stream() {
         if (m) cudaSetDevice(m->device);
+        if (prefill) free_prefill(prefill);
         if (g_temporal) cudaGraphExecDestroy(g_temporal);
         if (g_depformer) cudaGraphExecDestroy(g_depformer);
         if (nccl_comm) nccl().CommDestroy(nccl_comm);
@@ -1696,6 +1699,34 @@ extern "C" int msx_gen_set_cache(msx_gen *g, const int32_t *cache) {
 }
 extern "C" int msx_gen_cache_rows(const msx_gen *g) { return g ? g->CT : -1; }
 
+// T prompt frames with ALL n_q+1 tokens given, as one batched-T prefill: the host side of moshi_lmgen_step's "provided"
+// branch (ring writes lm.h:812-818, input gather 826-833, no output write-back 933-943, offset++) for every frame, then
+// msx_stream_prefill on the gathered inputs.  The libc rand() draws the per-frame sampler would have consumed are
+// consumed here too, so a sampled conversation continues with the reference's random sequence.
+extern "C" int msx_stream_prefill(msx_stream *s, const int32_t *tokens, int T);
+extern "C" int msx_gen_prefill(msx_gen *g, const int32_t *rows, int T) {
+    if (!g || !rows || T <= 0 || !g->s) return fail(MSX_ERR_ARG, "bad argument / callback generator");
+    const msx_config &c = g->cfg;
+    const int CT = g->CT, ncb = g->ncb;
+    if (g->s->host_offset + T > g->s->cap) return fail(MSX_ERR_ARG, "prefill must not wrap the KV ring");
+    std::vector<int32_t> inputs((size_t)T * ncb), cache = g->cache;
+    int offset = g->offset;
+    for (int f = 0; f < T; f++) {
+        for (int i = 0; i < ncb; i++) cache[(size_t)((offset + c.delays[i]) % CT) * ncb + i] = rows[(size_t)f * ncb + i];
+        const int pos = offset % CT;
+        for (int i = 0; i < ncb; i++) inputs[(size_t)f * ncb + i] = (offset <= c.delays[i]) ? g->initial[i] : cache[(size_t)pos * ncb + i];
+        offset++;
+    }
+    if (int e = msx_stream_prefill(g->s, inputs.data(), T)) return e;
+    g->cache.swap(cache); g->offset = offset;
+    if (g->s->temp_text > 0.f || g->s->temp_audio > 0.f) {
+        const int kt = std::min(std::min(g->s->top_k_text, c.text_card), kSampleMaxK), ka = std::min(std::min(g->s->top_k_audio, c.card), kSampleMaxK);
+        const long draws = (long)T * ((g->s->temp_text > 0.f ? kt : 0) + (g->s->temp_audio > 0.f ? (long)c.dep_q * ka : 0));
+        for (long i = 0; i < draws; i++) (void)rand();
+    }
+    return 0;
+}
+
 extern "C" int msx_gen_set_text_hook(msx_gen *g, msx_text_hook fn, void *user) {
     if (!g) return fail(MSX_ERR_ARG, "null generator");
     g->text_hook = fn; g->text_user = user;
@@ -1916,3 +1947,5 @@ extern "C" int msx_test_dequant_repacked(int device, int type, const void *w, in
 }
 
 #include "batch.inl"
+
+static void free_prefill(struct msx_batch *b) { delete b; }

@@ -351,7 +351,17 @@ static void personaplex_prompts(moshi_lm_gen_t *gen) {
     const int ncb = c.n_q + 1;
     if (ncb != 17) return;                                     // the reference's table has 17 entries
     int32_t row[MSX_MAX_CODEBOOKS], text, audio[MSX_MAX_STEPS];
-    auto step = [&]() { msx_gen_step(gen->gen, row, ncb, 0, &text, audio); };
+    // every prompt frame is a full token row: collect them all, then run them as ONE batched-T prefill (8 frames per
+    // weight pass); models / situations the prefill does not cover fall back to one decode step per frame like the reference
+    std::vector<int32_t> rows;
+    auto push_row = [&]() { rows.insert(rows.end(), row, row + ncb); };
+    auto flush = [&]() {
+        if (rows.empty()) return;
+        const int T = (int)(rows.size() / ncb);
+        if (msx_gen_prefill(gen->gen, rows.data(), T) != 0)
+            for (int f = 0; f < T; f++) msx_gen_step(gen->gen, rows.data() + (size_t)f * ncb, ncb, 0, &text, audio);
+        rows.clear();
+    };
     if (gen->prompt_rows > 0) {                                // embedding variant (lm.h:1005-1051)
         for (int i = 0; i < gen->prompt_rows; i++) msx_gen_prompt_embedding(gen->gen, gen->prompt_embeddings.data() + (size_t)i * c.dim);
         if (gen->prompt_cache_rows == msx_gen_cache_rows(gen->gen)) msx_gen_set_cache(gen->gen, gen->prompt_cache.data());
@@ -360,13 +370,14 @@ static void personaplex_prompts(moshi_lm_gen_t *gen) {
         for (int i = 0; i < ncb; i++) row[i] = PROMPT_TOKENS[i];
         const auto &codes = gen->prompt_audio.front();
         for (int j = 0; j < 8 && j < (int)codes.size(); j++) row[j + 1] = codes[j];
-        step();
+        push_row();
         gen->prompt_audio.pop_front();
     }
-    auto silence = [&](int n) { for (int f = 0; f < n; f++) { for (int i = 0; i < ncb; i++) row[i] = PROMPT_TOKENS[i]; step(); } };
+    auto silence = [&](int n) { for (int f = 0; f < n; f++) { for (int i = 0; i < ncb; i++) row[i] = PROMPT_TOKENS[i]; push_row(); } };
     silence(6);
-    for (int tok : gen->text_prompt_tokens) { for (int i = 0; i < ncb; i++) row[i] = PROMPT_TOKENS[i]; row[0] = tok; step(); }
+    for (int tok : gen->text_prompt_tokens) { for (int i = 0; i < ncb; i++) row[i] = PROMPT_TOKENS[i]; row[0] = tok; push_row(); }
     silence(6);
+    flush();
 }
 
 void moshi_lm_start(moshi_context_t *, moshi_lm_gen_t *gen, float depth_temperature, float text_temperature, bool) {

@@ -515,3 +515,54 @@ def test_voice_embedding_prompt_matches_oracle(msx, orc, gguf_for):
         assert np.array_equal(a_gpu, a_ref)
         toks = np.concatenate([[t_ref], a_ref, rng.integers(0, cfg["card"], size=cfg["n_q"] - cfg["dep_q"])]).astype(np.int32)
     assert gs.offset == 11 and os_.offset == 11
+
+
+@pytest.mark.parametrize("preset,T", [("tiny", 19), ("tiny_pplex", 8), ("moshi7b_l2", 11)])
+def test_batched_prefill_equals_serial_prompt_steps(msx, gguf_for, preset, T):
+    """T fully-given prompt frames run 8 positions at a time through the tensor-core GEMM leave the
+    same KV rings / position as T one-frame steps, so the conversation that follows is identical (bit for bit)."""
+    path, cfg = gguf_for(preset, "q4_k")
+    gm = msx.Model(path, cfg)
+    a, b = msx.Stream(gm), msx.Stream(gm)
+    rng = np.random.default_rng(31)
+    rows = rng.integers(0, cfg["card"], size=(T, cfg["n_q"] + 1)).astype(np.int32)
+    rows[:, 0] = rng.integers(0, cfg["text_card"], size=T)
+    rows[2, 3] = -1
+    a.prefill(rows)
+    for f in range(T):
+        b.step_temporal(rows[f], want_logits=False)
+    assert a.offset == b.offset == T
+    for layer in (0, cfg["num_layers"] - 1):
+        for head in (0, cfg["num_heads"] - 1):
+            for slot in (0, T // 2, T - 1):
+                ka, va = a.get_kv(layer, head, slot); kb, vb = b.get_kv(layer, head, slot)
+                assert np.array_equal(ka, kb) and np.array_equal(va, vb), f"KV row layer {layer} head {head} slot {slot}"
+    toks = rng.integers(0, cfg["card"], size=cfg["n_q"] + 1).astype(np.int32)
+    for f in range(4):
+        ta, la, _ = a.step_temporal(toks); tb, lb, _ = b.step_temporal(toks)
+        assert ta == tb and np.array_equal(la.view(np.uint32), lb.view(np.uint32)), f"frame {f} after the prompt"
+        xa, _ = a.step_depformer(ta); xb, _ = b.step_depformer(tb)
+        assert np.array_equal(xa, xb)
+        toks = np.concatenate([[ta], xa, rng.integers(0, cfg["card"], size=cfg["n_q"] - cfg["dep_q"])]).astype(np.int32)
+    # ring wrap is refused
+    with pytest.raises(msx.MsxError):
+        a.prefill(np.zeros((cfg["context"], cfg["n_q"] + 1), dtype=np.int32))
+
+
+def test_generator_prefill_equals_provided_steps(msx, gguf_for):
+    """msx_gen_prefill == the same rows through msx_gen_step with all 17 tokens provided (delay ring + model state)"""
+    path, cfg = gguf_for("tiny_pplex", "q4_k")
+    gm = msx.Model(path, cfg)
+    sa, sb = msx.Stream(gm), msx.Stream(gm)
+    ga, gb = msx.Gen(sa), msx.Gen(sb)
+    rng = np.random.default_rng(8)
+    rows = rng.integers(0, cfg["card"], size=(13, cfg["n_q"] + 1)).astype(np.int32)
+    ga.prefill(rows)
+    for f in range(13):
+        gb.step(rows[f])
+    assert ga.offset == gb.offset == 13
+    n_user = cfg["n_q"] - 8
+    for f in range(12):
+        user = rng.integers(0, cfg["card"], size=n_user).astype(np.int32)
+        ra, rb = ga.step(user), gb.step(user)
+        assert ra[0] == rb[0] and ra[1] == rb[1] and np.array_equal(ra[2], rb[2]), f"frame {f}"
