@@ -135,6 +135,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--streams", type=int, default=8,
                     help="also time a lock-step batch of this many streams per GPU (BASELINE config 5; q4_k only, 0 = skip)")
+    ap.add_argument("--tp", action="store_true",
+                    help="tensor-parallel: the N ranks serve ONE stream (BASELINE config 4; strong scaling, fused peer-memory all-reduce)")
+    ap.add_argument("--fill", type=int, default=0, help="--tp: frames replayed before timing (e.g. 3000 = full KV ring)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -180,6 +183,37 @@ def main():
 
     from moshi_cpp_b200 import binding as msx
     path = ensure_gguf(args.preset, args.quant, rank, world, barrier)
+    if args.tp and world > 1:
+        # ---- config 4: one stream sharded over all ranks ------------------------------------------------
+        ids = [msx.tp_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        model = msx.Model(path, cfg, device=local_rank, tp_rank=rank, tp_world=world)
+        stream = msx.Stream(model, nccl_id=ids[0])
+        hs = [None] * world
+        dist.all_gather_object(hs, stream.tp_export())
+        stream.tp_connect(hs)
+        K, W = args.steps, max(3, args.warmup)
+        if args.fill:
+            stream.run_resident(frames, args.fill)
+        stream.run_resident(frames, W)
+        sampler = ClockSampler(local_rank); barrier(); torch.cuda.synchronize(local_rank); sampler.start()
+        ms_res, _ = stream.run_resident(frames, K)
+        torch.cuda.synchronize(local_rank); barrier()
+        clocks = sampler.stop()
+        t = torch.tensor([ms_res], device=f"cuda:{local_rank}", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_res = float(t[0])
+        if rank == 0:
+            fps = K / (ms_res * 1e-3)
+            cfg4 = dict(base_cfg, workload=f"{args.preset} {args.quant} single stream, tensor-parallel over {world} GPUs (heads / hidden shards, "
+                        "fp64 partial sums, fused GEMV -> peer-memory all-reduce)", sharding=f"tensor parallel x{world}", kv_slots_at_timing=min(stream.offset, cfg["context"]))
+            print(json.dumps({"metric": "frames_per_s", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
+                              "ms_per_step": ms_res / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                              "dtype": "int8 dot / f32, f64 partial sums", "data": "synthetic", "config": cfg4,
+                              "realtime_factor": fps / FRAME_RATE, "gpu_launches": stream.launches_per_frame * K,
+                              "launches_per_frame": stream.launches_per_frame, "clocks": clocks}))
+        dist.destroy_process_group()
+        return 0
     t_load = time.perf_counter()
     model = msx.Model(path, cfg, device=local_rank)
     stream = msx.Stream(model)
