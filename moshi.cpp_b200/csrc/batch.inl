@@ -95,10 +95,21 @@ struct BatchLauncher {
         L.launch_pdl(quant_q8k_kernel, dim3(b->n_active, quant_parts_for(K)), dim3(kGemmThreads), 0, q);
         L.check();
     }
+    // y = W (norm?)(x): one launch with the fused prologue when the inner dimension is short, else quantise + GEMM
+    void linear(const float *x, int ld, const float *alpha, const QLinear &w, float *out, int out_ld, int epi, int family, int key_index = -1) {
+        if (fuse_small && gemm_can_fuse_quant(w.K, b->n_active)) {
+            gemm(w, out, out_ld, epi, family, key_index, nullptr, 0, nullptr, x, ld, alpha);
+        } else {
+            quant(x, ld, alpha, nullptr, 0, w.K, family);
+            gemm(w, out, out_ld, epi, family, key_index);
+        }
+    }
+    bool fuse_small = true;
     void gemm(const QLinear &w, float *out, int ld, int epi, int family, int key_index = -1, const EmbTable *emb = nullptr, int emb_step = 0,
-              const uint8_t *img = nullptr) {
+              const uint8_t *img = nullptr, const float *xsrc = nullptr, int xld = 0, const float *alpha = nullptr) {
         GemmArgs g;
         if (int e = tiles_of(b->m, w, &g.w)) { err = e; return; }
+        g.xsrc = xsrc; g.xld = xld; g.alpha = alpha; g.eps = 1e-8f;
         g.img = img ? img : b->img; g.out = out; g.ld = ld; g.nb = b->n_active; g.epi = epi; g.ctrl = b->ctrl; g.key_index = key_index; g.emb_step = emb_step;
         if (emb) g.emb = *emb;
         g.stages = gemm_stages_for(w.K);
@@ -114,8 +125,7 @@ void enqueue_layer_b(BatchLauncher &B, const LayerW &lw, int w, bool temporal, i
     const int cap = temporal ? b->cap : m->dep_cap;
     const int hidden = temporal ? m->hidden : m->dep_hidden;
     float *x = temporal ? b->x : b->dx, *qkv = temporal ? b->qkv : b->dqkv, *ctx = temporal ? b->ctx : b->dctx, *gate = temporal ? b->gate : b->dgate;
-    B.quant(x, dim, lw.norm1, nullptr, 0, dim, temporal ? FAM_IN_PROJ : FAM_DEP_IN_PROJ);
-    B.gemm(lw.in_proj[w], qkv, 3 * dim, EPI_STORE, temporal ? FAM_IN_PROJ : FAM_DEP_IN_PROJ);
+    B.linear(x, dim, lw.norm1, lw.in_proj[w], qkv, 3 * dim, EPI_STORE, temporal ? FAM_IN_PROJ : FAM_DEP_IN_PROJ);
     AttnArgs a;
     a.qkv = qkv; a.ctx = ctx; a.ctrl = b->ctrl; a.pos_const = pos_const; a.cap = cap; a.dim = dim;
     a.max_period = temporal ? c.max_period : c.dep_max_period;
@@ -137,12 +147,9 @@ void enqueue_layer_b(BatchLauncher &B, const LayerW &lw, int w, bool temporal, i
         B.L.check();
     }
     B.L.attn(a, heads, dim / heads, temporal ? b->attn_split : 1, temporal ? FAM_ATTN : FAM_DEP_ATTN, b->n_active);
-    B.quant(ctx, dim, nullptr, nullptr, 0, dim, temporal ? FAM_OUT_PROJ : FAM_DEP_OUT_PROJ);
-    B.gemm(lw.out_proj[w], x, dim, EPI_RESID, temporal ? FAM_OUT_PROJ : FAM_DEP_OUT_PROJ);
-    B.quant(x, dim, lw.norm2, nullptr, 0, dim, temporal ? FAM_LIN_IN : FAM_DEP_LIN_IN);
-    B.gemm(lw.lin_in[w], gate, hidden, EPI_GATE, temporal ? FAM_LIN_IN : FAM_DEP_LIN_IN);
-    B.quant(gate, hidden, nullptr, nullptr, 0, hidden, temporal ? FAM_LIN_OUT : FAM_DEP_LIN_OUT);
-    B.gemm(lw.lin_out[w], x, dim, EPI_RESID, temporal ? FAM_LIN_OUT : FAM_DEP_LIN_OUT);
+    B.linear(ctx, dim, nullptr, lw.out_proj[w], x, dim, EPI_RESID, temporal ? FAM_OUT_PROJ : FAM_DEP_OUT_PROJ);
+    B.linear(x, dim, lw.norm2, lw.lin_in[w], gate, hidden, EPI_GATE, temporal ? FAM_LIN_IN : FAM_DEP_LIN_IN);
+    B.linear(gate, hidden, nullptr, lw.lin_out[w], x, dim, EPI_RESID, temporal ? FAM_LIN_OUT : FAM_DEP_LIN_OUT);
 }
 
 void enqueue_temporal_b(BatchLauncher &B) {
@@ -173,8 +180,7 @@ void enqueue_depformer_b(BatchLauncher &B) {
         if (k == 0) B.quant(b->tout, c.dim, nullptr, nullptr, 0, c.dim, FAM_DEP_IN, b->img_tout);
         B.gemm(m->dep_in[w], b->dx, c.dep_dim, EPI_ADD_EMB, FAM_DEP_IN, -1, k == 0 ? &m->dep_text_emb : &m->dep_emb[k - 1], k, b->img_tout);
         for (int l = 0; l < c.dep_layers; l++) enqueue_layer_b(B, m->dep_layers[l], w, false, l, k);
-        B.quant(b->dx, c.dep_dim, nullptr, nullptr, 0, c.dep_dim, FAM_DEP_HEAD);
-        B.gemm(m->linears[k], b->audio_logits + (size_t)k * c.card, c.dep_q * c.card, EPI_ARGMAX, FAM_DEP_HEAD, k);
+        B.linear(b->dx, c.dep_dim, nullptr, m->linears[k], b->audio_logits + (size_t)k * c.card, c.dep_q * c.card, EPI_ARGMAX, FAM_DEP_HEAD, k);
     }
     L.fam = FAM_DEP_FINALIZE; L.begin();
     L.launch_pdl(finalize_depformer_kernel, dim3(b->n_active), dim3(64), 0, b->ctrl, (int)c.dep_q);

@@ -223,7 +223,14 @@ struct GemmArgs {
     int32_t emb_step = 0;             // EPI_ADD_EMB
     EmbTable emb;
     long long *stamps = nullptr;      // debug: [grid][8] globaltimer stamps
+    // fused activation prologue for short inner dimensions (K * nb <= 16384): every CTA normalises + quantises the nb
+    // columns itself instead of copying an image produced by a separate quant_q8k_kernel launch (one launch less in
+    // the depformer's dependent chain)
+    const float *xsrc = nullptr; int32_t xld = 0;
+    const float *alpha = nullptr; float eps = 0.f;
 };
+constexpr int kFusedMaxPairs = 4;     // (column, 256-block) pairs per warp in the fused prologue
+__host__ __device__ inline bool gemm_can_fuse_quant(int K, int nb) { return (K >> 8) * nb <= kGemmWarps * kFusedMaxPairs && K <= 1024; }
 
 __device__ __forceinline__ void mbar_init(uint32_t addr, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count) : "memory"); }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t addr, uint32_t bytes) {
@@ -285,6 +292,88 @@ __device__ __forceinline__ void unit_compute(const uint8_t *slot, const uint8_t 
     acc[1] = fma((double)__fmul_rn(dmg.x, dxv.y), (double)(lo[1] + (hi[1] >> 4)), acc[1]); acc[1] = fma(-(double)__fmul_rn(dmg.y, dxv.y), (double)mn[1], acc[1]);
     acc[2] = fma((double)__fmul_rn(dmh.x, dxv.x), (double)(lo[2] + (hi[2] >> 4)), acc[2]); acc[2] = fma(-(double)__fmul_rn(dmh.y, dxv.x), (double)mn[2], acc[2]);
     acc[3] = fma((double)__fmul_rn(dmh.x, dxv.y), (double)(lo[3] + (hi[3] >> 4)), acc[3]); acc[3] = fma(-(double)__fmul_rn(dmh.y, dxv.y), (double)mn[3], acc[3]);
+}
+
+// fused prologue: (column, block) pairs p = warp, warp + 16, ... ; same arithmetic and image layout as quant_q8k_kernel
+__device__ __forceinline__ void fused_quant_columns(const GemmArgs &a, uint8_t *img, double *sscratch, int warp, int lane) {
+    const int K = a.w.K, nblk = K >> 8, npairs = a.nb * nblk;
+    const bool norm = a.alpha != nullptr;
+    float v[kFusedMaxPairs][8], al[kFusedMaxPairs][8];
+    auto load8 = [&](const float *src, float (&d)[8]) {
+        const float4 p0 = __ldcg(reinterpret_cast<const float4 *>(src)), p1 = __ldcg(reinterpret_cast<const float4 *>(src + 4));
+        d[0] = p0.x; d[1] = p0.y; d[2] = p0.z; d[3] = p0.w; d[4] = p1.x; d[5] = p1.y; d[6] = p1.z; d[7] = p1.w;
+    };
+#pragma unroll
+    for (int j = 0; j < kFusedMaxPairs; j++) {
+        const int p = warp + j * kGemmWarps;
+        if (p < npairs) {
+            const int col = p / nblk, blk = p - col * nblk, e0 = blk * 256 + lane * 8;
+            load8(a.xsrc + (size_t)col * a.xld + e0, v[j]);
+            if (norm) load8(a.alpha + e0, al[j]);
+        }
+    }
+    if (norm) {
+#pragma unroll
+        for (int j = 0; j < kFusedMaxPairs; j++) {
+            const int p = warp + j * kGemmWarps;
+            if (p < npairs) {
+                double ss = 0.0;
+#pragma unroll
+                for (int i = 0; i < 8; i++) ss += (double)(v[j][i] * v[j][i]);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+                if (lane == 0) sscratch[p] = ss;
+            }
+        }
+        __syncthreads();
+    }
+    uint32_t *bsw = reinterpret_cast<uint32_t *>(img + (size_t)K * 8);
+    float *dx = reinterpret_cast<float *>(img + (size_t)K * 8 + (K >> 1));
+#pragma unroll
+    for (int j = 0; j < kFusedMaxPairs; j++) {
+        const int p = warp + j * kGemmWarps;
+        if (p >= npairs) continue;                          // warp-uniform
+        const int col = p / nblk, blk = p - col * nblk;
+        if (norm) {
+            double tot = 0.0;
+            for (int b = 0; b < nblk; b++) tot += sscratch[col * nblk + b];
+            const float mean = (K & (K - 1)) == 0 ? (float)scalbn(tot, -(31 - __clz(K))) : (float)(tot / K);
+            const float scale = 1.0f / sqrtf(mean + a.eps);
+#pragma unroll
+            for (int i = 0; i < 8; i++) v[j][i] = __fmul_rn(al[j][i], __fmul_rn(v[j][i], scale));
+        }
+        float amax = 0.f, mx = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; i++) { const float ax = fabsf(v[j][i]); if (ax > amax) { amax = ax; mx = v[j][i]; } }
+        const float wmax = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(amax)));
+        const unsigned hit = __ballot_sync(0xffffffffu, amax == wmax);
+        const float carrier = __shfl_sync(0xffffffffu, mx, __ffs(hit) - 1);
+        int q[8];
+        float d = 0.f;
+        if (wmax == 0.f) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) q[i] = 0;
+        } else {
+            const float iscale = -127.f / carrier;
+#pragma unroll
+            for (int i = 0; i < 8; i++) { const int t = __float2int_rn(iscale * v[j][i]); q[i] = t < 127 ? t : 127; }
+            d = 1.f / iscale;
+        }
+        int s = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) s += q[i];
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        const int s_next = __shfl_down_sync(0xffffffffu, s, 4);
+        const int sbk = lane >> 2, jj = lane & 3;
+        const int pr = 4 * blk + (sbk >> 1);
+        if ((lane & 7) == 0) bsw[(size_t)pr * 8 + col] = (uint32_t)(s & 0xffff) | ((uint32_t)(s_next & 0xffff) << 16);
+        if (lane == 0) dx[(size_t)blk * 8 + col] = d;
+        const uint2 pk = pack8(q);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(img + ((size_t)pr * 32 + col * 4) * 16) + (sbk & 1) * 2 + (jj >> 1);
+        dst[(2 * (jj & 1)) * 4] = pk.x;
+        dst[(2 * (jj & 1) + 1) * 4] = pk.y;
+    }
 }
 
 // Work schedule of one CTA.  The CTA owns a contiguous range of R tiles and walks it in "rounds": a round
@@ -360,13 +449,18 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_q4k_kernel(const GemmArg
     if (stamp && threadIdx.x == 0) stamp[1] = global_ns();
     griddep_wait();
     if (stamp && threadIdx.x == 0) stamp[2] = global_ns();
-    // activation image: 16 bulk copies (one per warp) so the L2 -> shared transfer is requested in parallel
-    if (threadIdx.x == 0) mbar_expect_tx(bar_u32, (uint32_t)img_sz);
-    if (lane == 0) {
-        const int piece = ((img_sz / kGemmWarps) + 15) & ~15;
-        const int off = warp * piece;
-        const int len = min(piece, img_sz - off);
-        if (len > 0) bulk_g2s((uint32_t)__cvta_generic_to_shared(img) + off, a.img + off, (uint32_t)len, bar_u32);
+    if (a.xsrc) {
+        fused_quant_columns(a, img, part, warp, lane);      // partial buffers double as the sum-of-squares scratch
+        __syncthreads();
+    } else {
+        // activation image: 16 bulk copies (one per warp) so the L2 -> shared transfer is requested in parallel
+        if (threadIdx.x == 0) mbar_expect_tx(bar_u32, (uint32_t)img_sz);
+        if (lane == 0) {
+            const int piece = ((img_sz / kGemmWarps) + 15) & ~15;
+            const int off = warp * piece;
+            const int len = min(piece, img_sz - off);
+            if (len > 0) bulk_g2s((uint32_t)__cvta_generic_to_shared(img) + off, a.img + off, (uint32_t)len, bar_u32);
+        }
     }
     // per-thread epilogue constants: as reducer this thread owns column 2t + (warp & 1)
     const int col = 2 * t + (warp & 1);
@@ -375,7 +469,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_q4k_kernel(const GemmArg
     int emb_token = 0;
     if (a.epi == EPI_ADD_EMB && col_live) emb_token = depformer_prev_token(a.ctrl + col, a.emb_step);
     unsigned long long best = 0ull;
-    mbar_wait(bar_u32, 0);
+    if (!a.xsrc) mbar_wait(bar_u32, 0);
     if (stamp && threadIdx.x == 0) stamp[3] = global_ns();
 
     WarpRound cr{t_begin, t_end - t_begin};
