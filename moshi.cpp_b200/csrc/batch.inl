@@ -166,7 +166,7 @@ void enqueue_temporal_b(BatchLauncher &B) {
     B.quant(b->x, c.dim, m->out_norm, b->tout, c.dim, c.dim, FAM_TEXT_HEAD);
     B.gemm(m->text_linear, b->text_logits, c.text_card, EPI_ARGMAX, FAM_TEXT_HEAD, -1);
     L.fam = FAM_FINALIZE; L.begin();
-    L.launch_pdl(finalize_temporal_kernel, dim3(b->n_active), dim3(32), 0, b->ctrl, c.dep_q > 0 ? 1 : 0);
+    L.launch_pdl(finalize_temporal_kernel, dim3(b->n_active), dim3(32), 0, b->ctrl, c.dep_q > 0 ? 1 : 0, (uint32_t *)nullptr);
     L.check();
 }
 

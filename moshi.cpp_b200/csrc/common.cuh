@@ -96,9 +96,15 @@ enum Epilogue : int {
 struct TpCtx {
     int32_t rank = 0, world = 1, dim = 0, pad = 0;
     uint4 *inbox[8] = {};         // inbox base of every rank (own entry = local pointer)
-    uint32_t *epoch = nullptr;    // local: number of completed reduces (seq of the running one = epoch + 1)
+    uint32_t *frame_ctr = nullptr;// local: temporal graphs completed (incremented by finalize_temporal_kernel); the sequence
+                                  // number of reduce i of a frame is frame_ctr * reduces_per_frame + i + 1: stable for the whole
+                                  // graph, so producers and consumers may read it at any time (no hand-over through a counter)
+    int32_t reduces_per_frame = 0, pad2 = 0;
     int32_t *error = nullptr;     // Ctrl::error (spin watchdog)
 };
+__device__ __forceinline__ uint32_t tp_seq(const TpCtx *tp, int idx) {
+    return *reinterpret_cast<const volatile uint32_t *>(tp->frame_ctr) * (uint32_t)tp->reduces_per_frame + (uint32_t)idx + 1u;
+}
 
 struct GemvArgs {
     QLinear w;
@@ -117,6 +123,7 @@ struct GemvArgs {
     const float *addvec = nullptr;  // EPI_ADD_VEC
     double *out_f64 = nullptr;      // EPI_STORE_F64
     const TpCtx *tp = nullptr;      // EPI_STORE_F64: push to the peers' inboxes instead (see TpCtx)
+    int32_t tp_idx = 0;             // which reduce of the frame this launch feeds
 };
 
 // warp index broadcast from lane 0: tells the compiler the value is warp-uniform, so loops and branches on it

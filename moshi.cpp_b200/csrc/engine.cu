@@ -687,6 +687,7 @@ struct msx_stream {
     // peer-memory all-reduce (msx_stream_tp_export / _connect): arena mapped by the peers through CUDA IPC
     uint8_t *tp_arena = nullptr;     // [inbox 2 x world x dim x {lo, seq, hi, seq} | epoch]
     TpCtx *d_tp = nullptr;           // device copy of the context
+    uint32_t *tp_frame_ctr = nullptr;
     std::vector<void *> tp_peer_maps;
     bool tp_p2p = false;
     struct msx_batch *prefill = nullptr;   // batched-T prompt prefill context (batch.inl), created on first use
@@ -755,11 +756,12 @@ void enqueue_layer(Launcher &L, const msx_stream *s, const LayerW &lw, int w, bo
     auto reduce_into_x = [&](GemvArgs &gg, int family) {
         if (s->tp_p2p) {
             // GEMV pushes its partial sums into every rank's inbox over NVLink; the consumer waits for the flags
-            gg.out_f64 = nullptr; gg.out = nullptr; gg.tp = s->d_tp;
+            const int idx = 2 * layer + (family == FAM_LIN_OUT ? 1 : 0);
+            gg.out_f64 = nullptr; gg.out = nullptr; gg.tp = s->d_tp; gg.tp_idx = idx;
             L.gemv(gg, PRO_PLAIN, EPI_STORE_F64, family);
             gg.tp = nullptr;
             L.fam = family; L.begin();
-            L.launch_pdl(tp_apply_p2p_kernel, dim3(1), dim3(1024), 0, x, (const TpCtx *)s->d_tp);
+            L.launch_pdl(tp_apply_p2p_kernel, dim3(1), dim3(1024), 0, x, (const TpCtx *)s->d_tp, idx);
             L.check();
             return;
         }
@@ -859,7 +861,7 @@ void enqueue_temporal(Launcher &L, const msx_stream *s) {
         L.check();
     }
     L.fam = FAM_FINALIZE;
-    L.launch_pdl(finalize_temporal_kernel, dim3(1), dim3(32), 0, s->ctrl, c.dep_q > 0 ? 1 : 0);
+    L.launch_pdl(finalize_temporal_kernel, dim3(1), dim3(32), 0, s->ctrl, c.dep_q > 0 ? 1 : 0, s->tp_p2p ? s->tp_frame_ctr : (uint32_t *)nullptr);
     L.check();
 }
 
@@ -1352,7 +1354,9 @@ extern "C" int msx_stream_tp_connect(msx_stream *s, const uint8_t *handles) {
         }
         h.inbox[r] = reinterpret_cast<uint4 *>(base);
     }
-    h.epoch = reinterpret_cast<uint32_t *>(s->tp_arena + inbox_bytes);
+    h.frame_ctr = reinterpret_cast<uint32_t *>(s->tp_arena + inbox_bytes);
+    h.reduces_per_frame = 2 * m->cfg.num_layers;
+    s->tp_frame_ctr = h.frame_ctr;
     h.error = &s->ctrl->error;
     if (!s->d_tp) if (int e = salloc(s, (void **)&s->d_tp, sizeof(TpCtx))) return e;
     CU(cudaMemcpy(s->d_tp, &h, sizeof(h), cudaMemcpyHostToDevice));

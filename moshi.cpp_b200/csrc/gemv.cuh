@@ -478,8 +478,8 @@ __device__ __forceinline__ void gemv_body(const GemvArgs &a, const float *x_over
     int emb_token = 0;
     if (EPI == EPI_ADD_EMB) emb_token = depformer_prev_token(a.ctrl, a.emb_step);
     unsigned long long best = 0ull;
-    uint32_t tp_epoch = 0, tp_parity = 0;
-    if (EPI == EPI_STORE_F64 && a.tp) { tp_epoch = __ldcg(a.tp->epoch); tp_parity = tp_epoch & 1u; }
+    uint32_t tp_epoch = 0, tp_parity = 0;      // tp_epoch + 1 = sequence number of this reduce
+    if (EPI == EPI_STORE_F64 && a.tp) { tp_epoch = tp_seq(a.tp, a.tp_idx) - 1u; tp_parity = (uint32_t)a.tp_idx & 1u; }
 
     double acc[kR];
 #pragma unroll

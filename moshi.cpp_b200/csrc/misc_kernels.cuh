@@ -75,7 +75,11 @@ __device__ __forceinline__ void finalize_temporal_body(Ctrl *c, int has_depforme
         }
     }
 }
-__global__ void finalize_temporal_kernel(Ctrl *c, int has_depformer) { griddep_launch(); griddep_wait(); finalize_temporal_body(c + blockIdx.x, has_depformer); }
+__global__ void finalize_temporal_kernel(Ctrl *c, int has_depformer, uint32_t *tp_frame_ctr = nullptr) {
+    griddep_launch(); griddep_wait();
+    finalize_temporal_body(c + blockIdx.x, has_depformer);
+    if (tp_frame_ctr && blockIdx.x == 0 && threadIdx.x == 0) *tp_frame_ctr += 1u;     // tensor parallel: next frame's sequence numbers
+}
 
 // end of the depformer graph: collect the dep_q greedy tokens (lm.h:548-552)
 // single warp does the whole job (dep_q <= 40: two passes of 32 lanes)
@@ -103,19 +107,19 @@ __global__ void tp_apply_kernel(float *x, const double *partial, int n) {
 }
 
 // peer-memory variant: poll the inbox entries (data and sequence number arrive together), add them in rank order
-// (identical on all ranks).  The epoch (which reduce this is) is only stable once the previous apply kernel has finished:
-// with chained programmatic launches this kernel can become resident several kernels early, so it waits first.
+// (identical on all ranks).  The sequence number depends only on the frame counter (stable for the whole temporal graph) and
+// on the launch's own reduce index, so the polling — which does not touch x — runs BEFORE the PDL wait and overlaps the tail
+// of the local GEMV; only the read-modify-write of x waits for the predecessor.
 __device__ __forceinline__ uint4 ld_volatile_v4(const uint4 *p) {
     uint4 v;
     asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
     return v;
 }
 constexpr int kTpApplyPer = 4;     // elements per thread (dim <= 4096 with 1024 threads)
-__global__ void __launch_bounds__(1024) tp_apply_p2p_kernel(float *x, const TpCtx *tp) {
+__global__ void __launch_bounds__(1024) tp_apply_p2p_kernel(float *x, const TpCtx *tp, int idx) {
     griddep_launch();
-    griddep_wait();
     const int world = tp->world, rank = tp->rank, dim = tp->dim;
-    const uint32_t e = *reinterpret_cast<const volatile uint32_t *>(tp->epoch), seq = e + 1u, parity = e & 1u;
+    const uint32_t seq = tp_seq(tp, idx), parity = (uint32_t)idx & 1u;
     const uint4 *in = tp->inbox[rank] + (size_t)parity * world * dim;
     double s[kTpApplyPer];
     long long t0 = 0; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
@@ -134,13 +138,12 @@ __global__ void __launch_bounds__(1024) tp_apply_p2p_kernel(float *x, const TpCt
             s[j] += __longlong_as_double((long long)(((unsigned long long)v.z << 32) | v.x));
         }
     }
+    griddep_wait();                  // x may still be read by the kernel before our predecessor
 #pragma unroll
     for (int j = 0; j < kTpApplyPer; j++) {
         const int i = threadIdx.x + j * blockDim.x;
         if (i < dim) x[i] = __ldcg(x + i) + (float)s[j];
     }
-    __syncthreads();
-    if (threadIdx.x == 0) *tp->epoch = e + 1u;
 }
 
 // ---- load-time repack (GGUF row-major blocks -> device tiles, see common.cuh QLinear) --------------
