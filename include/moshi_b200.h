@@ -123,6 +123,11 @@ MSX_API int msx_stream_set_noise(msx_stream *s, const float *noise_text, const f
  * the single-GPU numbers.  msx_tp_unique_id on one rank, ship the 128 bytes to the others (torch.distributed, MPI, a
  * file), then msx_stream_create_tp on every rank (collective).  NCCL is bound with dlopen("libnccl.so.2"). */
 MSX_API int msx_model_load_gguf_tp(const char *path, const msx_config *cfg, int device, int tp_rank, int tp_world, msx_model **out);
+/* the general loader: tensor-parallel shard (rank 0 of 1 = everything) and quantise-on-load.  quantize = 8 (GGML Q8_0):
+ * f32 / f16 / bf16 linears AND embedding tables of the file are quantised to Q8_0 on the GPU while loading, with ggml's
+ * quantize_row_q8_0 arithmetic (reference: moshi_lm_quantize "q8_0", src/moshi.cpp:654-673, src/loader.h:149-233);
+ * 0 = take the file as it is.  q4_k has no on-load quantiser here (quantize_row_q4_K is a search; files must be q4_k). */
+MSX_API int msx_model_load_gguf_ex(const char *path, const msx_config *cfg, int device, int tp_rank, int tp_world, int quantize, msx_model **out);
 MSX_API int msx_tp_unique_id(uint8_t *out128);
 MSX_API int msx_stream_create_tp(msx_model *model, int context_override, const uint8_t *nccl_id128, msx_stream **out);
 /* Fused GEMV -> all-reduce over peer memory (replaces the NCCL launches of a tensor-parallel stream): every rank exports

@@ -93,6 +93,7 @@ def lib():
     L.msx_model_free.argtypes = [vp]
     L.msx_model_load_gguf_tp.argtypes = [C.c_char_p, C.POINTER(MsxConfig), C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
     L.msx_tp_unique_id.argtypes = [vp]
+    L.msx_model_load_gguf_ex.argtypes = [C.c_char_p, C.POINTER(MsxConfig), C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
     L.msx_stream_create_tp.argtypes = [vp, C.c_int, vp, C.POINTER(vp)]
     L.msx_stream_tp_export.argtypes = [vp, vp]
     L.msx_stream_prefill.argtypes = [vp, vp, C.c_int]
@@ -195,12 +196,13 @@ def tp_unique_id() -> bytes:
 
 
 class Model:
-    def __init__(self, gguf_path: str, cfg: dict, device: int = 0, tp_rank: int = 0, tp_world: int = 1):
+    def __init__(self, gguf_path: str, cfg: dict, device: int = 0, tp_rank: int = 0, tp_world: int = 1, quantize: str | None = None):
         self.cfg = cfg
         self._c = make_config(cfg)
         self.tp_rank, self.tp_world = tp_rank, tp_world
         h = C.c_void_p()
-        _check(lib().msx_model_load_gguf_tp(gguf_path.encode(), C.byref(self._c), device, tp_rank, tp_world, C.byref(h)))
+        q = {None: 0, "q8_0": 8}[quantize]
+        _check(lib().msx_model_load_gguf_ex(gguf_path.encode(), C.byref(self._c), device, tp_rank, tp_world, q, C.byref(h)))
         self.h = h
 
     @property

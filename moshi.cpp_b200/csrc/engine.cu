@@ -102,6 +102,8 @@ struct msx_model {
     // hidden slice [f0, f1); everything else (embeddings, text head, depformer) is replicated
     int tp_rank = 0, tp_world = 1;
     int heads_local = 0, adim = 0, h0 = 0, f0 = 0, hidden_local = 0;
+    int quantize = 0;                 // T_Q8_0: f32 / f16 / bf16 tensors of the file are quantised to Q8_0 while loading
+    uint8_t *qstaging = nullptr; size_t qstaging_bytes = 0;
     std::vector<EmbTable> emb;        // [n_q+1]: text, audio 0..n_q-1
     EmbTable *d_emb = nullptr;        // device copy of `emb`
     EmbTable dep_text_emb;
@@ -128,6 +130,7 @@ struct msx_model {
         cudaSetDevice(device);
         for (void *p : allocs) cudaFree(p);
         if (staging) cudaFree(staging);
+        if (qstaging) cudaFree(qstaging);
     }
 };
 
@@ -149,15 +152,37 @@ int ensure_staging(msx_model *m, size_t bytes) {
     return 0;
 }
 
+// quantise-on-load (moshi_lm_quantize "q8_0" on an unquantised file): the float rows already sit in m->staging; on return
+// *blocks points at GGUF-format Q8_0 rows on the device
+int quantize_staging_q8_0(msx_model *m, int src_type, int64_t K, int64_t rows, const uint8_t **blocks) {
+    if (K % 32) return fail(MSX_ERR_FORMAT, "q8_0 needs K % 32 == 0");
+    const size_t need = (size_t)(K / 32) * 34 * rows;
+    if (need > m->qstaging_bytes) {
+        if (m->qstaging) cudaFree(m->qstaging);
+        m->qstaging = nullptr; m->qstaging_bytes = 0;
+        CU(cudaMalloc((void **)&m->qstaging, need));
+        m->qstaging_bytes = need;
+    }
+    const long long nblk = (long long)(K / 32) * rows;
+    quantize_rows_q8_0_kernel<<<(unsigned)((nblk * 32 + 255) / 256), 256>>>(m->staging, src_type, nblk, m->qstaging);
+    CU(cudaGetLastError());
+    *blocks = m->qstaging;
+    return 0;
+}
+bool is_float_type(int t) { return t == T_F32 || t == T_F16 || t == T_BF16; }
+
 // Upload a GGUF tensor [rows][K] and repack it into device tiles. perm_half: see repack kernels.
 int upload_linear(msx_model *m, const void *host, int type, int64_t K, int64_t rows, int perm_half, QLinear *out) {
-    if (type != T_Q4_K && type != T_Q8_0)
+    const bool on_load = m->quantize == T_Q8_0 && is_float_type(type);
+    if (type != T_Q4_K && type != T_Q8_0 && !on_load)
         return fail(MSX_ERR_FORMAT, std::string("linear weights must be q4_k or q8_0, got ") + ggml_type_name(type));
     const int64_t rs = ggml_row_size(type, K);
     if (rs < 0) return fail(MSX_ERR_FORMAT, "K is not a multiple of the block size");
     const size_t raw = (size_t)rs * rows;
     if (int e = ensure_staging(m, raw)) return e;
     CU(cudaMemcpy(m->staging, host, raw, cudaMemcpyHostToDevice));
+    const uint8_t *src_blocks = m->staging;
+    if (on_load) { if (int e = quantize_staging_q8_0(m, type, K, rows, &src_blocks)) return e; type = T_Q8_0; }
     QLinear w;
     w.type = type; w.K = (int)K; w.rows = (int)rows; w.gs = K >= 4096 ? 32 : 16; w.gate = perm_half > 0;
     void *qs = nullptr, *sc = nullptr, *dd = nullptr;
@@ -166,13 +191,13 @@ int upload_linear(msx_model *m, const void *host, int type, int64_t K, int64_t r
         if (int e = dev_alloc(m, &sc, (size_t)rows * (K / 64) * 4)) return e;
         if (int e = dev_alloc(m, &dd, (size_t)rows * (K / 256) * 4)) return e;
         const long long n = (long long)rows * (K / 64);
-        repack_q4k_kernel<<<(unsigned)((n + 255) / 256), 256>>>(m->staging, (uint8_t *)qs, (uint32_t *)sc, (uint32_t *)dd,
+        repack_q4k_kernel<<<(unsigned)((n + 255) / 256), 256>>>(src_blocks, (uint8_t *)qs, (uint32_t *)sc, (uint32_t *)dd,
                                                                 (int)rows, (int)K, w.gs, perm_half);
     } else {
         if (int e = dev_alloc(m, &qs, (size_t)rows * K)) return e;
         if (int e = dev_alloc(m, &dd, (size_t)rows * (K / 32) * 2)) return e;
         const long long n = (long long)rows * (K / 32);
-        repack_q8_0_kernel<<<(unsigned)((n + 255) / 256), 256>>>(m->staging, (uint8_t *)qs, (uint16_t *)dd, (int)rows, (int)K, w.gs, perm_half);
+        repack_q8_0_kernel<<<(unsigned)((n + 255) / 256), 256>>>(src_blocks, (uint8_t *)qs, (uint16_t *)dd, (int)rows, (int)K, w.gs, perm_half);
     }
     CU(cudaGetLastError());
     CU(cudaDeviceSynchronize());
@@ -182,10 +207,22 @@ int upload_linear(msx_model *m, const void *host, int type, int64_t K, int64_t r
 }
 
 int upload_table(msx_model *m, const void *host, int type, int64_t K, int64_t rows, EmbTable *out) {
-    const int64_t rs = ggml_row_size(type, K);
+    int64_t rs = ggml_row_size(type, K);
     if (rs < 0 || type == T_Q4_K)
         return fail(MSX_ERR_FORMAT, std::string("embedding table type not supported: ") + ggml_type_name(type));
     void *d = nullptr;
+    if (m->quantize == T_Q8_0 && is_float_type(type) && K % 32 == 0) {
+        // the reference quantises embedding tables with the model (lm_utils.h:131-147): float rows -> Q8_0 rows
+        if (int e = ensure_staging(m, (size_t)rs * rows)) return e;
+        CU(cudaMemcpy(m->staging, host, (size_t)rs * rows, cudaMemcpyHostToDevice));
+        const uint8_t *blocks = nullptr;
+        if (int e = quantize_staging_q8_0(m, type, K, rows, &blocks)) return e;
+        type = T_Q8_0; rs = ggml_row_size(type, K);
+        if (int e = dev_alloc(m, &d, (size_t)rs * rows)) return e;
+        CU(cudaMemcpy(d, blocks, (size_t)rs * rows, cudaMemcpyDeviceToDevice));
+        out->data = (const uint8_t *)d; out->type = type; out->K = (int)K; out->rows = (int)rows; out->row_bytes = (int)rs;
+        return 0;
+    }
     if (int e = dev_alloc(m, &d, (size_t)rs * rows)) return e;
     CU(cudaMemcpy(d, host, (size_t)rs * rows, cudaMemcpyHostToDevice));
     out->data = (const uint8_t *)d; out->type = type; out->K = (int)K; out->rows = (int)rows; out->row_bytes = (int)rs;
@@ -209,7 +246,7 @@ struct Loader {
         if ((K > 0 && t->ne[0] != K) || (rows > 0 && t->ne[1] != rows))
             return fail(MSX_ERR_FORMAT, "shape mismatch for " + name + ": got [" + std::to_string(t->ne[0]) + "," +
                                             std::to_string(t->ne[1]) + "], want [" + std::to_string(K) + "," + std::to_string(rows) + "]");
-        linear_bytes = t->nbytes;
+        linear_bytes = (m->quantize == T_Q8_0 && is_float_type(t->type)) ? t->ne[1] * (t->ne[0] / 32 * 34) : t->nbytes;
         return upload_linear(m, t->data, t->type, t->ne[0], t->ne[1], perm_half, out);
     }
     // tensor-parallel shard of a linear: the listed row ranges (concatenated) x the K-slice [k0, k1) of every row
@@ -276,7 +313,14 @@ extern "C" int msx_model_load_gguf(const char *path, const msx_config *cfg, int 
 }
 
 extern "C" int msx_model_load_gguf_tp(const char *path, const msx_config *cfg, int device, int tp_rank, int tp_world, msx_model **out) {
+    return msx_model_load_gguf_ex(path, cfg, device, tp_rank, tp_world, 0, out);
+}
+
+extern "C" int msx_model_load_gguf_ex(const char *path, const msx_config *cfg, int device, int tp_rank, int tp_world, int quantize,
+                                      msx_model **out) {
     if (!path || !out) return fail(MSX_ERR_ARG, "null argument");
+    if (quantize != 0 && quantize != T_Q8_0) return fail(MSX_ERR_ARG, "quantise-on-load supports q8_0 (8) only; q4_k files must be quantised beforehand");
+    if (quantize && tp_world > 1) return fail(MSX_ERR_ARG, "quantise-on-load is not combined with tensor-parallel shards");
     *out = nullptr;
     if (int e = check_config(cfg)) return e;
     if (tp_world < 1 || tp_rank < 0 || tp_rank >= tp_world) return fail(MSX_ERR_ARG, "bad tensor-parallel rank / world");
@@ -305,7 +349,7 @@ extern "C" int msx_model_load_gguf_tp(const char *path, const msx_config *cfg, i
     Loader L{m.get(), f};
     const int d = c.dim;
     const int Dh = d / c.num_heads;
-    m->tp_rank = tp_rank; m->tp_world = tp_world;
+    m->tp_rank = tp_rank; m->tp_world = tp_world; m->quantize = quantize;
     m->heads_local = c.num_heads / tp_world; m->h0 = tp_rank * m->heads_local; m->adim = m->heads_local * Dh;
 
     // embeddings (lm.h:386-391)
@@ -403,7 +447,8 @@ extern "C" int msx_model_load_gguf_tp(const char *path, const msx_config *cfg, i
         auto small = [&](const std::string &name, EmbTable *out) -> int {
             const GgufTensor *t = L.need(name);
             if (!t) return MSX_ERR_FORMAT;
-            if (t->type != T_Q4_0 && t->type != T_Q8_0) return fail(MSX_ERR_FORMAT, name + ": small projections must be q4_0 or q8_0");
+            if (t->type != T_Q4_0 && t->type != T_Q8_0 && !(m->quantize && is_float_type(t->type)))
+                return fail(MSX_ERR_FORMAT, name + ": small projections must be q4_0 or q8_0");
             return L.table(name, de, dd, out);
         };
         if (int e = L.table("lm.depformer_text_emb.weight", de, c.text_card + 1, &m->dep_text_emb)) return e;
@@ -474,6 +519,7 @@ extern "C" int msx_model_load_gguf_tp(const char *path, const msx_config *cfg, i
     if (c.dep_q > 0)
         if (int e = make_freq(c.dep_dim / c.dep_heads, c.dep_max_period, &m->dep_rope_freq)) return e;
     if (m->staging) { cudaFree(m->staging); m->staging = nullptr; m->staging_bytes = 0; }
+    if (m->qstaging) { cudaFree(m->qstaging); m->qstaging = nullptr; m->qstaging_bytes = 0; }
     *out = m.release();
     return 0;
 }

@@ -146,6 +146,27 @@ __global__ void __launch_bounds__(1024) tp_apply_p2p_kernel(float *x, const TpCt
     }
 }
 
+// ---- quantise-on-load: f32 / f16 / bf16 rows -> GGUF Q8_0 blocks (ggml quantize_row_q8_0_ref: d = amax / 127, id = 1 / d,
+// q = roundf(x * id), d stored as fp16).  One warp per 32-element block; the blocks then go through the normal repack.
+// Reference: src/loader.h:149-233 (quantise while loading), ggml_cast in transformer.h:807.
+__global__ void quantize_rows_q8_0_kernel(const uint8_t *src, int src_type, long long n_blocks, uint8_t *dst) {
+    const long long b = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (b >= n_blocks) return;
+    const long long e = b * 32 + lane;
+    float x;
+    if (src_type == 0) x = reinterpret_cast<const float *>(src)[e];
+    else if (src_type == 1) x = __half2float(reinterpret_cast<const __half *>(src)[e]);
+    else x = bf16_bits_to_f32(reinterpret_cast<const uint16_t *>(src)[e]);
+    const float amax = warp_max(fabsf(x));
+    const float d = amax / 127.f;
+    const float id = d ? 1.0f / d : 0.0f;
+    const int q = (int)roundf(x * id);
+    uint8_t *blk = dst + b * 34;
+    if (lane == 0) *reinterpret_cast<__half *>(blk) = __float2half_rn(d);
+    reinterpret_cast<int8_t *>(blk + 2)[lane] = (int8_t)q;
+}
+
 // ---- load-time repack (GGUF row-major blocks -> device tiles, see common.cuh QLinear) --------------
 // perm_half > 0 interleaves rows for the gated MLP: stored row v <- source row (v&1 ? perm_half + v/2 : v/2)
 __device__ __forceinline__ int src_row_of(int v, int perm_half) { return perm_half > 0 ? ((v & 1) ? perm_half + (v >> 1) : (v >> 1)) : v; }

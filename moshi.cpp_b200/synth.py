@@ -82,7 +82,7 @@ def random_tensor(rng, gtype: int, rows: int, k: int, std: float) -> np.ndarray:
         return random_q8_0(rng, rows, k, std)
     if gtype == GGML_Q4_0:
         return random_q4_0(rng, rows, k, std)
-    x = (rng.standard_normal(size=(rows, k), dtype=np.float32) * std)
+    x = (rng.standard_normal(size=(rows, k), dtype=np.float32) * np.float32(std)).astype(np.float32)
     if gtype == GGML_F32:
         return x.view(np.uint8).reshape(rows, -1)
     if gtype == GGML_F16:
@@ -213,6 +213,33 @@ def write_gguf(path: str, cfg: dict, quant: str = "q4_k", seed: int = 1234) -> d
     with open(path + ".json", "w") as f:
         json.dump({"preset": cfg, "config": configs.to_config_json(cfg), "quant": quant, "seed": seed}, f)
     return {"bytes": len(hdr) + offs, "tensors": len(man)}
+
+
+def write_gguf_tensors(path: str, tensors) -> None:
+    """Write a GGUF v3 file from explicit data: tensors = [(name, gtype, k, rows, uint8 array of rows*row_bytes)] (rows == 1 and
+    F32 -> 1-D tensor like the norm vectors).  Used to build a quantised twin of an unquantised model in the tests."""
+    infos, offs = [], 0
+    for name, gtype, k, rows, data in tensors:
+        nbytes = row_bytes(gtype, k) * rows
+        assert data.size == nbytes, (name, data.size, nbytes)
+        infos.append((name, gtype, k, rows, offs, nbytes))
+        offs += (nbytes + ALIGN - 1) // ALIGN * ALIGN
+    hdr = bytearray()
+    hdr += struct.pack("<IIQQ", 0x46554747, 3, len(tensors), 0)
+    for name, gtype, k, rows, off, _ in infos:
+        nb = name.encode()
+        hdr += struct.pack("<Q", len(nb)) + nb
+        if rows == 1 and gtype == GGML_F32:
+            hdr += struct.pack("<IQ", 1, k)
+        else:
+            hdr += struct.pack("<IQQ", 2, k, rows)
+        hdr += struct.pack("<IQ", gtype, off)
+    hdr += b"\0" * ((-len(hdr)) % ALIGN)
+    with open(path, "wb") as f:
+        f.write(hdr)
+        for (_, _, _, _, data), (_, _, _, _, _, nbytes) in zip(tensors, infos):
+            f.write(np.ascontiguousarray(data).tobytes())
+            f.write(b"\0" * ((-nbytes) % ALIGN))
 
 
 def cached_gguf(preset: str, quant: str = "q4_k", seed: int = 1234, root: str | None = None) -> str:

@@ -566,3 +566,54 @@ def test_generator_prefill_equals_provided_steps(msx, gguf_for):
         user = rng.integers(0, cfg["card"], size=n_user).astype(np.int32)
         ra, rb = ga.step(user), gb.step(user)
         assert ra[0] == rb[0] and ra[1] == rb[1] and np.array_equal(ra[2], rb[2]), f"frame {f}"
+
+
+@pytest.mark.parametrize("preset,src", [("tiny", "bf16"), ("tiny_stt", "f16"), ("tiny_lowrank", "bf16")])
+def test_quantize_on_load_q8_0(msx, orc, preset, src, tmp_path):
+    """SURVEY.md §8f rank 3 (q8_0 half): an unquantised GGUF loaded with quantize="q8_0" (GPU quantize_row_q8_0 of every linear
+    and embedding table) == the same weights quantised offline with gguf-py (ggml's own Q8_0 quantiser, pinned in
+    tests/test_oracle_pins.py) and run through the oracle."""
+    import gguf
+    from moshi_cpp_b200 import configs, synth
+    cfg = configs.get(preset)
+    fp = str(tmp_path / f"{preset}-{src}.gguf")
+    synth.write_gguf(fp, cfg, src, seed=77)
+    rd = gguf.GGUFReader(fp)
+    twin = []
+    for t in rd.tensors:
+        k = int(t.shape[0]); rows = int(t.shape[1]) if len(t.shape) > 1 else 1
+        gt = int(t.tensor_type)
+        raw = np.ascontiguousarray(t.data).view(np.uint8).reshape(-1)
+        if gt in (synth.GGML_BF16, synth.GGML_F16) or (gt == synth.GGML_F32 and rows > 1):
+            if gt == synth.GGML_BF16:
+                f32 = (raw.view(np.uint16).astype(np.uint32) << 16).view(np.float32)
+            elif gt == synth.GGML_F16:
+                f32 = raw.view(np.float16).astype(np.float32)
+            else:
+                f32 = raw.view(np.float32)
+            q = gguf.quants.quantize(f32.reshape(rows, k), gguf.GGMLQuantizationType.Q8_0)
+            twin.append((t.name, synth.GGML_Q8_0, k, rows, np.ascontiguousarray(q).view(np.uint8).reshape(-1)))
+        else:
+            twin.append((t.name, gt, k, rows, raw))
+    qp = str(tmp_path / f"{preset}-q8_0-twin.gguf")
+    synth.write_gguf_tensors(qp, twin)
+    gm = msx.Model(fp, cfg, quantize="q8_0"); gs = msx.Stream(gm)
+    g2 = msx.Stream(msx.Model(qp, cfg))                     # the offline-quantised twin through the GPU path too
+    om = orc.Model(qp, cfg); os_ = orc.State(om)
+    assert gm.weight_bytes_per_frame == msx.Model(qp, cfg).weight_bytes_per_frame
+    rng = np.random.default_rng(4)
+    toks = np.array([cfg["text_card"]] + [cfg["card"]] * cfg["n_q"], dtype=np.int32)
+    for f in range(8):
+        t_ref, lg_ref, _ = os_.step_temporal(toks)
+        t_gpu, lg_gpu, _ = gs.step_temporal(toks)
+        t_g2, lg_g2, _ = g2.step_temporal(toks)
+        assert np.array_equal(lg_gpu.view(np.uint32), lg_g2.view(np.uint32)), f"frame {f}: on-load quantisation != offline Q8_0 file"
+        assert max_rel(lg_gpu, lg_ref) < LOGIT_TOL and t_gpu == t_ref, f"frame {f}"
+        nxt = [t_ref]
+        if cfg["dep_q"] > 0:
+            a_ref, al_ref = os_.step_depformer(t_ref)
+            a_gpu, al_gpu = gs.step_depformer(t_ref, force=a_ref)
+            g2.step_depformer(t_ref, force=a_ref)
+            assert max_rel(al_gpu, al_ref) < LOGIT_TOL
+            nxt += list(a_ref)
+        toks = np.array(nxt + list(rng.integers(0, cfg["card"], size=cfg["n_q"] + 1 - len(nxt))), dtype=np.int32)
