@@ -298,7 +298,7 @@ def main():
 
     # ---- batched streams (config 5): n conversations per GPU, weights read once per frame for all -------------
     batched = None
-    if args.streams > 1 and args.quant == "q4_k":
+    if args.streams > 1 and args.quant in ("q4_k", "q8_0"):
         nb = min(8, args.streams)
         t_b = time.perf_counter()
         batch = msx.Batch(model, nb)
@@ -326,7 +326,7 @@ def main():
             t = torch.tensor([ms_b, ms_be], device=f"cuda:{local_rank}", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms_b, ms_be = float(t[0]), float(t[1])
-        gemm_us = msx.bench_gemm_batch(raw, cfg["dim"], nb, 8, 200, 2, False, device=local_rank) if args.quant == "q4_k" else None
+        gemm_us = msx.bench_gemm_batch(raw, cfg["dim"], nb, 8, 200, 2, False, device=local_rank) if args.quant == "q4_k" else None   # (micro-benchmark hook is q4_k only)
         b_bytes = w_bytes + 0.5 * (bkv0 + bkv1)
         batched = {
             "workload": f"{args.preset} {args.quant}, {nb} independent streams per GPU stepped as one batch (BASELINE.json config 5)",

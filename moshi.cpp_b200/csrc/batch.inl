@@ -57,13 +57,19 @@ int balloc(msx_batch *b, void **p, size_t bytes) {
 int tiles_of(msx_model *m, const QLinear &w, QTiles *out) {
     auto it = m->tiles.find(w.qs);
     if (it != m->tiles.end()) { *out = it->second; return 0; }
-    if (w.type != T_Q4_K) return fail(MSX_ERR_ARG, "batched streams need q4_k linear weights");
+    if (w.type != T_Q4_K && w.type != T_Q8_0) return fail(MSX_ERR_ARG, "batched streams need q4_k or q8_0 linear weights");
+    if (w.type == T_Q8_0 && (w.K % 128)) return fail(MSX_ERR_ARG, "batched q8_0 streams need K % 128 == 0");
     QTiles t;
-    t.K = w.K; t.rows = w.rows; t.nsb = w.K >> 8; t.n_tiles = (w.rows + 15) / 16;
+    t.type = w.type; t.K = w.K; t.rows = w.rows; t.nsb = w.K / unit_weights_of(w.type); t.n_tiles = (w.rows + 15) / 16;
     void *u = nullptr;
-    if (int e = dev_alloc(m, &u, (size_t)t.n_tiles * t.nsb * kUnitBytes)) return e;
-    const long long n = (long long)t.n_tiles * t.nsb * 148;
-    tile_q4k_kernel<<<(unsigned)((n + 255) / 256), 256>>>(w, w.gate, (uint8_t *)u, t.n_tiles);
+    if (int e = dev_alloc(m, &u, (size_t)t.n_tiles * t.nsb * unit_bytes_of(w.type))) return e;
+    if (w.type == T_Q4_K) {
+        const long long n = (long long)t.n_tiles * t.nsb * 148;
+        tile_q4k_kernel<<<(unsigned)((n + 255) / 256), 256>>>(w, w.gate, (uint8_t *)u, t.n_tiles);
+    } else {
+        const long long n = (long long)t.n_tiles * t.nsb * 136;
+        tile_q8_0_kernel<<<(unsigned)((n + 255) / 256), 256>>>(w, w.gate, (uint8_t *)u, t.n_tiles);
+    }
     CU(cudaGetLastError());
     t.units = (const uint8_t *)u;
     m->tiles[w.qs] = t;
@@ -89,15 +95,17 @@ struct BatchLauncher {
     int err = 0;
 
     void quant(const float *x, int ld, const float *alpha, float *norm_out, int norm_ld, int K, int family, uint8_t *img = nullptr) {
+        const int wt = b->m->text_linear.type;          // a model is q4_k or q8_0 throughout
         QuantArgs q;
         q.x = x; q.ld = ld; q.alpha = alpha; q.eps = 1e-8f; q.norm_out = norm_out; q.norm_ld = norm_ld; q.img = img ? img : b->img; q.K = K;
         L.fam = family; L.begin();
-        L.launch_pdl(quant_q8k_kernel, dim3(b->n_active, quant_parts_for(K)), dim3(kGemmThreads), 0, q);
+        if (wt == T_Q4_K) L.launch_pdl(quant_q8k_kernel, dim3(b->n_active, quant_parts_for(K)), dim3(kGemmThreads), 0, q);
+        else L.launch_pdl(quant_q8_0_kernel, dim3(b->n_active, quant_parts_for(K)), dim3(kGemmThreads), 0, q);
         L.check();
     }
     // y = W (norm?)(x): one launch with the fused prologue when the inner dimension is short, else quantise + GEMM
     void linear(const float *x, int ld, const float *alpha, const QLinear &w, float *out, int out_ld, int epi, int family, int key_index = -1) {
-        if (fuse_small && gemm_can_fuse_quant(w.K, b->n_active)) {
+        if (fuse_small && w.type == T_Q4_K && gemm_can_fuse_quant(w.K, b->n_active)) {
             gemm(w, out, out_ld, epi, family, key_index, nullptr, 0, nullptr, x, ld, alpha);
         } else {
             quant(x, ld, alpha, nullptr, 0, w.K, family);
@@ -112,9 +120,10 @@ struct BatchLauncher {
         g.xsrc = xsrc; g.xld = xld; g.alpha = alpha; g.eps = 1e-8f;
         g.img = img ? img : b->img; g.out = out; g.ld = ld; g.nb = b->n_active; g.epi = epi; g.ctrl = b->ctrl; g.key_index = key_index; g.emb_step = emb_step;
         if (emb) g.emb = *emb;
-        g.stages = gemm_stages_for(w.K);
+        g.stages = gemm_stages_for(w.K, w.type);
         L.fam = family; L.begin();
-        L.launch_pdl(gemm_q4k_kernel, dim3(gemm_grid_for(g.w.n_tiles, L.num_sms)), dim3(kGemmThreads), (size_t)gemm_smem_bytes(w.K, g.stages), g);
+        if (w.type == T_Q4_K) L.launch_pdl(gemm_q4k_kernel, dim3(gemm_grid_for(g.w.n_tiles, L.num_sms)), dim3(kGemmThreads), (size_t)gemm_smem_bytes(w.K, g.stages, 12), g);
+        else L.launch_pdl(gemm_q8_0_kernel, dim3(gemm_grid_for(g.w.n_tiles, L.num_sms)), dim3(kGemmThreads), (size_t)gemm_smem_bytes(w.K, g.stages, 8), g);
         L.check();
     }
 };
@@ -242,6 +251,7 @@ static int batch_create_impl(msx_model *m, int n_streams, int context_override, 
     CU(cudaSetDevice(m->device));
     if (int e = set_smem_attrs()) return e;
     CU(cudaFuncSetAttribute(gemm_q4k_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemMax));
+    CU(cudaFuncSetAttribute(gemm_q8_0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemMax));
     if (int e = ensure_all_tiles(m)) return e;
     std::unique_ptr<msx_batch> b(new msx_batch);
     b->m = m; b->n = n_streams; b->n_active = n_streams; b->prefill_of = prefill_of;
@@ -281,9 +291,10 @@ static int batch_create_impl(msx_model *m, int n_streams, int context_override, 
         if (int e = balloc(b.get(), (void **)&b->audio_logits, n * c.dep_q * c.card * 4)) return e;
         maxK = std::max(maxK, std::max(c.dep_dim, m->dep_hidden));
     }
-    if (gemm_stages_for(maxK) < 2) return fail(MSX_ERR_ARG, "inner dimension too large for the batched GEMM's shared-memory image");
-    if (int e = balloc(b.get(), (void **)&b->img, (size_t)act_image_bytes(maxK))) return e;
-    if (int e = balloc(b.get(), (void **)&b->img_tout, (size_t)act_image_bytes(c.dim))) return e;
+    const int wt = m->text_linear.type;
+    if (gemm_stages_for(maxK, wt) < 2) return fail(MSX_ERR_ARG, "inner dimension too large for the batched GEMM's shared-memory image");
+    if (int e = balloc(b.get(), (void **)&b->img, (size_t)act_image_bytes(maxK, wt))) return e;
+    if (int e = balloc(b.get(), (void **)&b->img_tout, (size_t)act_image_bytes(c.dim, wt))) return e;
     std::vector<Ctrl> hc(n_streams);
     memset(hc.data(), 0, sizeof(Ctrl) * n);
     for (Ctrl &h : hc) { h.n_in = c.n_q + 1; h.text_override = INT32_MIN; for (int i = 0; i < 40; i++) h.force[i] = INT32_MIN; }
@@ -482,12 +493,13 @@ extern "C" int msx_test_gemm_batch(int device, int type, const void *w, int64_t 
     if (int e = upload_linear(m.get(), w, type, k, rows, 0, &ql)) return e;
     QTiles qt;
     if (int e = tiles_of(m.get(), ql, &qt)) return e;
-    if (gemm_stages_for((int)k) < 2) return fail(MSX_ERR_ARG, "k too large");
+    CU(cudaFuncSetAttribute(gemm_q8_0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemMax));
+    if (gemm_stages_for((int)k, type) < 2) return fail(MSX_ERR_ARG, "k too large");
     float *dx = nullptr, *dy = nullptr, *da = nullptr; uint8_t *img = nullptr;
     if (int e = dev_alloc(m.get(), (void **)&dx, (size_t)nb * k * 4)) return e;
     if (int e = dev_alloc(m.get(), (void **)&dy, (size_t)nb * rows * 4)) return e;
-    if (int e = dev_alloc(m.get(), (void **)&img, (size_t)act_image_bytes((int)k))) return e;
-    CU(cudaMemset(img, 0xff, (size_t)act_image_bytes((int)k)));      // dead columns hold garbage in production too
+    if (int e = dev_alloc(m.get(), (void **)&img, (size_t)act_image_bytes((int)k, type))) return e;
+    CU(cudaMemset(img, 0xff, (size_t)act_image_bytes((int)k, type)));      // dead columns hold garbage in production too
     CU(cudaMemcpy(dx, x, (size_t)nb * k * 4, cudaMemcpyHostToDevice));
     if (alpha) {
         if (int e = dev_alloc(m.get(), (void **)&da, (size_t)k * 4)) return e;
@@ -495,11 +507,13 @@ extern "C" int msx_test_gemm_batch(int device, int type, const void *w, int64_t 
     }
     QuantArgs q;
     q.x = dx; q.ld = (int)k; q.alpha = da; q.eps = 1e-8f; q.img = img; q.K = (int)k;
-    quant_q8k_kernel<<<dim3(nb, quant_parts_for((int)k)), kGemmThreads>>>(q);
+    if (type == T_Q4_K) quant_q8k_kernel<<<dim3(nb, quant_parts_for((int)k)), kGemmThreads>>>(q);
+    else quant_q8_0_kernel<<<dim3(nb, quant_parts_for((int)k)), kGemmThreads>>>(q);
     GemmArgs g;
     g.w = qt; g.img = img; g.out = dy; g.ld = (int)rows; g.nb = nb; g.epi = EPI_STORE;
-    g.stages = gemm_stages_for((int)k);
-    gemm_q4k_kernel<<<gemm_grid_for(qt.n_tiles, m->num_sms), kGemmThreads, gemm_smem_bytes((int)k, g.stages)>>>(g);
+    g.stages = gemm_stages_for((int)k, type);
+    if (type == T_Q4_K) gemm_q4k_kernel<<<gemm_grid_for(qt.n_tiles, m->num_sms), kGemmThreads, gemm_smem_bytes((int)k, g.stages, 12)>>>(g);
+    else gemm_q8_0_kernel<<<gemm_grid_for(qt.n_tiles, m->num_sms), kGemmThreads, gemm_smem_bytes((int)k, g.stages, 8)>>>(g);
     CU(cudaGetLastError());
     CU(cudaDeviceSynchronize());
     CU(cudaMemcpy(y, dy, (size_t)nb * rows * 4, cudaMemcpyDeviceToHost));

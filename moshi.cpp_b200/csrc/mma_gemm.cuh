@@ -37,21 +37,28 @@ constexpr int kGemmSmemMax = 227 * 1024;
 
 struct QTiles {
     const uint8_t *units = nullptr;
-    int32_t K = 0, rows = 0, n_tiles = 0, nsb = 0;
+    int32_t K = 0, rows = 0, n_tiles = 0, nsb = 0;   // nsb = units per tile row (K / 256 for Q4_K, K / 128 for Q8_0)
+    int32_t type = 12;
 };
+// Q8_0 units: 16 rows x 128 weights (4 blocks of 32) = [4 blocks][32 lanes] 16 B of int8 in A-fragment order
+// {row g: k-word t, row g+8: k-word t, row g: k-word 4+t, row g+8: k-word 4+t} + [16 rows][4 blocks] fp16 d = 2176 bytes
+constexpr int kUnitBytesQ8 = 2176;
+__host__ __device__ constexpr int unit_bytes_of(int wt) { return wt == 12 ? 2368 : kUnitBytesQ8; }
+__host__ __device__ constexpr int unit_weights_of(int wt) { return wt == 12 ? 256 : 128; }
 
 // Quantised activation image of one GEMM input: written by quant_q8k_kernel, bulk-copied verbatim into
 // shared memory by the GEMM.
 //     xq  [K/64 pairs][32 lanes] 16 B : B-fragments {sub-block 2p: k 4t.., k 16+4t..; sub-block 2p+1: same}, col = lane/4
 //     bsw [K/64 pairs][8 cols]   4 B  : int16 sums of the two 32-element sub-blocks (for the dmin term)
 //     dx  [K/256][8 cols]        f32  : Q8_K block scales
-__host__ __device__ inline int act_image_bytes(int K) { return K * 8 + K / 2 + K / 8; }
-__host__ __device__ inline int gemm_fixed_smem(int K) { return ((act_image_bytes(K) + 127) & ~127) + kPartBytes + 1024; }
-__host__ inline int gemm_stages_for(int K) {
-    const int s = (kGemmSmemMax - gemm_fixed_smem(K)) / (kGemmWarps * kUnitBytes);
-    return s > kGemmMaxStages ? kGemmMaxStages : s;
+// Q8_0 image: xq as above (sub-block = 32-block) + dx [K/32][8 cols] f32 (fp16-rounded Q8_0 block scales)
+__host__ __device__ inline int act_image_bytes(int K, int wt = 12) { return wt == 12 ? K * 8 + K / 2 + K / 8 : K * 8 + K; }
+__host__ __device__ inline int gemm_fixed_smem(int K, int wt = 12) { return ((act_image_bytes(K, wt) + 127) & ~127) + kPartBytes + 1024; }
+__host__ inline int gemm_stages_for(int K, int wt = 12) {
+    const int s = (kGemmSmemMax - gemm_fixed_smem(K, wt)) / (kGemmWarps * unit_bytes_of(wt));
+    return s > 4 ? 4 : s;
 }
-__host__ inline int gemm_smem_bytes(int K, int stages) { return gemm_fixed_smem(K) + stages * kGemmWarps * kUnitBytes; }
+__host__ inline int gemm_smem_bytes(int K, int stages, int wt = 12) { return gemm_fixed_smem(K, wt) + stages * kGemmWarps * unit_bytes_of(wt); }
 
 // ---- load-time: QLinear planes (common.cuh) -> units ------------------------------------------------
 // gate != 0: the planes hold interleaved (gate j, up j) rows; tile row r <- virtual row 16*tile + 2*(r&7) + (r>>3)
@@ -92,6 +99,48 @@ __global__ void tile_q4k_kernel(const QLinear w, int gate, uint8_t *units, int n
         o = make_uint4(v[0], v[1], v[2], v[3]);
     }
     reinterpret_cast<uint4 *>(units + (size_t)u * kUnitBytes)[chunk] = o;
+}
+
+// Q8_0 planes (common.cuh) -> Q8_0 units
+__global__ void tile_q8_0_kernel(const QLinear w, int gate, uint8_t *units, int n_tiles) {
+    const int nsb = w.K >> 7, P = w.K >> 5;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;     // (tile, unit, 16-byte chunk): 136 chunks per unit
+    if (idx >= (long long)n_tiles * nsb * 136) return;
+    const int chunk = (int)(idx % 136);
+    const long long u = idx / 136;
+    const int sb = (int)(u % nsb), tile = (int)(u / nsb);
+    auto vrow = [&](int r) { return gate ? 16 * tile + 2 * (r & 7) + (r >> 3) : 16 * tile + r; };
+    uint4 o = make_uint4(0, 0, 0, 0);
+    if (chunk < 128) {
+        const int bi = chunk >> 5, lane = chunk & 31, g = lane >> 2, t = lane & 3;
+        const int pp = sb * 4 + bi;                                            // 32-block index inside the row
+        const int G = pp / w.gs, q = pp % w.gs, gsz = min(w.gs, P - G * w.gs);
+        uint32_t v[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int row = vrow(g + 8 * h);
+            if (row < w.rows) {
+                const uint32_t *c0 = reinterpret_cast<const uint32_t *>(w.qs + (size_t)row * w.K + (size_t)G * w.gs * 32 + q * 16);
+                v[h] = c0[t];
+                v[2 + h] = c0[gsz * 4 + t];
+            }
+        }
+        o = make_uint4(v[0], v[1], v[2], v[3]);
+    } else {
+        // dd: [16 rows][4 blocks] fp16 = 8 bytes per row -> chunk c holds rows 2c, 2c+1
+        uint32_t v[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            const int row = vrow((chunk - 128) * 2 + i);
+            if (row < w.rows) {
+                const uint16_t *d = reinterpret_cast<const uint16_t *>(w.dd) + (size_t)row * P + sb * 4;
+                v[2 * i] = (uint32_t)d[0] | ((uint32_t)d[1] << 16);
+                v[2 * i + 1] = (uint32_t)d[2] | ((uint32_t)d[3] << 16);
+            }
+        }
+        o = make_uint4(v[0], v[1], v[2], v[3]);
+    }
+    reinterpret_cast<uint4 *>(units + (size_t)u * kUnitBytesQ8)[chunk] = o;
 }
 
 // ---- activation quantisation: one CTA per stream ------------------------------------------------------
@@ -210,6 +259,82 @@ __global__ void __launch_bounds__(kGemmThreads) quant_q8k_kernel(const QuantArgs
     }
 }
 
+// Q8_0 activations (ggml quantize_row_q8_0 per 32: d = amax / 127, q = roundf(x / d), d kept as fp16) in the same fragment
+// order; dx [K/32][8 cols] f32.  One CTA per stream, same structure as quant_q8k_kernel.
+__global__ void __launch_bounds__(kGemmThreads) quant_q8_0_kernel(const QuantArgs a) {
+    __shared__ double red[kGemmWarps];
+    griddep_launch();
+    griddep_wait();
+    const int col = blockIdx.x, lane = threadIdx.x & 31, warp = uniform_warp_id();
+    const int K = a.K, nblk = (K + 255) >> 8;
+    const float *x = a.x + (size_t)col * a.ld;
+    const int nb_w = warp < nblk ? (nblk - warp + kGemmWarps - 1) / kGemmWarps : 0;
+    const bool norm = a.alpha != nullptr;
+    float scale = 1.f;
+    auto load8 = [&](int e0, float (&d)[8], const float *src) {
+        if (e0 < K) {
+            const float4 p0 = __ldcg(reinterpret_cast<const float4 *>(src + e0)), p1 = __ldcg(reinterpret_cast<const float4 *>(src + e0 + 4));
+            d[0] = p0.x; d[1] = p0.y; d[2] = p0.z; d[3] = p0.w; d[4] = p1.x; d[5] = p1.y; d[6] = p1.z; d[7] = p1.w;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; i++) d[i] = 0.f;
+        }
+    };
+    if (norm) {
+        double ss = 0.0;
+        for (int j = 0; j < nb_w; j++) {
+            float v[8];
+            load8((warp + j * kGemmWarps) * 256 + lane * 8, v, x);
+#pragma unroll
+            for (int i = 0; i < 8; i++) ss += (double)(v[i] * v[i]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        if (lane == 0) red[warp] = ss;
+        __syncthreads();
+        double tot = 0.0;
+        for (int w = 0; w < kGemmWarps; w++) tot += red[w];
+        const float mean = (K & (K - 1)) == 0 ? (float)scalbn(tot, -(31 - __clz(K))) : (float)(tot / K);
+        scale = 1.0f / sqrtf(mean + a.eps);
+    }
+    float *dx = reinterpret_cast<float *>(a.img + (size_t)K * 8);
+    for (int j = 0; j < nb_w; j++) {
+        if (j % (int)gridDim.y != (int)blockIdx.y) continue;
+        const int e0 = (warp + j * kGemmWarps) * 256 + lane * 8;
+        float v[8], al[8];
+        load8(e0, v, x);
+        const bool act = e0 < K;
+        if (norm) {
+            load8(e0, al, a.alpha);
+#pragma unroll
+            for (int i = 0; i < 8; i++) v[i] = __fmul_rn(al[i], __fmul_rn(v[i], scale));
+            if (a.norm_out && act) {
+                float *no = a.norm_out + (size_t)col * a.norm_ld + e0;
+                *reinterpret_cast<float4 *>(no) = make_float4(v[0], v[1], v[2], v[3]);
+                *reinterpret_cast<float4 *>(no + 4) = make_float4(v[4], v[5], v[6], v[7]);
+            }
+        }
+        float amax = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; i++) amax = fmaxf(amax, fabsf(v[i]));
+        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));        // the lane's 32-element block
+        const float d = amax / 127.f;
+        const float id = d ? 1.0f / d : 0.0f;
+        if (!act) continue;
+        int q[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) q[i] = (int)roundf(v[i] * id);
+        const int blk32 = e0 >> 5, jj = lane & 3;                       // 32-block index in the row
+        const int p = blk32 >> 1;                                         // fragment "pair" of two 32-blocks
+        if (jj == 0) dx[(size_t)blk32 * 8 + col] = __half2float(__float2half_rn(d));
+        const uint2 pk = pack8(q);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(a.img + ((size_t)p * 32 + col * 4) * 16) + (blk32 & 1) * 2 + (jj >> 1);
+        dst[(2 * (jj & 1)) * 4] = pk.x;
+        dst[(2 * (jj & 1) + 1) * 4] = pk.y;
+    }
+}
+
 // ---- the GEMM -----------------------------------------------------------------------------------------
 struct GemmArgs {
     QTiles w;
@@ -260,6 +385,39 @@ __device__ __forceinline__ int dp2a_hi_su(uint32_t a, uint32_t b, int c) {
 }
 
 // one unit (16 rows x 256 weights) against the 8 activation columns: acc[] = {(row g, col 2t), (g, 2t+1), (g+8, 2t), (g+8, 2t+1)}
+__device__ __forceinline__ void mma_s8s8(int (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+                 : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "r"(0));
+}
+// Q8_0 unit (16 rows x 4 blocks of 32) against the 8 columns: ggml_vec_dot_q8_0_q8_0 per block: sumi * (fp16 d_w * fp16 d_x),
+// the block terms accumulated in double
+__device__ __forceinline__ void unit_compute_q8(const uint8_t *slot, const uint8_t *img, int K, int sb, int lane, double (&acc)[4]) {
+    const int g = lane >> 2, t = lane & 3;
+    const uint2 ddg2 = *reinterpret_cast<const uint2 *>(slot + 2048 + g * 8);
+    const uint2 ddh2 = *reinterpret_cast<const uint2 *>(slot + 2048 + (g + 8) * 8);
+    const uint32_t ddg[2] = {ddg2.x, ddg2.y}, ddh[2] = {ddh2.x, ddh2.y};
+    const uint8_t *xq = img + (size_t)sb * 1024 + lane * 16;
+    const float *dx = reinterpret_cast<const float *>(img + (size_t)K * 8) + (size_t)sb * 32 + 2 * t;
+#pragma unroll
+    for (int p = 0; p < 2; p++) {
+        const uint4 w0 = *reinterpret_cast<const uint4 *>(slot + (2 * p) * 512 + lane * 16);
+        const uint4 w1 = *reinterpret_cast<const uint4 *>(slot + (2 * p + 1) * 512 + lane * 16);
+        const uint4 xb = *reinterpret_cast<const uint4 *>(xq + p * 512);
+        int c[4], d[4];
+        mma_s8s8(c, w0.x, w0.y, w0.z, w0.w, xb.x, xb.y);
+        mma_s8s8(d, w1.x, w1.y, w1.z, w1.w, xb.z, xb.w);
+        const float2 wg = __half22float2(*reinterpret_cast<const __half2 *>(&ddg[p]));      // d of blocks 2p, 2p+1, row g
+        const float2 wh = __half22float2(*reinterpret_cast<const __half2 *>(&ddh[p]));      // row g+8
+        const float2 x0 = *reinterpret_cast<const float2 *>(dx + (2 * p) * 8);               // block 2p: columns 2t, 2t+1
+        const float2 x1 = *reinterpret_cast<const float2 *>(dx + (2 * p + 1) * 8);
+        acc[0] = fma((double)__fmul_rn(wg.x, x0.x), (double)c[0], acc[0]); acc[1] = fma((double)__fmul_rn(wg.x, x0.y), (double)c[1], acc[1]);
+        acc[2] = fma((double)__fmul_rn(wh.x, x0.x), (double)c[2], acc[2]); acc[3] = fma((double)__fmul_rn(wh.x, x0.y), (double)c[3], acc[3]);
+        acc[0] = fma((double)__fmul_rn(wg.y, x1.x), (double)d[0], acc[0]); acc[1] = fma((double)__fmul_rn(wg.y, x1.y), (double)d[1], acc[1]);
+        acc[2] = fma((double)__fmul_rn(wh.y, x1.x), (double)d[2], acc[2]); acc[3] = fma((double)__fmul_rn(wh.y, x1.y), (double)d[3], acc[3]);
+    }
+}
+
 __device__ __forceinline__ void unit_compute(const uint8_t *slot, const uint8_t *img, int K, int sb, int lane, double (&acc)[4]) {
     const int g = lane >> 2, t = lane & 3;
     const uint4 scg4 = *reinterpret_cast<const uint4 *>(slot + 2048 + g * 16);
@@ -398,7 +556,9 @@ __device__ __forceinline__ void round_next(WarpRound &w, int warp, int nsb) {
     round_setup(w, warp, nsb);
 }
 
-__global__ void __launch_bounds__(kGemmThreads, 1) gemm_q4k_kernel(const GemmArgs a) {
+template <int WT>
+__global__ void __launch_bounds__(kGemmThreads, 1) gemm_mma_kernel(const GemmArgs a) {
+    constexpr int kUB = unit_bytes_of(WT);
     extern __shared__ __align__(16) uint8_t smem[];
     griddep_launch();
     long long *stamp = a.stamps ? a.stamps + (size_t)blockIdx.x * 8 : nullptr;
@@ -406,11 +566,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_q4k_kernel(const GemmArg
     const int lane = threadIdx.x & 31, warp = uniform_warp_id();
     const int g = lane >> 2, t = lane & 3;
     const int K = a.w.K, nsb = a.w.nsb, S = a.stages;
-    const int img_sz = act_image_bytes(K);
+    const int img_sz = act_image_bytes(K, WT);
     uint8_t *img = smem;
     double *part = reinterpret_cast<double *>(smem + ((img_sz + 127) & ~127));            // [2][16 warps][4][32]
     uint8_t *bar_base = reinterpret_cast<uint8_t *>(part) + kPartBytes;                 // mbarriers: [0] image, [1 + warp*4 + s]
-    uint8_t *ring = bar_base + 1024 + (size_t)warp * S * kUnitBytes;
+    uint8_t *ring = bar_base + 1024 + (size_t)warp * S * kUB;
     const uint32_t bar_u32 = (uint32_t)__cvta_generic_to_shared(bar_base);
     const uint32_t ring_u32 = (uint32_t)__cvta_generic_to_shared(ring);
     const uint32_t my_bar = bar_u32 + 8 + warp * (kGemmMaxStages * 8);
@@ -428,17 +588,17 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_q4k_kernel(const GemmArg
     WarpRound pc{t_begin, t_end - t_begin};
     round_setup(pc, warp, nsb);
     int pi = 0, ps = 0;                 // unit inside the round, ring slot
-    const uint8_t *psrc = a.w.units + ((size_t)pc.tile * nsb + pc.wq) * kUnitBytes;
+    const uint8_t *psrc = a.w.units + ((size_t)pc.tile * nsb + pc.wq) * kUB;
     auto issue = [&]() -> bool {       // lane 0 only; false when the warp's work list is exhausted
         if (pi >= pc.upr) {
             do { round_next(pc, warp, nsb); } while (pc.rem > 0 && pc.upr == 0);
             if (pc.rem <= 0) return false;
             pi = 0;
-            psrc = a.w.units + ((size_t)pc.tile * nsb + pc.wq) * kUnitBytes;
+            psrc = a.w.units + ((size_t)pc.tile * nsb + pc.wq) * kUB;
         }
-        mbar_expect_tx(my_bar + ps * 8, kUnitBytes);
-        bulk_g2s(ring_u32 + ps * kUnitBytes, psrc, kUnitBytes, my_bar + ps * 8);
-        psrc += (size_t)kUnitBytes << pc.lw;
+        mbar_expect_tx(my_bar + ps * 8, kUB);
+        bulk_g2s(ring_u32 + ps * kUB, psrc, kUB, my_bar + ps * 8);
+        psrc += (size_t)kUB << pc.lw;
         pi++;
         if (++ps == S) ps = 0;
         return true;
@@ -449,7 +609,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_q4k_kernel(const GemmArg
     if (stamp && threadIdx.x == 0) stamp[1] = global_ns();
     griddep_wait();
     if (stamp && threadIdx.x == 0) stamp[2] = global_ns();
-    if (a.xsrc) {
+    if (WT == 12 && a.xsrc) {
         fused_quant_columns(a, img, part, warp, lane);      // partial buffers double as the sum-of-squares scratch
         __syncthreads();
     } else {
@@ -469,7 +629,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_q4k_kernel(const GemmArg
     int emb_token = 0;
     if (a.epi == EPI_ADD_EMB && col_live) emb_token = depformer_prev_token(a.ctrl + col, a.emb_step);
     unsigned long long best = 0ull;
-    if (!a.xsrc) mbar_wait(bar_u32, 0);
+    if (!(WT == 12 && a.xsrc)) mbar_wait(bar_u32, 0);
     if (stamp && threadIdx.x == 0) stamp[3] = global_ns();
 
     WarpRound cr{t_begin, t_end - t_begin};
@@ -494,7 +654,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_q4k_kernel(const GemmArg
 #pragma unroll 1
             for (int i = 0; i < cr.upr; i++) {
                 mbar_wait(my_bar + cs * 8, cphase);
-                unit_compute(ring + (size_t)cs * kUnitBytes, img, K, cr.wq + (i << cr.lw), lane, acc);
+                if (WT == 12) unit_compute(ring + (size_t)cs * kUB, img, K, cr.wq + (i << cr.lw), lane, acc);
+                else unit_compute_q8(ring + (size_t)cs * kUB, img, K, cr.wq + (i << cr.lw), lane, acc);
                 __syncwarp();
                 if (lane == 0) issue();
                 if (++cs == S) { cs = 0; cphase ^= 1; }
@@ -735,6 +896,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm1_q4k_kernel(const GemvAr
     }
 }
 
+#define gemm_q4k_kernel gemm_mma_kernel<12>
+#define gemm_q8_0_kernel gemm_mma_kernel<8>
 __host__ inline int gemm_grid_for(int n_tiles, int num_sms) { return n_tiles < num_sms ? n_tiles : num_sms; }
 
 }  // namespace msx

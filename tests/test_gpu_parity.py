@@ -346,32 +346,35 @@ def test_top_k_sampling_matches_oracle(msx, orc, gguf_for, preset, quant):
 GEMM_SHAPES = [(4096, 512), (4096, 12288), (11264, 256), (1024, 3072), (2816, 1024), (1024, 2048), (4096, 6), (256, 40), (768, 520)]
 
 
+@pytest.mark.parametrize("quant", ["q4_k", "q8_0"])
 @pytest.mark.parametrize("k,rows", GEMM_SHAPES)
 @pytest.mark.parametrize("nb,rms", [(8, False), (8, True), (3, True), (1, False)])
-def test_batched_gemm_vs_oracle(msx, orc, k, rows, nb, rms):
+def test_batched_gemm_vs_oracle(msx, orc, quant, k, rows, nb, rms):
     """every column of the batched quantise + mma GEMM equals the oracle's ggml-faithful mul_mat of that column"""
     from moshi_cpp_b200 import synth
     rng = np.random.default_rng(k * 17 + rows + nb)
-    raw = synth.random_tensor(rng, synth.GGML_Q4_K, rows, k, 1.0 / np.sqrt(k))
+    GT = synth.TYPE_NAMES[quant]
+    raw = synth.random_tensor(rng, GT, rows, k, 1.0 / np.sqrt(k))
     x = rng.standard_normal((nb, k)).astype(np.float32) * 1.3
     x[0, 5] = 0.0
     if nb > 1:
         x[1, :256] = 0.0                                  # an all-zero Q8_K block (d = 0)
     alpha = (1.0 + 0.1 * rng.standard_normal(k)).astype(np.float32) if rms else None
-    got = msx.test_gemm_batch(synth.GGML_Q4_K, raw, k, x, alpha)
+    got = msx.test_gemm_batch(GT, raw, k, x, alpha)
     for b in range(nb):
         xin = orc.rms_norm(x[b], alpha) if rms else x[b]
-        ref = orc.mul_mat_vec(synth.GGML_Q4_K, raw, k, xin)
+        ref = orc.mul_mat_vec(GT, raw, k, xin)
         assert max_rel(got[b], ref) < GEMV_TOL, f"column {b}"
         assert_bitwise_mostly(got[b], ref, f"gemm column {b}")
 
 
-@pytest.mark.parametrize("preset,n", [("tiny", 8), ("tiny", 3), ("tiny_pplex", 5), ("moshi7b_l2", 8)])
-def test_batch_equals_independent_streams(msx, gguf_for, preset, n):
+@pytest.mark.parametrize("preset,n,quant", [("tiny", 8, "q4_k"), ("tiny", 3, "q4_k"), ("tiny_pplex", 5, "q4_k"), ("moshi7b_l2", 8, "q4_k"),
+                                            ("tiny", 8, "q8_0"), ("moshi7b_l2", 5, "q8_0")])
+def test_batch_equals_independent_streams(msx, gguf_for, preset, n, quant):
     """n streams stepped as one batch (different inputs, free running) produce the tokens and logits of n
     single msx_streams: the batched kernels share the single-stream arithmetic (double accumulation of exact
     block terms), only the summation order of the fp64 partials differs."""
-    path, cfg = gguf_for(preset, "q4_k")
+    path, cfg = gguf_for(preset, quant)
     gm = msx.Model(path, cfg)
     batch = msx.Batch(gm, n)
     singles = [msx.Stream(gm) for _ in range(n)]
@@ -417,8 +420,8 @@ def test_batch_stream_restart_and_resident(msx, gguf_for):
             assert np.array_equal(tok[s, 6 + f], outs2[f][s])
 
 
-def test_batch_rejects_q8_0_and_bad_sizes(msx, gguf_for):
-    path, cfg = gguf_for("tiny", "q8_0")
+def test_batch_rejects_unsupported_models_and_bad_sizes(msx, gguf_for):
+    path, cfg = gguf_for("tiny_tts", "q4_k")                 # cross-attention / demux layers are single-stream only
     gm = msx.Model(path, cfg)
     with pytest.raises(msx.MsxError):
         msx.Batch(gm, 4)
@@ -517,11 +520,11 @@ def test_voice_embedding_prompt_matches_oracle(msx, orc, gguf_for):
     assert gs.offset == 11 and os_.offset == 11
 
 
-@pytest.mark.parametrize("preset,T", [("tiny", 19), ("tiny_pplex", 8), ("moshi7b_l2", 11)])
-def test_batched_prefill_equals_serial_prompt_steps(msx, gguf_for, preset, T):
+@pytest.mark.parametrize("preset,T,quant", [("tiny", 19, "q4_k"), ("tiny_pplex", 8, "q4_k"), ("moshi7b_l2", 11, "q4_k"), ("tiny_pplex", 13, "q8_0")])
+def test_batched_prefill_equals_serial_prompt_steps(msx, gguf_for, preset, T, quant):
     """T fully-given prompt frames run 8 positions at a time through the tensor-core GEMM leave the
     same KV rings / position as T one-frame steps, so the conversation that follows is identical (bit for bit)."""
-    path, cfg = gguf_for(preset, "q4_k")
+    path, cfg = gguf_for(preset, quant)
     gm = msx.Model(path, cfg)
     a, b = msx.Stream(gm), msx.Stream(gm)
     rng = np.random.default_rng(31)
