@@ -220,7 +220,8 @@ MSX_API int msx_stream_prefill(msx_stream *s, const int32_t *tokens, int n_frame
 /* ---- lock-step batch of independent streams (BASELINE.json config 5) ------------------
  * n_streams (1..8) conversations share every weight read: one activation-quantisation launch and one
  * tensor-core dequant-GEMM launch per linear layer serve all of them; KV rings, positions and delay state
- * stay private, so stream i of a batch computes exactly what a single msx_stream would.  q4_k models only. */
+ * stay private, so stream i of a batch computes exactly what a single msx_stream would.  q4_k and q8_0 models
+ * (q8_0: K % 128 == 0); not the TTS-family layers. */
 typedef struct msx_batch msx_batch;
 MSX_API int msx_batch_create(msx_model *model, int n_streams, int context_override, msx_batch **out);
 MSX_API void msx_batch_free(msx_batch *b);
