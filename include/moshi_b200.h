@@ -233,6 +233,10 @@ MSX_API int64_t msx_batch_kv_bytes_next(const msx_batch *b);
 MSX_API int msx_batch_reset_stream(msx_batch *b, int stream);
 /* tokens [n][n_q+1] -> out_tokens [n][1+dep_q] (greedy), one fused frame for every stream */
 MSX_API int msx_batch_step(msx_batch *b, const int32_t *tokens, int32_t *out_tokens);
+/* sampling for every stream of the batch (sampling.h:4-64): softmax(l / temp) -> top-k -> arg-max of p / Exp(1); the Exp(1)
+ * draws of the next frame come from the host: noise_text [n][kt], noise_audio [n][dep_q][ka], kt / ka = min(top_k, card, 256) */
+MSX_API int msx_batch_set_sampling(msx_batch *b, float temp_text, float temp_audio, int top_k_text, int top_k_audio);
+MSX_API int msx_batch_set_noise(msx_batch *b, const float *noise_text, const float *noise_audio);
 MSX_API int msx_batch_get_logits(msx_batch *b, int stream, float *text_logits, float *audio_logits);
 /* frames [n][n_frames][n_q+1] copied to the device once, n_steps frames replayed; out_tokens [n][n_steps][1+dep_q] or NULL */
 MSX_API int msx_batch_run_resident(msx_batch *b, const int32_t *frames, int n_frames, int n_steps, int32_t *out_tokens, float *elapsed_ms);

@@ -146,6 +146,8 @@ def lib():
     L.msx_batch_kv_bytes_next.restype = C.c_int64; L.msx_batch_kv_bytes_next.argtypes = [vp]
     L.msx_batch_reset_stream.argtypes = [vp, C.c_int]
     L.msx_batch_step.argtypes = [vp, vp, vp]
+    L.msx_batch_set_sampling.argtypes = [vp, C.c_float, C.c_float, C.c_int, C.c_int]
+    L.msx_batch_set_noise.argtypes = [vp, vp, vp]
     L.msx_batch_get_logits.argtypes = [vp, C.c_int, vp, vp]
     L.msx_batch_run_resident.argtypes = [vp, vp, C.c_int, C.c_int, vp, C.POINTER(C.c_float)]
     L.msx_batch_profile_frame.argtypes = [vp, vp, vp, vp, C.c_int]
@@ -455,6 +457,13 @@ class Batch:
         out = np.empty((self.n, 1 + cfg["dep_q"]), dtype=np.int32)
         _check(lib().msx_batch_step(self.h, _p(tok), _p(out)))
         return out
+
+    def set_sampling(self, temp_text, temp_audio, top_k_text=25, top_k_audio=250):
+        _check(lib().msx_batch_set_sampling(self.h, temp_text, temp_audio, top_k_text, top_k_audio))
+
+    def set_noise(self, noise_text, noise_audio):
+        nt = np.ascontiguousarray(noise_text, dtype=np.float32); na = np.ascontiguousarray(noise_audio, dtype=np.float32)
+        _check(lib().msx_batch_set_noise(self.h, _p(nt), _p(na)))
 
     def logits(self, stream: int):
         cfg = self.model.cfg

@@ -28,6 +28,10 @@ struct msx_batch {
     // share its KV rings and its CUDA stream; n_active <= n columns are live in the launches being enqueued
     msx_stream *prefill_of = nullptr;
     int n_active = 0;
+    // sampling (sampling.h:46-64) per stream: temperature <= 0 = greedy; Exp(1) noise supplied by the host per frame
+    float temp_text = 0.f, temp_audio = 0.f;
+    int top_k_text = 25, top_k_audio = 250;
+    float *d_noise = nullptr, *h_noise = nullptr, *d_probs = nullptr;      // noise [n][1 + MSX_MAX_STEPS][kSampleMaxK]
     uint8_t *h_hdr = nullptr;             // pinned [n][32]: Ctrl headers (position per column)
 
     ~msx_batch() {
@@ -38,6 +42,7 @@ struct msx_batch {
         if (h_in) cudaFreeHost(h_in);
         if (h_out) cudaFreeHost(h_out);
         if (h_hdr) cudaFreeHost(h_hdr);
+        if (h_noise) cudaFreeHost(h_noise);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         if (st && !prefill_of) cudaStreamDestroy(st);
@@ -174,6 +179,16 @@ void enqueue_temporal_b(BatchLauncher &B) {
     if (b->prefill_of) return;           // prompt frames only populate the KV rings: no head, no sampling, no depformer
     B.quant(b->x, c.dim, m->out_norm, b->tout, c.dim, c.dim, FAM_TEXT_HEAD);
     B.gemm(m->text_linear, b->text_logits, c.text_card, EPI_ARGMAX, FAM_TEXT_HEAD, -1);
+    if (b->temp_text > 0.f) {          // moshi_sample_token per stream: overwrites the arg-max key with the sampled token
+        SampleArgs sa;
+        sa.logits = b->text_logits; sa.logits_stride = c.text_card; sa.n = c.text_card;
+        sa.k = std::min(std::min(b->top_k_text, c.text_card), kSampleMaxK); sa.inv_temp = 1.f / b->temp_text;
+        sa.noise = b->d_noise; sa.noise_stride = (1 + MSX_MAX_STEPS) * kSampleMaxK;
+        sa.probs = b->d_probs; sa.probs_stride = std::max(c.text_card, c.card); sa.ctrl = b->ctrl; sa.key_index = -1;
+        L.fam = FAM_TEXT_HEAD; L.begin();
+        L.launch_pdl(sample_kernel, dim3(b->n_active), dim3(kSampleThreads), 0, sa);
+        L.check();
+    }
     L.fam = FAM_FINALIZE; L.begin();
     L.launch_pdl(finalize_temporal_kernel, dim3(b->n_active), dim3(32), 0, b->ctrl, c.dep_q > 0 ? 1 : 0, (uint32_t *)nullptr);
     L.check();
@@ -190,6 +205,16 @@ void enqueue_depformer_b(BatchLauncher &B) {
         B.gemm(m->dep_in[w], b->dx, c.dep_dim, EPI_ADD_EMB, FAM_DEP_IN, -1, k == 0 ? &m->dep_text_emb : &m->dep_emb[k - 1], k, b->img_tout);
         for (int l = 0; l < c.dep_layers; l++) enqueue_layer_b(B, m->dep_layers[l], w, false, l, k);
         B.linear(b->dx, c.dep_dim, nullptr, m->linears[k], b->audio_logits + (size_t)k * c.card, c.dep_q * c.card, EPI_ARGMAX, FAM_DEP_HEAD, k);
+        if (b->temp_audio > 0.f) {
+            SampleArgs sa;
+            sa.logits = b->audio_logits + (size_t)k * c.card; sa.logits_stride = c.dep_q * c.card; sa.n = c.card;
+            sa.k = std::min(std::min(b->top_k_audio, c.card), kSampleMaxK); sa.inv_temp = 1.f / b->temp_audio;
+            sa.noise = b->d_noise + (size_t)(1 + k) * kSampleMaxK; sa.noise_stride = (1 + MSX_MAX_STEPS) * kSampleMaxK;
+            sa.probs = b->d_probs; sa.probs_stride = std::max(c.text_card, c.card); sa.ctrl = b->ctrl; sa.key_index = k;
+            L.fam = FAM_DEP_HEAD; L.begin();
+            L.launch_pdl(sample_kernel, dim3(b->n_active), dim3(kSampleThreads), 0, sa);
+            L.check();
+        }
     }
     L.fam = FAM_DEP_FINALIZE; L.begin();
     L.launch_pdl(finalize_depformer_kernel, dim3(b->n_active), dim3(64), 0, b->ctrl, (int)c.dep_q);
@@ -295,6 +320,13 @@ static int batch_create_impl(msx_model *m, int n_streams, int context_override, 
     if (gemm_stages_for(maxK, wt) < 2) return fail(MSX_ERR_ARG, "inner dimension too large for the batched GEMM's shared-memory image");
     if (int e = balloc(b.get(), (void **)&b->img, (size_t)act_image_bytes(maxK, wt))) return e;
     if (int e = balloc(b.get(), (void **)&b->img_tout, (size_t)act_image_bytes(c.dim, wt))) return e;
+    if (!prefill_of) {
+        const size_t nf = n * (1 + MSX_MAX_STEPS) * kSampleMaxK;
+        if (int e = balloc(b.get(), (void **)&b->d_noise, nf * 4)) return e;
+        if (int e = balloc(b.get(), (void **)&b->d_probs, n * std::max(c.text_card, c.card) * 4)) return e;
+        CU(cudaMallocHost((void **)&b->h_noise, nf * 4));
+        for (size_t i = 0; i < nf; i++) b->h_noise[i] = 1.f;
+    }
     std::vector<Ctrl> hc(n_streams);
     memset(hc.data(), 0, sizeof(Ctrl) * n);
     for (Ctrl &h : hc) { h.n_in = c.n_q + 1; h.text_override = INT32_MIN; for (int i = 0; i < 40; i++) h.force[i] = INT32_MIN; }
@@ -352,6 +384,47 @@ extern "C" int msx_stream_prefill(msx_stream *s, const int32_t *tokens, int T) {
     s->host_offset += T;
     CU(cudaMemcpyAsync(&s->ctrl->offset, &s->host_offset, 4, cudaMemcpyHostToDevice, s->st));
     CU(cudaStreamSynchronize(s->st));
+    return 0;
+}
+
+static int batch_build_graphs(msx_batch *b) {
+    const msx_config &c = b->m->cfg;
+    if (b->g_temporal) { cudaGraphExecDestroy(b->g_temporal); b->g_temporal = nullptr; }
+    if (b->g_depformer) { cudaGraphExecDestroy(b->g_depformer); b->g_depformer = nullptr; }
+    if (int e = capture_b(b, [&](BatchLauncher &B) { enqueue_temporal_b(B); }, &b->g_temporal, &b->launches_temporal)) return e;
+    if (c.dep_q > 0 && !b->prefill_of)
+        if (int e = capture_b(b, [&](BatchLauncher &B) { enqueue_depformer_b(B); }, &b->g_depformer, &b->launches_depformer)) return e;
+    return 0;
+}
+
+// temperatures / top-k of every stream of the batch (moshi_lm_start: 250 audio / 25 text); temperature <= 0 = greedy
+extern "C" int msx_batch_set_sampling(msx_batch *b, float temp_text, float temp_audio, int top_k_text, int top_k_audio) {
+    if (!b || b->prefill_of) return fail(MSX_ERR_ARG, "bad batch");
+    if (top_k_text < 1 || top_k_audio < 1) return fail(MSX_ERR_ARG, "top_k must be >= 1");
+    if (std::min(top_k_text, b->m->cfg.text_card) > kSampleMaxK || std::min(top_k_audio, b->m->cfg.card) > kSampleMaxK)
+        return fail(MSX_ERR_ARG, "top_k > 256 is not supported");
+    CU(cudaSetDevice(b->m->device));
+    CU(cudaStreamSynchronize(b->st));
+    b->temp_text = temp_text; b->temp_audio = temp_audio; b->top_k_text = top_k_text; b->top_k_audio = top_k_audio;
+    if (int e = batch_build_graphs(b)) return e;
+    CU(cudaStreamSynchronize(b->st));
+    return 0;
+}
+
+// Exp(1) draws of the next frame: noise_text [n][kt], noise_audio [n][dep_q][ka] (kt / ka = min(top_k, cardinality, 256))
+extern "C" int msx_batch_set_noise(msx_batch *b, const float *noise_text, const float *noise_audio) {
+    if (!b || b->prefill_of) return fail(MSX_ERR_ARG, "bad batch");
+    const msx_config &c = b->m->cfg;
+    CU(cudaSetDevice(b->m->device));
+    CU(cudaStreamSynchronize(b->st));
+    const int kt = std::min(std::min(b->top_k_text, c.text_card), kSampleMaxK), ka = std::min(std::min(b->top_k_audio, c.card), kSampleMaxK);
+    const size_t per = (size_t)(1 + MSX_MAX_STEPS) * kSampleMaxK;
+    for (int s = 0; s < b->n; s++) {
+        float *h = b->h_noise + per * s;
+        if (noise_text) memcpy(h, noise_text + (size_t)s * kt, (size_t)kt * 4);
+        if (noise_audio) for (int k = 0; k < c.dep_q; k++) memcpy(h + (size_t)(1 + k) * kSampleMaxK, noise_audio + ((size_t)s * c.dep_q + k) * ka, (size_t)ka * 4);
+    }
+    CU(cudaMemcpyAsync(b->d_noise, b->h_noise, per * b->n * 4, cudaMemcpyHostToDevice, b->st));
     return 0;
 }
 

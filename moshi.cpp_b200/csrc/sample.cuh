@@ -25,6 +25,10 @@ struct SampleArgs {
     const float *noise = nullptr;    // [k] Exp(1) draws, candidate j = j-th largest probability
     unsigned long long *key = nullptr;
     float *probs = nullptr;          // [n] scratch: the probabilities are computed once and re-read by the selection passes
+    // batched steps: one CTA per stream (blockIdx.x); per-stream strides in elements, key = a field of the stream's Ctrl
+    int32_t logits_stride = 0, noise_stride = 0, probs_stride = 0;
+    Ctrl *ctrl = nullptr;            // non-null: key = ctrl[stream].text_key (key_index < 0) or .audio_key[key_index]
+    int32_t key_index = -1;
 };
 
 __device__ __forceinline__ double block_sum_d(double v, double *scratch) {
@@ -39,9 +43,15 @@ __device__ __forceinline__ double block_sum_d(double v, double *scratch) {
     return t;
 }
 
-__global__ void __launch_bounds__(kSampleThreads) sample_kernel(const SampleArgs a) {
+__global__ void __launch_bounds__(kSampleThreads) sample_kernel(const SampleArgs a0) {
     griddep_launch();
     griddep_wait();
+    SampleArgs a = a0;
+    {
+        const int b = blockIdx.x;
+        a.logits += (size_t)b * a.logits_stride; a.noise += (size_t)b * a.noise_stride; a.probs += (size_t)b * a.probs_stride;
+        if (a.ctrl) a.key = a.key_index < 0 ? &a.ctrl[b].text_key : &a.ctrl[b].audio_key[a.key_index];
+    }
     __shared__ double s_d[kSampleThreads / 32];
     __shared__ float s_f[kSampleThreads / 32];
     __shared__ unsigned s_hist[256];

@@ -620,3 +620,31 @@ def test_quantize_on_load_q8_0(msx, orc, preset, src, tmp_path):
             assert max_rel(al_gpu, al_ref) < LOGIT_TOL
             nxt += list(a_ref)
         toks = np.array(nxt + list(rng.integers(0, cfg["card"], size=cfg["n_q"] + 1 - len(nxt))), dtype=np.int32)
+
+
+def test_batch_sampling_equals_independent_streams(msx, gguf_for):
+    """temperature > 0 in a batch: every stream samples with its own host noise exactly like a single msx_stream"""
+    path, cfg = gguf_for("tiny", "q4_k")
+    gm = msx.Model(path, cfg)
+    n = 4
+    batch = msx.Batch(gm, n); batch.set_sampling(0.7, 0.8, 25, 250)
+    singles = [msx.Stream(gm) for _ in range(n)]
+    for s in singles:
+        s.set_sampling(0.7, 0.8, 25, 250)
+    kt, ka = min(25, cfg["text_card"]), min(250, cfg["card"])
+    rng = np.random.default_rng(12)
+    toks = rng.integers(0, cfg["card"], size=(n, cfg["n_q"] + 1)).astype(np.int32)
+    toks[:, 0] = rng.integers(0, cfg["text_card"], size=n)
+    diff_from_greedy = 0
+    for f in range(8):
+        nt = rng.exponential(size=(n, kt)).astype(np.float32); na = rng.exponential(size=(n, cfg["dep_q"], ka)).astype(np.float32)
+        batch.set_noise(nt, na)
+        out = batch.step(toks)
+        for i in range(n):
+            singles[i].set_noise(nt[i], na[i])
+            t, tl, _ = singles[i].step_temporal(toks[i])
+            a, _ = singles[i].step_depformer(t)
+            assert out[i, 0] == t and np.array_equal(out[i, 1:], a), f"frame {f} stream {i}"
+            diff_from_greedy += int(t != int(np.argmax(tl)))
+        toks = np.concatenate([out, rng.integers(0, cfg["card"], size=(n, cfg["n_q"] - cfg["dep_q"]))], axis=1).astype(np.int32)
+    assert diff_from_greedy > 0, "sampling should not collapse to greedy"
