@@ -313,14 +313,19 @@ def main():
         ms_b, _ = batch.run_resident(bframes, Kb)
         torch.cuda.synchronize(local_rank); barrier()
         bkv1 = batch.kv_bytes_next()
-        # end to end: host tokens in (n x 336 B), tokens out (n x 176 B), host sync every frame
+        # end to end through the batched generator (per-conversation delay rings, msx_bgen_step): host user codes in,
+        # delayed tokens out, n x 336 B H2D + n x 176 B D2H and a host sync every frame
+        batch.reset()
+        bgen = msx.BatchGen(batch)
+        n_user_b = cfg["n_q"] - cfg["dep_q"] if cfg["dep_q"] > 0 else cfg["n_q"]
         for i in range(W):
-            batch.step(bframes[:, i % bframes.shape[1]])
+            bgen.step(bframes[:, i % bframes.shape[1], -n_user_b:])
         barrier(); torch.cuda.synchronize(local_rank)
         t0 = time.perf_counter()
         for i in range(Kb):
-            batch.step(bframes[:, (W + i) % bframes.shape[1]])
+            bgen.step(bframes[:, (W + i) % bframes.shape[1], -n_user_b:])
         ms_be = (time.perf_counter() - t0) * 1e3
+        bgen.close()
         torch.cuda.synchronize(local_rank); barrier()
         if dist is not None:
             t = torch.tensor([ms_b, ms_be], device=f"cuda:{local_rank}", dtype=torch.float64)
@@ -333,7 +338,7 @@ def main():
             "streams_per_gpu": nb, "value": world * nb * Kb / (ms_b * 1e-3), "unit": "frames/s (all streams, all GPUs)",
             "ms_per_step": ms_b / Kb, "per_stream_fps": Kb / (ms_b * 1e-3), "per_stream_realtime_factor": Kb / (ms_b * 1e-3) / FRAME_RATE,
             "e2e": {"value": world * nb * Kb / (ms_be * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": 336 * nb, "d2h_bytes_per_step": 176 * nb,
-                    "timing": "wall clock around msx_batch_step (host sync inside every call)"},
+                    "timing": "wall clock around msx_bgen_step (per-stream delay rings on the host, one msx_batch_step, host sync inside every call)"},
             "step_bytes": {"weights_read_once": w_bytes, "kv_avg": 0.5 * (bkv0 + bkv1), "gbs": b_bytes / (ms_b / Kb * 1e-3) / 1e9},
             "launches_per_frame": batch.launches_per_frame, "steps": Kb,
             "gemm": {"kernel": "gemm_q4k_kernel gating.linear_in (mma.sync m16n8k32 u8 x s8, TMA unit ring, silu gate)",

@@ -241,6 +241,14 @@ MSX_API int msx_batch_get_logits(msx_batch *b, int stream, float *text_logits, f
 /* frames [n][n_frames][n_q+1] copied to the device once, n_steps frames replayed; out_tokens [n][n_steps][1+dep_q] or NULL */
 MSX_API int msx_batch_run_resident(msx_batch *b, const int32_t *frames, int n_frames, int n_steps, int32_t *out_tokens, float *elapsed_ms);
 MSX_API int msx_batch_profile_frame(msx_batch *b, const int32_t *tokens, float *family_ms, int32_t *family_launches, int max_families);
+/* Batched generator: the LMGen host logic (token delay ring, delayed emit; lm.h:715-743, 778-979) for every stream of a batch
+ * around ONE msx_batch_step.  in_tokens [n][n_in] -> out_text [n], out_audio [n][dep_q], valid [n]. */
+typedef struct msx_bgen msx_bgen;
+MSX_API int msx_bgen_create(msx_batch *b, int delay_steps, msx_bgen **out);
+MSX_API void msx_bgen_free(msx_bgen *g);
+MSX_API int msx_bgen_offset(const msx_bgen *g, int stream);
+MSX_API int msx_bgen_reset_stream(msx_bgen *g, int stream);     /* a new conversation takes over this slot */
+MSX_API int msx_bgen_step(msx_bgen *g, const int32_t *in_tokens, int n_in, int32_t *out_text, int32_t *out_audio, int32_t *valid);
 /* test / measurement hooks of the batched GEMM */
 MSX_API int msx_test_gemm_batch(int device, int type, const void *w, int64_t k, int64_t rows, const float *x, int nb, const float *alpha, float *y);
 MSX_API int msx_bench_gemm_batch(int device, const void *w, int64_t k, int64_t rows, int nb, int n_mats, int iters, int epilogue, int with_quant,

@@ -146,6 +146,11 @@ def lib():
     L.msx_batch_kv_bytes_next.restype = C.c_int64; L.msx_batch_kv_bytes_next.argtypes = [vp]
     L.msx_batch_reset_stream.argtypes = [vp, C.c_int]
     L.msx_batch_step.argtypes = [vp, vp, vp]
+    L.msx_bgen_create.argtypes = [vp, C.c_int, C.POINTER(vp)]
+    L.msx_bgen_free.argtypes = [vp]
+    L.msx_bgen_offset.argtypes = [vp, C.c_int]
+    L.msx_bgen_reset_stream.argtypes = [vp, C.c_int]
+    L.msx_bgen_step.argtypes = [vp, vp, C.c_int, vp, vp, vp]
     L.msx_batch_set_sampling.argtypes = [vp, C.c_float, C.c_float, C.c_int, C.c_int]
     L.msx_batch_set_noise.argtypes = [vp, vp, vp]
     L.msx_batch_get_logits.argtypes = [vp, C.c_int, vp, vp]
@@ -492,6 +497,40 @@ class Batch:
     def close(self):
         if self.h:
             lib().msx_batch_free(self.h); self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class BatchGen:
+    """LMGen host logic (delay ring, delayed emit) for every stream of a Batch around one batched model step"""
+
+    def __init__(self, batch: Batch, delay_steps: int = 0):
+        self.batch = batch
+        self.h = C.c_void_p()
+        _check(lib().msx_bgen_create(batch.h, delay_steps, C.byref(self.h)))
+
+    def offset(self, stream: int) -> int:
+        return lib().msx_bgen_offset(self.h, stream)
+
+    def reset(self, stream: int):
+        _check(lib().msx_bgen_reset_stream(self.h, stream))
+
+    def step(self, in_tokens):
+        """in_tokens [n][n_in] -> (valid [n], text [n], audio [n][dep_q])"""
+        cfg = self.batch.model.cfg
+        n = self.batch.n
+        tok = np.ascontiguousarray(in_tokens, dtype=np.int32).reshape(n, -1)
+        text = np.zeros(n, dtype=np.int32); audio = np.full((n, max(1, cfg["dep_q"])), -7, dtype=np.int32); valid = np.zeros(n, dtype=np.int32)
+        _check(lib().msx_bgen_step(self.h, _p(tok), tok.shape[1], _p(text), _p(audio), _p(valid)))
+        return valid, text, audio[:, : cfg["dep_q"]]
+
+    def close(self):
+        if self.h:
+            lib().msx_bgen_free(self.h); self.h = None
 
     def __del__(self):
         try:

@@ -660,3 +660,74 @@ extern "C" int msx_bench_gemm_batch_ex(int device, const void *w, int64_t k, int
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaStreamDestroy(st);
     return 0;
 }
+
+
+// ---- batched generator: one delay ring (moshi_lmgen_state_t) per stream of a batch -------------------------------------
+// The per-stream host logic is msx_gen's (gen_prepare / gen_finish, lm.h:778-979); the model step is ONE msx_batch_step.
+struct msx_bgen {
+    msx_batch *b = nullptr;
+    std::vector<std::unique_ptr<msx_gen>> gens;
+    std::vector<int32_t> inputs, outs;
+};
+
+extern "C" int msx_bgen_create(msx_batch *b, int delay_steps, msx_bgen **out) {
+    if (!b || !out || b->prefill_of) return fail(MSX_ERR_ARG, "bad argument");
+    std::unique_ptr<msx_bgen> g(new msx_bgen);
+    g->b = b;
+    for (int i = 0; i < b->n; i++) {
+        std::unique_ptr<msx_gen> gi(new msx_gen);
+        gi->cfg = b->m->cfg;
+        gen_init(gi.get(), delay_steps);
+        g->gens.push_back(std::move(gi));
+    }
+    g->inputs.resize((size_t)b->n * (b->m->cfg.n_q + 1));
+    g->outs.resize((size_t)b->n * (1 + b->m->cfg.dep_q));
+    *out = g.release();
+    return 0;
+}
+extern "C" void msx_bgen_free(msx_bgen *g) { delete g; }
+extern "C" int msx_bgen_offset(const msx_bgen *g, int stream) { return (g && stream >= 0 && stream < g->b->n) ? g->gens[stream]->offset : -1; }
+
+// a new conversation takes over slot `stream`: fresh delay ring, KV rings cleared, position 0; the other slots go on
+extern "C" int msx_bgen_reset_stream(msx_bgen *g, int stream) {
+    if (!g || stream < 0 || stream >= g->b->n) return fail(MSX_ERR_ARG, "bad argument");
+    const int ds = g->gens[stream]->delay_steps;
+    std::unique_ptr<msx_gen> gi(new msx_gen);
+    gi->cfg = g->b->m->cfg;
+    gen_init(gi.get(), ds);
+    g->gens[stream] = std::move(gi);
+    return msx_batch_reset_stream(g->b, stream);
+}
+
+// in_tokens [n][n_in] (n_in = the user codes of a frame, or n_q+1 when everything is provided) -> out_text [n],
+// out_audio [n][dep_q], valid [n] (1 = this stream emitted a frame, 0 = still inside its delay window)
+extern "C" int msx_bgen_step(msx_bgen *g, const int32_t *in_tokens, int n_in, int32_t *out_text, int32_t *out_audio, int32_t *valid) {
+    if (!g || !out_text || !out_audio || !valid) return fail(MSX_ERR_ARG, "null argument");
+    msx_batch *b = g->b; const msx_config &c = b->m->cfg;
+    const int n = b->n, ncb = c.n_q + 1;
+    std::vector<GenPrep> prep(n);
+    for (int i = 0; i < n; i++) {
+        if (int e = gen_prepare(g->gens[i].get(), in_tokens ? in_tokens + (size_t)i * n_in : nullptr, n_in, &prep[i])) return e;
+        memcpy(g->inputs.data() + (size_t)i * ncb, prep[i].input, (size_t)ncb * 4);
+    }
+    if (b->temp_text > 0.f || b->temp_audio > 0.f) {
+        // Exp(1) draws from libc rand() like context.h:464-480, stream by stream (text candidates, then the codebooks)
+        const int kt = std::min(std::min(b->top_k_text, c.text_card), kSampleMaxK), ka = std::min(std::min(b->top_k_audio, c.card), kSampleMaxK);
+        std::vector<float> nt((size_t)n * kt, 1.f), na((size_t)n * std::max(1, c.dep_q) * ka, 1.f);
+        for (int i = 0; i < n; i++) {
+            if (b->temp_text > 0.f) for (int j = 0; j < kt; j++) nt[(size_t)i * kt + j] = -logf(rand() / (float)RAND_MAX);
+            if (b->temp_audio > 0.f) for (size_t j = 0; j < (size_t)c.dep_q * ka; j++) na[(size_t)i * c.dep_q * ka + j] = -logf(rand() / (float)RAND_MAX);
+        }
+        if (int e = msx_batch_set_noise(b, nt.data(), na.data())) return e;
+    }
+    if (int e = msx_batch_step(b, g->inputs.data(), g->outs.data())) return e;
+    for (int i = 0; i < n; i++) {
+        int32_t out[1 + MSX_MAX_STEPS];
+        for (int k = 0; k < 1 + MSX_MAX_STEPS; k++) out[k] = -1;
+        memcpy(out, g->outs.data() + (size_t)i * (1 + c.dep_q), (size_t)(1 + c.dep_q) * 4);
+        const int rc = gen_finish(g->gens[i].get(), prep[i], out, 0, &out_text[i], out_audio + (size_t)i * c.dep_q);
+        if (rc < 0) return rc;
+        valid[i] = rc;
+    }
+    return 0;
+}

@@ -1788,29 +1788,71 @@ extern "C" int msx_gen_set_audio_hook(msx_gen *g, msx_audio_hook fn, void *user)
     return 0;
 }
 
-extern "C" int msx_gen_step(msx_gen *g, const int32_t *in_tokens, int n_in, int depformer_replace_tokens, int32_t *out_text, int32_t *out_audio) {
-    if (!g || !out_text || !out_audio) return fail(MSX_ERR_ARG, "null argument");
-    msx_stream *s = g->s;
+// moshi_lmgen_step (lm.h:778-979) around the model call: gen_prepare = ring write of the incoming tokens + input gather,
+// gen_finish = audio hooks, ring write of the generated tokens, delayed emit.  Shared by msx_gen_step (one stream) and
+// msx_bgen_step (a batch of streams, batch.inl).
+struct GenPrep { bool provided = false; int32_t input[MSX_MAX_CODEBOOKS]; };
+static int gen_prepare(msx_gen *g, const int32_t *in_tokens, int n_in, GenPrep *p) {
     const msx_config &c = g->cfg;
     const int CT = g->CT, ncb = g->ncb;
     int dep_q = c.dep_q;
     if (c.personaplex) dep_q = 8;                                             // lm.h:802-805
     const int dep_q_1 = dep_q + 1;
     const int needed = ncb - dep_q - 1;
-    bool provided = false;
+    p->provided = false;
     if (needed > 0) {
         if (!in_tokens || n_in < needed) return fail(MSX_ERR_ARG, "not enough input tokens");   // reference: assert (lm.h:810)
         if (n_in == ncb) {
             for (int i = 0; i < ncb; i++) g->cache[(size_t)((g->offset + c.delays[i]) % CT) * ncb + i] = in_tokens[i];
-            provided = true;
+            p->provided = true;
         } else {
             for (int i = 0; i < needed; i++)
                 g->cache[(size_t)((g->offset + c.delays[dep_q_1 + i]) % CT) * ncb + dep_q_1 + i] = in_tokens[i];
         }
     }
     const int pos = g->offset % CT;
-    int32_t input[MSX_MAX_CODEBOOKS];
-    for (int i = 0; i < ncb; i++) input[i] = (g->offset <= c.delays[i]) ? g->initial[i] : g->cache[(size_t)pos * ncb + i];
+    for (int i = 0; i < ncb; i++) p->input[i] = (g->offset <= c.delays[i]) ? g->initial[i] : g->cache[(size_t)pos * ncb + i];
+    return 0;
+}
+static int gen_finish(msx_gen *g, const GenPrep &p, int32_t *out, int depformer_replace_tokens, int32_t *out_text, int32_t *out_audio) {
+    const msx_config &c = g->cfg;
+    const int CT = g->CT, ncb = g->ncb;
+    int dep_q = c.dep_q;
+    if (c.personaplex) dep_q = 8;
+    const int dep_q_1 = dep_q + 1;
+    const int text_token = out[0];
+    int32_t *audio = out + 1;
+    if (c.dep_q > 0 && g->delay_steps)
+        for (int q = 0; q < c.dep_q; q++)
+            if (g->offset < c.delays[q + 1] + g->delay_steps) audio[q] = -1;  // lm.h:915-921
+    if (c.dep_q > 0 && g->audio_hook) {                                       // audio prefix (lm.h:922-931)
+        const int sk = g->audio_hook(g->audio_user, g->offset, audio, c.dep_q);
+        if (sk >= 0) g->skip = sk;
+    }
+    g->offset++;
+    if (!p.provided) {
+        const int pp = g->offset % CT;
+        g->cache[(size_t)pp * ncb + 0] = text_token;
+        for (int q = 0; q < c.dep_q; q++) g->cache[(size_t)pp * ncb + q + 1] = audio[q];
+    }
+    for (int q = 0; q < c.dep_q; q++) out_audio[q] = audio[q];
+    if (g->skip > 0) { --g->skip; return 0; }                                 // lm.h:944-947
+    if (g->offset <= g->max_delay || depformer_replace_tokens) return 0;
+    *out_text = g->cache[(size_t)((g->offset - g->max_delay + c.delays[0]) % CT) * ncb + 0];
+    for (int i = 1; i < dep_q_1; i++)
+        out_audio[i - 1] = g->cache[(size_t)((g->offset - g->max_delay + c.delays[i]) % CT) * ncb + i];
+    for (int q = 0; q < c.dep_q; q++)
+        if (out_audio[q] == -1) return 0;
+    return 1;
+}
+
+extern "C" int msx_gen_step(msx_gen *g, const int32_t *in_tokens, int n_in, int depformer_replace_tokens, int32_t *out_text, int32_t *out_audio) {
+    if (!g || !out_text || !out_audio) return fail(MSX_ERR_ARG, "null argument");
+    msx_stream *s = g->s;
+    const msx_config &c = g->cfg;
+    GenPrep p;
+    if (int e = gen_prepare(g, in_tokens, n_in, &p)) return e;
+    const int32_t *input = p.input;
 
     int32_t out[1 + MSX_MAX_STEPS];
     for (int i = 0; i < 1 + MSX_MAX_STEPS; i++) out[i] = -1;
@@ -1838,30 +1880,7 @@ extern "C" int msx_gen_step(msx_gen *g, const int32_t *in_tokens, int n_in, int 
     } else {
         if (int e = msx_step_temporal(s, input, &out[0], nullptr, nullptr)) return e;
     }
-    const int text_token = out[0];
-    int32_t *audio = out + 1;
-    if (c.dep_q > 0 && g->delay_steps)
-        for (int q = 0; q < c.dep_q; q++)
-            if (g->offset < c.delays[q + 1] + g->delay_steps) audio[q] = -1;  // lm.h:915-921
-    if (c.dep_q > 0 && g->audio_hook) {                                       // audio prefix (lm.h:922-931)
-        const int sk = g->audio_hook(g->audio_user, g->offset, audio, c.dep_q);
-        if (sk >= 0) g->skip = sk;
-    }
-    g->offset++;
-    if (!provided) {
-        const int p = g->offset % CT;
-        g->cache[(size_t)p * ncb + 0] = text_token;
-        for (int q = 0; q < c.dep_q; q++) g->cache[(size_t)p * ncb + q + 1] = audio[q];
-    }
-    for (int q = 0; q < c.dep_q; q++) out_audio[q] = audio[q];
-    if (g->skip > 0) { --g->skip; return 0; }                                 // lm.h:944-947
-    if (g->offset <= g->max_delay || depformer_replace_tokens) return 0;
-    *out_text = g->cache[(size_t)((g->offset - g->max_delay + c.delays[0]) % CT) * ncb + 0];
-    for (int i = 1; i < dep_q_1; i++)
-        out_audio[i - 1] = g->cache[(size_t)((g->offset - g->max_delay + c.delays[i]) % CT) * ncb + i];
-    for (int q = 0; q < c.dep_q; q++)
-        if (out_audio[q] == -1) return 0;
-    return 1;
+    return gen_finish(g, p, out, depformer_replace_tokens, out_text, out_audio);
 }
 
 // -------------------------------------------------------------------------------------------------

@@ -648,3 +648,31 @@ def test_batch_sampling_equals_independent_streams(msx, gguf_for):
             diff_from_greedy += int(t != int(np.argmax(tl)))
         toks = np.concatenate([out, rng.integers(0, cfg["card"], size=(n, cfg["n_q"] - cfg["dep_q"]))], axis=1).astype(np.int32)
     assert diff_from_greedy > 0, "sampling should not collapse to greedy"
+
+
+@pytest.mark.parametrize("preset", ["tiny", "tiny_pplex"])
+def test_batched_generator_equals_independent_generators(msx, gguf_for, preset):
+    """config 5 end to end: n conversations with their own delay rings on one batch == n (msx_stream + msx_gen) pairs,
+    including a conversation that is replaced mid-run"""
+    path, cfg = gguf_for(preset, "q4_k")
+    gm = msx.Model(path, cfg)
+    n = 5
+    bg = msx.BatchGen(msx.Batch(gm, n))
+    streams = [msx.Stream(gm) for _ in range(n)]
+    gens = [msx.Gen(s) for s in streams]
+    rng = np.random.default_rng(6)
+    n_user = cfg["n_q"] - (8 if cfg["model_type"] == "personaplex" else cfg["dep_q"])
+    emitted = 0
+    for f in range(30):
+        if f == 11:                                   # slot 3 starts a new conversation
+            bg.reset(3)
+            streams[3].reset(); gens[3] = msx.Gen(streams[3])
+        user = rng.integers(0, cfg["card"], size=(n, n_user)).astype(np.int32)
+        valid, text, audio = bg.step(user)
+        for i in range(n):
+            rc, t, a = gens[i].step(user[i])
+            assert valid[i] == rc, f"frame {f} stream {i}"
+            if rc:
+                emitted += 1
+                assert text[i] == t and np.array_equal(audio[i], a), f"frame {f} stream {i}"
+    assert emitted > n * 20 and bg.offset(3) == 19 and bg.offset(0) == 30
