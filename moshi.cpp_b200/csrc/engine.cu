@@ -605,7 +605,15 @@ struct Launcher {
         const int n_tiles = (a.w.rows + tr - 1) / tr;
         const int grid = std::max(1, std::min(num_sms, (n_tiles + 7) / 8));
         const int smem = gemv_smem_bytes(a.w.type, a.w.K);
-        if (a.w.type == T_Q4_K) {
+        if (a.tp) {          // tensor-parallel partial sums pushed to the peers: separate instantiations
+            if (a.w.type == T_Q4_K) {
+                if (a.w.gs == 32) launch_pdl(gemv_kernel<12, 32, true>, dim3(grid), dim3(kGemvThreads), smem, a, pro, epi);
+                else launch_pdl(gemv_kernel<12, 16, true>, dim3(grid), dim3(kGemvThreads), smem, a, pro, epi);
+            } else {
+                if (a.w.gs == 32) launch_pdl(gemv_kernel<8, 32, true>, dim3(grid), dim3(kGemvThreads), smem, a, pro, epi);
+                else launch_pdl(gemv_kernel<8, 16, true>, dim3(grid), dim3(kGemvThreads), smem, a, pro, epi);
+            }
+        } else if (a.w.type == T_Q4_K) {
             if (a.w.gs == 32) launch_pdl(gemv_kernel<12, 32>, dim3(grid), dim3(kGemvThreads), smem, a, pro, epi);
             else launch_pdl(gemv_kernel<12, 16>, dim3(grid), dim3(kGemvThreads), smem, a, pro, epi);
         } else {
@@ -1054,6 +1062,10 @@ int set_smem_attrs() {
     CU(cudaFuncSetAttribute(gemv_kernel<12, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CU(cudaFuncSetAttribute(gemv_kernel<8, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CU(cudaFuncSetAttribute(gemv_kernel<8, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU(cudaFuncSetAttribute(gemv_kernel<12, 32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU(cudaFuncSetAttribute(gemv_kernel<12, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU(cudaFuncSetAttribute(gemv_kernel<8, 32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU(cudaFuncSetAttribute(gemv_kernel<8, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CU(cudaFuncSetAttribute(gemv_local_attn_kernel<12, 32, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CU(cudaFuncSetAttribute(gemv_local_attn_kernel<12, 32, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CU(cudaFuncSetAttribute(gemv_local_attn_kernel<12, 16, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));

@@ -428,7 +428,9 @@ __device__ __forceinline__ void compute_step(const uint8_t *slot, int K, int it,
 // PRO / EPI are run-time (warp-uniform) selectors on purpose: one copy of the main loop per (WT, LANES).
 // `a` may live in kernel-parameter space (standalone kernels) or in shared memory (phase descriptor of the
 // persistent kernel); it is never copied to local memory.  x_over replaces a.x when non-null.
-template <int WT, int LANES, bool PDL = false>
+// TPPUSH: the tensor-parallel peer-memory epilogue (EPI_STORE_F64 with a.tp) lives in its own instantiation so that the
+// single-GPU kernels carry none of its code (measured: 4 % slower frames when it was compiled into the common kernel).
+template <int WT, int LANES, bool PDL = false, bool TPPUSH = false>
 __device__ __forceinline__ void gemv_body(const GemvArgs &a, const float *x_over, const bool norm_out_cta, const int PRO, const int EPI,
                                           uint8_t *smem, const int cta, const int n_cta, const BlockGeom bg,
                                           unsigned long long *progress = nullptr) {
@@ -479,7 +481,7 @@ __device__ __forceinline__ void gemv_body(const GemvArgs &a, const float *x_over
     if (EPI == EPI_ADD_EMB) emb_token = depformer_prev_token(a.ctrl, a.emb_step);
     unsigned long long best = 0ull;
     uint32_t tp_epoch = 0, tp_parity = 0;      // tp_epoch + 1 = sequence number of this reduce
-    if (EPI == EPI_STORE_F64 && a.tp) { tp_epoch = tp_seq(a.tp, a.tp_idx) - 1u; tp_parity = (uint32_t)a.tp_idx & 1u; }
+    if (TPPUSH) { tp_epoch = tp_seq(a.tp, a.tp_idx) - 1u; tp_parity = (uint32_t)a.tp_idx & 1u; }
 
     double acc[kR];
 #pragma unroll
@@ -503,7 +505,7 @@ __device__ __forceinline__ void gemv_body(const GemvArgs &a, const float *x_over
 #pragma unroll
             for (int o = LANES / 2; o > 0; o >>= 1) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], o);
             if (EPI == EPI_STORE_F64 && l == 0 && cons.row0 + r < a.w.rows) {
-                if (a.tp) {      // partial sum + sequence number straight into every rank's inbox (own rank included)
+                if (TPPUSH) {    // partial sum + sequence number straight into every rank's inbox (own rank included)
                     const size_t o = ((size_t)tp_parity * a.tp->world + a.tp->rank) * a.tp->dim + cons.row0 + r;
                     const unsigned long long bits = (unsigned long long)__double_as_longlong(acc[r]);
                     const uint4 pk = make_uint4((uint32_t)bits, tp_epoch + 1u, (uint32_t)(bits >> 32), tp_epoch + 1u);
@@ -557,11 +559,11 @@ __device__ __forceinline__ void gemv_body(const GemvArgs &a, const float *x_over
 // 512 threads, one CTA per SM: half as many CTAs repeat the activation prologue, and each prologue has 16
 // warps to spread its 256-element blocks over (K = 11264: 3 block iterations per warp instead of 6)
 constexpr int kGemvThreads = 512;
-template <int WT, int LANES>
+template <int WT, int LANES, bool TPPUSH = false>
 __global__ void __launch_bounds__(kGemvThreads, 1) gemv_kernel(const GemvArgs a, const int pro, const int epi) {
     extern __shared__ __align__(16) uint8_t smem[];
     griddep_launch();      // the next kernel may start launching: it prefetches its weights and then waits for us
-    gemv_body<WT, LANES, true>(a, nullptr, blockIdx.x == 0, pro, epi, smem, blockIdx.x, gridDim.x, BlockGeom{kGemvThreads, kGemvThreads / 32});
+    gemv_body<WT, LANES, true, TPPUSH>(a, nullptr, blockIdx.x == 0, pro, epi, smem, blockIdx.x, gridDim.x, BlockGeom{kGemvThreads, kGemvThreads / 32});
 }
 
 }  // namespace msx
