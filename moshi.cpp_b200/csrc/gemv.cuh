@@ -430,7 +430,11 @@ __device__ __forceinline__ void compute_step(const uint8_t *slot, int K, int it,
 // persistent kernel); it is never copied to local memory.  x_over replaces a.x when non-null.
 // TPPUSH: the tensor-parallel peer-memory epilogue (EPI_STORE_F64 with a.tp) lives in its own instantiation so that the
 // single-GPU kernels carry none of its code (measured: 4 % slower frames when it was compiled into the common kernel).
-template <int WT, int LANES, bool PDL = false, bool TPPUSH = false>
+// LEAN: store / residual / silu-gate epilogues only — the kernel of 4 of every 5 launches of a frame carries no embedding,
+// arg-max, fp64-partial or add-vector code (measured: linear_in 13.96 -> 13.17 us).  Kernel SIZE matters as much: one body per
+// kernel, because consecutive launches of a frame alternate between variants and a large kernel image thrashes the
+// instruction caches (five specialised bodies in one kernel made the frame 10 % slower although each was faster in isolation).
+template <int WT, int LANES, bool PDL = false, bool TPPUSH = false, bool LEAN = false>
 __device__ __forceinline__ void gemv_body(const GemvArgs &a, const float *x_over, const bool norm_out_cta, const int PRO, const int EPI,
                                           uint8_t *smem, const int cta, const int n_cta, const BlockGeom bg,
                                           unsigned long long *progress = nullptr) {
@@ -478,7 +482,7 @@ __device__ __forceinline__ void gemv_body(const GemvArgs &a, const float *x_over
     if (bg.stamp && threadIdx.x == 0) bg.stamp[1] = global_ns();
 
     int emb_token = 0;
-    if (EPI == EPI_ADD_EMB) emb_token = depformer_prev_token(a.ctrl, a.emb_step);
+    if (!LEAN && EPI == EPI_ADD_EMB) emb_token = depformer_prev_token(a.ctrl, a.emb_step);
     unsigned long long best = 0ull;
     uint32_t tp_epoch = 0, tp_parity = 0;      // tp_epoch + 1 = sequence number of this reduce
     if (TPPUSH) { tp_epoch = tp_seq(a.tp, a.tp_idx) - 1u; tp_parity = (uint32_t)a.tp_idx & 1u; }
@@ -504,7 +508,7 @@ __device__ __forceinline__ void gemv_body(const GemvArgs &a, const float *x_over
         for (int r = 0; r < kR; r++) {
 #pragma unroll
             for (int o = LANES / 2; o > 0; o >>= 1) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], o);
-            if (EPI == EPI_STORE_F64 && l == 0 && cons.row0 + r < a.w.rows) {
+            if (!LEAN && EPI == EPI_STORE_F64 && l == 0 && cons.row0 + r < a.w.rows) {
                 if (TPPUSH) {    // partial sum + sequence number straight into every rank's inbox (own rank included)
                     const size_t o = ((size_t)tp_parity * a.tp->world + a.tp->rank) * a.tp->dim + cons.row0 + r;
                     const unsigned long long bits = (unsigned long long)__double_as_longlong(acc[r]);
@@ -519,6 +523,14 @@ __device__ __forceinline__ void gemv_body(const GemvArgs &a, const float *x_over
             if (EPI == EPI_RESID) {                        // residual already in registers
 #pragma unroll
                 for (int r = 0; r < kR; r++) { const int row = cons.row0 + r; if (row < a.w.rows) a.out[row] = resid[r] + accf[r]; }
+            } else if (LEAN) {               // STORE / GATE only (RESID is handled above)
+#pragma unroll
+                for (int r = 0; r < kR; r++) {
+                    const int row = cons.row0 + r;
+                    if (row >= a.w.rows) break;
+                    if (EPI == EPI_STORE) a.out[row] = accf[r];
+                    else if ((r & 1) == 0) { const float g = accf[r]; a.out[row >> 1] = (g / (1.0f + (float)exp((double)(-g)))) * accf[r + 1]; }
+                }
             } else if (EPI != EPI_STORE_F64) gemv_epilogue<kR>(a, EPI, cons.row0, accf, emb_token, best);
         }
         if (progress && lane == 0) atomicAdd(progress, tile_bytes);
@@ -540,7 +552,7 @@ __device__ __forceinline__ void gemv_body(const GemvArgs &a, const float *x_over
     }
     if (bg.stamp && threadIdx.x == 0) bg.stamp[2] = global_ns();
 
-    if (EPI == EPI_ARGMAX) {
+    if (!LEAN && EPI == EPI_ARGMAX) {
         // CTA-level max, then one atomic per CTA
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { unsigned long long t = __shfl_xor_sync(0xffffffffu, best, o); best = t > best ? t : best; }
@@ -559,11 +571,11 @@ __device__ __forceinline__ void gemv_body(const GemvArgs &a, const float *x_over
 // 512 threads, one CTA per SM: half as many CTAs repeat the activation prologue, and each prologue has 16
 // warps to spread its 256-element blocks over (K = 11264: 3 block iterations per warp instead of 6)
 constexpr int kGemvThreads = 512;
-template <int WT, int LANES, bool TPPUSH = false>
+template <int WT, int LANES, bool TPPUSH = false, bool LEAN = false>
 __global__ void __launch_bounds__(kGemvThreads, 1) gemv_kernel(const GemvArgs a, const int pro, const int epi) {
     extern __shared__ __align__(16) uint8_t smem[];
     griddep_launch();      // the next kernel may start launching: it prefetches its weights and then waits for us
-    gemv_body<WT, LANES, true, TPPUSH>(a, nullptr, blockIdx.x == 0, pro, epi, smem, blockIdx.x, gridDim.x, BlockGeom{kGemvThreads, kGemvThreads / 32});
+    gemv_body<WT, LANES, true, TPPUSH, LEAN>(a, nullptr, blockIdx.x == 0, pro, epi, smem, blockIdx.x, gridDim.x, BlockGeom{kGemvThreads, kGemvThreads / 32});
 }
 
 }  // namespace msx
