@@ -613,7 +613,7 @@ struct Launcher {
                 if (a.w.gs == 32) launch_pdl(gemv_kernel<8, 32, true>, dim3(grid), dim3(kGemvThreads), smem, a, pro, epi);
                 else launch_pdl(gemv_kernel<8, 16, true>, dim3(grid), dim3(kGemvThreads), smem, a, pro, epi);
             }
-        } else if ((epi == EPI_STORE || epi == EPI_RESID || epi == EPI_GATE) && !a.xparts) {
+        } else if ((epi == EPI_STORE || epi == EPI_RESID || epi == EPI_GATE) && !a.xparts && !a.norm_out) {
             // the lean kernels: store / residual / gate epilogues only (4 of every 5 launches of a frame)
             if (a.w.type == T_Q4_K) {
                 if (a.w.gs == 32) launch_pdl(gemv_kernel<12, 32, false, true>, dim3(grid), dim3(kGemvThreads), smem, a, pro, epi);

@@ -74,8 +74,9 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 
 // 8 consecutive activations starting at e0: plain f32 vector, or the sum of `nparts` double partial vectors
 // (attention context written by the split-KV phase of the persistent kernel)
+template <bool LEAN = false>
 __device__ __forceinline__ void load_x8(const GemvArgs &a, const float *xin, int e0, float (&v)[8]) {
-    if (a.xparts) {
+    if (!LEAN && a.xparts) {
         double s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         for (int c = 0; c < a.nparts; c++) {
             const double2 *p = reinterpret_cast<const double2 *>(a.xparts + (size_t)c * a.part_stride + e0);
@@ -196,7 +197,7 @@ __device__ __forceinline__ void quantize_block_q8_0(int b, int lane, const float
 // sum-of-squares pass and the quantisation pass: the activation vector is read exactly once.
 constexpr int kChunk = 3;
 
-template <int WT, int LAYOUT = 0>
+template <int WT, int LAYOUT = 0, bool LEAN = false>
 __device__ __forceinline__ void gemv_prologue(const GemvArgs &a, const float *xin, const bool norm_out_cta, const int PRO, int K, int8_t *x8,
                                               int *bs, float *dx, double *red, const BlockGeom &bg) {
     const int lane = threadIdx.x & 31, warp = uniform_warp_id();
@@ -214,7 +215,7 @@ __device__ __forceinline__ void gemv_prologue(const GemvArgs &a, const float *xi
 #pragma unroll
             for (int j = 0; j < kChunk; j++) {
                 const int e0 = e0_of(c0 + j);
-                if (c0 + j < nb_w && e0 < K) { load_x8(a, xin, e0, v[j]); if (keep) load_alpha8(a, e0, al[j]); }
+                if (c0 + j < nb_w && e0 < K) { load_x8<LEAN>(a, xin, e0, v[j]); if (keep) load_alpha8(a, e0, al[j]); }
                 else {
 #pragma unroll
                     for (int i = 0; i < 8; i++) v[j][i] = 0.f;
@@ -242,7 +243,7 @@ __device__ __forceinline__ void gemv_prologue(const GemvArgs &a, const float *xi
 #pragma unroll
             for (int j = 0; j < kChunk; j++) {
                 const int e0 = e0_of(c0 + j);
-                if (c0 + j < nb_w && e0 < K) { load_x8(a, xin, e0, v[j]); if (PRO == PRO_RMS) load_alpha8(a, e0, al[j]); }
+                if (c0 + j < nb_w && e0 < K) { load_x8<LEAN>(a, xin, e0, v[j]); if (PRO == PRO_RMS) load_alpha8(a, e0, al[j]); }
                 else {
 #pragma unroll
                     for (int i = 0; i < 8; i++) v[j][i] = 0.f;
@@ -257,7 +258,7 @@ __device__ __forceinline__ void gemv_prologue(const GemvArgs &a, const float *xi
                 if (PRO == PRO_RMS && act) {
 #pragma unroll
                     for (int i = 0; i < 8; i++) v[j][i] = __fmul_rn(al[j][i], __fmul_rn(v[j][i], scale));   // alpha * (x * scale)
-                    if (a.norm_out && norm_out_cta) {
+                    if (!LEAN && a.norm_out && norm_out_cta) {
                         *reinterpret_cast<float4 *>(a.norm_out + e0) = make_float4(v[j][0], v[j][1], v[j][2], v[j][3]);
                         *reinterpret_cast<float4 *>(a.norm_out + e0 + 4) = make_float4(v[j][4], v[j][5], v[j][6], v[j][7]);
                     }
@@ -267,7 +268,7 @@ __device__ __forceinline__ void gemv_prologue(const GemvArgs &a, const float *xi
             }
         }
     }
-    if (bg.stamp && threadIdx.x == 0) bg.stamp[7] = global_ns();
+    if (!LEAN && bg.stamp && threadIdx.x == 0) bg.stamp[7] = global_ns();
 }
 
 // ---- epilogue ------------------------------------------------------------------------------------
@@ -472,14 +473,14 @@ __device__ __forceinline__ void gemv_body(const GemvArgs &a, const float *x_over
         bs = reinterpret_cast<int *>(smem + K);
         dx = reinterpret_cast<float *>(smem + K + (K >> 6) * 8);
         red = reinterpret_cast<double *>(smem + gemv_q_bytes(12, K) - 128);
-        gemv_prologue<12>(a, xin, norm_out_cta, PRO, K, x8, bs, dx, red, bg);
+        gemv_prologue<12, 0, LEAN>(a, xin, norm_out_cta, PRO, K, x8, bs, dx, red, bg);
     } else {
         dx = reinterpret_cast<float *>(smem + K);
         red = reinterpret_cast<double *>(smem + gemv_q_bytes(8, K) - 128);
-        gemv_prologue<8>(a, xin, norm_out_cta, PRO, K, x8, nullptr, dx, red, bg);
+        gemv_prologue<8, 0, LEAN>(a, xin, norm_out_cta, PRO, K, x8, nullptr, dx, red, bg);
     }
     block_sync(bg);
-    if (bg.stamp && threadIdx.x == 0) bg.stamp[1] = global_ns();
+    if (!LEAN && bg.stamp && threadIdx.x == 0) bg.stamp[1] = global_ns();
 
     int emb_token = 0;
     if (!LEAN && EPI == EPI_ADD_EMB) emb_token = depformer_prev_token(a.ctrl, a.emb_step);
@@ -533,7 +534,7 @@ __device__ __forceinline__ void gemv_body(const GemvArgs &a, const float *x_over
                 }
             } else if (EPI != EPI_STORE_F64) gemv_epilogue<kR>(a, EPI, cons.row0, accf, emb_token, best);
         }
-        if (progress && lane == 0) atomicAdd(progress, tile_bytes);
+        if (!LEAN && progress && lane == 0) atomicAdd(progress, tile_bytes);
     };
 #pragma unroll 1
     for (int s = 0; s < n_steps; s++) {
@@ -550,7 +551,7 @@ __device__ __forceinline__ void gemv_body(const GemvArgs &a, const float *x_over
         if (cons.it == nit - 1) finish_tile();
         advance<LANES>(cons, nit, row_stride);
     }
-    if (bg.stamp && threadIdx.x == 0) bg.stamp[2] = global_ns();
+    if (!LEAN && bg.stamp && threadIdx.x == 0) bg.stamp[2] = global_ns();
 
     if (!LEAN && EPI == EPI_ARGMAX) {
         // CTA-level max, then one atomic per CTA
