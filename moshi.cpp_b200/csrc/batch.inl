@@ -127,8 +127,17 @@ struct BatchLauncher {
         if (emb) g.emb = *emb;
         g.stages = gemm_stages_for(w.K, w.type);
         L.fam = family; L.begin();
-        if (w.type == T_Q4_K) L.launch_pdl(gemm_q4k_kernel, dim3(gemm_grid_for(g.w.n_tiles, L.num_sms)), dim3(kGemmThreads), (size_t)gemm_smem_bytes(w.K, g.stages, 12), g);
-        else L.launch_pdl(gemm_q8_0_kernel, dim3(gemm_grid_for(g.w.n_tiles, L.num_sms)), dim3(kGemmThreads), (size_t)gemm_smem_bytes(w.K, g.stages, 8), g);
+        const dim3 grid(gemm_grid_for(g.w.n_tiles, L.num_sms)), block(kGemmThreads);
+        const size_t smem = (size_t)gemm_smem_bytes(w.K, g.stages, w.type);
+        const bool lean = epi == EPI_STORE || epi == EPI_RESID || epi == EPI_GATE;
+        if (w.type == T_Q4_K) {
+            if (lean && xsrc) L.launch_pdl(gemm_mma_kernel<12, 2>, grid, block, smem, g);
+            else if (lean) L.launch_pdl(gemm_mma_kernel<12, 1>, grid, block, smem, g);
+            else L.launch_pdl(gemm_mma_kernel<12, 0>, grid, block, smem, g);
+        } else {
+            if (lean) L.launch_pdl(gemm_mma_kernel<8, 1>, grid, block, smem, g);
+            else L.launch_pdl(gemm_mma_kernel<8, 0>, grid, block, smem, g);
+        }
         L.check();
     }
 };
@@ -275,8 +284,11 @@ static int batch_create_impl(msx_model *m, int n_streams, int context_override, 
         return fail(MSX_ERR_ARG, "batched streams do not cover the TTS-family layers (cross-attention, demux / low-rank embeddings)");
     CU(cudaSetDevice(m->device));
     if (int e = set_smem_attrs()) return e;
-    CU(cudaFuncSetAttribute(gemm_q4k_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemMax));
-    CU(cudaFuncSetAttribute(gemm_q8_0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemMax));
+    CU(cudaFuncSetAttribute(gemm_mma_kernel<12, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemMax));
+    CU(cudaFuncSetAttribute(gemm_mma_kernel<12, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemMax));
+    CU(cudaFuncSetAttribute(gemm_mma_kernel<12, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemMax));
+    CU(cudaFuncSetAttribute(gemm_mma_kernel<8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemMax));
+    CU(cudaFuncSetAttribute(gemm_mma_kernel<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemMax));
     if (int e = ensure_all_tiles(m)) return e;
     std::unique_ptr<msx_batch> b(new msx_batch);
     b->m = m; b->n = n_streams; b->n_active = n_streams; b->prefill_of = prefill_of;

@@ -556,12 +556,16 @@ __device__ __forceinline__ void round_next(WarpRound &w, int warp, int nsb) {
     round_setup(w, warp, nsb);
 }
 
-template <int WT>
+// VAR: 0 = everything (heads, depformer_in, debug stamps), 1 = lean (store / residual / gate epilogues, image from the quantise
+// kernel), 2 = lean with the fused short-K activation prologue.  One small body per kernel: consecutive launches of a frame
+// alternate between variants, and kernel size costs instruction-cache misses (see gemv.cuh).
+template <int WT, int VAR = 0>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_mma_kernel(const GemmArgs a) {
+    constexpr bool LEAN = VAR != 0, FUSED = VAR == 2 || (VAR == 0 && WT == 12);
     constexpr int kUB = unit_bytes_of(WT);
     extern __shared__ __align__(16) uint8_t smem[];
     griddep_launch();
-    long long *stamp = a.stamps ? a.stamps + (size_t)blockIdx.x * 8 : nullptr;
+    long long *stamp = (!LEAN && a.stamps) ? a.stamps + (size_t)blockIdx.x * 8 : nullptr;
     if (stamp && threadIdx.x == 0) stamp[0] = global_ns();
     const int lane = threadIdx.x & 31, warp = uniform_warp_id();
     const int g = lane >> 2, t = lane & 3;
@@ -609,7 +613,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_mma_kernel(const GemmArg
     if (stamp && threadIdx.x == 0) stamp[1] = global_ns();
     griddep_wait();
     if (stamp && threadIdx.x == 0) stamp[2] = global_ns();
-    if (WT == 12 && a.xsrc) {
+    if (FUSED && (VAR == 2 || a.xsrc)) {
         fused_quant_columns(a, img, part, warp, lane);      // partial buffers double as the sum-of-squares scratch
         __syncthreads();
     } else {
@@ -627,9 +631,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_mma_kernel(const GemmArg
     const bool col_live = col < a.nb;
     float *const ocol = a.out + (size_t)col * a.ld;
     int emb_token = 0;
-    if (a.epi == EPI_ADD_EMB && col_live) emb_token = depformer_prev_token(a.ctrl + col, a.emb_step);
+    if (!LEAN && a.epi == EPI_ADD_EMB && col_live) emb_token = depformer_prev_token(a.ctrl + col, a.emb_step);
     unsigned long long best = 0ull;
-    if (!(WT == 12 && a.xsrc)) mbar_wait(bar_u32, 0);
+    if (!(FUSED && (VAR == 2 || a.xsrc))) mbar_wait(bar_u32, 0);
     if (stamp && threadIdx.x == 0) stamp[3] = global_ns();
 
     WarpRound cr{t_begin, t_end - t_begin};
@@ -677,6 +681,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_mma_kernel(const GemmArg
             } else if (a.epi == EPI_RESID) {
                 if (row0 < a.w.rows) ocol[row0] = old0 + v0;
                 if (row1 < a.w.rows) ocol[row1] = old1 + v1;
+            } else if (LEAN) {
+                if (row0 < a.w.rows) ocol[row0] = v0;
+                if (row1 < a.w.rows) ocol[row1] = v1;
             } else {
 #pragma unroll
                 for (int hh = 0; hh < 2; hh++) {
@@ -699,7 +706,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_mma_kernel(const GemmArg
         }
     }
     if (stamp && threadIdx.x == 0) stamp[4] = global_ns();
-    if (a.epi == EPI_ARGMAX) {
+    if (!LEAN && a.epi == EPI_ARGMAX) {
         // best over the 8 row groups of the warp (lanes sharing t), then over the warps of equal parity
 #pragma unroll
         for (int o = 4; o < 32; o <<= 1) { const unsigned long long x = __shfl_xor_sync(0xffffffffu, best, o); best = x > best ? x : best; }
@@ -896,8 +903,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm1_q4k_kernel(const GemvAr
     }
 }
 
-#define gemm_q4k_kernel gemm_mma_kernel<12>
-#define gemm_q8_0_kernel gemm_mma_kernel<8>
+#define gemm_q4k_kernel gemm_mma_kernel<12, 0>
+#define gemm_q8_0_kernel gemm_mma_kernel<8, 0>
 __host__ inline int gemm_grid_for(int n_tiles, int num_sms) { return n_tiles < num_sms ? n_tiles : num_sms; }
 
 }  // namespace msx
