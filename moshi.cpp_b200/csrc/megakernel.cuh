@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(kGemvThreads, 1) gemv_local_attn_kernel(const 
     griddep_wait();                                  // qkv comes from the previous kernel
     attn_local<DH>(a, heads, ctx_s, scratch, blockIdx.x == 0, bg.nwarps);
     block_sync(bg);
-    gemv_body<WT, LANES, false>(g, ctx_s, false, pro, epi, smem, blockIdx.x, gridDim.x, bg);
+    gemv_body<WT, LANES, false, false, true>(g, ctx_s, false, pro, epi, smem, blockIdx.x, gridDim.x, bg);   // lean body: only the residual epilogue is used here
 }
 __host__ __device__ inline int local_attn_smem_bytes(int gemv_bytes, int dim, int dh) {
     return (gemv_bytes + 15) / 16 * 16 + dim * 4 + (kGemvThreads / 32) * (2 * dh + 64) * 4 + 64;
