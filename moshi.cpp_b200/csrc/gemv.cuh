@@ -435,10 +435,13 @@ __device__ __forceinline__ void compute_step(const uint8_t *slot, int K, int it,
 // arg-max, fp64-partial or add-vector code (measured: linear_in 13.96 -> 13.17 us).  Kernel SIZE matters as much: one body per
 // kernel, because consecutive launches of a frame alternate between variants and a large kernel image thrashes the
 // instruction caches (five specialised bodies in one kernel made the frame 10 % slower although each was faster in isolation).
-template <int WT, int LANES, bool PDL = false, bool TPPUSH = false, bool LEAN = false>
+struct NoMid { __device__ __forceinline__ void operator()() const {} };
+// `mid` runs after the first weight steps have been requested and before the activation prologue: the PDL wait of the
+// standalone kernels, or wait + local attention of the fused kernel (its weights stream in under the attention)
+template <int WT, int LANES, bool PDL = false, bool TPPUSH = false, bool LEAN = false, typename Mid = NoMid>
 __device__ __forceinline__ void gemv_body(const GemvArgs &a, const float *x_over, const bool norm_out_cta, const int PRO, const int EPI,
                                           uint8_t *smem, const int cta, const int n_cta, const BlockGeom bg,
-                                          unsigned long long *progress = nullptr) {
+                                          unsigned long long *progress = nullptr, Mid mid = Mid()) {
     const float *xin = x_over ? x_over : a.x;
     constexpr int TR = tile_rows(LANES);
     const int K = a.w.K;
@@ -466,6 +469,7 @@ __device__ __forceinline__ void gemv_body(const GemvArgs &a, const float *x_over
         cp_async_commit();
     }
     if (PDL) griddep_wait();
+    mid();
 
     int8_t *x8 = reinterpret_cast<int8_t *>(smem);
     int *bs = nullptr; float *dx = nullptr; double *red = nullptr;

@@ -204,10 +204,14 @@ __global__ void __launch_bounds__(kGemvThreads, 1) gemv_local_attn_kernel(const 
     const BlockGeom bg{kGemvThreads, kGemvThreads / 32};
     float *ctx_s = reinterpret_cast<float *>(smem + gemv_region);
     float *scratch = ctx_s + a.dim;
-    griddep_wait();                                  // qkv comes from the previous kernel
-    attn_local<DH>(a, heads, ctx_s, scratch, blockIdx.x == 0, bg.nwarps);
-    block_sync(bg);
-    gemv_body<WT, LANES, false, false, true>(g, ctx_s, false, pro, epi, smem, blockIdx.x, gridDim.x, bg);   // lean body: only the residual epilogue is used here
+    // the out_proj weights do not depend on qkv: gemv_body requests its first steps, THEN waits for the previous kernel and
+    // runs the attention (the whole 0.6 MB matrix of a depformer layer is in flight under it)
+    auto mid = [&]() {
+        griddep_wait();                              // qkv comes from the previous kernel
+        attn_local<DH>(a, heads, ctx_s, scratch, blockIdx.x == 0, bg.nwarps);
+        block_sync(bg);
+    };
+    gemv_body<WT, LANES, false, false, true, decltype(mid)>(g, ctx_s, false, pro, epi, smem, blockIdx.x, gridDim.x, bg, nullptr, mid);   // lean body: residual epilogue only
 }
 __host__ __device__ inline int local_attn_smem_bytes(int gemv_bytes, int dim, int dh) {
     return (gemv_bytes + 15) / 16 * 16 + dim * 4 + (kGemvThreads / 32) * (2 * dh + 64) * 4 + 64;
