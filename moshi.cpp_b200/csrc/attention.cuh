@@ -99,11 +99,12 @@ __global__ void __launch_bounds__(kThreads) attn_kernel(const AttnArgs a0) {
     constexpr int LPS = DH / 8;             // lanes per slot (8 dims = 16 B of bf16 each)
     constexpr int NG = kThreads / LPS;      // slots in flight per CTA iteration
     griddep_launch();
-    griddep_wait();        // qkv comes from the previous kernel (PDL)
     int S = gridDim.x, c = blockIdx.x;
     const int h = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = uniform_warp_id();
     const int cap = a.cap;
+    // the position is stable for the whole graph (advanced by the finalize kernel of the previous frame), so it may be read
+    // before the PDL wait
     const int pos = a.pos_const >= 0 ? a.pos_const : a.ctrl->offset;
     const int slot = pos % cap;
     const int n_valid = (pos >= cap - 1) ? cap : pos + 1;
@@ -112,6 +113,19 @@ __global__ void __launch_bounds__(kThreads) attn_kernel(const AttnArgs a0) {
     // (uniform decision across the cluster, so nobody waits at a barrier)
     const bool use_cluster = CLUSTER && n_valid > min(a.small_ctx, per - 1);
     if (CLUSTER && !use_cluster) { if (c != 0) return; S = 1; c = 0; }
+    {
+        // the ring rows of earlier frames do not depend on the previous kernel either: pull this CTA's first K / V rows into
+        // L2 while that kernel drains (between frames the 4 GB weight stream evicts them, so they come from HBM)
+        const int plo = (int)((long long)n_valid * c / S), phi = (int)((long long)n_valid * (c + 1) / S);
+        constexpr int LPR = DH * 2 / 128;            // 128-byte lines per row
+        const int n_lines = min(phi - plo, 128) * 2 * LPR;
+        for (int j = tid; j < n_lines; j += kThreads) {
+            const int r = plo + j / (2 * LPR), part = j % (2 * LPR);
+            const uint16_t *p = (part < LPR ? a.kc : a.vc) + ((size_t)h * cap + r) * DH + (part % LPR) * 64;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+        }
+    }
+    griddep_wait();        // qkv comes from the previous kernel (PDL)
 
     double *x_sum = reinterpret_cast<double *>(smem);                  // [kAttnMaxSplit] cluster exchange: row sums
     double *dred = x_sum + kAttnMaxSplit;                              // [8] block reduce scratch
