@@ -123,10 +123,13 @@ MSX_API int msx_stream_set_noise(msx_stream *s, const float *noise_text, const f
  * the single-GPU numbers.  msx_tp_unique_id on one rank, ship the 128 bytes to the others (torch.distributed, MPI, a
  * file), then msx_stream_create_tp on every rank (collective).  NCCL is bound with dlopen("libnccl.so.2"). */
 MSX_API int msx_model_load_gguf_tp(const char *path, const msx_config *cfg, int device, int tp_rank, int tp_world, msx_model **out);
-/* the general loader: tensor-parallel shard (rank 0 of 1 = everything) and quantise-on-load.  quantize = 8 (GGML Q8_0):
- * f32 / f16 / bf16 linears AND embedding tables of the file are quantised to Q8_0 on the GPU while loading, with ggml's
- * quantize_row_q8_0 arithmetic (reference: moshi_lm_quantize "q8_0", src/moshi.cpp:654-673, src/loader.h:149-233);
- * 0 = take the file as it is.  q4_k has no on-load quantiser here (quantize_row_q4_K is a search; files must be q4_k). */
+/* the general loader: tensor-parallel shard (rank 0 of 1 = everything) and quantise-on-load (reference:
+ * moshi_lm_quantize, src/moshi.cpp:654-673; type rules src/loader.h:149-233, src/moshi/models/lm_utils.h:131-147).
+ * quantize = 8 (GGML_TYPE_Q8_0): f32 / f16 / bf16 linears AND embedding tables of the file become Q8_0 on the GPU while
+ * loading (ggml quantize_row_q8_0 arithmetic).  quantize = 12 (GGML_TYPE_Q4_K): linears become Q4_K (ggml
+ * quantize_row_q4_K: the make_qkx2_quants scale / min search per 32-element sub-block, run with the scalar code's
+ * sequential fp32 arithmetic), embedding tables and K % 256 != 0 projections Q4_0 (quantize_row_q4_0).  0 = take the
+ * file as it is.  Already quantised tensors are never touched. */
 MSX_API int msx_model_load_gguf_ex(const char *path, const msx_config *cfg, int device, int tp_rank, int tp_world, int quantize, msx_model **out);
 MSX_API int msx_tp_unique_id(uint8_t *out128);
 MSX_API int msx_stream_create_tp(msx_model *model, int context_override, const uint8_t *nccl_id128, msx_stream **out);
@@ -266,6 +269,9 @@ MSX_API int msx_bench_gemv(int device, int type, const void *w, int64_t k, int64
 MSX_API int msx_test_dequant_rows(int device, int type, const void *table, int64_t k, int64_t table_rows,
                                   const int32_t *row_ids, int n_rows, float *out);
 /* device Q4_K -> f32 of the REPACKED tiles (checks the repack is lossless) */
+/* the on-load quantisers alone: rows x k values of GGML type src_type (0 f32, 1 f16, 30 bf16) -> GGUF blocks of dst_type
+ * (8 Q8_0, 2 Q4_0, 12 Q4_K) in `out` (host) */
+MSX_API int msx_test_quantize_rows(int device, int src_type, int dst_type, const void *x, int64_t k, int64_t rows, void *out);
 MSX_API int msx_test_dequant_repacked(int device, int type, const void *w, int64_t k, int64_t rows, float *out);
 
 #ifdef __cplusplus

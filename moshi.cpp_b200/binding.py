@@ -161,6 +161,7 @@ def lib():
     L.msx_bench_gemm_batch.argtypes = [C.c_int, vp, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]
     L.msx_test_dequant_rows.argtypes = [C.c_int, C.c_int, vp, C.c_int64, C.c_int64, vp, C.c_int, vp]
     L.msx_test_dequant_repacked.argtypes = [C.c_int, C.c_int, vp, C.c_int64, C.c_int64, vp]
+    L.msx_test_quantize_rows.argtypes = [C.c_int, C.c_int, C.c_int, vp, C.c_int64, C.c_int64, vp]
     _lib = L
     return L
 
@@ -208,7 +209,7 @@ class Model:
         self._c = make_config(cfg)
         self.tp_rank, self.tp_world = tp_rank, tp_world
         h = C.c_void_p()
-        q = {None: 0, "q8_0": 8}[quantize]
+        q = {None: 0, "q8_0": 8, "q4_k": 12}[quantize]
         _check(lib().msx_model_load_gguf_ex(gguf_path.encode(), C.byref(self._c), device, tp_rank, tp_world, q, C.byref(h)))
         self.h = h
 
@@ -561,6 +562,16 @@ def test_dequant_repacked(gtype: int, w_raw: np.ndarray, k: int, device: int = 0
     w_raw = np.ascontiguousarray(w_raw)
     out = np.empty((w_raw.shape[0], k), dtype=np.float32)
     _check(lib().msx_test_dequant_repacked(device, gtype, _p(w_raw), k, w_raw.shape[0], _p(out)))
+    return out
+
+
+def test_quantize_rows(dst_type: int, x: np.ndarray, src_type: int = 0, device: int = 0) -> np.ndarray:
+    """GGUF blocks of the on-load quantisers; x is [rows][k] f32 (src_type 0), f16 bits (1) or bf16 bits (30)"""
+    x = np.ascontiguousarray(x)
+    rows, k = x.shape
+    per = {8: (32, 34), 2: (32, 18), 12: (256, 144)}[dst_type]
+    out = np.empty((rows, k // per[0] * per[1]), dtype=np.uint8)
+    _check(lib().msx_test_quantize_rows(device, src_type, dst_type, _p(x), k, rows, _p(out)))
     return out
 
 

@@ -102,7 +102,7 @@ struct msx_model {
     // hidden slice [f0, f1); everything else (embeddings, text head, depformer) is replicated
     int tp_rank = 0, tp_world = 1;
     int heads_local = 0, adim = 0, h0 = 0, f0 = 0, hidden_local = 0;
-    int quantize = 0;                 // T_Q8_0: f32 / f16 / bf16 tensors of the file are quantised to Q8_0 while loading
+    int quantize = 0;                 // T_Q8_0 / T_Q4_K: f32 / f16 / bf16 tensors of the file are quantised while loading
     uint8_t *qstaging = nullptr; size_t qstaging_bytes = 0;
     std::vector<EmbTable> emb;        // [n_q+1]: text, audio 0..n_q-1
     EmbTable *d_emb = nullptr;        // device copy of `emb`
@@ -152,19 +152,29 @@ int ensure_staging(msx_model *m, size_t bytes) {
     return 0;
 }
 
-// quantise-on-load (moshi_lm_quantize "q8_0" on an unquantised file): the float rows already sit in m->staging; on return
-// *blocks points at GGUF-format Q8_0 rows on the device
-int quantize_staging_q8_0(msx_model *m, int src_type, int64_t K, int64_t rows, const uint8_t **blocks) {
-    if (K % 32) return fail(MSX_ERR_FORMAT, "q8_0 needs K % 32 == 0");
-    const size_t need = (size_t)(K / 32) * 34 * rows;
+// quantise-on-load (moshi_lm_quantize on an unquantised file): the float rows already sit in m->staging; on return
+// *blocks points at GGUF-format rows of dst_type (Q8_0, Q4_0 or Q4_K) on the device
+int quantize_staging(msx_model *m, int src_type, int dst_type, int64_t K, int64_t rows, const uint8_t **blocks) {
+    const int64_t rs = ggml_row_size(dst_type, K);
+    if (rs < 0) return fail(MSX_ERR_FORMAT, std::string("K is not a multiple of the block size of ") + ggml_type_name(dst_type));
+    const size_t need = (size_t)rs * rows;
     if (need > m->qstaging_bytes) {
         if (m->qstaging) cudaFree(m->qstaging);
         m->qstaging = nullptr; m->qstaging_bytes = 0;
         CU(cudaMalloc((void **)&m->qstaging, need));
         m->qstaging_bytes = need;
     }
-    const long long nblk = (long long)(K / 32) * rows;
-    quantize_rows_q8_0_kernel<<<(unsigned)((nblk * 32 + 255) / 256), 256>>>(m->staging, src_type, nblk, m->qstaging);
+    if (dst_type == T_Q4_K) {
+        const long long nblk = (long long)(K / 256) * rows;
+        quantize_rows_q4_K_kernel<<<(unsigned)((nblk * 8 + kQ4kQuantThreads - 1) / kQ4kQuantThreads), kQ4kQuantThreads>>>(
+            m->staging, src_type, nblk, m->qstaging);
+    } else {
+        const long long nblk = (long long)(K / 32) * rows;
+        const unsigned grid = (unsigned)((nblk * 32 + 255) / 256);
+        if (dst_type == T_Q8_0) quantize_rows_q8_0_kernel<<<grid, 256>>>(m->staging, src_type, nblk, m->qstaging);
+        else if (dst_type == T_Q4_0) quantize_rows_q4_0_kernel<<<grid, 256>>>(m->staging, src_type, nblk, m->qstaging);
+        else return fail(MSX_ERR_ARG, "quantise-on-load: unsupported target type");
+    }
     CU(cudaGetLastError());
     *blocks = m->qstaging;
     return 0;
@@ -173,16 +183,19 @@ bool is_float_type(int t) { return t == T_F32 || t == T_F16 || t == T_BF16; }
 
 // Upload a GGUF tensor [rows][K] and repack it into device tiles. perm_half: see repack kernels.
 int upload_linear(msx_model *m, const void *host, int type, int64_t K, int64_t rows, int perm_half, QLinear *out) {
-    const bool on_load = m->quantize == T_Q8_0 && is_float_type(type);
+    const bool on_load = m->quantize && is_float_type(type);
     if (type != T_Q4_K && type != T_Q8_0 && !on_load)
         return fail(MSX_ERR_FORMAT, std::string("linear weights must be q4_k or q8_0, got ") + ggml_type_name(type));
+    // loader.h:161-172 would fall back to Q4_0 rows for K % 256 != 0; the GEMV paths take Q4_K / Q8_0 only
+    if (on_load && m->quantize == T_Q4_K && K % 256)
+        return fail(MSX_ERR_FORMAT, "quantise-on-load q4_k: a linear with K % 256 != 0 would become q4_0, which the linears do not take");
     const int64_t rs = ggml_row_size(type, K);
     if (rs < 0) return fail(MSX_ERR_FORMAT, "K is not a multiple of the block size");
     const size_t raw = (size_t)rs * rows;
     if (int e = ensure_staging(m, raw)) return e;
     CU(cudaMemcpy(m->staging, host, raw, cudaMemcpyHostToDevice));
     const uint8_t *src_blocks = m->staging;
-    if (on_load) { if (int e = quantize_staging_q8_0(m, type, K, rows, &src_blocks)) return e; type = T_Q8_0; }
+    if (on_load) { if (int e = quantize_staging(m, type, m->quantize, K, rows, &src_blocks)) return e; type = m->quantize; }
     QLinear w;
     w.type = type; w.K = (int)K; w.rows = (int)rows; w.gs = K >= 4096 ? 32 : 16; w.gate = perm_half > 0;
     void *qs = nullptr, *sc = nullptr, *dd = nullptr;
@@ -211,13 +224,15 @@ int upload_table(msx_model *m, const void *host, int type, int64_t K, int64_t ro
     if (rs < 0 || type == T_Q4_K)
         return fail(MSX_ERR_FORMAT, std::string("embedding table type not supported: ") + ggml_type_name(type));
     void *d = nullptr;
-    if (m->quantize == T_Q8_0 && is_float_type(type) && K % 32 == 0) {
-        // the reference quantises embedding tables with the model (lm_utils.h:131-147): float rows -> Q8_0 rows
+    if (m->quantize && is_float_type(type) && K % 32 == 0) {
+        // the reference quantises embedding tables with the model (lm_utils.h:131-147): float rows -> Q8_0 rows for a
+        // q8_0 model, Q4_0 rows for a q4_k model
+        const int dst_type = m->quantize == T_Q4_K ? T_Q4_0 : T_Q8_0;
         if (int e = ensure_staging(m, (size_t)rs * rows)) return e;
         CU(cudaMemcpy(m->staging, host, (size_t)rs * rows, cudaMemcpyHostToDevice));
         const uint8_t *blocks = nullptr;
-        if (int e = quantize_staging_q8_0(m, type, K, rows, &blocks)) return e;
-        type = T_Q8_0; rs = ggml_row_size(type, K);
+        if (int e = quantize_staging(m, type, dst_type, K, rows, &blocks)) return e;
+        type = dst_type; rs = ggml_row_size(type, K);
         if (int e = dev_alloc(m, &d, (size_t)rs * rows)) return e;
         CU(cudaMemcpy(d, blocks, (size_t)rs * rows, cudaMemcpyDeviceToDevice));
         out->data = (const uint8_t *)d; out->type = type; out->K = (int)K; out->rows = (int)rows; out->row_bytes = (int)rs;
@@ -246,7 +261,7 @@ struct Loader {
         if ((K > 0 && t->ne[0] != K) || (rows > 0 && t->ne[1] != rows))
             return fail(MSX_ERR_FORMAT, "shape mismatch for " + name + ": got [" + std::to_string(t->ne[0]) + "," +
                                             std::to_string(t->ne[1]) + "], want [" + std::to_string(K) + "," + std::to_string(rows) + "]");
-        linear_bytes = (m->quantize == T_Q8_0 && is_float_type(t->type)) ? t->ne[1] * (t->ne[0] / 32 * 34) : t->nbytes;
+        linear_bytes = (m->quantize && is_float_type(t->type)) ? t->ne[1] * ggml_row_size(m->quantize, t->ne[0]) : t->nbytes;
         return upload_linear(m, t->data, t->type, t->ne[0], t->ne[1], perm_half, out);
     }
     // tensor-parallel shard of a linear: the listed row ranges (concatenated) x the K-slice [k0, k1) of every row
@@ -319,7 +334,7 @@ extern "C" int msx_model_load_gguf_tp(const char *path, const msx_config *cfg, i
 extern "C" int msx_model_load_gguf_ex(const char *path, const msx_config *cfg, int device, int tp_rank, int tp_world, int quantize,
                                       msx_model **out) {
     if (!path || !out) return fail(MSX_ERR_ARG, "null argument");
-    if (quantize != 0 && quantize != T_Q8_0) return fail(MSX_ERR_ARG, "quantise-on-load supports q8_0 (8) only; q4_k files must be quantised beforehand");
+    if (quantize != 0 && quantize != T_Q8_0 && quantize != T_Q4_K) return fail(MSX_ERR_ARG, "quantise-on-load takes 0 (as is), 8 (q8_0) or 12 (q4_k)");
     if (quantize && tp_world > 1) return fail(MSX_ERR_ARG, "quantise-on-load is not combined with tensor-parallel shards");
     *out = nullptr;
     if (int e = check_config(cfg)) return e;
@@ -449,6 +464,8 @@ extern "C" int msx_model_load_gguf_ex(const char *path, const msx_config *cfg, i
             if (!t) return MSX_ERR_FORMAT;
             if (t->type != T_Q4_0 && t->type != T_Q8_0 && !(m->quantize && is_float_type(t->type)))
                 return fail(MSX_ERR_FORMAT, name + ": small projections must be q4_0 or q8_0");
+            if (m->quantize == T_Q4_K && is_float_type(t->type) && de % 256 == 0)
+                return fail(MSX_ERR_FORMAT, name + ": the reference would make this projection q4_k (K % 256 == 0); small projections take q4_0 / q8_0");
             return L.table(name, de, dd, out);
         };
         if (int e = L.table("lm.depformer_text_emb.weight", de, c.text_card + 1, &m->dep_text_emb)) return e;
@@ -2037,6 +2054,22 @@ extern "C" int msx_test_dequant_repacked(int device, int type, const void *w, in
     dequant_repacked_kernel<<<(unsigned)((n + 255) / 256), 256>>>(ql, o);
     CU(cudaGetLastError());
     CU(cudaMemcpy(out, o, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// GGUF blocks of the on-load quantisers (dst_type 8 = Q8_0, 2 = Q4_0, 12 = Q4_K) for `rows` rows of k f32 / f16 / bf16 values
+extern "C" int msx_test_quantize_rows(int device, int src_type, int dst_type, const void *x, int64_t k, int64_t rows, void *out) {
+    if (!x || !out) return fail(MSX_ERR_ARG, "null argument");
+    if (!is_float_type(src_type)) return fail(MSX_ERR_ARG, "source must be f32 / f16 / bf16");
+    std::unique_ptr<msx_model> m;
+    if (int e = test_setup(device, m)) return e;
+    const size_t raw = (size_t)ggml_row_size(src_type, k) * rows;
+    if (int e = ensure_staging(m.get(), raw)) return e;
+    CU(cudaMemcpy(m->staging, x, raw, cudaMemcpyHostToDevice));
+    const uint8_t *blocks = nullptr;
+    if (int e = quantize_staging(m.get(), src_type, dst_type, k, rows, &blocks)) return e;
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(out, blocks, (size_t)ggml_row_size(dst_type, k) * rows, cudaMemcpyDeviceToHost));
     return 0;
 }
 

@@ -167,6 +167,178 @@ __global__ void quantize_rows_q8_0_kernel(const uint8_t *src, int src_type, long
     reinterpret_cast<int8_t *>(blk + 2)[lane] = (int8_t)q;
 }
 
+// ---- quantise-on-load, q4_k models: Q4_0 for the embedding tables (lm_utils.h:131-147), Q4_K for the linears ----------
+__device__ __forceinline__ float load_src_element(const uint8_t *src, int src_type, long long e) {
+    if (src_type == 0) return reinterpret_cast<const float *>(src)[e];
+    if (src_type == 1) return __half2float(reinterpret_cast<const __half *>(src)[e]);
+    return bf16_bits_to_f32(reinterpret_cast<const uint16_t *>(src)[e]);
+}
+
+// ggml quantize_row_q4_0_ref: the FIRST element of largest magnitude keeps its sign, d = that / -8,
+// q = min(15, trunc(x * (1 / d) + 8.5)); low nibbles = elements 0..15, high = 16..31.  One warp per block.
+__global__ void quantize_rows_q4_0_kernel(const uint8_t *src, int src_type, long long n_blocks, uint8_t *dst) {
+    const long long b = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (b >= n_blocks) return;
+    const float x = load_src_element(src, src_type, b * 32 + lane);
+    const float amax = warp_max(fabsf(x));
+    const unsigned first = __ballot_sync(0xffffffffu, fabsf(x) == amax);
+    const float carrier = amax > 0.f ? __shfl_sync(0xffffffffu, x, __ffs(first) - 1) : 0.f;
+    const float d = carrier * -0.125f;
+    const float id = d ? __fdiv_rn(1.0f, d) : 0.0f;
+    int q = (int)(int8_t)(int)__fadd_rn(__fmul_rn(x, id), 8.5f);
+    q = min(q, 15);
+    const int hi = __shfl_down_sync(0xffffffffu, q, 16);
+    uint8_t *blk = dst + b * 18;
+    if (lane == 0) *reinterpret_cast<__half *>(blk) = __float2half_rn(d);
+    if (lane < 16) blk[2 + lane] = (uint8_t)(q | (hi << 4));
+}
+
+// ggml quantize_row_q4_K_ref + make_qkx2_quants(32, 15, ..., rmin -1, rdelta 0.1, nstep 20): eight threads per
+// 256-element block, one per 32-element sub-block, each running the scalar search with the same sequential fp32
+// arithmetic (explicit _rn intrinsics: no contraction) so that the blocks equal the CPU quantiser's bit for bit.
+constexpr int kQ4kQuantThreads = 128;
+__device__ __forceinline__ int clamp_nibble(int v) { return max(0, min(15, v)); }
+__device__ __forceinline__ uint32_t spread_nibbles4(uint32_t h) {          // 4 nibbles (16 bits) -> 4 bytes
+    uint32_t v = h & 0xFFFFu;
+    v = (v | (v << 8)) & 0x00FF00FFu;
+    return (v | (v << 4)) & 0x0F0F0F0Fu;
+}
+__global__ void __launch_bounds__(kQ4kQuantThreads) quantize_rows_q4_K_kernel(const uint8_t *src, int src_type, long long n_blocks,
+                                                                              uint8_t *dst) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = (t >> 3) < n_blocks;
+    const long long b = live ? (t >> 3) : n_blocks - 1;      // idle tail threads redo the last block (shuffles stay full)
+    const int j = (int)(t & 7);
+    float x[32];
+#pragma unroll
+    for (int l = 0; l < 32; l++) x[l] = load_src_element(src, src_type, b * 256 + j * 32 + l);
+    float sum_x2 = 0.f;
+#pragma unroll
+    for (int l = 0; l < 32; l++) sum_x2 = __fadd_rn(sum_x2, __fmul_rn(x[l], x[l]));
+    const float av_x = __fsqrt_rn(__fmul_rn(sum_x2, 0.03125f));
+    auto weight = [&](int l) { return __fadd_rn(av_x, fabsf(x[l])); };
+
+    // ---- make_qkx2_quants ----
+    float lo = x[0], hi = x[0], sum_w = weight(0), sum_x = __fmul_rn(sum_w, x[0]);
+#pragma unroll
+    for (int l = 1; l < 32; l++) {
+        lo = x[l] < lo ? x[l] : lo;
+        hi = x[l] > hi ? x[l] : hi;
+        const float w = weight(l);
+        sum_w = __fadd_rn(sum_w, w);
+        sum_x = __fadd_rn(sum_x, __fmul_rn(w, x[l]));
+    }
+    if (lo > 0.f) lo = 0.f;
+    uint32_t L[4] = {0u, 0u, 0u, 0u};
+    float scale = 0.f;
+    if (hi != lo) {
+        float iscale = __fdiv_rn(15.f, __fsub_rn(hi, lo));
+        scale = __fdiv_rn(1.f, iscale);
+        float best = 0.f;
+#pragma unroll
+        for (int l = 0; l < 32; l++) {
+            const int q = clamp_nibble(__float2int_rn(__fmul_rn(iscale, __fsub_rn(x[l], lo))));
+            L[l >> 3] |= (uint32_t)q << (4 * (l & 7));
+            const float diff = __fsub_rn(__fadd_rn(__fmul_rn(scale, (float)q), lo), x[l]);
+            best = __fadd_rn(best, __fmul_rn(weight(l), __fmul_rn(diff, diff)));
+        }
+#pragma unroll 1
+        for (int is = 0; is <= 20; is++) {
+            iscale = __fdiv_rn(__fadd_rn(__fadd_rn(-1.f, __fmul_rn(0.1f, (float)is)), 15.f), __fsub_rn(hi, lo));
+            uint32_t A[4] = {0u, 0u, 0u, 0u};
+            float sum_l = 0.f, sum_l2 = 0.f, sum_xl = 0.f;
+#pragma unroll
+            for (int l = 0; l < 32; l++) {
+                const int q = clamp_nibble(__float2int_rn(__fmul_rn(iscale, __fsub_rn(x[l], lo))));
+                A[l >> 3] |= (uint32_t)q << (4 * (l & 7));
+                const float wl = __fmul_rn(weight(l), (float)q);
+                sum_l = __fadd_rn(sum_l, wl);
+                sum_l2 = __fadd_rn(sum_l2, __fmul_rn(wl, (float)q));
+                sum_xl = __fadd_rn(sum_xl, __fmul_rn(wl, x[l]));
+            }
+            const float D = __fsub_rn(__fmul_rn(sum_w, sum_l2), __fmul_rn(sum_l, sum_l));
+            if (D > 0.f) {
+                float this_scale = __fdiv_rn(__fsub_rn(__fmul_rn(sum_w, sum_xl), __fmul_rn(sum_x, sum_l)), D);
+                float this_min = __fdiv_rn(__fsub_rn(__fmul_rn(sum_l2, sum_x), __fmul_rn(sum_l, sum_xl)), D);
+                if (this_min > 0.f) { this_min = 0.f; this_scale = __fdiv_rn(sum_xl, sum_l2); }
+                float err = 0.f;
+#pragma unroll
+                for (int l = 0; l < 32; l++) {
+                    const float q = (float)((A[l >> 3] >> (4 * (l & 7))) & 15u);
+                    const float diff = __fsub_rn(__fadd_rn(__fmul_rn(this_scale, q), this_min), x[l]);
+                    err = __fadd_rn(err, __fmul_rn(weight(l), __fmul_rn(diff, diff)));
+                }
+                if (err < best) {
+                    L[0] = A[0]; L[1] = A[1]; L[2] = A[2]; L[3] = A[3];
+                    best = err; scale = this_scale; lo = this_min;
+                }
+            }
+        }
+    }
+    const float neg_min = -lo;
+
+    // ---- block level: 6-bit scales / mins against the block maxima, then the final rounding of every element ----
+    float max_scale = fmaxf(scale, 0.f), max_min = fmaxf(neg_min, 0.f);
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+        max_scale = fmaxf(max_scale, __shfl_xor_sync(0xffffffffu, max_scale, o));
+        max_min = fmaxf(max_min, __shfl_xor_sync(0xffffffffu, max_min, o));
+    }
+    const float inv_scale = max_scale > 0.f ? __fdiv_rn(63.f, max_scale) : 0.f;
+    const float inv_min = max_min > 0.f ? __fdiv_rn(63.f, max_min) : 0.f;
+    const int ls = min(63, __float2int_rn(__fmul_rn(inv_scale, scale)) & 255);
+    const int lm = min(63, __float2int_rn(__fmul_rn(inv_min, neg_min)) & 255);
+    const __half d16 = __float2half_rn(__fdiv_rn(max_scale, 63.f)), dmin16 = __float2half_rn(__fdiv_rn(max_min, 63.f));
+    const float d = __fmul_rn(__half2float(d16), (float)ls);
+    if (d != 0.f) {
+        const float dm = __fmul_rn(__half2float(dmin16), (float)lm);
+        L[0] = L[1] = L[2] = L[3] = 0u;
+#pragma unroll
+        for (int l = 0; l < 32; l++) {
+            const int q = clamp_nibble(__float2int_rn(__fdiv_rn(__fadd_rn(x[l], dm), d)));
+            L[l >> 3] |= (uint32_t)q << (4 * (l & 7));
+        }
+    }
+    const int lane = threadIdx.x & 31, base = lane & ~7;
+    uint32_t lsv[8], lmv[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        lsv[k] = (uint32_t)__shfl_sync(0xffffffffu, ls, base + k);
+        lmv[k] = (uint32_t)__shfl_sync(0xffffffffu, lm, base + k);
+    }
+    uint32_t P[4];                        // partner sub-block's nibbles (2p <-> 2p+1 share 32 bytes of qs)
+#pragma unroll
+    for (int k = 0; k < 4; k++) P[k] = __shfl_xor_sync(0xffffffffu, L[k], 1);
+    if (!live) return;
+    uint8_t *blk = dst + b * 144;
+    if (j == 0) {
+        uint32_t sb[12];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            sb[k] = lsv[k] | ((lsv[k + 4] >> 4) << 6);
+            sb[k + 4] = lmv[k] | ((lmv[k + 4] >> 4) << 6);
+            sb[k + 8] = (lsv[k + 4] & 0xFu) | ((lmv[k + 4] & 0xFu) << 4);
+        }
+        uint4 head;
+        head.x = (uint32_t)__half_as_ushort(d16) | ((uint32_t)__half_as_ushort(dmin16) << 16);
+        head.y = sb[0] | (sb[1] << 8) | (sb[2] << 16) | (sb[3] << 24);
+        head.z = sb[4] | (sb[5] << 8) | (sb[6] << 16) | (sb[7] << 24);
+        head.w = sb[8] | (sb[9] << 8) | (sb[10] << 16) | (sb[11] << 24);
+        *reinterpret_cast<uint4 *>(blk) = head;
+    }
+    // bytes [16*(j&1), +16) of pair j>>1: byte l = even sub-block's nibble l | odd sub-block's nibble l << 4
+    const int half = j & 1;
+    const uint32_t e0 = half ? P[2] : L[0], e1 = half ? P[3] : L[1];       // even sub-block's nibbles 16*half .. +15
+    const uint32_t o0 = half ? L[2] : P[0], o1 = half ? L[3] : P[1];       // odd sub-block's
+    uint4 q;
+    q.x = spread_nibbles4(e0) | (spread_nibbles4(o0) << 4);
+    q.y = spread_nibbles4(e0 >> 16) | (spread_nibbles4(o0 >> 16) << 4);
+    q.z = spread_nibbles4(e1) | (spread_nibbles4(o1) << 4);
+    q.w = spread_nibbles4(e1 >> 16) | (spread_nibbles4(o1 >> 16) << 4);
+    *reinterpret_cast<uint4 *>(blk + 16 + (j >> 1) * 32 + half * 16) = q;
+}
+
 // ---- load-time repack (GGUF row-major blocks -> device tiles, see common.cuh QLinear) --------------
 // perm_half > 0 interleaves rows for the gated MLP: stored row v <- source row (v&1 ? perm_half + v/2 : v/2)
 __device__ __forceinline__ int src_row_of(int v, int perm_half) { return perm_half > 0 ? ((v & 1) ? perm_half + (v >> 1) : (v >> 1)) : v; }

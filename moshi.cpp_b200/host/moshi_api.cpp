@@ -173,8 +173,9 @@ void moshi_lm_set_delay_steps(moshi_lm_t *lm, int d) { lm->delay_steps = d; }
 int moshi_lm_get_max_delay(moshi_lm_t *lm) { int m = lm->cfg.delays[0]; for (int i = 0; i < lm->cfg.n_delays; i++) m = std::max(m, lm->cfg.delays[i]); return m; }
 int moshi_lm_get_delay_steps(moshi_lm_t *lm) { return lm->delay_steps; }
 bool moshi_lm_quantize(moshi_lm_t *lm, const char *quant) {
-    // reference: q4_0 / q4_k / q8_0 accepted, anything else false (moshi.cpp:654-673).  q8_0 is applied while loading when
-    // the GGUF holds f32 / f16 / bf16 tensors; q4_k / q4_0 files must already carry that type.
+    // reference: q4_0 / q4_k / q8_0 accepted, anything else false (moshi.cpp:654-673).  q8_0 and q4_k are applied while
+    // loading when the GGUF holds f32 / f16 / bf16 tensors; a q4_0 model must already be a q4_0 file (and its linears are
+    // rejected by the loader: the GEMV paths take q4_k / q8_0).
     const std::string q = quant ? quant : "";
     if (q != "q4_0" && q != "q4_k" && q != "q8_0") return false;
     lm->want_quant = q;
@@ -182,9 +183,10 @@ bool moshi_lm_quantize(moshi_lm_t *lm, const char *quant) {
 }
 int moshi_lm_load(moshi_lm_t *lm) {
     if (lm->model) return 0;
-    // moshi_lm_quantize("q8_0") on an unquantised (f32 / f16 / bf16) GGUF: quantise while loading like the reference
-    // (loader.h:149-233); already-quantised tensors are taken as they are
-    return msx_model_load_gguf_ex(lm->filepath.c_str(), &lm->cfg, lm->device, 0, 1, lm->want_quant == "q8_0" ? 8 : 0, &lm->model);
+    // moshi_lm_quantize("q8_0" / "q4_k") on an unquantised (f32 / f16 / bf16) GGUF: quantise while loading like the
+    // reference (loader.h:149-233); already-quantised tensors are taken as they are
+    const int q = lm->want_quant == "q8_0" ? 8 : lm->want_quant == "q4_k" ? 12 : 0;
+    return msx_model_load_gguf_ex(lm->filepath.c_str(), &lm->cfg, lm->device, 0, 1, q, &lm->model);
 }
 
 // ---- TTS text scheduling: TokenIds / State / StateMachine (src/moshi/models/lm.h:5-194) -------------------------

@@ -136,6 +136,129 @@ void orc_quantize_row_q8_0(const float *x, void *dst, int64_t k) {
     }
 }
 
+/* quantize_row_q4_0_ref (ggml-quants.c; cross-checked bit for bit with gguf/quants.py Q4_0.quantize_blocks):
+ * the element of largest magnitude keeps its sign, d = that / -8, q = min(15, trunc(x / d + 8.5)). */
+void orc_quantize_row_q4_0(const float *x, void *dst, int64_t k) {
+    block_q4_0 *y = dst;
+    for (int64_t i = 0; i < k / QK4_0; i++) {
+        const float *xb = x + i * QK4_0;
+        float amax = 0.0f, carrier = 0.0f;
+        for (int j = 0; j < QK4_0; j++) if (amax < fabsf(xb[j])) { amax = fabsf(xb[j]); carrier = xb[j]; }
+        const float d = carrier / -8;
+        const float id = d ? 1.0f / d : 0.0f;
+        y[i].d = orc_fp32_to_fp16(d);
+        for (int j = 0; j < QK4_0 / 2; j++) {
+            const int lo = (int8_t)(xb[j] * id + 8.5f), hi = (int8_t)(xb[QK4_0 / 2 + j] * id + 8.5f);
+            y[i].qs[j] = (uint8_t)((lo < 15 ? lo : 15) | ((hi < 15 ? hi : 15) << 4));
+        }
+    }
+}
+
+/* make_qkx2_quants (ggml-quants.c) as quantize_row_q4_K_ref calls it: n = 32, nmax = 15, rmin = -1, rdelta = 0.1,
+ * nstep = 20, squared error.  Weighted least squares for x ~ scale * L + min over a grid of 21 candidate inverse
+ * scales; returns scale, *neg_min = -min (>= 0).  All sums run sequentially in fp32 like the scalar C code. */
+static float q4k_fit_sub_block(const float *x, const float *w, uint8_t *L, float *neg_min) {
+    enum { N = 32, NMAX = 15 };
+    uint8_t Laux[N];
+    float lo = x[0], hi = x[0], sum_w = w[0], sum_x = sum_w * x[0];
+    for (int i = 1; i < N; i++) {
+        if (x[i] < lo) lo = x[i];
+        if (x[i] > hi) hi = x[i];
+        sum_w += w[i];
+        sum_x += w[i] * x[i];
+    }
+    if (lo > 0) lo = 0;
+    if (hi == lo) { memset(L, 0, N); *neg_min = -lo; return 0.f; }
+    float iscale = NMAX / (hi - lo), scale = 1 / iscale, best = 0;
+    for (int i = 0; i < N; i++) {
+        int l = nearest_int(iscale * (x[i] - lo));
+        L[i] = (uint8_t)(l < 0 ? 0 : l > NMAX ? NMAX : l);
+        float diff = scale * L[i] + lo - x[i];
+        best += w[i] * (diff * diff);
+    }
+    for (int is = 0; is <= 20; is++) {
+        iscale = (-1.f + 0.1f * is + NMAX) / (hi - lo);
+        float sum_l = 0, sum_l2 = 0, sum_xl = 0;
+        for (int i = 0; i < N; i++) {
+            int l = nearest_int(iscale * (x[i] - lo));
+            l = l < 0 ? 0 : l > NMAX ? NMAX : l;
+            Laux[i] = (uint8_t)l;
+            sum_l += w[i] * l;
+            sum_l2 += w[i] * l * l;
+            sum_xl += w[i] * l * x[i];
+        }
+        const float D = sum_w * sum_l2 - sum_l * sum_l;
+        if (D > 0) {
+            float this_scale = (sum_w * sum_xl - sum_x * sum_l) / D;
+            float this_min = (sum_l2 * sum_x - sum_l * sum_xl) / D;
+            if (this_min > 0) { this_min = 0; this_scale = sum_xl / sum_l2; }
+            float err = 0;
+            for (int i = 0; i < N; i++) {
+                float diff = this_scale * Laux[i] + this_min - x[i];
+                err += w[i] * (diff * diff);
+            }
+            if (err < best) { memcpy(L, Laux, N); best = err; scale = this_scale; lo = this_min; }
+        }
+    }
+    *neg_min = -lo;
+    return scale;
+}
+
+/* quantize_row_q4_K_ref (ggml-quants.c): per 32-element sub-block a (scale, min) fit with weights rms(x) + |x|,
+ * the 8 scales / mins quantised to 6 bits against the block maxima (d = max_scale / 63, dmin = max_min / 63, fp16),
+ * then every element re-rounded against the quantised scale / min: q = clamp(nearest_int((x + dmin*m) / (d*sc)), 0, 15).
+ * Reference call site: ggml_cast in src/loader.h:183 (quantise while loading). */
+void orc_quantize_row_q4_K(const float *x, void *dst, int64_t k) {
+    block_q4_K *y = dst;
+    for (int64_t i = 0; i < k / QK_K; i++, x += QK_K) {
+        uint8_t L[QK_K];
+        float scales[QK_K / 32], mins[QK_K / 32], w[32];
+        float max_scale = 0, max_min = 0;
+        for (int j = 0; j < QK_K / 32; j++) {
+            const float *xb = x + 32 * j;
+            float sum_x2 = 0;
+            for (int l = 0; l < 32; l++) sum_x2 += xb[l] * xb[l];
+            const float av_x = sqrtf(sum_x2 / 32);
+            for (int l = 0; l < 32; l++) w[l] = av_x + fabsf(xb[l]);
+            scales[j] = q4k_fit_sub_block(xb, w, L + 32 * j, &mins[j]);
+            if (scales[j] > max_scale) max_scale = scales[j];
+            if (mins[j] > max_min) max_min = mins[j];
+        }
+        const float inv_scale = max_scale > 0 ? 63.f / max_scale : 0.f;
+        const float inv_min = max_min > 0 ? 63.f / max_min : 0.f;
+        memset(y[i].scales, 0, sizeof(y[i].scales));
+        for (int j = 0; j < QK_K / 32; j++) {
+            int ls = nearest_int(inv_scale * scales[j]), lm = nearest_int(inv_min * mins[j]);
+            ls = (uint8_t)ls; lm = (uint8_t)lm;
+            if (ls > 63) ls = 63;
+            if (lm > 63) lm = 63;
+            if (j < 4) { y[i].scales[j] = (uint8_t)ls; y[i].scales[j + 4] = (uint8_t)lm; }
+            else {
+                y[i].scales[j + 4] = (uint8_t)((ls & 0xF) | ((lm & 0xF) << 4));
+                y[i].scales[j - 4] |= (uint8_t)((ls >> 4) << 6);
+                y[i].scales[j] |= (uint8_t)((lm >> 4) << 6);
+            }
+        }
+        y[i].d = orc_fp32_to_fp16(max_scale / 63.f);
+        y[i].dmin = orc_fp32_to_fp16(max_min / 63.f);
+        const float fd = orc_fp16_to_fp32(y[i].d), fdmin = orc_fp16_to_fp32(y[i].dmin);
+        for (int j = 0; j < QK_K / 32; j++) {
+            uint8_t sc, m;
+            get_scale_min_k4(j, y[i].scales, &sc, &m);
+            const float d = fd * sc;
+            if (!d) continue;
+            const float dm = fdmin * m;
+            for (int l = 0; l < 32; l++) {
+                int q = nearest_int((x[32 * j + l] + dm) / d);
+                L[32 * j + l] = (uint8_t)(q < 0 ? 0 : q > 15 ? 15 : q);
+            }
+        }
+        uint8_t *q = y[i].qs;
+        for (int j = 0; j < QK_K; j += 64, q += 32)
+            for (int l = 0; l < 32; l++) q[l] = (uint8_t)(L[j + l] | (L[j + l + 32] << 4));
+    }
+}
+
 /* quantize_row_q8_K_ref: iscale = -127/max(|x|-carrier), q = min(127, nearest_int(iscale*x)), d = 1/iscale */
 void orc_quantize_row_q8_K(const float *x, int8_t *qs, float *dout, int16_t *bsums, int64_t k) {
     for (int64_t i = 0; i < k / QK_K; i++) {

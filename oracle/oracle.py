@@ -52,6 +52,8 @@ def lib():
         L.orc_dequantize_row.argtypes = [C.c_int, vp, vp, C.c_int64]
         L.orc_quantize_row_q8_0.argtypes = [vp, vp, C.c_int64]
         L.orc_quantize_row_q8_K.argtypes = [vp, vp, vp, vp, C.c_int64]
+        L.orc_quantize_row_q4_0.argtypes = [vp, vp, C.c_int64]
+        L.orc_quantize_row_q4_K.argtypes = [vp, vp, C.c_int64]
         L.orc_mul_mat_vec.argtypes = [C.c_int, vp, C.c_int64, C.c_int64, vp, vp]
         L.orc_mul_mat_vec_ideal.argtypes = [C.c_int, vp, C.c_int64, C.c_int64, vp, vp]
         L.orc_rms_norm.argtypes = [vp, vp, C.c_float, vp, C.c_int64]
@@ -123,6 +125,21 @@ def quantize_q8_0(x: np.ndarray) -> np.ndarray:
     x = np.ascontiguousarray(x, dtype=np.float32)
     out = np.empty(x.size // 32 * 34, dtype=np.uint8)
     lib().orc_quantize_row_q8_0(_p(x), _p(out), x.size)
+    return out
+
+
+def quantize_q4_0(x: np.ndarray) -> np.ndarray:
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    out = np.empty(x.size // 32 * 18, dtype=np.uint8)
+    lib().orc_quantize_row_q4_0(_p(x), _p(out), x.size)
+    return out
+
+
+def quantize_q4_K(x: np.ndarray) -> np.ndarray:
+    """quantize_row_q4_K_ref restated (scale / min search per 32-element sub-block); x.size % 256 == 0"""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    out = np.empty(x.size // 256 * 144, dtype=np.uint8)
+    lib().orc_quantize_row_q4_K(_p(x), _p(out), x.size)
     return out
 
 

@@ -571,11 +571,56 @@ def test_generator_prefill_equals_provided_steps(msx, gguf_for):
         assert ra[0] == rb[0] and ra[1] == rb[1] and np.array_equal(ra[2], rb[2]), f"frame {f}"
 
 
-@pytest.mark.parametrize("preset,src", [("tiny", "bf16"), ("tiny_stt", "f16"), ("tiny_lowrank", "bf16")])
-def test_quantize_on_load_q8_0(msx, orc, preset, src, tmp_path):
-    """SURVEY.md §8f rank 3 (q8_0 half): an unquantised GGUF loaded with quantize="q8_0" (GPU quantize_row_q8_0 of every linear
-    and embedding table) == the same weights quantised offline with gguf-py (ggml's own Q8_0 quantiser, pinned in
-    tests/test_oracle_pins.py) and run through the oracle."""
+def _quant_cases(rng, k, rows):
+    """rows of k values with the edge cases the quantisers branch on"""
+    x = (rng.standard_normal((rows, k)) * 0.05).astype(np.float32)
+    x[0, :32] = 0.0                                    # all-zero sub-block
+    x[1] = 0.0                                         # all-zero row
+    x[2, :64] = 0.125                                  # constant positive (max == min after the clamp at 0 is false: 0 .. 0.125)
+    x[3, :32] = -0.25                                  # constant negative: hi == lo, scale 0, min 0.25
+    x[4] = np.abs(x[4])                                # all positive: min clamps to 0
+    x[5] *= np.repeat(np.float32(2.0) ** (np.arange(k // 32) % 12 - 6), 32)   # sub-block scales spread over 2^11
+    x[6, ::2] = x[6, 1::2]                             # ties for the carrier / max
+    x[7] *= 1e-6                                       # tiny magnitudes (fp16 d goes subnormal)
+    x[8] *= 300.0                                      # large magnitudes
+    return x
+
+
+@pytest.mark.parametrize("dst,k", [("q4_k", 256), ("q4_k", 4096), ("q4_0", 128), ("q4_0", 4096), ("q8_0", 1024)])
+@pytest.mark.parametrize("src", ["f32", "bf16", "f16"])
+def test_quantize_rows_bit_exact(msx, orc, dst, k, src):
+    """the GPU on-load quantisers produce the CPU quantiser's GGUF blocks bit for bit
+    (quantize_row_q4_K incl. the make_qkx2_quants search, quantize_row_q4_0, quantize_row_q8_0); the Q4_0 / Q8_0 oracles
+    are pinned against gguf-py in tests/test_oracle_pins.py."""
+    rng = np.random.default_rng(101)
+    x = _quant_cases(rng, k, 40)
+    if src == "bf16":
+        bits = ((x.view(np.uint32) + 0x7FFF + ((x.view(np.uint32) >> 16) & 1)) >> 16).astype(np.uint16)
+        dev_in, st = bits, 30
+        x = (bits.astype(np.uint32) << 16).view(np.float32)
+    elif src == "f16":
+        h = x.astype(np.float16)
+        dev_in, st = h.view(np.uint16), 1
+        x = h.astype(np.float32)
+    else:
+        dev_in, st = x, 0
+    gt = {"q4_k": 12, "q4_0": 2, "q8_0": 8}[dst]
+    got = msx.test_quantize_rows(gt, dev_in, src_type=st)
+    fn = {"q4_k": orc.quantize_q4_K, "q4_0": orc.quantize_q4_0, "q8_0": orc.quantize_q8_0}[dst]
+    ref = np.stack([fn(x[r]) for r in range(x.shape[0])])
+    bad = np.argwhere(got != ref)
+    assert bad.size == 0, f"{len(bad)} bytes differ, first at row {bad[0][0]} byte {bad[0][1]}"
+
+
+_TABLE_RE = __import__("re").compile(r"(^|\.)(text_emb|emb\.\d+|depformer_emb\.\d+|depformer_text_emb)\.weight$")
+
+
+@pytest.mark.parametrize("preset,src,quant", [("tiny", "bf16", "q8_0"), ("tiny_stt", "f16", "q8_0"), ("tiny_lowrank", "bf16", "q8_0"),
+                                              ("tiny", "bf16", "q4_k"), ("tiny_stt", "f16", "q4_k"), ("tiny_lowrank", "bf16", "q4_k")])
+def test_quantize_on_load(msx, orc, preset, src, quant, tmp_path):
+    """an unquantised GGUF loaded with quantize="q8_0" / "q4_k" (every linear and embedding table
+    quantised on the GPU with the reference's type rules, loader.h:161-172, lm_utils.h:131-147) == the same weights
+    quantised offline on the CPU (gguf-py's Q8_0; the oracle's quantize_row_q4_K / q4_0) and run through the oracle."""
     import gguf
     from moshi_cpp_b200 import configs, synth
     cfg = configs.get(preset)
@@ -594,13 +639,18 @@ def test_quantize_on_load_q8_0(msx, orc, preset, src, tmp_path):
                 f32 = raw.view(np.float16).astype(np.float32)
             else:
                 f32 = raw.view(np.float32)
-            q = gguf.quants.quantize(f32.reshape(rows, k), gguf.GGMLQuantizationType.Q8_0)
-            twin.append((t.name, synth.GGML_Q8_0, k, rows, np.ascontiguousarray(q).view(np.uint8).reshape(-1)))
+            if quant == "q8_0":
+                q = gguf.quants.quantize(f32.reshape(rows, k), gguf.GGMLQuantizationType.Q8_0)
+                twin.append((t.name, synth.GGML_Q8_0, k, rows, np.ascontiguousarray(q).view(np.uint8).reshape(-1)))
+            elif _TABLE_RE.search(t.name) or k % 256:
+                twin.append((t.name, synth.GGML_Q4_0, k, rows, orc.quantize_q4_0(f32)))
+            else:
+                twin.append((t.name, synth.GGML_Q4_K, k, rows, orc.quantize_q4_K(f32)))
         else:
             twin.append((t.name, gt, k, rows, raw))
-    qp = str(tmp_path / f"{preset}-q8_0-twin.gguf")
+    qp = str(tmp_path / f"{preset}-{quant}-twin.gguf")
     synth.write_gguf_tensors(qp, twin)
-    gm = msx.Model(fp, cfg, quantize="q8_0"); gs = msx.Stream(gm)
+    gm = msx.Model(fp, cfg, quantize=quant); gs = msx.Stream(gm)
     g2 = msx.Stream(msx.Model(qp, cfg))                     # the offline-quantised twin through the GPU path too
     om = orc.Model(qp, cfg); os_ = orc.State(om)
     assert gm.weight_bytes_per_frame == msx.Model(qp, cfg).weight_bytes_per_frame
@@ -610,7 +660,7 @@ def test_quantize_on_load_q8_0(msx, orc, preset, src, tmp_path):
         t_ref, lg_ref, _ = os_.step_temporal(toks)
         t_gpu, lg_gpu, _ = gs.step_temporal(toks)
         t_g2, lg_g2, _ = g2.step_temporal(toks)
-        assert np.array_equal(lg_gpu.view(np.uint32), lg_g2.view(np.uint32)), f"frame {f}: on-load quantisation != offline Q8_0 file"
+        assert np.array_equal(lg_gpu.view(np.uint32), lg_g2.view(np.uint32)), f"frame {f}: on-load quantisation != offline {quant} file"
         assert max_rel(lg_gpu, lg_ref) < LOGIT_TOL and t_gpu == t_ref, f"frame {f}"
         nxt = [t_ref]
         if cfg["dep_q"] > 0:
