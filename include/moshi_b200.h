@@ -131,6 +131,12 @@ MSX_API int msx_model_load_gguf_tp(const char *path, const msx_config *cfg, int 
  * sequential fp32 arithmetic), embedding tables and K % 256 != 0 projections Q4_0 (quantize_row_q4_0).  0 = take the
  * file as it is.  Already quantised tensors are never touched. */
 MSX_API int msx_model_load_gguf_ex(const char *path, const msx_config *cfg, int device, int tp_rank, int tp_world, int quantize, msx_model **out);
+/* GGUF -> GGUF quantiser: every f32 / f16 / bf16 2-D "lm." tensor of in_path is quantised on the GPU with the rules of
+ * msx_model_load_gguf_ex (linears -> quantize, Q4_K needs K % 256 == 0 else Q4_0, needs K % 32 == 0 else unchanged; embedding
+ * tables of a q4_k model -> Q4_0), everything else is copied; out_path is GGUF v3 without key/value pairs, like the
+ * reference's own files.  Replaces `-q <quant> -g out.gguf` (moshi_lm_quantize + moshi_lm_save_gguf, src/moshi.cpp:654-695,
+ * WeightLoader::save_gguf src/loader.h:227-233). */
+MSX_API int msx_gguf_quantize(const char *in_path, const char *out_path, int quantize, int device);
 MSX_API int msx_tp_unique_id(uint8_t *out128);
 MSX_API int msx_stream_create_tp(msx_model *model, int context_override, const uint8_t *nccl_id128, msx_stream **out);
 /* Fused GEMV -> all-reduce over peer memory (replaces the NCCL launches of a tensor-parallel stream): every rank exports

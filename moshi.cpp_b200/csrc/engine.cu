@@ -2073,6 +2073,87 @@ extern "C" int msx_test_quantize_rows(int device, int src_type, int dst_type, co
     return 0;
 }
 
+// ---- GGUF -> GGUF quantiser (reference: `moshi-sts -q q4_k -g out.gguf`: moshi_lm_quantize + moshi_lm_save_gguf,
+// src/moshi.cpp:654-695, WeightLoader::save_gguf src/loader.h:227-233) --------------------------------------------------
+namespace {
+// the tensors moshi_scaled_embedding_t fetches (lm_utils.h:131-147): lm.text_emb, lm.emb.{c}, lm.depformer_emb.{k},
+// lm.depformer_text_emb — a q4_k model stores them as Q4_0
+bool is_embedding_table_name(const std::string &name) {
+    const std::string tail = ".weight";
+    if (name.size() <= tail.size() || name.compare(name.size() - tail.size(), tail.size(), tail)) return false;
+    std::string stem = name.substr(0, name.size() - tail.size());
+    size_t e = stem.size();
+    while (e > 0 && stem[e - 1] >= '0' && stem[e - 1] <= '9') e--;
+    if (e < stem.size() && e > 0 && stem[e - 1] == '.') stem.resize(e - 1);
+    return stem.size() >= 3 && stem.compare(stem.size() - 3, 3, "emb") == 0;
+}
+// loader.h:161-172: Q4_K needs K % 256 == 0 else Q4_0, Q4_0 / Q8_0 need K % 32 == 0 else the tensor stays as it is
+int on_load_type(int quantize, const GgufTensor &t) {
+    if (!quantize || !is_float_type(t.type) || t.n_dims != 2 || t.name.rfind("lm.", 0) != 0) return t.type;
+    int dst = quantize;
+    if (dst == T_Q4_K && is_embedding_table_name(t.name)) dst = T_Q4_0;
+    if (dst == T_Q4_K && t.ne[0] % 256) dst = T_Q4_0;
+    if ((dst == T_Q4_0 || dst == T_Q8_0) && t.ne[0] % 32) dst = t.type;
+    return dst;
+}
+struct FileCloser { void operator()(FILE *f) const { if (f) fclose(f); } };
+template <typename T> bool put(FILE *f, T v) { return fwrite(&v, sizeof(T), 1, f) == 1; }
+}  // namespace
+
+extern "C" int msx_gguf_quantize(const char *in_path, const char *out_path, int quantize, int device) {
+    if (!in_path || !out_path) return fail(MSX_ERR_ARG, "null argument");
+    if (quantize != 0 && quantize != T_Q8_0 && quantize != T_Q4_K) return fail(MSX_ERR_ARG, "quantize takes 0 (copy), 8 (q8_0) or 12 (q4_k)");
+    GgufFile f;
+    std::string err;
+    if (!f.open(in_path, err)) {
+        const bool io = err.rfind("cannot open", 0) == 0 || err.rfind("cannot stat", 0) == 0;
+        return fail(io ? MSX_ERR_IO : MSX_ERR_FORMAT, err);
+    }
+    std::unique_ptr<msx_model> m;
+    if (int e = test_setup(device, m)) return e;
+    // GGUF v3, no key/value pairs (the reference writes none), 32-byte alignment
+    const auto &ts = f.tensors();
+    std::vector<int> dst_type(ts.size());
+    std::vector<uint64_t> offset(ts.size()), nbytes(ts.size());
+    uint64_t data_bytes = 0;
+    for (size_t i = 0; i < ts.size(); i++) {
+        if (!ts[i].data) return fail(MSX_ERR_FORMAT, "tensor " + ts[i].name + " has unsupported type " + std::to_string(ts[i].type));
+        dst_type[i] = on_load_type(quantize, ts[i]);
+        nbytes[i] = dst_type[i] == ts[i].type ? (uint64_t)ts[i].nbytes : (uint64_t)ggml_row_size(dst_type[i], ts[i].ne[0]) * (uint64_t)ts[i].ne[1];
+        offset[i] = data_bytes;
+        data_bytes = (data_bytes + nbytes[i] + 31) / 32 * 32;
+    }
+    std::unique_ptr<FILE, FileCloser> out(fopen(out_path, "wb"));
+    if (!out) return fail(MSX_ERR_IO, std::string("cannot open ") + out_path + " for writing");
+    FILE *o = out.get();
+    bool ok = fwrite("GGUF", 1, 4, o) == 4 && put<uint32_t>(o, 3) && put<uint64_t>(o, ts.size()) && put<uint64_t>(o, 0);
+    for (size_t i = 0; ok && i < ts.size(); i++) {
+        ok = put<uint64_t>(o, ts[i].name.size()) && fwrite(ts[i].name.data(), 1, ts[i].name.size(), o) == ts[i].name.size() &&
+             put<uint32_t>(o, (uint32_t)ts[i].n_dims);
+        for (int d = 0; ok && d < ts[i].n_dims; d++) ok = put<uint64_t>(o, (uint64_t)ts[i].ne[d]);
+        ok = ok && put<uint32_t>(o, (uint32_t)dst_type[i]) && put<uint64_t>(o, offset[i]);
+    }
+    static const uint8_t zeros[32] = {0};
+    auto pad32 = [&](uint64_t pos) { const size_t n = (size_t)((32 - pos % 32) % 32); return n == 0 || fwrite(zeros, 1, n, o) == n; };
+    ok = ok && pad32((uint64_t)ftell(o));
+    std::vector<uint8_t> host;
+    for (size_t i = 0; ok && i < ts.size(); i++) {
+        const uint8_t *src = ts[i].data;
+        if (dst_type[i] != ts[i].type) {
+            if (int e = ensure_staging(m.get(), (size_t)ts[i].nbytes)) return e;
+            CU(cudaMemcpy(m->staging, ts[i].data, (size_t)ts[i].nbytes, cudaMemcpyHostToDevice));
+            const uint8_t *blocks = nullptr;
+            if (int e = quantize_staging(m.get(), ts[i].type, dst_type[i], ts[i].ne[0], ts[i].ne[1], &blocks)) return e;
+            host.resize((size_t)nbytes[i]);
+            CU(cudaMemcpy(host.data(), blocks, (size_t)nbytes[i], cudaMemcpyDeviceToHost));
+            src = host.data();
+        }
+        ok = fwrite(src, 1, (size_t)nbytes[i], o) == (size_t)nbytes[i] && pad32(nbytes[i]);
+    }
+    if (!ok || fflush(o) != 0) return fail(MSX_ERR_IO, std::string("write failed: ") + out_path);
+    return 0;
+}
+
 #include "batch.inl"
 
 static void free_prefill(struct msx_batch *b) { delete b; }

@@ -189,6 +189,14 @@ int moshi_lm_load(moshi_lm_t *lm) {
     return msx_model_load_gguf_ex(lm->filepath.c_str(), &lm->cfg, lm->device, 0, 1, q, &lm->model);
 }
 
+// moshi.cpp:693-695: the weights as loaded (i.e. after moshi_lm_quantize) written as a GGUF; here a file-to-file pass on
+// the GPU with the same quantisers and type rules as the loader.  The reference returns void; failures go to stderr.
+void moshi_lm_save_gguf(moshi_lm_t *lm, const char *filepath) {
+    const int q = lm->want_quant == "q8_0" ? 8 : lm->want_quant == "q4_k" ? 12 : 0;
+    if (msx_gguf_quantize(lm->filepath.c_str(), filepath, q, lm->device) != 0)
+        fprintf(stderr, "moshi_lm_save_gguf: %s\n", msx_last_error());
+}
+
 // ---- TTS text scheduling: TokenIds / State / StateMachine (src/moshi/models/lm.h:5-194) -------------------------
 // The model proposes PAD or NEW_WORD; the machine decides what is actually fed: queued word tokens, forced
 // padding after a word, at most max_padding pads in a row, the look-ahead word on the second text stream.

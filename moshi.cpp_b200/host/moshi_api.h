@@ -1,7 +1,7 @@
 // moshi_api.h — C++ mirror of the LM part of the reference's public API (include/moshi/moshi.h:111-203),
 // implemented on top of the C ABI in include/moshi_b200.h.  Same function names, argument meaning and
 // error behaviour as the reference, so a tool written against moshi.h keeps compiling for the LM path:
-//   moshi_get_config, moshi_lm_from_files, moshi_lm_quantize, moshi_lm_load, moshi_lm_set_delay_steps,
+//   moshi_get_config, moshi_lm_from_files, moshi_lm_quantize, moshi_lm_load, moshi_lm_save_gguf, moshi_lm_set_delay_steps,
 //   moshi_lm_get_max_delay, moshi_lm_get_delay_steps, moshi_lm_generator, moshi_lm_start, moshi_lm_send2,
 //   moshi_lm_receive, moshi_lm_receive2, moshi_lm_personaplex_audio_prompt, moshi_lm_personaplex_system_prompt,
 //   unref(...).
@@ -60,8 +60,9 @@ MOSHI_API void unref(moshi_lm_t *lm);
 MOSHI_API void moshi_lm_set_delay_steps(moshi_lm_t *lm, int delay_steps);
 MOSHI_API int moshi_lm_get_max_delay(moshi_lm_t *lm);
 MOSHI_API int moshi_lm_get_delay_steps(moshi_lm_t *lm);
-MOSHI_API bool moshi_lm_quantize(moshi_lm_t *lm, const char *quant);   // true only if the GGUF already holds that type (no quantise-on-load yet)
+MOSHI_API bool moshi_lm_quantize(moshi_lm_t *lm, const char *quant);   // "q8_0" / "q4_k": float tensors are quantised on the GPU while loading
 MOSHI_API int moshi_lm_load(moshi_lm_t *lm);                           // 0 ok
+MOSHI_API void moshi_lm_save_gguf(moshi_lm_t *lm, const char *filepath);  // the (quantised) weights as a GGUF (moshi.h:175)
 
 struct moshi_lm_gen_t;
 MOSHI_API moshi_lm_gen_t *moshi_lm_generator(moshi_lm_t *lm);

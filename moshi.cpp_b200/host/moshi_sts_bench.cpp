@@ -1,7 +1,9 @@
 // moshi_sts_bench.cpp — the `--bench` entry point of the reference's speech-to-speech tools
 // (tools/moshi-sts.cpp:731-808, tools/personaplex.cpp) reduced to the LM path: the Mimi encoder/decoder and
 // SDL/FFmpeg I/O are out of scope, so user audio codes are synthetic (seeded LCG) instead of encoded silence.
-//   moshi-sts-bench <model.gguf> <config.json> [frames=125] [device=0] [--print-tokens]
+//   moshi-sts-bench <model.gguf> <config.json> [frames=125] [device=0] [--print-tokens] [-q q8_0|q4_k] [-g out.gguf]
+// -q quantises an unquantised (f32 / f16 / bf16) GGUF while loading, -g writes the quantised weights as a GGUF and exits
+// (tools/moshi-sts.cpp `-q`, `-g`: moshi_lm_quantize, moshi_lm_save_gguf).
 // For a TTS model (model_type "tts": no user stream, cross-attention conditioning) it runs the moshi-tts --bench loop
 // instead (tools/moshi-tts.cpp:770-781): a synthetic conditioning memory, a script of LCG "words" sent as Entry
 // objects, receive() while moshi_lm_is_active().
@@ -17,16 +19,23 @@
 
 int main(int argc, char **argv) {
     if (argc < 3) { fprintf(stderr, "usage: %s model.gguf config.json [frames] [device] [--print-tokens]\n", argv[0]); return 2; }
-    const int frames = argc > 3 ? atoi(argv[3]) : 125;
-    const int device = argc > 4 ? atoi(argv[4]) : 0;
+    int frames = 125, device = 0, positional = 0;
     bool print_tokens = false;
-    for (int i = 3; i < argc; i++) if (!strcmp(argv[i], "--print-tokens")) print_tokens = true;
+    const char *quant = nullptr, *save_path = nullptr;
+    for (int i = 3; i < argc; i++) {
+        if (!strcmp(argv[i], "--print-tokens")) print_tokens = true;
+        else if (!strcmp(argv[i], "-q") && i + 1 < argc) quant = argv[++i];
+        else if (!strcmp(argv[i], "-g") && i + 1 < argc) save_path = argv[++i];
+        else if (argv[i][0] != '-') { (positional == 0 ? frames : device) = atoi(argv[i]); positional++; }
+    }
 
     moshi_config_t config;
     if (moshi_get_config(&config, argv[2]) != 0) return 1;
     moshi_context_t *moshi = moshi_alloc_b200(device);
     moshi_lm_t *lm = moshi_lm_from_files(moshi, &config, argv[1]);
     if (!lm) { fprintf(stderr, "error: could not open %s\n", argv[1]); return 1; }
+    if (quant && !moshi_lm_quantize(lm, quant)) { fprintf(stderr, "error: unknown quantisation %s\n", quant); return 1; }
+    if (save_path) { moshi_lm_save_gguf(lm, save_path); unref(lm); return 0; }
     if (moshi_lm_load(lm) != 0) { fprintf(stderr, "error: %s\n", moshi_b200_last_error()); return 1; }
     moshi_lm_gen_t *gen = moshi_lm_generator(lm);
     if (config.model_type == "tts") {

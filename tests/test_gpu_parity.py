@@ -612,6 +612,56 @@ def test_quantize_rows_bit_exact(msx, orc, dst, k, src):
     assert bad.size == 0, f"{len(bad)} bytes differ, first at row {bad[0][0]} byte {bad[0][1]}"
 
 
+@pytest.mark.parametrize("preset,src,quant", [("tiny_lowrank", "bf16", "q4_k"), ("tiny", "f16", "q8_0"), ("tiny_stt", "bf16", None)])
+def test_gguf_quantize_file(msx, orc, preset, src, quant, tmp_path):
+    """`-q <quant> -g out.gguf` (moshi_lm_quantize + moshi_lm_save_gguf, moshi.cpp:654-695): the GPU file-to-file quantiser
+    writes a GGUF that gguf-py parses, whose blocks equal the CPU quantisers' and whose types follow loader.h:161-172 /
+    lm_utils.h:131-147; the written file then loads and steps like the on-load path."""
+    import gguf
+    from moshi_cpp_b200 import configs, synth
+    cfg = configs.get(preset)
+    fp = str(tmp_path / "src.gguf"); qp = str(tmp_path / "out.gguf")
+    synth.write_gguf(fp, cfg, src, seed=91)
+    msx.gguf_quantize(fp, qp, quant)
+    a, b = gguf.GGUFReader(fp), gguf.GGUFReader(qp)
+    assert [t.name for t in a.tensors] == [t.name for t in b.tensors]
+    assert len(b.fields) <= 3                                # GGUF.version / tensor_count / kv_count only: no key/value pairs
+    seen = set()
+    for ta, tb in zip(a.tensors, b.tensors):
+        k = int(ta.shape[0]); rows = int(ta.shape[1]) if len(ta.shape) > 1 else 1
+        assert [int(v) for v in ta.shape] == [int(v) for v in tb.shape], ta.name
+        raw = np.ascontiguousarray(ta.data).view(np.uint8).reshape(-1)
+        gt = int(ta.tensor_type)
+        is_float2d = len(ta.shape) == 2 and gt in (synth.GGML_F32, synth.GGML_F16, synth.GGML_BF16)
+        if quant is None or not is_float2d:
+            want_t, want = gt, raw
+        else:
+            f32 = ((raw.view(np.uint16).astype(np.uint32) << 16).view(np.float32) if gt == synth.GGML_BF16
+                   else raw.view(np.float16).astype(np.float32) if gt == synth.GGML_F16 else raw.view(np.float32))
+            if quant == "q8_0":
+                want_t, want = synth.GGML_Q8_0, orc.quantize_q8_0(f32)
+            elif _TABLE_RE.search(ta.name) or k % 256:
+                want_t, want = synth.GGML_Q4_0, orc.quantize_q4_0(f32)
+            else:
+                want_t, want = synth.GGML_Q4_K, orc.quantize_q4_K(f32)
+        assert int(tb.tensor_type) == want_t, ta.name
+        assert np.array_equal(np.ascontiguousarray(tb.data).view(np.uint8).reshape(-1), want), ta.name
+        seen.add(want_t)
+    if quant == "q4_k":
+        assert {synth.GGML_Q4_K, synth.GGML_Q4_0, synth.GGML_F32} <= seen
+    if quant is None:
+        return
+    ga = msx.Stream(msx.Model(fp, cfg, quantize=quant)); gb = msx.Stream(msx.Model(qp, cfg))
+    toks = np.array([cfg["text_card"]] + [cfg["card"]] * cfg["n_q"], dtype=np.int32)
+    for f in range(3):
+        ta_, la, _ = ga.step_temporal(toks); tb_, lb, _ = gb.step_temporal(toks)
+        assert ta_ == tb_ and np.array_equal(la.view(np.uint32), lb.view(np.uint32))
+        if cfg["dep_q"] > 0:
+            aa, _ = ga.step_depformer(ta_); ab, _ = gb.step_depformer(tb_)
+            assert np.array_equal(aa, ab)
+            toks = np.array([ta_] + list(aa) + [0] * (cfg["n_q"] - len(aa)), dtype=np.int32)
+
+
 _TABLE_RE = __import__("re").compile(r"(^|\.)(text_emb|emb\.\d+|depformer_emb\.\d+|depformer_text_emb)\.weight$")
 
 

@@ -48,6 +48,28 @@ def test_tool_error_paths(tool, gguf_for, tmp_path):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("quant", ["q4_k", "q8_0"])
+def test_tool_quantize_and_save_gguf(tool, tmp_path, quant):
+    """`moshi-sts -q <quant> -g out.gguf` then running the saved file == `-q <quant>` on the unquantised file
+    (moshi_lm_quantize / moshi_lm_save_gguf / moshi_lm_load, moshi.cpp:654-695)."""
+    from moshi_cpp_b200 import synth
+    cfg = configs.get("tiny")
+    src = str(tmp_path / "tiny-bf16.gguf"); out = str(tmp_path / f"tiny-{quant}.gguf")
+    synth.write_gguf(src, cfg, "bf16", seed=5)
+    cj = tmp_path / "config.json"; write_config(cj, cfg)
+    r = subprocess.run([tool, src, str(cj), "-q", quant, "-g", out], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and os.path.getsize(out) < os.path.getsize(src) * 0.6, r.stderr
+    a = subprocess.run([tool, src, str(cj), "30", "0", "--print-tokens", "-q", quant], capture_output=True, text=True, timeout=300)
+    b = subprocess.run([tool, out, str(cj), "30", "0", "--print-tokens"], capture_output=True, text=True, timeout=300)
+    assert a.returncode == 0 and b.returncode == 0, a.stderr + b.stderr
+    ta = [l for l in a.stdout.splitlines() if l[:1].isdigit()]
+    tb = [l for l in b.stdout.splitlines() if l[:1].isdigit()]
+    assert len(ta) == 30 and ta == tb
+    r = subprocess.run([tool, src, str(cj), "-q", "q3_x"], capture_output=True, text=True)
+    assert r.returncode == 1 and "unknown quantisation" in r.stderr     # moshi_lm_quantize -> false (moshi.cpp:667-668)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("preset", ["tiny", "tiny_pplex", "tiny_stt"])
 def test_cpp_api_matches_c_abi(tool, gguf_for, tmp_path, preset):
     quant = "q8_0" if preset == "tiny_stt" else "q4_k"

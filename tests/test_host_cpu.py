@@ -41,6 +41,9 @@ def test_no_cpu_fallback(gguf_for):
     with pytest.raises(msx.MsxError) as e:
         msx.test_gemv(synth.GGML_Q4_K, raw, 256, np.zeros(256, np.float32))
     assert e.value.code == -4
+    with pytest.raises(msx.MsxError) as e:                      # the quantisers too: no host implementation behind them
+        msx.test_quantize_rows(synth.GGML_Q4_K, np.zeros((1, 256), np.float32))
+    assert e.value.code == -4
 
 
 def test_loader_errors_before_device(gguf_for, tmp_path):
@@ -60,6 +63,12 @@ def test_loader_errors_before_device(gguf_for, tmp_path):
     with pytest.raises(msx.MsxError) as e:
         msx.Model(path, wrong)
     assert e.value.code == -1
+    with pytest.raises(msx.MsxError) as e:                      # file-to-file quantiser: same error codes
+        msx.gguf_quantize(str(tmp_path / "nope.gguf"), str(tmp_path / "out.gguf"), "q4_k")
+    assert e.value.code == -2
+    with pytest.raises(msx.MsxError) as e:
+        msx.gguf_quantize(str(bad), str(tmp_path / "out.gguf"), "q8_0")
+    assert e.value.code == -3
 
 
 def test_gguf_roundtrip_with_gguf_py(gguf_for):
