@@ -137,6 +137,12 @@ MSX_API int msx_model_load_gguf_ex(const char *path, const msx_config *cfg, int 
  * reference's own files.  Replaces `-q <quant> -g out.gguf` (moshi_lm_quantize + moshi_lm_save_gguf, src/moshi.cpp:654-695,
  * WeightLoader::save_gguf src/loader.h:227-233). */
 MSX_API int msx_gguf_quantize(const char *in_path, const char *out_path, int quantize, int device);
+/* the same from the reference's own starting point, a model.safetensors with torch names (bf16 / f16 / f32): tensors are
+ * renamed "lm." + name, *.in_proj_weight / *.out_proj.weight are split into the per-step *.in_projs.{i}.weight /
+ * *.out_projs.{i}.weight the loader expects, vectors (norm alpha, biases) become F32, 2-D tensors follow the quantisation
+ * rules above (WeightLoader::from_safetensor + fetch + save_gguf, src/loader.h:77-83, 149-233;
+ * src/moshi/modules/transformer.h:764-849). */
+MSX_API int msx_safetensors_to_gguf(const char *in_path, const char *out_path, int quantize, int device);
 MSX_API int msx_tp_unique_id(uint8_t *out128);
 MSX_API int msx_stream_create_tp(msx_model *model, int context_override, const uint8_t *nccl_id128, msx_stream **out);
 /* Fused GEMV -> all-reduce over peer memory (replaces the NCCL launches of a tensor-parallel stream): every rank exports

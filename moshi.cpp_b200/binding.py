@@ -162,6 +162,7 @@ def lib():
     L.msx_test_dequant_rows.argtypes = [C.c_int, C.c_int, vp, C.c_int64, C.c_int64, vp, C.c_int, vp]
     L.msx_test_dequant_repacked.argtypes = [C.c_int, C.c_int, vp, C.c_int64, C.c_int64, vp]
     L.msx_gguf_quantize.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int]
+    L.msx_safetensors_to_gguf.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int]
     L.msx_test_quantize_rows.argtypes = [C.c_int, C.c_int, C.c_int, vp, C.c_int64, C.c_int64, vp]
     _lib = L
     return L
@@ -569,6 +570,11 @@ def test_dequant_repacked(gtype: int, w_raw: np.ndarray, k: int, device: int = 0
 def gguf_quantize(in_path: str, out_path: str, quantize: str | None, device: int = 0) -> None:
     """unquantised GGUF -> q8_0 / q4_k GGUF on the GPU (the reference's `-q <quant> -g out.gguf`)"""
     _check(lib().msx_gguf_quantize(in_path.encode(), out_path.encode(), {None: 0, "q8_0": 8, "q4_k": 12}[quantize], device))
+
+
+def safetensors_to_gguf(in_path: str, out_path: str, quantize: str | None, device: int = 0) -> None:
+    """model.safetensors (torch names) -> GGUF with the reference loader's names, splits and quantisation rules"""
+    _check(lib().msx_safetensors_to_gguf(in_path.encode(), out_path.encode(), {None: 0, "q8_0": 8, "q4_k": 12}[quantize], device))
 
 
 def test_quantize_rows(dst_type: int, x: np.ndarray, src_type: int = 0, device: int = 0) -> np.ndarray:

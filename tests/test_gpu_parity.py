@@ -612,6 +612,87 @@ def test_quantize_rows_bit_exact(msx, orc, dst, k, src):
     assert bad.size == 0, f"{len(bad)} bytes differ, first at row {bad[0][0]} byte {bad[0][1]}"
 
 
+def _expected_quantised(orc, name, gt, k, n_dims, raw, quant):
+    """(type, bytes) the reference's type rules (loader.h:161-172, lm_utils.h:131-147) + the CPU quantisers give for one tensor"""
+    from moshi_cpp_b200 import synth
+    if quant is None or n_dims != 2 or gt not in (synth.GGML_F32, synth.GGML_F16, synth.GGML_BF16):
+        return gt, raw
+    f32 = ((raw.view(np.uint16).astype(np.uint32) << 16).view(np.float32) if gt == synth.GGML_BF16
+           else raw.view(np.float16).astype(np.float32) if gt == synth.GGML_F16 else raw.view(np.float32))
+    if quant == "q8_0":
+        return synth.GGML_Q8_0, orc.quantize_q8_0(f32)
+    if _TABLE_RE.search(name) or k % 256:
+        return synth.GGML_Q4_0, orc.quantize_q4_0(f32)
+    return synth.GGML_Q4_K, orc.quantize_q4_K(f32)
+
+
+def _write_safetensors(path, tensors):
+    """tensors: [(name, dtype string, shape, bytes)] -> the safetensors container (8-byte header length, JSON, data)"""
+    import json
+    hdr, off = {"__metadata__": {"format": "pt", "note": "written by tests, {nested: [1, 2]}"}}, 0
+    for name, dtype, shape, raw in tensors:
+        hdr[name] = {"dtype": dtype, "shape": [int(v) for v in shape], "data_offsets": [off, off + len(raw)]}
+        off += len(raw)
+    js = json.dumps(hdr).encode()
+    js += b" " * (-len(js) % 8)
+    with open(path, "wb") as f:
+        f.write(len(js).to_bytes(8, "little")); f.write(js)
+        for _, _, _, raw in tensors:
+            f.write(raw)
+
+
+@pytest.mark.parametrize("preset,quant", [("tiny", "q4_k"), ("tiny_pplex", "q8_0"), ("tiny_tts", "q4_k"), ("tiny_stt", None)])
+def test_safetensors_to_gguf(msx, orc, preset, quant, tmp_path):
+    """The reference's starting point is model.safetensors with torch names (WeightLoader::from_safetensor, loader.h:77-83):
+    fused in_proj_weight / out_proj.weight of all depformer steps, bf16 norm vectors of shape [1,1,d].  The converter
+    must give the GGUF the reference would save (`-q <quant> -g`): "lm." names, per-step splits
+    (transformer.h:764-849), F32 vectors, quantised 2-D tensors — and that file must load and step."""
+    import gguf, re
+    from moshi_cpp_b200 import configs, synth
+    cfg = configs.get(preset)
+    fp = str(tmp_path / "src.gguf"); sp = str(tmp_path / "model.safetensors"); qp = str(tmp_path / "out.gguf")
+    synth.write_gguf(fp, cfg, "bf16", seed=92)
+    src = {t.name: t for t in gguf.GGUFReader(fp).tensors}
+    dt = {synth.GGML_F32: "F32", synth.GGML_F16: "F16", synth.GGML_BF16: "BF16"}
+    fused, st, expect = {}, [], {}
+    for name, t in src.items():
+        raw = np.ascontiguousarray(t.data).view(np.uint8).reshape(-1)
+        gt = int(t.tensor_type)
+        shape = [int(v) for v in t.shape][::-1]                   # torch order
+        m = re.match(r"lm\.(.*)\.(in|out)_projs\.(\d+)\.weight$", name)
+        if m:
+            fused.setdefault((m.group(1), m.group(2)), {})[int(m.group(3))] = (gt, shape, raw)
+            expect[name] = _expected_quantised(orc, name, gt, shape[-1], 2, raw, quant) + (shape,)
+        elif len(shape) == 1 and gt == synth.GGML_F32:             # norm vectors: bf16 [1,1,d] in the checkpoint
+            f = raw.view(np.float32)
+            bits = ((f.view(np.uint32) + 0x7FFF + ((f.view(np.uint32) >> 16) & 1)) >> 16).astype(np.uint16)
+            st.append((name[3:], "BF16", [1, 1, shape[0]], bits.tobytes()))
+            expect[name] = (synth.GGML_F32, (bits.astype(np.uint32) << 16).view(np.uint8), [1, 1, shape[0]])
+        else:
+            st.append((name[3:], dt[gt], shape, raw.tobytes()))
+            expect[name] = _expected_quantised(orc, name, gt, shape[-1], len(shape), raw, quant) + (shape,)
+    for (stem, kind), parts in fused.items():
+        gt, shape, _ = parts[0]
+        blob = b"".join(parts[i][2].tobytes() for i in range(len(parts)))
+        st.append((f"{stem}.in_proj_weight" if kind == "in" else f"{stem}.out_proj.weight", dt[gt], [shape[0] * len(parts), shape[1]], blob))
+    assert any(len(p) > 1 for p in fused.values()) or cfg["dep_q"] == 0      # per-step depformer weights really are fused
+    _write_safetensors(sp, st)
+    msx.safetensors_to_gguf(sp, qp, quant)
+    out = {t.name: t for t in gguf.GGUFReader(qp).tensors}
+    assert set(out) == set(expect)
+    for name, (want_t, want, shape) in expect.items():
+        t = out[name]
+        assert int(t.tensor_type) == want_t, name
+        assert [int(v) for v in t.shape][::-1] == shape, name
+        assert np.array_equal(np.ascontiguousarray(t.data).view(np.uint8).reshape(-1), np.frombuffer(bytes(want), np.uint8)), name
+    if quant is None:
+        return
+    gm = msx.Model(qp, cfg); gs = msx.Stream(gm)
+    toks = np.array([cfg["text_card"]] + [cfg["card"]] * cfg["n_q"], dtype=np.int32)
+    t0, lg, _ = gs.step_temporal(toks)
+    assert np.isfinite(lg).all()
+
+
 @pytest.mark.parametrize("preset,src,quant", [("tiny_lowrank", "bf16", "q4_k"), ("tiny", "f16", "q8_0"), ("tiny_stt", "bf16", None)])
 def test_gguf_quantize_file(msx, orc, preset, src, quant, tmp_path):
     """`-q <quant> -g out.gguf` (moshi_lm_quantize + moshi_lm_save_gguf, moshi.cpp:654-695): the GPU file-to-file quantiser
@@ -631,19 +712,7 @@ def test_gguf_quantize_file(msx, orc, preset, src, quant, tmp_path):
         k = int(ta.shape[0]); rows = int(ta.shape[1]) if len(ta.shape) > 1 else 1
         assert [int(v) for v in ta.shape] == [int(v) for v in tb.shape], ta.name
         raw = np.ascontiguousarray(ta.data).view(np.uint8).reshape(-1)
-        gt = int(ta.tensor_type)
-        is_float2d = len(ta.shape) == 2 and gt in (synth.GGML_F32, synth.GGML_F16, synth.GGML_BF16)
-        if quant is None or not is_float2d:
-            want_t, want = gt, raw
-        else:
-            f32 = ((raw.view(np.uint16).astype(np.uint32) << 16).view(np.float32) if gt == synth.GGML_BF16
-                   else raw.view(np.float16).astype(np.float32) if gt == synth.GGML_F16 else raw.view(np.float32))
-            if quant == "q8_0":
-                want_t, want = synth.GGML_Q8_0, orc.quantize_q8_0(f32)
-            elif _TABLE_RE.search(ta.name) or k % 256:
-                want_t, want = synth.GGML_Q4_0, orc.quantize_q4_0(f32)
-            else:
-                want_t, want = synth.GGML_Q4_K, orc.quantize_q4_K(f32)
+        want_t, want = _expected_quantised(orc, ta.name, int(ta.tensor_type), k, len(ta.shape), raw, quant)
         assert int(tb.tensor_type) == want_t, ta.name
         assert np.array_equal(np.ascontiguousarray(tb.data).view(np.uint8).reshape(-1), want), ta.name
         seen.add(want_t)

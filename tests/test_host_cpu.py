@@ -69,6 +69,15 @@ def test_loader_errors_before_device(gguf_for, tmp_path):
     with pytest.raises(msx.MsxError) as e:
         msx.gguf_quantize(str(bad), str(tmp_path / "out.gguf"), "q8_0")
     assert e.value.code == -3
+    with pytest.raises(msx.MsxError) as e:                      # safetensors front end
+        msx.safetensors_to_gguf(str(tmp_path / "nope.safetensors"), str(tmp_path / "out.gguf"), "q4_k")
+    assert e.value.code == -2
+    for blob in (b"\x10\0\0\0\0\0\0\0" + b'{"a": {"dtype"', (1 << 40).to_bytes(8, "little") + b"{}" * 8,
+                 b"\x30\0\0\0\0\0\0\0" + b'{"a":{"dtype":"F32","shape":[4],"data_offsets":[0,64]}}'.ljust(48)):
+        st = tmp_path / "bad.safetensors"; st.write_bytes(blob)
+        with pytest.raises(msx.MsxError) as e:
+            msx.safetensors_to_gguf(str(st), str(tmp_path / "out.gguf"), None)
+        assert e.value.code == -3
 
 
 def test_gguf_roundtrip_with_gguf_py(gguf_for):
