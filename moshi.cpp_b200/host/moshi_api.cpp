@@ -5,6 +5,8 @@
 #include <cctype>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
+#include <unistd.h>
 
 #include "../../include/moshi_b200.h"
 
@@ -172,6 +174,10 @@ void unref(moshi_lm_t *lm) { if (lm) { msx_model_free(lm->model); delete lm; } }
 void moshi_lm_set_delay_steps(moshi_lm_t *lm, int d) { lm->delay_steps = d; }
 int moshi_lm_get_max_delay(moshi_lm_t *lm) { int m = lm->cfg.delays[0]; for (int i = 0; i < lm->cfg.n_delays; i++) m = std::max(m, lm->cfg.delays[i]); return m; }
 int moshi_lm_get_delay_steps(moshi_lm_t *lm) { return lm->delay_steps; }
+static bool is_safetensors(const std::string &path) {
+    const std::string ext = ".safetensors";
+    return path.size() > ext.size() && path.compare(path.size() - ext.size(), ext.size(), ext) == 0;
+}
 bool moshi_lm_quantize(moshi_lm_t *lm, const char *quant) {
     // reference: q4_0 / q4_k / q8_0 accepted, anything else false (moshi.cpp:654-673).  q8_0 and q4_k are applied while
     // loading when the GGUF holds f32 / f16 / bf16 tensors; a q4_0 model must already be a q4_0 file (and its linears are
@@ -186,6 +192,18 @@ int moshi_lm_load(moshi_lm_t *lm) {
     // moshi_lm_quantize("q8_0" / "q4_k") on an unquantised (f32 / f16 / bf16) GGUF: quantise while loading like the
     // reference (loader.h:149-233); already-quantised tensors are taken as they are
     const int q = lm->want_quant == "q8_0" ? 8 : lm->want_quant == "q4_k" ? 12 : 0;
+    if (is_safetensors(lm->filepath)) {
+        // the reference's WeightLoader::from_safetensor path (moshi.cpp:611-636): quantise into a scratch GGUF on the GPU,
+        // load that, drop it.  The linears need q4_k / q8_0, so -q is mandatory for a safetensors checkpoint.
+        std::string tmp = "/tmp/moshi_b200_XXXXXX";
+        const int fd = mkstemp(&tmp[0]);
+        if (fd < 0) return -2;
+        close(fd);
+        int e = msx_safetensors_to_gguf(lm->filepath.c_str(), tmp.c_str(), q, lm->device);
+        if (!e) e = msx_model_load_gguf_ex(tmp.c_str(), &lm->cfg, lm->device, 0, 1, 0, &lm->model);
+        unlink(tmp.c_str());
+        return e;
+    }
     return msx_model_load_gguf_ex(lm->filepath.c_str(), &lm->cfg, lm->device, 0, 1, q, &lm->model);
 }
 
@@ -193,7 +211,7 @@ int moshi_lm_load(moshi_lm_t *lm) {
 // the GPU with the same quantisers and type rules as the loader.  The reference returns void; failures go to stderr.
 void moshi_lm_save_gguf(moshi_lm_t *lm, const char *filepath) {
     const int q = lm->want_quant == "q8_0" ? 8 : lm->want_quant == "q4_k" ? 12 : 0;
-    if (msx_gguf_quantize(lm->filepath.c_str(), filepath, q, lm->device) != 0)
+    if ((is_safetensors(lm->filepath) ? msx_safetensors_to_gguf : msx_gguf_quantize)(lm->filepath.c_str(), filepath, q, lm->device) != 0)
         fprintf(stderr, "moshi_lm_save_gguf: %s\n", msx_last_error());
 }
 

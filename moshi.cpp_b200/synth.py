@@ -250,3 +250,18 @@ def cached_gguf(preset: str, quant: str = "q4_k", seed: int = 1234, root: str | 
     if not os.path.exists(path):
         write_gguf(path, configs.get(preset), quant, seed)
     return path
+
+
+def write_safetensors(path, tensors):
+    """tensors: [(name, dtype string, shape, bytes)] -> the safetensors container (8-byte header length, JSON, data)"""
+    import json
+    hdr, off = {"__metadata__": {"format": "pt", "note": "written by tests, {nested: [1, 2]}"}}, 0
+    for name, dtype, shape, raw in tensors:
+        hdr[name] = {"dtype": dtype, "shape": [int(v) for v in shape], "data_offsets": [off, off + len(raw)]}
+        off += len(raw)
+    js = json.dumps(hdr).encode()
+    js += b" " * (-len(js) % 8)
+    with open(path, "wb") as f:
+        f.write(len(js).to_bytes(8, "little")); f.write(js)
+        for _, _, _, raw in tensors:
+            f.write(raw)

@@ -626,21 +626,6 @@ def _expected_quantised(orc, name, gt, k, n_dims, raw, quant):
     return synth.GGML_Q4_K, orc.quantize_q4_K(f32)
 
 
-def _write_safetensors(path, tensors):
-    """tensors: [(name, dtype string, shape, bytes)] -> the safetensors container (8-byte header length, JSON, data)"""
-    import json
-    hdr, off = {"__metadata__": {"format": "pt", "note": "written by tests, {nested: [1, 2]}"}}, 0
-    for name, dtype, shape, raw in tensors:
-        hdr[name] = {"dtype": dtype, "shape": [int(v) for v in shape], "data_offsets": [off, off + len(raw)]}
-        off += len(raw)
-    js = json.dumps(hdr).encode()
-    js += b" " * (-len(js) % 8)
-    with open(path, "wb") as f:
-        f.write(len(js).to_bytes(8, "little")); f.write(js)
-        for _, _, _, raw in tensors:
-            f.write(raw)
-
-
 @pytest.mark.parametrize("preset,quant", [("tiny", "q4_k"), ("tiny_pplex", "q8_0"), ("tiny_tts", "q4_k"), ("tiny_stt", None)])
 def test_safetensors_to_gguf(msx, orc, preset, quant, tmp_path):
     """The reference's starting point is model.safetensors with torch names (WeightLoader::from_safetensor, loader.h:77-83):
@@ -676,7 +661,7 @@ def test_safetensors_to_gguf(msx, orc, preset, quant, tmp_path):
         blob = b"".join(parts[i][2].tobytes() for i in range(len(parts)))
         st.append((f"{stem}.in_proj_weight" if kind == "in" else f"{stem}.out_proj.weight", dt[gt], [shape[0] * len(parts), shape[1]], blob))
     assert any(len(p) > 1 for p in fused.values()) or cfg["dep_q"] == 0      # per-step depformer weights really are fused
-    _write_safetensors(sp, st)
+    synth.write_safetensors(sp, st)
     msx.safetensors_to_gguf(sp, qp, quant)
     out = {t.name: t for t in gguf.GGUFReader(qp).tensors}
     assert set(out) == set(expect)

@@ -65,6 +65,16 @@ def test_tool_quantize_and_save_gguf(tool, tmp_path, quant):
     ta = [l for l in a.stdout.splitlines() if l[:1].isdigit()]
     tb = [l for l in b.stdout.splitlines() if l[:1].isdigit()]
     assert len(ta) == 30 and ta == tb
+    if quant == "q4_k":      # the same checkpoint as model.safetensors (torch names; here no fused tensors): -q on the fly == the saved file
+        import gguf
+        dt = {0: "F32", 1: "F16", 30: "BF16"}
+        st = [(t.name[3:], dt[int(t.tensor_type)], [int(v) for v in t.shape][::-1], np.ascontiguousarray(t.data).tobytes())
+              for t in gguf.GGUFReader(src).tensors]
+        sp = str(tmp_path / "model.safetensors")
+        synth.write_safetensors(sp, st)
+        c = subprocess.run([tool, sp, str(cj), "30", "0", "--print-tokens", "-q", quant], capture_output=True, text=True, timeout=300)
+        assert c.returncode == 0, c.stderr
+        assert [l for l in c.stdout.splitlines() if l[:1].isdigit()] == ta
     r = subprocess.run([tool, src, str(cj), "-q", "q3_x"], capture_output=True, text=True)
     assert r.returncode == 1 and "unknown quantisation" in r.stderr     # moshi_lm_quantize -> false (moshi.cpp:667-668)
 
