@@ -158,6 +158,17 @@ MSX_API int msx_stream_tp_connect(msx_stream *s, const uint8_t *handles /* [worl
  * through every layer's cross_attention.in_proj rows [dim, 3*dim) into the f32 k_cross / v_cross memory.  The
  * conditioners that PRODUCE these tensors (src/moshi.cpp:296-366) are outside the per-frame path. */
 MSX_API int msx_stream_set_condition(msx_stream *s, const float *cond_sum, const float *cond_cross, int tc);
+/* the conditioners themselves (voice_condition, src/moshi.cpp:296-366; weights tts.h:16-35, optional in the GGUF):
+ * cond_sum = cfg.output_proj . cfg.embed[2] + control.output_proj . control.embed[0]; cond_cross [5 * frames][dim] = the
+ * speaker embedding projected by speaker_wavs.output_proj in rows [0, frames), speaker_wavs.learnt_padding in the rest,
+ * plus ggml_timestep_embedding(row, dim, 10000); then msx_stream_set_condition.  speaker_wavs: the voice file's tensor as
+ * stored, [channels][frames] f32.  sum_out [dim] / cross_out [5 * frames][dim] (host, nullable) receive the tensors.
+ * MSX_ERR_STATE without cross-attention (reference: -1) or without conditioner tensors (reference: -2). */
+MSX_API int msx_stream_set_voice(msx_stream *s, const float *speaker_wavs, int channels, int frames, float *sum_out, float *cross_out);
+/* moshi_lm_set_voice_condition + moshi_lm_load_voice_condition (src/moshi.cpp:729-760): reads "speaker_wavs" ([1,] channels,
+ * frames; f32 / f16 / bf16) from a voice .safetensors and calls msx_stream_set_voice */
+MSX_API int msx_stream_load_voice(msx_stream *s, const char *safetensors_path);
+MSX_API int msx_model_has_conditioners(const msx_model *model);   /* 1 when the GGUF carried the conditioner tensors */
 MSX_API int msx_vad(msx_stream *s, float *vad);
 
 /* Device-resident replay for throughput measurement: frames[n_frames][n_q+1] (host) are uploaded

@@ -117,6 +117,9 @@ def lib():
     L.msx_step.argtypes = [vp, vp, vp]
     L.msx_vad.argtypes = [vp, C.POINTER(C.c_float)]
     L.msx_stream_set_condition.argtypes = [vp, vp, vp, C.c_int]
+    L.msx_stream_set_voice.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp]
+    L.msx_stream_load_voice.argtypes = [vp, C.c_char_p]
+    L.msx_model_has_conditioners.argtypes = [vp]
     L.msx_stream_set_sampling.argtypes = [vp, C.c_float, C.c_float, C.c_int, C.c_int]
     L.msx_stream_set_noise.argtypes = [vp, vp, vp]
     L.msx_gen_seed.argtypes = [vp, C.c_uint]
@@ -324,6 +327,17 @@ class Stream:
         cs = np.ascontiguousarray(cond_sum, dtype=np.float32) if cond_sum is not None else None
         cc = np.ascontiguousarray(cond_cross, dtype=np.float32) if cond_cross is not None else None
         _check(lib().msx_stream_set_condition(self.h, _p(cs), _p(cc), 0 if cc is None else cc.shape[0]))
+
+    def set_voice(self, speaker_wavs):
+        """TTS voice conditioners on the GPU; speaker_wavs [channels][frames].  Returns (cond_sum [dim], cond_cross [5T][dim])"""
+        w = np.ascontiguousarray(speaker_wavs, dtype=np.float32)
+        dim = self.model.cfg["dim"]
+        cs = np.empty(dim, dtype=np.float32); cc = np.empty((5 * w.shape[1], dim), dtype=np.float32)
+        _check(lib().msx_stream_set_voice(self.h, _p(w), w.shape[0], w.shape[1], _p(cs), _p(cc)))
+        return cs, cc
+
+    def load_voice(self, path: str):
+        _check(lib().msx_stream_load_voice(self.h, path.encode()))
 
     def vad(self) -> float:
         v = C.c_float(0)

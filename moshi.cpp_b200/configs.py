@@ -101,6 +101,8 @@ PRESETS = {
         cross_attention=True, demux=True, dep_low_rank=128,
     ),
 }
+# tiny_tts whose GGUF also carries the voice conditioners (tts.h:16-35): voice files go through msx_stream_set_voice
+PRESETS["tiny_tts_voice"] = _derive(PRESETS["tiny_tts"], name="tiny_tts_voice", conditioners=True)
 for _c in PRESETS.values():
     _c.setdefault("cross_attention", False); _c.setdefault("demux", False); _c.setdefault("dep_low_rank", 0)
 

@@ -120,6 +120,10 @@ struct msx_model {
     EmbTable dep_text_out1, dep_text_out2, dep_text_lr;
     std::vector<EmbTable> dep_emb_lr;
     bool dep_small = false;           // depformer embeddings go through small_linear_kernel
+    // TTS voice conditioners (tts.h:5-35), present when the GGUF carries lm.condition_provider.conditioners.*
+    FloatTensor cfg_embed, cfg_proj, control_embed, control_proj, spk_pad, spk_proj;
+    const float *cond_freq = nullptr; // [dim/2] timestep-embedding frequencies
+    bool has_conditioners = false;
     std::vector<void *> allocs;
     std::unordered_map<const void *, QTiles> tiles;   // MMA unit layout of a linear, keyed by its qs plane (batch.inl)
     int64_t weight_bytes_per_frame = 0;
@@ -291,6 +295,19 @@ struct Loader {
         if (t->ne[0] != K || t->ne[1] != rows)
             return fail(MSX_ERR_FORMAT, "shape mismatch for " + name);
         return upload_table(m, t->data, t->type, K, rows, out);
+    }
+    // an unquantised tensor kept in its file type (the conditioners: loader.h fetch() without a destination type)
+    int float_tensor(const std::string &name, int64_t ne0, FloatTensor *out) {
+        const GgufTensor *t = need(name);
+        if (!t) return MSX_ERR_FORMAT;
+        if (!is_float_type(t->type)) return fail(MSX_ERR_FORMAT, name + " must be f32 / f16 / bf16");
+        if (ne0 > 0 && t->ne[0] != ne0) return fail(MSX_ERR_FORMAT, "shape mismatch for " + name);
+        void *d = nullptr;
+        if (int e = dev_alloc(m, &d, (size_t)t->nbytes)) return e;
+        CU(cudaMemcpy(d, t->data, (size_t)t->nbytes, cudaMemcpyHostToDevice));
+        out->data = (const uint8_t *)d; out->type = t->type; out->ne0 = (int32_t)t->ne[0];
+        out->ne1 = (int32_t)(t->ne[1] * t->ne[2] * t->ne[3]);
+        return 0;
     }
     int vec_f32(const std::string &name, int64_t n, const float **out) {
         const GgufTensor *t = need(name);
@@ -536,6 +553,20 @@ extern "C" int msx_model_load_gguf_ex(const char *path, const msx_config *cfg, i
     if (int e = make_freq(c.dim / c.num_heads, c.max_period, &m->rope_freq)) return e;
     if (c.dep_q > 0)
         if (int e = make_freq(c.dep_dim / c.dep_heads, c.dep_max_period, &m->dep_rope_freq)) return e;
+    // voice conditioners (tts.h:16-35): optional — files made for externally computed conditioning do not carry them
+    const std::string cp = "lm.condition_provider.conditioners.";
+    if (c.cross_attention && f.find(cp + "cfg.embed.weight")) {
+        if (int e = L.float_tensor(cp + "cfg.embed.weight", 0, &m->cfg_embed)) return e;
+        if (int e = L.float_tensor(cp + "cfg.output_proj.weight", m->cfg_embed.ne0, &m->cfg_proj)) return e;
+        if (int e = L.float_tensor(cp + "control.embed.weight", 0, &m->control_embed)) return e;
+        if (int e = L.float_tensor(cp + "control.output_proj.weight", m->control_embed.ne0, &m->control_proj)) return e;
+        if (int e = L.float_tensor(cp + "speaker_wavs.learnt_padding", d, &m->spk_pad)) return e;
+        if (int e = L.float_tensor(cp + "speaker_wavs.output_proj.weight", 0, &m->spk_proj)) return e;
+        if (m->cfg_proj.ne1 != d || m->control_proj.ne1 != d || m->spk_proj.ne1 != d || m->cfg_embed.ne1 < 3)
+            return fail(MSX_ERR_FORMAT, "conditioner projections must map to dim; cfg.embed needs >= 3 rows");
+        if (int e = make_freq(d, 10000, &m->cond_freq)) return e;          // ggml_timestep_embedding(positions, dim, 10000)
+        m->has_conditioners = true;
+    }
     if (m->staging) { cudaFree(m->staging); m->staging = nullptr; m->staging_bytes = 0; }
     if (m->qstaging) { cudaFree(m->qstaging); m->qstaging = nullptr; m->qstaging_bytes = 0; }
     *out = m.release();
@@ -1493,6 +1524,82 @@ extern "C" int msx_stream_set_condition(msx_stream *s, const float *cond_sum, co
     return 0;
 }
 
+// voice_condition() (src/moshi.cpp:296-366): condition_sum = cfg_proj . cfg_embed[2] + control_proj . control_embed[0]
+// ("cfg 2.0", "control ok"); condition_cross [5T][dim] = the projected speaker embedding in the first T rows, the learnt
+// padding in the other 4T, plus the sinusoidal position embedding; then the cross-attention K / V memory as in
+// msx_stream_set_condition.  speaker_wavs is the voice file's tensor as stored: [channels][frames], frames fastest.
+extern "C" int msx_stream_set_voice(msx_stream *s, const float *speaker_wavs, int channels, int frames, float *sum_out, float *cross_out) {
+    if (!s || !speaker_wavs) return fail(MSX_ERR_ARG, "null argument");
+    msx_model *m = s->m;
+    if (!m->cfg.cross_attention) return fail(MSX_ERR_STATE, "model has no cross-attention layers (moshi_lm_load_voice_condition returns -1, moshi.cpp:740-742)");
+    if (!m->has_conditioners) return fail(MSX_ERR_STATE, "the GGUF carries no lm.condition_provider.conditioners.* tensors (moshi_lm_load_voice_condition returns -2, moshi.cpp:744-745)");
+    if (frames <= 0 || channels != m->spk_proj.ne0) return fail(MSX_ERR_ARG, "speaker_wavs must be [" + std::to_string(m->spk_proj.ne0) + "][frames]");
+    CU(cudaSetDevice(m->device));
+    CU(cudaStreamSynchronize(s->st));
+    const int dim = m->cfg.dim, tc = 5 * frames;
+    float *buf = nullptr;      // wavs [C][T] | speaker [T][dim] | cfg [dim] | control [dim] | sum [dim] | cross [5T][dim]
+    const size_t n_w = (size_t)channels * frames, n_s = (size_t)frames * dim, n_c = (size_t)tc * dim;
+    CU(cudaMalloc((void **)&buf, (n_w + n_s + 3 * (size_t)dim + n_c) * 4));
+    float *d_w = buf, *d_s = d_w + n_w, *d_cfg = d_s + n_s, *d_ctl = d_cfg + dim, *d_sum = d_ctl + dim, *d_cross = d_sum + dim;
+    std::vector<float> sum(dim), cross(n_c);
+    cudaError_t e = cudaMemcpy(d_w, speaker_wavs, n_w * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        const dim3 rows((dim + 7) / 8, 1);
+        CondLinearArgs a;
+        a.w = m->cfg_proj; a.table = m->cfg_embed; a.row = 2; a.y = d_cfg;
+        cond_linear_kernel<<<rows, 256, 0, s->st>>>(a);
+        a.w = m->control_proj; a.table = m->control_embed; a.row = 0; a.y = d_ctl;
+        cond_linear_kernel<<<rows, 256, 0, s->st>>>(a);
+        cond_add_kernel<<<(dim + 255) / 256, 256, 0, s->st>>>(d_cfg, d_ctl, d_sum, dim);
+        CondLinearArgs b;                                              // column t of the transposed wavs: x[k] = wavs[k][t]
+        b.w = m->spk_proj; b.row = -1; b.x = d_w; b.xstride = frames; b.xcol = 1; b.y = d_s;
+        cond_linear_kernel<<<dim3((dim + 7) / 8, frames), 256, 0, s->st>>>(b);
+        cond_cross_kernel<<<tc, 256, 0, s->st>>>(d_s, m->spk_pad, m->cond_freq, d_cross, frames, dim);
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaMemcpyAsync(sum.data(), d_sum, (size_t)dim * 4, cudaMemcpyDeviceToHost, s->st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(cross.data(), d_cross, n_c * 4, cudaMemcpyDeviceToHost, s->st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s->st);
+    }
+    cudaFree(buf);
+    if (e != cudaSuccess) return fail(MSX_ERR_CUDA, std::string("voice conditioners: ") + cudaGetErrorString(e));
+    if (sum_out) memcpy(sum_out, sum.data(), (size_t)dim * 4);
+    if (cross_out) memcpy(cross_out, cross.data(), n_c * 4);
+    return msx_stream_set_condition(s, sum.data(), cross.data(), tc);
+}
+
+// moshi_lm_set_voice_condition + moshi_lm_load_voice_condition (moshi.cpp:729-760): the voice file is a safetensors whose
+// "speaker_wavs" tensor ([1,] channels, frames; f32 / f16 / bf16) feeds the conditioners
+extern "C" int msx_model_has_conditioners(const msx_model *m) { return m && m->has_conditioners ? 1 : 0; }
+
+extern "C" int msx_stream_load_voice(msx_stream *s, const char *path) {
+    if (!s || !path) return fail(MSX_ERR_ARG, "null argument");
+    SafeTensorsFile f;
+    std::string err;
+    if (!f.open(path, err)) {
+        const bool io = err.rfind("cannot", 0) == 0;
+        return fail(io ? MSX_ERR_IO : MSX_ERR_FORMAT, err);
+    }
+    for (const SafeTensor &t : f.tensors()) {
+        if (t.name != "speaker_wavs") continue;
+        std::vector<int64_t> shape = t.shape;
+        while (shape.size() > 2 && shape.front() == 1) shape.erase(shape.begin());
+        const int esz = t.dtype == "F32" ? 4 : (t.dtype == "F16" || t.dtype == "BF16") ? 2 : 0;
+        if (shape.size() != 2 || !esz || (uint64_t)(shape[0] * shape[1] * esz) != t.nbytes)
+            return fail(MSX_ERR_FORMAT, "speaker_wavs must be a [channels, frames] float tensor");
+        std::vector<float> w((size_t)(shape[0] * shape[1]));
+        for (size_t i = 0; i < w.size(); i++) {
+            if (esz == 4) memcpy(&w[i], t.data + i * 4, 4);
+            else {
+                uint16_t h; memcpy(&h, t.data + i * 2, 2);
+                if (t.dtype == "BF16") { const uint32_t u = (uint32_t)h << 16; memcpy(&w[i], &u, 4); }
+                else { __half v; memcpy(&v, &h, 2); w[i] = __half2float(v); }
+            }
+        }
+        return msx_stream_set_voice(s, w.data(), (int)shape[0], (int)shape[1], nullptr, nullptr);
+    }
+    return fail(MSX_ERR_FORMAT, std::string(path) + " has no speaker_wavs tensor");
+}
+
 extern "C" int msx_vad(msx_stream *s, float *vad) {
     if (!s || !vad) return fail(MSX_ERR_ARG, "null argument");
     const msx_model *m = s->m;
@@ -2091,6 +2198,7 @@ bool is_embedding_table_name(const std::string &name) {
 // loader.h:161-172: Q4_K needs K % 256 == 0 else Q4_0, Q4_0 / Q8_0 need K % 32 == 0 else the tensor stays as it is
 int on_load_type(int quantize, const std::string &name, int type, int n_dims, int64_t K) {
     if (!quantize || !is_float_type(type) || n_dims != 2 || name.rfind("lm.", 0) != 0) return type;
+    if (name.find("condition_provider") != std::string::npos) return type;      // fetched without a destination type (tts.h:16-35)
     int dst = quantize;
     if (dst == T_Q4_K && is_embedding_table_name(name)) dst = T_Q4_0;
     if (dst == T_Q4_K && K % 256) dst = T_Q4_0;

@@ -219,4 +219,60 @@ __global__ void __launch_bounds__(kSmallThreads) small_linear_kernel(const Small
     else a.out[row] = y;
 }
 
+// ---- voice conditioners (one-off per voice; src/moshi.cpp:296-366 voice_condition) --------------------------------
+// FloatTensor: an unquantised GGUF tensor kept in its file type (f32 / f16 / bf16), [ne1][ne0] row-major.
+struct FloatTensor {
+    const uint8_t *data = nullptr;
+    int32_t type = 0;                // 0 f32, 1 f16, 30 bf16
+    int32_t ne0 = 0, ne1 = 1;
+};
+__device__ __forceinline__ float float_tensor_at(const FloatTensor &t, long long i) {
+    if (t.type == 0) return reinterpret_cast<const float *>(t.data)[i];
+    if (t.type == 1) return __half2float(reinterpret_cast<const __half *>(t.data)[i]);
+    return bf16_bits_to_f32(reinterpret_cast<const uint16_t *>(t.data)[i]);
+}
+// ggml_mul_mat with an f32 / f16 / bf16 weight: the activation is rounded to the weight's type (vec_dot_type), products
+// are exact in double, summed in double, rounded once (order-independent like every other reduction here).
+// y[col][r] = sum_k W[r][k] * x[col * xcol + k * xstride]; row < 0: x is a vector, row >= 0: x = row `row` of `table`.
+struct CondLinearArgs {
+    FloatTensor w, table;
+    int32_t row = -1;
+    const float *x = nullptr;
+    long long xstride = 1, xcol = 0;
+    float *y = nullptr;              // [ncols][w.ne1]
+};
+__global__ void __launch_bounds__(256) cond_linear_kernel(const CondLinearArgs a) {
+    const int lane = threadIdx.x & 31, r = blockIdx.x * 8 + (threadIdx.x >> 5), col = blockIdx.y;
+    if (r >= a.w.ne1) return;
+    double acc = 0.0;
+    for (int k = lane; k < a.w.ne0; k += 32) {
+        float xv = a.row >= 0 ? float_tensor_at(a.table, (long long)a.row * a.table.ne0 + k) : a.x[col * a.xcol + k * a.xstride];
+        if (a.w.type == 1) xv = __half2float(__float2half_rn(xv));
+        else if (a.w.type == 30) xv = __bfloat162float(__float2bfloat16_rn(xv));
+        acc += (double)float_tensor_at(a.w, (long long)r * a.w.ne0 + k) * (double)xv;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) a.y[(size_t)col * a.w.ne1 + r] = (float)acc;
+}
+// condition_cross[t][d] = (t < T ? speaker[t][d] : learnt_padding[d]) + timestep_embedding(t)[d], t in [0, 5T):
+// ggml_timestep_embedding = [cos(t f_j) | sin(t f_j)], f_j = expf(-logf(P) j / half) (host-computed like the RoPE table);
+// cos / sin in double, rounded once.
+__global__ void cond_cross_kernel(const float *speaker, FloatTensor pad, const float *freq, float *out, int T, int dim) {
+    const int t = blockIdx.x, half = dim >> 1;
+    for (int d = threadIdx.x; d < dim; d += blockDim.x) {
+        const float base = t < T ? speaker[(size_t)t * dim + d] : float_tensor_at(pad, d);
+        float pos = 0.f;
+        if (d < 2 * half) {
+            const float arg = __fmul_rn((float)t, freq[d < half ? d : d - half]);
+            pos = d < half ? (float)cos((double)arg) : (float)sin((double)arg);
+        }
+        out[(size_t)t * dim + d] = __fadd_rn(base, pos);
+    }
+}
+__global__ void cond_add_kernel(const float *a, const float *b, float *y, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = __fadd_rn(a[i], b[i]);
+}
+
 }  // namespace msx

@@ -304,6 +304,7 @@ struct moshi_lm_gen_t {
     // TTS (voice_t + machine of the reference's moshi_lm_gen_t, moshi.cpp:586-606)
     bool has_voice = false;
     std::vector<float> cond_sum, cond_cross; int tc = 0;
+    std::string voice_path; bool voice_from_file = false;      // moshi_lm_set_voice_condition / _load_voice_condition
     std::deque<int> text_prefixes;
     std::deque<std::vector<int>> audio_prefixes;
     moshi_tts_machine_t *machine = nullptr;
@@ -318,11 +319,26 @@ int moshi_lm_set_condition(moshi_lm_gen_t *gen, const float *cond_sum, const flo
     gen->cond_sum.clear(); gen->cond_cross.clear(); gen->tc = 0;
     if (cond_sum) gen->cond_sum.assign(cond_sum, cond_sum + c.dim);
     if (cond_cross && tc > 0) { gen->cond_cross.assign(cond_cross, cond_cross + (size_t)tc * c.dim); gen->tc = tc; }
-    gen->has_voice = true;
+    gen->has_voice = true; gen->voice_from_file = false;
     return 0;
 }
-int moshi_lm_set_voice_condition(moshi_context_t *, moshi_lm_gen_t *gen, const char *) { return gen->lm->cfg.cross_attention ? -2 : -1; }
-int moshi_lm_load_voice_condition(moshi_context_t *, moshi_lm_gen_t *gen) { return gen->lm->cfg.cross_attention ? -2 : -1; }
+// moshi.cpp:729-760: -1 without cross-attention or when the voice file cannot be opened, -2 when the model carries no
+// conditioners; the conditioners themselves run on the GPU at moshi_lm_start (msx_stream_load_voice)
+int moshi_lm_set_voice_condition(moshi_context_t *, moshi_lm_gen_t *gen, const char *filepath) {
+    if (!gen->lm->cfg.cross_attention) return -1;
+    FILE *f = filepath ? fopen(filepath, "rb") : nullptr;
+    if (!f) return -1;
+    fclose(f);
+    gen->voice_path = filepath;
+    return 0;
+}
+int moshi_lm_load_voice_condition(moshi_context_t *, moshi_lm_gen_t *gen) {
+    if (!gen->lm->cfg.cross_attention) return -1;
+    if (!gen->lm->model || !msx_model_has_conditioners(gen->lm->model)) return -2;
+    if (gen->voice_path.empty()) return -1;
+    gen->has_voice = gen->voice_from_file = true;
+    return 0;
+}
 int moshi_lm_voice_prefix(moshi_lm_gen_t *gen, std::deque<int> &text_prefix, std::deque<std::vector<int>> &audio_prefix) {
     gen->text_prefixes.clear(); gen->audio_prefixes.clear();
     gen->text_prefixes.swap(text_prefix);                      // the reference swaps (steals) both deques (moshi.cpp:768-769)
@@ -420,7 +436,9 @@ void moshi_lm_start(moshi_context_t *, moshi_lm_gen_t *gen, float depth_temperat
         if (msx_stream_set_sampling(gen->stream, text_temperature, depth_temperature, 25, 250) != 0) { fprintf(stderr, "moshi_b200: %s\n", msx_last_error()); return; }
     if (gen->has_voice && !gen->lm->cfg.personaplex) {
         // TTS: conditioning memory + state machine (moshi.cpp:857-871: max_padding 8, initial_padding 2)
-        if (!gen->cond_sum.empty() || gen->tc > 0)
+        if (gen->voice_from_file) {
+            if (msx_stream_load_voice(gen->stream, gen->voice_path.c_str()) != 0) { fprintf(stderr, "moshi_b200: %s\n", msx_last_error()); return; }
+        } else if (!gen->cond_sum.empty() || gen->tc > 0)
             if (msx_stream_set_condition(gen->stream, gen->cond_sum.empty() ? nullptr : gen->cond_sum.data(),
                                          gen->tc > 0 ? gen->cond_cross.data() : nullptr, gen->tc) != 0) { fprintf(stderr, "moshi_b200: %s\n", msx_last_error()); return; }
         delete gen->machine;

@@ -1,7 +1,7 @@
 // moshi_sts_bench.cpp — the `--bench` entry point of the reference's speech-to-speech tools
 // (tools/moshi-sts.cpp:731-808, tools/personaplex.cpp) reduced to the LM path: the Mimi encoder/decoder and
 // SDL/FFmpeg I/O are out of scope, so user audio codes are synthetic (seeded LCG) instead of encoded silence.
-//   moshi-sts-bench <model.gguf> <config.json> [frames=125] [device=0] [--print-tokens] [-q q8_0|q4_k] [-g out.gguf]
+//   moshi-sts-bench <model.gguf> <config.json> [frames=125] [device=0] [--print-tokens] [-q q8_0|q4_k] [-g out.gguf] [--voice v.safetensors]
 // -q quantises an unquantised (f32 / f16 / bf16) GGUF while loading, -g writes the quantised weights as a GGUF and exits
 // (tools/moshi-sts.cpp `-q`, `-g`: moshi_lm_quantize, moshi_lm_save_gguf).
 // For a TTS model (model_type "tts": no user stream, cross-attention conditioning) it runs the moshi-tts --bench loop
@@ -21,11 +21,12 @@ int main(int argc, char **argv) {
     if (argc < 3) { fprintf(stderr, "usage: %s model.gguf config.json [frames] [device] [--print-tokens]\n", argv[0]); return 2; }
     int frames = 125, device = 0, positional = 0;
     bool print_tokens = false;
-    const char *quant = nullptr, *save_path = nullptr;
+    const char *quant = nullptr, *save_path = nullptr, *voice_path = nullptr;
     for (int i = 3; i < argc; i++) {
         if (!strcmp(argv[i], "--print-tokens")) print_tokens = true;
         else if (!strcmp(argv[i], "-q") && i + 1 < argc) quant = argv[++i];
         else if (!strcmp(argv[i], "-g") && i + 1 < argc) save_path = argv[++i];
+        else if (!strcmp(argv[i], "--voice") && i + 1 < argc) voice_path = argv[++i];
         else if (argv[i][0] != '-') { (positional == 0 ? frames : device) = atoi(argv[i]); positional++; }
     }
 
@@ -46,7 +47,11 @@ int main(int argc, char **argv) {
         auto rnd = [&]() { l2 = l2 * 1664525u + 1013904223u; return ((l2 >> 8) % 2001) / 1000.f - 1.f; };
         for (float &v : sum) v = 0.2f * rnd();
         for (float &v : cross) v = rnd();
-        if (moshi_lm_set_condition(gen, sum.data(), config.cross_attention ? cross.data() : nullptr, tc) != 0) { fprintf(stderr, "error: set_condition\n"); return 1; }
+        if (voice_path) {            // tools/moshi-tts.cpp: a voice file through the model's own conditioners
+            const int a = moshi_lm_set_voice_condition(moshi, gen, voice_path);
+            const int b = a == 0 ? moshi_lm_load_voice_condition(moshi, gen) : 0;
+            if (a != 0 || b != 0) { fprintf(stderr, "error: voice condition (%d, %d)\n", a, b); return 1; }
+        } else if (moshi_lm_set_condition(gen, sum.data(), config.cross_attention ? cross.data() : nullptr, tc) != 0) { fprintf(stderr, "error: set_condition\n"); return 1; }
         moshi_lm_start(moshi, gen, 0.f, 0.f);
         uint32_t l3 = 99;
         for (int w = 0; w < 6; w++) {                                // six "words" of 1-3 tokens, padding 0-1

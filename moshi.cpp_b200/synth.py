@@ -94,6 +94,9 @@ def random_tensor(rng, gtype: int, rows: int, k: int, std: float) -> np.ndarray:
     raise ValueError(gtype)
 
 
+COND_EMBED, COND_CHANNELS = 64, 96       # conditioner embedding width / speaker_wavs channels of the synthetic TTS preset
+
+
 def linear_type(qtype: int, k: int) -> int:
     """loader.h:162-173: Q4_K needs K%256==0 else Q4_0, Q4_0/Q8_0 need K%32==0 else source dtype (bf16)."""
     if qtype == GGML_Q4_K and k % 256:
@@ -168,6 +171,16 @@ def manifest(cfg: dict, qtype: int):
             lin(f"lm.linears.{k}.weight", dd, cfg["card"])
     for j in range(cfg["extra_heads"]):
         lin(f"lm.extra_heads.{j}.weight", d, cfg["extra_heads_dim"])
+    if cfg.get("conditioners"):                                            # tts.h:16-35; never quantised (fetched as stored)
+        cp, E, C = "lm.condition_provider.conditioners.", COND_EMBED, COND_CHANNELS
+        out.append((cp + "cfg.embed.weight", GGML_F32, E, 7, 0.5))
+        bias(cp + "cfg.learnt_padding", d)
+        out.append((cp + "cfg.output_proj.weight", GGML_BF16, E, d, 1.0 / np.sqrt(E)))
+        out.append((cp + "control.embed.weight", GGML_BF16, E, 2, 0.5))
+        bias(cp + "control.learnt_padding", d)
+        out.append((cp + "control.output_proj.weight", GGML_F32, E, d, 1.0 / np.sqrt(E)))
+        bias(cp + "speaker_wavs.learnt_padding", d)
+        out.append((cp + "speaker_wavs.output_proj.weight", GGML_F16, C, d, 1.0 / np.sqrt(C)))
     return out
 
 

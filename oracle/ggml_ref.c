@@ -136,6 +136,12 @@ void orc_quantize_row_q8_0(const float *x, void *dst, int64_t k) {
     }
 }
 
+/* ggml_timestep_embedding frequencies: freq_j = expf(-logf(max_period) * j / half), libm single precision like the host
+ * side of both implementations (used by the voice conditioners' position embedding, src/moshi.cpp:338-341) */
+void orc_timestep_freq(int half, int max_period, float *out) {
+    for (int j = 0; j < half; j++) out[j] = (float)expf(-logf((float)max_period) * j / half);
+}
+
 /* quantize_row_q4_0_ref (ggml-quants.c; cross-checked bit for bit with gguf/quants.py Q4_0.quantize_blocks):
  * the element of largest magnitude keeps its sign, d = that / -8, q = min(15, trunc(x / d + 8.5)). */
 void orc_quantize_row_q4_0(const float *x, void *dst, int64_t k) {

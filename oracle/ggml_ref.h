@@ -52,6 +52,7 @@ typedef struct orc_lmgen orc_lmgen;
 int64_t orc_row_size(int type, int64_t k);                       /* bytes of one row of k elements */
 void orc_dequantize_row(int type, const void *src, float *dst, int64_t k);
 void orc_quantize_row_q8_0(const float *x, void *dst, int64_t k);
+void orc_timestep_freq(int half, int max_period, float *out);
 void orc_quantize_row_q4_0(const float *x, void *dst, int64_t k);
 void orc_quantize_row_q4_K(const float *x, void *dst, int64_t k);
 void orc_quantize_row_q8_K(const float *x, int8_t *qs, float *d, int16_t *bsums, int64_t k);

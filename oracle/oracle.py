@@ -53,6 +53,7 @@ def lib():
         L.orc_quantize_row_q8_0.argtypes = [vp, vp, C.c_int64]
         L.orc_quantize_row_q8_K.argtypes = [vp, vp, vp, vp, C.c_int64]
         L.orc_quantize_row_q4_0.argtypes = [vp, vp, C.c_int64]
+        L.orc_timestep_freq.argtypes = [C.c_int, C.c_int, vp]
         L.orc_quantize_row_q4_K.argtypes = [vp, vp, C.c_int64]
         L.orc_mul_mat_vec.argtypes = [C.c_int, vp, C.c_int64, C.c_int64, vp, vp]
         L.orc_mul_mat_vec_ideal.argtypes = [C.c_int, vp, C.c_int64, C.c_int64, vp, vp]
@@ -178,6 +179,8 @@ class Model:
         self.h = lib().orc_model_new(C.byref(self._ccfg))
         self._keep = []
         for t in self.reader.tensors:
+            if ".condition_provider." in t.name:    # voice conditioners: used by voice_condition() below, not by the step
+                continue
             shape = [int(s) for s in t.shape]       # ggml order: ne0 fastest
             ne0 = shape[0]; ne1 = shape[1] if len(shape) > 1 else 1
             data = t.data
@@ -304,3 +307,61 @@ class LMGen:
                 lib().orc_lmgen_free(self.h); self.h = None
         except Exception:
             pass
+
+
+# ---- voice conditioners (one-off per voice) ------------------------------------------------------------------------
+def _tensor_f32(t):
+    """(float32 [rows, ne0], ggml type) of a GGUFReader tensor stored as f32 / f16 / bf16"""
+    raw = np.ascontiguousarray(t.data).view(np.uint8).reshape(-1)
+    gt = int(t.tensor_type)
+    ne0 = int(t.shape[0])
+    if gt == 0:
+        v = raw.view(np.float32)
+    elif gt == 1:
+        v = raw.view(np.float16).astype(np.float32)
+    elif gt == 30:
+        v = (raw.view(np.uint16).astype(np.uint32) << 16).view(np.float32)
+    else:
+        raise ValueError(f"{t.name}: conditioner tensors are unquantised, got type {gt}")
+    return v.reshape(-1, ne0), gt
+
+
+def _round_to_type(x, gt):
+    """ggml_mul_mat rounds the activation to the weight's type (vec_dot_type): f16 / bf16 RNE, f32 as is"""
+    x = np.asarray(x, dtype=np.float32)
+    if gt == 1:
+        return x.astype(np.float16).astype(np.float32)
+    if gt == 30:
+        u = x.view(np.uint32)
+        return (((u + (0x7FFF + ((u >> 16) & 1))) >> 16).astype(np.uint32) << 16).view(np.float32)
+    return x
+
+
+def voice_condition(gguf_path: str, cfg: dict, speaker_wavs: np.ndarray):
+    """voice_condition() of the reference (src/moshi.cpp:296-366) restated with the order-independent arithmetic of the
+    rest of the oracle (exact products, double sums, one rounding).  speaker_wavs: [channels][frames] as stored in the
+    voice file.  Returns (condition_sum [dim], condition_cross [5 * frames][dim]).  PARITY UNPINNED: the reference ships
+    no voice fixtures; ggml's own summation order and libm cosf / sinf differ from this in the last bit."""
+    from gguf import GGUFReader
+    tens = {t.name: t for t in GGUFReader(gguf_path).tensors}
+    cp = "lm.condition_provider.conditioners."
+
+    def proj(wname, x):
+        w, gt = _tensor_f32(tens[cp + wname])
+        return (w.astype(np.float64) @ _round_to_type(x, gt).astype(np.float64)).astype(np.float32)
+
+    cfg_emb = _tensor_f32(tens[cp + "cfg.embed.weight"])[0][2]            # cfg 2.0 -> row 2
+    control_emb = _tensor_f32(tens[cp + "control.embed.weight"])[0][0]    # control "ok" -> row 0
+    cond_sum = proj("cfg.output_proj.weight", cfg_emb) + proj("control.output_proj.weight", control_emb)
+    wavs = np.ascontiguousarray(speaker_wavs, dtype=np.float32)
+    T, dim = wavs.shape[1], cfg["dim"]
+    pad = _tensor_f32(tens[cp + "speaker_wavs.learnt_padding"])[0].reshape(-1)
+    cross = np.tile(pad, (5 * T, 1)).astype(np.float32)
+    for t in range(T):
+        cross[t] = proj("speaker_wavs.output_proj.weight", wavs[:, t])
+    half = dim // 2                                                      # ggml_timestep_embedding(positions, dim, 10000)
+    freq = np.empty(half, dtype=np.float32)
+    lib().orc_timestep_freq(half, 10000, _p(freq))
+    arg = (np.arange(5 * T, dtype=np.float32)[:, None] * freq[None, :]).astype(np.float32)
+    pos = np.concatenate([np.cos(arg.astype(np.float64)), np.sin(arg.astype(np.float64))], axis=1).astype(np.float32)
+    return cond_sum.astype(np.float32), (cross + pos).astype(np.float32)

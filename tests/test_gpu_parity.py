@@ -494,6 +494,63 @@ def test_condition_changes_output_and_can_be_replaced(msx, orc, gguf_for):
         s2.set_condition(None, np.zeros((2, cfg2["dim"]), dtype=np.float32))
 
 
+@pytest.mark.parametrize("quant,frames", [("q4_k", 5), ("q8_0", 12)])
+def test_voice_conditioners_match_oracle(msx, orc, gguf_for, quant, frames, tmp_path):
+    """SURVEY.md §8f rank 1, the conditioners (voice_condition, moshi.cpp:296-366): cfg / control look-up tables and their
+    projections, the projected speaker embedding + learnt padding + sinusoidal positions -> condition_sum / condition_cross
+    on the GPU == the oracle's restatement; the frames that follow agree with the oracle fed the oracle's own tensors;
+    a voice .safetensors (bf16 [1, C, T]) gives the same as its values passed directly."""
+    from moshi_cpp_b200 import synth
+    path, cfg = gguf_for("tiny_tts_voice", quant)
+    gm = msx.Model(path, cfg); gs = msx.Stream(gm)
+    assert msx.lib().msx_model_has_conditioners(gm.h) == 1
+    om = orc.Model(path, cfg); os_ = orc.State(om)
+    rng = np.random.default_rng(31)
+    wavs = rng.standard_normal((synth.COND_CHANNELS, frames)).astype(np.float32)
+    cs, cc = gs.set_voice(wavs)
+    rs, rc = orc.voice_condition(path, cfg, wavs)
+    assert cc.shape == rc.shape == (5 * frames, cfg["dim"])
+    assert np.abs(cs - rs).max() <= 1e-6 and np.abs(cc - rc).max() <= 1e-6
+    exact = (cs.view(np.uint32) == rs.view(np.uint32)).mean(), (cc.view(np.uint32) == rc.view(np.uint32)).mean()
+    assert min(exact) > 0.999, exact
+    assert np.abs(cc[frames:2 * frames] - cc[2 * frames:3 * frames]).max() > 1e-3   # padding rows differ by their positions only
+    os_.set_condition(rs, rc)
+    toks = np.array([cfg["text_card"]] + [cfg["card"]] * cfg["n_q"], dtype=np.int32)
+    for f in range(4):
+        t_ref, lg_ref, _ = os_.step_temporal(toks)
+        t_gpu, lg_gpu, _ = gs.step_temporal(toks)
+        assert max_rel(lg_gpu, lg_ref) < LOGIT_TOL and t_gpu == t_ref, f"frame {f}"
+        a_ref, _ = os_.step_depformer(t_ref)
+        a_gpu, _ = gs.step_depformer(t_ref)
+        assert np.array_equal(a_ref, a_gpu)
+        toks = np.array([t_ref] + list(a_ref) + [0] * (cfg["n_q"] - len(a_ref)), dtype=np.int32)
+    # the voice file form
+    bits = ((wavs.view(np.uint32) + 0x7FFF + ((wavs.view(np.uint32) >> 16) & 1)) >> 16).astype(np.uint16)
+    vp = str(tmp_path / "voice.safetensors")
+    synth.write_safetensors(vp, [("speaker_wavs", "BF16", [1, synth.COND_CHANNELS, frames], bits.tobytes())])
+    g2 = msx.Stream(gm); g3 = msx.Stream(gm)
+    g2.load_voice(vp)
+    g3.set_voice((bits.astype(np.uint32) << 16).view(np.float32))
+    toks = np.array([cfg["text_card"]] + [cfg["card"]] * cfg["n_q"], dtype=np.int32)
+    _, l2, _ = g2.step_temporal(toks); _, l3, _ = g3.step_temporal(toks)
+    assert np.array_equal(l2.view(np.uint32), l3.view(np.uint32))
+    # error behaviour: wrong channel count; a TTS model without conditioner tensors (reference -2); no cross-attention (-1)
+    with pytest.raises(msx.MsxError) as e:
+        gs.set_voice(np.zeros((synth.COND_CHANNELS + 1, 3), np.float32))
+    assert e.value.code == -1
+    p2, c2 = gguf_for("tiny_tts", quant)
+    with pytest.raises(msx.MsxError) as e:
+        msx.Stream(msx.Model(p2, c2)).set_voice(wavs)
+    assert e.value.code == -5
+    p3, c3 = gguf_for("tiny", "q4_k")
+    with pytest.raises(msx.MsxError) as e:
+        msx.Stream(msx.Model(p3, c3)).load_voice(vp)
+    assert e.value.code == -5
+    with pytest.raises(msx.MsxError) as e:
+        gs.load_voice(str(tmp_path / "missing.safetensors"))
+    assert e.value.code == -2
+
+
 def test_voice_embedding_prompt_matches_oracle(msx, orc, gguf_for):
     """PersonaPlex voice-embedding prompt (lm.h:694-709, 1005-1036): f32 rows fed straight into the
     temporal transformer, text forced to 3, depformer run; then normal token frames continue on the same KV state"""

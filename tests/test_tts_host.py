@@ -58,16 +58,26 @@ def test_state_machine_matches_restatement(host, ahead, seed):
 
 
 @pytest.mark.gpu
-def test_tts_loop_cpp_api_vs_c_abi(gguf_for, tmp_path):
+@pytest.mark.parametrize("voice", [False, True])
+def test_tts_loop_cpp_api_vs_c_abi(gguf_for, tmp_path, voice):
     """moshi_lm_set_condition / start / send(Entry) / receive-while-is_active through the C++ mirror (the tool) ==
     the same loop in Python: delay ring (lm.h:796-979, no user stream), state machine between the two graphs."""
     tool = msx.STS_BENCH
     msx.build_host()
-    path, cfg = gguf_for("tiny_tts", "q4_k")
+    path, cfg = gguf_for("tiny_tts_voice" if voice else "tiny_tts", "q4_k")
     cj = tmp_path / "config.json"
     with open(cj, "w") as f:
         json.dump(configs.to_config_json(cfg), f)
-    r = subprocess.run([tool, path, str(cj), "60", "0", "--print-tokens"], capture_output=True, text=True, timeout=300)
+    extra = []
+    if voice:      # moshi_lm_set_voice_condition + moshi_lm_load_voice_condition (moshi.cpp:729-760): a voice file, the model's conditioners
+        from moshi_cpp_b200 import synth
+        wavs = np.random.default_rng(8).standard_normal((synth.COND_CHANNELS, 7)).astype(np.float32)
+        vp = str(tmp_path / "voice.safetensors")
+        synth.write_safetensors(vp, [("speaker_wavs", "F32", [1, synth.COND_CHANNELS, 7], wavs.tobytes())])
+        extra = ["--voice", vp]
+        bad = subprocess.run([tool, gguf_for("tiny_tts", "q4_k")[0], str(cj), "4", "0", "--voice", vp], capture_output=True, text=True, timeout=300)
+        assert bad.returncode == 1 and "(0, -2)" in bad.stderr          # no conditioner tensors in that GGUF
+    r = subprocess.run([tool, path, str(cj), "60", "0", "--print-tokens"] + extra, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr
     got = [[int(v) for v in l.split()] for l in r.stdout.strip().splitlines()]
 
@@ -89,7 +99,10 @@ def test_tts_loop_cpp_api_vs_c_abi(gguf_for, tmp_path):
         machine.push(toks, w % 2)
 
     gm = msx.Model(path, cfg); gs = msx.Stream(gm)
-    gs.set_condition(cs, cc)
+    if voice:
+        gs.load_voice(vp)
+    else:
+        gs.set_condition(cs, cc)
     ncb, dep_q, delays = cfg["n_q"] + 1, cfg["dep_q"], cfg["delays"]
     max_delay = max(delays); CT = max_delay + 2
     cache = np.full((CT, ncb), -2, dtype=np.int64)
