@@ -107,16 +107,42 @@ def ensure_gguf(preset, quant, rank, world, barrier):
     return path
 
 
+def user_codes(cfg, row):
+    """the codes the caller supplies per frame: the user stream (n_q - dep_q codebooks), all n_q for STT, none for TTS"""
+    n_user = cfg["n_q"] - cfg["dep_q"] if cfg["dep_q"] > 0 else cfg["n_q"]
+    return row[len(row) - n_user:]
+
+
+def tts_condition(cfg, tc=125):
+    """synthetic conditioning of a cross-attention (TTS) model: condition_sum [dim] and a memory of tc = 5 x 25 rows, the
+    shape voice_condition (moshi.cpp:296-366) produces for a 25-frame speaker embedding"""
+    rng = np.random.default_rng(SEED_TOKENS + 1)
+    return (0.2 * rng.standard_normal(cfg["dim"])).astype(np.float32), rng.standard_normal((tc, cfg["dim"])).astype(np.float32)
+
+
 def cpu_reference_fps(path, cfg, frames, max_frames, budget_s):
     """The oracle (CPU restatement of the reference's ggml-CPU path) on the host cores, greedy LMGen."""
     import oracle
     om = oracle.Model(path, cfg)
-    og = oracle.LMGen(om)
-    n_user = cfg["n_q"] - cfg["dep_q"] if cfg["dep_q"] > 0 else cfg["n_q"]
-    og.step(frames[0][-n_user:])                       # warm-up frame (page-in of the mmapped weights)
+    if cfg.get("cross_attention"):                      # TTS: the same two graphs per frame on a conditioned state
+        st = oracle.State(om)
+        st.set_condition(*tts_condition(cfg))
+        toks = np.array([cfg["text_card"]] + [cfg["card"]] * cfg["n_q"], dtype=np.int32)
+
+        def step(_):
+            nonlocal toks
+            t, _, _ = st.step_temporal(toks)
+            a, _ = st.step_depformer(t)
+            toks = np.array([t] + list(a) + [0] * (cfg["n_q"] - len(a)), dtype=np.int32)
+    else:
+        og = oracle.LMGen(om)
+
+        def step(i):
+            og.step(user_codes(cfg, frames[i % len(frames)]))
+    step(0)                                            # warm-up frame (page-in of the mmapped weights)
     t0 = time.perf_counter(); n = 0
     while n < max_frames:
-        og.step(frames[(n + 1) % len(frames)][-n_user:]); n += 1
+        step(n + 1); n += 1
         if time.perf_counter() - t0 > budget_s:
             break
     dt = time.perf_counter() - t0
@@ -143,7 +169,9 @@ def main():
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     cfg = configs.get(args.preset)
-    workload = f"{args.preset} {args.quant} speech-to-speech step (temporal transformer + depformer), single stream per GPU"
+    kind = {"tts": "text-to-speech decode step (temporal transformer with cross-attention + depformer)",
+            "stt": "speech-to-text step (temporal transformer)"}.get(cfg.get("model_type"), "speech-to-speech step (temporal transformer + depformer)")
+    workload = f"{args.preset} {args.quant} {kind}, single stream per GPU"
     base_cfg = {"workload": workload, "streams_per_gpu": 1, "sharding": "independent conversation streams (replicas), no data-path collective",
                 "l2": "inputs larger than L2 (each frame streams the full weight set, 4.1 GB >> 126 MB)",
                 "model_seed": SEED_MODEL, "token_seed": SEED_TOKENS, "context": cfg["context"]}
@@ -219,6 +247,8 @@ def main():
     stream = msx.Stream(model)
     t_load = time.perf_counter() - t_load
     K, W = args.steps, max(3, args.warmup)
+    if cfg.get("cross_attention"):
+        stream.set_condition(*tts_condition(cfg))
 
     sampler = ClockSampler(local_rank)
     # ---- value: device-resident replay ---------------------------------------------------------
@@ -232,14 +262,13 @@ def main():
     # ---- e2e: public per-frame API, host tokens in / out every frame ------------------------------
     stream.reset()
     gen = msx.Gen(stream)
-    n_user = cfg["n_q"] - cfg["dep_q"] if cfg["dep_q"] > 0 else cfg["n_q"]
     for i in range(W):
-        gen.step(frames[i % len(frames)][-n_user:])
+        gen.step(user_codes(cfg, frames[i % len(frames)]))
     barrier(); torch.cuda.synchronize(local_rank)
     stream.timer_start()
     t0 = time.perf_counter()
     for i in range(K):
-        gen.step(frames[(W + i) % len(frames)][-n_user:])
+        gen.step(user_codes(cfg, frames[(W + i) % len(frames)]))
     ms_e2e = stream.timer_stop()
     wall_e2e = (time.perf_counter() - t0) * 1e3
     torch.cuda.synchronize(local_rank); barrier()
@@ -298,7 +327,7 @@ def main():
 
     # ---- batched streams (config 5): n conversations per GPU, weights read once per frame for all -------------
     batched = None
-    if args.streams > 1 and args.quant in ("q4_k", "q8_0"):
+    if args.streams > 1 and args.quant in ("q4_k", "q8_0") and not (cfg.get("cross_attention") or cfg.get("demux") or cfg.get("dep_low_rank")):
         nb = min(8, args.streams)
         t_b = time.perf_counter()
         batch = msx.Batch(model, nb)
