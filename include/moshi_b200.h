@@ -240,7 +240,8 @@ MSX_API int msx_gen_max_delay(const msx_gen *g);
 /* Batched-T prompt prefill: T frames whose n_q+1 tokens are all given (PersonaPlex voice / system
  * prompt rows, lm.h:983-1134) are run 8 positions at a time as the 8 columns of the tensor-core GEMM.  Only the temporal
  * KV rings and the position advance — exactly what T "provided" steps leave behind (their logits, sampled tokens and
- * depformer output are discarded, lm.h:933-943).  tokens [T][n_q+1]; offset + T must not exceed the ring; q4_k models. */
+ * depformer output are discarded, lm.h:933-943).  tokens [T][n_q+1].  Up to the end of the ring's first lap 8 positions go
+ * through each weight pass; positions beyond it (every insert overwrites a slot the previous position still sees) one per pass. */
 MSX_API int msx_stream_prefill(msx_stream *s, const int32_t *tokens, int n_frames);
 
 /* ---- lock-step batch of independent streams (BASELINE.json config 5) ------------------

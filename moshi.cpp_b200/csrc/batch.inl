@@ -360,7 +360,7 @@ extern "C" int msx_stream_prefill(msx_stream *s, const int32_t *tokens, int T) {
     if (!s || !tokens || T <= 0) return fail(MSX_ERR_ARG, "bad argument");
     msx_model *m = s->m; const msx_config &c = m->cfg;
     if (m->tp_world > 1 || c.cross_attention || c.demux_second_stream) return fail(MSX_ERR_STATE, "prefill covers plain single-GPU models");
-    if (s->host_offset + T > s->cap) return fail(MSX_ERR_ARG, "prefill must not wrap the KV ring (offset + T <= context)");
+    if (s->host_offset < 0 || T > (1 << 24)) return fail(MSX_ERR_ARG, "bad prompt length");
     CU(cudaSetDevice(m->device));
     if (!s->prefill) {
         msx_batch *pb = nullptr;
@@ -369,8 +369,11 @@ extern "C" int msx_stream_prefill(msx_stream *s, const int32_t *tokens, int T) {
     }
     msx_batch *b = s->prefill;
     const int n_in = c.n_q + 1;
-    for (int c0 = 0; c0 < T; c0 += b->n) {
-        const int nb = std::min(b->n, T - c0);
+    for (int c0 = 0, nb = 0; c0 < T; c0 += nb) {
+        // all columns of a pass are inserted before any of them attends, so a pass must not overwrite a slot an earlier
+        // column still sees: up to the end of the ring's first lap 8 positions per pass, beyond it one position per pass
+        const int pos0 = s->host_offset + c0;
+        nb = pos0 >= s->cap ? 1 : std::min(std::min(b->n, T - c0), s->cap - pos0);
         CU(cudaStreamSynchronize(b->st));            // the pinned staging buffers are reused per chunk
         for (int j = 0; j < b->n; j++) {
             Ctrl hdr; memset(&hdr, 0, sizeof(hdr));

@@ -1908,7 +1908,6 @@ extern "C" int msx_gen_prefill(msx_gen *g, const int32_t *rows, int T) {
     if (!g || !rows || T <= 0 || !g->s) return fail(MSX_ERR_ARG, "bad argument / callback generator");
     const msx_config &c = g->cfg;
     const int CT = g->CT, ncb = g->ncb;
-    if (g->s->host_offset + T > g->s->cap) return fail(MSX_ERR_ARG, "prefill must not wrap the KV ring");
     std::vector<int32_t> inputs((size_t)T * ncb), cache = g->cache;
     int offset = g->offset;
     for (int f = 0; f < T; f++) {

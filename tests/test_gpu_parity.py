@@ -604,9 +604,18 @@ def test_batched_prefill_equals_serial_prompt_steps(msx, gguf_for, preset, T, qu
         xa, _ = a.step_depformer(ta); xb, _ = b.step_depformer(tb)
         assert np.array_equal(xa, xb)
         toks = np.concatenate([[ta], xa, rng.integers(0, cfg["card"], size=cfg["n_q"] - cfg["dep_q"])]).astype(np.int32)
-    # ring wrap is refused
-    with pytest.raises(msx.MsxError):
-        a.prefill(np.zeros((cfg["context"], cfg["n_q"] + 1), dtype=np.int32))
+    # a prompt that runs past the end of the ring (first lap 8 positions per pass, then one per pass) == serial steps
+    more = rng.integers(0, cfg["card"], size=(cfg["context"] + 5, cfg["n_q"] + 1)).astype(np.int32)
+    more[:, 0] = rng.integers(0, cfg["text_card"], size=len(more))
+    a.prefill(more)
+    for f in range(len(more)):
+        b.step_temporal(more[f], want_logits=False)
+    assert a.offset == b.offset
+    for slot in (0, 3, cfg["context"] - 1):
+        ka, va = a.get_kv(0, 0, slot); kb, vb = b.get_kv(0, 0, slot)
+        assert np.array_equal(ka, kb) and np.array_equal(va, vb), f"KV row slot {slot} after the wrap"
+    ta, la, _ = a.step_temporal(toks); tb, lb, _ = b.step_temporal(toks)
+    assert ta == tb and np.array_equal(la.view(np.uint32), lb.view(np.uint32))
 
 
 def test_generator_prefill_equals_provided_steps(msx, gguf_for):
