@@ -149,7 +149,25 @@ def cpu_reference_fps(path, cfg, frames, max_frames, budget_s):
     return n / dt, n, dt
 
 
+_JSON_FD = None
+
+
+def emit(line: dict) -> None:
+    """the ONE JSON line of the contract, on the process's real stdout"""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    # libraries print to stdout behind our back (NCCL's "NCCL version ..." banner under torchrun): keep the real stdout
+    # for the JSON line and send everything else to stderr
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=300)
@@ -194,7 +212,7 @@ def main():
                 "realtime_factor": fps / FRAME_RATE,
                 "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": ncores, "kind": "port", "sample": sample},
                 "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     # ------------------------------------------------------------------------------------------ our arm
@@ -235,11 +253,11 @@ def main():
             fps = K / (ms_res * 1e-3)
             cfg4 = dict(base_cfg, workload=f"{args.preset} {args.quant} single stream, tensor-parallel over {world} GPUs (heads / hidden shards, "
                         "fp64 partial sums, fused GEMV -> peer-memory all-reduce)", sharding=f"tensor parallel x{world}", kv_slots_at_timing=min(stream.offset, cfg["context"]))
-            print(json.dumps({"metric": "frames_per_s", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
+            emit({"metric": "frames_per_s", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
                               "ms_per_step": ms_res / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                               "dtype": "int8 dot / f32, f64 partial sums", "data": "synthetic", "config": cfg4,
                               "realtime_factor": fps / FRAME_RATE, "gpu_launches": stream.launches_per_frame * K,
-                              "launches_per_frame": stream.launches_per_frame, "clocks": clocks}))
+                  "launches_per_frame": stream.launches_per_frame, "clocks": clocks})
         dist.destroy_process_group()
         return 0
     t_load = time.perf_counter()
@@ -402,7 +420,7 @@ def main():
             "clocks": clocks, "load_s": t_load,
             "batched_streams": batched,
         }
-        print(json.dumps(line))
+        emit(line)
     if dist is not None:
         dist.destroy_process_group()
     return 0
