@@ -2273,6 +2273,10 @@ int write_gguf(msx_model *m, const std::vector<OutTensor> &ts, const char *out_p
     if (!ok || fflush(o) != 0) return fail(MSX_ERR_IO, std::string("write failed: ") + out_path);
     return 0;
 }
+bool same_file(const char *a, const char *b) {
+    struct stat sa, sb;
+    return stat(a, &sa) == 0 && stat(b, &sb) == 0 && sa.st_dev == sb.st_dev && sa.st_ino == sb.st_ino;
+}
 bool ends_with(const std::string &s, const char *tail) {
     const size_t n = strlen(tail);
     return s.size() >= n && s.compare(s.size() - n, n, tail) == 0;
@@ -2282,6 +2286,7 @@ bool ends_with(const std::string &s, const char *tail) {
 extern "C" int msx_gguf_quantize(const char *in_path, const char *out_path, int quantize, int device) {
     if (!in_path || !out_path) return fail(MSX_ERR_ARG, "null argument");
     if (quantize != 0 && quantize != T_Q8_0 && quantize != T_Q4_K) return fail(MSX_ERR_ARG, "quantize takes 0 (copy), 8 (q8_0) or 12 (q4_k)");
+    if (same_file(in_path, out_path)) return fail(MSX_ERR_ARG, "output path is the input file (it is memory-mapped while the output is written)");
     GgufFile f;
     std::string err;
     if (!f.open(in_path, err)) {
@@ -2312,6 +2317,7 @@ extern "C" int msx_gguf_quantize(const char *in_path, const char *out_path, int 
 extern "C" int msx_safetensors_to_gguf(const char *in_path, const char *out_path, int quantize, int device) {
     if (!in_path || !out_path) return fail(MSX_ERR_ARG, "null argument");
     if (quantize != 0 && quantize != T_Q8_0 && quantize != T_Q4_K) return fail(MSX_ERR_ARG, "quantize takes 0 (copy), 8 (q8_0) or 12 (q4_k)");
+    if (same_file(in_path, out_path)) return fail(MSX_ERR_ARG, "output path is the input file (it is memory-mapped while the output is written)");
     SafeTensorsFile f;
     std::string err;
     if (!f.open(in_path, err)) {

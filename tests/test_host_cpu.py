@@ -69,6 +69,9 @@ def test_loader_errors_before_device(gguf_for, tmp_path):
     with pytest.raises(msx.MsxError) as e:
         msx.gguf_quantize(str(bad), str(tmp_path / "out.gguf"), "q8_0")
     assert e.value.code == -3
+    with pytest.raises(msx.MsxError) as e:                      # writing over the (memory-mapped) input is refused
+        msx.gguf_quantize(path, path, "q8_0")
+    assert e.value.code == -1
     with pytest.raises(msx.MsxError) as e:                      # safetensors front end
         msx.safetensors_to_gguf(str(tmp_path / "nope.safetensors"), str(tmp_path / "out.gguf"), "q4_k")
     assert e.value.code == -2
