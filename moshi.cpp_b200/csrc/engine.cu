@@ -2329,7 +2329,7 @@ extern "C" int msx_safetensors_to_gguf(const char *in_path, const char *out_path
     std::vector<OutTensor> ts;
     for (const SafeTensor &st : f.tensors()) {
         const int type = st.dtype == "F32" ? T_F32 : st.dtype == "F16" ? T_F16 : st.dtype == "BF16" ? T_BF16 : -1;
-        if (type < 0) return fail(MSX_ERR_FORMAT, "tensor " + st.name + " has unsupported dtype " + st.dtype);
+        if (type < 0) continue;      // integer / bool bookkeeping tensors: the reference's loader never fetches them, save_gguf never writes them
         if (st.shape.empty() || st.shape.size() > 4) return fail(MSX_ERR_FORMAT, "tensor " + st.name + " has unsupported rank");
         int64_t count = 1;
         for (int64_t v : st.shape) count *= v;

@@ -727,6 +727,7 @@ def test_safetensors_to_gguf(msx, orc, preset, quant, tmp_path):
         blob = b"".join(parts[i][2].tobytes() for i in range(len(parts)))
         st.append((f"{stem}.in_proj_weight" if kind == "in" else f"{stem}.out_proj.weight", dt[gt], [shape[0] * len(parts), shape[1]], blob))
     assert any(len(p) > 1 for p in fused.values()) or cfg["dep_q"] == 0      # per-step depformer weights really are fused
+    st.append(("num_batches_tracked", "I64", [1], (7).to_bytes(8, "little")))   # bookkeeping tensors are left out, like save_gguf does
     synth.write_safetensors(sp, st)
     msx.safetensors_to_gguf(sp, qp, quant)
     out = {t.name: t for t in gguf.GGUFReader(qp).tensors}
