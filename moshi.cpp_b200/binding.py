@@ -70,7 +70,7 @@ def build_host(force: bool = False) -> str:
         os.path.getmtime(s) > min(os.path.getmtime(HOST_SO_PATH), os.path.getmtime(STS_BENCH)) for s in srcs)
     if force or stale:
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", "-DMOSHI_BUILD", "-o", HOST_SO_PATH,
-                               srcs[0], "-L" + _HERE, "-lmoshi_b200", "-Wl,-rpath,$ORIGIN"])
+                               srcs[0], os.path.join(_HERE, "csrc", "gguf_file.cpp"), "-L" + _HERE, "-lmoshi_b200", "-Wl,-rpath,$ORIGIN"])
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", STS_BENCH, srcs[2], "-L" + _HERE, "-lmoshi", "-lmoshi_b200", "-Wl,-rpath,$ORIGIN"])
     return HOST_SO_PATH
 
@@ -426,6 +426,17 @@ class Gen:
     @property
     def offset(self):
         return lib().msx_gen_offset(self.h)
+
+    def prompt_embedding(self, x):
+        """one PersonaPlex voice-prompt frame given as an embedding row [dim] (lm.h:1005-1036)"""
+        xx = np.ascontiguousarray(x, dtype=np.float32)
+        _check(lib().msx_gen_prompt_embedding(self.h, _p(xx)))
+
+    def set_cache(self, ring):
+        """replace the token delay ring [CT][n_q+1] (lm.h:1038-1051)"""
+        r = np.ascontiguousarray(ring, dtype=np.int32)
+        assert r.shape[0] == lib().msx_gen_cache_rows(self.h)
+        _check(lib().msx_gen_set_cache(self.h, _p(r)))
 
     def prefill(self, rows):
         """rows [T][n_q+1] (all tokens given): batched-T prompt prefill with the generator's ring bookkeeping"""

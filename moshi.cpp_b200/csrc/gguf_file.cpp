@@ -12,7 +12,7 @@ namespace msx {
 
 int64_t ggml_row_size(int type, int64_t k) {
     switch (type) {
-        case T_F32: return 4 * k;
+        case T_F32: case 26 /* I32: PersonaPlex voice.cache */: return 4 * k;
         case T_F16: case T_BF16: return 2 * k;
         case T_Q4_0: return (k % 32) ? -1 : k / 32 * 18;
         case T_Q8_0: return (k % 32) ? -1 : k / 32 * 34;

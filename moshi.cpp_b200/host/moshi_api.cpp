@@ -3,12 +3,15 @@
 
 #include <algorithm>
 #include <cctype>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
 #include <unistd.h>
 
 #include "../../include/moshi_b200.h"
+#include "../csrc/gguf_file.h"
+#include "../csrc/safetensors_file.h"
 
 // ---- context -------------------------------------------------------------------------------------------
 struct moshi_context_t { int device = 0; };
@@ -384,6 +387,60 @@ int moshi_lm_personaplex_voice_tensors(moshi_lm_gen_t *gen, const float *embeddi
     gen->prompt_cache.assign(cache, cache + (size_t)cache_rows * (c.n_q + 1));
     gen->prompt_cache_rows = cache_rows;
     return 0;
+}
+// element i of a float / integer tensor stored as `dtype` (safetensors names) -> double
+static bool voice_element(const uint8_t *p, const std::string &dt, size_t i, double &out) {
+    if (dt == "F32") { float v; memcpy(&v, p + i * 4, 4); out = v; }
+    else if (dt == "BF16") { uint16_t h; memcpy(&h, p + i * 2, 2); const uint32_t u = (uint32_t)h << 16; float v; memcpy(&v, &u, 4); out = v; }
+    else if (dt == "F16") {
+        uint16_t h; memcpy(&h, p + i * 2, 2);
+        const int e = (h >> 10) & 31, m = h & 1023;
+        const double mag = e == 0 ? std::ldexp((double)m, -24) : e == 31 ? (m ? NAN : INFINITY) : std::ldexp((double)(m | 1024), e - 25);
+        out = (h & 0x8000) ? -mag : mag;
+    }
+    else if (dt == "I32") { int32_t v; memcpy(&v, p + i * 4, 4); out = v; }
+    else if (dt == "I64") { int64_t v; memcpy(&v, p + i * 8, 8); out = (double)v; }
+    else return false;
+    return true;
+}
+int moshi_lm_personaplex_load_voice(moshi_context_t *, moshi_lm_gen_t *gen, const char *filepath) {
+    if (!gen || !filepath) return -1;
+    const std::string filename = filepath;
+    const auto ext_index = filename.find_last_of('.');
+    if (ext_index == std::string::npos) return -1;
+    const std::string ext = filename.substr(ext_index);
+    const msx_config &c = gen->lm->cfg;
+    const int ncb = c.n_q + 1;
+    // (data, dtype, element count, innermost extent) of the two tensors
+    const uint8_t *emb = nullptr, *cache = nullptr;
+    std::string emb_dt, cache_dt;
+    int64_t emb_n = 0, cache_n = 0, cache_inner = 0;
+    msx::SafeTensorsFile st;
+    msx::GgufFile gg;
+    std::string err;
+    if (ext == ".safetensors") {
+        if (!st.open(filename, err)) return -1;
+        for (const auto &t : st.tensors()) {
+            int64_t n = 1;
+            for (int64_t v : t.shape) n *= v;
+            if (t.name == "embeddings") { emb = t.data; emb_dt = t.dtype; emb_n = n; }
+            else if (t.name == "cache" && !t.shape.empty()) { cache = t.data; cache_dt = t.dtype; cache_n = n; cache_inner = t.shape.back(); }
+        }
+    } else if (ext == ".gguf") {
+        if (!gg.open(filename, err)) return -1;
+        auto dt = [](int type) { return type == 0 ? "F32" : type == 1 ? "F16" : type == 30 ? "BF16" : type == 26 ? "I32" : ""; };
+        if (const msx::GgufTensor *t = gg.find("voice.embeddings")) if (t->data) { emb = t->data; emb_dt = dt(t->type); emb_n = t->ne[0] * t->ne[1] * t->ne[2] * t->ne[3]; }
+        if (const msx::GgufTensor *t = gg.find("voice.cache")) if (t->data) { cache = t->data; cache_dt = dt(t->type); cache_n = t->ne[0] * t->ne[1] * t->ne[2] * t->ne[3]; cache_inner = t->ne[0]; }
+    } else return -1;
+    if (!emb || !cache || emb_n <= 0 || emb_n % c.dim || cache_n <= 0 || cache_n != cache_inner * ncb) return -1;
+    std::vector<float> rows((size_t)emb_n);
+    for (size_t i = 0; i < rows.size(); i++) { double v; if (!voice_element(emb, emb_dt, i, v)) return -1; rows[i] = (float)v; }
+    // the file holds cache[codebook][time] (lm.h:1047-1051: state->cache[i][j] = cache[i + j * height]); ours is [time][codebook]
+    const int CT = (int)cache_inner;
+    std::vector<int32_t> ring((size_t)cache_n);
+    for (int j = 0; j < ncb; j++)
+        for (int i = 0; i < CT; i++) { double v; if (!voice_element(cache, cache_dt, (size_t)j * CT + i, v)) return -1; ring[(size_t)i * ncb + j] = (int32_t)v; }
+    return moshi_lm_personaplex_voice_tensors(gen, rows.data(), (int)(emb_n / c.dim), ring.data(), CT);
 }
 int moshi_lm_personaplex_system_prompt_tokens(moshi_lm_gen_t *gen, const std::vector<int> &text_tokens) {
     gen->text_prompt_tokens = text_tokens;

@@ -71,6 +71,9 @@ MOSHI_API int moshi_lm_personaplex_audio_prompt(moshi_lm_gen_t *gen, std::deque<
 // voice prompt, embedding variant: the tensors moshi_lm_personaplex_load_voice reads from a voice file ("voice.embeddings"
 // as n_rows x dim f32, "voice.cache" as the token ring [CT][n_q+1] row-major; the file stores it transposed, lm.h:1047-1051)
 MOSHI_API int moshi_lm_personaplex_voice_tensors(moshi_lm_gen_t *gen, const float *embeddings, int n_rows, const int32_t *cache, int cache_rows);
+// moshi.cpp:789-836: a voice file (.safetensors: "embeddings" [N, 1, 1, dim] float + "cache" [n_q+1, CT] I32; .gguf:
+// "voice.embeddings" / "voice.cache") -> the two tensors above.  -1 for an unknown extension or an unreadable file.
+MOSHI_API int moshi_lm_personaplex_load_voice(moshi_context_t *moshi, moshi_lm_gen_t *gen, const char *filepath);
 // the reference tokenises `prompt` with sentencepiece (moshi.cpp:838-849); without a tokenizer the caller passes ids
 MOSHI_API int moshi_lm_personaplex_system_prompt_tokens(moshi_lm_gen_t *gen, const std::vector<int> &text_tokens);
 MOSHI_API void moshi_lm_start(moshi_context_t *moshi, moshi_lm_gen_t *gen, float depth_temperature, float text_temperature, bool logging = false);

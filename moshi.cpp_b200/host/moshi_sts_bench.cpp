@@ -1,7 +1,7 @@
 // moshi_sts_bench.cpp — the `--bench` entry point of the reference's speech-to-speech tools
 // (tools/moshi-sts.cpp:731-808, tools/personaplex.cpp) reduced to the LM path: the Mimi encoder/decoder and
 // SDL/FFmpeg I/O are out of scope, so user audio codes are synthetic (seeded LCG) instead of encoded silence.
-//   moshi-sts-bench <model.gguf> <config.json> [frames=125] [device=0] [--print-tokens] [-q q8_0|q4_k] [-g out.gguf] [--voice v.safetensors]
+//   moshi-sts-bench <model.gguf> <config.json> [frames=125] [device=0] [--print-tokens] [-q q8_0|q4_k] [-g out.gguf] [--voice v.safetensors] [--pplex-voice v.safetensors|v.gguf]
 // -q quantises an unquantised (f32 / f16 / bf16) GGUF while loading, -g writes the quantised weights as a GGUF and exits
 // (tools/moshi-sts.cpp `-q`, `-g`: moshi_lm_quantize, moshi_lm_save_gguf).
 // For a TTS model (model_type "tts": no user stream, cross-attention conditioning) it runs the moshi-tts --bench loop
@@ -21,12 +21,13 @@ int main(int argc, char **argv) {
     if (argc < 3) { fprintf(stderr, "usage: %s model.gguf config.json [frames] [device] [--print-tokens]\n", argv[0]); return 2; }
     int frames = 125, device = 0, positional = 0;
     bool print_tokens = false;
-    const char *quant = nullptr, *save_path = nullptr, *voice_path = nullptr;
+    const char *quant = nullptr, *save_path = nullptr, *voice_path = nullptr, *pplex_voice = nullptr;
     for (int i = 3; i < argc; i++) {
         if (!strcmp(argv[i], "--print-tokens")) print_tokens = true;
         else if (!strcmp(argv[i], "-q") && i + 1 < argc) quant = argv[++i];
         else if (!strcmp(argv[i], "-g") && i + 1 < argc) save_path = argv[++i];
         else if (!strcmp(argv[i], "--voice") && i + 1 < argc) voice_path = argv[++i];
+        else if (!strcmp(argv[i], "--pplex-voice") && i + 1 < argc) pplex_voice = argv[++i];
         else if (argv[i][0] != '-') { (positional == 0 ? frames : device) = atoi(argv[i]); positional++; }
     }
 
@@ -79,6 +80,9 @@ int main(int argc, char **argv) {
     if (config.model_type == "personaplex") {
         std::deque<std::vector<int16_t>> voice;                      // 4 frames of synthetic voice-prompt codes
         for (int f = 0; f < 4; f++) { std::vector<int16_t> c(8); for (int j = 0; j < 8; j++) c[j] = (int16_t)((f * 131 + j * 17) % config.card); voice.push_back(c); }
+        if (pplex_voice) {           // personaplex.cpp: a pre-computed voice (prompt embeddings + token ring) instead of prompt audio
+            if (moshi_lm_personaplex_load_voice(moshi, gen, pplex_voice) != 0) { fprintf(stderr, "error: could not load voice %s\n", pplex_voice); return 1; }
+        } else
         moshi_lm_personaplex_audio_prompt(gen, voice);
         moshi_lm_personaplex_system_prompt_tokens(gen, {5, 17, 99, 250});
     }

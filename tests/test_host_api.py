@@ -48,6 +48,62 @@ def test_tool_error_paths(tool, gguf_for, tmp_path):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("container", ["safetensors", "gguf"])
+def test_personaplex_voice_file(tool, gguf_for, tmp_path, container):
+    """moshi_lm_personaplex_load_voice (moshi.cpp:789-836): prompt embeddings [N,1,1,dim] + the token ring stored
+    [codebook][time] (lm.h:1005-1051) from a .safetensors / .gguf voice file == the same tensors fed through the C ABI."""
+    from moshi_cpp_b200 import synth
+    path, cfg = gguf_for("tiny_pplex", "q4_k")
+    cj = tmp_path / "config.json"; write_config(cj, cfg)
+    rng = np.random.default_rng(12)
+    ncb, dim = cfg["n_q"] + 1, cfg["dim"]
+    CT = max(cfg["delays"]) + 3                                   # max_delay + 2, + 1 for PersonaPlex (lm.h:715-743)
+    emb = (0.3 * rng.standard_normal((5, dim))).astype(np.float32)
+    ring = rng.integers(0, cfg["card"], size=(CT, ncb)).astype(np.int32)
+    ring[:, 0] = rng.integers(0, cfg["text_card"], size=CT)
+    if container == "safetensors":
+        vp = str(tmp_path / "voice.safetensors")
+        bits = ((emb.view(np.uint32) + 0x7FFF + ((emb.view(np.uint32) >> 16) & 1)) >> 16).astype(np.uint16)
+        emb = (bits.astype(np.uint32) << 16).view(np.float32)     # the file carries bf16 embeddings
+        synth.write_safetensors(vp, [("embeddings", "BF16", [5, 1, 1, dim], bits.tobytes()),
+                                     ("cache", "I32", [1, ncb, CT], np.ascontiguousarray(ring.T).tobytes())])
+    else:
+        vp = str(tmp_path / "voice.gguf")
+        import gguf
+        w = gguf.GGUFWriter(vp, "voice")
+        w.add_tensor("voice.embeddings", emb.reshape(5, 1, 1, dim))
+        w.add_tensor("voice.cache", np.ascontiguousarray(ring.T).reshape(1, ncb, CT))
+        w.write_header_to_file(); w.write_kv_data_to_file(); w.write_tensors_to_file(); w.close()
+    frames = 30
+    r = subprocess.run([tool, path, str(cj), str(frames), "0", "--print-tokens", "--pplex-voice", vp], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    lines = [l.split() for l in r.stdout.strip().splitlines()]
+    assert len(lines) == frames
+    gs = msx.Stream(msx.Model(path, cfg)); gg = msx.Gen(gs)
+    for row_ in emb:
+        gg.prompt_embedding(row_)
+    gg.set_cache(ring)
+    def row(text=None):
+        t = list(PROMPT_TOKENS)
+        if text is not None: t[0] = text
+        return t
+    for _ in range(6): gg.step(row())
+    for tok in (5, 17, 99, 250): gg.step(row(text=tok))
+    for _ in range(6): gg.step(row())
+    users = lcg_user_codes(frames, cfg["n_q"] - 8, cfg["card"])
+    n_ok = 0
+    for f in range(frames):
+        ok, text, audio = gg.step(users[f])
+        assert int(lines[f][1]) == ok, f"frame {f}"
+        if ok:
+            n_ok += 1
+            assert int(lines[f][2]) == text and [int(v) for v in lines[f][3:]] == list(audio), f"frame {f}"
+    assert n_ok > 20
+    bad = subprocess.run([tool, path, str(cj), "4", "0", "--pplex-voice", str(tmp_path / "voice.pt")], capture_output=True, text=True)
+    assert bad.returncode == 1 and "could not load voice" in bad.stderr     # unknown extension -> -1 (moshi.cpp:808-810)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("quant", ["q4_k", "q8_0"])
 def test_tool_quantize_and_save_gguf(tool, tmp_path, quant):
     """`moshi-sts -q <quant> -g out.gguf` then running the saved file == `-q <quant>` on the unquantised file
