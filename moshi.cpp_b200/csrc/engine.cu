@@ -681,6 +681,25 @@ struct Launcher {
         check();
     }
 
+    // n GEMVs of one shape over the same input in one launch (lean store epilogue)
+    void gemv_multi(const GemvArgs &a, const GemvMulti &mm, int n, int family) {
+        fam = family; begin();
+        const int smem = gemv_smem_bytes(a.w.type, a.w.K);
+        const dim3 grid(n * mm.per), block(kGemvThreads);
+        if (a.w.type == T_Q4_K) {
+            if (a.w.gs == 32) launch_pdl(gemv_multi_kernel<12, 32>, grid, block, smem, a, mm, (int)PRO_PLAIN, (int)EPI_STORE);
+            else launch_pdl(gemv_multi_kernel<12, 16>, grid, block, smem, a, mm, (int)PRO_PLAIN, (int)EPI_STORE);
+        } else {
+            if (a.w.gs == 32) launch_pdl(gemv_multi_kernel<8, 32>, grid, block, smem, a, mm, (int)PRO_PLAIN, (int)EPI_STORE);
+            else launch_pdl(gemv_multi_kernel<8, 16>, grid, block, smem, a, mm, (int)PRO_PLAIN, (int)EPI_STORE);
+        }
+        check();
+    }
+    int gemv_ctas(const QLinear &w) const {
+        const int tr = tile_rows(w.gs);
+        return std::max(1, std::min(num_sms, ((w.rows + tr - 1) / tr + 7) / 8));
+    }
+
     // fused local attention + out_proj (tiny rings)
     void gemv_local_attn(const GemvArgs &g, const AttnArgs &a, int heads, int dh, int pro, int epi, int family = 0) {
         fam = family; begin();
@@ -793,6 +812,7 @@ struct msx_stream {
     float *demux_l = nullptr, *demux_r = nullptr, *demux_y1 = nullptr, *demux_y2 = nullptr;   // [dim]
     float *embed_in = nullptr;       // [dim] voice-embedding prompt row (msx_step_temporal_embedding)
     float *dep_e = nullptr;          // [dep_dim] embedding of the previous token after its low-rank / demux projection
+    float *dep_d = nullptr;          // [dep_q][dep_dim] depformer_in[k] . t_out of every step, computed by one launch up front
     // tensor parallelism: double partial sums of out_proj / linear_out, all-reduced with NCCL inside the graph
     double *tp_partial = nullptr;    // [dim]
     void *nccl_comm = nullptr;
@@ -979,12 +999,26 @@ void enqueue_temporal(Launcher &L, const msx_stream *s) {
 
 void enqueue_depformer(Launcher &L, const msx_stream *s) {
     const msx_model *m = s->m; const msx_config &c = m->cfg;
+    auto weights_of = [&](int k) { const int wsel = c.schedule_len ? c.schedule[k] : k; return m->dep_nw == 1 ? 0 : wsel; };   // lm.h:457-462, transformer.h:74-83
+    // depformer_in[w_k](transformer_out) does not depend on the codebook chain: all dep_q of them in ONE launch up front
+    // (same kernel body, same arithmetic); the steps then only add the previous token's embedding (lm.h:464-467, 494-516)
+    const bool hoist = c.dep_q <= kGemvMultiMax;
+    if (hoist) {
+        GemvMulti mm;
+        for (int k = 0; k < c.dep_q; k++) {
+            const QLinear &w = m->dep_in[weights_of(k)];
+            mm.qs[k] = w.qs; mm.sc[k] = w.sc; mm.dd[k] = w.dd; mm.out[k] = s->dep_d + (size_t)k * c.dep_dim;
+        }
+        GemvArgs g;
+        g.ctrl = s->ctrl; g.eps = 1e-8f; g.w = m->dep_in[weights_of(0)]; g.x = s->tout; g.out = s->dep_d;
+        mm.per = L.gemv_ctas(g.w);
+        L.gemv_multi(g, mm, c.dep_q, FAM_DEP_IN);
+    }
     for (int k = 0; k < c.dep_q; k++) {
-        const int wsel = c.schedule_len ? c.schedule[k] : k;            // lm.h:457-462
-        const int w = m->dep_nw == 1 ? 0 : wsel;                        // transformer.h:74-83
+        const int w = weights_of(k);
+        const float *dk = s->dep_d + (size_t)k * c.dep_dim;
         GemvArgs g;
         g.ctrl = s->ctrl; g.eps = 1e-8f;
-        // depformer_in[w](transformer_out) + embedding of the previous token (lm.h:464-467, 494-516)
         g.w = m->dep_in[w]; g.x = s->tout; g.out = s->dx;
         if (m->dep_small) {
             // previous token's embedding through its low-rank / demux projection first (lm_utils.h:42-66, 155-168, 209-217)
@@ -994,15 +1028,24 @@ void enqueue_depformer(Launcher &L, const msx_stream *s) {
                 sl.table = m->dep_text_emb; sl.w = m->dep_text_out1; sl.mode = 2;
                 L.small_linear(sl, FAM_DEP_IN);
                 sl.w = m->dep_text_out2; sl.mode = 3;
+                if (hoist) { sl.addvec = dk; sl.dst = s->dx; }
                 L.small_linear(sl, FAM_DEP_IN);
             } else {
                 sl.table = k == 0 ? m->dep_text_emb : m->dep_emb[k - 1];
                 sl.w = k == 0 ? m->dep_text_lr : m->dep_emb_lr[k - 1];
                 sl.mode = k == 0 ? 0 : 1;
+                if (hoist) { sl.addvec = dk; sl.dst = s->dx; }
                 L.small_linear(sl, FAM_DEP_IN);
             }
-            g.addvec = s->dep_e;
-            L.gemv(g, PRO_PLAIN, EPI_ADD_VEC, FAM_DEP_IN);
+            if (!hoist) {
+                g.addvec = s->dep_e;
+                L.gemv(g, PRO_PLAIN, EPI_ADD_VEC, FAM_DEP_IN);
+            }
+        } else if (hoist) {
+            L.fam = FAM_DEP_IN; L.begin();
+            L.launch_pdl(dep_embed_add_kernel, dim3((c.dep_dim + 255) / 256), dim3(256), 0, (const Ctrl *)s->ctrl, dk,
+                         k == 0 ? m->dep_text_emb : m->dep_emb[k - 1], k, s->dx, (int)c.dep_dim);
+            L.check();
         } else {
             g.emb = k == 0 ? m->dep_text_emb : m->dep_emb[k - 1];
             g.emb_step = k;
@@ -1117,6 +1160,10 @@ int capture(msx_stream *s, F &&body, cudaGraphExec_t *exec, int *launches) {
 int set_smem_attrs() {
     const int big = 220 * 1024;   // dynamic part; the kernels also have a little static shared memory
     CU(cudaFuncSetAttribute(gemv_kernel<12, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU(cudaFuncSetAttribute(gemv_multi_kernel<12, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU(cudaFuncSetAttribute(gemv_multi_kernel<12, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU(cudaFuncSetAttribute(gemv_multi_kernel<8, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU(cudaFuncSetAttribute(gemv_multi_kernel<8, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CU(cudaFuncSetAttribute(gemv_kernel<12, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CU(cudaFuncSetAttribute(gemv_kernel<8, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CU(cudaFuncSetAttribute(gemv_kernel<8, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
@@ -1243,6 +1290,7 @@ static int stream_create_impl(msx_model *m, int context_override, int flags, con
     }
     if (m->dep_small)
         if (int e = salloc(s.get(), (void **)&s->dep_e, (size_t)c.dep_dim * 4)) return e;
+        if (int e = salloc(s.get(), (void **)&s->dep_d, (size_t)c.dep_q * c.dep_dim * 4)) return e;
     s->noise_floats = kSampleMaxK * (1 + MSX_MAX_STEPS);
     if (int e = salloc(s.get(), (void **)&s->d_noise, (size_t)s->noise_floats * 4)) return e;
     if (int e = salloc(s.get(), (void **)&s->d_probs, (size_t)std::max(c.text_card, c.card) * 4)) return e;

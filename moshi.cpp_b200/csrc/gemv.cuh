@@ -583,4 +583,24 @@ __global__ void __launch_bounds__(kGemvThreads, 1) gemv_kernel(const GemvArgs a,
     gemv_body<WT, LANES, true, TPPUSH, LEAN>(a, nullptr, blockIdx.x == 0, pro, epi, smem, blockIdx.x, gridDim.x, BlockGeom{kGemvThreads, kGemvThreads / 32});
 }
 
+// Several GEMVs of one shape over the SAME input in one launch (the depformer_in[k] . t_out of all codebook steps, which
+// do not depend on the serial chain): CTA blockIdx.x works on matrix blockIdx.x / per as CTA blockIdx.x % per of `per`.
+constexpr int kGemvMultiMax = 40;
+struct GemvMulti {
+    const uint8_t *qs[kGemvMultiMax];
+    const uint32_t *sc[kGemvMultiMax];
+    const void *dd[kGemvMultiMax];
+    float *out[kGemvMultiMax];
+    int32_t per = 1;
+};
+template <int WT, int LANES>
+__global__ void __launch_bounds__(kGemvThreads, 1) gemv_multi_kernel(const GemvArgs a, const __grid_constant__ GemvMulti m, const int pro, const int epi) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    griddep_launch();
+    const int mat = blockIdx.x / m.per, cta = blockIdx.x - mat * m.per;
+    GemvArgs b = a;
+    b.w.qs = m.qs[mat]; b.w.sc = m.sc[mat]; b.w.dd = m.dd[mat]; b.out = m.out[mat];
+    gemv_body<WT, LANES, true, false, true>(b, nullptr, false, pro, epi, smem, cta, m.per, BlockGeom{kGemvThreads, kGemvThreads / 32});
+}
+
 }  // namespace msx

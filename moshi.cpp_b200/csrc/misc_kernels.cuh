@@ -1,6 +1,7 @@
 // misc_kernels.cuh — embedding sum, frame bookkeeping, load-time repack and test-only dequant kernels.
 #pragma once
 #include "common.cuh"
+#include "gemv.cuh"
 
 namespace msx {
 
@@ -143,6 +144,22 @@ __global__ void __launch_bounds__(1024) tp_apply_p2p_kernel(float *x, const TpCt
     for (int j = 0; j < kTpApplyPer; j++) {
         const int i = threadIdx.x + j * blockDim.x;
         if (i < dim) x[i] = __ldcg(x + i) + (float)s[j];
+    }
+}
+
+// ---- depformer step input: depformer_in[k] . t_out (hoisted, `d`) + embedding of the previous token (lm.h:464-467, 494-516;
+// the EPI_ADD_EMB epilogue as a kernel of its own: -1 -> zeros and other negatives -> row 0 for the text table)
+__global__ void __launch_bounds__(256) dep_embed_add_kernel(const Ctrl *ctrl, const float *d, const EmbTable emb, const int step, float *out, const int n) {
+    griddep_launch();
+    griddep_wait();
+    const int token = depformer_prev_token(ctrl, step);
+    for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < n; row += gridDim.x * blockDim.x) {
+        float e;
+        if (step == 0) {
+            e = emb_element(emb, token < 0 ? 0 : token, row);
+            e = e * (token == -1 ? 0.f : 1.f);
+        } else e = emb_element(emb, token, row);
+        out[row] = __ldcg(d + row) + e;
     }
 }
 

@@ -160,6 +160,8 @@ struct SmallLinearArgs {
     const Ctrl *ctrl = nullptr;
     int32_t step = 0, mode = 0, num_embeddings = 0;
     float *out = nullptr;
+    const float *addvec = nullptr;   // non-null: the result (after mode 3's accumulate) + addvec goes to dst
+    float *dst = nullptr;
 };
 constexpr int kSmallThreads = 256;
 constexpr int kSmallMaxK = 2048;
@@ -215,8 +217,9 @@ __global__ void __launch_bounds__(kSmallThreads) small_linear_kernel(const Small
         acc = fma((double)__fmul_rn(dw, dx[b]), (double)sumi, acc);
     }
     const float y = (float)acc;
-    if (a.mode == 3) a.out[row] = __fadd_rn(a.out[row], __fmul_rn(y, out_scale));
-    else a.out[row] = y;
+    const float r = a.mode == 3 ? __fadd_rn(a.out[row], __fmul_rn(y, out_scale)) : y;
+    if (a.addvec) a.dst[row] = __fadd_rn(__ldcg(a.addvec + row), r);
+    else a.out[row] = r;
 }
 
 // ---- voice conditioners (one-off per voice; src/moshi.cpp:296-366 voice_condition) --------------------------------
