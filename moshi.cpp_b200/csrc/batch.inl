@@ -575,7 +575,7 @@ extern "C" int msx_test_gemm_batch(int device, int type, const void *w, int64_t 
                                    float *y) {
     if (!w || !x || !y || nb < 1 || nb > kMmaCols) return fail(MSX_ERR_ARG, "bad argument");
     std::unique_ptr<msx_model> m;
-    if (int e = test_setup(device, m)) return e;
+    if (int e = device_setup(device, m)) return e;
     CU(cudaFuncSetAttribute(gemm_q4k_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemMax));
     QLinear ql;
     if (int e = upload_linear(m.get(), w, type, k, rows, 0, &ql)) return e;
@@ -619,7 +619,7 @@ extern "C" int msx_bench_gemm_batch_ex(int device, const void *w, int64_t k, int
                                        int with_quant, float *avg_us, long long *stamps_out) {
     if (!w || !avg_us || n_mats < 1 || iters < 1 || nb < 1 || nb > kMmaCols) return fail(MSX_ERR_ARG, "bad argument");
     std::unique_ptr<msx_model> m;
-    if (int e = test_setup(device, m)) return e;
+    if (int e = device_setup(device, m)) return e;
     CU(cudaFuncSetAttribute(gemm_q4k_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemMax));
     std::vector<QTiles> mats(n_mats);
     for (int i = 0; i < n_mats; i++) {

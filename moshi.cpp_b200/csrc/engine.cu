@@ -2084,7 +2084,7 @@ extern "C" int msx_gen_step(msx_gen *g, const int32_t *in_tokens, int n_in, int 
 // unit-level test entry points
 // -------------------------------------------------------------------------------------------------
 namespace {
-int test_setup(int device, std::unique_ptr<msx_model> &m) {
+int device_setup(int device, std::unique_ptr<msx_model> &m) {
     int ndev = 0;
     CU(cudaGetDeviceCount(&ndev));
     if (device < 0 || device >= ndev) return fail(MSX_ERR_CUDA, "no such CUDA device");
@@ -2101,7 +2101,7 @@ int test_setup(int device, std::unique_ptr<msx_model> &m) {
 extern "C" int msx_test_gemv(int device, int type, const void *w, int64_t k, int64_t rows, const float *x, const float *alpha, int prologue, float *y) {
     if (!w || !x || !y) return fail(MSX_ERR_ARG, "null argument");
     std::unique_ptr<msx_model> m;
-    if (int e = test_setup(device, m)) return e;
+    if (int e = device_setup(device, m)) return e;
     QLinear ql;
     if (int e = upload_linear(m.get(), w, type, k, rows, 0, &ql)) return e;
     float *dx = nullptr, *dy = nullptr, *da = nullptr;
@@ -2130,7 +2130,7 @@ extern "C" int msx_bench_gemv(int device, int type, const void *w, int64_t k, in
                               int prologue, int epilogue, float *avg_us) {
     if (!w || !avg_us || n_mats < 1 || iters < 1) return fail(MSX_ERR_ARG, "bad argument");
     std::unique_ptr<msx_model> m;
-    if (int e = test_setup(device, m)) return e;
+    if (int e = device_setup(device, m)) return e;
     std::vector<QLinear> mats(n_mats);
     for (int i = 0; i < n_mats; i++)
         if (int e = upload_linear(m.get(), w, type, k, rows, epilogue == EPI_GATE ? (int)(rows / 2) : 0, &mats[i])) return e;
@@ -2183,7 +2183,7 @@ extern "C" int msx_bench_gemv(int device, int type, const void *w, int64_t k, in
 extern "C" int msx_test_dequant_rows(int device, int type, const void *table, int64_t k, int64_t table_rows, const int32_t *row_ids, int n_rows, float *out) {
     if (!table || !row_ids || !out) return fail(MSX_ERR_ARG, "null argument");
     std::unique_ptr<msx_model> m;
-    if (int e = test_setup(device, m)) return e;
+    if (int e = device_setup(device, m)) return e;
     EmbTable t;
     if (int e = upload_table(m.get(), table, type, k, table_rows, &t)) return e;
     int32_t *ids = nullptr; float *o = nullptr;
@@ -2200,7 +2200,7 @@ extern "C" int msx_test_dequant_rows(int device, int type, const void *table, in
 extern "C" int msx_test_dequant_repacked(int device, int type, const void *w, int64_t k, int64_t rows, float *out) {
     if (!w || !out) return fail(MSX_ERR_ARG, "null argument");
     std::unique_ptr<msx_model> m;
-    if (int e = test_setup(device, m)) return e;
+    if (int e = device_setup(device, m)) return e;
     QLinear ql;
     if (int e = upload_linear(m.get(), w, type, k, rows, 0, &ql)) return e;
     float *o = nullptr;
@@ -2217,7 +2217,7 @@ extern "C" int msx_test_quantize_rows(int device, int src_type, int dst_type, co
     if (!x || !out) return fail(MSX_ERR_ARG, "null argument");
     if (!is_float_type(src_type)) return fail(MSX_ERR_ARG, "source must be f32 / f16 / bf16");
     std::unique_ptr<msx_model> m;
-    if (int e = test_setup(device, m)) return e;
+    if (int e = device_setup(device, m)) return e;
     const size_t raw = (size_t)ggml_row_size(src_type, k) * rows;
     if (int e = ensure_staging(m.get(), raw)) return e;
     CU(cudaMemcpy(m->staging, x, raw, cudaMemcpyHostToDevice));
@@ -2342,7 +2342,7 @@ extern "C" int msx_gguf_quantize(const char *in_path, const char *out_path, int 
         return fail(io ? MSX_ERR_IO : MSX_ERR_FORMAT, err);
     }
     std::unique_ptr<msx_model> m;
-    if (int e = test_setup(device, m)) return e;
+    if (int e = device_setup(device, m)) return e;
     std::vector<OutTensor> ts;
     for (const GgufTensor &g : f.tensors()) {
         if (!g.data) return fail(MSX_ERR_FORMAT, "tensor " + g.name + " has unsupported type " + std::to_string(g.type));
@@ -2373,7 +2373,7 @@ extern "C" int msx_safetensors_to_gguf(const char *in_path, const char *out_path
         return fail(io ? MSX_ERR_IO : MSX_ERR_FORMAT, err);
     }
     std::unique_ptr<msx_model> m;
-    if (int e = test_setup(device, m)) return e;
+    if (int e = device_setup(device, m)) return e;
     std::vector<OutTensor> ts;
     for (const SafeTensor &st : f.tensors()) {
         const int type = st.dtype == "F32" ? T_F32 : st.dtype == "F16" ? T_F16 : st.dtype == "BF16" ? T_BF16 : -1;
