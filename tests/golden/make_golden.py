@@ -56,3 +56,22 @@ np.savez_compressed(os.path.join(HERE, "golden.npz"), **arrays)
 with open(os.path.join(HERE, "golden.json"), "w") as f:
     json.dump(meta, f)
 print("wrote", {k: v.shape for k, v in arrays.items()})
+
+# ---- quantisers (second file, so the vectors above never move): gguf-py's Q4_0 / Q8_0 blocks are reference outputs
+# (ggml's own python implementation); the Q4_K blocks and the voice-conditioner tensors are the oracle's, pinned as a
+# regression (gguf-py has no Q4_K quantiser and the reference ships no voice fixtures)
+from gguf.quants import quantize  # noqa: E402
+rq = np.random.default_rng(2027)
+xq = (rq.standard_normal((6, 512)) * 0.05).astype(np.float32)
+xq[0, :32] = 0.0; xq[1] = np.abs(xq[1]); xq[2, 256:] *= 40.0; xq[3, ::2] = xq[3, 1::2]
+qa = {"x": xq,
+      "q4_0": np.ascontiguousarray(quantize(xq, QT.Q4_0)).view(np.uint8).reshape(6, -1),
+      "q8_0": np.ascontiguousarray(quantize(xq, QT.Q8_0)).view(np.uint8).reshape(6, -1),
+      "q4_k_oracle": np.stack([oracle.quantize_q4_K(r) for r in xq])}
+vcfg = configs.get("tiny_tts_voice")
+vpath = synth.cached_gguf("tiny_tts_voice", "q4_k")
+wav = rq.standard_normal((synth.COND_CHANNELS, 3)).astype(np.float32)
+vs, vc = oracle.voice_condition(vpath, vcfg, wav)
+qa["voice_wavs"] = wav; qa["voice_sum_oracle"] = vs; qa["voice_cross_oracle"] = vc
+np.savez_compressed(os.path.join(HERE, "golden_quant.npz"), **qa)
+print("wrote", {k: v.shape for k, v in qa.items()})
