@@ -236,6 +236,24 @@ def test_two_rank_gloo_plumbing(tmp_path):
     assert "OK 20.0 5" in out.stdout
 
 
+def test_bench_reference_arm_contract_under_torchrun():
+    """`bench.py --impl reference` launched like the driver launches it for N > 1: rank 0 alone times the CPU path and prints
+    ONE JSON line on stdout (nothing else reaches stdout), the other rank exits 0 without work."""
+    import json
+    env = dict(os.environ, OMP_NUM_THREADS="2")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29543", os.path.join(ROOT, "bench.py"),
+                          "--impl", "reference", "--preset", "tiny", "--gpus", "2", "--steps", "3", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=300, env=env, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, out.stdout[:500]
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["value"] > 0 and d["unit"] == "frames/s"
+    assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+    assert set(("metric", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config")) <= set(d)
+
+
 @pytest.mark.parametrize("preset", ["moshi7b", "personaplex7b", "tiny", "stt1b"])
 @pytest.mark.parametrize("world", [1, 2, 4, 8])
 def test_tensor_parallel_shards_tile_the_model(preset, world):
