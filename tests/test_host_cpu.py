@@ -44,6 +44,17 @@ def test_no_cpu_fallback(gguf_for):
     with pytest.raises(msx.MsxError) as e:                      # the quantisers too: no host implementation behind them
         msx.test_quantize_rows(synth.GGML_Q4_K, np.zeros((1, 256), np.float32))
     assert e.value.code == -4
+    # file converters: a well-formed input parses (no -3) and then stops at the missing device (-4), no host quantiser
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        st = os.path.join(d, "m.safetensors")
+        synth.write_safetensors(st, [("text_emb.weight", "F32", [3, 32], np.zeros((3, 32), np.float32).tobytes()),
+                                     ("out_norm.alpha", "BF16", [1, 1, 32], np.zeros(32, np.uint16).tobytes())])
+        for fn, src in ((msx.safetensors_to_gguf, st), (msx.gguf_quantize, path)):
+            with pytest.raises(msx.MsxError) as e:
+                fn(src, os.path.join(d, "out.gguf"), "q8_0")
+            assert e.value.code == -4
+            assert not os.path.exists(os.path.join(d, "out.gguf"))
 
 
 def test_loader_errors_before_device(gguf_for, tmp_path):
