@@ -84,6 +84,7 @@ MSX_API int msx_stream_create(msx_model *m, int context_override, msx_stream **o
  * kernel with grid barriers (164 launches / 7B frame instead of 420).  Results are bit-identical; on B200 the
  * default PDL-chained launches are currently faster, so this stays opt-in (cross-check + research path). */
 #define MSX_STREAM_PERSISTENT_DEPFORMER 1
+#define MSX_STREAM_LAUNCH_CHAIN 2          /* PDL-chained launches instead of the persistent step kernel (cross-check path) */
 MSX_API int msx_stream_create_ex(msx_model *m, int context_override, int flags, msx_stream **out);
 MSX_API void msx_stream_free(msx_stream *s);
 MSX_API int msx_stream_reset(msx_stream *s);   /* offset = 0, KV rings zeroed */

@@ -238,7 +238,9 @@ class Model:
 
 
 class Stream:
-    def __init__(self, model: Model, context: int = 0, persistent_depformer: bool = False, nccl_id: bytes | None = None):
+    def __init__(self, model: Model, context: int = 0, persistent_depformer: bool = False, nccl_id: bytes | None = None,
+                 launch_chain: bool = False):
+        """launch_chain: PDL-chained launches (one kernel per linear / attention) instead of the persistent step kernel"""
         self.model = model
         h = C.c_void_p()
         if nccl_id is not None:
@@ -246,7 +248,7 @@ class Stream:
             assert idb.size == 128
             _check(lib().msx_stream_create_tp(model.h, context, _p(idb), C.byref(h)))
         else:
-            _check(lib().msx_stream_create_ex(model.h, context, 1 if persistent_depformer else 0, C.byref(h)))
+            _check(lib().msx_stream_create_ex(model.h, context, (1 if persistent_depformer else 0) | (2 if launch_chain else 0), C.byref(h)))
         self.h = h
 
     @property

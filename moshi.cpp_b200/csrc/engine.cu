@@ -24,6 +24,7 @@
 #include "mma_gemm.cuh"
 #include "safetensors_file.h"
 #include "sample.cuh"
+#include "step_kernel.cuh"
 #include "tts_kernels.cuh"
 
 using namespace msx;
@@ -126,6 +127,12 @@ struct msx_model {
     bool has_conditioners = false;
     std::vector<void *> allocs;
     std::unordered_map<const void *, QTiles> tiles;   // MMA unit layout of a linear, keyed by its qs plane (batch.inl)
+    // stream layout of a linear for the persistent step kernel (step_kernel.cuh), keyed by its qs plane
+    struct StreamW { const uint8_t *p = nullptr; int gran = 1; };
+    std::unordered_map<const void *, StreamW> wstream;
+    bool stream_ok = true;            // every linear of the decode step has a stream-layout copy of one weight type
+    int stream_type = 0;
+    QLinear dep_in_all;               // depformer_in[w_k] of all dep_q steps as ONE matrix [dep_q * dep_dim][dim] (stream layout only)
     int64_t weight_bytes_per_frame = 0;
     int64_t device_bytes = 0;
     uint8_t *staging = nullptr;
@@ -187,7 +194,22 @@ int quantize_staging(msx_model *m, int src_type, int dst_type, int64_t K, int64_
 bool is_float_type(int t) { return t == T_F32 || t == T_F16 || t == T_BF16; }
 
 // Upload a GGUF tensor [rows][K] and repack it into device tiles. perm_half: see repack kernels.
-int upload_linear(msx_model *m, const void *host, int type, int64_t K, int64_t rows, int perm_half, QLinear *out) {
+// Raw GGUF blocks (device) -> stream layout of the persistent step kernel
+int upload_stream(msx_model *m, const uint8_t *d_blocks, int type, int64_t K, int64_t rows, int perm_half, const void *key) {
+    const size_t qbytes = (size_t)ggml_row_size(type, K) * rows;
+    void *ws = nullptr;
+    if (int e = dev_alloc(m, &ws, qbytes)) return e;
+    const long long n = (long long)rows * (K / 256);
+    const int gran = perm_half > 0 ? 2 : 1;
+    sk::repack_stream_kernel<<<(unsigned)((n + 255) / 256), 256>>>(d_blocks, (uint8_t *)ws, type, (int)rows, (int)K, gran, m->num_sms, perm_half);
+    CU(cudaGetLastError());
+    m->wstream[key] = msx_model::StreamW{(const uint8_t *)ws, gran};
+    m->stream_type = type;
+    return 0;
+}
+
+// blocks_copy: optional device buffer that receives the (quantised) GGUF blocks of this matrix as they are
+int upload_linear(msx_model *m, const void *host, int type, int64_t K, int64_t rows, int perm_half, QLinear *out, uint8_t *blocks_copy = nullptr) {
     const bool on_load = m->quantize && is_float_type(type);
     if (type != T_Q4_K && type != T_Q8_0 && !on_load)
         return fail(MSX_ERR_FORMAT, std::string("linear weights must be q4_k or q8_0, got ") + ggml_type_name(type));
@@ -218,8 +240,13 @@ int upload_linear(msx_model *m, const void *host, int type, int64_t K, int64_t r
         repack_q8_0_kernel<<<(unsigned)((n + 255) / 256), 256>>>(src_blocks, (uint8_t *)qs, (uint16_t *)dd, (int)rows, (int)K, w.gs, perm_half);
     }
     CU(cudaGetLastError());
-    CU(cudaDeviceSynchronize());
     w.qs = (const uint8_t *)qs; w.sc = (const uint32_t *)sc; w.dd = dd;
+    // second copy in the stream layout of the persistent step kernel: CTA spans of 32-row x super-block units, GGUF bytes exactly
+    if (m->tp_world == 1 && K % 256 == 0 && rows % (perm_half > 0 ? 2 : 1) == 0 && (m->stream_type == 0 || m->stream_type == type)) {
+        if (int e = upload_stream(m, src_blocks, type, K, rows, perm_half, w.qs)) return e;
+    } else m->stream_ok = false;
+    if (blocks_copy) CU(cudaMemcpyAsync(blocks_copy, src_blocks, (size_t)ggml_row_size(type, K) * rows, cudaMemcpyDeviceToDevice, 0));
+    CU(cudaDeviceSynchronize());
     *out = w;
     return 0;
 }
@@ -260,14 +287,14 @@ struct Loader {
         if (!t->data) { fail(MSX_ERR_FORMAT, "tensor " + name + " has unsupported type " + std::to_string(t->type)); return nullptr; }
         return t;
     }
-    int linear(const std::string &name, int64_t K, int64_t rows, QLinear *out, int perm_half = 0) {
+    int linear(const std::string &name, int64_t K, int64_t rows, QLinear *out, int perm_half = 0, uint8_t *blocks_copy = nullptr) {
         const GgufTensor *t = need(name);
         if (!t) return MSX_ERR_FORMAT;
         if ((K > 0 && t->ne[0] != K) || (rows > 0 && t->ne[1] != rows))
             return fail(MSX_ERR_FORMAT, "shape mismatch for " + name + ": got [" + std::to_string(t->ne[0]) + "," +
                                             std::to_string(t->ne[1]) + "], want [" + std::to_string(K) + "," + std::to_string(rows) + "]");
         linear_bytes = (m->quantize && is_float_type(t->type)) ? t->ne[1] * ggml_row_size(m->quantize, t->ne[0]) : t->nbytes;
-        return upload_linear(m, t->data, t->type, t->ne[0], t->ne[1], perm_half, out);
+        return upload_linear(m, t->data, t->type, t->ne[0], t->ne[1], perm_half, out, blocks_copy);
     }
     // tensor-parallel shard of a linear: the listed row ranges (concatenated) x the K-slice [k0, k1) of every row
     int linear_slice(const std::string &name, int64_t K, int64_t rows, const std::vector<std::pair<int64_t, int64_t>> &ranges,
@@ -468,10 +495,33 @@ extern "C" int msx_model_load_gguf_ex(const char *path, const msx_config *cfg, i
         m->dep_cap = c.dep_context ? c.dep_context : c.schedule_len;
         m->dep_in.resize(nw);
         std::vector<int64_t> dep_in_bytes(nw), layer_bytes(nw, 0);
+        // the GGUF blocks of every depformer_in are kept on the device until the per-step concatenation below
+        const GgufTensor *dep_in0 = f.find("lm.depformer_in.0.weight");
+        const int dep_in_type = !dep_in0 ? 0 : (m->quantize && is_float_type(dep_in0->type)) ? m->quantize : dep_in0->type;
+        const int64_t dep_in_rs = ggml_row_size(dep_in_type, d);
+        uint8_t *cat_w = nullptr;
+        if (dep_in_rs > 0 && tp_world == 1) CU(cudaMalloc((void **)&cat_w, (size_t)nw * dd * dep_in_rs));
+        struct CatFree { uint8_t *p; ~CatFree() { if (p) cudaFree(p); } } cat_free{cat_w};
         for (int k = 0; k < nw; k++) {
-            if (int e = L.linear("lm.depformer_in." + std::to_string(k) + ".weight", d, dd, &m->dep_in[k])) return e;
+            if (int e = L.linear("lm.depformer_in." + std::to_string(k) + ".weight", d, dd, &m->dep_in[k], 0, cat_w ? cat_w + (size_t)k * dd * dep_in_rs : nullptr)) return e;
             dep_in_bytes[k] = L.linear_bytes;
+            if (m->dep_in[k].type != dep_in_type) m->stream_ok = false;
         }
+        if (cat_w && m->stream_ok && d % 256 == 0) {
+            // depformer_in[w_k] . t_out of ALL codebook steps does not depend on the chain: one matrix, one phase of the step kernel
+            uint8_t *cat_k = nullptr;
+            CU(cudaMalloc((void **)&cat_k, (size_t)c.dep_q * dd * dep_in_rs));
+            CatFree cat_k_free{cat_k};
+            for (int k = 0; k < c.dep_q; k++) {
+                const int wsel = c.schedule_len ? c.schedule[k] : k, w = nw == 1 ? 0 : wsel;
+                CU(cudaMemcpy(cat_k + (size_t)k * dd * dep_in_rs, cat_w + (size_t)w * dd * dep_in_rs, (size_t)dd * dep_in_rs, cudaMemcpyDeviceToDevice));
+            }
+            m->dep_in_all = m->dep_in[0];
+            m->dep_in_all.rows = c.dep_q * dd;
+            m->dep_in_all.qs = reinterpret_cast<const uint8_t *>(&m->dep_in_all);      // key only: this matrix exists in stream layout alone
+            if (int e = upload_stream(m.get(), cat_k, dep_in_type, d, (int64_t)c.dep_q * dd, 0, m->dep_in_all.qs)) return e;
+            CU(cudaDeviceSynchronize());
+        } else m->stream_ok = false;
         // low-rank / demux depformer embeddings: table rows are [lr] wide and go through a small projection
         // (lm_utils.h:126-217; lm_default.h:196-214)
         const int de = c.dep_low_rank ? c.dep_low_rank : dd;
@@ -591,13 +641,13 @@ namespace {
 enum Family : int {
     FAM_EMBED = 0, FAM_IN_PROJ, FAM_ATTN, FAM_OUT_PROJ, FAM_LIN_IN, FAM_LIN_OUT, FAM_TEXT_HEAD, FAM_FINALIZE,
     FAM_DEP_IN, FAM_DEP_IN_PROJ, FAM_DEP_ATTN, FAM_DEP_OUT_PROJ, FAM_DEP_LIN_IN, FAM_DEP_LIN_OUT, FAM_DEP_HEAD, FAM_DEP_FINALIZE,
-    FAM_DEP_MEGA,
+    FAM_DEP_MEGA, FAM_STEP_TEMPORAL, FAM_STEP_DEPFORMER,
     FAM_COUNT
 };
 const char *kFamilyNames[FAM_COUNT] = {
     "embed", "in_proj", "attn", "out_proj", "linear_in", "linear_out", "text_head", "finalize",
     "dep_in", "dep_in_proj", "dep_attn", "dep_out_proj", "dep_linear_in", "dep_linear_out", "dep_head", "dep_finalize",
-    "depformer_persistent"};
+    "depformer_persistent", "step_temporal", "step_depformer"};
 
 int tiles_of(msx_model *m, const QLinear &w, QTiles *out);     // batch.inl
 int ensure_all_tiles(msx_model *m);
@@ -791,6 +841,11 @@ int attn_split_for(int heads, int cap, int num_sms) {
 // stream
 // -------------------------------------------------------------------------------------------------
 static void free_prefill(struct msx_batch *b);
+struct StepBuffers {      // LL vectors of the persistent step kernel (step_kernel.cuh), one set per stream
+    sk::LL *xA = nullptr, *xB = nullptr, *qkv = nullptr, *ctx = nullptr, *gate = nullptr, *tkeys = nullptr;
+    sk::LL *xmax = nullptr, *xsum = nullptr, *xpart = nullptr;
+    sk::LL *dep_d = nullptr, *dxA = nullptr, *dxB = nullptr, *dqkv = nullptr, *dctx = nullptr, *dgate = nullptr, *dkeys = nullptr;
+};
 struct msx_stream {
     msx_model *m = nullptr;
     int cap = 0;
@@ -834,6 +889,12 @@ struct msx_stream {
     float *d_noise = nullptr, *h_noise = nullptr, *d_probs = nullptr;
     int noise_floats = 0;
     bool noise_fresh = false;
+    // persistent step kernel (step_kernel.cuh): phase programs of the two stacks, LL vectors, launch counter
+    StepBuffers step_buf;
+    sk::StepPhase *d_prog_t = nullptr, *d_prog_d = nullptr;
+    int n_prog_t = 0, n_prog_d = 0;
+    uint32_t *d_epoch = nullptr;
+    bool step_kernel = false;        // the graphs hold one cooperative step_kernel launch each
     // persistent phase-program kernel (megakernel.cuh)
     int flags = 0;
     Phase *d_dep_prog = nullptr;
@@ -1184,6 +1245,8 @@ int set_smem_attrs() {
     CU(cudaFuncSetAttribute(gemv_local_attn_kernel<8, 16, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CU(cudaFuncSetAttribute(gemv_local_attn_kernel<8, 16, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CU(cudaFuncSetAttribute(mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU(cudaFuncSetAttribute(sk::step_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, sk::kSmemBytes));
+    CU(cudaFuncSetAttribute(sk::step_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, sk::kSmemBytes));
     CU(cudaFuncSetAttribute(gemm1_q4k_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemMax));
     // all kernels stay below the 48 KB default except long-context attention with split 1
     CU(cudaFuncSetAttribute(attn_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
@@ -1194,6 +1257,8 @@ int set_smem_attrs() {
 }
 
 }  // namespace
+
+#include "step_program.inl"
 
 static int build_graphs(msx_stream *sp);
 
@@ -1316,6 +1381,21 @@ static int build_graphs(msx_stream *sp) {
     const int flags = sp->flags;
     if (sp->g_temporal) { cudaGraphExecDestroy(sp->g_temporal); sp->g_temporal = nullptr; }
     if (sp->g_depformer) { cudaGraphExecDestroy(sp->g_depformer); sp->g_depformer = nullptr; }
+    // default: each stack of the frame is ONE persistent kernel (step_kernel.cuh); models it does not take run as PDL-chained launches
+    sp->step_kernel = false;
+    if (step_kernel_eligible(sp)) {
+        int per_sm = 0;
+        const void *fn = m->stream_type == T_Q4_K ? (const void *)sk::step_kernel<12> : (const void *)sk::step_kernel<8>;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, sk::kThreads, sk::kSmemBytes));
+        if (per_sm >= 1) {
+            if (!sp->d_prog_t) if (int e = build_step_programs(sp)) return e;
+            if (int e = capture(s.get(), [&](Launcher &L) { enqueue_step_kernel(L, s.get(), true); }, &s->g_temporal, &s->launches_temporal)) return e;
+            if (c.dep_q > 0)
+                if (int e = capture(s.get(), [&](Launcher &L) { enqueue_step_kernel(L, s.get(), false); }, &s->g_depformer, &s->launches_depformer)) return e;
+            sp->step_kernel = true;
+            return 0;
+        }
+    }
     if (int e = capture(s.get(), [&](Launcher &L) { enqueue_temporal(L, s.get()); }, &s->g_temporal, &s->launches_temporal)) return e;
     if (c.dep_q > 0) {
         // persistent phase-program kernel for the depformer chain: opt-in (measured slower than PDL-chained launches on B200)
@@ -1717,9 +1797,12 @@ extern "C" int msx_profile_frame(msx_stream *s, const int32_t *tokens, int32_t *
     Launcher L{s->st, s->m->num_sms};
     L.model = s->m; L.mma = s->use_mma;
     L.events = &ev; L.families = &fam;
-    enqueue_temporal(L, s);
-    s->host_offset++;
-    if (c.dep_q > 0) { if (s->mega_depformer) enqueue_depformer_mega(L, s); else enqueue_depformer(L, s); }
+    if (s->step_kernel) { enqueue_step_kernel(L, s, true); s->host_offset++; if (c.dep_q > 0) enqueue_step_kernel(L, s, false); }
+    else {
+        enqueue_temporal(L, s);
+        s->host_offset++;
+        if (c.dep_q > 0) { if (s->mega_depformer) enqueue_depformer_mega(L, s); else enqueue_depformer(L, s); }
+    }
     if (L.err != cudaSuccess) return fail(MSX_ERR_CUDA, std::string("launch failed: ") + cudaGetErrorString(L.err));
     if (int e = pull_outputs(s)) return e;
     if (out_tokens) for (int k = 0; k < 1 + c.dep_q; k++) out_tokens[k] = s->h_out[k];

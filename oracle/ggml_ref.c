@@ -21,9 +21,29 @@
 #include <string.h>
 #include <limits.h>
 
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
 #define QK_K 256
 #define QK8_0 32
 #define QK4_0 32
+
+/* host threads of the row-parallel loops: set explicitly by the benchmark's CPU legs (torchrun exports OMP_NUM_THREADS=1) */
+void orc_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+int orc_max_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
 
 /* ------------------------------------------------------------------------------------------------
  * scalar conversions (ggml-impl.h: ggml_compute_fp32_to_bf16, GGML_FP16_TO_FP32)

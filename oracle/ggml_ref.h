@@ -49,6 +49,9 @@ typedef struct orc_state orc_state;
 typedef struct orc_lmgen orc_lmgen;
 
 /* ---- T0: block formats ---------------------------------------------------------- */
+/* OpenMP threads used by the row-parallel loops (benchmark CPU legs set this explicitly) */
+void orc_set_threads(int n);
+int orc_max_threads(void);
 int64_t orc_row_size(int type, int64_t k);                       /* bytes of one row of k elements */
 void orc_dequantize_row(int type, const void *src, float *dst, int64_t k);
 void orc_quantize_row_q8_0(const float *x, void *dst, int64_t k);

@@ -39,6 +39,17 @@ def build(force: bool = False) -> str:
 _lib = None
 
 
+def set_threads(n: int) -> int:
+    """use n OpenMP threads from now on (torchrun exports OMP_NUM_THREADS=1, which would otherwise pin the CPU legs to one core);
+    returns the thread count the runtime reports afterwards"""
+    lib().orc_set_threads(int(n))
+    return int(lib().orc_max_threads())
+
+
+def max_threads() -> int:
+    return int(lib().orc_max_threads())
+
+
 def lib():
     global _lib
     if _lib is None:
@@ -48,6 +59,7 @@ def lib():
             _lib = C.CDLL(build(force=True))
         L = _lib
         vp, i32p, fp = C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_float)
+        L.orc_set_threads.argtypes = [C.c_int]; L.orc_max_threads.restype = C.c_int
         L.orc_row_size.restype = C.c_int64; L.orc_row_size.argtypes = [C.c_int, C.c_int64]
         L.orc_dequantize_row.argtypes = [C.c_int, vp, vp, C.c_int64]
         L.orc_quantize_row_q8_0.argtypes = [vp, vp, C.c_int64]
