@@ -80,11 +80,12 @@ MSX_API int msx_model_device(const msx_model *m);
 /* ---- per-conversation state: replaces StateContext + moshi_lmmodel_states (lm.h:423-444) ------
  * context_override > 0 shrinks the temporal ring capacity (tools' "-c N", moshi-sts.cpp:254-264). */
 MSX_API int msx_stream_create(msx_model *m, int context_override, msx_stream **out);
-/* flags: MSX_STREAM_PERSISTENT_DEPFORMER = run the whole depformer chain as ONE cooperative "phase program"
- * kernel with grid barriers (164 launches / 7B frame instead of 420).  Results are bit-identical; on B200 the
- * default PDL-chained launches are currently faster, so this stays opt-in (cross-check + research path). */
-#define MSX_STREAM_PERSISTENT_DEPFORMER 1
-#define MSX_STREAM_LAUNCH_CHAIN 2          /* PDL-chained launches instead of the persistent step kernel (cross-check path) */
+/* flags: MSX_STREAM_STEP_KERNEL = run each stack of the frame (temporal transformer + text head; depformer chain) as ONE
+ * persistent cooperative kernel (csrc/step_kernel.cuh: TMA weight ring across phases, flag-in-data activation exchange) instead
+ * of PDL-chained launches: 2 launches per frame instead of 373.  Results are bit-identical.  Opt-in: on B200 the launch chain
+ * is currently ~15 % faster per frame (profiles/r2_step_kernel.md); models the kernel does not take (cross-attention, tensor
+ * parallel, temperature sampling, mixed weight types) silently use the launch chain. */
+#define MSX_STREAM_STEP_KERNEL 1
 MSX_API int msx_stream_create_ex(msx_model *m, int context_override, int flags, msx_stream **out);
 MSX_API void msx_stream_free(msx_stream *s);
 MSX_API int msx_stream_reset(msx_stream *s);   /* offset = 0, KV rings zeroed */
@@ -191,9 +192,8 @@ MSX_API int msx_profile_frame(msx_stream *s, const int32_t *tokens, int32_t *out
 /* CUDA-event stopwatch on the stream's own CUDA stream: start .. stop spans everything enqueued between them */
 MSX_API int msx_timer_start(msx_stream *s);
 MSX_API int msx_timer_stop(msx_stream *s, float *elapsed_ms);
-MSX_API int msx_debug_barrier_timeline(msx_stream *s, int n, long long *stamps, int mode);
-MSX_API int msx_debug_repeat_phase(msx_stream *s, int index, int n, long long *stamps);
-MSX_API int msx_debug_depformer_timeline(msx_stream *s, int32_t text_token, long long *stamps, int max_phases, int *n_phases);
+/* one frame with the step kernels' in-kernel timeline: rows [n_phases][n_cta][9] = {family, start, end, after prologue, after main loop, input loaded, rms scale known, epilogue stored, -} ns */
+MSX_API int msx_step_timeline(msx_stream *s, const int32_t *tokens, long long *rows, int max_rows, int *n_phases, int *n_cta);
 MSX_API int msx_family_count(void);
 MSX_API const char *msx_family_name(int i);
 /* KV read-back for parity tests: bf16 bits of K and V for (layer, head, slot), Dh values each */

@@ -128,6 +128,7 @@ def lib():
     L.msx_run_resident_async.argtypes = [vp, vp, C.c_int, C.c_int]
     L.msx_stream_wait.argtypes = [vp, C.POINTER(C.c_float)]
     L.msx_profile_frame.argtypes = [vp, vp, vp, vp, vp, C.c_int]
+    L.msx_step_timeline.argtypes = [vp, vp, vp, C.c_int, vp, vp]
     L.msx_family_count.restype = C.c_int
     L.msx_timer_start.argtypes = [vp]
     L.msx_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
@@ -238,9 +239,8 @@ class Model:
 
 
 class Stream:
-    def __init__(self, model: Model, context: int = 0, persistent_depformer: bool = False, nccl_id: bytes | None = None,
-                 launch_chain: bool = False):
-        """launch_chain: PDL-chained launches (one kernel per linear / attention) instead of the persistent step kernel"""
+    def __init__(self, model: Model, context: int = 0, step_kernel: bool = False, nccl_id: bytes | None = None):
+        """step_kernel: one persistent cooperative kernel per stack (MSX_STREAM_STEP_KERNEL) instead of PDL-chained launches"""
         self.model = model
         h = C.c_void_p()
         if nccl_id is not None:
@@ -248,7 +248,7 @@ class Stream:
             assert idb.size == 128
             _check(lib().msx_stream_create_tp(model.h, context, _p(idb), C.byref(h)))
         else:
-            _check(lib().msx_stream_create_ex(model.h, context, (1 if persistent_depformer else 0) | (2 if launch_chain else 0), C.byref(h)))
+            _check(lib().msx_stream_create_ex(model.h, context, 1 if step_kernel else 0, C.byref(h)))
         self.h = h
 
     @property
@@ -364,6 +364,17 @@ class Stream:
         _check(lib().msx_profile_frame(self.h, _p(tok), _p(out), _p(ms), _p(cnt), n))
         fam = {lib().msx_family_name(i).decode(): (float(ms[i]), int(cnt[i])) for i in range(n) if cnt[i]}
         return out, fam
+
+    def step_timeline(self, tokens):
+        """one frame through the persistent step kernels -> (families [n_phases], stamps [n_phases][n_cta][8] ns =
+        start, end, after prologue, after main loop, input loaded, rms scale known, epilogue stored, -)"""
+        tok = np.ascontiguousarray(tokens, dtype=np.int32)
+        max_rows = 4096 * 160
+        rows = np.zeros((max_rows, 9), dtype=np.int64); n = C.c_int(0); nc = C.c_int(0)
+        _check(lib().msx_step_timeline(self.h, _p(tok), _p(rows), max_rows, C.byref(n), C.byref(nc)))
+        r = rows[: n.value * nc.value].reshape(n.value, nc.value, 9)
+        fams = [lib().msx_family_name(int(f)).decode() for f in r[:, 0, 0]]
+        return fams, r[:, :, 1:]
 
     def timer_start(self):
         _check(lib().msx_timer_start(self.h))

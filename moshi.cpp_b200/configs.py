@@ -53,6 +53,19 @@ PRESETS = {
         depformer_dim=256, depformer_num_heads=4, depformer_num_layers=2, depformer_context=8,
         depformer_max_period=0, dep_hidden=512, schedule=[], extra_heads=0, extra_heads_dim=0,
     ),
+    # depformer_weights_per_step_schedule (lm.h:457-462, transformer.h:74-83): 8 codebook steps share 4 weight sets in a
+    # non-identity order; depformer_in / in_projs / out_projs / gating pick schedule[k], linears / embeddings stay per step
+    "tiny_sched": dict(
+        name="tiny_sched", model_type="moshi",
+        dim=512, num_heads=4, num_layers=2, context=24, max_period=10000,
+        n_q=16, dep_q=8, card=256, text_card=1000, delays=_DELAYS_7B,
+        hidden=768,
+        depformer_dim=256, depformer_num_heads=4, depformer_num_layers=2, depformer_context=8,
+        depformer_max_period=0, dep_hidden=512, schedule=[0, 1, 2, 3, 3, 1, 0, 2], extra_heads=0, extra_heads_dim=0,
+    ),
+    # PersonaPlex shapes (dep_q 16), 2 temporal layers, ring of 1100 slots: fills in seconds on the CPU oracle and takes the
+    # long-ring attention path (> 1024 slots) at full 7B head / layer shapes
+    "pplex7b_l2_c1100": _derive(MOSHI_7B, name="pplex7b_l2_c1100", model_type="personaplex", dep_q=16, num_layers=2, context=1100),
     # STT-like: no depformer, 32 input codebooks, extra heads (VAD)
     "tiny_stt": dict(
         name="tiny_stt", model_type="stt",

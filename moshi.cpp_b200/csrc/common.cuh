@@ -32,14 +32,8 @@ struct Ctrl {
     int32_t pad1_[3];
     unsigned long long text_key;    // arg-max keys (see argmax_key())
     unsigned long long audio_key[40];
-    // ---- persistent-kernel grid barrier (megakernel.cuh) ----
-    unsigned long long bar_counter; // monotonic arrival counter (atomics only)
-    unsigned long long pad3_[15];   // keep counter and flag on different 128-byte lines
-    unsigned long long bar_flag;    // last completed barrier target: the only word waiters poll
-    unsigned long long pad4_[15];
-    unsigned long long bar_base;    // counter value at the start of the next launch
-    int32_t error;                  // set by the barrier watchdog
-    int32_t bar_mode;               // 0 = poll the flag word, 1 = poll the counter (measurement only)
+    int32_t error;                  // set by a device-side watchdog (step kernel waits, tensor-parallel inbox polls)
+    int32_t pad2_;
 };
 constexpr size_t kCtrlInOffset = 32;
 constexpr size_t kCtrlInBytes = 84 * 4;
@@ -135,6 +129,8 @@ __device__ __forceinline__ int uniform_warp_id() { return __shfl_sync(0xffffffff
 // (or overwrite its inputs) before griddep_wait().  griddep_launch() lets the NEXT kernel start early.
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+__device__ __forceinline__ long long global_ns() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 
 // ---- small device helpers -------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {

@@ -19,7 +19,7 @@
 #include "common.cuh"
 #include "gemv.cuh"
 #include "gguf_file.h"
-#include "megakernel.cuh"
+#include "local_attn.cuh"
 #include "misc_kernels.cuh"
 #include "mma_gemm.cuh"
 #include "safetensors_file.h"
@@ -641,13 +641,13 @@ namespace {
 enum Family : int {
     FAM_EMBED = 0, FAM_IN_PROJ, FAM_ATTN, FAM_OUT_PROJ, FAM_LIN_IN, FAM_LIN_OUT, FAM_TEXT_HEAD, FAM_FINALIZE,
     FAM_DEP_IN, FAM_DEP_IN_PROJ, FAM_DEP_ATTN, FAM_DEP_OUT_PROJ, FAM_DEP_LIN_IN, FAM_DEP_LIN_OUT, FAM_DEP_HEAD, FAM_DEP_FINALIZE,
-    FAM_DEP_MEGA, FAM_STEP_TEMPORAL, FAM_STEP_DEPFORMER,
+    FAM_STEP_TEMPORAL, FAM_STEP_DEPFORMER,
     FAM_COUNT
 };
 const char *kFamilyNames[FAM_COUNT] = {
     "embed", "in_proj", "attn", "out_proj", "linear_in", "linear_out", "text_head", "finalize",
     "dep_in", "dep_in_proj", "dep_attn", "dep_out_proj", "dep_linear_in", "dep_linear_out", "dep_head", "dep_finalize",
-    "depformer_persistent", "step_temporal", "step_depformer"};
+    "step_temporal", "step_depformer"};
 
 int tiles_of(msx_model *m, const QLinear &w, QTiles *out);     // batch.inl
 int ensure_all_tiles(msx_model *m);
@@ -843,7 +843,7 @@ int attn_split_for(int heads, int cap, int num_sms) {
 static void free_prefill(struct msx_batch *b);
 struct StepBuffers {      // LL vectors of the persistent step kernel (step_kernel.cuh), one set per stream
     sk::LL *xA = nullptr, *xB = nullptr, *qkv = nullptr, *ctx = nullptr, *gate = nullptr, *tkeys = nullptr;
-    sk::LL *xmax = nullptr, *xsum = nullptr, *xpart = nullptr;
+    sk::LL *scores = nullptr;
     sk::LL *dep_d = nullptr, *dxA = nullptr, *dxB = nullptr, *dqkv = nullptr, *dctx = nullptr, *dgate = nullptr, *dkeys = nullptr;
 };
 struct msx_stream {
@@ -893,14 +893,10 @@ struct msx_stream {
     StepBuffers step_buf;
     sk::StepPhase *d_prog_t = nullptr, *d_prog_d = nullptr;
     int n_prog_t = 0, n_prog_d = 0;
+    std::vector<int> prog_fam_t, prog_fam_d;   // kernel family of every phase (timeline)
     uint32_t *d_epoch = nullptr;
     bool step_kernel = false;        // the graphs hold one cooperative step_kernel launch each
-    // persistent phase-program kernel (megakernel.cuh)
     int flags = 0;
-    Phase *d_dep_prog = nullptr;
-    int n_dep_phases = 0;
-    int mega_smem = 0, mega_gemv_region = 0, mega_local_dim = 0;
-    bool mega_depformer = false;
     int host_offset = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<void *> allocs;
@@ -1133,74 +1129,6 @@ void enqueue_depformer(Launcher &L, const msx_stream *s) {
     L.check();
 }
 
-// ---- persistent-kernel program for the depformer chain -------------------------------------------------
-// dep_q x (depformer_in+emb | per layer: in_proj | local attention + out_proj | linear_in+gate | linear_out) | head),
-// then the token collection: 26 phases per codebook step instead of 32 launches.
-std::vector<Phase> build_depformer_program(const msx_stream *s, int *max_gemv_smem) {
-    const msx_model *m = s->m; const msx_config &c = m->cfg;
-    std::vector<Phase> prog;
-    int mx = 0;
-    auto gemv = [&](const GemvArgs &g, int pro, int epi) {
-        Phase ph; ph.type = PH_GEMV; ph.pro = pro; ph.epi = epi; ph.g = g;
-        mx = std::max(mx, gemv_smem_bytes(g.w.type, g.w.K));
-        prog.push_back(ph);
-    };
-    const int dd = c.dep_dim;
-    for (int k = 0; k < c.dep_q; k++) {
-        const int wsel = c.schedule_len ? c.schedule[k] : k;
-        const int w = m->dep_nw == 1 ? 0 : wsel;
-        GemvArgs g;
-        g.ctrl = s->ctrl; g.eps = 1e-8f;
-        g.w = m->dep_in[w]; g.x = s->tout; g.out = s->dx;
-        g.emb = k == 0 ? m->dep_text_emb : m->dep_emb[k - 1];
-        g.emb_step = k;
-        gemv(g, PRO_PLAIN, EPI_ADD_EMB);
-        for (int l = 0; l < c.dep_layers; l++) {
-            const LayerW &lw = m->dep_layers[l];
-            GemvArgs a1;
-            a1.ctrl = s->ctrl; a1.eps = 1e-8f;
-            a1.w = lw.in_proj[w]; a1.x = s->dx; a1.alpha = lw.norm1; a1.out = s->dqkv;
-            gemv(a1, PRO_RMS, EPI_STORE);
-            Phase ph;
-            ph.type = PH_GEMV_LOCAL_ATTN; ph.pro = PRO_PLAIN; ph.epi = EPI_RESID;
-            ph.heads = c.dep_heads; ph.dh = dd / c.dep_heads;
-            ph.a.qkv = s->dqkv; ph.a.ctx = nullptr; ph.a.ctrl = s->ctrl; ph.a.pos_const = k; ph.a.cap = m->dep_cap; ph.a.dim = dd;
-            ph.a.max_period = c.dep_max_period; ph.a.rope_freq = m->dep_rope_freq;
-            const size_t lstride = (size_t)m->dep_cap * dd;
-            ph.a.kc = s->dkc + (size_t)l * lstride; ph.a.vc = s->dvc + (size_t)l * lstride;
-            ph.g.ctrl = s->ctrl; ph.g.w = lw.out_proj[w]; ph.g.x = nullptr; ph.g.out = s->dx;
-            mx = std::max(mx, gemv_smem_bytes(ph.g.w.type, ph.g.w.K));
-            prog.push_back(ph);
-            GemvArgs a3;
-            a3.ctrl = s->ctrl; a3.eps = 1e-8f;
-            a3.w = lw.lin_in[w]; a3.x = s->dx; a3.alpha = lw.norm2; a3.out = s->dgate;
-            gemv(a3, PRO_RMS, EPI_GATE);
-            GemvArgs a4;
-            a4.ctrl = s->ctrl;
-            a4.w = lw.lin_out[w]; a4.x = s->dgate; a4.out = s->dx;
-            gemv(a4, PRO_PLAIN, EPI_RESID);
-        }
-        GemvArgs h;
-        h.ctrl = s->ctrl;
-        h.w = m->linears[k]; h.x = s->dx; h.out = s->audio_logits + (size_t)k * c.card; h.key = &s->ctrl->audio_key[k];
-        gemv(h, PRO_PLAIN, EPI_ARGMAX);
-    }
-    Phase fin; fin.type = PH_FINALIZE_DEPFORMER; fin.dep_q = c.dep_q;
-    prog.push_back(fin);
-    *max_gemv_smem = mx;
-    return prog;
-}
-
-void enqueue_depformer_mega(Launcher &L, const msx_stream *s) {
-    MegaArgs ma; ma.phases = s->d_dep_prog; ma.n_phases = s->n_dep_phases; ma.ctrl = s->ctrl;
-    int region = s->mega_gemv_region, ldim = s->mega_local_dim;
-    void *args[] = {(void *)&ma, (void *)&region, (void *)&ldim};
-    L.fam = FAM_DEP_MEGA; L.begin();
-    cudaError_t e = cudaLaunchCooperativeKernel((const void *)mega_kernel, dim3(s->m->num_sms), dim3(kMegaThreads), args, (size_t)s->mega_smem, L.st);
-    if (L.err == cudaSuccess) L.err = e;
-    L.check();
-}
-
 template <typename F>
 int capture(msx_stream *s, F &&body, cudaGraphExec_t *exec, int *launches) {
     Launcher L{s->st, s->m->num_sms};
@@ -1244,7 +1172,6 @@ int set_smem_attrs() {
     CU(cudaFuncSetAttribute(gemv_local_attn_kernel<8, 32, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CU(cudaFuncSetAttribute(gemv_local_attn_kernel<8, 16, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CU(cudaFuncSetAttribute(gemv_local_attn_kernel<8, 16, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    CU(cudaFuncSetAttribute(mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CU(cudaFuncSetAttribute(sk::step_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, sk::kSmemBytes));
     CU(cudaFuncSetAttribute(sk::step_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, sk::kSmemBytes));
     CU(cudaFuncSetAttribute(gemm1_q4k_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemMax));
@@ -1325,7 +1252,6 @@ static int stream_create_impl(msx_model *m, int context_override, int flags, con
         memcpy(id.internal, nccl_id, 128);
         const int rc = n.CommInitRank(&s->nccl_comm, m->tp_world, id, m->tp_rank);
         if (rc != 0) { s->nccl_comm = nullptr; return fail(MSX_ERR_CUDA, std::string("ncclCommInitRank: ") + n.GetErrorString(rc)); }
-        flags &= ~MSX_STREAM_PERSISTENT_DEPFORMER;
     }
     if (int e = salloc(s.get(), (void **)&s->tout, (size_t)c.dim * 4)) return e;
     if (int e = salloc(s.get(), (void **)&s->text_logits, (size_t)c.text_card * 4)) return e;
@@ -1378,10 +1304,10 @@ static int build_graphs(msx_stream *sp) {
     struct Holder { msx_stream *p; msx_stream *get() const { return p; } msx_stream *operator->() const { return p; } } s{sp};
     msx_model *m = sp->m;
     const msx_config &c = m->cfg;
-    const int flags = sp->flags;
     if (sp->g_temporal) { cudaGraphExecDestroy(sp->g_temporal); sp->g_temporal = nullptr; }
     if (sp->g_depformer) { cudaGraphExecDestroy(sp->g_depformer); sp->g_depformer = nullptr; }
-    // default: each stack of the frame is ONE persistent kernel (step_kernel.cuh); models it does not take run as PDL-chained launches
+    // MSX_STREAM_STEP_KERNEL: each stack of the frame is ONE persistent kernel (step_kernel.cuh); models it does not take, and
+    // every stream without the flag, run as PDL-chained launches (measured faster on B200: profiles/r2_step_kernel.md)
     sp->step_kernel = false;
     if (step_kernel_eligible(sp)) {
         int per_sm = 0;
@@ -1398,29 +1324,7 @@ static int build_graphs(msx_stream *sp) {
     }
     if (int e = capture(s.get(), [&](Launcher &L) { enqueue_temporal(L, s.get()); }, &s->g_temporal, &s->launches_temporal)) return e;
     if (c.dep_q > 0) {
-        // persistent phase-program kernel for the depformer chain: opt-in (measured slower than PDL-chained launches on B200)
-        const bool want_mega = (flags & MSX_STREAM_PERSISTENT_DEPFORMER) && m->dep_cap <= 64 && sp->temp_audio <= 0.f && !sp->d_dep_prog && !m->dep_small;
-        if (sp->temp_audio > 0.f) sp->mega_depformer = false;
-        if (want_mega) {
-            int mx = 0;
-            std::vector<Phase> prog = build_depformer_program(s.get(), &mx);
-            s->mega_gemv_region = (mx + 15) / 16 * 16;
-            s->mega_local_dim = c.dep_dim;
-            s->mega_smem = mega_smem_bytes(mx, c.dep_dim, c.dep_dim / c.dep_heads);
-            int per_sm = 0;
-            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mega_kernel, kMegaThreads, s->mega_smem));
-            if (per_sm >= 1) {
-                if (int e = salloc(s.get(), (void **)&s->d_dep_prog, prog.size() * sizeof(Phase))) return e;
-                CU(cudaMemcpy(s->d_dep_prog, prog.data(), prog.size() * sizeof(Phase), cudaMemcpyHostToDevice));
-                s->n_dep_phases = (int)prog.size();
-                s->mega_depformer = true;
-            }
-        }
-        if (s->mega_depformer) {
-            if (int e = capture(s.get(), [&](Launcher &L) { enqueue_depformer_mega(L, s.get()); }, &s->g_depformer, &s->launches_depformer)) return e;
-        } else {
-            if (int e = capture(s.get(), [&](Launcher &L) { enqueue_depformer(L, s.get()); }, &s->g_depformer, &s->launches_depformer)) return e;
-        }
+        if (int e = capture(s.get(), [&](Launcher &L) { enqueue_depformer(L, s.get()); }, &s->g_depformer, &s->launches_depformer)) return e;
     }
     return 0;
 }
@@ -1801,7 +1705,7 @@ extern "C" int msx_profile_frame(msx_stream *s, const int32_t *tokens, int32_t *
     else {
         enqueue_temporal(L, s);
         s->host_offset++;
-        if (c.dep_q > 0) { if (s->mega_depformer) enqueue_depformer_mega(L, s); else enqueue_depformer(L, s); }
+        if (c.dep_q > 0) enqueue_depformer(L, s);
     }
     if (L.err != cudaSuccess) return fail(MSX_ERR_CUDA, std::string("launch failed: ") + cudaGetErrorString(L.err));
     if (int e = pull_outputs(s)) return e;
@@ -1815,72 +1719,37 @@ extern "C" int msx_profile_frame(msx_stream *s, const int32_t *tokens, int32_t *
     for (cudaEvent_t e : ev) cudaEventDestroy(e);
     return 0;
 }
-// debug: pure grid-barrier cost — a program of n empty phases, timeline as below
-extern "C" int msx_debug_barrier_timeline(msx_stream *s, int n, long long *stamps, int mode) {
-    if (!s || !stamps || n < 2) return fail(MSX_ERR_ARG, "bad argument");
+// One frame through the step kernels with the in-kernel timeline enabled.  rows: [n_phases][n_cta][9] int64 =
+// {family, start, end, after prologue, after main loop, input loaded, rms scale known, epilogue stored, -} (globaltimer ns; 0 where
+// a phase has no such stage); temporal
+// phases first.  Returns the number of phases in *n_phases and the CTA count in *n_cta; rows must hold max_rows * 9 values.
+extern "C" int msx_step_timeline(msx_stream *s, const int32_t *tokens, long long *rows, int max_rows, int *n_phases, int *n_cta) {
+    if (!s || !tokens || !rows || !n_phases || !n_cta) return fail(MSX_ERR_ARG, "null argument");
+    if (!s->step_kernel) return fail(MSX_ERR_STATE, "stream does not run the persistent step kernel");
     CU(cudaSetDevice(s->m->device));
-    CU(cudaMemcpy(&s->ctrl->bar_mode, &mode, 4, cudaMemcpyHostToDevice));
-    std::vector<Phase> prog(n);
-    for (auto &ph : prog) ph.type = 99;
-    Phase *dp = nullptr; long long *d = nullptr;
-    CU(cudaMalloc((void **)&dp, n * sizeof(Phase)));
-    CU(cudaMemcpy(dp, prog.data(), n * sizeof(Phase), cudaMemcpyHostToDevice));
-    CU(cudaMalloc((void **)&d, (size_t)n * 8 * 8));
-    CU(cudaMemset(d, 0, (size_t)n * 8 * 8));
-    MegaArgs ma; ma.phases = dp; ma.n_phases = n; ma.ctrl = s->ctrl; ma.dbg = d;
-    int region = s->mega_gemv_region, ldim = s->mega_local_dim;
-    void *args[] = {(void *)&ma, (void *)&region, (void *)&ldim};
-    for (int rep = 0; rep < 2; rep++)
-        CU(cudaLaunchCooperativeKernel((const void *)mega_kernel, dim3(s->m->num_sms), dim3(kMegaThreads), args, (size_t)s->mega_smem, s->st));
-    CU(cudaStreamSynchronize(s->st));
-    CU(cudaMemcpy(stamps, d, (size_t)n * 8 * 8, cudaMemcpyDeviceToHost));
-    cudaFree(d); cudaFree(dp);
-    mode = 0;
-    CU(cudaMemcpy(&s->ctrl->bar_mode, &mode, 4, cudaMemcpyHostToDevice));
-    return 0;
-}
-
-// debug: a program made of n copies of phase `index` of the depformer program (steady-state cost of one phase type)
-extern "C" int msx_debug_repeat_phase(msx_stream *s, int index, int n, long long *stamps) {
-    if (!s || !stamps || n < 2 || !s->mega_depformer || index < 0 || index >= s->n_dep_phases) return fail(MSX_ERR_ARG, "bad argument");
-    CU(cudaSetDevice(s->m->device));
-    Phase one;
-    CU(cudaMemcpy(&one, s->d_dep_prog + index, sizeof(Phase), cudaMemcpyDeviceToHost));
-    std::vector<Phase> prog(n, one);
-    Phase *dp = nullptr; long long *d = nullptr;
-    CU(cudaMalloc((void **)&dp, n * sizeof(Phase)));
-    CU(cudaMemcpy(dp, prog.data(), n * sizeof(Phase), cudaMemcpyHostToDevice));
-    CU(cudaMalloc((void **)&d, (size_t)n * 8 * 8));
-    CU(cudaMemset(d, 0, (size_t)n * 8 * 8));
-    MegaArgs ma; ma.phases = dp; ma.n_phases = n; ma.ctrl = s->ctrl; ma.dbg = d;
-    int region = s->mega_gemv_region, ldim = s->mega_local_dim;
-    void *args[] = {(void *)&ma, (void *)&region, (void *)&ldim};
-    for (int rep = 0; rep < 2; rep++)
-        CU(cudaLaunchCooperativeKernel((const void *)mega_kernel, dim3(s->m->num_sms), dim3(kMegaThreads), args, (size_t)s->mega_smem, s->st));
-    CU(cudaStreamSynchronize(s->st));
-    CU(cudaMemcpy(stamps, d, (size_t)n * 8 * 8, cudaMemcpyDeviceToHost));
-    cudaFree(d); cudaFree(dp);
-    return 0;
-}
-
-// debug: run the persistent depformer kernel once with the in-kernel timeline enabled (5 stamps per phase, ns)
-extern "C" int msx_debug_depformer_timeline(msx_stream *s, int32_t text_token, long long *stamps, int max_phases, int *n_phases) {
-    if (!s || !stamps || !n_phases) return fail(MSX_ERR_ARG, "null argument");
-    if (!s->mega_depformer) return fail(MSX_ERR_STATE, "stream does not use the persistent depformer kernel");
-    CU(cudaSetDevice(s->m->device));
-    const int n = std::min(max_phases, s->n_dep_phases);
+    const int nt = s->n_prog_t, nd = s->n_prog_d, nc = s->m->num_sms;
+    if ((size_t)(nt + nd) * nc > (size_t)max_rows) return fail(MSX_ERR_ARG, "timeline buffer too small");
     long long *d = nullptr;
-    CU(cudaMalloc((void **)&d, (size_t)s->n_dep_phases * 8 * 8));
-    CU(cudaMemset(d, 0, (size_t)s->n_dep_phases * 8 * 8));
-    if (int e = push_inputs(s, nullptr, text_token, nullptr)) return e;
-    MegaArgs ma; ma.phases = s->d_dep_prog; ma.n_phases = s->n_dep_phases; ma.ctrl = s->ctrl; ma.dbg = d;
-    int region = s->mega_gemv_region, ldim = s->mega_local_dim;
-    void *args[] = {(void *)&ma, (void *)&region, (void *)&ldim};
-    CU(cudaLaunchCooperativeKernel((const void *)mega_kernel, dim3(s->m->num_sms), dim3(kMegaThreads), args, (size_t)s->mega_smem, s->st));
-    if (int e = pull_outputs(s)) return e;
-    CU(cudaMemcpy(stamps, d, (size_t)n * 8 * 8, cudaMemcpyDeviceToHost));
+    const size_t words = (size_t)(nt + nd) * nc * 8;
+    CU(cudaMalloc((void **)&d, words * 8));
+    CU(cudaMemset(d, 0, words * 8));
+    if (int e = push_inputs(s, tokens, INT32_MIN, nullptr)) { cudaFree(d); return e; }
+    Launcher L{s->st, s->m->num_sms};
+    enqueue_step_kernel(L, s, true, d);
+    s->host_offset++;
+    if (nd) enqueue_step_kernel(L, s, false, d + (size_t)nt * nc * 8);
+    if (L.err != cudaSuccess) { cudaFree(d); return fail(MSX_ERR_CUDA, std::string("launch failed: ") + cudaGetErrorString(L.err)); }
+    if (int e = pull_outputs(s)) { cudaFree(d); return e; }
+    std::vector<long long> h(words);
+    CU(cudaMemcpy(h.data(), d, words * 8, cudaMemcpyDeviceToHost));
     cudaFree(d);
-    *n_phases = n;
+    for (int i = 0; i < nt + nd; i++)
+        for (int c = 0; c < nc; c++) {
+            long long *r = rows + ((size_t)i * nc + c) * 9;
+            r[0] = i < nt ? s->prog_fam_t[i] : s->prog_fam_d[i - nt];
+            for (int j = 0; j < 8; j++) r[1 + j] = h[((size_t)i * nc + c) * 8 + j];
+        }
+    *n_phases = nt + nd; *n_cta = nc;
     return 0;
 }
 

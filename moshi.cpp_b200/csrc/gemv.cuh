@@ -28,11 +28,9 @@ __device__ __forceinline__ int dp4a_us(unsigned a, int b, int c) {
 }
 
 
-// The GEMV body runs either as a whole CTA (standalone kernels, 256 threads) or as the consumer part
-// of the persistent kernel's CTA (480 of 512 threads): geometry comes in at run time and block-level
-// synchronisation uses named barrier 1 over exactly the participating threads.
-struct BlockGeom { int nthr; int nwarps; long long *stamp = nullptr; };
-__device__ __forceinline__ long long global_ns() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+// Geometry of the GEMV body comes in at run time; block-level synchronisation uses named barrier 1 over exactly the
+// participating threads.
+struct BlockGeom { int nthr; int nwarps; };
 __device__ __forceinline__ void block_sync(const BlockGeom &bg) { asm volatile("bar.sync 1, %0;" ::"r"(bg.nthr) : "memory"); }
 
 // Activation vectors are produced by other CTAs (previous kernel, or previous phase of the persistent
@@ -268,7 +266,6 @@ __device__ __forceinline__ void gemv_prologue(const GemvArgs &a, const float *xi
             }
         }
     }
-    if (!LEAN && bg.stamp && threadIdx.x == 0) bg.stamp[7] = global_ns();
 }
 
 // ---- epilogue ------------------------------------------------------------------------------------
@@ -441,7 +438,7 @@ struct NoMid { __device__ __forceinline__ void operator()() const {} };
 template <int WT, int LANES, bool PDL = false, bool TPPUSH = false, bool LEAN = false, typename Mid = NoMid>
 __device__ __forceinline__ void gemv_body(const GemvArgs &a, const float *x_over, const bool norm_out_cta, const int PRO, const int EPI,
                                           uint8_t *smem, const int cta, const int n_cta, const BlockGeom bg,
-                                          unsigned long long *progress = nullptr, Mid mid = Mid()) {
+                                          Mid mid = Mid()) {
     const float *xin = x_over ? x_over : a.x;
     constexpr int TR = tile_rows(LANES);
     const int K = a.w.K;
@@ -484,7 +481,6 @@ __device__ __forceinline__ void gemv_body(const GemvArgs &a, const float *x_over
         gemv_prologue<8, 0, LEAN>(a, xin, norm_out_cta, PRO, K, x8, nullptr, dx, red, bg);
     }
     block_sync(bg);
-    if (!LEAN && bg.stamp && threadIdx.x == 0) bg.stamp[1] = global_ns();
 
     int emb_token = 0;
     if (!LEAN && EPI == EPI_ADD_EMB) emb_token = depformer_prev_token(a.ctrl, a.emb_step);
@@ -504,8 +500,6 @@ __device__ __forceinline__ void gemv_body(const GemvArgs &a, const float *x_over
             for (int r = 0; r < kR; r++) { const int row = cons.row0 + r; if (row < a.w.rows) resid[r] = __ldcg(a.out + row); }
         }
     };
-    const unsigned long long tile_bytes = WT == 12 ? (unsigned long long)TR * ((K >> 1) + P * 4 + (K >> 8) * 4)
-                                                   : (unsigned long long)TR * (K + P * 2);
     // end of a tile: reduce the lane partials, run the epilogue, reset
     auto finish_tile = [&]() {
         float accf[kR];
@@ -538,7 +532,6 @@ __device__ __forceinline__ void gemv_body(const GemvArgs &a, const float *x_over
                 }
             } else if (EPI != EPI_STORE_F64) gemv_epilogue<kR>(a, EPI, cons.row0, accf, emb_token, best);
         }
-        if (!LEAN && progress && lane == 0) atomicAdd(progress, tile_bytes);
     };
 #pragma unroll 1
     for (int s = 0; s < n_steps; s++) {
@@ -555,7 +548,6 @@ __device__ __forceinline__ void gemv_body(const GemvArgs &a, const float *x_over
         if (cons.it == nit - 1) finish_tile();
         advance<LANES>(cons, nit, row_stride);
     }
-    if (!LEAN && bg.stamp && threadIdx.x == 0) bg.stamp[2] = global_ns();
 
     if (!LEAN && EPI == EPI_ARGMAX) {
         // CTA-level max, then one atomic per CTA

@@ -10,7 +10,7 @@
 // around 2-8 us of HBM streaming.  Here a stack is a list of *phases* executed by 148 co-resident CTAs:
 //
 //   * one PRODUCER warp per CTA walks the whole phase list ahead of the consumers and streams this CTA's share of every
-//     weight matrix through a 9-slot (162 KB) shared-memory ring with cp.async.bulk (TMA) + mbarrier completion.  Weights
+//     weight matrix through a 8-slot (144 KB) shared-memory ring with cp.async.bulk (TMA) + mbarrier completion.  Weights
 //     do not depend on activations, so the HBM stream never stops at a phase boundary: while the consumers exchange
 //     activations the ring absorbs ~3.7 us worth of the next matrices.
 //   * 16 CONSUMER warps: lane = weight row, unit = (<= 32 rows) x (one 256-weight super-block), x broadcast from shared
@@ -35,7 +35,8 @@ constexpr int kConsumerWarps = 16;
 constexpr int kConsumers = kConsumerWarps * 32;      // 512
 constexpr int kThreads = kConsumers + 32;            // + one producer warp
 constexpr int kSlotBytes = 18432;                    // 4 Q4_K units (32 rows x 144 B) or 2 Q8_0 units (32 rows x 272 B)
-constexpr int kSlots = 9;
+constexpr int kSlots = 8;                            // a multiple of the consumer-group count (4 or 8): a slot is always drained by the
+                                                     // same warps, so no waiter can be more than one mbarrier phase away from its barrier
 constexpr int kMaxRowsCta = 224;                     // rows of one matrix owned by one CTA (text head: 32000 / 148 = 217)
 constexpr int kMaxK = 16384;
 constexpr int kMaxSplit = 8;                         // split-KV factor of the ring attention
@@ -63,6 +64,7 @@ enum PhaseType : int { PH_EMBED = 0, PH_GEMV = 1, PH_ATTN = 2, PH_DEP_EMBED = 3,
 // that wrote the vector, which fixes the sequence number a reader waits for.
 struct __align__(16) StepPhase {
     int32_t type = 0, pro = 0, epi = 0, gran = 1;
+    int32_t fam = 0, pad_[3] = {};    // kernel family of the phase (engine.cu Family), for the timeline only
     // ---- PH_GEMV ----
     const uint8_t *w = nullptr;       // matrix in stream layout (see repack_stream_kernel)
     int32_t K = 0, rows = 0;          // stored rows (gate / up rows interleaved for EPI_GATE)
@@ -81,7 +83,7 @@ struct __align__(16) StepPhase {
     uint16_t *kc = nullptr, *vc = nullptr;   // this layer's ring [H][cap][DH] bf16
     int32_t heads = 0, dh = 0, cap = 0, split = 1;
     int32_t pos_const = -1, max_period = 0;
-    LL *xmax = nullptr, *xsum = nullptr, *xpart = nullptr;   // split exchange: [H][S], [H][S][2], [H][S][DH][2]
+    LL *scores = nullptr;             // split exchange: the scores of every head [H][cap]
     // ---- PH_EMBED / PH_DEP_EMBED ----
     const EmbTable *tables = nullptr; // PH_EMBED: device array [n_tables]
     int32_t n_tables = 0, dim = 0;
@@ -99,7 +101,7 @@ struct StepArgs {
     const float *rope_freq = nullptr;
     Ctrl *ctrl = nullptr;
     uint32_t *epoch = nullptr;        // launch counter of the stream (device); CTA 0 advances it in its finalize phase
-    long long *dbg = nullptr;         // optional timeline: [n_phases][4] globaltimer stamps from CTA 0
+    long long *dbg = nullptr;         // optional timeline: [n_phases][n_cta][8] globaltimer ns = {start, end, after prologue, after main loop, input loaded, rms scale known, epilogue stored, -}
 };
 
 // ---- small PTX helpers -----------------------------------------------------------------------------------------------
@@ -194,6 +196,14 @@ __device__ __forceinline__ void ll_wait8(const LL *p, uint32_t seq, float (&v)[8
         }
     }
 }
+// one attempt at 8 consecutive entries (no waiting): all four loads are in flight together
+__device__ __forceinline__ bool ll_try8(const LL *p, uint32_t seq, float (&v)[8]) {
+    const ulonglong2 a = ll_ld2(p), b = ll_ld2(p + 2), c = ll_ld2(p + 4), d = ll_ld2(p + 6);
+    v[0] = __uint_as_float((uint32_t)a.x); v[1] = __uint_as_float((uint32_t)a.y); v[2] = __uint_as_float((uint32_t)b.x); v[3] = __uint_as_float((uint32_t)b.y);
+    v[4] = __uint_as_float((uint32_t)c.x); v[5] = __uint_as_float((uint32_t)c.y); v[6] = __uint_as_float((uint32_t)d.x); v[7] = __uint_as_float((uint32_t)d.y);
+    return (uint32_t)(a.x >> 32) == seq && (uint32_t)(a.y >> 32) == seq && (uint32_t)(b.x >> 32) == seq && (uint32_t)(b.y >> 32) == seq &&
+           (uint32_t)(c.x >> 32) == seq && (uint32_t)(c.y >> 32) == seq && (uint32_t)(d.x >> 32) == seq && (uint32_t)(d.y >> 32) == seq;
+}
 __device__ __forceinline__ void ll_store_f64(LL *p, double v, uint32_t seq) {
     const unsigned long long b = (unsigned long long)__double_as_longlong(v);
     ll_store_u32(p, (uint32_t)b, seq); ll_store_u32(p + 1, (uint32_t)(b >> 32), seq);
@@ -243,25 +253,67 @@ __host__ __device__ inline uint32_t unit_off(const Span &s, int u) {
 }
 
 // ---- producer warp ---------------------------------------------------------------------------------------------------
+// A slot holds kUnitsPerSlot units at fixed offsets (32 rows apart, whatever their height), so the consumers need no
+// address arithmetic beyond (tile, super-block); the producer issues one bulk copy per unit and one expect_tx per slot.
+//
+// (An L2 look-ahead — a second cursor issuing cp.async.bulk.prefetch.L2 16 chunks ahead of the loads — was measured and removed:
+// the main loops became 30-40 % slower, see profiles/r2_step_kernel.md.)
+template <int WT>
+struct ChunkCursor {
+    static constexpr int UPS = Fmt<WT>::kUnitsPerSlot, RB = Fmt<WT>::kRowBytes;
+    const StepArgs &a;
+    int p = -1, c = 0, tile = 0, sb = 0, u = 0;
+    Span s{};
+    const uint8_t *src = nullptr;
+    bool new_phase = false;
+    __device__ __forceinline__ explicit ChunkCursor(const StepArgs &a_) : a(a_) { s.n_chunks = 0; }
+    // moves to the next chunk; false at the end of the program.  After a true return: src / n_u / ub[] describe the chunk.
+    int n_u = 0;
+    uint32_t ub[UPS], bytes = 0;
+    __device__ __forceinline__ bool next() {
+        new_phase = false;
+        while (c >= s.n_chunks) {
+            if (++p >= a.n_phases) return false;
+            const StepPhase *ph = a.phases + p;
+            if (__ldg(&ph->type) != PH_GEMV) continue;
+            s = span_of<WT>(__ldg(&ph->K), __ldg(&ph->rows), __ldg(&ph->gran), (int)gridDim.x, (int)blockIdx.x);
+            src = reinterpret_cast<const uint8_t *>(__ldg(reinterpret_cast<const unsigned long long *>(&ph->w))) + s.base;
+            c = 0; tile = 0; sb = 0; u = 0; new_phase = true; bytes = 0;
+        }
+        src += bytes;                                            // past the previous chunk
+        n_u = min(UPS, s.n_units - u);
+        bytes = 0;
+#pragma unroll
+        for (int k = 0; k < UPS; k++) {
+            ub[k] = 0;
+            if (k < n_u) {
+                ub[k] = (uint32_t)min(32, s.n_rows - tile * 32) * RB;
+                bytes += ub[k];
+                if (++sb == s.nsb) { sb = 0; tile++; }
+            }
+        }
+        u += n_u; c++;
+        return true;
+    }
+};
 template <int WT>
 __device__ __forceinline__ void producer_loop(const StepArgs &a, uint8_t *smem, Watch &wd) {
-    const int cta = blockIdx.x, n_cta = gridDim.x;
+    constexpr int UPS = Fmt<WT>::kUnitsPerSlot, UB = 32 * Fmt<WT>::kRowBytes;
     const uint32_t ring = smem_u32(smem + kOffRing), bars = smem_u32(smem + kOffBars);
-    uint32_t q = 0;                                             // chunks issued so far (whole launch)
+    uint32_t slot = 0, lap = 0;                                 // position of the next chunk in the ring (whole launch)
     const unsigned long long pol = policy_evict_first();
-    for (int p = 0; p < a.n_phases; p++) {
-        const StepPhase *ph = a.phases + p;
-        if (__ldg(&ph->type) != PH_GEMV) continue;
-        const Span s = span_of<WT>(__ldg(&ph->K), __ldg(&ph->rows), __ldg(&ph->gran), n_cta, cta);
-        const uint8_t *src = reinterpret_cast<const uint8_t *>(__ldg(reinterpret_cast<const unsigned long long *>(&ph->w))) + s.base;
-        for (int c = 0; c < s.n_chunks; c++, q++) {
-            const uint32_t slot = q % kSlots, lap = q / kSlots;
-            mbar_wait(bars + (kSlots + slot) * 8, (lap & 1u) ^ 1u, wd);        // slot drained by its consumers
-            if (*wd.abort_flag) return;
-            const uint32_t o0 = unit_off<WT>(s, c * Fmt<WT>::kUnitsPerSlot), o1 = unit_off<WT>(s, (c + 1) * Fmt<WT>::kUnitsPerSlot);
-            mbar_expect_tx(bars + slot * 8, o1 - o0);
-            bulk_g2s(ring + slot * kSlotBytes, src + o0, o1 - o0, bars + slot * 8, pol);
+    ChunkCursor<WT> ld(a);
+    while (ld.next()) {
+        mbar_wait(bars + (kSlots + slot) * 8, (lap & 1u) ^ 1u, wd);            // slot drained by its consumers
+        if (*wd.abort_flag) return;
+        mbar_expect_tx(bars + slot * 8, ld.bytes);
+        const uint8_t *src = ld.src;
+#pragma unroll
+        for (int k = 0; k < UPS; k++) if (k < ld.n_u) {
+            bulk_g2s(ring + slot * kSlotBytes + k * UB, src, ld.ub[k], bars + slot * 8, pol);
+            src += ld.ub[k];
         }
+        if (++slot == kSlots) { slot = 0; lap++; }
     }
 }
 
@@ -317,7 +369,7 @@ __device__ __forceinline__ void quant_q8_0_block(int b, int lane, const float (&
 }
 
 template <int WT>
-__device__ __forceinline__ void gemv_prologue(const StepPhase &ph, uint32_t epoch_bits, uint8_t *smem, Watch &wd) {
+__device__ __forceinline__ void gemv_prologue(const StepPhase &ph, uint32_t epoch_bits, uint8_t *smem, Watch &wd, long long *stamp) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int K = ph.K, nblk = K >> 8;
     int8_t *x8 = reinterpret_cast<int8_t *>(smem + kOffX8);
@@ -325,66 +377,65 @@ __device__ __forceinline__ void gemv_prologue(const StepPhase &ph, uint32_t epoc
     float *dx = reinterpret_cast<float *>(smem + kOffDx);
     double *red = reinterpret_cast<double *>(smem + kOffRed);
     const uint32_t seq = epoch_bits | (uint32_t)(ph.x_src + 1);
-    constexpr int kKeep = 3;
+    constexpr int kKeep = 4;                                    // blocks of one warp kept in registers (K <= 16384)
     const int nb_w = warp < nblk ? (nblk - warp + kConsumerWarps - 1) / kConsumerWarps : 0;
-    const bool keep = nb_w <= kKeep;
+    // Warp w takes the blocks (w + 16 i + rot) mod nblk.  rot differs from CTA to CTA, so that the 148 CTAs — which all read the
+    // same vector at the same moment — start on different L2 lines instead of queueing on one slice after the other.
+    const int rot = (int)(blockIdx.x % (unsigned)nblk);
+    int blk[kKeep];
+#pragma unroll
+    for (int i = 0; i < kKeep; i++) { int b = warp + i * kConsumerWarps + rot; if (b >= nblk) b -= nblk; blk[i] = b; }
     float v[kKeep][8];
-    auto load = [&](int b, float (&o)[8]) {
-        const int e0 = b * 256 + lane * 8;
-        if (ph.x_ll) ll_wait8(ph.x_ll + e0, seq, o, wd);
-        else {
+    // the warp's blocks are requested together (one L2 round trip); a block whose producer has not stored yet is re-polled
+    if (ph.x_ll) {
+        bool ok[kKeep];
+#pragma unroll
+        for (int i = 0; i < kKeep; i++) ok[i] = i < nb_w ? ll_try8(ph.x_ll + blk[i] * 256 + lane * 8, seq, v[i]) : true;
+#pragma unroll
+        for (int i = 0; i < kKeep; i++) if (!ok[i]) ll_wait8(ph.x_ll + blk[i] * 256 + lane * 8, seq, v[i], wd);
+    } else {
+#pragma unroll
+        for (int i = 0; i < kKeep; i++) if (i < nb_w) {
+            const int e0 = blk[i] * 256 + lane * 8;
             const float4 p0 = __ldcg(reinterpret_cast<const float4 *>(ph.x_plain + e0)), p1 = __ldcg(reinterpret_cast<const float4 *>(ph.x_plain + e0 + 4));
-            o[0] = p0.x; o[1] = p0.y; o[2] = p0.z; o[3] = p0.w; o[4] = p1.x; o[5] = p1.y; o[6] = p1.z; o[7] = p1.w;
+            v[i][0] = p0.x; v[i][1] = p0.y; v[i][2] = p0.z; v[i][3] = p0.w; v[i][4] = p1.x; v[i][5] = p1.y; v[i][6] = p1.z; v[i][7] = p1.w;
         }
-    };
+    }
+    if (stamp && threadIdx.x == 0) stamp[4] = gtime_ns();
     float scale = 1.f;
     if (ph.pro == PRO_RMS) {
         double ss = 0.0;
-        for (int i = 0; i < nb_w; i++) {
-            float t[8];
-            load(warp + i * kConsumerWarps, t);
 #pragma unroll
-            for (int j = 0; j < 8; j++) ss += (double)(t[j] * t[j]);
-            if (keep) {
+        for (int i = 0; i < kKeep; i++) if (i < nb_w) {
 #pragma unroll
-                for (int kk = 0; kk < kKeep; kk++) if (kk == i) {
-#pragma unroll
-                    for (int j = 0; j < 8; j++) v[kk][j] = t[j];
-                }
-            }
+            for (int j = 0; j < 8; j++) ss += (double)(v[i][j] * v[i][j]);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
         if (lane == 0) red[warp] = ss;
         consumer_sync();
         double tot = 0.0;
-#pragma unroll 1
+#pragma unroll
         for (int w = 0; w < kConsumerWarps; w++) tot += red[w];
         const float mean = (K & (K - 1)) == 0 ? (float)scalbn(tot, -(31 - __clz(K))) : (float)(tot / K);
         scale = 1.0f / sqrtf(mean + ph.eps);
     }
-    for (int i = 0; i < nb_w; i++) {
-        const int b = warp + i * kConsumerWarps, e0 = b * 256 + lane * 8;
-        float t[8];
-        if (ph.pro == PRO_RMS && keep) {
+    if (stamp && threadIdx.x == 0) stamp[5] = gtime_ns();
 #pragma unroll
-            for (int kk = 0; kk < kKeep; kk++) if (kk == i) {
-#pragma unroll
-                for (int j = 0; j < 8; j++) t[j] = v[kk][j];
-            }
-        } else load(b, t);
+    for (int i = 0; i < kKeep; i++) if (i < nb_w) {
+        const int b = blk[i], e0 = b * 256 + lane * 8;
         if (ph.pro == PRO_RMS) {
             const float4 a0 = __ldg(reinterpret_cast<const float4 *>(ph.alpha + e0)), a1 = __ldg(reinterpret_cast<const float4 *>(ph.alpha + e0 + 4));
             const float al[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
 #pragma unroll
-            for (int j = 0; j < 8; j++) t[j] = __fmul_rn(al[j], __fmul_rn(t[j], scale));      // alpha * (x * scale)
+            for (int j = 0; j < 8; j++) v[i][j] = __fmul_rn(al[j], __fmul_rn(v[i][j], scale));      // alpha * (x * scale)
             if (ph.norm_out && blockIdx.x == 0) {
-                *reinterpret_cast<float4 *>(ph.norm_out + e0) = make_float4(t[0], t[1], t[2], t[3]);
-                *reinterpret_cast<float4 *>(ph.norm_out + e0 + 4) = make_float4(t[4], t[5], t[6], t[7]);
+                *reinterpret_cast<float4 *>(ph.norm_out + e0) = make_float4(v[i][0], v[i][1], v[i][2], v[i][3]);
+                *reinterpret_cast<float4 *>(ph.norm_out + e0 + 4) = make_float4(v[i][4], v[i][5], v[i][6], v[i][7]);
             }
         }
-        if (WT == 12) quant_q8k_block(b, lane, t, x8, bs, dx);
-        else quant_q8_0_block(b, lane, t, x8, dx);
+        if (WT == 12) quant_q8k_block(b, lane, v[i], x8, bs, dx);
+        else quant_q8_0_block(b, lane, v[i], x8, dx);
     }
 }
 
@@ -452,7 +503,7 @@ __device__ __forceinline__ double unit_q8_0(const uint8_t *ub, int th, int lane,
 
 // ---- GEMV phase (consumer side) ----------------------------------------------------------------------------------------
 template <int WT>
-__device__ __forceinline__ void gemv_phase(const StepPhase &ph, uint32_t epoch_bits, int p, uint32_t &q_base, uint8_t *smem, Watch &wd) {
+__device__ __forceinline__ void gemv_phase(const StepPhase &ph, uint32_t epoch_bits, int p, uint32_t &q_base, uint8_t *smem, Watch &wd, long long *stamp) {
     constexpr int UPS = Fmt<WT>::kUnitsPerSlot, NG = kConsumerWarps / UPS;
     const int cta = blockIdx.x, n_cta = gridDim.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, tid = threadIdx.x;
@@ -460,23 +511,27 @@ __device__ __forceinline__ void gemv_phase(const StepPhase &ph, uint32_t epoch_b
     const uint32_t seq_out = epoch_bits | (uint32_t)(p + 1);
     const uint32_t bars = smem_u32(smem + kOffBars);
     double *part = reinterpret_cast<double *>(smem + kOffPart);
+    // the old residual values of this CTA's rows were complete phases ago: request them now, use them in the epilogue
+    unsigned long long resid_raw = 0ull;
+    if (ph.epi == EPI_RESID && tid < s.n_rows) resid_raw = ll_ld1(ph.resid + s.r0 + tid);
     if (s.n_rows > 0) {
-        gemv_prologue<WT>(ph, epoch_bits, smem, wd);
+        gemv_prologue<WT>(ph, epoch_bits, smem, wd, stamp);
         consumer_sync();
+        if (stamp && tid == 0) stamp[2] = gtime_ns();
         const int8_t *x8 = reinterpret_cast<const int8_t *>(smem + kOffX8);
         const int16_t *bs = reinterpret_cast<const int16_t *>(smem + kOffBs);
         const float *dx = reinterpret_cast<const float *>(smem + kOffDx);
         // chunk c of this phase is global chunk q_base + c; it is consumed by warp group (q % NG): warp w takes unit w % UPS of it
         const int grp = warp / UPS, sub = warp % UPS;
         int c = (int)((grp + NG - (q_base % NG)) % NG);
+        uint32_t slot = (q_base + (uint32_t)c) % kSlots, lap = (q_base + (uint32_t)c) / kSlots;
+        int u = c * UPS + sub;
+        int tile = u / s.nsb, sb = u - tile * s.nsb;                         // advanced incrementally below (16 units per round)
         for (; c < s.n_chunks; c += NG) {
-            const uint32_t q = q_base + (uint32_t)c, slot = q % kSlots, lap = q / kSlots;
             mbar_wait(bars + slot * 8, lap & 1u, wd);
-            const int u = c * UPS + sub;
             if (u < s.n_units) {
-                const int tile = u / s.nsb, sb = u - tile * s.nsb;
                 const int th = min(32, s.n_rows - tile * 32);
-                const uint8_t *ub = smem + kOffRing + slot * kSlotBytes + (unit_off<WT>(s, u) - unit_off<WT>(s, c * UPS));
+                const uint8_t *ub = smem + kOffRing + slot * kSlotBytes + sub * (32 * Fmt<WT>::kRowBytes);
                 if (lane < th) {
                     double acc;
                     if (WT == 12) acc = unit_q4k(ub, th, lane, x8 + sb * 256, bs + sb * 8, dx[sb]);
@@ -487,8 +542,12 @@ __device__ __forceinline__ void gemv_phase(const StepPhase &ph, uint32_t epoch_b
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(bars + (kSlots + slot) * 8);
+            u += kConsumerWarps; sb += kConsumerWarps;
+            while (sb >= s.nsb) { sb -= s.nsb; tile++; }
+            slot += NG; if (slot >= kSlots) { slot -= kSlots; lap++; }
         }
         consumer_sync();
+        if (stamp && tid == 0) stamp[3] = gtime_ns();
     }
     q_base += (uint32_t)s.n_chunks;
 
@@ -509,7 +568,8 @@ __device__ __forceinline__ void gemv_phase(const StepPhase &ph, uint32_t epoch_b
             const int row = s.r0 + tid;
             const float v = total(tid);
             if (ph.epi == EPI_RESID) {
-                const float old = ll_wait1(ph.resid + row, epoch_bits | (uint32_t)(ph.resid_src + 1), wd);
+                const uint32_t rseq = epoch_bits | (uint32_t)(ph.resid_src + 1);
+                const float old = (uint32_t)(resid_raw >> 32) == rseq ? __uint_as_float((uint32_t)resid_raw) : ll_wait1(ph.resid + row, rseq, wd);
                 ll_store(ph.out + row, old + v, seq_out);
             } else if (ph.epi == EPI_ARGMAX) {
                 if (ph.out) ll_store(ph.out + row, v, seq_out);
@@ -518,6 +578,7 @@ __device__ __forceinline__ void gemv_phase(const StepPhase &ph, uint32_t epoch_b
             } else ll_store(ph.out + row, v, seq_out);
         }
     }
+    if (stamp && tid == 0) stamp[6] = gtime_ns();
     if (ph.epi == EPI_ARGMAX) {
         // CTA maximum -> this CTA's key entry (every CTA writes one, also those without rows: readers poll all of them)
         unsigned long long *sb = reinterpret_cast<unsigned long long *>(smem + kOffRed) + 16;
@@ -612,38 +673,79 @@ __device__ __forceinline__ void dep_embed_phase(const StepPhase &ph, const StepA
 }
 
 // ---- RoPE + ring insert + single-query attention over the bf16 ring (attention.cuh arithmetic) ------------------------------
-// CTA (h, c) = (cta / S, cta % S) handles split c of head h; max, sum and partial contexts of the S splits are exchanged
-// as LL words; split 0 writes the head's context.
+// CTA (h, c) = (cta / S, cta % S) of head h:  scores of slot range c  ->  ONE exchange (the scores of the head, as LL words)  ->
+// every split has all scores, so max, exp, sum and the bf16-rounded probabilities are computed locally and identically  ->
+// context dims [c DH/S, (c+1) DH/S) over ALL slots (V is cut by dims, so no partial contexts have to be merged).
+// Short rings (<= kSoloCtx valid slots: the depformer, the first frames of a conversation) are handled by split 0 alone.
+// The first batch of K and V rows is requested BEFORE q / k / v of this step are polled: the ring rows of earlier steps do
+// not depend on the predecessor phase, so their round trip overlaps the wait.
+constexpr int kSoloCtx = 64;
 template <int DH>
 __device__ __forceinline__ void attn_phase(const StepPhase &ph, const StepArgs &a, uint32_t epoch_bits, int p, uint8_t *smem, Watch &wd) {
-    constexpr int LPS = DH / 8;                   // lanes per slot (8 dims = 16 B of bf16 each)
+    constexpr int LPS = DH / 8;                   // lanes per slot in the score pass (8 dims = 16 B of bf16 each)
     constexpr int NG = kConsumers / LPS;          // slots in flight per CTA iteration
+    constexpr int U = 4;
     const int cta = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int S = ph.split;
-    if (cta >= ph.heads * S) return;
-    const int h = cta / S, c = cta - h * S;
+    if (cta >= ph.heads * ph.split) return;
+    const int h = cta / ph.split, c = cta - h * ph.split;
     const int cap = ph.cap, dim = ph.heads * DH;
     const int pos = ph.pos_const >= 0 ? ph.pos_const : a.ctrl->offset;
     const int slot = pos % cap;
     const int n_valid = (pos >= cap - 1) ? cap : pos + 1;
+    const bool solo = n_valid <= kSoloCtx;
+    if (solo && c != 0) return;
+    const int S = solo ? 1 : ph.split;
     const uint32_t seq_in = epoch_bits | (uint32_t)(ph.x_src + 1), seq_out = epoch_bits | (uint32_t)(p + 1);
 
     uint8_t *scr = smem + kOffX8;
-    double *part = reinterpret_cast<double *>(scr);                          // [NG][DH]
-    float *q_s = reinterpret_cast<float *>(scr + NG * DH * 8);               // [DH] bf16-rounded q'
+    double *part = reinterpret_cast<double *>(scr);                          // [512 / (DS/8)][DS] = 32 KB
+    float *q_s = reinterpret_cast<float *>(scr + 32768);                     // [DH] bf16-rounded q'
     uint16_t *knew = reinterpret_cast<uint16_t *>(q_s + DH);                 // [DH]
     uint16_t *vnew = knew + DH;                                              // [DH]
-    float *sc_s = reinterpret_cast<float *>(vnew + DH);                      // [per]
+    float *sc_s = reinterpret_cast<float *>(vnew + DH);                      // [n_valid]
     double *dred = reinterpret_cast<double *>(smem + kOffRed);
     float *fred = reinterpret_cast<float *>(smem + kOffRed) + 32;
     const float *rope = reinterpret_cast<const float *>(smem + kOffRope);
 
-    // ---- 1. q / k / v of this head, RoPE (interleaved pairs -> [re half | im half]) ----
+    const int lo = (int)((long long)n_valid * c / S), hi = (int)((long long)n_valid * (c + 1) / S);
+    const int DS = DH / S, LPV = DS / 8, NGV = kConsumers / LPV;              // context pass: lanes per slot, slots in flight
+    const int g = tid / LPS, sl = tid % LPS;                                  // score pass
+    const int gv = tid / LPV, slv = tid - gv * LPV;                           // context pass
+    const uint16_t *kbase = ph.kc + (size_t)h * cap * DH + sl * 8, *vbase = ph.vc + (size_t)h * cap * DH + c * DS + slv * 8;
+    uint4 kk[U], vv[U];
+    auto load_k = [&](int i0) {
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int i = i0 + u * NG + g;
+            kk[u] = make_uint4(0, 0, 0, 0);
+            if (i < hi && i != slot) kk[u] = __ldcg(reinterpret_cast<const uint4 *>(kbase + (size_t)i * DH));
+        }
+    };
+    auto load_v = [&](int i0) {
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int i = i0 + u * NGV;
+            vv[u] = make_uint4(0, 0, 0, 0);
+            if (i < n_valid && i != slot) vv[u] = __ldcg(reinterpret_cast<const uint4 *>(vbase + (size_t)i * DH));
+        }
+    };
+    load_k(lo);
+    load_v(gv);
+
+    // ---- 1. q / k / v of this head (all six words requested together), RoPE (interleaved pairs -> [re half | im half]) ----
     if (tid < DH / 2) {
         const int j = tid;
-        const float qr = ll_wait1(ph.x_ll + h * DH + 2 * j, seq_in, wd), qi = ll_wait1(ph.x_ll + h * DH + 2 * j + 1, seq_in, wd);
-        const float kr = ll_wait1(ph.x_ll + dim + h * DH + 2 * j, seq_in, wd), ki = ll_wait1(ph.x_ll + dim + h * DH + 2 * j + 1, seq_in, wd);
-        const float vr = ll_wait1(ph.x_ll + 2 * dim + h * DH + 2 * j, seq_in, wd), vi = ll_wait1(ph.x_ll + 2 * dim + h * DH + 2 * j + 1, seq_in, wd);
+        const LL *pq = ph.x_ll + h * DH + 2 * j, *pk = pq + dim, *pv = pk + dim;
+        wd.reset();
+        ulonglong2 rq = ll_ld2(pq), rk = ll_ld2(pk), rv = ll_ld2(pv);
+        while ((uint32_t)(rq.x >> 32) != seq_in || (uint32_t)(rq.y >> 32) != seq_in || (uint32_t)(rk.x >> 32) != seq_in ||
+               (uint32_t)(rk.y >> 32) != seq_in || (uint32_t)(rv.x >> 32) != seq_in || (uint32_t)(rv.y >> 32) != seq_in) {
+            if (wd.expired()) break;
+            rq = ll_ld2(pq); rk = ll_ld2(pk); rv = ll_ld2(pv);
+        }
+        const float qr = __uint_as_float((uint32_t)rq.x), qi = __uint_as_float((uint32_t)rq.y);
+        const float kr = __uint_as_float((uint32_t)rk.x), ki = __uint_as_float((uint32_t)rk.y);
+        const float vr = __uint_as_float((uint32_t)rv.x), vi = __uint_as_float((uint32_t)rv.y);
         if (ph.max_period) {
             const float cs = rope[j], sn = rope[DH / 2 + j];
             q_s[j] = bf16_round(__fsub_rn(__fmul_rn(qr, cs), __fmul_rn(qi, sn)));
@@ -663,115 +765,123 @@ __device__ __forceinline__ void attn_phase(const StepPhase &ph, const StepArgs &
         else if (tid >= 64 && tid < 64 + DH / 4) reinterpret_cast<uint2 *>(ph.vc + o)[tid - 64] = reinterpret_cast<const uint2 *>(vnew)[tid - 64];
     }
 
-    // ---- 2. scores over this split's share of the valid slots ----
-    const int lo = (int)((long long)n_valid * c / S), hi = (int)((long long)n_valid * (c + 1) / S);
-    const int g = tid / LPS, sl = tid % LPS;
-    const float scale = 1.f / sqrtf((float)DH);
-    float qv[8];
+    // ---- 2. scores over this split's share of the valid slots; published to the other splits of the head ----
+    {
+        const float scale = 1.f / sqrtf((float)DH);
+        float qv[8];
 #pragma unroll
-    for (int i = 0; i < 8; i++) qv[i] = q_s[sl * 8 + i];
-    float lmax = -INFINITY;
-    constexpr int U = 4;
-    for (int i0 = lo; i0 < hi; i0 += NG * U) {
-        uint4 kk[U];
+        for (int i = 0; i < 8; i++) qv[i] = q_s[sl * 8 + i];
+        for (int i0 = lo; i0 < hi; i0 += NG * U) {
+            if (i0 != lo) load_k(i0);
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-            const int i = i0 + u * NG + g;
-            kk[u] = make_uint4(0, 0, 0, 0);
-            if (i < hi) {
-                if (i == slot) kk[u] = reinterpret_cast<const uint4 *>(knew)[sl];
-                else kk[u] = __ldcg(reinterpret_cast<const uint4 *>(ph.kc + ((size_t)h * cap + i) * DH + sl * 8));
-            }
-        }
+            for (int u = 0; u < U; u++) {
+                const int i = i0 + u * NG + g;
+                if (i == slot && i < hi) kk[u] = reinterpret_cast<const uint4 *>(knew)[sl];
+                // bf16 x bf16 products are exact in fp32; they are summed in double (order-independent)
+                double d = 0.0;
+                d += (double)(bf16_bits_to_f32(kk[u].x & 0xffff) * qv[0]); d += (double)(bf16_bits_to_f32(kk[u].x >> 16) * qv[1]);
+                d += (double)(bf16_bits_to_f32(kk[u].y & 0xffff) * qv[2]); d += (double)(bf16_bits_to_f32(kk[u].y >> 16) * qv[3]);
+                d += (double)(bf16_bits_to_f32(kk[u].z & 0xffff) * qv[4]); d += (double)(bf16_bits_to_f32(kk[u].z >> 16) * qv[5]);
+                d += (double)(bf16_bits_to_f32(kk[u].w & 0xffff) * qv[6]); d += (double)(bf16_bits_to_f32(kk[u].w >> 16) * qv[7]);
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-            const int i = i0 + u * NG + g;
-            double d = 0.0;
-            d += (double)(bf16_bits_to_f32(kk[u].x & 0xffff) * qv[0]); d += (double)(bf16_bits_to_f32(kk[u].x >> 16) * qv[1]);
-            d += (double)(bf16_bits_to_f32(kk[u].y & 0xffff) * qv[2]); d += (double)(bf16_bits_to_f32(kk[u].y >> 16) * qv[3]);
-            d += (double)(bf16_bits_to_f32(kk[u].z & 0xffff) * qv[4]); d += (double)(bf16_bits_to_f32(kk[u].z >> 16) * qv[5]);
-            d += (double)(bf16_bits_to_f32(kk[u].w & 0xffff) * qv[6]); d += (double)(bf16_bits_to_f32(kk[u].w >> 16) * qv[7]);
-#pragma unroll
-            for (int o = LPS / 2; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-            const float sv = (float)d * scale + 0.0f;
-            if (i < hi) {
-                if (sl == 0) sc_s[i - lo] = sv;
-                lmax = fmaxf(lmax, sv);
+                for (int o = LPS / 2; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+                const float sv = (float)d * scale + 0.0f;
+                if (i < hi && sl == 0) {
+                    sc_s[i] = sv;
+                    if (S > 1) ll_store(ph.scores + (size_t)h * cap + i, sv, seq_out);
+                }
             }
         }
     }
+    if (S > 1) {       // the other splits' scores: up to 8 words per thread requested together, missing ones re-polled
+        const LL *src = ph.scores + (size_t)h * cap;
+        for (int i0 = tid; i0 < n_valid; i0 += 8 * kConsumers) {
+            unsigned long long r[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) { const int i = i0 + u * kConsumers; r[u] = (i < n_valid && (i < lo || i >= hi)) ? ll_ld1(src + i) : 0ull; }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int i = i0 + u * kConsumers;
+                if (i < n_valid && (i < lo || i >= hi)) {
+                    wd.reset();
+                    while ((uint32_t)(r[u] >> 32) != seq_out) { if (wd.expired()) break; r[u] = ll_ld1(src + i); }
+                    sc_s[i] = __uint_as_float((uint32_t)r[u]);
+                }
+            }
+        }
+    }
+    consumer_sync();
+
+    // ---- 3. max, exp and row sum over ALL slots (ggml soft_max: expf(x - max), sum in double, scale by 1 / sum) ----
+    float lmax = -INFINITY;
+    for (int i = tid; i < n_valid; i += kConsumers) lmax = fmaxf(lmax, sc_s[i]);
     lmax = warp_max(lmax);
     if (lane == 0) fred[warp] = lmax;
     consumer_sync();
-    float cmax = fred[0];
+    float gmax = fred[0];
 #pragma unroll
-    for (int w = 1; w < kConsumerWarps; w++) cmax = fmaxf(cmax, fred[w]);
-    float gmax = cmax;
-    if (S > 1) {
-        if (tid == 0) ll_store(ph.xmax + h * S + c, cmax, seq_out);
-        for (int r = 0; r < S; r++) gmax = fmaxf(gmax, r == c ? cmax : ll_wait1(ph.xmax + h * S + r, seq_out, wd));
-    }
-
-    // ---- 3. exp and row sum (ggml soft_max: expf(x - max), sum in double, scale by 1 / sum) ----
+    for (int w = 1; w < kConsumerWarps; w++) gmax = fmaxf(gmax, fred[w]);
     double lsum = 0.0;
-    for (int i = lo + tid; i < hi; i += kConsumers) { const float e = (float)exp((double)(sc_s[i - lo] - gmax)); sc_s[i - lo] = e; lsum += (double)e; }
+    for (int i = tid; i < n_valid; i += kConsumers) { const float e = (float)exp((double)(sc_s[i] - gmax)); sc_s[i] = e; lsum += (double)e; }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
     if (lane == 0) dred[warp] = lsum;
     consumer_sync();
-    double csum = 0.0;
+    double gsum = 0.0;
 #pragma unroll
-    for (int w = 0; w < kConsumerWarps; w++) csum += dred[w];
-    double gsum = csum;
-    if (S > 1) {
-        if (tid == 0) ll_store_f64(ph.xsum + (h * S + c) * 2, csum, seq_out);
-        gsum = 0.0;
-        for (int r = 0; r < S; r++) gsum += r == c ? csum : ll_wait_f64(ph.xsum + (h * S + r) * 2, seq_out, wd);
-    }
+    for (int w = 0; w < kConsumerWarps; w++) gsum += dred[w];
     const float inv = (float)(1.0 / gsum);
 
-    // ---- 4. context = sum_i bf16(p_i) * V_i over this split's slots ----
-    double acc[8];
+    // ---- 4. context dims [c DS, (c+1) DS) = sum_i bf16(p_i) * V_i over all slots ----
+    {
+        double acc[8];
 #pragma unroll
-    for (int i = 0; i < 8; i++) acc[i] = 0.0;
-    for (int i0 = lo + g; i0 < hi; i0 += NG * U) {
-        uint4 vv[U];
+        for (int i = 0; i < 8; i++) acc[i] = 0.0;
+        for (int i0 = gv; i0 < n_valid; i0 += NGV * U) {
+            if (i0 != gv) load_v(i0);
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-            const int i = i0 + u * NG;
-            vv[u] = make_uint4(0, 0, 0, 0);
-            if (i < hi) {
-                if (i == slot) vv[u] = reinterpret_cast<const uint4 *>(vnew)[sl];
-                else vv[u] = __ldcg(reinterpret_cast<const uint4 *>(ph.vc + ((size_t)h * cap + i) * DH + sl * 8));
+            for (int u = 0; u < U; u++) {
+                const int i = i0 + u * NGV;
+                if (i < n_valid) {
+                    if (i == slot) vv[u] = reinterpret_cast<const uint4 *>(vnew)[c * LPV + slv];
+                    const float pr = bf16_round(sc_s[i] * inv);
+                    acc[0] += (double)(bf16_bits_to_f32(vv[u].x & 0xffff) * pr); acc[1] += (double)(bf16_bits_to_f32(vv[u].x >> 16) * pr);
+                    acc[2] += (double)(bf16_bits_to_f32(vv[u].y & 0xffff) * pr); acc[3] += (double)(bf16_bits_to_f32(vv[u].y >> 16) * pr);
+                    acc[4] += (double)(bf16_bits_to_f32(vv[u].z & 0xffff) * pr); acc[5] += (double)(bf16_bits_to_f32(vv[u].z >> 16) * pr);
+                    acc[6] += (double)(bf16_bits_to_f32(vv[u].w & 0xffff) * pr); acc[7] += (double)(bf16_bits_to_f32(vv[u].w >> 16) * pr);
+                }
             }
         }
+        // only the groups that saw a slot write their partials (n_valid is small in the depformer and early in a conversation)
+        if (gv < n_valid) {
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-            const int i = i0 + u * NG;
-            if (i < hi) {
-                const float pr = bf16_round(sc_s[i - lo] * inv);
-                acc[0] += (double)(bf16_bits_to_f32(vv[u].x & 0xffff) * pr); acc[1] += (double)(bf16_bits_to_f32(vv[u].x >> 16) * pr);
-                acc[2] += (double)(bf16_bits_to_f32(vv[u].y & 0xffff) * pr); acc[3] += (double)(bf16_bits_to_f32(vv[u].y >> 16) * pr);
-                acc[4] += (double)(bf16_bits_to_f32(vv[u].z & 0xffff) * pr); acc[5] += (double)(bf16_bits_to_f32(vv[u].z >> 16) * pr);
-                acc[6] += (double)(bf16_bits_to_f32(vv[u].w & 0xffff) * pr); acc[7] += (double)(bf16_bits_to_f32(vv[u].w >> 16) * pr);
-            }
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < 8; i++) part[g * DH + sl * 8 + i] = acc[i];
-    consumer_sync();
-    if (tid < DH) {
-        double tot = 0.0;
-        for (int gg = 0; gg < NG; gg++) tot += part[gg * DH + tid];
-        if (S > 1 && c != 0) ll_store_f64(ph.xpart + ((size_t)(h * S + c) * DH + tid) * 2, tot, seq_out);
-        else {
-            for (int r = 1; r < S; r++) tot += ll_wait_f64(ph.xpart + ((size_t)(h * S + r) * DH + tid) * 2, seq_out, wd);
-            ll_store(ph.out + h * DH + tid, (float)tot, seq_out);
+            for (int i = 0; i < 8; i++) part[gv * DS + slv * 8 + i] = acc[i];
         }
     }
     consumer_sync();
-    // the scratch aliases the GEMV operand area and `part` must read zero again
-    for (int j = tid; j < kAttnScratch / 16; j += kConsumers) reinterpret_cast<uint4 *>(scr)[j] = make_uint4(0, 0, 0, 0);
+    {   // reduce over the groups: 4 threads per dim take a quarter of the groups each, then a fixed-order sum of the four
+        const int ng = min(NGV, n_valid);
+        double *qsum = reinterpret_cast<double *>(scr + 32768);               // [4][DS]: q / k / v rows and the probabilities are dead now
+        if (tid < 4 * DS) {
+            const int qd = tid / DS, d = tid - qd * DS;
+            const int g0 = (ng * qd) / 4, g1 = (ng * (qd + 1)) / 4;
+            double t = 0.0;
+            for (int gg = g0; gg < g1; gg++) t += part[gg * DS + d];
+            qsum[qd * DS + d] = t;
+        }
+        consumer_sync();
+        if (tid < DS) {
+            const double t = ((qsum[tid] + qsum[DS + tid]) + qsum[2 * DS + tid]) + qsum[3 * DS + tid];
+            ll_store(ph.out + h * DH + c * DS + tid, (float)t, seq_out);
+        }
+    }
+    consumer_sync();
+    // the scratch aliases the GEMV accumulation area, which must read zero again (only what this phase can have touched)
+    {
+        const int used = 32768 + max(DH * 8 + n_valid * 4 + 16, 4 * DS * 8);  // bytes of scratch written, from kOffX8
+        const int z0 = kOffPart - kOffX8, z1 = min(used, kOffRed - kOffX8);
+        for (int j = z0 / 16 + tid; j < (z1 + 15) / 16; j += kConsumers) reinterpret_cast<uint4 *>(scr)[j] = make_uint4(0, 0, 0, 0);
+    }
     consumer_sync();
 }
 
@@ -821,9 +931,9 @@ __global__ void __launch_bounds__(kThreads, 1) step_kernel(const StepArgs a) {
             const int j = tid + i * kConsumers;
             nw[i] = (more && j < n4) ? __ldg(reinterpret_cast<const uint32_t *>(a.phases + p + 1) + j) : 0u;
         }
-        if (a.dbg && cta == 0 && tid == 0) a.dbg[(size_t)p * 4] = gtime_ns();
+        if (a.dbg && tid == 0) a.dbg[((size_t)p * gridDim.x + cta) * 8] = gtime_ns();
         switch (ph.type) {
-            case PH_GEMV: gemv_phase<WT>(ph, epoch_bits, p, q_base, smem, wd); break;
+            case PH_GEMV: gemv_phase<WT>(ph, epoch_bits, p, q_base, smem, wd, a.dbg ? a.dbg + ((size_t)p * gridDim.x + cta) * 8 : nullptr); break;
             case PH_ATTN: if (ph.dh == 128) attn_phase<128>(ph, a, epoch_bits, p, smem, wd); else attn_phase<64>(ph, a, epoch_bits, p, smem, wd); break;
             case PH_EMBED: embed_phase(ph, a, epoch_bits, p, smem); break;
             case PH_DEP_EMBED: dep_embed_phase(ph, a, epoch_bits, p, smem, wd); break;
@@ -856,7 +966,7 @@ __global__ void __launch_bounds__(kThreads, 1) step_kernel(const StepArgs a) {
                 break;
             }
         }
-        if (a.dbg && cta == 0 && tid == 0) a.dbg[(size_t)p * 4 + 1] = gtime_ns();
+        if (a.dbg && tid == 0) a.dbg[((size_t)p * gridDim.x + cta) * 8 + 1] = gtime_ns();
         if (more) {
 #pragma unroll
             for (int i = 0; i < (n4 + kConsumers - 1) / kConsumers; i++) {

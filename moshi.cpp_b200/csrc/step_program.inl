@@ -9,10 +9,10 @@
 namespace {
 
 // Models the step kernel takes: one weight type, every linear in stream layout, self-attention only, plain embeddings,
-// one GPU.  Everything else (TTS family, tensor parallel, temperature sampling) runs on the PDL-chained launches.
+// one GPU, greedy decoding.  Opt-in (MSX_STREAM_STEP_KERNEL); everything else runs on the PDL-chained launches.
 bool step_kernel_eligible(const msx_stream *s) {
     const msx_model *m = s->m; const msx_config &c = m->cfg;
-    if (s->flags & MSX_STREAM_LAUNCH_CHAIN) return false;
+    if (!(s->flags & MSX_STREAM_STEP_KERNEL)) return false;
     if (!m->stream_ok || m->tp_world != 1 || c.cross_attention || c.demux_second_stream || m->dep_small) return false;
     if (m->stream_type != T_Q4_K && m->stream_type != T_Q8_0) return false;
     if (s->temp_text > 0.f || s->temp_audio > 0.f) return false;
@@ -29,9 +29,8 @@ bool step_kernel_eligible(const msx_stream *s) {
         if (!fits(l.in_proj[0], 1) || !fits(l.out_proj[0], 1) || !fits(l.lin_in[0], 2) || !fits(l.lin_out[0], 1)) return false;
     if (!fits(m->text_linear, 1)) return false;
     if (c.num_heads > m->num_sms) return false;
-    const int S = std::max(1, std::min(sk::kMaxSplit, m->num_sms / c.num_heads));
-    // attention scratch: [NG][DH] doubles | q | k, v | scores of one split
-    if (32768 + dh * 8 + ((s->cap + S - 1) / S + 2) * 4 > sk::kAttnScratch) return false;
+    // attention scratch: 32 KB of partial contexts | q | k, v | scores / probabilities of the whole ring
+    if (32768 + dh * 8 + (s->cap + 2) * 4 > sk::kAttnScratch) return false;
     if (c.dep_q > 0) {
         if (!fits(m->dep_in_all, 1)) return false;
         for (const LayerW &l : m->dep_layers)
@@ -50,24 +49,23 @@ int build_step_programs(msx_stream *s) {
     StepBuffers &b = s->step_buf;
     auto ll = [&](sk::LL **p, size_t n) { return salloc(s, (void **)p, (n + 8) * sizeof(sk::LL)); };
     const int dh = c.dim / c.num_heads;
-    const int S = std::max(1, std::min(sk::kMaxSplit, n_cta / c.num_heads));
+    int S = 1;                                                 // split factor of the temporal attention: power of two, <= 8, heads * S CTAs
+    while (S * 2 <= sk::kMaxSplit && c.num_heads * S * 2 <= n_cta && dh / (S * 2) >= 8) S *= 2;
     if (int e = ll(&b.xA, c.dim)) return e;
     if (int e = ll(&b.xB, c.dim)) return e;
     if (int e = ll(&b.qkv, (size_t)3 * c.dim)) return e;
     if (int e = ll(&b.ctx, c.dim)) return e;
     if (int e = ll(&b.gate, m->hidden)) return e;
     if (int e = ll(&b.tkeys, (size_t)2 * n_cta)) return e;
-    if (int e = ll(&b.xmax, (size_t)c.num_heads * S)) return e;
-    if (int e = ll(&b.xsum, (size_t)c.num_heads * S * 2)) return e;
-    if (int e = ll(&b.xpart, (size_t)c.num_heads * S * dh * 2)) return e;
+    if (int e = ll(&b.scores, (size_t)c.num_heads * s->cap)) return e;
     if (int e = salloc(s, (void **)&s->d_epoch, 64)) return e;
     const uint32_t one = 1u;
     CU(cudaMemcpy(s->d_epoch, &one, 4, cudaMemcpyHostToDevice));
 
     auto stream_of = [&](const QLinear &w) { return m->wstream.at(w.qs); };
-    auto gemv = [&](std::vector<sk::StepPhase> &prog, const QLinear &w, int pro, int epi) -> sk::StepPhase & {
+    auto gemv = [&](std::vector<sk::StepPhase> &prog, const QLinear &w, int pro, int epi, int fam) -> sk::StepPhase & {
         sk::StepPhase ph;
-        ph.type = sk::PH_GEMV; ph.pro = pro; ph.epi = epi;
+        ph.type = sk::PH_GEMV; ph.pro = pro; ph.epi = epi; ph.fam = fam;
         const auto sw = stream_of(w);
         ph.w = sw.p; ph.gran = sw.gran; ph.K = w.K; ph.rows = w.rows; ph.eps = 1e-8f;
         prog.push_back(ph);
@@ -77,27 +75,27 @@ int build_step_programs(msx_stream *s) {
     auto layer = [&](std::vector<sk::StepPhase> &prog, const LayerW &lw, int w, bool temporal, int li, int step, sk::LL *xa, sk::LL *xb,
                      sk::LL *qkv, sk::LL *ctx, sk::LL *gate, int &x_src) {
         const int heads = temporal ? c.num_heads : c.dep_heads, dim = temporal ? c.dim : c.dep_dim, cap = temporal ? s->cap : m->dep_cap;
-        {   sk::StepPhase &g = gemv(prog, lw.in_proj[w], PRO_RMS, EPI_STORE);
+        {   sk::StepPhase &g = gemv(prog, lw.in_proj[w], PRO_RMS, EPI_STORE, temporal ? FAM_IN_PROJ : FAM_DEP_IN_PROJ);
             g.x_ll = xa; g.x_src = x_src; g.alpha = lw.norm1; g.out = qkv; }
         const int p_qkv = (int)prog.size() - 1;
         {   sk::StepPhase a;
-            a.type = sk::PH_ATTN; a.x_ll = qkv; a.x_src = p_qkv; a.out = ctx;
+            a.type = sk::PH_ATTN; a.fam = temporal ? FAM_ATTN : FAM_DEP_ATTN; a.x_ll = qkv; a.x_src = p_qkv; a.out = ctx;
             a.heads = heads; a.dh = dim / heads; a.cap = cap; a.split = temporal ? S : 1;
             a.pos_const = temporal ? -1 : step; a.step = step;
             a.max_period = temporal ? c.max_period : c.dep_max_period;
             const size_t lstride = (size_t)cap * dim;
             a.kc = (temporal ? s->kc : s->dkc) + (size_t)li * lstride;
             a.vc = (temporal ? s->vc : s->dvc) + (size_t)li * lstride;
-            a.xmax = b.xmax; a.xsum = b.xsum; a.xpart = b.xpart;
+            a.scores = b.scores;
             prog.push_back(a); }
         const int p_ctx = (int)prog.size() - 1;
-        {   sk::StepPhase &g = gemv(prog, lw.out_proj[w], PRO_PLAIN, EPI_RESID);
+        {   sk::StepPhase &g = gemv(prog, lw.out_proj[w], PRO_PLAIN, EPI_RESID, temporal ? FAM_OUT_PROJ : FAM_DEP_OUT_PROJ);
             g.x_ll = ctx; g.x_src = p_ctx; g.resid = xa; g.resid_src = x_src; g.out = xb; }
         const int p_xb = (int)prog.size() - 1;
-        {   sk::StepPhase &g = gemv(prog, lw.lin_in[w], PRO_RMS, EPI_GATE);
+        {   sk::StepPhase &g = gemv(prog, lw.lin_in[w], PRO_RMS, EPI_GATE, temporal ? FAM_LIN_IN : FAM_DEP_LIN_IN);
             g.x_ll = xb; g.x_src = p_xb; g.alpha = lw.norm2; g.out = gate; }
         const int p_gate = (int)prog.size() - 1;
-        {   sk::StepPhase &g = gemv(prog, lw.lin_out[w], PRO_PLAIN, EPI_RESID);
+        {   sk::StepPhase &g = gemv(prog, lw.lin_out[w], PRO_PLAIN, EPI_RESID, temporal ? FAM_LIN_OUT : FAM_DEP_LIN_OUT);
             g.x_ll = gate; g.x_src = p_gate; g.resid = xb; g.resid_src = p_xb; g.out = xa; }
         x_src = (int)prog.size() - 1;
     };
@@ -105,19 +103,20 @@ int build_step_programs(msx_stream *s) {
     // ---- temporal ----
     std::vector<sk::StepPhase> pt;
     {   sk::StepPhase e;
-        e.type = sk::PH_EMBED; e.tables = m->d_emb; e.n_tables = c.n_q + 1; e.dim = c.dim; e.out = b.xA; e.embed_in = s->embed_in;
+        e.type = sk::PH_EMBED; e.fam = FAM_EMBED; e.tables = m->d_emb; e.n_tables = c.n_q + 1; e.dim = c.dim; e.out = b.xA; e.embed_in = s->embed_in;
         pt.push_back(e); }
     int x_src = 0;
     for (int l = 0; l < c.num_layers; l++) layer(pt, m->layers[l], 0, true, l, 0, b.xA, b.xB, b.qkv, b.ctx, b.gate, x_src);
-    {   sk::StepPhase &g = gemv(pt, m->text_linear, PRO_RMS, EPI_ARGMAX);
+    {   sk::StepPhase &g = gemv(pt, m->text_linear, PRO_RMS, EPI_ARGMAX, FAM_TEXT_HEAD);
         g.x_ll = b.xA; g.x_src = x_src; g.alpha = m->out_norm; g.norm_out = s->tout; g.out_plain = s->text_logits; g.keys = b.tkeys; }
     {   sk::StepPhase f;
-        f.type = sk::PH_FINALIZE_T; f.prev_keys = b.tkeys; f.prev_src = (int)pt.size() - 1; f.has_depformer = c.dep_q > 0 ? 1 : 0;
+        f.type = sk::PH_FINALIZE_T; f.fam = FAM_FINALIZE; f.prev_keys = b.tkeys; f.prev_src = (int)pt.size() - 1; f.has_depformer = c.dep_q > 0 ? 1 : 0;
         pt.push_back(f); }
     if (pt.size() > 4000) return fail(MSX_ERR_ARG, "step program too long");
     if (int e = salloc(s, (void **)&s->d_prog_t, pt.size() * sizeof(sk::StepPhase))) return e;
     CU(cudaMemcpy(s->d_prog_t, pt.data(), pt.size() * sizeof(sk::StepPhase), cudaMemcpyHostToDevice));
     s->n_prog_t = (int)pt.size();
+    for (const sk::StepPhase &ph : pt) s->prog_fam_t.push_back(ph.fam);
 
     // ---- depformer ----
     if (c.dep_q > 0) {
@@ -130,22 +129,22 @@ int build_step_programs(msx_stream *s) {
         if (int e = ll(&b.dgate, m->dep_hidden)) return e;
         if (int e = ll(&b.dkeys, (size_t)c.dep_q * 2 * n_cta)) return e;
         std::vector<sk::StepPhase> pd;
-        {   sk::StepPhase &g = gemv(pd, m->dep_in_all, PRO_PLAIN, EPI_STORE);
+        {   sk::StepPhase &g = gemv(pd, m->dep_in_all, PRO_PLAIN, EPI_STORE, FAM_DEP_IN);
             g.x_plain = s->tout; g.out = b.dep_d; }
         sk::StepPhase fin;
-        fin.type = sk::PH_FINALIZE_D; fin.dep_q = c.dep_q; fin.prev_keys = b.dkeys; fin.keys_stride = 2 * n_cta;
+        fin.type = sk::PH_FINALIZE_D; fin.fam = FAM_DEP_FINALIZE; fin.dep_q = c.dep_q; fin.prev_keys = b.dkeys; fin.keys_stride = 2 * n_cta;
         int prev_head = -1;
         for (int k = 0; k < c.dep_q; k++) {
             const int wsel = c.schedule_len ? c.schedule[k] : k, w = m->dep_nw == 1 ? 0 : wsel;     // lm.h:457-462, transformer.h:74-83
             {   sk::StepPhase e;
-                e.type = sk::PH_DEP_EMBED; e.step = k; e.dim = dd; e.x_ll = b.dep_d + (size_t)k * dd; e.x_src = 0;
+                e.type = sk::PH_DEP_EMBED; e.fam = FAM_DEP_IN; e.step = k; e.dim = dd; e.x_ll = b.dep_d + (size_t)k * dd; e.x_src = 0;
                 e.emb = k == 0 ? m->dep_text_emb : m->dep_emb[k - 1];
                 e.prev_keys = k > 0 ? b.dkeys + (size_t)(k - 1) * 2 * n_cta : nullptr; e.prev_src = prev_head;
                 e.out = b.dxA;
                 pd.push_back(e); }
             int dx_src = (int)pd.size() - 1;
             for (int l = 0; l < c.dep_layers; l++) layer(pd, m->dep_layers[l], w, false, l, k, b.dxA, b.dxB, b.dqkv, b.dctx, b.dgate, dx_src);
-            {   sk::StepPhase &g = gemv(pd, m->linears[k], PRO_PLAIN, EPI_ARGMAX);       // no final norm (lm.h:472)
+            {   sk::StepPhase &g = gemv(pd, m->linears[k], PRO_PLAIN, EPI_ARGMAX, FAM_DEP_HEAD);       // no final norm (lm.h:472)
                 g.x_ll = b.dxA; g.x_src = dx_src; g.out_plain = s->audio_logits + (size_t)k * c.card; g.keys = b.dkeys + (size_t)k * 2 * n_cta; }
             prev_head = (int)pd.size() - 1;
             fin.key_src[k] = prev_head;
@@ -155,6 +154,7 @@ int build_step_programs(msx_stream *s) {
         if (int e = salloc(s, (void **)&s->d_prog_d, pd.size() * sizeof(sk::StepPhase))) return e;
         CU(cudaMemcpy(s->d_prog_d, pd.data(), pd.size() * sizeof(sk::StepPhase), cudaMemcpyHostToDevice));
         s->n_prog_d = (int)pd.size();
+        for (const sk::StepPhase &ph : pd) s->prog_fam_d.push_back(ph.fam);
     }
     return 0;
 }

@@ -1,5 +1,5 @@
-"""dev: bring-up of the persistent step kernel — A/B against the PDL-chained launches (same C ABI), then timing.
-usage: dev_step_kernel.py [stage ...]   stages: tiny tiny8 pplex stt l2 time time8 oracle"""
+"""A/B of the persistent step kernel (MSX_STREAM_STEP_KERNEL) against the PDL-chained launches through the same C ABI, then timing.
+usage: step_kernel_check.py [stage ...]   stages: tiny tiny8 pplex stt l2 time time8 oracle"""
 import os, sys, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -11,7 +11,7 @@ from moshi_cpp_b200 import configs, synth, binding as msx
 def ab(preset, quant, n_frames, context=0):
     cfg = configs.get(preset); path = synth.cached_gguf(preset, quant)
     m = msx.Model(path, cfg)
-    a = msx.Stream(m, context=context); b = msx.Stream(m, context=context, launch_chain=True)
+    a = msx.Stream(m, context=context, step_kernel=True); b = msx.Stream(m, context=context)
     print(f"[{preset} {quant}] launches/frame: step-kernel {a.launches_per_frame}, chain {b.launches_per_frame}", flush=True)
     rng = np.random.default_rng(7)
     toks = np.array([cfg["text_card"]] + [cfg["card"]] * cfg["n_q"], dtype=np.int32)
@@ -43,7 +43,7 @@ def ab(preset, quant, n_frames, context=0):
 def oracle_check(preset, quant, n_frames):
     import oracle
     cfg = configs.get(preset); path = synth.cached_gguf(preset, quant)
-    m = msx.Model(path, cfg); s = msx.Stream(m)
+    m = msx.Model(path, cfg); s = msx.Stream(m, step_kernel=True)
     om = oracle.Model(path, cfg); os_ = oracle.State(om)
     rng = np.random.default_rng(3)
     toks = np.array([cfg["text_card"]] + [cfg["card"]] * cfg["n_q"], dtype=np.int32)
@@ -66,8 +66,8 @@ def timing(preset, quant, n=300, context=0):
     rng = np.random.default_rng(0)
     frames = rng.integers(0, cfg["card"], size=(32, cfg["n_q"] + 1)).astype(np.int32)
     gb = m.weight_bytes_per_frame / 1e9
-    for name, chain in (("step-kernel", False), ("chain", True), ("step-kernel", False)):
-        s = msx.Stream(m, context=context, launch_chain=chain)
+    for name, sk in (("step-kernel", True), ("chain", False), ("step-kernel", True)):
+        s = msx.Stream(m, context=context, step_kernel=sk)
         s.run_resident(frames, 30)
         ms, _ = s.run_resident(frames, n)
         print(f"[{preset} {quant}] {name:12s} launches/frame {s.launches_per_frame:4d}  {ms / n:.4f} ms/frame  {n / ms * 1e3:.1f} fps  "
