@@ -210,7 +210,9 @@ MSX_API int msx_gen_create(msx_stream *s, int delay_steps, msx_gen **out);
 typedef int (*msx_step_fn)(void *user, const int32_t *tokens, int depformer_replace_tokens, int32_t *out);
 MSX_API int msx_gen_create_with_callback(const msx_config *cfg, int delay_steps, msx_step_fn fn, void *user, msx_gen **out);
 MSX_API void msx_gen_free(msx_gen *g);
-/* srand() for the Exp(1) draws of sampled generation (the reference never seeds except in --bench: srand(0)) */
+/* seed of this generator's Exp(1) draws (sampled generation).  Every generator owns a private glibc random state (random_r)
+ * that yields the sequence srand(seed) / rand() would: one generator reproduces the reference's draws (which never seeds
+ * except in --bench: srand(0)); several generators or threads do not disturb each other. */
 MSX_API void msx_gen_seed(msx_gen *g, unsigned seed);
 /* T prompt frames with all n_q+1 tokens given (rows [T][n_q+1]) as one batched-T prefill: delay-ring bookkeeping of
  * moshi_lmgen_step's "provided" branch + msx_stream_prefill; same final state as T msx_gen_step calls with n_in == n_q+1 */

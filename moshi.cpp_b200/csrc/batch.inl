@@ -250,6 +250,7 @@ int capture_b(msx_batch *b, F &&body, cudaGraphExec_t *exec, int *launches) {
 
 int push_inputs_b(msx_batch *b, const int32_t *tokens) {
     const msx_config &c = b->m->cfg;
+    if (int e = check_tokens(b->m, tokens, b->n, INT32_MIN, nullptr)) return e;
     const int w = (int)(kCtrlInBytes / 4);
     for (int s = 0; s < b->n; s++) {
         int32_t *h = b->h_in + (size_t)s * w;
@@ -509,6 +510,7 @@ extern "C" int msx_batch_get_logits(msx_batch *b, int stream, float *text_logits
 // frames [n][n_frames][n_q+1] resident on the device, n_steps frames replayed back to back for every stream
 extern "C" int msx_batch_run_resident(msx_batch *b, const int32_t *frames, int n_frames, int n_steps, int32_t *out_tokens, float *elapsed_ms) {
     if (!b || !frames || n_frames <= 0 || n_steps <= 0) return fail(MSX_ERR_ARG, "bad argument");
+    if (int e = check_tokens(b->m, frames, b->n * n_frames, INT32_MIN, nullptr)) return e;
     const msx_config &c = b->m->cfg;
     CU(cudaSetDevice(b->m->device));
     const int n_in = c.n_q + 1, n_out = 1 + c.dep_q;
@@ -726,12 +728,12 @@ extern "C" int msx_bgen_step(msx_bgen *g, const int32_t *in_tokens, int n_in, in
         memcpy(g->inputs.data() + (size_t)i * ncb, prep[i].input, (size_t)ncb * 4);
     }
     if (b->temp_text > 0.f || b->temp_audio > 0.f) {
-        // Exp(1) draws from libc rand() like context.h:464-480, stream by stream (text candidates, then the codebooks)
+        // Exp(1) draws like context.h:464-480 (text candidates, then the codebooks), every conversation from its own generator state
         const int kt = std::min(std::min(b->top_k_text, c.text_card), kSampleMaxK), ka = std::min(std::min(b->top_k_audio, c.card), kSampleMaxK);
         std::vector<float> nt((size_t)n * kt, 1.f), na((size_t)n * std::max(1, c.dep_q) * ka, 1.f);
         for (int i = 0; i < n; i++) {
-            if (b->temp_text > 0.f) for (int j = 0; j < kt; j++) nt[(size_t)i * kt + j] = -logf(rand() / (float)RAND_MAX);
-            if (b->temp_audio > 0.f) for (size_t j = 0; j < (size_t)c.dep_q * ka; j++) na[(size_t)i * c.dep_q * ka + j] = -logf(rand() / (float)RAND_MAX);
+            if (b->temp_text > 0.f) for (int j = 0; j < kt; j++) nt[(size_t)i * kt + j] = g->gens[i]->rng.exp1();
+            if (b->temp_audio > 0.f) for (size_t j = 0; j < (size_t)c.dep_q * ka; j++) na[(size_t)i * c.dep_q * ka + j] = g->gens[i]->rng.exp1();
         }
         if (int e = msx_batch_set_noise(b, nt.data(), na.data())) return e;
     }

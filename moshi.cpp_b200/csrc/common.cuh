@@ -176,7 +176,9 @@ __device__ __forceinline__ int argmax_key_index(unsigned long long key) {
 }
 
 // one element of a GGUF-format row (Q4_0 / Q8_0 / F32 / F16 / BF16): ggml dequantize_row_* per element
+// (the host validates token ids — check_tokens in engine.cu; the clamp keeps a stray id inside the table regardless)
 __device__ __forceinline__ float emb_element(const EmbTable &t, int row, int i) {
+    row = max(0, min(row, t.rows - 1));
     const uint8_t *r = t.data + (size_t)row * t.row_bytes;
     switch (t.type) {
         case 0: return reinterpret_cast<const float *>(r)[i];

@@ -2,6 +2,8 @@
 // declared in include/moshi_b200.h.  See DESIGN.md for the mapping to the reference.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <climits>
@@ -1279,9 +1281,11 @@ static int stream_create_impl(msx_model *m, int context_override, int flags, con
         if (int e = salloc(s.get(), (void **)&s->demux_y1, (size_t)c.dim * 4)) return e;
         if (int e = salloc(s.get(), (void **)&s->demux_y2, (size_t)c.dim * 4)) return e;
     }
-    if (m->dep_small)
+    if (m->dep_small) {
         if (int e = salloc(s.get(), (void **)&s->dep_e, (size_t)c.dep_dim * 4)) return e;
-        if (int e = salloc(s.get(), (void **)&s->dep_d, (size_t)c.dep_q * c.dep_dim * 4)) return e;
+    }
+    // depformer_in[k] . t_out of every step (hoisted launch): needed with and without the small-embedding path
+    if (int e = salloc(s.get(), (void **)&s->dep_d, (size_t)c.dep_q * c.dep_dim * 4)) return e;
     s->noise_floats = kSampleMaxK * (1 + MSX_MAX_STEPS);
     if (int e = salloc(s.get(), (void **)&s->d_noise, (size_t)s->noise_floats * 4)) return e;
     if (int e = salloc(s.get(), (void **)&s->d_probs, (size_t)std::max(c.text_card, c.card) * 4)) return e;
@@ -1383,8 +1387,34 @@ extern "C" int msx_stream_launches_per_frame(const msx_stream *s) { return s ? s
 
 namespace {
 
+// Token ids index embedding tables on the device: reject anything outside the tables here, on the host (a stray id would
+// read device memory out of bounds and the resulting fault would take every stream of the process with it).
+//   input tokens (lm.h:555-584): -1 = zero embedding, other negatives = row 0 ("ungenerated", lm_utils.h:172-182), else a row of
+//   the table (text: text_card + 1 rows, or the two-stream demux range; audio: card + 1 rows)
+//   text_override / force (depformer feed-forward, lm.h:494-516): INT32_MIN = none, else a row of the step's table
+int check_tokens(const msx_model *m, const int32_t *tokens, int n_rows, int32_t text_override, const int32_t *force) {
+    const msx_config &c = m->cfg;
+    const long long n_text = (long long)c.text_card + 1;
+    const long long text_max = c.demux_second_stream ? n_text * (n_text + 1) - 1 : n_text - 1;
+    if (tokens)
+        for (int r = 0; r < n_rows; r++) {
+            const int32_t *t = tokens + (size_t)r * (c.n_q + 1);
+            if (t[0] < -2 || t[0] > text_max) return fail(MSX_ERR_ARG, "text token " + std::to_string(t[0]) + " is outside the embedding table");
+            for (int i = 1; i <= c.n_q; i++)
+                if (t[i] < -2 || t[i] > c.card) return fail(MSX_ERR_ARG, "audio token " + std::to_string(t[i]) + " (codebook " + std::to_string(i - 1) + ") is outside the embedding table");
+        }
+    if (text_override != INT32_MIN && (text_override < -2 || text_override > text_max))
+        return fail(MSX_ERR_ARG, "text token " + std::to_string(text_override) + " is outside the depformer text embedding table");
+    if (force)
+        for (int k = 0; k < c.dep_q; k++)
+            if (force[k] != INT32_MIN && (force[k] < 0 || force[k] > c.card))
+                return fail(MSX_ERR_ARG, "forced audio token " + std::to_string(force[k]) + " (step " + std::to_string(k) + ") is outside the embedding table");
+    return 0;
+}
+
 int push_inputs(msx_stream *s, const int32_t *tokens, int32_t text_override, const int32_t *force) {
     const msx_config &c = s->m->cfg;
+    if (int e = check_tokens(s->m, tokens, 1, text_override, force)) return e;
     int32_t *h = s->h_in;
     h[0] = text_override;
     if (tokens) for (int i = 0; i < c.n_q + 1; i++) h[1 + i] = tokens[i];
@@ -1661,6 +1691,7 @@ extern "C" int msx_run_resident(msx_stream *s, const int32_t *frames, int n_fram
     const msx_config &c = s->m->cfg;
     CU(cudaSetDevice(s->m->device));
     const int n_in = c.n_q + 1, n_out = 1 + c.dep_q;
+    if (int e = check_tokens(s->m, frames, n_frames, INT32_MIN, nullptr)) return e;
     int32_t *d_feed = nullptr, *d_trace = nullptr;
     CU(cudaMalloc((void **)&d_feed, (size_t)n_frames * n_in * 4));
     if (out_tokens) CU(cudaMalloc((void **)&d_trace, (size_t)n_steps * n_out * 4));
@@ -1781,6 +1812,7 @@ extern "C" int msx_run_resident_async(msx_stream *s, const int32_t *frames, int 
     const msx_config &c = s->m->cfg;
     CU(cudaSetDevice(s->m->device));
     const int n_in = c.n_q + 1;
+    if (int e = check_tokens(s->m, frames, n_frames, INT32_MIN, nullptr)) return e;
     if (s->d_feed) { cudaFree(s->d_feed); s->d_feed = nullptr; }
     CU(cudaMalloc((void **)&s->d_feed, (size_t)n_frames * n_in * 4));
     CU(cudaMemcpy(s->d_feed, frames, (size_t)n_frames * n_in * 4, cudaMemcpyHostToDevice));
@@ -1827,7 +1859,21 @@ extern "C" int msx_stream_get_kv(msx_stream *s, int layer, int head, int slot, u
 // -------------------------------------------------------------------------------------------------
 // LMGen host logic (reference lm.h:715-743 state, lm.h:778-979 step; greedy, no state machine)
 // -------------------------------------------------------------------------------------------------
+// Per-generator libc random state.  The reference draws its Exp(1) noise with rand() (context.h:464-480), i.e. glibc's
+// process-global TYPE_3 additive-feedback generator; random_r on a private 128-byte state produces the same sequence for the
+// same seed (rand() before any srand() behaves like seed 1), so a single generator reproduces the reference's draws while
+// several generators / threads no longer perturb each other.
+struct GenRng {
+    struct random_data rd;
+    char state[128];
+    GenRng() { seed(1u); }
+    void seed(unsigned v) { memset(&rd, 0, sizeof(rd)); memset(state, 0, sizeof(state)); initstate_r(v, state, sizeof(state), &rd); }
+    int next() { int32_t r = 0; random_r(&rd, &r); return (int)r; }
+    float exp1() { return -logf(next() / (float)RAND_MAX); }
+};
+
 struct msx_gen {
+    GenRng rng;
     msx_stream *s = nullptr;
     msx_config cfg{};
     msx_step_fn fn = nullptr;         // host-logic tests: the model step is a caller-supplied callback
@@ -1877,7 +1923,7 @@ static void gen_init_impl(msx_gen *g, int delay_steps) {
     g->initial[0] = c.text_card;
 }
 extern "C" void msx_gen_free(msx_gen *g) { delete g; }
-extern "C" void msx_gen_seed(msx_gen *, unsigned seed) { srand(seed); }
+extern "C" void msx_gen_seed(msx_gen *g, unsigned seed) { if (g) g->rng.seed(seed); }
 extern "C" int msx_gen_offset(const msx_gen *g) { return g ? g->offset : -1; }
 extern "C" int msx_gen_max_delay(const msx_gen *g) { return g ? g->max_delay : -1; }
 
@@ -1886,6 +1932,16 @@ extern "C" int msx_gen_max_delay(const msx_gen *g) { return g ? g->max_delay : -
 extern "C" int msx_gen_prompt_embedding(msx_gen *g, const float *row) {
     if (!g || !row || !g->s) return fail(MSX_ERR_ARG, "null argument / callback generator");
     int32_t text = 0, audio[MSX_MAX_STEPS];
+    msx_stream *s = g->s; const msx_config &c = g->cfg;
+    if (s->temp_text > 0.f || s->temp_audio > 0.f) {
+        // the sampled graphs read this frame's Exp(1) noise: draw it exactly like msx_gen_step (and like the reference's
+        // moshi_lmgen_step_voice_prompt, whose two graphs consume kt + dep_q * ka draws per prompt frame)
+        const int kt = std::min(std::min(s->top_k_text, c.text_card), kSampleMaxK), ka = std::min(std::min(s->top_k_audio, c.card), kSampleMaxK);
+        std::vector<float> nt(kt), na((size_t)std::max(1, c.dep_q) * ka);
+        if (s->temp_text > 0.f) for (int i = 0; i < kt; i++) nt[i] = g->rng.exp1();
+        if (s->temp_audio > 0.f) for (size_t i = 0; i < (size_t)c.dep_q * ka; i++) na[i] = g->rng.exp1();
+        if (int e = msx_stream_set_noise(s, nt.data(), na.data())) return e;
+    }
     if (int e = msx_step_temporal_embedding(g->s, row, &text, nullptr, nullptr)) return e;
     if (g->cfg.dep_q > 0) if (int e = msx_step_depformer(g->s, 3, nullptr, audio, nullptr)) return e;
     g->offset++;
@@ -1921,7 +1977,7 @@ extern "C" int msx_gen_prefill(msx_gen *g, const int32_t *rows, int T) {
     if (g->s->temp_text > 0.f || g->s->temp_audio > 0.f) {
         const int kt = std::min(std::min(g->s->top_k_text, c.text_card), kSampleMaxK), ka = std::min(std::min(g->s->top_k_audio, c.card), kSampleMaxK);
         const long draws = (long)T * ((g->s->temp_text > 0.f ? kt : 0) + (g->s->temp_audio > 0.f ? (long)c.dep_q * ka : 0));
-        for (long i = 0; i < draws; i++) (void)rand();
+        for (long i = 0; i < draws; i++) (void)g->rng.next();
     }
     return 0;
 }
@@ -2010,8 +2066,8 @@ extern "C" int msx_gen_step(msx_gen *g, const int32_t *in_tokens, int n_in, int 
         // top-k candidate, text graph first, then the depformer codebooks in order
         const int kt = std::min(std::min(s->top_k_text, c.text_card), kSampleMaxK), ka = std::min(std::min(s->top_k_audio, c.card), kSampleMaxK);
         std::vector<float> nt(kt), na((size_t)std::max(1, c.dep_q) * ka);
-        if (s->temp_text > 0.f) for (int i = 0; i < kt; i++) nt[i] = -logf(rand() / (float)RAND_MAX);
-        if (s->temp_audio > 0.f && !depformer_replace_tokens) for (size_t i = 0; i < (size_t)c.dep_q * ka; i++) na[i] = -logf(rand() / (float)RAND_MAX);
+        if (s->temp_text > 0.f) for (int i = 0; i < kt; i++) nt[i] = g->rng.exp1();
+        if (s->temp_audio > 0.f && !depformer_replace_tokens) for (size_t i = 0; i < (size_t)c.dep_q * ka; i++) na[i] = g->rng.exp1();
         if (int e = msx_stream_set_noise(s, nt.data(), na.data())) return e;
     }
     if (g->fn) {
@@ -2224,7 +2280,7 @@ uint64_t out_tensor_bytes(const OutTensor &t) {
     return (uint64_t)ggml_row_size(t.dst_type, t.ne[0]) * (uint64_t)rows;
 }
 // GGUF v3, no key/value pairs (the reference writes none, loader.h:227-233), 32-byte alignment
-int write_gguf(msx_model *m, const std::vector<OutTensor> &ts, const char *out_path) {
+int write_gguf_impl(msx_model *m, const std::vector<OutTensor> &ts, const char *out_path) {
     std::vector<uint64_t> offset(ts.size()), nbytes(ts.size());
     uint64_t data_bytes = 0;
     for (size_t i = 0; i < ts.size(); i++) {
@@ -2272,6 +2328,12 @@ int write_gguf(msx_model *m, const std::vector<OutTensor> &ts, const char *out_p
     }
     if (!ok || fflush(o) != 0) return fail(MSX_ERR_IO, std::string("write failed: ") + out_path);
     return 0;
+}
+// a failed conversion never leaves a truncated output file behind
+int write_gguf(msx_model *m, const std::vector<OutTensor> &ts, const char *out_path) {
+    const int rc = write_gguf_impl(m, ts, out_path);
+    if (rc != 0) unlink(out_path);
+    return rc;
 }
 bool same_file(const char *a, const char *b) {
     struct stat sa, sb;
@@ -2324,15 +2386,16 @@ extern "C" int msx_safetensors_to_gguf(const char *in_path, const char *out_path
         const bool io = err.rfind("cannot open", 0) == 0 || err.rfind("cannot stat", 0) == 0 || err.rfind("cannot mmap", 0) == 0;
         return fail(io ? MSX_ERR_IO : MSX_ERR_FORMAT, err);
     }
-    std::unique_ptr<msx_model> m;
-    if (int e = device_setup(device, m)) return e;
-    std::vector<OutTensor> ts;
+    std::vector<OutTensor> ts;                  // the tensor list is validated on the host before the device is touched
     for (const SafeTensor &st : f.tensors()) {
         const int type = st.dtype == "F32" ? T_F32 : st.dtype == "F16" ? T_F16 : st.dtype == "BF16" ? T_BF16 : -1;
         if (type < 0) continue;      // integer / bool bookkeeping tensors: the reference's loader never fetches them, save_gguf never writes them
         if (st.shape.empty() || st.shape.size() > 4) return fail(MSX_ERR_FORMAT, "tensor " + st.name + " has unsupported rank");
         int64_t count = 1;
-        for (int64_t v : st.shape) count *= v;
+        for (int64_t v : st.shape) {
+            if (v <= 0 || v > ((int64_t)1 << 40) || count > ((int64_t)1 << 46) / v) return fail(MSX_ERR_FORMAT, "tensor " + st.name + ": bad shape");
+            count *= v;
+        }
         if ((uint64_t)count * (type == T_F32 ? 4 : 2) != st.nbytes) return fail(MSX_ERR_FORMAT, "tensor " + st.name + ": shape does not match its bytes");
         const std::string name = "lm." + st.name;
         const int64_t K = st.shape.back();
@@ -2354,6 +2417,8 @@ extern "C" int msx_safetensors_to_gguf(const char *in_path, const char *out_path
             ts.push_back(std::move(t));
         }
     }
+    std::unique_ptr<msx_model> m;
+    if (int e = device_setup(device, m)) return e;
     return write_gguf(m.get(), ts, out_path);
 }
 

@@ -465,6 +465,14 @@ __device__ __forceinline__ void gemv_body(const GemvArgs &a, const float *x_over
         if (i < n_steps) { issue_step<WT, LANES>(a.w, ring_u32 + i * kSlotBytes, ring + i * kSlotBytes, prod, l, lane, P); advance<LANES>(prod, nit, row_stride); }
         cp_async_commit();
     }
+    if (PDL && PRO == PRO_RMS) {
+        // the RMSNorm weights do not depend on the predecessor either, and after a frame's 4 GB of weights they come from HBM:
+        // pull this warp's blocks into L2 while the predecessor drains, so the loads after the wait are L2 hits
+        for (int b = warp; b * 256 < K; b += bg.nwarps) {
+            const float *ap = a.alpha + b * 256 + lane * 8;
+            if (b * 256 + lane * 8 < K) asm volatile("prefetch.global.L2 [%0];" ::"l"(ap));
+        }
+    }
     if (PDL) griddep_wait();
     mid();
 

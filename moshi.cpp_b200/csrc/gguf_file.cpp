@@ -69,6 +69,7 @@ bool skip_value(Cursor &c, uint32_t t, uint32_t *align_out, bool is_align) {
         if (!c.ok) return false;
         if (et == V_STR) { for (uint64_t i = 0; i < n && c.ok; i++) c.str(); return c.ok; }
         size_t es = scalar_size(et); if (!es) return false;
+        if (n > (uint64_t)(c.end - c.p) / es) { c.ok = false; return false; }      // n * es cannot wrap
         c.skip(n * es); return c.ok;
     }
     size_t s = scalar_size(t); if (!s) return false;
@@ -93,6 +94,8 @@ bool GgufFile::open(const std::string &path, std::string &err) {
     version_ = (int)c.get<uint32_t>();
     if (version_ != 2 && version_ != 3) { err = "unsupported GGUF version " + std::to_string(version_); return false; }
     uint64_t n_tensors = c.get<uint64_t>(), n_kv = c.get<uint64_t>();
+    // header counts come from the (downloaded) file: every key / tensor record takes at least 12 / 24 bytes of it
+    if (!c.ok || n_kv > size_ / 12 || n_tensors > size_ / 24) { err = "corrupt GGUF header (tensor / key counts exceed the file size)"; return false; }
     uint32_t alignment = 32;
     for (uint64_t i = 0; i < n_kv; i++) {
         std::string key = c.str();
@@ -106,19 +109,28 @@ bool GgufFile::open(const std::string &path, std::string &err) {
         t.name = c.str();
         t.n_dims = (int)c.get<uint32_t>();
         if (!c.ok || t.n_dims < 1 || t.n_dims > 4) { err = "corrupt GGUF tensor info"; return false; }
-        for (int d = 0; d < t.n_dims; d++) t.ne[d] = (int64_t)c.get<uint64_t>();
+        for (int d = 0; d < t.n_dims; d++) {
+            const uint64_t v = c.get<uint64_t>();
+            if (!c.ok || v == 0 || v > (uint64_t)1 << 40) { err = "corrupt GGUF tensor info (dimension of " + t.name + ")"; return false; }
+            t.ne[d] = (int64_t)v;
+        }
         t.type = (int)c.get<uint32_t>();
         t.offset = c.get<uint64_t>();
         if (!c.ok) { err = "corrupt GGUF tensor info"; return false; }
     }
     size_t hdr = (size_t)(c.p - map_);
     size_t data_off = (hdr + alignment - 1) / alignment * alignment;
+    if (data_off > size_) { err = "corrupt GGUF header (no tensor data)"; return false; }
+    const uint64_t data_bytes = size_ - data_off;
     for (auto &t : tensors_) {
         int64_t rs = ggml_row_size(t.type, t.ne[0]);
         if (rs < 0) { t.data = nullptr; t.nbytes = -1; }   // unsupported type: only an error if the LM needs it
         else {
-            t.nbytes = rs * t.ne[1] * t.ne[2] * t.ne[3];
-            if (data_off + t.offset + (uint64_t)t.nbytes > size_) { err = "GGUF tensor " + t.name + " exceeds file size"; return false; }
+            // checked product (dimensions are <= 2^40 each, the file is far smaller than 2^63 bytes)
+            unsigned __int128 nb = (unsigned __int128)(uint64_t)rs;
+            for (int d = 1; d < 4; d++) { nb *= (uint64_t)t.ne[d]; if (nb > data_bytes) break; }
+            if (nb > data_bytes || t.offset > data_bytes - (uint64_t)nb) { err = "GGUF tensor " + t.name + " exceeds file size"; return false; }
+            t.nbytes = (int64_t)nb;
             t.data = map_ + data_off + t.offset;
         }
         index_[t.name] = (size_t)(&t - tensors_.data());

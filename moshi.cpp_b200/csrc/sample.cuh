@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(kSampleThreads) sample_kernel(const SampleArgs
     }
     // ---- multinomial: argmax_j p_j / e_j (first maximum) ----
     if (warp == 0) {
-        float best = -INFINITY; int bestj = 0x7fffffff;
+        float best = -INFINITY; int bestj = 0;      // (all-NaN candidates fall back to the most probable one)
         for (int j = lane; j < a.k; j += 32) {
             const float p = __uint_as_float((unsigned)(s_keys[j] >> 32));
             const float q = p / a.noise[j];
@@ -150,6 +150,7 @@ __global__ void __launch_bounds__(kSampleThreads) sample_kernel(const SampleArgs
             const float ob = __shfl_xor_sync(0xffffffffu, best, o);
             const int oj = __shfl_xor_sync(0xffffffffu, bestj, o);
             if (ob > best || (ob == best && oj < bestj)) { best = ob; bestj = oj; }
+            bestj = min(bestj, a.k - 1);
         }
         if (lane == 0) {
             const int token = (int)(0xffffffffu - (unsigned)(s_keys[bestj] & 0xffffffffull));

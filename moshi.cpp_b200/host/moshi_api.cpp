@@ -518,9 +518,15 @@ int moshi_lm_receive(moshi_lm_gen_t *gen, int &text_token, std::vector<int16_t> 
     if (!gen->gen) return 0;
     const msx_config &c = gen->lm->cfg;
     const int replace = msx_gen_offset(gen->gen) < gen->lm->delay_steps;                 // moshi.cpp:905
-    int32_t out[MSX_MAX_STEPS], text = 0;
+    int32_t out[MSX_MAX_STEPS] = {0}, text = 0;
     const int rc = msx_gen_step(gen->gen, gen->audio_tokens.data(), (int)gen->audio_tokens.size(), replace, &text, out);
     audio_tokens.resize(c.dep_q);
+    if (rc < 0) {
+        // a failed step (bad token id, CUDA error) must not feed whatever is in `out` into the next frame; the reference would
+        // have asserted — here the previous tokens stay, the error is reported and the caller sees a negative code
+        fprintf(stderr, "moshi_lm_receive: %s\n", msx_last_error());
+        return rc;
+    }
     if (rc == 1) { text_token = text; for (int i = 0; i < c.dep_q; i++) audio_tokens[i] = (int16_t)out[i]; }
     // like the reference, the generated row becomes the "sent" tokens of the next call unless send2 overwrites them
     gen->audio_tokens.assign(out, out + c.dep_q);
@@ -529,7 +535,11 @@ int moshi_lm_receive(moshi_lm_gen_t *gen, int &text_token, std::vector<int16_t> 
 
 void moshi_lm_receive2(moshi_lm_gen_t *gen, int &text_token, float &vad) {
     if (!gen->gen) return;
-    int32_t out[MSX_MAX_STEPS], text = 0;
-    if (msx_gen_step(gen->gen, gen->audio_tokens.data(), (int)gen->audio_tokens.size(), 0, &text, out) == 1) text_token = text;
-    msx_vad(gen->stream, &vad);
+    int32_t out[MSX_MAX_STEPS] = {0}, text = 0;
+    const int rc = msx_gen_step(gen->gen, gen->audio_tokens.data(), (int)gen->audio_tokens.size(), 0, &text, out);
+    if (rc < 0) { fprintf(stderr, "moshi_lm_receive2: %s\n", msx_last_error()); return; }
+    if (rc == 1) {                       // the reference evaluates the VAD head only on frames that emit (lm.h:950-977)
+        text_token = text;
+        msx_vad(gen->stream, &vad);
+    }
 }

@@ -312,6 +312,39 @@ def test_errors(msx, gguf_for, tmp_path):
     assert e.value.code == -3
 
 
+def test_out_of_range_tokens_are_rejected(msx, gguf_for):
+    """token ids index embedding tables on the device: ids outside a table are refused on the host with MSX_ERR_ARG (-1) on
+    every input path (per-frame steps, depformer overrides, resident replay, batch, prefill) and the stream keeps working
+    (a stray id used to read device memory out of bounds)."""
+    path, cfg = gguf_for("tiny", "q4_k")
+    gm = msx.Model(path, cfg); gs = msx.Stream(gm)
+    good = np.array([cfg["text_card"]] + [cfg["card"]] * cfg["n_q"], dtype=np.int32)
+    t0, _, _ = gs.step_temporal(good)
+    for pos, val in ((0, cfg["text_card"] + 1), (0, -3), (3, cfg["card"] + 1), (cfg["n_q"], 1 << 30), (5, -7)):
+        bad = good.copy(); bad[pos] = val
+        for call in (lambda: gs.step_temporal(bad), lambda: gs.step(bad), lambda: gs.run_resident(np.stack([good, bad]), 2),
+                     lambda: gs.prefill(np.stack([good, bad]))):
+            with pytest.raises(msx.MsxError) as e:
+                call()
+            assert e.value.code == -1
+    for call in (lambda: gs.step_depformer(cfg["text_card"] + 1), lambda: gs.step_depformer(3, force=[cfg["card"] + 1] * cfg["dep_q"]),
+                 lambda: gs.step_depformer(3, force=[-1] * cfg["dep_q"])):
+        with pytest.raises(msx.MsxError) as e:
+            call()
+        assert e.value.code == -1
+    batch = msx.Batch(gm, 2)
+    bad = good.copy(); bad[2] = cfg["card"] + 5
+    with pytest.raises(msx.MsxError) as e:
+        batch.step(np.stack([good, bad]))
+    assert e.value.code == -1
+    gs.reset()
+    t1, _, _ = gs.step_temporal(good)
+    assert t1 == t0                                           # nothing was consumed or corrupted by the refused calls
+    for tok in (-1, -2):                                      # the two negative ids the reference defines stay legal
+        ok = good.copy(); ok[1] = tok
+        gs.step_temporal(ok)
+
+
 @pytest.mark.parametrize("preset,quant", [("tiny", "q4_k"), ("tiny_pplex", "q8_0"), ("moshi7b_l2", "q4_k")])
 def test_step_kernel_matches_launch_chain(msx, gguf_for, preset, quant):
     """The persistent step kernels and the one-launch-per-op path share their arithmetic and accumulate order-independently:

@@ -94,6 +94,54 @@ def test_loader_errors_before_device(gguf_for, tmp_path):
         assert e.value.code == -3
 
 
+def _gguf(n_tensors, n_kv, infos=b"", pad=64):
+    """hand-made GGUF v3 header: magic, version, tensor count, key count, raw tensor-info bytes, zero padding"""
+    return b"GGUF" + (3).to_bytes(4, "little") + n_tensors.to_bytes(8, "little") + n_kv.to_bytes(8, "little") + infos + b"\0" * pad
+
+
+def _info(name, ne, ggml_type, offset):
+    b = len(name).to_bytes(8, "little") + name.encode() + len(ne).to_bytes(4, "little")
+    for v in ne:
+        b += v.to_bytes(8, "little")
+    return b + ggml_type.to_bytes(4, "little") + offset.to_bytes(8, "little")
+
+
+def test_hostile_gguf_headers_are_rejected(gguf_for, tmp_path):
+    """header fields of a (downloaded) model file are untrusted: counts beyond the file, zero / huge dimensions, sizes that
+    wrap and offsets outside the mapping all end in MSX_ERR_FORMAT (-3) — no allocation of attacker-chosen size, no abort,
+    no pointer outside the mmap."""
+    _, cfg = gguf_for("tiny", "q4_k")
+    cases = {
+        "huge_tensor_count": _gguf(1 << 60, 0),
+        "huge_key_count": _gguf(0, 1 << 61),
+        "zero_dim": _gguf(1, 0, _info("lm.text_emb.weight", [0, 7], 0, 0)),
+        "huge_dim": _gguf(1, 0, _info("lm.text_emb.weight", [1 << 62, 1 << 62], 0, 0)),
+        "size_wraps": _gguf(1, 0, _info("lm.text_emb.weight", [1 << 33, 1 << 33, 1 << 33, 1 << 33], 0, 0)),
+        "offset_wraps": _gguf(1, 0, _info("lm.text_emb.weight", [4, 2], 0, (1 << 64) - 16)),
+        "offset_past_end": _gguf(1, 0, _info("lm.text_emb.weight", [4, 2], 0, 1 << 20)),
+        "array_value_wraps": b"GGUF" + (3).to_bytes(4, "little") + (0).to_bytes(8, "little") + (1).to_bytes(8, "little")
+                             + (1).to_bytes(8, "little") + b"k" + (9).to_bytes(4, "little") + (10).to_bytes(4, "little") + ((1 << 62) + 1).to_bytes(8, "little") + b"\0" * 64,
+    }
+    for name, blob in cases.items():
+        f = tmp_path / f"{name}.gguf"; f.write_bytes(blob)
+        with pytest.raises(msx.MsxError) as e:
+            msx.Model(str(f), cfg)
+        assert e.value.code == -3, name
+        with pytest.raises(msx.MsxError) as e:
+            msx.gguf_quantize(str(f), str(tmp_path / "out.gguf"), "q8_0")
+        assert e.value.code == -3, name
+        assert not (tmp_path / "out.gguf").exists()
+    # safetensors converter: zero dimension (division by zero in the reference's split logic) and overflowing shapes
+    for shape in ([3, 0], [1 << 40, 1 << 40]):
+        hdr = ('{"self_attn.in_proj_weight":{"dtype":"F32","shape":%s,"data_offsets":[0,0]}}' % str(shape).replace(" ", "")).encode()
+        hdr += b" " * (-len(hdr) % 8)
+        st = tmp_path / "z.safetensors"; st.write_bytes(len(hdr).to_bytes(8, "little") + hdr)
+        with pytest.raises(msx.MsxError) as e:
+            msx.safetensors_to_gguf(str(st), str(tmp_path / "out.gguf"), "q8_0")
+        assert e.value.code == -3, shape
+        assert not (tmp_path / "out.gguf").exists()
+
+
 def test_gguf_roundtrip_with_gguf_py(gguf_for):
     from gguf import GGUFReader
     path, cfg = gguf_for("tiny", "q8_0")
