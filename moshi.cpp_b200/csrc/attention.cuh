@@ -45,14 +45,25 @@ struct AttnArgs {
 };
 
 constexpr int kAttnMaxSplit = 8;
+// K / V rows of the valid slots stream through a shared-memory ring of kAttnRing chunks of kAttnChunkRows rows, filled with
+// cp.async.bulk (TMA) + mbarrier completion: the rows of a (head, split) are contiguous in the ring cache [H][cap][DH], so a
+// chunk is ONE bulk copy.  The K chunks are followed by the V chunks of the same rows; the first kAttnRing chunks are
+// requested at kernel entry, BEFORE the PDL wait (ring rows of earlier frames do not depend on the predecessor), and the V
+// chunks land while the row maximum / row sum travel across the cluster, so the HBM stream does not stop at the softmax.
+// (Round 1 fetched 8 rows per lane group per round trip through registers and reached 28 % of the measured HBM peak with a
+// full 3000-slot ring; see profiles/r2_attention.md.)
+constexpr int kAttnRing = 6;
+constexpr int kAttnChunkRows = 32;
 
-// shared-memory layout (bytes): x_sum[8] f64 | red[8] f64 | x_ctx[8][DH] f64 | part[NG][DH] f64 |
-//                               q[DH] f32 | knew,vnew [2*DH] bf16 | x_max[8] f32 | scores[per] f32
+// shared-memory layout (bytes): ring[kAttnRing][32][DH] bf16 | full[R], empty[R] mbarriers | x_sum[8] f64 | red[8] f64 |
+//                               x_ctx[8][DH] f64 | part[NG][DH] f64 | q[DH] f32 | knew,vnew [2*DH] bf16 | x_max[8] f32 | scores[per] f32
+template <int DH>
+__host__ __device__ inline int attn_ring_bytes() { return kAttnRing * kAttnChunkRows * DH * 2 + 128; }
 template <int DH>
 __host__ __device__ inline int attn_smem_bytes(int cap, int S) {
     const int per = (cap + S - 1) / S + 1;
     const int ng = kThreads / (DH / 8);
-    return (64 + 64 + kAttnMaxSplit * DH * 8 + ng * DH * 8 + DH * 4 + DH * 4 + 32 + per * 4 + 15) / 16 * 16;
+    return attn_ring_bytes<DH>() + (64 + 64 + kAttnMaxSplit * DH * 8 + ng * DH * 8 + DH * 4 + DH * 4 + 32 + per * 4 + 15) / 16 * 16;
 }
 
 // q' (bf16-rounded, RoPE'd), and the bf16 K / V rows of this step for head h; threads tid < DH/2 work
@@ -97,7 +108,9 @@ __global__ void __launch_bounds__(kThreads) attn_kernel(const AttnArgs a0) {
         a.ctrl += b; if (a.rope_cs) a.rope_cs += (size_t)b * DH;
     }
     constexpr int LPS = DH / 8;             // lanes per slot (8 dims = 16 B of bf16 each)
-    constexpr int NG = kThreads / LPS;      // slots in flight per CTA iteration
+    constexpr int NG = kThreads / LPS;      // slots per pass over a chunk
+    constexpr int CH = kAttnChunkRows, CHB = CH * DH * 2;
+    static_assert(CH % NG == 0 || NG % CH == 0, "chunk / group geometry");
     griddep_launch();
     int S = gridDim.x, c = blockIdx.x;
     const int h = blockIdx.y;
@@ -113,21 +126,14 @@ __global__ void __launch_bounds__(kThreads) attn_kernel(const AttnArgs a0) {
     // (uniform decision across the cluster, so nobody waits at a barrier)
     const bool use_cluster = CLUSTER && n_valid > min(a.small_ctx, per - 1);
     if (CLUSTER && !use_cluster) { if (c != 0) return; S = 1; c = 0; }
-    {
-        // the ring rows of earlier frames do not depend on the previous kernel either: pull this CTA's first K / V rows into
-        // L2 while that kernel drains (between frames the 4 GB weight stream evicts them, so they come from HBM)
-        const int plo = (int)((long long)n_valid * c / S), phi = (int)((long long)n_valid * (c + 1) / S);
-        constexpr int LPR = DH * 2 / 128;            // 128-byte lines per row
-        const int n_lines = min(phi - plo, 128) * 2 * LPR;
-        for (int j = tid; j < n_lines; j += kThreads) {
-            const int r = plo + j / (2 * LPR), part = j % (2 * LPR);
-            const uint16_t *p = (part < LPR ? a.kc : a.vc) + ((size_t)h * cap + r) * DH + (part % LPR) * 64;
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-        }
-    }
-    griddep_wait();        // qkv comes from the previous kernel (PDL)
+    const int lo = (int)((long long)n_valid * c / S), hi = (int)((long long)n_valid * (c + 1) / S);
+    const int n_ck = (hi - lo + CH - 1) / CH, n_chunks = 2 * n_ck;      // K chunks, then V chunks of the same rows
 
-    double *x_sum = reinterpret_cast<double *>(smem);                  // [kAttnMaxSplit] cluster exchange: row sums
+    uint8_t *ring = smem;
+    const uint32_t ring_u32 = (uint32_t)__cvta_generic_to_shared(ring);
+    const uint32_t bars = ring_u32 + kAttnRing * CHB;                    // full[R] then empty[R]
+    uint8_t *rest = smem + attn_ring_bytes<DH>();
+    double *x_sum = reinterpret_cast<double *>(rest);                  // [kAttnMaxSplit] cluster exchange: row sums
     double *dred = x_sum + kAttnMaxSplit;                              // [8] block reduce scratch
     float *red = reinterpret_cast<float *>(dred);                      // aliases dred (used at different times)
     double *x_ctx = dred + 8;                                          // [kAttnMaxSplit][DH] cluster exchange: partial contexts
@@ -138,6 +144,36 @@ __global__ void __launch_bounds__(kThreads) attn_kernel(const AttnArgs a0) {
     float *x_max = reinterpret_cast<float *>(vnew + DH);               // [kAttnMaxSplit] cluster exchange: row maxima
     float *sc_s = x_max + kAttnMaxSplit;                               // [per]
     (void)per;
+
+    // chunk j of the stream: rows [lo + (j % n_ck) * CH, ...) of K (j < n_ck) or V
+    auto issue = [&](int j) {
+        const int jj = j < n_ck ? j : j - n_ck;
+        const int r0 = lo + jj * CH, nr = min(CH, hi - r0);
+        const uint16_t *src = (j < n_ck ? a.kc : a.vc) + ((size_t)h * cap + r0) * DH;
+        const uint32_t s = (uint32_t)(j % kAttnRing);
+        mbar_expect_tx(bars + s * 8, (uint32_t)nr * DH * 2);
+        bulk_g2s(ring_u32 + s * CHB, src, (uint32_t)nr * DH * 2, bars + s * 8);
+    };
+    if (tid == 0) {
+        for (int s = 0; s < kAttnRing; s++) { mbar_init(bars + s * 8, 1); mbar_init(bars + (kAttnRing + s) * 8, kWarps); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        // (batched-T prefill: the rows of this pass's other columns are written by the kv_insert kernel right before us)
+        if (!a.skip_insert) for (int j = 0; j < min(kAttnRing, n_chunks); j++) issue(j);
+    }
+    __syncthreads();       // barriers initialised before anybody waits on them
+    griddep_wait();        // qkv comes from the previous kernel (PDL)
+    if (tid == 0 && a.skip_insert) for (int j = 0; j < min(kAttnRing, n_chunks); j++) issue(j);
+
+    // every warp arrives on empty[slot] when it is done with chunk j; thread 0 then refills the slot with chunk j + kAttnRing
+    auto release = [&](int j) {
+        __syncwarp();
+        const uint32_t s = (uint32_t)(j % kAttnRing);
+        if (lane == 0) mbar_arrive(bars + (kAttnRing + s) * 8);
+        if (tid == 0 && j + kAttnRing < n_chunks) {
+            mbar_wait(bars + (kAttnRing + s) * 8, (uint32_t)((j / kAttnRing) & 1));
+            issue(j + kAttnRing);
+        }
+    };
 
     // ---- 1. RoPE (interleaved pairs -> [re half | im half]) and the new K/V row -------------------
     rope_rows<DH>(a, h, pos, tid, q_s, knew, vnew);
@@ -153,36 +189,26 @@ __global__ void __launch_bounds__(kThreads) attn_kernel(const AttnArgs a0) {
     }
 
     // ---- 2. scores over this CTA's share of the valid slots ----------------------------------------
-    const int lo = (int)((long long)n_valid * c / S), hi = (int)((long long)n_valid * (c + 1) / S);
     const int g = tid / LPS, sl = tid % LPS;
     const float scale = 1.f / sqrtf((float)DH);
     float qv[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) qv[i] = q_s[sl * 8 + i];
     float lmax = -INFINITY;
-    // U slots per group and iteration: all U key rows are requested before the first is used, so the
-    // (HBM-latency-bound) loop pays one round trip per U slots.  Trip count is warp-uniform (shuffles below).
-    constexpr int U = 8;
-    for (int i0 = lo; i0 < hi; i0 += NG * U) {
-        uint4 kk[U];
+    for (int j = 0; j < n_ck; j++) {
+        mbar_wait(bars + (j % kAttnRing) * 8, (uint32_t)((j / kAttnRing) & 1));
+        const uint16_t *ck = reinterpret_cast<const uint16_t *>(ring + (j % kAttnRing) * CHB);
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-            const int i = i0 + u * NG + g;
-            kk[u] = make_uint4(0, 0, 0, 0);
-            if (i < hi) {
-                if (i == slot) kk[u] = reinterpret_cast<const uint4 *>(knew)[sl];
-                else kk[u] = *reinterpret_cast<const uint4 *>(a.kc + ((size_t)h * cap + i) * DH + sl * 8);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            const int i = i0 + u * NG + g;
+        for (int r = g; r < CH; r += NG) {
+            const int i = lo + j * CH + r;
+            uint4 kk = make_uint4(0, 0, 0, 0);
+            if (i < hi) kk = (i == slot && !a.skip_insert) ? reinterpret_cast<const uint4 *>(knew)[sl] : reinterpret_cast<const uint4 *>(ck + r * DH)[sl];
             // bf16 x bf16 products are exact in fp32; they are summed in double (order-independent)
             double d = 0.0;
-            d += (double)(bf16_bits_to_f32(kk[u].x & 0xffff) * qv[0]); d += (double)(bf16_bits_to_f32(kk[u].x >> 16) * qv[1]);
-            d += (double)(bf16_bits_to_f32(kk[u].y & 0xffff) * qv[2]); d += (double)(bf16_bits_to_f32(kk[u].y >> 16) * qv[3]);
-            d += (double)(bf16_bits_to_f32(kk[u].z & 0xffff) * qv[4]); d += (double)(bf16_bits_to_f32(kk[u].z >> 16) * qv[5]);
-            d += (double)(bf16_bits_to_f32(kk[u].w & 0xffff) * qv[6]); d += (double)(bf16_bits_to_f32(kk[u].w >> 16) * qv[7]);
+            d += (double)(bf16_bits_to_f32(kk.x & 0xffff) * qv[0]); d += (double)(bf16_bits_to_f32(kk.x >> 16) * qv[1]);
+            d += (double)(bf16_bits_to_f32(kk.y & 0xffff) * qv[2]); d += (double)(bf16_bits_to_f32(kk.y >> 16) * qv[3]);
+            d += (double)(bf16_bits_to_f32(kk.z & 0xffff) * qv[4]); d += (double)(bf16_bits_to_f32(kk.z >> 16) * qv[5]);
+            d += (double)(bf16_bits_to_f32(kk.w & 0xffff) * qv[6]); d += (double)(bf16_bits_to_f32(kk.w >> 16) * qv[7]);
 #pragma unroll
             for (int o = LPS / 2; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
             const float sv = (float)d * scale + 0.0f;
@@ -191,6 +217,7 @@ __global__ void __launch_bounds__(kThreads) attn_kernel(const AttnArgs a0) {
                 lmax = fmaxf(lmax, sv);
             }
         }
+        release(j);
     }
     lmax = warp_max(lmax);
     if (lane == 0) red[warp] = lmax;
@@ -234,28 +261,22 @@ __global__ void __launch_bounds__(kThreads) attn_kernel(const AttnArgs a0) {
     double acc[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) acc[i] = 0.0;
-    for (int i0 = lo + g; i0 < hi; i0 += NG * U) {
-        uint4 vv[U];
+    for (int j = n_ck; j < n_chunks; j++) {
+        mbar_wait(bars + (j % kAttnRing) * 8, (uint32_t)((j / kAttnRing) & 1));
+        const uint16_t *ck = reinterpret_cast<const uint16_t *>(ring + (j % kAttnRing) * CHB);
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-            const int i = i0 + u * NG;
-            vv[u] = make_uint4(0, 0, 0, 0);
+        for (int r = g; r < CH; r += NG) {
+            const int i = lo + (j - n_ck) * CH + r;
             if (i < hi) {
-                if (i == slot) vv[u] = reinterpret_cast<const uint4 *>(vnew)[sl];
-                else vv[u] = *reinterpret_cast<const uint4 *>(a.vc + ((size_t)h * cap + i) * DH + sl * 8);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            const int i = i0 + u * NG;
-            if (i < hi) {
+                const uint4 vv = (i == slot && !a.skip_insert) ? reinterpret_cast<const uint4 *>(vnew)[sl] : reinterpret_cast<const uint4 *>(ck + r * DH)[sl];
                 const float p = bf16_round(sc_s[i - lo] * inv);
-                acc[0] += (double)(bf16_bits_to_f32(vv[u].x & 0xffff) * p); acc[1] += (double)(bf16_bits_to_f32(vv[u].x >> 16) * p);
-                acc[2] += (double)(bf16_bits_to_f32(vv[u].y & 0xffff) * p); acc[3] += (double)(bf16_bits_to_f32(vv[u].y >> 16) * p);
-                acc[4] += (double)(bf16_bits_to_f32(vv[u].z & 0xffff) * p); acc[5] += (double)(bf16_bits_to_f32(vv[u].z >> 16) * p);
-                acc[6] += (double)(bf16_bits_to_f32(vv[u].w & 0xffff) * p); acc[7] += (double)(bf16_bits_to_f32(vv[u].w >> 16) * p);
+                acc[0] += (double)(bf16_bits_to_f32(vv.x & 0xffff) * p); acc[1] += (double)(bf16_bits_to_f32(vv.x >> 16) * p);
+                acc[2] += (double)(bf16_bits_to_f32(vv.y & 0xffff) * p); acc[3] += (double)(bf16_bits_to_f32(vv.y >> 16) * p);
+                acc[4] += (double)(bf16_bits_to_f32(vv.z & 0xffff) * p); acc[5] += (double)(bf16_bits_to_f32(vv.z >> 16) * p);
+                acc[6] += (double)(bf16_bits_to_f32(vv.w & 0xffff) * p); acc[7] += (double)(bf16_bits_to_f32(vv.w >> 16) * p);
             }
         }
+        release(j);
     }
 #pragma unroll
     for (int i = 0; i < 8; i++) part[g * DH + sl * 8 + i] = acc[i];

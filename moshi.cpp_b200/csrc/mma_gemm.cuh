@@ -357,21 +357,6 @@ struct GemmArgs {
 constexpr int kFusedMaxPairs = 4;     // (column, 256-block) pairs per warp in the fused prologue
 __host__ __device__ inline bool gemm_can_fuse_quant(int K, int nb) { return (K >> 8) * nb <= kGemmWarps * kFusedMaxPairs && K <= 1024; }
 
-__device__ __forceinline__ void mbar_init(uint32_t addr, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count) : "memory"); }
-__device__ __forceinline__ void mbar_expect_tx(uint32_t addr, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(addr), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t mbar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t addr, uint32_t parity) {
-    uint32_t ok;
-    do {
-        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
-    } while (!ok);
-}
 __device__ __forceinline__ void mma_u8s8(int (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
     asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
                  : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3])

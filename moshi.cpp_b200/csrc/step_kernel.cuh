@@ -888,7 +888,7 @@ __device__ __forceinline__ void attn_phase(const StepPhase &ph, const StepArgs &
 // ---- the kernel ----------------------------------------------------------------------------------------------------------
 template <int WT>
 __global__ void __launch_bounds__(kThreads, 1) step_kernel(const StepArgs a) {
-    extern __shared__ __align__(128) uint8_t smem[];
+    extern __shared__ __align__(16) uint8_t smem[];
     __shared__ __align__(16) StepPhase s_ph[2];
     volatile int *abort_flag = reinterpret_cast<volatile int *>(smem + kOffMisc);
     const int tid = threadIdx.x, cta = blockIdx.x;
