@@ -48,47 +48,82 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed regions run."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock / power / throttle reasons sampled every few milliseconds WHILE the timed regions run (NVML in a thread; the
+    timed regions of a default run last tens of milliseconds, far below nvidia-smi's 200 ms polling period)."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
-    def __init__(self, gpu_index: int):
-        self.gpu_index, self.lines, self.proc, self.t = gpu_index, [], None, None
+    def __init__(self, gpu_index: int, period_s: float = 0.004):
+        self.gpu_index, self.period, self.samples, self.stop_flag, self.t, self.err = gpu_index, period_s, [], False, None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # CUDA_VISIBLE_DEVICES remaps CUDA ordinals; NVML sees physical indices
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = gpu_index
+            if vis:
+                ids = [v.strip() for v in vis.split(",") if v.strip()]
+                if gpu_index < len(ids) and ids[gpu_index].isdigit():
+                    phys = int(ids[gpu_index])
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(phys)
+        except Exception as e:                       # noqa: BLE001
+            self.nv, self.h, self.err = None, None, f"NVML unavailable: {e}"
+
+    def _loop(self):
+        nv, h = self.nv, self.h
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.samples.append((sm, pw, int(rs)))
+            except Exception as e:                   # noqa: BLE001
+                self.err = str(e); return
+            time.sleep(self.period)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.gpu_index)],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-        except OSError:
+        if self.nv is None:
             return
-        self.t = threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True)
+        self.t = threading.Thread(target=self._loop, daemon=True)
         self.t.start()
 
     def stop(self) -> dict:
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
+        if self.nv is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [self.err or "NVML unavailable"]}
+        self.stop_flag = True
+        self.t.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [self.err or "no samples"]}
+        sm = [x[0] for x in self.samples]
         try:
-            self.proc.wait(timeout=3)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons, pw = [], [], set(), []
-        for l in self.lines:
-            f = [x.strip() for x in l.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        busy = [s for s in sm if s > 0.5 * max(sm)] or sm
-        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
-                "samples": len(sm), "reasons": sorted(reasons)}
+            mx = float(self.nv.nvmlDeviceGetMaxClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+        except Exception:                            # noqa: BLE001
+            mx = float(max(sm))
+        bits = 0
+        for x in self.samples:
+            bits |= x[2]
+        busy = [v for v in sm if v > 0.5 * max(sm)] or sm
+        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": mx, "power_w_max": float(max(x[1] for x in self.samples)),
+                "samples": len(sm), "reasons": sorted(n for b, n in self.REASONS.items() if bits & b), "how": "NVML, 4 ms period, timed regions only"}
+
+
+def stored_bytes(quant: str, K: int, rows: int) -> int:
+    """bytes one launch of the GEMV reads from the repacked planes: q4_k stores 148 B per 256 weights"""
+    return rows * (K // 256) * 148 if quant == "q4_k" else rows * (K // 32) * 34
+
+
+def committed_traffic(kernel: str, quant: str, K: int, rows: int):
+    """DRAM bytes per launch measured by ncu for this kernel / shape (profiles/kernel_traffic.json, written from a --set full
+    capture), or None when no capture matches the layout this build stores — a stale number is worse than none"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "kernel_traffic.json")) as f:
+            for e in json.load(f)["captures"]:
+                if e["kernel"] == kernel and e["quant"] == quant and e["K"] == K and e["rows"] == rows and \
+                        e["stored_bytes_per_launch"] == stored_bytes(quant, K, rows):
+                    return e["dram_bytes_read"] + e["dram_bytes_write"]
+    except (OSError, KeyError, ValueError):
+        pass
+    return None
 
 
 def make_frames(cfg, n=64):
@@ -120,10 +155,21 @@ def tts_condition(cfg, tc=125):
     return (0.2 * rng.standard_normal(cfg["dim"])).astype(np.float32), rng.standard_normal((tc, cfg["dim"])).astype(np.float32)
 
 
+def host_threads() -> int:
+    """cores this process may run on (torchrun pins nothing but exports OMP_NUM_THREADS=1, which must not decide this)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def cpu_reference_fps(path, cfg, frames, max_frames, budget_s):
-    """The oracle (CPU restatement of the reference's ggml-CPU path) on the host cores, greedy LMGen."""
+    """The oracle (CPU restatement of the reference's ggml-CPU path) on the host cores, greedy LMGen.
+    -> (frames/s, frames timed, seconds, OpenMP threads actually used, emitted tokens per frame [(ok, text, audio...)])"""
     import oracle
+    threads = oracle.set_threads(host_threads())       # explicit: OMP_NUM_THREADS=1 under torchrun would otherwise win
     om = oracle.Model(path, cfg)
+    trace = []
     if cfg.get("cross_attention"):                      # TTS: the same two graphs per frame on a conditioned state
         st = oracle.State(om)
         st.set_condition(*tts_condition(cfg))
@@ -133,12 +179,14 @@ def cpu_reference_fps(path, cfg, frames, max_frames, budget_s):
             nonlocal toks
             t, _, _ = st.step_temporal(toks)
             a, _ = st.step_depformer(t)
+            trace.append((1, int(t)) + tuple(int(v) for v in a))
             toks = np.array([t] + list(a) + [0] * (cfg["n_q"] - len(a)), dtype=np.int32)
     else:
         og = oracle.LMGen(om)
 
         def step(i):
-            og.step(user_codes(cfg, frames[i % len(frames)]))
+            ok, t, a = og.step(user_codes(cfg, frames[i % len(frames)]))
+            trace.append((int(ok), int(t)) + tuple(int(v) for v in a))
     step(0)                                            # warm-up frame (page-in of the mmapped weights)
     t0 = time.perf_counter(); n = 0
     while n < max_frames:
@@ -146,7 +194,27 @@ def cpu_reference_fps(path, cfg, frames, max_frames, budget_s):
         if time.perf_counter() - t0 > budget_s:
             break
     dt = time.perf_counter() - t0
-    return n / dt, n, dt
+    return n / dt, n, dt, threads, trace
+
+
+def gpu_token_trace(msx, stream, cfg, frames, n):
+    """the first n frames of the SAME protocol as cpu_reference_fps through the product's public per-frame API"""
+    stream.reset()
+    trace = []
+    if cfg.get("cross_attention"):
+        toks = np.array([cfg["text_card"]] + [cfg["card"]] * cfg["n_q"], dtype=np.int32)
+        for _ in range(n):
+            t, _, _ = stream.step_temporal(toks, want_logits=False)
+            a, _ = stream.step_depformer(t, want_logits=False)
+            trace.append((1, int(t)) + tuple(int(v) for v in a))
+            toks = np.array([t] + list(a) + [0] * (cfg["n_q"] - len(a)), dtype=np.int32)
+    else:
+        gen = msx.Gen(stream)
+        for i in range(n):
+            ok, t, a = gen.step(user_codes(cfg, frames[i % len(frames)]))
+            trace.append((int(ok), int(t)) + tuple(int(v) for v in a))
+        gen.close()
+    return trace
 
 
 _JSON_FD = None
@@ -194,16 +262,14 @@ def main():
                 "l2": "inputs larger than L2 (each frame streams the full weight set, 4.1 GB >> 126 MB)",
                 "model_seed": SEED_MODEL, "token_seed": SEED_TOKENS, "context": cfg["context"]}
     frames = make_frames(cfg)
-    ncores = os.cpu_count() or 1
 
     # ------------------------------------------------------------------------------------------ reference arm
     if args.impl == "reference":
         if rank != 0:
             return 0
         path = ensure_gguf(args.preset, args.quant, 0, 1, lambda: None)
-        os.environ.setdefault("OMP_NUM_THREADS", str(ncores))
         budget = 150.0
-        fps, n, dt = cpu_reference_fps(path, cfg, frames, max(1, args.steps), budget)
+        fps, n, dt, ncores, _ = cpu_reference_fps(path, cfg, frames, max(1, args.steps), budget)
         sample = (f"{n} of the requested {args.steps} frames (capped at {budget:.0f} s of CPU time), greedy LMGen, same GGUF and token seed; "
                   "CPU restatement of the reference's ggml-CPU path (oracle/ggml_ref.c, OpenMP) — ggml itself is not buildable here")
         line = {"impl": "reference", "metric": "frames_per_s", "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
@@ -329,9 +395,9 @@ def main():
     roofline = {"bound": "hbm", "kernel": "gemv_kernel<Q4_K,32> gating.linear_in (rms_norm + q8_K quant + dequant-GEMV + silu gate)",
                 "achieved": achieved, "peak": peaks["hbm_gbs"], "peak_source": f"{peak_src} copy bandwidth (MEASURED_PEAKS.json)",
                 "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel / shape from the committed ncu --set full capture
-                # (profiles/r1d_linear_in_ncu_summary.md: 53.44 MB read = the stored 148 B / 256 weights, no re-reads)
-                "traffic": 53_440_000 if (args.quant == "q4_k" and args.preset.startswith(("moshi7b", "personaplex7b"))) else None,
+                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel and shape, from the committed ncu --set full capture
+                # (profiles/kernel_traffic.json); used only while the capture's stored-layout bytes equal this build's
+                "traffic": committed_traffic("gemv_kernel linear_in", args.quant, cfg["dim"], 2 * cfg["hidden"]),
                 "bytes_per_launch": dom_bytes, "launch_us": dom_ms * 1e3, "launches_timed": fam_n[dom],
                 "graph_replay": {"launch_us": us.value, "achieved": replay_gbs, "frac": (replay_gbs or 0) / peaks["hbm_gbs"],
                                  "how": "200 launches of the same kernel/shape in one CUDA graph over 8 rotating matrices (415 MB > L2)"},
@@ -396,12 +462,66 @@ def main():
         }
         batch.close()
 
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        fps_cpu, n, dt = cpu_reference_fps(path, cfg, frames, 64, args.cpu_budget)
-        cpu = {"value": fps_cpu, "unit": "frames/s", "cores": ncores, "kind": "port",
+    # ---- persistent step kernel (opt-in path), for the record --------------------------------------------------
+    step_kernel = None
+    try:
+        sk_stream = msx.Stream(model, step_kernel=True)
+        if sk_stream.launches_per_frame <= 2:
+            sk_stream.run_resident(frames, W)
+            barrier(); torch.cuda.synchronize(local_rank)
+            ms_sk, _ = sk_stream.run_resident(frames, K)
+            step_kernel = {"ms_per_step": ms_sk / K, "frames_per_s": K / (ms_sk * 1e-3), "launches_per_frame": sk_stream.launches_per_frame,
+                           "what": "MSX_STREAM_STEP_KERNEL: one persistent cooperative kernel per stack (TMA weight ring, flag-in-data "
+                                   "activation exchange), same frames, this rank only"}
+        sk_stream.close()
+    except Exception as e:                           # noqa: BLE001
+        step_kernel = {"error": str(e)[:200]}
+
+    # ---- config 4 when the driver runs N > 1: the N ranks also serve ONE tensor-parallel stream -----------------
+    tensor_parallel = None
+    if dist is not None and not cfg.get("cross_attention") and cfg["num_heads"] % world == 0:
+        try:
+            ids = [msx.tp_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(ids, src=0)
+            tpm = msx.Model(path, cfg, device=local_rank, tp_rank=rank, tp_world=world)
+            tps = msx.Stream(tpm, nccl_id=ids[0])
+            hs = [None] * world
+            dist.all_gather_object(hs, tps.tp_export())
+            tps.tp_connect(hs)
+            tps.run_resident(frames, W)
+            barrier(); torch.cuda.synchronize(local_rank)
+            ms_tp, tok_tp = tps.run_resident(frames, min(K, 200), want_tokens=True)
+            torch.cuda.synchronize(local_rank); barrier()
+            t = torch.tensor([ms_tp], device=f"cuda:{local_rank}", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ref = msx.Stream(model)
+            ref.run_resident(frames, W)
+            ms_one, tok_one = ref.run_resident(frames, min(K, 200), want_tokens=True)
+            ref.close()
+            same = torch.tensor([int(np.array_equal(tok_tp, tok_one))], device=f"cuda:{local_rank}")
+            dist.all_reduce(same, op=dist.ReduceOp.MIN)
+            tensor_parallel = {"world": world, "ms_per_step": float(t[0]) / min(K, 200), "one_gpu_ms": ms_one / min(K, 200),
+                               "speedup_vs_one_gpu": (ms_one / min(K, 200)) / (float(t[0]) / min(K, 200)),
+                               "allreduce": f"{2 * cfg['num_layers']} fused GEMV -> peer-memory all-reduces per frame (f64 partial sums over NVLink)",
+                               "tokens_identical_to_one_gpu": bool(int(same[0])), "steps": min(K, 200),
+                               "workload": f"{args.preset} {args.quant} ONE stream, tensor-parallel x{world} (BASELINE.json config 4 mode)"}
+            tps.close(); tpm.close()
+        except Exception as e:                       # noqa: BLE001
+            tensor_parallel = {"error": str(e)[:300]}
+            barrier()
+
+    # ---- CPU baseline (rank 0, every N) + parity of the timed model against it --------------------------------------
+    cpu, parity = None, None
+    if rank == 0 and not args.no_cpu_baseline:
+        fps_cpu, n, dt, threads, cpu_trace = cpu_reference_fps(path, cfg, frames, 64, args.cpu_budget)
+        cpu = {"value": fps_cpu, "unit": "frames/s", "cores": threads, "kind": "port",
                "sample": f"{n} frames ({dt:.1f} s) of the same {args.preset} {args.quant} GGUF and token seed through oracle/ggml_ref.c "
-                         "(CPU restatement of the reference's ggml-CPU path, OpenMP on all host cores)"}
+                         f"(CPU restatement of the reference's ggml-CPU path, OpenMP, {threads} threads set explicitly)"}
+        gpu_trace = gpu_token_trace(msx, stream, cfg, frames, len(cpu_trace))
+        bad = next((i for i, (a, b) in enumerate(zip(gpu_trace, cpu_trace)) if a != b), None)
+        parity = {"frames": len(cpu_trace), "identical": bad is None, "first_mismatch": bad,
+                  "what": "greedy text + audio tokens of the timed GGUF through the per-frame API vs the CPU oracle, same inputs"}
+    barrier()
 
     if rank == 0:
         line = {
@@ -419,6 +539,8 @@ def main():
             "launches_per_frame": stream.launches_per_frame,
             "clocks": clocks, "load_s": t_load,
             "batched_streams": batched,
+            "parity_checked": parity["frames"] if parity else 0, "parity": parity,
+            "step_kernel": step_kernel, "tensor_parallel": tensor_parallel,
         }
         emit(line)
     if dist is not None:

@@ -297,9 +297,11 @@ def test_two_rank_gloo_plumbing(tmp_path):
 
 def test_bench_reference_arm_contract_under_torchrun():
     """`bench.py --impl reference` launched like the driver launches it for N > 1: rank 0 alone times the CPU path and prints
-    ONE JSON line on stdout (nothing else reaches stdout), the other rank exits 0 without work."""
+    ONE JSON line on stdout (nothing else reaches stdout), the other rank exits 0 without work.  torchrun exports
+    OMP_NUM_THREADS=1 to its workers: the arm must still use every host core it may run on and say how many it used
+    (the SCALE reference numbers at N >= 2 ran on one thread while reporting 32 cores)."""
     import json
-    env = dict(os.environ, OMP_NUM_THREADS="2")
+    env = dict(os.environ, OMP_NUM_THREADS="1")
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
                           "--master-addr", "127.0.0.1", "--master-port", "29543", os.path.join(ROOT, "bench.py"),
                           "--impl", "reference", "--preset", "tiny", "--gpus", "2", "--steps", "3", "--warmup", "1"],
@@ -310,6 +312,10 @@ def test_bench_reference_arm_contract_under_torchrun():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["value"] > 0 and d["unit"] == "frames/s"
     assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+    avail = len(os.sched_getaffinity(0))
+    assert d["cpu_baseline"]["cores"] == avail, "the reference arm must set its OpenMP thread count explicitly"
+    if avail > 1:
+        assert d["cpu_baseline"]["cores"] > 1
     assert set(("metric", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config")) <= set(d)
 
 
