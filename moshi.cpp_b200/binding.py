@@ -63,15 +63,29 @@ HOST_DIR = os.path.join(_HERE, "host")
 STS_BENCH = os.path.join(_HERE, "moshi-sts-bench")
 
 
+TOOLS_DIR = os.path.join(ROOT, "tools")
+BIN_DIR = os.path.join(_HERE, "bin")
+TOOLS = ("moshi-sts", "personaplex", "moshi-tts", "moshi-stt")
+
+
 def build_host(force: bool = False) -> str:
-    """g++: the C++ mirror of the reference's moshi_lm_* API (libmoshi.so) and the moshi-sts --bench style tool."""
+    """g++: the C++ side of the drop-in boundary — libmoshi.so (include/moshi/moshi.h on top of the C ABI), the four LM tools
+    of the reference (tools/*.cpp -> moshi.cpp_b200/bin/) and the API test driver (moshi-sts-bench)."""
     srcs = [os.path.join(HOST_DIR, f) for f in ("moshi_api.cpp", "moshi_api.h", "moshi_sts_bench.cpp")]
-    stale = (not os.path.exists(HOST_SO_PATH)) or (not os.path.exists(STS_BENCH)) or any(
-        os.path.getmtime(s) > min(os.path.getmtime(HOST_SO_PATH), os.path.getmtime(STS_BENCH)) for s in srcs)
+    hdrs = [os.path.join(ROOT, "include", "moshi", f) for f in ("moshi.h", "ptrs.h", "ggml-backend.h")]
+    tool_srcs = [os.path.join(TOOLS_DIR, t + ".cpp") for t in TOOLS] + [os.path.join(TOOLS_DIR, "lm_tool.h")]
+    outs = [HOST_SO_PATH, STS_BENCH] + [os.path.join(BIN_DIR, t) for t in TOOLS]
+    stale = any(not os.path.exists(o) for o in outs) or any(
+        os.path.getmtime(s) > min(os.path.getmtime(o) for o in outs) for s in srcs + hdrs + tool_srcs)
     if force or stale:
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", "-DMOSHI_BUILD", "-o", HOST_SO_PATH,
+        inc = "-I" + os.path.join(ROOT, "include")
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", "-DMOSHI_BUILD", inc, "-o", HOST_SO_PATH,
                                srcs[0], os.path.join(_HERE, "csrc", "gguf_file.cpp"), "-L" + _HERE, "-lmoshi_b200", "-Wl,-rpath,$ORIGIN"])
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", STS_BENCH, srcs[2], "-L" + _HERE, "-lmoshi", "-lmoshi_b200", "-Wl,-rpath,$ORIGIN"])
+        subprocess.check_call(["g++", "-O2", "-std=c++17", inc, "-o", STS_BENCH, srcs[2], "-L" + _HERE, "-lmoshi", "-lmoshi_b200", "-Wl,-rpath,$ORIGIN"])
+        os.makedirs(BIN_DIR, exist_ok=True)
+        for t in TOOLS:
+            subprocess.check_call(["g++", "-O2", "-std=c++17", inc, "-o", os.path.join(BIN_DIR, t), os.path.join(TOOLS_DIR, t + ".cpp"),
+                                   "-L" + _HERE, "-lmoshi", "-lmoshi_b200", "-Wl,-rpath,$ORIGIN/.."])
     return HOST_SO_PATH
 
 

@@ -1401,7 +1401,11 @@ int check_tokens(const msx_model *m, const int32_t *tokens, int n_rows, int32_t 
             const int32_t *t = tokens + (size_t)r * (c.n_q + 1);
             if (t[0] < -2 || t[0] > text_max) return fail(MSX_ERR_ARG, "text token " + std::to_string(t[0]) + " is outside the embedding table");
             for (int i = 1; i <= c.n_q; i++)
-                if (t[i] < -2 || t[i] > c.card) return fail(MSX_ERR_ARG, "audio token " + std::to_string(t[i]) + " (codebook " + std::to_string(i - 1) + ") is outside the embedding table");
+                if (t[i] < -2 || t[i] > c.card) {
+                    std::string rowtxt;
+                    for (int j = 0; j <= c.n_q; j++) rowtxt += " " + std::to_string(t[j]);
+                    return fail(MSX_ERR_ARG, "audio token " + std::to_string(t[i]) + " (codebook " + std::to_string(i - 1) + ") is outside the embedding table; row:" + rowtxt);
+                }
         }
     if (text_override != INT32_MIN && (text_override < -2 || text_override > text_max))
         return fail(MSX_ERR_ARG, "text token " + std::to_string(text_override) + " is outside the depformer text embedding table");

@@ -8,6 +8,8 @@
 #include <cstring>
 #include <cstdlib>
 #include <unistd.h>
+#include <deque>
+#include <unordered_map>
 
 #include "../../include/moshi_b200.h"
 #include "../csrc/gguf_file.h"
@@ -77,6 +79,33 @@ int moshi_get_config(moshi_config_t *c, const char *filename) {
         return false;
     };
     auto string_or_null = [&](std::string &dst) { j.ws(); if (j.lit("null")) { dst.clear(); return true; } return j.str(dst); };
+    auto f32 = [&](float &dst) { j.ws(); if (j.lit("null")) return true; double d = 0; if (!j.num(d)) return false; dst = (float)d; return true; };
+    auto str_arr = [&](std::vector<std::string> &dst) {
+        j.ws(); dst.clear();
+        if (j.lit("null")) return true;
+        if (j.p >= j.e || *j.p != '[') return false; j.p++; j.ws();
+        if (j.p < j.e && *j.p == ']') { j.p++; return true; }
+        while (j.p < j.e) { std::string v; if (!j.str(v)) return false; dst.push_back(v); j.ws();
+            if (j.p < j.e && *j.p == ',') { j.p++; continue; } if (j.p < j.e && *j.p == ']') { j.p++; return true; } return false; }
+        return false;
+    };
+    // a nested object: `field(key)` consumes the value of one key
+    auto object = [&](auto field) {
+        j.ws();
+        if (j.lit("null")) return true;
+        if (j.p >= j.e || *j.p != '{') return false;
+        j.p++;
+        while (true) {
+            j.ws();
+            if (j.p < j.e && *j.p == '}') { j.p++; return true; }
+            std::string kk;
+            if (!j.str(kk)) return false;
+            j.ws(); if (j.p >= j.e || *j.p != ':') return false; j.p++;
+            if (!field(kk)) return false;
+            j.ws();
+            if (j.p < j.e && *j.p == ',') j.p++;
+        }
+    };
     while (true) {
         j.ws();
         if (j.p < j.e && *j.p == '}') break;
@@ -103,25 +132,35 @@ int moshi_get_config(moshi_config_t *c, const char *filename) {
         else if (k == "depformer_weights_per_step_schedule") ok = arr(c->depformer_weights_per_step_schedule);
         else if (k == "model_type") ok = string_or_null(c->model_type); else if (k == "tokenizer_name") ok = string_or_null(c->tokenizer_name);
         else if (k == "mimi_name") ok = string_or_null(c->mimi_name); else if (k == "moshi_name") ok = string_or_null(c->moshi_name);
-        else if (k == "tts_config") {                              // config_tts_parse (config.h:54-70)
-            j.ws();
-            if (j.lit("null")) ok = true;
-            else if (j.p < j.e && *j.p == '{') {
-                j.p++;
-                while (ok) {
-                    j.ws();
-                    if (j.p < j.e && *j.p == '}') { j.p++; break; }
-                    std::string kk;
-                    if (!j.str(kk)) { ok = false; break; }
-                    j.ws(); if (j.p >= j.e || *j.p != ':') { ok = false; break; } j.p++;
-                    if (kk == "second_stream_ahead") ok = i64(c->tts_config.second_stream_ahead);
-                    else if (kk == "audio_delay") { double d = 0; j.ws(); ok = j.num(d); c->tts_config.audio_delay = (float)d; }
-                    else ok = j.skip();
-                    j.ws();
-                    if (j.p < j.e && *j.p == ',') j.p++;
-                }
-            } else ok = false;
-        }
+        else if (k == "tts_config")                                // config_tts_parse (config.h:54-70)
+            ok = object([&](const std::string &kk) {
+                if (kk == "second_stream_ahead") return i64(c->tts_config.second_stream_ahead);
+                if (kk == "audio_delay") return f32(c->tts_config.audio_delay);
+                return j.skip(); });
+        else if (k == "stt_config")                                // config_stt_parse (config.h:75-92)
+            ok = object([&](const std::string &kk) {
+                if (kk == "audio_delay_seconds") return f32(c->stt_config.audio_delay_seconds);
+                if (kk == "audio_silence_prefix_seconds") return f32(c->stt_config.audio_silence_prefix_seconds);
+                return j.skip(); });
+        else if (k == "model_id")                                  // config_model_id_parse (config.h:96-114)
+            ok = object([&](const std::string &kk) {
+                if (kk == "sig") return string_or_null(c->model_id.sig);
+                if (kk == "epoch") return i64(c->model_id.epoch);
+                return j.skip(); });
+        else if (k == "lm_gen_config")                             // config_lm_gen_parse (config.h:118-145)
+            ok = object([&](const std::string &kk) {
+                if (kk == "temp") return f32(c->lm_gen_config.temp);
+                if (kk == "temp_text") return f32(c->lm_gen_config.temp_text);
+                if (kk == "top_k") return i64(c->lm_gen_config.top_k);
+                if (kk == "top_k_text") return i64(c->lm_gen_config.top_k_text);
+                return j.skip(); });
+        else if (k == "fuser")                                     // config_fuser_parse (config.h:20-50)
+            ok = object([&](const std::string &kk) {
+                if (kk == "cross_attention_pos_emb") return boolean(c->fuser.cross_attention_pos_emb);
+                if (kk == "cross_attention_pos_emb_scale") return f32(c->fuser.cross_attention_pos_emb_scale);
+                if (kk == "sum") return str_arr(c->fuser.sum);
+                if (kk == "cross") return str_arr(c->fuser.cross);
+                return j.skip(); });
         else ok = j.skip();
         if (!ok) { fprintf(stderr, "error: reading config %s\n", filename); return -1; }
         j.ws();
@@ -442,6 +481,89 @@ int moshi_lm_personaplex_load_voice(moshi_context_t *, moshi_lm_gen_t *gen, cons
         for (int i = 0; i < CT; i++) { double v; if (!voice_element(cache, cache_dt, (size_t)j * CT + i, v)) return -1; ring[(size_t)i * ncb + j] = (int32_t)v; }
     return moshi_lm_personaplex_voice_tensors(gen, rows.data(), (int)(emb_n / c.dim), ring.data(), CT);
 }
+// ---- tokenizer: plain vocabulary file, greedy longest match (the reference wraps sentencepiece, which this build lacks) ------
+struct tokenizer_t {
+    std::vector<std::string> pieces;                     // id -> piece ("\xe2\x96\x81" = U+2581 marks a word start)
+    std::unordered_map<std::string, int> ids;
+    size_t longest = 1;
+    bool insert_bos = true;
+    std::deque<Entry> pending;
+    std::vector<int> encode(const std::string &text) const {
+        std::vector<int> out;
+        std::string norm;                                 // sentencepiece normalisation, reduced: spaces -> U+2581, one in front
+        norm = "\xe2\x96\x81";
+        for (char ch : text) { if (ch == ' ') norm += "\xe2\x96\x81"; else norm.push_back(ch); }
+        size_t i = 0;
+        while (i < norm.size()) {
+            size_t n = std::min(longest, norm.size() - i);
+            int id = -1;
+            for (; n > 0; n--) { auto it = ids.find(norm.substr(i, n)); if (it != ids.end()) { id = it->second; break; } }
+            if (id < 0) { id = 0; n = 1; while (i + n < norm.size() && ((unsigned char)norm[i + n] & 0xC0) == 0x80) n++; }   // <unk>, one UTF-8 character
+            out.push_back(id);
+            i += n;
+        }
+        return out;
+    }
+};
+tokenizer_t *tokenizer_alloc(const char *filepath, bool insert_bos) {
+    FILE *f = filepath ? fopen(filepath, "rb") : nullptr;
+    if (!f) return nullptr;
+    std::string raw; char buf[4096]; size_t n;
+    while ((n = fread(buf, 1, sizeof(buf), f)) > 0) raw.append(buf, n);
+    fclose(f);
+    if (raw.find('\0') != std::string::npos) return nullptr;       // a sentencepiece .model protobuf, not a vocabulary listing
+    tokenizer_t *t = new tokenizer_t;
+    t->insert_bos = insert_bos;
+    size_t a = 0;
+    while (a < raw.size()) {
+        size_t b = raw.find('\n', a); if (b == std::string::npos) b = raw.size();
+        std::string piece = raw.substr(a, b - a);
+        if (!piece.empty() && piece.back() == '\r') piece.pop_back();
+        const size_t tab = piece.find('\t'); if (tab != std::string::npos) piece.resize(tab);      // "piece<TAB>score" listings
+        if (!piece.empty() && piece[0] == ' ') piece = "\xe2\x96\x81" + piece.substr(1);
+        t->ids.emplace(piece, (int)t->pieces.size());
+        t->longest = std::max(t->longest, piece.size());
+        t->pieces.push_back(piece);
+        a = b + 1;
+    }
+    if (t->pieces.empty()) { delete t; return nullptr; }
+    return t;
+}
+void unref(tokenizer_t *tok) { delete tok; }
+bool tokenizer_empty(tokenizer_t *tok) { return !tok || tok->pending.empty(); }
+// text -> one Entry per word (the TTS word queue, moshi.h:63-68): word tokens, the word itself, padding 0
+int tokenizer_send(tokenizer_t *tok, std::string text) {
+    if (!tok) return -1;
+    size_t a = 0; int n = 0;
+    while (a < text.size()) {
+        while (a < text.size() && isspace((unsigned char)text[a])) a++;
+        size_t b = a;
+        while (b < text.size() && !isspace((unsigned char)text[b])) b++;
+        if (b > a) {
+            Entry e; e.text = text.substr(a, b - a); e.tokens = tok->encode(e.text); e.padding = 0;
+            if (tok->insert_bos && tok->pending.empty() && n == 0) e.tokens.insert(e.tokens.begin(), 1);
+            tok->pending.push_back(std::move(e)); n++;
+        }
+        a = b;
+    }
+    return n;
+}
+int tokenizer_receive(tokenizer_t *tok, Entry *entry) {
+    if (!tok || !entry || tok->pending.empty()) return 0;
+    *entry = std::move(tok->pending.front()); tok->pending.pop_front();
+    return 1;
+}
+std::string tokenizer_id_to_piece(tokenizer_t *tok, int token) {
+    if (!tok || token < 0 || (size_t)token >= tok->pieces.size()) return std::string();
+    return tok->pieces[(size_t)token];
+}
+
+// moshi.cpp:838-849: "<system> " + prompt + " <system>" through the tokenizer
+int moshi_lm_personaplex_system_prompt(moshi_context_t *, moshi_lm_gen_t *gen, tokenizer_t *tok, const char *prompt) {
+    if (!gen || !tok || !prompt) return -1;
+    gen->text_prompt_tokens = tok->encode(std::string("<system> ") + prompt + " <system>");
+    return 0;
+}
 int moshi_lm_personaplex_system_prompt_tokens(moshi_lm_gen_t *gen, const std::vector<int> &text_tokens) {
     gen->text_prompt_tokens = text_tokens;
     return 0;
@@ -454,6 +576,10 @@ static void personaplex_prompts(moshi_lm_gen_t *gen) {
     const int ncb = c.n_q + 1;
     if (ncb != 17) return;                                     // the reference's table has 17 entries
     int32_t row[MSX_MAX_CODEBOOKS], text, audio[MSX_MAX_STEPS];
+    // The table holds codes of the PersonaPlex-7B codebooks (card 2048).  A model with smaller tables (test models) cannot embed
+    // them — the reference would index past its tables — so they are folded into this model's range; for card 2048 a no-op.
+    int32_t prompt_row[17];
+    for (int i = 0; i < 17; i++) prompt_row[i] = PROMPT_TOKENS[i] % (i == 0 ? c.text_card + 1 : c.card);
     // every prompt frame is a full token row: collect them all, then run them as ONE batched-T prefill (8 frames per
     // weight pass); models / situations the prefill does not cover fall back to one decode step per frame like the reference
     std::vector<int32_t> rows;
@@ -470,15 +596,15 @@ static void personaplex_prompts(moshi_lm_gen_t *gen) {
         if (gen->prompt_cache_rows == msx_gen_cache_rows(gen->gen)) msx_gen_set_cache(gen->gen, gen->prompt_cache.data());
     } else
     while (!gen->prompt_audio.empty()) {                       // voice prompt: codes of the 8 moshi codebooks
-        for (int i = 0; i < ncb; i++) row[i] = PROMPT_TOKENS[i];
+        for (int i = 0; i < ncb; i++) row[i] = prompt_row[i];
         const auto &codes = gen->prompt_audio.front();
         for (int j = 0; j < 8 && j < (int)codes.size(); j++) row[j + 1] = codes[j];
         push_row();
         gen->prompt_audio.pop_front();
     }
-    auto silence = [&](int n) { for (int f = 0; f < n; f++) { for (int i = 0; i < ncb; i++) row[i] = PROMPT_TOKENS[i]; push_row(); } };
+    auto silence = [&](int n) { for (int f = 0; f < n; f++) { for (int i = 0; i < ncb; i++) row[i] = prompt_row[i]; push_row(); } };
     silence(6);
-    for (int tok : gen->text_prompt_tokens) { for (int i = 0; i < ncb; i++) row[i] = PROMPT_TOKENS[i]; row[0] = tok; push_row(); }
+    for (int tok : gen->text_prompt_tokens) { for (int i = 0; i < ncb; i++) row[i] = prompt_row[i]; row[0] = tok; push_row(); }
     silence(6);
     flush();
 }
