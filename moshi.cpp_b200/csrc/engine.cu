@@ -654,13 +654,15 @@ const char *kFamilyNames[FAM_COUNT] = {
 int tiles_of(msx_model *m, const QLinear &w, QTiles *out);     // batch.inl
 int ensure_all_tiles(msx_model *m);
 
+// tiles of a small matrix one CTA takes at least: the grid shrinks below one CTA per SM for tiny matrices (measured on B200,
+// moshi 7B frame: 4 -> 2.153 ms, 8 -> 2.152, 16 -> 2.231, 32 -> 2.649, 64 -> 3.616)
+constexpr int kTilesPerCta = 8;
+
 struct Launcher {
     cudaStream_t st;
     int num_sms;
     int count = 0;
-    // Q4_K linears through the tensor-core unit kernel (gemm1_q4k_kernel) when the model carries the units layout
     msx_model *model = nullptr;
-    bool mma = false;
     cudaError_t err = cudaSuccess;
     // optional per-launch timing (eager mode only): events[i], events[i+1] bracket launch i
     std::vector<cudaEvent_t> *events = nullptr;
@@ -692,19 +694,9 @@ struct Launcher {
 
     void gemv(const GemvArgs &a, int pro, int epi, int family = 0) {
         fam = family; begin();
-        if (mma && model && a.w.type == T_Q4_K && !a.tp) {
-            auto it = model->tiles.find(a.w.qs);
-            if (it != model->tiles.end() && a.w.rows == it->second.rows) {
-                const QTiles &wt = it->second;
-                const int S = gemm1_stages_for(wt.K);
-                launch_pdl(gemm1_q4k_kernel, dim3(gemm_grid_for(wt.n_tiles, num_sms)), dim3(kGemmThreads), (size_t)gemm1_smem_bytes(wt.K, S), a, wt, pro, epi, S);
-                check();
-                return;
-            }
-        }
         const int tr = tile_rows(a.w.gs);
         const int n_tiles = (a.w.rows + tr - 1) / tr;
-        const int grid = std::max(1, std::min(num_sms, (n_tiles + 7) / 8));
+        const int grid = std::max(1, std::min(num_sms, (n_tiles + kTilesPerCta - 1) / kTilesPerCta));
         const int smem = gemv_smem_bytes(a.w.type, a.w.K);
         if (a.tp) {          // tensor-parallel partial sums pushed to the peers: separate instantiations
             if (a.w.type == T_Q4_K) {
@@ -749,7 +741,7 @@ struct Launcher {
     }
     int gemv_ctas(const QLinear &w) const {
         const int tr = tile_rows(w.gs);
-        return std::max(1, std::min(num_sms, ((w.rows + tr - 1) / tr + 7) / 8));
+        return std::max(1, std::min(num_sms, ((w.rows + tr - 1) / tr + kTilesPerCta - 1) / kTilesPerCta));
     }
 
     // fused local attention + out_proj (tiny rings)
@@ -757,7 +749,7 @@ struct Launcher {
         fam = family; begin();
         const int tr = tile_rows(g.w.gs);
         const int n_tiles = (g.w.rows + tr - 1) / tr;
-        const int grid = std::max(1, std::min(num_sms, (n_tiles + 7) / 8));
+        const int grid = std::max(1, std::min(num_sms, (n_tiles + kTilesPerCta - 1) / kTilesPerCta));
         const int region = (gemv_smem_bytes(g.w.type, g.w.K) + 15) / 16 * 16;
         const int smem = local_attn_smem_bytes(region, a.dim, dh);
 #define MSX_LA(WT, LN, DH) launch_pdl(gemv_local_attn_kernel<WT, LN, DH>, dim3(grid), dim3(kGemvThreads), smem, g, a, heads, pro, epi, region)
@@ -881,7 +873,6 @@ struct msx_stream {
     bool tp_p2p = false;
     struct msx_batch *prefill = nullptr;   // batched-T prompt prefill context (batch.inl), created on first use
     bool embed_override_next = false;
-    bool use_mma = false;            // Q4_K linears on the tensor-core unit kernel (MSX_MMA=1)
     int32_t *d_feed = nullptr;       // msx_run_resident_async
     cudaGraphExec_t g_temporal = nullptr, g_depformer = nullptr;
     int launches_temporal = 0, launches_depformer = 0;
@@ -977,7 +968,7 @@ void enqueue_layer(Launcher &L, const msx_stream *s, const LayerW &lw, int w, bo
     a.max_period = temporal ? c.max_period : c.dep_max_period;
     a.rope_freq = temporal ? m->rope_freq : m->dep_rope_freq;
     a.rope_cs = (temporal && c.max_period) ? s->rope_cs : nullptr;
-    { const char *e = getenv("MSX_ATTN_SMALL"); a.small_ctx = e ? atoi(e) : 32; }
+    a.small_ctx = 32;        // up to 32 valid slots one CTA per head handles the ring alone (no cluster barriers)
     const size_t lstride = (size_t)cap * adim;
     a.kc = (temporal ? s->kc : s->dkc) + (size_t)layer * lstride;
     a.vc = (temporal ? s->vc : s->dvc) + (size_t)layer * lstride;
@@ -1134,7 +1125,7 @@ void enqueue_depformer(Launcher &L, const msx_stream *s) {
 template <typename F>
 int capture(msx_stream *s, F &&body, cudaGraphExec_t *exec, int *launches) {
     Launcher L{s->st, s->m->num_sms};
-    L.model = s->m; L.mma = s->use_mma;
+    L.model = s->m;
     CU(cudaStreamBeginCapture(s->st, cudaStreamCaptureModeThreadLocal));
     body(L);
     cudaGraph_t graph = nullptr;
@@ -1176,7 +1167,6 @@ int set_smem_attrs() {
     CU(cudaFuncSetAttribute(gemv_local_attn_kernel<8, 16, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CU(cudaFuncSetAttribute(sk::step_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, sk::kSmemBytes));
     CU(cudaFuncSetAttribute(sk::step_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, sk::kSmemBytes));
-    CU(cudaFuncSetAttribute(gemm1_q4k_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemMax));
     // all kernels stay below the 48 KB default except long-context attention with split 1
     CU(cudaFuncSetAttribute(attn_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     CU(cudaFuncSetAttribute(attn_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
@@ -1228,11 +1218,6 @@ static int stream_create_impl(msx_model *m, int context_override, int flags, con
     const msx_config &c = m->cfg;
     s->cap = context_override > 0 ? std::min(context_override, c.context) : c.context;
     s->attn_split = attn_split_for(m->heads_local, s->cap, m->num_sms);
-    { const char *e = getenv("MSX_MMA"); s->use_mma = e && atoi(e) != 0; }
-    if (s->use_mma) {
-        bool all_q4k = m->text_linear.type == T_Q4_K;
-        if (all_q4k) { if (int e = ensure_all_tiles(m)) return e; } else s->use_mma = false;
-    }
     CU(cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking));
     CU(cudaEventCreate(&s->ev0)); CU(cudaEventCreate(&s->ev1));
     CU(cudaMallocHost((void **)&s->h_in, kCtrlInBytes));
@@ -1734,7 +1719,7 @@ extern "C" int msx_profile_frame(msx_stream *s, const int32_t *tokens, int32_t *
     std::vector<cudaEvent_t> ev;
     std::vector<int> fam;
     Launcher L{s->st, s->m->num_sms};
-    L.model = s->m; L.mma = s->use_mma;
+    L.model = s->m;
     L.events = &ev; L.families = &fam;
     if (s->step_kernel) { enqueue_step_kernel(L, s, true); s->host_offset++; if (c.dep_q > 0) enqueue_step_kernel(L, s, false); }
     else {
@@ -2126,7 +2111,6 @@ extern "C" int msx_test_gemv(int device, int type, const void *w, int64_t k, int
         CU(cudaMemcpy(da, alpha, (size_t)k * 4, cudaMemcpyHostToDevice));
     }
     Launcher L{nullptr, m->num_sms};
-    if (type == T_Q4_K) { const char *e = getenv("MSX_MMA"); if (e && atoi(e)) { QTiles qt; if (int er = tiles_of(m.get(), ql, &qt)) return er; L.model = m.get(); L.mma = true; } }
     GemvArgs g;
     g.w = ql; g.x = dx; g.alpha = da; g.eps = 1e-8f; g.out = dy;
     L.gemv(g, prologue == PRO_RMS ? PRO_RMS : PRO_PLAIN, EPI_STORE);
@@ -2146,9 +2130,6 @@ extern "C" int msx_bench_gemv(int device, int type, const void *w, int64_t k, in
     std::vector<QLinear> mats(n_mats);
     for (int i = 0; i < n_mats; i++)
         if (int e = upload_linear(m.get(), w, type, k, rows, epilogue == EPI_GATE ? (int)(rows / 2) : 0, &mats[i])) return e;
-    bool bench_mma = false;
-    if (type == T_Q4_K) { const char *e = getenv("MSX_MMA"); bench_mma = e && atoi(e); }
-    if (bench_mma) for (int i = 0; i < n_mats; i++) { QTiles qt; if (int e = tiles_of(m.get(), mats[i], &qt)) return e; }
     float *dx = nullptr, *dy = nullptr, *da = nullptr;
     if (int e = dev_alloc(m.get(), (void **)&dx, (size_t)k * 4)) return e;
     if (int e = dev_alloc(m.get(), (void **)&dy, (size_t)std::max<int64_t>(rows, k) * 4)) return e;
@@ -2161,7 +2142,7 @@ extern "C" int msx_bench_gemv(int device, int type, const void *w, int64_t k, in
     cudaStream_t st;
     CU(cudaStreamCreate(&st));
     Launcher L{st, m->num_sms};
-    L.model = m.get(); L.mma = bench_mma;
+    L.model = m.get();
     cudaEvent_t e0, e1;
     CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
     unsigned long long *dkey = nullptr;

@@ -132,43 +132,6 @@ __device__ __forceinline__ void quantize_block_q8k(int b, int lane, const float 
     *reinterpret_cast<uint2 *>(x8 + ((size_t)piece * P + p) * 16 + (lane & 1) * 8) = pack8(q);
 }
 
-// Same quantisation, stored as the single-column activation image of the tensor-core unit kernel (mma_gemm.cuh):
-//   xq  [K/64 pairs][4 t] 16 B = {sub-block 2p: k 4t.., k 16+4t..; sub-block 2p+1: k 4t.., k 16+4t..}   (B fragments of column 0)
-//   bsw [K/64 pairs] u32 = int16 sums of the pair's two 32-element sub-blocks;  dx [K/256] f32
-__device__ __forceinline__ void quantize_block_q8k_frag(int b, int lane, const float (&v)[8], int8_t *xq, int *bsw, float *dx) {
-    float amax = 0.f, mx = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; i++) { float ax = fabsf(v[i]); if (ax > amax) { amax = ax; mx = v[i]; } }
-    const float wmax = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(amax)));
-    const unsigned hit = __ballot_sync(0xffffffffu, amax == wmax);
-    const float carrier = __shfl_sync(0xffffffffu, mx, __ffs(hit) - 1);
-    int q[8];
-    float d = 0.f;
-    if (wmax == 0.f) {
-#pragma unroll
-        for (int i = 0; i < 8; i++) q[i] = 0;
-    } else {
-        const float iscale = -127.f / carrier;
-#pragma unroll
-        for (int i = 0; i < 8; i++) { int t = __float2int_rn(iscale * v[i]); q[i] = t < 127 ? t : 127; }
-        d = 1.f / iscale;
-    }
-    int s = 0;
-#pragma unroll
-    for (int i = 0; i < 8; i++) s += q[i];
-    s += __shfl_xor_sync(0xffffffffu, s, 1);
-    s += __shfl_xor_sync(0xffffffffu, s, 2);
-    const int s_next = __shfl_down_sync(0xffffffffu, s, 4);
-    const int sbk = lane >> 2, jj = lane & 3;
-    const int p = 4 * b + (sbk >> 1);
-    if ((lane & 7) == 0) bsw[p] = (int)((uint32_t)(s & 0xffff) | ((uint32_t)(s_next & 0xffff) << 16));
-    if (lane == 0) dx[b] = d;
-    const uint2 pk = pack8(q);
-    uint32_t *dst = reinterpret_cast<uint32_t *>(xq + (size_t)p * 64) + (sbk & 1) * 2 + (jj >> 1);
-    dst[(2 * (jj & 1)) * 4] = pk.x;
-    dst[(2 * (jj & 1) + 1) * 4] = pk.y;
-}
-
 // quantize_row_q8_0 for the 8 blocks of 32 inside 256-block b: d = amax/127, q = roundf(x/d), d kept as fp16
 __device__ __forceinline__ void quantize_block_q8_0(int b, int lane, const float (&v)[8], bool act, int P, int8_t *x8, float *dx) {
     float amax = 0.f;
@@ -261,7 +224,7 @@ __device__ __forceinline__ void gemv_prologue(const GemvArgs &a, const float *xi
                         *reinterpret_cast<float4 *>(a.norm_out + e0 + 4) = make_float4(v[j][4], v[j][5], v[j][6], v[j][7]);
                     }
                 }
-                if (WT == 12) { if (LAYOUT == 0) quantize_block_q8k(b, lane, v[j], P, x8, bs, dx); else quantize_block_q8k_frag(b, lane, v[j], x8, bs, dx); }
+                if (WT == 12) quantize_block_q8k(b, lane, v[j], P, x8, bs, dx);
                 else quantize_block_q8_0(b, lane, v[j], act, P, x8, dx);
             }
         }

@@ -28,8 +28,31 @@ __device__ __forceinline__ void attn_local(const AttnArgs &a, int heads, float *
     uint16_t *vnew = knew + DH;
     float *sc_s = q_s + DH + DH;
     const float scale = 1.f / sqrtf((float)DH);
+    constexpr int KPRE = 4, VPRE = 16, NV = DH / 64;       // ring rows kept in registers: KPRE * SPI (K), VPRE (V) slots
+    const bool pre = n_valid <= KPRE * SPI && n_valid <= VPRE;
     for (int h = warp; h < heads; h += nwarps) {
         const float *q = a.qkv + h * DH, *k = a.qkv + a.dim + h * DH, *v = a.qkv + 2 * a.dim + h * DH;
+        const int g = lane / LPS, sl = lane % LPS;
+        // Every load of this head — q / k / v of the step and the K and V rows of ALL valid slots — is requested here, before the
+        // first use: one L2 round trip (~0.5 us) instead of one per loop iteration (the tiny rings of the depformer made this
+        // kernel a chain of ~10 dependent round trips).
+        uint4 kpre[KPRE];
+        uint32_t vpre[NV][VPRE];
+        if (pre) {
+#pragma unroll
+            for (int u = 0; u < KPRE; u++) {
+                const int i = u * SPI + g;
+                kpre[u] = make_uint4(0, 0, 0, 0);
+                if (i < n_valid && i != slot) kpre[u] = __ldcg(reinterpret_cast<const uint4 *>(a.kc + ((size_t)h * cap + i) * DH + sl * 8));
+            }
+#pragma unroll
+            for (int s = 0; s < NV; s++)
+#pragma unroll
+                for (int i = 0; i < VPRE; i++) {
+                    vpre[s][i] = 0u;
+                    if (i < n_valid && i != slot) vpre[s][i] = __ldcg(reinterpret_cast<const uint32_t *>(a.vc + ((size_t)h * cap + i) * DH + 2 * lane + 64 * s));
+                }
+        }
         for (int j = lane; j < DH / 2; j += 32) {
             const float2 qq = __ldcg(reinterpret_cast<const float2 *>(q + 2 * j));
             const float2 kk = __ldcg(reinterpret_cast<const float2 *>(k + 2 * j));
@@ -55,19 +78,13 @@ __device__ __forceinline__ void attn_local(const AttnArgs &a, int heads, float *
                 reinterpret_cast<uint2 *>(a.vc + o)[t] = reinterpret_cast<const uint2 *>(vnew)[t];
             }
         }
-        const int g = lane / LPS, sl = lane % LPS;
         float qv[8];
 #pragma unroll
         for (int i = 0; i < 8; i++) qv[i] = q_s[sl * 8 + i];
         float lmax = -INFINITY;
-        for (int i0 = 0; i0 < n_valid; i0 += SPI) {
-            const int i = i0 + g;
+        auto score = [&](int i, uint4 kk) {
             const bool valid = i < n_valid;
-            uint4 kk = make_uint4(0, 0, 0, 0);
-            if (valid) {
-                if (i == slot) kk = reinterpret_cast<const uint4 *>(knew)[sl];
-                else kk = __ldcg(reinterpret_cast<const uint4 *>(a.kc + ((size_t)h * cap + i) * DH + sl * 8));
-            }
+            if (valid && i == slot) kk = reinterpret_cast<const uint4 *>(knew)[sl];
             double d = 0.0;
             d += (double)(bf16_bits_to_f32(kk.x & 0xffff) * qv[0]); d += (double)(bf16_bits_to_f32(kk.x >> 16) * qv[1]);
             d += (double)(bf16_bits_to_f32(kk.y & 0xffff) * qv[2]); d += (double)(bf16_bits_to_f32(kk.y >> 16) * qv[3]);
@@ -77,6 +94,17 @@ __device__ __forceinline__ void attn_local(const AttnArgs &a, int heads, float *
             for (int o = LPS / 2; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
             const float s = (float)d * scale + 0.0f;
             if (valid) { if (sl == 0) sc_s[i] = s; lmax = fmaxf(lmax, s); }
+        };
+        if (pre) {
+#pragma unroll
+            for (int u = 0; u < KPRE; u++) if (u * SPI < n_valid) score(u * SPI + g, kpre[u]);     // warp-uniform trip count
+        } else {
+            for (int i0 = 0; i0 < n_valid; i0 += SPI) {
+                const int i = i0 + g;
+                uint4 kk = make_uint4(0, 0, 0, 0);
+                if (i < n_valid && i != slot) kk = __ldcg(reinterpret_cast<const uint4 *>(a.kc + ((size_t)h * cap + i) * DH + sl * 8));
+                score(i, kk);
+            }
         }
         lmax = warp_max(lmax);
         __syncwarp();
@@ -87,15 +115,27 @@ __device__ __forceinline__ void attn_local(const AttnArgs &a, int heads, float *
         const float inv = (float)(1.0 / lsum);
         __syncwarp();
         // context: lane owns dims {2*lane, 2*lane+1} (+64 for DH = 128)
-        for (int d0 = 2 * lane; d0 < DH; d0 += 64) {
+#pragma unroll
+        for (int s = 0; s < NV; s++) {
+            const int d0 = 2 * lane + 64 * s;
             double acc0 = 0.0, acc1 = 0.0;
-            for (int i = 0; i < n_valid; i++) {
-                const float p = bf16_round(sc_s[i] * inv);
-                uint32_t vv;
-                if (i == slot) vv = *reinterpret_cast<const uint32_t *>(vnew + d0);
-                else vv = __ldcg(reinterpret_cast<const uint32_t *>(a.vc + ((size_t)h * cap + i) * DH + d0));
-                acc0 += (double)(bf16_bits_to_f32(vv & 0xffff) * p);
-                acc1 += (double)(bf16_bits_to_f32(vv >> 16) * p);
+            if (pre) {
+#pragma unroll
+                for (int i = 0; i < VPRE; i++) if (i < n_valid) {
+                    const float p = bf16_round(sc_s[i] * inv);
+                    const uint32_t vv = i == slot ? *reinterpret_cast<const uint32_t *>(vnew + d0) : vpre[s][i];
+                    acc0 += (double)(bf16_bits_to_f32(vv & 0xffff) * p);
+                    acc1 += (double)(bf16_bits_to_f32(vv >> 16) * p);
+                }
+            } else {
+                for (int i = 0; i < n_valid; i++) {
+                    const float p = bf16_round(sc_s[i] * inv);
+                    uint32_t vv;
+                    if (i == slot) vv = *reinterpret_cast<const uint32_t *>(vnew + d0);
+                    else vv = __ldcg(reinterpret_cast<const uint32_t *>(a.vc + ((size_t)h * cap + i) * DH + d0));
+                    acc0 += (double)(bf16_bits_to_f32(vv & 0xffff) * p);
+                    acc1 += (double)(bf16_bits_to_f32(vv >> 16) * p);
+                }
             }
             ctx_s[h * DH + d0] = (float)acc0; ctx_s[h * DH + d0 + 1] = (float)acc1;
         }

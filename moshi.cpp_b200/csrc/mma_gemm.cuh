@@ -708,186 +708,6 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_mma_kernel(const GemmArg
     }
 }
 
-// =====================================================================================================
-// Single-stream variant: ONE activation column, the activation prologue (RMSNorm + Q8_K quantisation) runs
-// inside the kernel like in gemv.cuh, the image is the single-column form (gemv.cuh quantize_block_q8k_frag).
-// Only the accumulators of column 0 (lanes with t == 0: rows g and g+8) are carried; the other MMA columns
-// are don't-care.  Same arithmetic, same epilogues as gemv_kernel — it replaces it for Q4_K matrices.
-// =====================================================================================================
-__host__ __device__ inline int gemm1_image_bytes(int K) { return ((K + (K >> 6) * 4 + (K >> 8) * 4 + 127) & ~127) + 128; }   // + prologue reduce scratch
-constexpr int kPart1Bytes = 2 * kGemmWarps * 16 * 8;          // double-buffered [warp][16 rows] fp64 partials
-__host__ inline int gemm1_smem_bytes(int K, int stages) { return gemm1_image_bytes(K) + kPart1Bytes + 1024 + stages * kGemmWarps * kUnitBytes; }
-__host__ inline int gemm1_stages_for(int K) {
-    int s = (kGemmSmemMax - (gemm1_image_bytes(K) + kPart1Bytes + 1024)) / (kGemmWarps * kUnitBytes);
-    return s > 5 ? 5 : s;
-}
-
-__device__ __forceinline__ void unit_compute1(const uint8_t *slot, const int8_t *xq, const int *bsw, const float *dx, int sb, int lane, double &acc0, double &acc1) {
-    const int g = lane >> 2, t = lane & 3;
-    const uint4 scg4 = *reinterpret_cast<const uint4 *>(slot + 2048 + g * 16);
-    const uint4 sch4 = *reinterpret_cast<const uint4 *>(slot + 2048 + (g + 8) * 16);
-    const uint32_t ddg = *reinterpret_cast<const uint32_t *>(slot + 2304 + g * 4);
-    const uint32_t ddh = *reinterpret_cast<const uint32_t *>(slot + 2304 + (g + 8) * 4);
-    const uint32_t scg[4] = {scg4.x, scg4.y, scg4.z, scg4.w}, sch[4] = {sch4.x, sch4.y, sch4.z, sch4.w};
-    int lo0 = 0, lo1 = 0, hi0 = 0, hi1 = 0, mn0 = 0, mn1 = 0;
-    const int4 bw4 = *reinterpret_cast<const int4 *>(bsw + sb * 4);
-    const int bwv[4] = {bw4.x, bw4.y, bw4.z, bw4.w};
-#pragma unroll
-    for (int p = 0; p < 4; p++) {
-        const uint4 w = *reinterpret_cast<const uint4 *>(slot + p * 512 + lane * 16);
-        const uint4 xb = *reinterpret_cast<const uint4 *>(xq + (size_t)(sb * 4 + p) * 64 + t * 16);
-        int c[4], d[4];
-        mma_u8s8(c, w.x & 0x0F0F0F0Fu, w.y & 0x0F0F0F0Fu, w.z & 0x0F0F0F0Fu, w.w & 0x0F0F0F0Fu, xb.x, xb.y);
-        mma_u8s8(d, w.x & 0xF0F0F0F0u, w.y & 0xF0F0F0F0u, w.z & 0xF0F0F0F0u, w.w & 0xF0F0F0F0u, xb.z, xb.w);
-        lo0 += (int)__byte_perm(scg[p], 0, 0x4440) * c[0]; lo1 += (int)__byte_perm(sch[p], 0, 0x4440) * c[2];
-        hi0 += (int)__byte_perm(scg[p], 0, 0x4441) * d[0]; hi1 += (int)__byte_perm(sch[p], 0, 0x4441) * d[2];
-        mn0 = dp2a_hi_su((uint32_t)bwv[p], scg[p], mn0); mn1 = dp2a_hi_su((uint32_t)bwv[p], sch[p], mn1);
-    }
-    const float dxv = dx[sb];
-    const float2 dmg = __half22float2(*reinterpret_cast<const __half2 *>(&ddg));
-    const float2 dmh = __half22float2(*reinterpret_cast<const __half2 *>(&ddh));
-    acc0 = fma((double)__fmul_rn(dmg.x, dxv), (double)(lo0 + (hi0 >> 4)), acc0); acc0 = fma(-(double)__fmul_rn(dmg.y, dxv), (double)mn0, acc0);
-    acc1 = fma((double)__fmul_rn(dmh.x, dxv), (double)(lo1 + (hi1 >> 4)), acc1); acc1 = fma(-(double)__fmul_rn(dmh.y, dxv), (double)mn1, acc1);
-}
-
-__global__ void __launch_bounds__(kGemmThreads, 1) gemm1_q4k_kernel(const GemvArgs a, const QTiles wt, const int pro, const int epi, const int S) {
-    extern __shared__ __align__(16) uint8_t smem[];
-    griddep_launch();
-    const int lane = threadIdx.x & 31, warp = uniform_warp_id();
-    const int g = lane >> 2, t = lane & 3;
-    const int K = wt.K, nsb = wt.nsb, rows = wt.rows;
-    const int img_sz = gemm1_image_bytes(K);
-    int8_t *xq = reinterpret_cast<int8_t *>(smem);
-    int *bsw = reinterpret_cast<int *>(smem + K);
-    float *dx = reinterpret_cast<float *>(smem + K + (K >> 6) * 4);
-    double *red = reinterpret_cast<double *>(smem + img_sz - 128);
-    double *part = reinterpret_cast<double *>(smem + img_sz);                            // [2][16 warps][16 rows]
-    uint8_t *bar_base = reinterpret_cast<uint8_t *>(part) + kPart1Bytes;
-    uint8_t *ring = bar_base + 1024 + (size_t)warp * S * kUnitBytes;
-    const uint32_t bar_u32 = (uint32_t)__cvta_generic_to_shared(bar_base);
-    const uint32_t ring_u32 = (uint32_t)__cvta_generic_to_shared(ring);
-    const uint32_t my_bar = bar_u32 + 8 + warp * (kGemmMaxStages * 8);
-
-    const int t_begin = (int)((long long)blockIdx.x * wt.n_tiles / gridDim.x);
-    const int t_end = (int)((long long)(blockIdx.x + 1) * wt.n_tiles / gridDim.x);
-
-    if (lane == 0) {
-        for (int s = 0; s < S; s++) mbar_init(my_bar + s * 8, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncwarp();
-    WarpRound pc{t_begin, t_end - t_begin};
-    round_setup(pc, warp, nsb);
-    int pi = 0, ps = 0;
-    const uint8_t *psrc = wt.units + ((size_t)pc.tile * nsb + pc.wq) * kUnitBytes;
-    auto issue = [&]() -> bool {
-        if (pi >= pc.upr) {
-            do { round_next(pc, warp, nsb); } while (pc.rem > 0 && pc.upr == 0);
-            if (pc.rem <= 0) return false;
-            pi = 0;
-            psrc = wt.units + ((size_t)pc.tile * nsb + pc.wq) * kUnitBytes;
-        }
-        mbar_expect_tx(my_bar + ps * 8, kUnitBytes);
-        bulk_g2s(ring_u32 + ps * kUnitBytes, psrc, kUnitBytes, my_bar + ps * 8);
-        psrc += (size_t)kUnitBytes << pc.lw;
-        pi++;
-        if (++ps == S) ps = 0;
-        return true;
-    };
-    if (lane == 0) for (int u = 0; u < S; u++) if (!issue()) break;
-    griddep_wait();
-
-    // activation prologue (gemv.cuh): RMSNorm + Q8_K quantisation of the ONE column into fragment order
-    const BlockGeom bg{kGemmThreads, kGemmWarps};
-    gemv_prologue<12, 1>(a, a.x, blockIdx.x == 0, pro, K, xq, bsw, dx, red, bg);
-    __syncthreads();
-
-    int emb_token = 0;
-    if (epi == EPI_ADD_EMB) emb_token = depformer_prev_token(a.ctrl, a.emb_step);
-    unsigned long long best = 0ull;
-
-    WarpRound cr{t_begin, t_end - t_begin};
-    round_setup(cr, warp, nsb);
-    int cs = 0; uint32_t cphase = 0;
-    int rr = 0;
-#pragma unroll 1
-    for (; cr.rem > 0; round_next(cr, warp, nsb), rr++) {
-        double *pbuf = part + (size_t)(rr & 1) * (kGemmWarps * 16);
-        // reducer role: warp (rr rotating) handles tiles 4i..4i+3 of the round: lane -> (tile lane/8, row pair lane%8)
-        const int rw = (warp - (rr & (kGemmWarps - 1))) & (kGemmWarps - 1);      // 0 or 1 are the reducer warps
-        const int rtile_in = rw * 4 + (lane >> 3), rg = lane & 7;
-        const bool reducer = rw < 2 && rtile_in < cr.n;
-        const int red_tile = cr.tile0 + rtile_in;
-        const int row0 = red_tile * 16 + rg, row1 = row0 + 8;
-        float old0 = 0.f, old1 = 0.f;
-        if (reducer && epi == EPI_RESID) {
-            if (row0 < rows) old0 = __ldcg(a.out + row0);
-            if (row1 < rows) old1 = __ldcg(a.out + row1);
-        }
-        if (cr.upr > 0) {
-            double acc0 = 0.0, acc1 = 0.0;
-#pragma unroll 1
-            for (int i = 0; i < cr.upr; i++) {
-                mbar_wait(my_bar + cs * 8, cphase);
-                unit_compute1(ring + (size_t)cs * kUnitBytes, xq, bsw, dx, cr.wq + (i << cr.lw), lane, acc0, acc1);
-                __syncwarp();
-                if (lane == 0) issue();
-                if (++cs == S) { cs = 0; cphase ^= 1; }
-            }
-            if (t == 0) { pbuf[warp * 16 + g] = acc0; pbuf[warp * 16 + 8 + g] = acc1; }
-        }
-        __syncthreads();
-        if (reducer) {
-            const int nw = min(1 << cr.lw, nsb);
-            double s0 = 0.0, s1 = 0.0;
-            const double *pj = pbuf + (rtile_in << cr.lw) * 16;
-            for (int j = 0; j < nw; j++, pj += 16) { s0 += pj[rg]; s1 += pj[8 + rg]; }
-            const float v0 = (float)s0, v1 = (float)s1;
-            if (epi == EPI_GATE) {
-                const int h = red_tile * 8 + rg;
-                if (2 * h < rows) a.out[h] = (v0 / (1.0f + (float)exp((double)(-v0)))) * v1;
-            } else if (epi == EPI_RESID) {
-                if (row0 < rows) a.out[row0] = old0 + v0;
-                if (row1 < rows) a.out[row1] = old1 + v1;
-            } else if (epi == EPI_STORE_F64) {
-                if (row0 < rows) a.out_f64[row0] = s0;
-                if (row1 < rows) a.out_f64[row1] = s1;
-            } else {
-#pragma unroll
-                for (int hh = 0; hh < 2; hh++) {
-                    const int row = hh ? row1 : row0;
-                    const float v = hh ? v1 : v0;
-                    if (row >= rows) continue;
-                    if (epi == EPI_STORE) a.out[row] = v;
-                    else if (epi == EPI_ARGMAX) {
-                        a.out[row] = v;
-                        const unsigned long long k = argmax_key(v, row);
-                        best = k > best ? k : best;
-                    } else if (epi == EPI_ADD_EMB) {
-                        float em;
-                        if (a.emb_step == 0) { em = emb_element(a.emb, emb_token < 0 ? 0 : emb_token, row); em = em * (emb_token == -1 ? 0.f : 1.f); }
-                        else em = emb_element(a.emb, emb_token, row);
-                        a.out[row] = v + em;
-                    } else if (epi == EPI_ADD_VEC) a.out[row] = v + __ldcg(a.addvec + row);
-                }
-            }
-        }
-    }
-    if (epi == EPI_ARGMAX) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { const unsigned long long x = __shfl_xor_sync(0xffffffffu, best, o); best = x > best ? x : best; }
-        unsigned long long *sbest = reinterpret_cast<unsigned long long *>(part);
-        __syncthreads();
-        if (lane == 0) sbest[warp] = best;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            unsigned long long bb = 0;
-            for (int w = 0; w < kGemmWarps; w++) bb = sbest[w] > bb ? sbest[w] : bb;
-            if (bb) atomicMax(a.key, bb);
-        }
-    }
-}
-
 #define gemm_q4k_kernel gemm_mma_kernel<12, 0>
 #define gemm_q8_0_kernel gemm_mma_kernel<8, 0>
 __host__ inline int gemm_grid_for(int n_tiles, int num_sms) { return n_tiles < num_sms ? n_tiles : num_sms; }
