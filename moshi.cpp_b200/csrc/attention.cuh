@@ -42,6 +42,7 @@ struct AttnArgs {
     int64_t kv_bstride = 0;
     int32_t qkv_bstride = 0, ctx_bstride = 0;
     int32_t skip_insert = 0;        // the ring rows of this step were written by kv_insert_kernel (batched-T prefill)
+    long long *dbg = nullptr;       // optional timeline (scripts/attn_probe.cu): [CTA][8] globaltimer ns
 };
 
 constexpr int kAttnMaxSplit = 8;
@@ -52,13 +53,13 @@ constexpr int kAttnMaxSplit = 8;
 // chunks land while the row maximum / row sum travel across the cluster, so the HBM stream does not stop at the softmax.
 // (Round 1 fetched 8 rows per lane group per round trip through registers and reached 28 % of the measured HBM peak with a
 // full 3000-slot ring; see profiles/r2_attention.md.)
-constexpr int kAttnRing = 6;
+constexpr int kAttnRing = 6;          // 8 and 10 slots measured: no change (the passes are bound by the F2F conversions, profiles/r2_attention.md)
 constexpr int kAttnChunkRows = 32;
 
 // shared-memory layout (bytes): ring[kAttnRing][32][DH] bf16 | full[R], empty[R] mbarriers | x_sum[8] f64 | red[8] f64 |
 //                               x_ctx[8][DH] f64 | part[NG][DH] f64 | q[DH] f32 | knew,vnew [2*DH] bf16 | x_max[8] f32 | scores[per] f32
 template <int DH>
-__host__ __device__ inline int attn_ring_bytes() { return kAttnRing * kAttnChunkRows * DH * 2 + 128; }
+__host__ __device__ inline int attn_ring_bytes() { return kAttnRing * kAttnChunkRows * DH * 2 + (kAttnRing * 20 + 127) / 128 * 128; }   // + full[R], empty[R], cnt[R]
 template <int DH>
 __host__ __device__ inline int attn_smem_bytes(int cap, int S) {
     const int per = (cap + S - 1) / S + 1;
@@ -126,12 +127,16 @@ __global__ void __launch_bounds__(kThreads) attn_kernel(const AttnArgs a0) {
     // (uniform decision across the cluster, so nobody waits at a barrier)
     const bool use_cluster = CLUSTER && n_valid > min(a.small_ctx, per - 1);
     if (CLUSTER && !use_cluster) { if (c != 0) return; S = 1; c = 0; }
+    // "this CTA has started" — arrive now, wait right before the first remote shared-memory write (after the score pass): by then
+    // every CTA of the cluster has long arrived, so the start-up handshake costs nothing
+    if (use_cluster) asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     const int lo = (int)((long long)n_valid * c / S), hi = (int)((long long)n_valid * (c + 1) / S);
     const int n_ck = (hi - lo + CH - 1) / CH, n_chunks = 2 * n_ck;      // K chunks, then V chunks of the same rows
 
     uint8_t *ring = smem;
     const uint32_t ring_u32 = (uint32_t)__cvta_generic_to_shared(ring);
     const uint32_t bars = ring_u32 + kAttnRing * CHB;                    // full[R] then empty[R]
+    int *cnt = reinterpret_cast<int *>(ring + kAttnRing * CHB + 2 * kAttnRing * 8);   // [R] warps through the chunk in a slot
     uint8_t *rest = smem + attn_ring_bytes<DH>();
     double *x_sum = reinterpret_cast<double *>(rest);                  // [kAttnMaxSplit] cluster exchange: row sums
     double *dred = x_sum + kAttnMaxSplit;                              // [8] block reduce scratch
@@ -155,23 +160,29 @@ __global__ void __launch_bounds__(kThreads) attn_kernel(const AttnArgs a0) {
         bulk_g2s(ring_u32 + s * CHB, src, (uint32_t)nr * DH * 2, bars + s * 8);
     };
     if (tid == 0) {
-        for (int s = 0; s < kAttnRing; s++) { mbar_init(bars + s * 8, 1); mbar_init(bars + (kAttnRing + s) * 8, kWarps); }
+        for (int s = 0; s < kAttnRing; s++) { mbar_init(bars + s * 8, 1); mbar_init(bars + (kAttnRing + s) * 8, kWarps); cnt[s] = 0; }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         // (batched-T prefill: the rows of this pass's other columns are written by the kv_insert kernel right before us)
         if (!a.skip_insert) for (int j = 0; j < min(kAttnRing, n_chunks); j++) issue(j);
     }
+    long long *stamp = a.dbg && tid == 0 ? a.dbg + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 : nullptr;
+    if (stamp) stamp[0] = global_ns();
     __syncthreads();       // barriers initialised before anybody waits on them
     griddep_wait();        // qkv comes from the previous kernel (PDL)
     if (tid == 0 && a.skip_insert) for (int j = 0; j < min(kAttnRing, n_chunks); j++) issue(j);
 
-    // every warp arrives on empty[slot] when it is done with chunk j; thread 0 then refills the slot with chunk j + kAttnRing
+    // every warp arrives on empty[slot] when it is done with chunk j; the LAST warp through refills the slot with chunk
+    // j + kAttnRing (nobody waits for a slower warp: a fixed refiller made warp 0 the pace of the whole CTA)
     auto release = [&](int j) {
         __syncwarp();
-        const uint32_t s = (uint32_t)(j % kAttnRing);
-        if (lane == 0) mbar_arrive(bars + (kAttnRing + s) * 8);
-        if (tid == 0 && j + kAttnRing < n_chunks) {
-            mbar_wait(bars + (kAttnRing + s) * 8, (uint32_t)((j / kAttnRing) & 1));
-            issue(j + kAttnRing);
+        if (lane == 0) {
+            const uint32_t s = (uint32_t)(j % kAttnRing);
+            mbar_arrive(bars + (kAttnRing + s) * 8);
+            if (j + kAttnRing < n_chunks && atomicAdd(&cnt[s], 1) == kWarps - 1) {
+                cnt[s] = 0;
+                mbar_wait(bars + (kAttnRing + s) * 8, (uint32_t)((j / kAttnRing) & 1));
+                issue(j + kAttnRing);
+            }
         }
     };
 
@@ -189,36 +200,51 @@ __global__ void __launch_bounds__(kThreads) attn_kernel(const AttnArgs a0) {
     }
 
     // ---- 2. scores over this CTA's share of the valid slots ----------------------------------------
-    const int g = tid / LPS, sl = tid % LPS;
+    // Work item = 16 rows of a chunk, taken by ONE warp: lanes [0,16) own dims [0, DH/2) of row (lane & 15), lanes [16,32) the other
+    // half, so a row is reduced inside its lane pair (one shuffle) and every lane runs four independent accumulation chains over
+    // DH/2 elements.  Lane r reads its row's 16-byte pieces in the rotated order (u + r) mod (DH/16): rows are DH * 2 bytes apart,
+    // i.e. all in the same banks, and the rotation spreads a quarter-warp over eight different pieces (conflict-free for DH = 128).
+    // bf16 x bf16 products are exact in fp32; they are summed in double (order-independent).
+    const int g = tid / LPS, sl = tid % LPS;       // context pass: row group, 8-dim slice
     const float scale = 1.f / sqrtf((float)DH);
-    float qv[8];
-#pragma unroll
-    for (int i = 0; i < 8; i++) qv[i] = q_s[sl * 8 + i];
     float lmax = -INFINITY;
-    for (int j = 0; j < n_ck; j++) {
-        mbar_wait(bars + (j % kAttnRing) * 8, (uint32_t)((j / kAttnRing) & 1));
-        const uint16_t *ck = reinterpret_cast<const uint16_t *>(ring + (j % kAttnRing) * CHB);
+    {
+        constexpr int HP = DH / 16;              // 16-byte pieces per half row
+        const int hl = lane & 15, hs = lane >> 4;
+        for (int j = 0; j < n_ck; j++) {
+            mbar_wait(bars + (j % kAttnRing) * 8, (uint32_t)((j / kAttnRing) & 1));     // every warp: keeps all warps inside the ring window
+            const uint16_t *ck = reinterpret_cast<const uint16_t *>(ring + (j % kAttnRing) * CHB);
 #pragma unroll
-        for (int r = g; r < CH; r += NG) {
-            const int i = lo + j * CH + r;
-            uint4 kk = make_uint4(0, 0, 0, 0);
-            if (i < hi) kk = (i == slot && !a.skip_insert) ? reinterpret_cast<const uint4 *>(knew)[sl] : reinterpret_cast<const uint4 *>(ck + r * DH)[sl];
-            // bf16 x bf16 products are exact in fp32; they are summed in double (order-independent)
-            double d = 0.0;
-            d += (double)(bf16_bits_to_f32(kk.x & 0xffff) * qv[0]); d += (double)(bf16_bits_to_f32(kk.x >> 16) * qv[1]);
-            d += (double)(bf16_bits_to_f32(kk.y & 0xffff) * qv[2]); d += (double)(bf16_bits_to_f32(kk.y >> 16) * qv[3]);
-            d += (double)(bf16_bits_to_f32(kk.z & 0xffff) * qv[4]); d += (double)(bf16_bits_to_f32(kk.z >> 16) * qv[5]);
-            d += (double)(bf16_bits_to_f32(kk.w & 0xffff) * qv[6]); d += (double)(bf16_bits_to_f32(kk.w >> 16) * qv[7]);
+            for (int half = 0; half < 2; half++) {
+                if (((2 * j + half) & (kWarps - 1)) != warp) continue;                  // item 2j + half belongs to warp (2j + half) mod 8
+                const int r = half * 16 + hl, i = lo + j * CH + r;
+                double d = 0.0;
+                if (i < hi) {
+                    const uint16_t *rowp = (i == slot && !a.skip_insert) ? knew : ck + r * DH;
+                    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll
-            for (int o = LPS / 2; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-            const float sv = (float)d * scale + 0.0f;
-            if (i < hi) {
-                if (sl == 0) sc_s[i - lo] = sv;
-                lmax = fmaxf(lmax, sv);
+                    for (int u = 0; u < HP; u++) {
+                        const int pc = hs * HP + ((u + hl) & (HP - 1));
+                        const uint4 kk = *reinterpret_cast<const uint4 *>(rowp + pc * 8);
+                        const float4 q0 = *reinterpret_cast<const float4 *>(q_s + pc * 8), q1 = *reinterpret_cast<const float4 *>(q_s + pc * 8 + 4);
+                        a0 += (double)(bf16_bits_to_f32(kk.x & 0xffff) * q0.x); a1 += (double)(bf16_bits_to_f32(kk.x >> 16) * q0.y);
+                        a2 += (double)(bf16_bits_to_f32(kk.y & 0xffff) * q0.z); a3 += (double)(bf16_bits_to_f32(kk.y >> 16) * q0.w);
+                        a0 += (double)(bf16_bits_to_f32(kk.z & 0xffff) * q1.x); a1 += (double)(bf16_bits_to_f32(kk.z >> 16) * q1.y);
+                        a2 += (double)(bf16_bits_to_f32(kk.w & 0xffff) * q1.z); a3 += (double)(bf16_bits_to_f32(kk.w >> 16) * q1.w);
+                    }
+                    d = (a0 + a1) + (a2 + a3);
+                }
+                d += __shfl_xor_sync(0xffffffffu, d, 16);
+                if (i < hi) {
+                    const float sv = (float)d * scale + 0.0f;
+                    if (hs == 0) sc_s[i - lo] = sv;
+                    lmax = fmaxf(lmax, sv);
+                }
             }
+            release(j);
         }
-        release(j);
     }
+    if (stamp) stamp[1] = global_ns();      // score pass done (warp 0)
     lmax = warp_max(lmax);
     if (lane == 0) red[warp] = lmax;
     __syncthreads();
@@ -230,13 +256,14 @@ __global__ void __launch_bounds__(kThreads) attn_kernel(const AttnArgs a0) {
     float gmax = cmax;
     if (use_cluster) {
         cg::cluster_group cl = cg::this_cluster();
-        cl.sync();      // every CTA of the cluster has started (its shared memory exists) before remote writes
+        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");   // every CTA of the cluster has started (its shared memory exists)
         if (tid < S) cl.map_shared_rank(x_max, tid)[c] = cmax;     // scatter my max to every CTA of the cluster
         cl.sync();
         gmax = x_max[0];
         for (int r = 1; r < S; r++) gmax = fmaxf(gmax, x_max[r]);
     }
 
+    if (stamp) stamp[2] = global_ns();      // row maximum known
     // ---- 3. exp and row sum (ggml soft_max: expf(x - max), sum in double, scale by 1/sum) -----------
     double lsum = 0.0;
     for (int i = lo + tid; i < hi; i += kThreads) { const float e = (float)exp((double)(sc_s[i - lo] - gmax)); sc_s[i - lo] = e; lsum += (double)e; }
@@ -256,6 +283,9 @@ __global__ void __launch_bounds__(kThreads) attn_kernel(const AttnArgs a0) {
         for (int r = 0; r < S; r++) gsum += x_sum[r];
     }
     const float inv = (float)(1.0 / gsum);
+    for (int i = lo + tid; i < hi; i += kThreads) sc_s[i - lo] = bf16_round(sc_s[i - lo] * inv);    // p_i, rounded to bf16 once per row
+    __syncthreads();
+    if (stamp) stamp[3] = global_ns();      // probabilities known
 
     // ---- 4. context = sum_i bf16(p_i) * V_i over this CTA's slots ------------------------------------
     double acc[8];
@@ -269,7 +299,7 @@ __global__ void __launch_bounds__(kThreads) attn_kernel(const AttnArgs a0) {
             const int i = lo + (j - n_ck) * CH + r;
             if (i < hi) {
                 const uint4 vv = (i == slot && !a.skip_insert) ? reinterpret_cast<const uint4 *>(vnew)[sl] : reinterpret_cast<const uint4 *>(ck + r * DH)[sl];
-                const float p = bf16_round(sc_s[i - lo] * inv);
+                const float p = sc_s[i - lo];
                 acc[0] += (double)(bf16_bits_to_f32(vv.x & 0xffff) * p); acc[1] += (double)(bf16_bits_to_f32(vv.x >> 16) * p);
                 acc[2] += (double)(bf16_bits_to_f32(vv.y & 0xffff) * p); acc[3] += (double)(bf16_bits_to_f32(vv.y >> 16) * p);
                 acc[4] += (double)(bf16_bits_to_f32(vv.z & 0xffff) * p); acc[5] += (double)(bf16_bits_to_f32(vv.z >> 16) * p);
@@ -278,6 +308,7 @@ __global__ void __launch_bounds__(kThreads) attn_kernel(const AttnArgs a0) {
         }
         release(j);
     }
+    if (stamp) stamp[4] = global_ns();      // context pass done (warp 0)
 #pragma unroll
     for (int i = 0; i < 8; i++) part[g * DH + sl * 8 + i] = acc[i];
     __syncthreads();
@@ -297,6 +328,7 @@ __global__ void __launch_bounds__(kThreads) attn_kernel(const AttnArgs a0) {
     } else {
         if (tid < DH) a.ctx[h * DH + tid] = (float)tot;
     }
+    if (stamp) stamp[5] = global_ns();
 }
 
 // Batched-T prefill: the K / V rows of ALL columns of a chunk are inserted first (columns = consecutive positions of ONE
