@@ -245,6 +245,8 @@ def main():
     ap.add_argument("--quant", default="q4_k")
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true",
+                    help="skip the short single-stream runs of BASELINE.json's other model configs (extra key other_configs, N = 1 only)")
     ap.add_argument("--streams", type=int, default=8,
                     help="also time a lock-step batch of this many streams per GPU (BASELINE config 5; q4_k only, 0 = skip)")
     ap.add_argument("--tp", action="store_true",
@@ -510,6 +512,39 @@ def main():
             tensor_parallel = {"error": str(e)[:300]}
             barrier()
 
+    # ---- BASELINE.json's other single-GPU configurations, for the record (N = 1, default workload only) ----------------
+    # config 0's model (stt-1b, q8_0), config 1 (tts-1.6b q4_k decode against a 125-row conditioning memory) and the headline model
+    # with its KV ring full (config 4's operating point on one GPU): 200 device-resident frames each, same timing rules.
+    other = None
+    if dist is None and not args.no_other_configs and args.preset == "moshi7b" and args.quant == "q4_k":
+        other = {}
+        try:
+            stream.reset()
+            stream.run_resident(frames, cfg["context"] + 8)                      # ring full
+            ms_f, _ = stream.run_resident(frames, 200)
+            other["moshi7b q4_k, KV ring full"] = {"ms_per_step": ms_f / 200, "frames_per_s": 200 / (ms_f * 1e-3), "kv_slots": min(stream.offset, cfg["context"]),
+                                                   "kv_bytes_per_step": int(stream.kv_bytes_next)}
+            stream.reset()
+        except Exception as e:                       # noqa: BLE001
+            other["moshi7b q4_k, KV ring full"] = {"error": str(e)[:200]}
+        for o_preset, o_quant in (("stt1b", "q8_0"), ("tts1_6b", "q4_k")):
+            key = f"{o_preset} {o_quant}"
+            try:
+                ocfg = configs.get(o_preset)
+                opath = ensure_gguf(o_preset, o_quant, rank, world, barrier)
+                om = msx.Model(opath, ocfg, device=local_rank); os_ = msx.Stream(om)
+                if ocfg.get("cross_attention"):
+                    os_.set_condition(*tts_condition(ocfg))
+                ofr = make_frames(ocfg)
+                os_.run_resident(ofr, W)
+                torch.cuda.synchronize(local_rank)
+                ms_o, _ = os_.run_resident(ofr, 200)
+                other[key] = {"ms_per_step": ms_o / 200, "frames_per_s": 200 / (ms_o * 1e-3), "realtime_factor": 200 / (ms_o * 1e-3) / FRAME_RATE,
+                              "launches_per_frame": os_.launches_per_frame, "weight_bytes_per_step": int(om.weight_bytes_per_frame)}
+                os_.close(); om.close()
+            except Exception as e:                   # noqa: BLE001
+                other[key] = {"error": str(e)[:200]}
+
     # ---- CPU baseline (rank 0, every N) + parity of the timed model against it --------------------------------------
     cpu, parity = None, None
     if rank == 0 and not args.no_cpu_baseline:
@@ -540,7 +575,7 @@ def main():
             "clocks": clocks, "load_s": t_load,
             "batched_streams": batched,
             "parity_checked": parity["frames"] if parity else 0, "parity": parity,
-            "step_kernel": step_kernel, "tensor_parallel": tensor_parallel,
+            "step_kernel": step_kernel, "tensor_parallel": tensor_parallel, "other_configs": other,
         }
         emit(line)
     if dist is not None:
