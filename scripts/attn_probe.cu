@@ -1,7 +1,7 @@
 // attn_probe.cu — dev harness: the ring attention kernel (csrc/attention.cuh) alone, at 7B shapes with a full ring, with its
 // optional in-kernel timeline.  Prints per-stage times (median over CTAs / slowest CTA) and the launch time from CUDA events with
 // the ring colder than L2 (32 layers of rings rotate, 1.57 GB).
-//   nvcc -gencode arch=compute_100a,code=sm_100a -std=c++17 -O3 -I moshi.cpp_b200/csrc -o /tmp/attn_probe scripts/attn_probe.cu && /tmp/attn_probe [n_valid] [split]
+//   nvcc -gencode arch=compute_100a,code=sm_100a -std=c++17 -O3 -I moshi.cpp_b200/csrc -o /tmp/attn_probe scripts/attn_probe.cu && /tmp/attn_probe [n_valid] [split] [small_ctx]
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -12,7 +12,7 @@ using namespace msx;
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); return 1; } } while (0)
 
 int main(int argc, char **argv) {
-    const int n_valid = argc > 1 ? atoi(argv[1]) : 3000, split = argc > 2 ? atoi(argv[2]) : 8;
+    const int n_valid = argc > 1 ? atoi(argv[1]) : 3000, split = argc > 2 ? atoi(argv[2]) : 8, small_ctx = argc > 3 ? atoi(argv[3]) : 32;
     const int H = 32, DH = 128, cap = 3000, dim = H * DH, L = 32;
     const size_t ring = (size_t)H * cap * DH;
     uint16_t *kc, *vc; float *qkv, *ctx; Ctrl *ctrl; long long *dbg;
@@ -30,7 +30,7 @@ int main(int argc, char **argv) {
         CK(cudaMemcpy(ctrl, &c, sizeof(c), cudaMemcpyHostToDevice));
     }
     CK(cudaFuncSetAttribute(attn_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_smem_bytes<128>(cap, split)));
-    AttnArgs a; a.qkv = qkv; a.ctx = ctx; a.ctrl = ctrl; a.cap = cap; a.dim = dim; a.max_period = 0; a.small_ctx = 32;
+    AttnArgs a; a.qkv = qkv; a.ctx = ctx; a.ctrl = ctrl; a.cap = cap; a.dim = dim; a.max_period = 0; a.small_ctx = small_ctx;
     auto launch = [&](int layer, long long *d) {
         a.kc = kc + layer * ring; a.vc = vc + layer * ring; a.dbg = d;
         cudaLaunchConfig_t cfg{};
@@ -49,7 +49,7 @@ int main(int argc, char **argv) {
     cudaEventRecord(e1); CK(cudaDeviceSynchronize());
     float ms; cudaEventElapsedTime(&ms, e0, e1);
     const double bytes = 2.0 * H * (double)std::min(n_valid, cap) * DH * 2;
-    printf("n_valid %d split %d smem %d B: %.2f us / launch back to back (%.0f GB/s of K+V)\n", n_valid, split, attn_smem_bytes<128>(cap, split), ms * 1e3 / reps, bytes / (ms * 1e-3 / reps) / 1e9);
+    printf("n_valid %d split %d small_ctx %d smem %d B: %.2f us / launch back to back (%.0f GB/s of K+V)\n", n_valid, split, small_ctx, attn_smem_bytes<128>(cap, split), ms * 1e3 / reps, bytes / (ms * 1e-3 / reps) / 1e9);
     CK(cudaMemset(dbg, 0, (size_t)H * split * 64));
     CK(launch(7, dbg)); CK(cudaDeviceSynchronize());
     std::vector<long long> h((size_t)H * split * 8);
