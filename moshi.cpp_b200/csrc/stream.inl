@@ -139,7 +139,7 @@ void enqueue_layer(Launcher &L, const msx_stream *s, const LayerW &lw, int w, bo
     a.max_period = temporal ? c.max_period : c.dep_max_period;
     a.rope_freq = temporal ? m->rope_freq : m->dep_rope_freq;
     a.rope_cs = (temporal && c.max_period) ? s->rope_cs : nullptr;
-    a.small_ctx = 32;        // up to 32 valid slots one CTA per head handles the ring alone (no cluster barriers)
+    a.small_ctx = 64;        // up to 64 valid slots one CTA per head handles the ring alone (no cluster barriers; profiles/r2_attention.md)
     const size_t lstride = (size_t)cap * adim;
     a.kc = (temporal ? s->kc : s->dkc) + (size_t)layer * lstride;
     a.vc = (temporal ? s->vc : s->dvc) + (size_t)layer * lstride;
