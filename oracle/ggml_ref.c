@@ -23,6 +23,9 @@
 
 #ifdef _OPENMP
 #include <omp.h>
+#ifdef __AVX2__
+#include <immintrin.h>
+#endif
 #endif
 
 #define QK_K 256
@@ -316,16 +319,58 @@ static float vec_dot_q4_K_q8_K(int64_t n, const block_q4_K *x, const int8_t *yqs
         const uint8_t *q4 = x[i].qs;
         const int8_t *q8 = yqs + (int64_t)i * QK_K;
         const int16_t *bs = ybsums + (int64_t)i * (QK_K / 16);
+#ifdef __AVX2__
+        {   /* get_scale_min_k4 for all eight sub-blocks with word operations (the 6-bit fields of the 12 packed bytes) */
+            uint32_t u[3]; memcpy(u, x[i].scales, 12);
+            const uint32_t sc_lo = u[0] & 0x3f3f3f3fu, m_lo = u[1] & 0x3f3f3f3fu;
+            const uint32_t sc_hi = (u[2] & 0x0f0f0f0fu) | ((u[0] >> 2) & 0x30303030u);
+            const uint32_t m_hi = ((u[2] >> 4) & 0x0f0f0f0fu) | ((u[1] >> 2) & 0x30303030u);
+            memcpy(scales, &sc_lo, 4); memcpy(scales + 4, &sc_hi, 4); memcpy(mins, &m_lo, 4); memcpy(mins + 4, &m_hi, 4);
+        }
+        int sumi;
+        {   /* sum_j bsums[j] * mins[j / 2]: pair sums of the 16 int16 block sums (<= 2 * 16 * 127) times the 8 mins */
+            const __m256i b16 = _mm256_loadu_si256((const __m256i *)bs);
+            const __m128i pair = _mm_hadd_epi16(_mm256_castsi256_si128(b16), _mm256_extracti128_si256(b16, 1));
+            const __m128i m16 = _mm_cvtepu8_epi16(_mm_loadl_epi64((const __m128i *)mins));
+            __m128i s4 = _mm_madd_epi16(pair, m16);
+            s4 = _mm_add_epi32(s4, _mm_shuffle_epi32(s4, 0x4E));
+            s4 = _mm_add_epi32(s4, _mm_shuffle_epi32(s4, 0xB1));
+            sumi = _mm_cvtsi128_si32(s4);
+        }
+#else
         for (int j = 0; j < 8; j++) get_scale_min_k4(j, x[i].scales, &scales[j], &mins[j]);
         int sumi = 0;
         for (int j = 0; j < QK_K / 16; ++j) sumi += bs[j] * mins[j / 2];
+#endif
         int32_t isum = 0;
+#ifdef __AVX2__
+        /* the same exact integers with the instructions ggml's AVX2 kernel uses (maddubs on unsigned nibbles x signed q8,
+         * madd with the sub-block scale): pair sums <= 2 * 15 * 127 fit int16, everything after that is int32 */
+        {
+            const __m256i m4 = _mm256_set1_epi8(0xF);
+            __m256i acc = _mm256_setzero_si256();
+            for (int j = 0; j < QK_K / 64; ++j) {
+                const __m256i q4b = _mm256_loadu_si256((const __m256i *)q4);
+                const __m256i lo8 = _mm256_and_si256(q4b, m4), hi8 = _mm256_and_si256(_mm256_srli_epi16(q4b, 4), m4);
+                const __m256i plo = _mm256_maddubs_epi16(lo8, _mm256_loadu_si256((const __m256i *)q8));
+                const __m256i phi = _mm256_maddubs_epi16(hi8, _mm256_loadu_si256((const __m256i *)(q8 + 32)));
+                acc = _mm256_add_epi32(acc, _mm256_madd_epi16(plo, _mm256_set1_epi16((short)scales[2 * j])));
+                acc = _mm256_add_epi32(acc, _mm256_madd_epi16(phi, _mm256_set1_epi16((short)scales[2 * j + 1])));
+                q4 += 32; q8 += 64;
+            }
+            __m128i s4 = _mm_add_epi32(_mm256_castsi256_si128(acc), _mm256_extracti128_si256(acc, 1));
+            s4 = _mm_add_epi32(s4, _mm_shuffle_epi32(s4, 0x4E));
+            s4 = _mm_add_epi32(s4, _mm_shuffle_epi32(s4, 0xB1));
+            isum = _mm_cvtsi128_si32(s4);
+        }
+#else
         for (int j = 0; j < QK_K / 64; ++j) {
             int32_t lo = 0, hi = 0;
             for (int l = 0; l < 32; ++l) { lo += (q4[l] & 0xF) * q8[l]; hi += (q4[l] >> 4) * q8[32 + l]; }
             isum += (int32_t)scales[2 * j] * lo + (int32_t)scales[2 * j + 1] * hi;
             q4 += 32; q8 += 64;
         }
+#endif
         const float d = orc_fp16_to_fp32(x[i].d) * yd[i];
         const float dmin = orc_fp16_to_fp32(x[i].dmin) * yd[i];
         sumd += (double)d * (double)isum;
@@ -340,7 +385,19 @@ static float vec_dot_q8_0_q8_0(int64_t n, const block_q8_0 *x, const block_q8_0 
     double sumd = 0.0;
     for (int ib = 0; ib < nb; ++ib) {
         int sumi = 0;
+#ifdef __AVX2__
+        {   /* |x| (unsigned) x sign(x)-adjusted y: pair sums <= 2 * 127 * 127 fit int16 (ggml's mul_sum_i8_pairs) */
+            const __m256i xv = _mm256_loadu_si256((const __m256i *)x[ib].qs), yv = _mm256_loadu_si256((const __m256i *)y[ib].qs);
+            const __m256i p16 = _mm256_maddubs_epi16(_mm256_sign_epi8(xv, xv), _mm256_sign_epi8(yv, xv));
+            const __m256i p32 = _mm256_madd_epi16(p16, _mm256_set1_epi16(1));
+            __m128i s4 = _mm_add_epi32(_mm256_castsi256_si128(p32), _mm256_extracti128_si256(p32, 1));
+            s4 = _mm_add_epi32(s4, _mm_shuffle_epi32(s4, 0x4E));
+            s4 = _mm_add_epi32(s4, _mm_shuffle_epi32(s4, 0xB1));
+            sumi = _mm_cvtsi128_si32(s4);
+        }
+#else
         for (int j = 0; j < QK8_0; j++) sumi += x[ib].qs[j] * y[ib].qs[j];
+#endif
         const float dd = orc_fp16_to_fp32(x[ib].d) * orc_fp16_to_fp32(y[ib].d);
         sumd += (double)dd * (double)sumi;
     }
