@@ -28,6 +28,9 @@ struct msx_batch {
     // share its KV rings and its CUDA stream; n_active <= n columns are live in the launches being enqueued
     msx_stream *prefill_of = nullptr;
     int n_active = 0;
+    bool tc = false;                      // prefill with 64 columns per pass on the tcgen05 GEMM (tc_gemm.cuh) instead of 8 on mma.sync
+    double *tc_partial = nullptr; size_t tc_partial_bytes = 0;     // split-K partial sums [tile][part][64][128]
+    unsigned int *tc_tickets = nullptr;                            // [tiles] arrival counters (zero between launches)
     // sampling (sampling.h:46-64) per stream: temperature <= 0 = greedy; Exp(1) noise supplied by the host per frame
     float temp_text = 0.f, temp_audio = 0.f;
     int top_k_text = 25, top_k_audio = 250;
@@ -103,6 +106,7 @@ struct BatchLauncher {
         const int wt = b->m->text_linear.type;          // a model is q4_k or q8_0 throughout
         QuantArgs q;
         q.x = x; q.ld = ld; q.alpha = alpha; q.eps = 1e-8f; q.norm_out = norm_out; q.norm_ld = norm_ld; q.img = img ? img : b->img; q.K = K;
+        q.plain = b->tc ? 1 : 0;
         L.fam = family; L.begin();
         if (wt == T_Q4_K) L.launch_pdl(quant_q8k_kernel, dim3(b->n_active, quant_parts_for(K)), dim3(kGemmThreads), 0, q);
         else L.launch_pdl(quant_q8_0_kernel, dim3(b->n_active, quant_parts_for(K)), dim3(kGemmThreads), 0, q);
@@ -110,6 +114,17 @@ struct BatchLauncher {
     }
     // y = W (norm?)(x): one launch with the fused prologue when the inner dimension is short, else quantise + GEMM
     void linear(const float *x, int ld, const float *alpha, const QLinear &w, float *out, int out_ld, int epi, int family, int key_index = -1) {
+        if (b->tc) {                     // 64 prompt columns: quantise (plain image) + tcgen05 GEMM
+            quant(x, ld, alpha, nullptr, 0, w.K, family);
+            tc::TcGemmArgs g;
+            g.w = b->m->wtc.at(w.qs); g.K = w.K; g.rows = w.rows; g.img = b->img; g.out = out; g.ld = out_ld; g.nb = b->n_active; g.epi = epi;
+            g.parts = tc::parts_for(w.rows / tc::kM, w.K >> 8, L.num_sms); g.partial = b->tc_partial; g.tickets = b->tc_tickets;
+            if ((size_t)(w.rows / tc::kM) * g.parts * tc::kN * tc::kM * 8 > b->tc_partial_bytes) { err = fail(MSX_ERR_STATE, "tc prefill: partial-sum buffer too small"); return; }
+            L.fam = family; L.begin();
+            L.launch_pdl(tc::tc_gemm_q4k_kernel, dim3((w.rows / tc::kM) * g.parts), dim3(tc::kThreads), (size_t)tc::kSmemBytes, g);
+            L.check();
+            return;
+        }
         if (fuse_small && w.type == T_Q4_K && gemm_can_fuse_quant(w.K, b->n_active)) {
             gemm(w, out, out_ld, epi, family, key_index, nullptr, 0, nullptr, x, ld, alpha);
         } else {
@@ -274,13 +289,23 @@ int pull_outputs_b(msx_batch *b) {
 }  // namespace
 
 static int batch_create_impl(msx_model *m, int n_streams, int context_override, msx_stream *prefill_of, msx_batch **out);
+// every linear of the temporal stack has the tc layout (Q4_K, rows % 128 == 0, K % 256 == 0, one GPU)
+static bool tc_prefill_ok(const msx_model *m) {
+    if (m->layers.empty()) return false;
+    for (const LayerW &l : m->layers)
+        for (const QLinear *w : {&l.in_proj[0], &l.out_proj[0], &l.lin_in[0], &l.lin_out[0]})
+            if (!m->wtc.count(w->qs)) return false;
+    return true;
+}
 extern "C" int msx_batch_create(msx_model *m, int n_streams, int context_override, msx_batch **out) {
     return batch_create_impl(m, n_streams, context_override, nullptr, out);
 }
 static int batch_create_impl(msx_model *m, int n_streams, int context_override, msx_stream *prefill_of, msx_batch **out) {
     if (!m || !out) return fail(MSX_ERR_ARG, "null argument");
     *out = nullptr;
-    if (n_streams < 1 || n_streams > kMmaCols) return fail(MSX_ERR_ARG, "a batch holds 1..8 streams");
+    // a prefill context of 64 columns runs its linears on the tcgen05 GEMM (Q4_K models whose temporal linears have the tc layout)
+    const bool tc_mode = prefill_of && n_streams == tc::kN && tc_prefill_ok(m);
+    if (n_streams < 1 || (n_streams > kMmaCols && !tc_mode)) return fail(MSX_ERR_ARG, "a batch holds 1..8 streams");
     if (m->cfg.cross_attention || m->cfg.demux_second_stream || m->cfg.dep_low_rank)
         return fail(MSX_ERR_ARG, "batched streams do not cover the TTS-family layers (cross-attention, demux / low-rank embeddings)");
     CU(cudaSetDevice(m->device));
@@ -290,9 +315,12 @@ static int batch_create_impl(msx_model *m, int n_streams, int context_override, 
     CU(cudaFuncSetAttribute(gemm_mma_kernel<12, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemMax));
     CU(cudaFuncSetAttribute(gemm_mma_kernel<8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemMax));
     CU(cudaFuncSetAttribute(gemm_mma_kernel<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemMax));
-    if (int e = ensure_all_tiles(m)) return e;
+    if (tc_mode) {
+        CU(cudaFuncSetAttribute(tc::tc_gemm_q4k_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes));
+    }
+    else if (int e = ensure_all_tiles(m)) return e;
     std::unique_ptr<msx_batch> b(new msx_batch);
-    b->m = m; b->n = n_streams; b->n_active = n_streams; b->prefill_of = prefill_of;
+    b->m = m; b->n = n_streams; b->n_active = n_streams; b->prefill_of = prefill_of; b->tc = tc_mode;
     const msx_config &c = m->cfg;
     const size_t n = (size_t)n_streams;
     b->cap = context_override > 0 ? std::min(context_override, c.context) : c.context;
@@ -330,8 +358,19 @@ static int batch_create_impl(msx_model *m, int n_streams, int context_override, 
         maxK = std::max(maxK, std::max(c.dep_dim, m->dep_hidden));
     }
     const int wt = m->text_linear.type;
-    if (gemm_stages_for(maxK, wt) < 2) return fail(MSX_ERR_ARG, "inner dimension too large for the batched GEMM's shared-memory image");
-    if (int e = balloc(b.get(), (void **)&b->img, (size_t)act_image_bytes(maxK, wt))) return e;
+    if (!tc_mode && gemm_stages_for(maxK, wt) < 2) return fail(MSX_ERR_ARG, "inner dimension too large for the batched GEMM's shared-memory image");
+    if (int e = balloc(b.get(), (void **)&b->img, tc_mode ? tc::image_bytes(maxK) : (size_t)act_image_bytes(maxK, wt))) return e;
+    if (tc_mode) {
+        size_t need = 0; int max_tiles = 0;
+        for (const QLinear *w : {&m->layers[0].in_proj[0], &m->layers[0].out_proj[0], &m->layers[0].lin_in[0], &m->layers[0].lin_out[0]}) {
+            const int tiles = w->rows / tc::kM;
+            need = std::max(need, (size_t)tiles * tc::parts_for(tiles, w->K >> 8, m->num_sms) * tc::kN * tc::kM * 8);
+            max_tiles = std::max(max_tiles, tiles);
+        }
+        b->tc_partial_bytes = need;
+        if (int e = balloc(b.get(), (void **)&b->tc_partial, need)) return e;
+        if (int e = balloc(b.get(), (void **)&b->tc_tickets, (size_t)max_tiles * 4)) return e;
+    }
     if (int e = balloc(b.get(), (void **)&b->img_tout, (size_t)act_image_bytes(c.dim, wt))) return e;
     if (!prefill_of) {
         const size_t nf = n * (1 + MSX_MAX_STEPS) * kSampleMaxK;
@@ -365,14 +404,14 @@ extern "C" int msx_stream_prefill(msx_stream *s, const int32_t *tokens, int T) {
     CU(cudaSetDevice(m->device));
     if (!s->prefill) {
         msx_batch *pb = nullptr;
-        if (int e = batch_create_impl(m, kMmaCols, s->cap, s, &pb)) return e;
+        if (int e = batch_create_impl(m, tc_prefill_ok(m) ? tc::kN : kMmaCols, s->cap, s, &pb)) return e;
         s->prefill = pb;
     }
     msx_batch *b = s->prefill;
     const int n_in = c.n_q + 1;
     for (int c0 = 0, nb = 0; c0 < T; c0 += nb) {
         // all columns of a pass are inserted before any of them attends, so a pass must not overwrite a slot an earlier
-        // column still sees: up to the end of the ring's first lap 8 positions per pass, beyond it one position per pass
+        // column still sees: up to the end of the ring's first lap b->n (64 or 8) positions per pass, beyond it one per pass
         const int pos0 = s->host_offset + c0;
         nb = pos0 >= s->cap ? 1 : std::min(std::min(b->n, T - c0), s->cap - pos0);
         CU(cudaStreamSynchronize(b->st));            // the pinned staging buffers are reused per chunk

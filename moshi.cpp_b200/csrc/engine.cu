@@ -41,6 +41,7 @@
 #include "sample.cuh"
 #include "step_kernel.cuh"
 #include "tts_kernels.cuh"
+#include "tc_gemm.cuh"
 
 using namespace msx;
 

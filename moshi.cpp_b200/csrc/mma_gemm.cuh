@@ -150,6 +150,7 @@ struct QuantArgs {
     float *norm_out = nullptr; int32_t norm_ld = 0;  // optional copy of the normalised vector (transformer_out)
     uint8_t *img = nullptr;
     int32_t K = 0;
+    int32_t plain = 0;                               // 1: image for the tcgen05 GEMM (tc_gemm.cuh: one record per super-block, operand layout)
 };
 
 constexpr int kQChunk = 3;
@@ -246,6 +247,13 @@ __global__ void __launch_bounds__(kGemmThreads) quant_q8k_kernel(const QuantArgs
             s += __shfl_xor_sync(0xffffffffu, s, 1);
             s += __shfl_xor_sync(0xffffffffu, s, 2);                 // sum of the lane's 32-element sub-block
             const int s_next = __shfl_down_sync(0xffffffffu, s, 4);    // the following sub-block
+            if (a.plain) {             // record of super-block blk: x8 tile in operand layout | sums per 32 [64][8] | scales [64]
+                uint8_t *rec = a.img + (size_t)blk * (64 * 256 + 64 * 16 + 64 * 4);
+                if ((lane & 3) == 0) reinterpret_cast<int16_t *>(rec + 64 * 256)[col * 8 + (lane >> 2)] = (int16_t)s;
+                if (lane == 0) reinterpret_cast<float *>(rec + 64 * 256 + 64 * 16)[col] = d;
+                *reinterpret_cast<uint2 *>(rec + (col >> 3) * 2048 + (lane >> 1) * 128 + (col & 7) * 16 + (lane & 1) * 8) = pack8(q);
+                continue;
+            }
             const int sbk = lane >> 2, jj = lane & 3;
             const int p = 4 * blk + (sbk >> 1);
             if ((lane & 7) == 0) bsw[(size_t)p * 8 + col] = (uint32_t)(s & 0xffff) | ((uint32_t)(s_next & 0xffff) << 16);

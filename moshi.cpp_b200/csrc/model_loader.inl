@@ -47,6 +47,8 @@ struct msx_model {
     // stream layout of a linear for the persistent step kernel (step_kernel.cuh), keyed by its qs plane
     struct StreamW { const uint8_t *p = nullptr; int gran = 1; };
     std::unordered_map<const void *, StreamW> wstream;
+    // tc layout of a Q4_K linear for the tcgen05 prefill GEMM (tc_gemm.cuh), keyed by its qs plane
+    std::unordered_map<const void *, const uint8_t *> wtc;
     bool stream_ok = true;            // every linear of the decode step has a stream-layout copy of one weight type
     int stream_type = 0;
     QLinear dep_in_all;               // depformer_in[w_k] of all dep_q steps as ONE matrix [dep_q * dep_dim][dim] (stream layout only)
@@ -162,6 +164,15 @@ int upload_linear(msx_model *m, const void *host, int type, int64_t K, int64_t r
     if (m->tp_world == 1 && K % 256 == 0 && rows % (perm_half > 0 ? 2 : 1) == 0 && (m->stream_type == 0 || m->stream_type == type)) {
         if (int e = upload_stream(m, src_blocks, type, K, rows, perm_half, w.qs)) return e;
     } else m->stream_ok = false;
+    // third copy for the tensor-core prompt prefill: [128-row tile][super-block][row][GGUF block]
+    if (m->tp_world == 1 && type == T_Q4_K && K % 256 == 0 && rows % tc::kM == 0) {
+        void *wt = nullptr;
+        if (int e = dev_alloc(m, &wt, (size_t)rows * (K / 256) * 144)) return e;
+        const long long n = (long long)rows * (K / 256) * 9;
+        tc::tc_layout_kernel<<<(unsigned)((n + 255) / 256), 256>>>(src_blocks, (uint8_t *)wt, (int)rows, (int)(K / 256), perm_half);
+        CU(cudaGetLastError());
+        m->wtc[w.qs] = (const uint8_t *)wt;
+    }
     if (blocks_copy) CU(cudaMemcpyAsync(blocks_copy, src_blocks, (size_t)ggml_row_size(type, K) * rows, cudaMemcpyDeviceToDevice, 0));
     CU(cudaDeviceSynchronize());
     *out = w;

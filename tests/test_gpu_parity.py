@@ -428,10 +428,12 @@ def test_long_ring_7b_shapes_q8_0_vs_oracle(msx, orc, gguf_for, step_kernel):
                 assert np.array_equal(kg, ko) and np.array_equal(vg, vo), f"KV row layer {layer} head {head} slot {sl}"
 
 
-@pytest.mark.parametrize("preset,T,quant", [("tiny", 19, "q4_k"), ("tiny_pplex", 13, "q8_0"), ("moshi7b_l2", 11, "q4_k")])
+@pytest.mark.parametrize("preset,T,quant", [("tiny", 19, "q4_k"), ("tiny_pplex", 13, "q8_0"), ("moshi7b_l2", 11, "q4_k"), ("moshi7b_l2", 139, "q4_k"),
+                                            ("moshi7b_l2", 70, "q8_0")])
 def test_batched_prefill_vs_oracle(msx, orc, gguf_for, preset, T, quant):
-    """Prompt prefill (8 positions per weight pass, tensor-core GEMM) against the ORACLE's T serial steps: KV rows bit-identical,
-    logits of the frames that follow within tolerance (the prefill was only compared with the serial GPU path)."""
+    """Prompt prefill against the ORACLE's T serial steps: KV rows bit-identical, logits of the frames that follow within tolerance
+    (the prefill was only compared with the serial GPU path).  Q4_K models run 64 positions per weight pass on the
+    tcgen05 kind::i8 GEMM (tc_gemm.cuh: T = 139 = two full passes + a tail of 11 columns), Q8_0 models 8 per pass on mma.sync."""
     path, cfg = gguf_for(preset, quant)
     gm = msx.Model(path, cfg); gs = msx.Stream(gm)
     om = orc.Model(path, cfg); os_ = orc.State(om)
