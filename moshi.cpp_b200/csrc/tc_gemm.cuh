@@ -13,11 +13,13 @@
 // dmin * dx * imin (fp32 scale products, exact in double) accumulated in double, one rounding at the end.
 //
 // One CTA = one tile of 128 weight rows x all 64 columns; per super-block: (a) the 128 raw GGUF blocks (18 KB, contiguous in the
-// "tc layout" built at load) and the 64 x 256 int8 activations go to shared memory, (b) every thread expands half a block into the
-// two s8 operand tiles in the canonical K-major no-swizzle layout (8-row x 16-byte core matrices), (c) one thread issues 16
-// tcgen05.mma (M 128, N 64, K 32) into two 64-column accumulators and commits to an mbarrier, (d) eight warps read the
-// accumulators back with tcgen05.ld (warp = 32 TMEM lanes x 32 columns) and fold them into 32 double accumulators per thread.
-// Two CTAs per SM overlap each other's stages.  Descriptor encodings pinned by scripts/tcgen05_probe.cu.
+// "tc layout" built at load) and the 64 x 256 int8 activations go to shared memory by TMA, (b) every thread expands half a block into
+// the two s8 operand tiles in the canonical K-major no-swizzle layout (8-row x 16-byte core matrices), (c) one thread issues 16
+// tcgen05.mma (M 128, N 64, K 32) into two 64-column accumulators and commits to an mbarrier, (d) sixteen warps read the
+// accumulators back with tcgen05.ld (warp = 32 TMEM lanes x 16 columns) and fold them into 16 double accumulators per thread.
+// The accumulators are double-buffered in tensor memory, so the tensor cores work on super-block i + 1 while the CUDA cores fold
+// super-block i and expand super-block i + 2 (pipeline at the shared-memory map below).  Descriptor encodings pinned by
+// scripts/tcgen05_probe.cu.
 #pragma once
 #include "common.cuh"
 
@@ -35,18 +37,22 @@ __host__ __device__ inline size_t image_bytes(int K) { return (size_t)(K >> 8) *
 __host__ __device__ inline size_t image_x8_offset(int col, int k) {      // byte of activation k of column col
     return (size_t)(k >> 8) * kImgRec + (size_t)(col >> 3) * kSBO + (size_t)((k & 255) >> 4) * 128 + (size_t)(col & 7) * 16 + (k & 15);
 }
-// shared memory: two buffers of everything a super-block step touches, so that the expansion of step i + 1 runs while the
-// tensor cores work on step i (one CTA per SM: kernels that allocate tensor memory are not co-scheduled)
+// shared memory.  The step of super-block i has three phases on three engines: (1) TMA brings the raw blocks and the activation
+// record, (2) all threads expand the blocks into the two s8 operand tiles, (3) the tensor cores multiply, (4) all threads fold the
+// accumulators into their doubles.  Steady state of iteration i:  MMA(i + 1) on the tensor cores  ||  fold(i) + expand(i + 2) on the
+// CUDA cores  ||  raw(i + 3), raw(i + 4), record(i + 2), record(i + 3) in flight.  That takes two raw buffers, two operand buffers,
+// two accumulator sets in tensor memory, and three buffers of what the fold reads (block headers, activation sums / scales) and of
+// the activation tile (its record is one TMA target).  One CTA per SM.
 constexpr int kOffRaw = 0;                             // 2 x 18432 raw blocks
-constexpr int kOffHdr = kOffRaw + 2 * kRawBytes;       // 2 x {d | dmin, scales[12]} of the 128 rows
-constexpr int kOffAlo = kOffHdr + 2 * kM * 16;         // 2 x s8 [128][256]
+constexpr int kOffHdr = kOffRaw + 2 * kRawBytes;       // 3 x {d | dmin, scales[12]} of the 128 rows
+constexpr int kOffAlo = kOffHdr + 3 * kM * 16;         // 2 x s8 [128][256]
 constexpr int kOffAhi = kOffAlo + 2 * kOperandBytes;
-constexpr int kOffB = kOffAhi + 2 * kOperandBytes;     // 2 x s8 [64][256]
-constexpr int kOffAux = kOffB + 2 * kImgX8;            // 2 x {sums, scales}
-constexpr int kOffMisc = kOffAux + 2 * kImgAux;        // mbarriers, TMEM base
-constexpr int kSmemBytes = kOffMisc + 64;
+constexpr int kOffB = kOffAhi + 2 * kOperandBytes;     // 3 x s8 [64][256]
+constexpr int kOffAux = kOffB + 3 * kImgX8;            // 3 x {sums, scales}
+constexpr int kOffMisc = kOffAux + 3 * kImgAux;        // mbarriers, TMEM base
+constexpr int kSmemBytes = kOffMisc + 96;
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
-constexpr int kTmemCols = 128;                         // [0, 64): sc_lo product, [64, 128): sc_hi product
+constexpr int kTmemCols = 256;                         // set s at 128 s: [0, 64) sc_lo product, [64, 128) sc_hi product
 // instruction descriptor, kind::i8 (cute/arch/mma_sm100_desc.hpp): D = S32, A = B = signed 8 bit, both K-major, N >> 3, M >> 4
 constexpr uint32_t kIdesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kN >> 3) << 17) | ((uint32_t)(kM >> 4) << 24);
 
@@ -104,12 +110,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_q4k_kernel(const TcGemmAr
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t smem_u = (uint32_t)__cvta_generic_to_shared(smem);
-    const uint32_t bar_mma = smem_u + kOffMisc, bar_raw = bar_mma + 8 /* [2] */, bar_b = bar_mma + 24 /* [2] */;
-    uint32_t *slot = reinterpret_cast<uint32_t *>(smem + kOffMisc + 40);
+    const uint32_t bar_mma = smem_u + kOffMisc /* [2] */, bar_raw = bar_mma + 16 /* [2] */, bar_b = bar_mma + 32 /* [3] */;
+    uint32_t *slot = reinterpret_cast<uint32_t *>(smem + kOffMisc + 64);
     griddep_launch();
     if (tid == 0) {
-        mbar_init(bar_mma, 1);
-        for (int i = 0; i < 2; i++) { mbar_init(bar_raw + 8 * i, 1); mbar_init(bar_b + 8 * i, 1); }
+        for (int i = 0; i < 2; i++) { mbar_init(bar_mma + 8 * i, 1); mbar_init(bar_raw + 8 * i, 1); }
+        for (int i = 0; i < 3; i++) mbar_init(bar_b + 8 * i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -130,9 +136,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_q4k_kernel(const TcGemmAr
     };
     auto issue_b = [&](int it) {
         const uint8_t *rec = a.img + (size_t)(sb0 + it) * kImgRec;
-        mbar_expect_tx(bar_b + 8 * (it & 1), kImgRec);
-        bulk_g2s(smem_u + kOffB + (it & 1) * kImgX8, rec, kImgX8, bar_b + 8 * (it & 1));
-        bulk_g2s(smem_u + kOffAux + (it & 1) * kImgAux, rec + kImgX8, kImgAux, bar_b + 8 * (it & 1));
+        const int b3 = it % 3;
+        mbar_expect_tx(bar_b + 8 * b3, kImgRec);
+        bulk_g2s(smem_u + kOffB + b3 * kImgX8, rec, kImgX8, bar_b + 8 * b3);
+        bulk_g2s(smem_u + kOffAux + b3 * kImgAux, rec + kImgX8, kImgAux, bar_b + 8 * b3);
     };
     // expansion of step `it`: thread = (row, 64-weight group): nibbles x 3-bit halves of the two sub-block scales -> s8 operand tiles
     const int er = tid & 127, ej = tid >> 7;
@@ -141,7 +148,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_q4k_kernel(const TcGemmAr
         mbar_wait(bar_raw + 8 * buf, (uint32_t)((it >> 1) & 1));
         const uint8_t *blk = smem + kOffRaw + buf * kRawBytes + er * 144;
         const uint4 hd = *reinterpret_cast<const uint4 *>(blk);                             // {d | dmin, scales[12]}
-        if (ej == 0) *reinterpret_cast<uint4 *>(smem + kOffHdr + buf * (kM * 16) + er * 16) = hd;
+        if (ej == 0) *reinterpret_cast<uint4 *>(smem + kOffHdr + (it % 3) * (kM * 16) + er * 16) = hd;
         const uint32_t sc_lo = hd.y & 0x3f3f3f3fu, sc_hi = (hd.w & 0x0f0f0f0fu) | ((hd.y >> 2) & 0x30303030u);   // get_scale_min_k4
         uint8_t *alo = smem + kOffAlo + buf * kOperandBytes + (er >> 3) * kSBO + (er & 7) * 16;
         uint8_t *ahi = smem + kOffAhi + buf * kOperandBytes + (er >> 3) * kSBO + (er & 7) * 16;
@@ -165,47 +172,51 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_q4k_kernel(const TcGemmAr
         *reinterpret_cast<uint4 *>(ahi + (4 * j + 3) * 128) = make_uint4(hi[4] * hb, hi[5] * hb, hi[6] * hb, hi[7] * hb);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");        // generic-proxy stores -> visible to the tensor-core proxy
     };
+    // 2 x 8 MMAs of K = 32 on step `it` into accumulator set it & 1 (one thread; operands expanded and block-synchronised before)
+    auto issue_mma = [&](int it) {
+        const int buf = it & 1, b3 = it % 3;
+        mbar_wait(bar_b + 8 * b3, (uint32_t)((it / 3) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t td = tmem + buf * 128;
+#pragma unroll
+        for (int ks = 0; ks < 8; ks++) {
+            const uint64_t db = make_desc(smem_u + kOffB + b3 * kImgX8 + ks * 256);
+            mma_i8(td, make_desc(smem_u + kOffAlo + buf * kOperandBytes + ks * 256), db, ks > 0 ? 1u : 0u);
+            mma_i8(td + kN, make_desc(smem_u + kOffAhi + buf * kOperandBytes + ks * 256), db, ks > 0 ? 1u : 0u);
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_mma + 8 * buf) : "memory");
+    };
     if (tid == 0) { issue_raw(0); if (total > 1) issue_raw(1); }
     griddep_wait();                                   // the activation image comes from the quantise kernel (PDL)
-    if (tid == 0) issue_b(0);
+    if (tid == 0) for (int i = 0; i < 3 && i < total; i++) issue_b(i);
     expand(0);
     __syncthreads();
+    if (tid == 0) { if (total > 2) issue_raw(2); issue_mma(0); }
+    if (total > 1) expand(1);
+    __syncthreads();
+    if (tid == 0 && total > 3) issue_raw(3);
 
-    const int q = warp & 3, cg = warp >> 2;           // epilogue: TMEM lane quadrant, group of 16 columns
+    const int q = warp & 3, cg = warp >> 2;           // fold: TMEM lane quadrant, group of 16 columns
     const int row = q * 32 + lane;
     double acc[16];
 #pragma unroll
     for (int c = 0; c < 16; c++) acc[c] = 0.0;
 
     for (int it = 0; it < total; it++) {
-        const int buf = it & 1;
-        // ---- 2 x 8 MMAs of K = 32 on step `it`; the loads of the following steps go out ----
-        if (tid == 0) {
-            if (it + 1 < total) issue_b(it + 1);      // buffer of step it - 1, whose MMAs were waited for
-            mbar_wait(bar_b + 8 * buf, (uint32_t)((it >> 1) & 1));
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-            for (int ks = 0; ks < 8; ks++) {
-                const uint64_t db = make_desc(smem_u + kOffB + buf * kImgX8 + ks * 256);
-                mma_i8(tmem, make_desc(smem_u + kOffAlo + buf * kOperandBytes + ks * 256), db, ks > 0 ? 1u : 0u);
-                mma_i8(tmem + kN, make_desc(smem_u + kOffAhi + buf * kOperandBytes + ks * 256), db, ks > 0 ? 1u : 0u);
-            }
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_mma) : "memory");
-        }
-        // ---- while the tensor cores run: operands of step it + 1 ----
-        if (it + 1 < total) expand(it + 1);
-        mbar_wait(bar_mma, (uint32_t)(it & 1));
+        const int buf = it & 1, b3 = it % 3;
+        if (tid == 0 && it + 1 < total) issue_mma(it + 1);       // runs while this iteration folds step `it` and expands step it + 2
+        mbar_wait(bar_mma + 8 * buf, (uint32_t)((it >> 1) & 1));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         // ---- accumulators -> registers, block terms in double (arithmetic of gemv.cuh compute_step) ----
         {
-            const uint4 hd = *reinterpret_cast<const uint4 *>(smem + kOffHdr + buf * (kM * 16) + row * 16);
+            const uint4 hd = *reinterpret_cast<const uint4 *>(smem + kOffHdr + b3 * (kM * 16) + row * 16);
             const uint32_t m_lo = hd.z & 0x3f3f3f3fu, m_hi = ((hd.w >> 4) & 0x0f0f0f0fu) | ((hd.z >> 2) & 0x30303030u);
             const float2 dm = __half22float2(*reinterpret_cast<const __half2 *>(&hd.x));
-            const uint8_t *aux = smem + kOffAux + buf * kImgAux;
+            const uint8_t *aux = smem + kOffAux + b3 * kImgAux;
             const int4 *bs_s = reinterpret_cast<const int4 *>(aux);
             const float *dx_s = reinterpret_cast<const float *>(aux + kN * 16);
             uint32_t plo[16], phi[16];
-            const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + cg * 16;
+            const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + buf * 128 + cg * 16;
             tmem_ld16(ta, plo);
             tmem_ld16(ta + kN, phi);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -223,9 +234,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_q4k_kernel(const TcGemmAr
                 acc[c] = fma(-(double)(dm.y * dxv), int_to_double(imin), acc[c]);
             }
         }
+        // ---- operands of step it + 2 into the buffers step `it` has released ----
+        if (it + 2 < total) expand(it + 2);
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();                              // step it + 1 is expanded, tensor memory and the buffers of step it are free
-        if (tid == 0 && it + 2 < total) issue_raw(it + 2);
+        __syncthreads();                              // accumulator set and record buffer of step `it`, raw buffer of step it + 2: free
+        if (tid == 0) {
+            if (it + 3 < total) issue_b(it + 3);
+            if (it + 4 < total) issue_raw(it + 4);
+        }
     }
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
 
@@ -236,17 +252,20 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_q4k_kernel(const TcGemmAr
         for (int c = 0; c < 16; c++) mine[(cg * 16 + c) * kM + row] = acc[c];
         __threadfence();
         __syncthreads();
-        unsigned int *flag = reinterpret_cast<unsigned int *>(smem + kOffMisc + 48);
+        unsigned int *flag = reinterpret_cast<unsigned int *>(smem + kOffMisc + 72);
         if (tid == 0) *flag = atomicAdd(a.tickets + tile, 1u);
         __syncthreads();
         if (*flag != (unsigned)(P - 1)) return;       // not the last part of this tile
         __threadfence();
-        const double *all = a.partial + (size_t)tile * P * (kN * kM);
+        const double *all = a.partial + (size_t)tile * P * (kN * kM) + (cg * 16) * kM + row;
 #pragma unroll
-        for (int c = 0; c < 16; c++) {
-            double t = 0.0;
-            for (int pp = 0; pp < P; pp++) t += __ldcg(all + (size_t)pp * (kN * kM) + (cg * 16 + c) * kM + row);
-            acc[c] = t;
+        for (int c = 0; c < 16; c++) acc[c] = 0.0;
+        for (int pp = 0; pp < P; pp++) {              // part order; the 16 loads of a part are independent and in flight together
+            double t[16];
+#pragma unroll
+            for (int c = 0; c < 16; c++) t[c] = __ldcg(all + (size_t)pp * (kN * kM) + c * kM);
+#pragma unroll
+            for (int c = 0; c < 16; c++) acc[c] += t[c];
         }
         if (tid == 0) a.tickets[tile] = 0u;           // ready for the next launch
     }
