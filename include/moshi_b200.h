@@ -246,6 +246,9 @@ MSX_API int msx_gen_max_delay(const msx_gen *g);
  * depformer output are discarded, lm.h:933-943).  tokens [T][n_q+1].  Up to the end of the ring's first lap 8 positions go
  * through each weight pass; positions beyond it (every insert overwrites a slot the previous position still sees) one per pass. */
 MSX_API int msx_stream_prefill(msx_stream *s, const int32_t *tokens, int n_frames);
+/* profiling tool: tokens [1 + pass][n_q+1] = one prompt row, then ONE full prefill pass launched eagerly with an event after every
+ * launch -> per-family kernel time (family order of msx_family_name) */
+MSX_API int msx_stream_prefill_profile(msx_stream *s, const int32_t *tokens, float *family_ms, int32_t *family_launches, int max_families);
 
 /* ---- lock-step batch of independent streams (BASELINE.json config 5) ------------------
  * n_streams (1..8) conversations share every weight read: one activation-quantisation launch and one

@@ -174,6 +174,7 @@ def lib():
     L.msx_batch_get_logits.argtypes = [vp, C.c_int, vp, vp]
     L.msx_batch_run_resident.argtypes = [vp, vp, C.c_int, C.c_int, vp, C.POINTER(C.c_float)]
     L.msx_batch_profile_frame.argtypes = [vp, vp, vp, vp, C.c_int]
+    L.msx_stream_prefill_profile.argtypes = [vp, vp, vp, vp, C.c_int]
     L.msx_test_gemm_batch.argtypes = [C.c_int, C.c_int, vp, C.c_int64, C.c_int64, vp, C.c_int, vp, vp]
     L.msx_bench_gemm_batch_ex.argtypes = [C.c_int, vp, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), vp]
     L.msx_bench_gemm_batch.argtypes = [C.c_int, vp, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]
@@ -327,6 +328,14 @@ class Stream:
         """tokens [T][n_q+1]: batched-T prompt prefill (KV rings + position only)"""
         tk = np.ascontiguousarray(tokens, dtype=np.int32).reshape(-1, self.model.cfg["n_q"] + 1)
         _check(lib().msx_stream_prefill(self.h, _p(tk), tk.shape[0]))
+
+    def prefill_profile(self, tokens):
+        """tokens [1 + pass][n_q+1]: one prompt row, then one full prefill pass launched eagerly -> {family: (ms, launches)}"""
+        tk = np.ascontiguousarray(tokens, dtype=np.int32).reshape(-1, self.model.cfg["n_q"] + 1)
+        n = lib().msx_family_count()
+        ms = np.zeros(n, dtype=np.float32); cnt = np.zeros(n, dtype=np.int32)
+        _check(lib().msx_stream_prefill_profile(self.h, _p(tk), _p(ms), _p(cnt), n))
+        return {lib().msx_family_name(i).decode(): (float(ms[i]), int(cnt[i])) for i in range(n) if cnt[i]}
 
     def tp_export(self) -> bytes:
         buf = np.zeros(64, dtype=np.uint8)

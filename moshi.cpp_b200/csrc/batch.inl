@@ -29,7 +29,7 @@ struct msx_batch {
     msx_stream *prefill_of = nullptr;
     int n_active = 0;
     bool tc = false;                      // prefill with 64 columns per pass on the tcgen05 GEMM (tc_gemm.cuh) instead of 8 on mma.sync
-    double *tc_partial = nullptr; size_t tc_partial_bytes = 0;     // split-K partial sums [tile][part][64][128]
+    double *tc_partial = nullptr; int tc_max_tiles = 0;            // stream-K partial sums [cta][2][64][128]
     unsigned int *tc_tickets = nullptr;                            // [tiles] arrival counters (zero between launches)
     // sampling (sampling.h:46-64) per stream: temperature <= 0 = greedy; Exp(1) noise supplied by the host per frame
     float temp_text = 0.f, temp_audio = 0.f;
@@ -118,10 +118,10 @@ struct BatchLauncher {
             quant(x, ld, alpha, nullptr, 0, w.K, family);
             tc::TcGemmArgs g;
             g.w = b->m->wtc.at(w.qs); g.K = w.K; g.rows = w.rows; g.img = b->img; g.out = out; g.ld = out_ld; g.nb = b->n_active; g.epi = epi;
-            g.parts = tc::parts_for(w.rows / tc::kM, w.K >> 8, L.num_sms); g.partial = b->tc_partial; g.tickets = b->tc_tickets;
-            if ((size_t)(w.rows / tc::kM) * g.parts * tc::kN * tc::kM * 8 > b->tc_partial_bytes) { err = fail(MSX_ERR_STATE, "tc prefill: partial-sum buffer too small"); return; }
+            g.partial = b->tc_partial; g.tickets = b->tc_tickets;
+            if (w.rows / tc::kM > b->tc_max_tiles) { err = fail(MSX_ERR_STATE, "tc prefill: ticket array too small"); return; }
             L.fam = family; L.begin();
-            L.launch_pdl(tc::tc_gemm_q4k_kernel, dim3((w.rows / tc::kM) * g.parts), dim3(tc::kThreads), (size_t)tc::kSmemBytes, g);
+            L.launch_pdl(tc::tc_gemm_q4k_kernel, dim3(tc::grid_for(w.rows / tc::kM, w.K >> 8, L.num_sms)), dim3(tc::kThreads), (size_t)tc::kSmemBytes, g);
             L.check();
             return;
         }
@@ -361,14 +361,11 @@ static int batch_create_impl(msx_model *m, int n_streams, int context_override, 
     if (!tc_mode && gemm_stages_for(maxK, wt) < 2) return fail(MSX_ERR_ARG, "inner dimension too large for the batched GEMM's shared-memory image");
     if (int e = balloc(b.get(), (void **)&b->img, tc_mode ? tc::image_bytes(maxK) : (size_t)act_image_bytes(maxK, wt))) return e;
     if (tc_mode) {
-        size_t need = 0; int max_tiles = 0;
-        for (const QLinear *w : {&m->layers[0].in_proj[0], &m->layers[0].out_proj[0], &m->layers[0].lin_in[0], &m->layers[0].lin_out[0]}) {
-            const int tiles = w->rows / tc::kM;
-            need = std::max(need, (size_t)tiles * tc::parts_for(tiles, w->K >> 8, m->num_sms) * tc::kN * tc::kM * 8);
-            max_tiles = std::max(max_tiles, tiles);
-        }
-        b->tc_partial_bytes = need;
-        if (int e = balloc(b.get(), (void **)&b->tc_partial, need)) return e;
+        int max_tiles = 0;
+        for (const QLinear *w : {&m->layers[0].in_proj[0], &m->layers[0].out_proj[0], &m->layers[0].lin_in[0], &m->layers[0].lin_out[0]})
+            max_tiles = std::max(max_tiles, w->rows / tc::kM);
+        b->tc_max_tiles = max_tiles;
+        if (int e = balloc(b.get(), (void **)&b->tc_partial, tc::partial_bytes(m->num_sms))) return e;
         if (int e = balloc(b.get(), (void **)&b->tc_tickets, (size_t)max_tiles * 4)) return e;
     }
     if (int e = balloc(b.get(), (void **)&b->img_tout, (size_t)act_image_bytes(c.dim, wt))) return e;
@@ -437,6 +434,45 @@ extern "C" int msx_stream_prefill(msx_stream *s, const int32_t *tokens, int T) {
         }
     }
     s->host_offset += T;
+    CU(cudaMemcpyAsync(&s->ctrl->offset, &s->host_offset, 4, cudaMemcpyHostToDevice, s->st));
+    CU(cudaStreamSynchronize(s->st));
+    return 0;
+}
+
+// per-family kernel time of ONE eagerly launched full prefill pass (CUDA event after every launch; the positions are inserted like
+// msx_stream_prefill would, so the stream advances by the pass).  Tool for profiles/, not on the product path.
+extern "C" int msx_stream_prefill_profile(msx_stream *s, const int32_t *tokens, float *family_ms, int32_t *family_launches, int max_families) {
+    if (!s || !tokens || !family_ms || !family_launches) return fail(MSX_ERR_ARG, "null argument");
+    if (int e = msx_stream_prefill(s, tokens, 1)) return e;              // creates the prefill context
+    msx_batch *b = s->prefill; msx_model *m = s->m; const msx_config &c = m->cfg;
+    if (s->host_offset + b->n > s->cap) return fail(MSX_ERR_STATE, "no room for a full pass in the ring's first lap");
+    const int n_in = c.n_q + 1;
+    for (int i = 0; i < max_families; i++) { family_ms[i] = 0.f; family_launches[i] = 0; }
+    CU(cudaStreamSynchronize(b->st));
+    for (int j = 0; j < b->n; j++) {
+        Ctrl hdr; memset(&hdr, 0, sizeof(hdr));
+        hdr.offset = s->host_offset + j; hdr.n_in = n_in;
+        memcpy(b->h_hdr + (size_t)j * kCtrlInOffset, &hdr, kCtrlInOffset);
+    }
+    CU(cudaMemcpy2DAsync(b->ctrl, sizeof(Ctrl), b->h_hdr, kCtrlInOffset, kCtrlInOffset, b->n, cudaMemcpyHostToDevice, b->st));
+    if (int e = push_inputs_b(b, tokens + n_in)) return e;
+    std::vector<cudaEvent_t> ev;
+    std::vector<int> fam;
+    Launcher L{b->st, m->num_sms};
+    L.events = &ev; L.families = &fam;
+    BatchLauncher B{L, b};
+    enqueue_temporal_b(B);
+    if (B.err) return B.err;
+    if (L.err != cudaSuccess) return fail(MSX_ERR_CUDA, std::string("prefill launch: ") + cudaGetErrorString(L.err));
+    CU(cudaStreamSynchronize(b->st));
+    for (size_t i = 0; i + 1 < ev.size(); i++) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+        const int f = fam[i];
+        if (f < max_families) { family_ms[f] += ms; family_launches[f] += 1; }
+    }
+    for (cudaEvent_t e : ev) cudaEventDestroy(e);
+    s->host_offset += b->n;
     CU(cudaMemcpyAsync(&s->ctrl->offset, &s->host_offset, 4, cudaMemcpyHostToDevice, s->st));
     CU(cudaStreamSynchronize(s->st));
     return 0;

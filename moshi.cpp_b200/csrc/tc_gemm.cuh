@@ -26,7 +26,9 @@
 namespace msx {
 namespace tc {
 
-constexpr int kM = 128, kN = 64, kThreads = 512;
+constexpr int kM = 128, kN = 64;
+constexpr int kComputeThreads = 512;                   // 16 warps expand and fold; warp 16 issues the MMAs, warp 17 the TMA copies
+constexpr int kThreads = kComputeThreads + 64;
 constexpr int kRawBytes = kM * 144;                    // 128 Q4_K blocks of one super-block column
 constexpr int kOperandBytes = kM * 256;                // s8 [128][256]
 constexpr int kSBO = (256 / 16) * 128;                 // bytes between 8-row groups of an operand tile
@@ -37,20 +39,22 @@ __host__ __device__ inline size_t image_bytes(int K) { return (size_t)(K >> 8) *
 __host__ __device__ inline size_t image_x8_offset(int col, int k) {      // byte of activation k of column col
     return (size_t)(k >> 8) * kImgRec + (size_t)(col >> 3) * kSBO + (size_t)((k & 255) >> 4) * 128 + (size_t)(col & 7) * 16 + (k & 15);
 }
-// shared memory.  The step of super-block i has three phases on three engines: (1) TMA brings the raw blocks and the activation
-// record, (2) all threads expand the blocks into the two s8 operand tiles, (3) the tensor cores multiply, (4) all threads fold the
-// accumulators into their doubles.  Steady state of iteration i:  MMA(i + 1) on the tensor cores  ||  fold(i) + expand(i + 2) on the
-// CUDA cores  ||  raw(i + 3), raw(i + 4), record(i + 2), record(i + 3) in flight.  That takes two raw buffers, two operand buffers,
-// two accumulator sets in tensor memory, and three buffers of what the fold reads (block headers, activation sums / scales) and of
-// the activation tile (its record is one TMA target).  One CTA per SM.
+// shared memory.  The step of super-block i has four phases on three engines: (1) TMA brings the raw blocks and the activation
+// record, (2) the compute warps expand the blocks into the two s8 operand tiles, (3) the tensor cores multiply, (4) the compute warps
+// fold the accumulators into their doubles.  Warp-specialised: 16 compute warps, one MMA-issuing thread (warp 16), one TMA-issuing
+// thread (warp 17) — both instruction kinds block their issuing thread for ~1.5 us per step, which a compute thread cannot afford.
+// Steady state of iteration i:  MMA(i + 1) on the tensor cores  ||  fold(i) + expand(i + 2) on the CUDA cores  ||  raw(i + 3),
+// raw(i + 4), record(i + 2), record(i + 3) in flight.  That takes two raw buffers, two operand buffers, two accumulator sets in tensor
+// memory, three buffers of the activation record (tile + sums / scales, one TMA target) and four of the block headers (a compute
+// warp may run one iteration ahead of another: they meet only at the mbarrier that releases iteration i's buffers).  One CTA per SM.
 constexpr int kOffRaw = 0;                             // 2 x 18432 raw blocks
-constexpr int kOffHdr = kOffRaw + 2 * kRawBytes;       // 3 x {d | dmin, scales[12]} of the 128 rows
-constexpr int kOffAlo = kOffHdr + 3 * kM * 16;         // 2 x s8 [128][256]
+constexpr int kOffHdr = kOffRaw + 2 * kRawBytes;       // 4 x {d | dmin, scales[12]} of the 128 rows
+constexpr int kOffAlo = kOffHdr + 4 * kM * 16;         // 2 x s8 [128][256]
 constexpr int kOffAhi = kOffAlo + 2 * kOperandBytes;
 constexpr int kOffB = kOffAhi + 2 * kOperandBytes;     // 3 x s8 [64][256]
 constexpr int kOffAux = kOffB + 3 * kImgX8;            // 3 x {sums, scales}
 constexpr int kOffMisc = kOffAux + 3 * kImgAux;        // mbarriers, TMEM base
-constexpr int kSmemBytes = kOffMisc + 96;
+constexpr int kSmemBytes = kOffMisc + 96;             // 9 mbarriers, TMEM base, ticket flag
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 constexpr int kTmemCols = 256;                         // set s at 128 s: [0, 64) sc_lo product, [64, 128) sc_hi product
 // instruction descriptor, kind::i8 (cute/arch/mma_sm100_desc.hpp): D = S32, A = B = signed 8 bit, both K-major, N >> 3, M >> 4
@@ -62,23 +66,30 @@ struct TcGemmArgs {
     const uint8_t *img = nullptr;     // activation image (see image_bytes)
     float *out = nullptr;             // out[col * ld + row]
     int32_t ld = 0, nb = 0, epi = 0;  // live columns, EPI_STORE / EPI_RESID / EPI_GATE
-    // split-K: `parts` CTAs share a tile (each takes a range of super-blocks) so that every SM holds two CTAs also for the
-    // 4096-row matrices; they leave their double partial sums in `partial` [tile][part][64][128] and the last one to arrive
-    // (ticket in `tickets[tile]`) adds them in part order — a fixed order, so the result does not depend on timing
-    int32_t parts = 1;
+    // stream-K: the launch is one CTA per SM; the tiles x super-blocks steps of the matrix are one sequence (contiguous in the tc
+    // layout) cut into gridDim.x equal ranges, so every SM does the same number of steps whatever the row count.  A tile whose
+    // steps lie in several ranges is finished by the last CTA to arrive (ticket in `tickets[tile]`): every contributor leaves its
+    // double partial sums in `partial` [cta][first / later tile of the range][64][128] and the finisher adds them in range order
+    // — a fixed order, so the result does not depend on timing
     double *partial = nullptr;
     unsigned int *tickets = nullptr;
 };
-// parts that minimise (waves of one CTA per SM) x (fixed cost + super-blocks per CTA), plus the cost of the ordered reduction
-__host__ inline int parts_for(int n_tiles, int nsb, int num_sms) {
-    int best = 1; double best_t = 1e30;
-    for (int p = 1; p <= 8 && nsb / p >= 2; p++) {
-        const int ctas = n_tiles * p, waves = (ctas + num_sms - 1) / num_sms, per = (nsb + p - 1) / p;
-        const double t = waves * (4.0 + per * 2.2) + (p > 1 ? 3.0 + 0.5 * p : 0.0);
-        if (t < best_t) { best_t = t; best = p; }
-    }
-    return best;
+// CTAs of a launch.  More tiles than SMs: one range per SM (stream-K proper).  Fewer: either one range per SM again, or `p` aligned
+// ranges per tile (plain split-K: every CTA leaves exactly one partial tile and no tile is cut at an odd place) — whichever is
+// shorter by the measured costs of scripts/tc_gemm_probe.cu (2.1 us per step, ~3 us per partial tile left, ~0.7 us per part added up)
+__host__ inline int grid_for(int n_tiles, int nsb, int num_sms) {
+    const long long S = (long long)n_tiles * nsb;
+    if (S <= num_sms) return (int)S;
+    if (n_tiles >= num_sms) return num_sms;
+    int p = num_sms / n_tiles;
+    while (p > 1 && nsb % p) p--;
+    const double step = 2.1, left = 3.0, add = 0.7;
+    const double aligned = (nsb / p) * step + (p > 1 ? left + add * p : 0.0);
+    const double spread = (double)((S + num_sms - 1) / num_sms);
+    const double stream = spread * step + 2 * left + add * (nsb / spread + 2);
+    return aligned <= stream ? n_tiles * p : num_sms;
 }
+__host__ inline size_t partial_bytes(int num_sms) { return (size_t)num_sms * 2 * kN * kM * sizeof(double); }
 
 // shared-memory matrix descriptor: start >> 4 | LBO (128 B between the two core matrices of a K = 32 step) | SBO | version 1
 __device__ __forceinline__ uint64_t make_desc(uint32_t addr) {
@@ -94,27 +105,34 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
                    "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
                  : "r"(taddr) : "memory");
 }
-// The epilogue converts two integers and two fp32 scale products per (row, column, super-block) to double; the conversion
-// instructions run on the 8-lane XU pipe and would bound the kernel.  Integers go through the 2^52 trick (one XOR + one DADD),
-// the d * dx product is widened with integer operations when it is a normal number (else converted), only dmin * dx uses F2F.
+// The fold converts two integers and two fp32 scale products per (row, column, super-block) to double.  Integers go through the
+// 2^52 trick (one XOR + one DADD on the 64-lane double-precision pipe); the products use F2F.F64.F32 (16 lanes / clk / SM, measured
+// with scripts/fp64_rate_probe.cu) — building them with integer operations instead costs 8 issue slots each and measured 12 % slower
+// once the fold was the only thing left on the critical path (scripts/tc_gemm_probe.cu).
 __device__ __forceinline__ double int_to_double(int i) {
     return __hiloint2double(0x43300000, (int)((uint32_t)i ^ 0x80000000u)) - 4503601774854144.0;      // 2^52 + 2^31
 }
-__device__ __forceinline__ double widen_f32(float p) {
-    const uint32_t b = __float_as_uint(p), e = b & 0x7f800000u;
-    if (e == 0u || e == 0x7f800000u) return (double)p;                                              // zero, denormal, inf, nan
-    return __hiloint2double((int)((((b & 0x7fffffffu) >> 3) + 0x38000000u) | (b & 0x80000000u)), (int)(b << 29));
-}
+
+#ifdef MSX_TC_TIMELINE      // scripts/tc_gemm_probe.cu: per-iteration stamps of CTA 0, thread 0 {loop top, accumulators ready, fold done, expand done}
+__device__ long long *g_tc_timeline;
+#define TC_STAMP(i, k) do { if (blockIdx.x == 0 && tid == 0 && (i) < 64) g_tc_timeline[(i) * 4 + (k)] = clock64(); } while (0)
+#else
+#define TC_STAMP(i, k) do { } while (0)
+#endif
+
+__device__ __forceinline__ void compute_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kComputeThreads) : "memory"); }
 
 __global__ void __launch_bounds__(kThreads, 1) tc_gemm_q4k_kernel(const TcGemmArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    TC_STAMP(60, 0);
     const uint32_t smem_u = (uint32_t)__cvta_generic_to_shared(smem);
-    const uint32_t bar_mma = smem_u + kOffMisc /* [2] */, bar_raw = bar_mma + 16 /* [2] */, bar_b = bar_mma + 32 /* [3] */;
-    uint32_t *slot = reinterpret_cast<uint32_t *>(smem + kOffMisc + 64);
+    const uint32_t bar_mma = smem_u + kOffMisc /* [2] */, bar_raw = bar_mma + 16 /* [2] */, bar_b = bar_mma + 32 /* [3] */, bar_done = bar_mma + 56 /* [2] */;
+    uint32_t *slot = reinterpret_cast<uint32_t *>(smem + kOffMisc + 72);
+    unsigned int *flag = reinterpret_cast<unsigned int *>(smem + kOffMisc + 80);
     griddep_launch();
     if (tid == 0) {
-        for (int i = 0; i < 2; i++) { mbar_init(bar_mma + 8 * i, 1); mbar_init(bar_raw + 8 * i, 1); }
+        for (int i = 0; i < 2; i++) { mbar_init(bar_mma + 8 * i, 1); mbar_init(bar_raw + 8 * i, 1); mbar_init(bar_done + 8 * i, kComputeThreads / 32); }
         for (int i = 0; i < 3; i++) mbar_init(bar_b + 8 * i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -127,28 +145,29 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_q4k_kernel(const TcGemmAr
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *slot;
 
-    const int K = a.K, nsb = K >> 8, P = a.parts;
-    const int tile = blockIdx.x / P, part = blockIdx.x - tile * P;
-    const int sb0 = (int)((long long)nsb * part / P), total = (int)((long long)nsb * (part + 1) / P) - sb0;   // super-blocks of this CTA
+    const int K = a.K, nsb = K >> 8, G = (int)gridDim.x, cta = (int)blockIdx.x;
+    const long long S = (long long)(a.rows / kM) * nsb;                   // steps of the whole matrix
+    const int g0 = (int)(S * cta / G), total = (int)(S * (cta + 1) / G) - g0;       // this CTA: steps [g0, g0 + total), total >= 1
+    const bool is_mma = tid == kComputeThreads, is_tma = tid == kComputeThreads + 32, is_compute = tid < kComputeThreads;
     auto issue_raw = [&](int it) {                    // weights do not depend on the predecessor kernel
         mbar_expect_tx(bar_raw + 8 * (it & 1), kRawBytes);
-        bulk_g2s(smem_u + kOffRaw + (it & 1) * kRawBytes, a.w + ((size_t)tile * nsb + sb0 + it) * kRawBytes, kRawBytes, bar_raw + 8 * (it & 1));
+        bulk_g2s(smem_u + kOffRaw + (it & 1) * kRawBytes, a.w + (size_t)(g0 + it) * kRawBytes, kRawBytes, bar_raw + 8 * (it & 1));
     };
     auto issue_b = [&](int it) {
-        const uint8_t *rec = a.img + (size_t)(sb0 + it) * kImgRec;
+        const uint8_t *rec = a.img + (size_t)((g0 + it) % nsb) * kImgRec;
         const int b3 = it % 3;
         mbar_expect_tx(bar_b + 8 * b3, kImgRec);
         bulk_g2s(smem_u + kOffB + b3 * kImgX8, rec, kImgX8, bar_b + 8 * b3);
         bulk_g2s(smem_u + kOffAux + b3 * kImgAux, rec + kImgX8, kImgAux, bar_b + 8 * b3);
     };
     // expansion of step `it`: thread = (row, 64-weight group): nibbles x 3-bit halves of the two sub-block scales -> s8 operand tiles
-    const int er = tid & 127, ej = tid >> 7;
+    const int er = tid & 127, ej = (tid >> 7) & 3;
     auto expand = [&](int it) {
         const int buf = it & 1;
         mbar_wait(bar_raw + 8 * buf, (uint32_t)((it >> 1) & 1));
         const uint8_t *blk = smem + kOffRaw + buf * kRawBytes + er * 144;
         const uint4 hd = *reinterpret_cast<const uint4 *>(blk);                             // {d | dmin, scales[12]}
-        if (ej == 0) *reinterpret_cast<uint4 *>(smem + kOffHdr + (it % 3) * (kM * 16) + er * 16) = hd;
+        if (ej == 0) *reinterpret_cast<uint4 *>(smem + kOffHdr + (it & 3) * (kM * 16) + er * 16) = hd;
         const uint32_t sc_lo = hd.y & 0x3f3f3f3fu, sc_hi = (hd.w & 0x0f0f0f0fu) | ((hd.y >> 2) & 0x30303030u);   // get_scale_min_k4
         uint8_t *alo = smem + kOffAlo + buf * kOperandBytes + (er >> 3) * kSBO + (er & 7) * 16;
         uint8_t *ahi = smem + kOffAhi + buf * kOperandBytes + (er >> 3) * kSBO + (er & 7) * 16;
@@ -172,7 +191,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_q4k_kernel(const TcGemmAr
         *reinterpret_cast<uint4 *>(ahi + (4 * j + 3) * 128) = make_uint4(hi[4] * hb, hi[5] * hb, hi[6] * hb, hi[7] * hb);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");        // generic-proxy stores -> visible to the tensor-core proxy
     };
-    // 2 x 8 MMAs of K = 32 on step `it` into accumulator set it & 1 (one thread; operands expanded and block-synchronised before)
+    // 2 x 8 MMAs of K = 32 on step `it` into accumulator set it & 1 (one thread; operands expanded and synchronised before)
     auto issue_mma = [&](int it) {
         const int buf = it & 1, b3 = it % 3;
         mbar_wait(bar_b + 8 * b3, (uint32_t)((it / 3) & 1));
@@ -186,30 +205,42 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_q4k_kernel(const TcGemmAr
         }
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_mma + 8 * buf) : "memory");
     };
-    if (tid == 0) { issue_raw(0); if (total > 1) issue_raw(1); }
+    // ---- start-up (all warps): two steps expanded, the first multiplication under way ----
+    if (is_tma) { issue_raw(0); if (total > 1) issue_raw(1); }
     griddep_wait();                                   // the activation image comes from the quantise kernel (PDL)
-    if (tid == 0) for (int i = 0; i < 3 && i < total; i++) issue_b(i);
-    expand(0);
+    if (is_tma) for (int i = 0; i < 3 && i < total; i++) issue_b(i);
+    if (is_compute) expand(0);
     __syncthreads();
-    if (tid == 0) { if (total > 2) issue_raw(2); issue_mma(0); }
-    if (total > 1) expand(1);
+    if (is_tma && total > 2) issue_raw(2);
+    if (is_mma) issue_mma(0);
+    if (is_compute && total > 1) expand(1);
     __syncthreads();
-    if (tid == 0 && total > 3) issue_raw(3);
+    if (is_tma && total > 3) issue_raw(3);
 
-    const int q = warp & 3, cg = warp >> 2;           // fold: TMEM lane quadrant, group of 16 columns
-    const int row = q * 32 + lane;
-    double acc[16];
+    if (is_mma) {
+        // ---- tensor-core issuer: step it + 1 as soon as the compute warps are through iteration it - 1 (operands of it + 1 expanded,
+        //      accumulator set of it - 1 folded) ----
+        for (int it = 0; it + 1 < total; it++) {
+            if (it >= 1) mbar_wait(bar_done + 8 * ((it - 1) & 1), (uint32_t)(((it - 1) >> 1) & 1));
+            issue_mma(it + 1);
+        }
+    } else if (is_tma) {
+        // ---- loader: the buffers iteration `it` released take the record of step it + 3 and the raw blocks of step it + 4 ----
+        for (int it = 0; it + 3 < total; it++) {
+            mbar_wait(bar_done + 8 * (it & 1), (uint32_t)((it >> 1) & 1));
+            issue_b(it + 3);
+            if (it + 4 < total) issue_raw(it + 4);
+        }
+    } else if (is_compute) {
+        const int q = warp & 3, cg = warp >> 2;       // fold: TMEM lane quadrant, group of 16 columns
+        const int row = q * 32 + lane;
+        double acc[16];
 #pragma unroll
-    for (int c = 0; c < 16; c++) acc[c] = 0.0;
-
-    for (int it = 0; it < total; it++) {
-        const int buf = it & 1, b3 = it % 3;
-        if (tid == 0 && it + 1 < total) issue_mma(it + 1);       // runs while this iteration folds step `it` and expands step it + 2
-        mbar_wait(bar_mma + 8 * buf, (uint32_t)((it >> 1) & 1));
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // ---- accumulators -> registers, block terms in double (arithmetic of gemv.cuh compute_step) ----
-        {
-            const uint4 hd = *reinterpret_cast<const uint4 *>(smem + kOffHdr + b3 * (kM * 16) + row * 16);
+        for (int c = 0; c < 16; c++) acc[c] = 0.0;
+        // block terms in double (arithmetic of gemv.cuh compute_step) from accumulator set it & 1
+        auto fold = [&](int it) {
+            const int buf = it & 1, b3 = it % 3;
+            const uint4 hd = *reinterpret_cast<const uint4 *>(smem + kOffHdr + (it & 3) * (kM * 16) + row * 16);
             const uint32_t m_lo = hd.z & 0x3f3f3f3fu, m_hi = ((hd.w >> 4) & 0x0f0f0f0fu) | ((hd.z >> 2) & 0x30303030u);
             const float2 dm = __half22float2(*reinterpret_cast<const __half2 *>(&hd.x));
             const uint8_t *aux = smem + kOffAux + b3 * kImgAux;
@@ -230,58 +261,102 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_q4k_kernel(const TcGemmAr
                 imin = __dp2a_hi(b4.y, (int)m_lo, imin);
                 imin = __dp2a_lo(b4.z, (int)m_hi, imin);
                 imin = __dp2a_hi(b4.w, (int)m_hi, imin);
-                acc[c] = fma(widen_f32(dm.x * dxv), int_to_double(isum), acc[c]);
+                acc[c] = fma((double)(dm.x * dxv), int_to_double(isum), acc[c]);
                 acc[c] = fma(-(double)(dm.y * dxv), int_to_double(imin), acc[c]);
             }
-        }
-        // ---- operands of step it + 2 into the buffers step `it` has released ----
-        if (it + 2 < total) expand(it + 2);
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();                              // accumulator set and record buffer of step `it`, raw buffer of step it + 2: free
-        if (tid == 0) {
-            if (it + 3 < total) issue_b(it + 3);
-            if (it + 4 < total) issue_raw(it + 4);
+        };
+        // range of the step sequence that holds step g: the largest c with floor(S c / G) <= g
+        auto owner = [&](long long g) { return (int)(((g + 1) * G - 1) / S); };
+        // end of this CTA's steps of `tile`: finish it (alone, or as the last of its contributors) or leave the partial sums
+        auto flush = [&](int tile) {
+            const int c_first = owner((long long)tile * nsb), c_last = owner((long long)tile * nsb + nsb - 1);
+            if (c_first != c_last) {
+                double *mine = a.partial + ((size_t)cta * 2 + (tile != g0 / nsb ? 1 : 0)) * (kN * kM) + (cg * 16) * kM + row;
+#pragma unroll
+                for (int c = 0; c < 16; c++) __stcg(mine + c * kM, acc[c]);
+                compute_barrier();
+                if (tid == 0) { __threadfence(); *flag = atomicAdd(a.tickets + tile, 1u); }
+                compute_barrier();
+                if (*flag != (unsigned)(c_last - c_first)) return;           // another contributor finishes this tile
+                __threadfence();
+#pragma unroll
+                for (int c = 0; c < 16; c++) acc[c] = 0.0;
+                auto part_of = [&](int cc) {
+                    return a.partial + ((size_t)cc * 2 + (tile != (int)(S * cc / G) / nsb ? 1 : 0)) * (kN * kM) + (cg * 16) * kM + row;
+                };
+                for (int cc = c_first; cc <= c_last; cc += 2) {               // range order = super-block order; two ranges' loads in flight
+                    const double *s0 = part_of(cc), *s1 = part_of(cc + 1 <= c_last ? cc + 1 : cc);
+                    double t0[16], t1[16];
+#pragma unroll
+                    for (int c = 0; c < 16; c++) { t0[c] = __ldcg(s0 + c * kM); t1[c] = __ldcg(s1 + c * kM); }
+                    const bool two = cc + 1 <= c_last;
+#pragma unroll
+                    for (int c = 0; c < 16; c++) { acc[c] += t0[c]; if (two) acc[c] += t1[c]; }
+                }
+                if (tid == 0) a.tickets[tile] = 0u;                            // ready for the next launch
+            }
+            const int grow = tile * kM + row;
+            if (a.epi == EPI_GATE) {
+                // (gate, up) rows are adjacent lanes.  The even lane finishes columns 0..7 of the pair's row, the odd lane columns 8..15,
+                // so every lane evaluates 8 double-precision exponentials instead of 16 with half of the lanes idle
+#pragma unroll
+                for (int c = 0; c < 8; c++) {
+                    const float lo = (float)acc[c], hi = (float)acc[c + 8];
+                    const float recv = __shfl_xor_sync(0xffffffffu, (lane & 1) ? lo : hi, 1);
+                    const float gte = (lane & 1) ? recv : lo, up = (lane & 1) ? hi : recv;
+                    const int col = cg * 16 + c + ((lane & 1) ? 8 : 0);
+                    if (col < a.nb) a.out[(size_t)col * a.ld + (grow >> 1)] = (gte / (1.0f + (float)exp((double)(-gte)))) * up;
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < 16; c++) {
+                    const int col = cg * 16 + c;
+                    if (col < a.nb) {
+                        float *o = a.out + (size_t)col * a.ld + grow;
+                        const float v = (float)acc[c];
+                        *o = a.epi == EPI_RESID ? *o + v : v;
+                    }
+                }
+            }
+        };
+        TC_STAMP(60, 1);
+        for (int it = 0; it < total; it++) {
+            const int buf = it & 1;
+            TC_STAMP(it, 0);
+            mbar_wait(bar_mma + 8 * buf, (uint32_t)((it >> 1) & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            TC_STAMP(it, 1);
+            // fold step `it`; operands of step it + 2 into the buffers step `it` has released.  Half of the warps take the two in the
+            // other order, so that the conversion / double-precision pipes and the integer / shared-memory pipes are busy at the same time
+            if (cg & 1) {
+                if (it + 2 < total) expand(it + 2);
+                fold(it);
+            } else {
+                fold(it);
+                TC_STAMP(it, 2);
+                if (it + 2 < total) expand(it + 2);
+            }
+            TC_STAMP(it, 3);
+            // this warp is through iteration `it` (no block barrier: the warps drift apart, which spreads their fold and expand phases
+            // over time); when all 16 have arrived the accumulator set and record buffer of step `it` and the raw buffer of step
+            // it + 2 are free, and the operands of step it + 2 are complete
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_done + 8 * buf);
+            const int g = g0 + it;
+            if (g % nsb == nsb - 1 || it == total - 1) {
+                TC_STAMP(61 + (it == total - 1 ? 1 : 0), 0);
+                flush(g / nsb);
+                TC_STAMP(61 + (it == total - 1 ? 1 : 0), 1);
+#pragma unroll
+                for (int c = 0; c < 16; c++) acc[c] = 0.0;
+            }
         }
     }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    TC_STAMP(60, 2);
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
-
-    // ---- tile epilogue: thread = row, 32 columns ----
-    if (P > 1) {
-        double *mine = a.partial + ((size_t)tile * P + part) * (kN * kM);
-#pragma unroll
-        for (int c = 0; c < 16; c++) mine[(cg * 16 + c) * kM + row] = acc[c];
-        __threadfence();
-        __syncthreads();
-        unsigned int *flag = reinterpret_cast<unsigned int *>(smem + kOffMisc + 72);
-        if (tid == 0) *flag = atomicAdd(a.tickets + tile, 1u);
-        __syncthreads();
-        if (*flag != (unsigned)(P - 1)) return;       // not the last part of this tile
-        __threadfence();
-        const double *all = a.partial + (size_t)tile * P * (kN * kM) + (cg * 16) * kM + row;
-#pragma unroll
-        for (int c = 0; c < 16; c++) acc[c] = 0.0;
-        for (int pp = 0; pp < P; pp++) {              // part order; the 16 loads of a part are independent and in flight together
-            double t[16];
-#pragma unroll
-            for (int c = 0; c < 16; c++) t[c] = __ldcg(all + (size_t)pp * (kN * kM) + c * kM);
-#pragma unroll
-            for (int c = 0; c < 16; c++) acc[c] += t[c];
-        }
-        if (tid == 0) a.tickets[tile] = 0u;           // ready for the next launch
-    }
-    const int grow = tile * kM + row;
-#pragma unroll
-    for (int c = 0; c < 16; c++) {
-        const int col = cg * 16 + c;
-        const float v = (float)acc[c];
-        if (a.epi == EPI_GATE) {
-            const float u = __shfl_down_sync(0xffffffffu, v, 1);                                     // (gate, up) rows are adjacent
-            if (col < a.nb && (lane & 1) == 0) a.out[(size_t)col * a.ld + (grow >> 1)] = (v / (1.0f + (float)exp((double)(-v)))) * u;
-        } else if (col < a.nb) {
-            float *o = a.out + (size_t)col * a.ld + grow;
-            *o = a.epi == EPI_RESID ? *o + v : v;
-        }
-    }
 }
 
 // GGUF row-major Q4_K blocks -> tc layout.  One thread per 16-byte piece; perm_half > 0 interleaves rows for the gated MLP
