@@ -114,15 +114,9 @@ struct BatchLauncher {
     }
     // y = W (norm?)(x): one launch with the fused prologue when the inner dimension is short, else quantise + GEMM
     void linear(const float *x, int ld, const float *alpha, const QLinear &w, float *out, int out_ld, int epi, int family, int key_index = -1) {
-        if (b->tc) {                     // 64 prompt columns: quantise (plain image) + tcgen05 GEMM
+        if (b->tc) {                     // more than 8 columns: quantise (plain image) + tcgen05 GEMM
             quant(x, ld, alpha, nullptr, 0, w.K, family);
-            tc::TcGemmArgs g;
-            g.w = b->m->wtc.at(w.qs); g.K = w.K; g.rows = w.rows; g.img = b->img; g.out = out; g.ld = out_ld; g.nb = b->n_active; g.epi = epi;
-            g.partial = b->tc_partial; g.tickets = b->tc_tickets;
-            if (w.rows / tc::kM > b->tc_max_tiles) { err = fail(MSX_ERR_STATE, "tc prefill: ticket array too small"); return; }
-            L.fam = family; L.begin();
-            L.launch_pdl(tc::tc_gemm_q4k_kernel, dim3(tc::grid_for(w.rows / tc::kM, w.K >> 8, L.num_sms)), dim3(tc::kThreads), (size_t)tc::kSmemBytes, g);
-            L.check();
+            gemm(w, out, out_ld, epi, family, key_index);
             return;
         }
         if (fuse_small && w.type == T_Q4_K && gemm_can_fuse_quant(w.K, b->n_active)) {
@@ -133,8 +127,35 @@ struct BatchLauncher {
         }
     }
     bool fuse_small = true;
+    // tcgen05 GEMM over the quantised image (tc_gemm.cuh); arg-max and embedding-add epilogues run as a small kernel behind it
+    void tc_gemm(const QLinear &w, float *out, int ld, int epi, int family, int key_index, const EmbTable *emb, int emb_step, const uint8_t *img) {
+        auto it = b->m->wtc.find(w.qs);
+        if (it == b->m->wtc.end()) { err = fail(MSX_ERR_STATE, "linear without a tensor-core layout in a wide batch"); return; }
+        tc::TcGemmArgs g;
+        g.w = it->second; g.K = w.K; g.rows = w.rows; g.img = img ? img : b->img; g.out = out; g.ld = ld; g.nb = b->n_active;
+        g.epi = (epi == EPI_ARGMAX || epi == EPI_ADD_EMB) ? (int)EPI_STORE : epi;
+        g.partial = b->tc_partial; g.tickets = b->tc_tickets;
+        if (w.rows / tc::kM > b->tc_max_tiles) { err = fail(MSX_ERR_STATE, "tc gemm: ticket array too small"); return; }
+        const dim3 grid(tc::grid_for(w.rows / tc::kM, w.K >> 8, L.num_sms)), block(tc::kThreads);
+        L.fam = family; L.begin();
+        const int nc = tc::columns_for(b->n_active);
+        if (nc == 16) L.launch_pdl(tc::tc_gemm_q4k_kernel<16>, grid, block, (size_t)tc::kSmemBytes, g);
+        else if (nc == 32) L.launch_pdl(tc::tc_gemm_q4k_kernel<32>, grid, block, (size_t)tc::kSmemBytes, g);
+        else L.launch_pdl(tc::tc_gemm_q4k_kernel<64>, grid, block, (size_t)tc::kSmemBytes, g);
+        L.check();
+        if (epi == EPI_ARGMAX) {
+            L.begin();
+            L.launch_pdl(tc::argmax_rows_kernel, dim3(b->n_active), dim3(256), 0, (const float *)out, ld, w.rows, b->ctrl, key_index);
+            L.check();
+        } else if (epi == EPI_ADD_EMB) {
+            L.begin();
+            L.launch_pdl(tc::dep_embed_add_cols_kernel, dim3((w.rows + 255) / 256, b->n_active), dim3(256), 0, (const Ctrl *)b->ctrl, *emb, emb_step, out, ld, w.rows);
+            L.check();
+        }
+    }
     void gemm(const QLinear &w, float *out, int ld, int epi, int family, int key_index = -1, const EmbTable *emb = nullptr, int emb_step = 0,
               const uint8_t *img = nullptr, const float *xsrc = nullptr, int xld = 0, const float *alpha = nullptr) {
+        if (b->tc) { tc_gemm(w, out, ld, epi, family, key_index, emb, emb_step, img); return; }
         GemmArgs g;
         if (int e = tiles_of(b->m, w, &g.w)) { err = e; return; }
         g.xsrc = xsrc; g.xld = xld; g.alpha = alpha; g.eps = 1e-8f;
@@ -297,6 +318,16 @@ static bool tc_prefill_ok(const msx_model *m) {
             if (!m->wtc.count(w->qs)) return false;
     return true;
 }
+// every linear of the whole decode step has the tc layout: batches of more than 8 streams run on the tcgen05 GEMM
+static bool tc_batch_ok(const msx_model *m) {
+    if (!tc_prefill_ok(m) || !m->wtc.count(m->text_linear.qs)) return false;
+    for (const QLinear &w : m->dep_in) if (!m->wtc.count(w.qs)) return false;
+    for (const QLinear &w : m->linears) if (!m->wtc.count(w.qs)) return false;
+    for (const LayerW &l : m->dep_layers)
+        for (const std::vector<QLinear> *v : {&l.in_proj, &l.out_proj, &l.lin_in, &l.lin_out})
+            for (const QLinear &w : *v) if (!m->wtc.count(w.qs)) return false;
+    return true;
+}
 extern "C" int msx_batch_create(msx_model *m, int n_streams, int context_override, msx_batch **out) {
     return batch_create_impl(m, n_streams, context_override, nullptr, out);
 }
@@ -304,8 +335,10 @@ static int batch_create_impl(msx_model *m, int n_streams, int context_override, 
     if (!m || !out) return fail(MSX_ERR_ARG, "null argument");
     *out = nullptr;
     // a prefill context of 64 columns runs its linears on the tcgen05 GEMM (Q4_K models whose temporal linears have the tc layout)
-    const bool tc_mode = prefill_of && n_streams == tc::kN && tc_prefill_ok(m);
-    if (n_streams < 1 || (n_streams > kMmaCols && !tc_mode)) return fail(MSX_ERR_ARG, "a batch holds 1..8 streams");
+    // ... and so does a batch of 9..64 streams when every linear of the step has it
+    const bool tc_mode = prefill_of ? (n_streams == tc::kN && tc_prefill_ok(m)) : (n_streams > kMmaCols && n_streams <= tc::kN && tc_batch_ok(m));
+    if (n_streams < 1 || (n_streams > kMmaCols && !tc_mode))
+        return fail(MSX_ERR_ARG, "a batch holds 1..8 streams (up to 64 for Q4_K models whose linears all have 128-row tiles and 256-multiple inner dimensions)");
     if (m->cfg.cross_attention || m->cfg.demux_second_stream || m->cfg.dep_low_rank)
         return fail(MSX_ERR_ARG, "batched streams do not cover the TTS-family layers (cross-attention, demux / low-rank embeddings)");
     CU(cudaSetDevice(m->device));
@@ -316,7 +349,9 @@ static int batch_create_impl(msx_model *m, int n_streams, int context_override, 
     CU(cudaFuncSetAttribute(gemm_mma_kernel<8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemMax));
     CU(cudaFuncSetAttribute(gemm_mma_kernel<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemMax));
     if (tc_mode) {
-        CU(cudaFuncSetAttribute(tc::tc_gemm_q4k_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes));
+        CU(cudaFuncSetAttribute(tc::tc_gemm_q4k_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes));
+        CU(cudaFuncSetAttribute(tc::tc_gemm_q4k_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes));
+        CU(cudaFuncSetAttribute(tc::tc_gemm_q4k_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes));
     }
     else if (int e = ensure_all_tiles(m)) return e;
     std::unique_ptr<msx_batch> b(new msx_batch);
@@ -362,13 +397,18 @@ static int batch_create_impl(msx_model *m, int n_streams, int context_override, 
     if (int e = balloc(b.get(), (void **)&b->img, tc_mode ? tc::image_bytes(maxK) : (size_t)act_image_bytes(maxK, wt))) return e;
     if (tc_mode) {
         int max_tiles = 0;
-        for (const QLinear *w : {&m->layers[0].in_proj[0], &m->layers[0].out_proj[0], &m->layers[0].lin_in[0], &m->layers[0].lin_out[0]})
+        for (const QLinear *w : {&m->layers[0].in_proj[0], &m->layers[0].out_proj[0], &m->layers[0].lin_in[0], &m->layers[0].lin_out[0], &m->text_linear})
             max_tiles = std::max(max_tiles, w->rows / tc::kM);
+        for (const LayerW &l : m->dep_layers)
+            for (const std::vector<QLinear> *v : {&l.in_proj, &l.out_proj, &l.lin_in, &l.lin_out})
+                for (const QLinear &w : *v) max_tiles = std::max(max_tiles, w.rows / tc::kM);
+        for (const QLinear &w : m->dep_in) max_tiles = std::max(max_tiles, w.rows / tc::kM);
+        for (const QLinear &w : m->linears) max_tiles = std::max(max_tiles, w.rows / tc::kM);
         b->tc_max_tiles = max_tiles;
         if (int e = balloc(b.get(), (void **)&b->tc_partial, tc::partial_bytes(m->num_sms))) return e;
         if (int e = balloc(b.get(), (void **)&b->tc_tickets, (size_t)max_tiles * 4)) return e;
     }
-    if (int e = balloc(b.get(), (void **)&b->img_tout, (size_t)act_image_bytes(c.dim, wt))) return e;
+    if (int e = balloc(b.get(), (void **)&b->img_tout, tc_mode ? tc::image_bytes(c.dim) : (size_t)act_image_bytes(c.dim, wt))) return e;
     if (!prefill_of) {
         const size_t nf = n * (1 + MSX_MAX_STEPS) * kSampleMaxK;
         if (int e = balloc(b.get(), (void **)&b->d_noise, nf * 4)) return e;

@@ -58,7 +58,7 @@ constexpr int kSmemBytes = kOffMisc + 96;             // 9 mbarriers, TMEM base,
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 constexpr int kTmemCols = 256;                         // set s at 128 s: [0, 64) sc_lo product, [64, 128) sc_hi product
 // instruction descriptor, kind::i8 (cute/arch/mma_sm100_desc.hpp): D = S32, A = B = signed 8 bit, both K-major, N >> 3, M >> 4
-constexpr uint32_t kIdesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kN >> 3) << 17) | ((uint32_t)(kM >> 4) << 24);
+__host__ __device__ constexpr uint32_t idesc_for(int n) { return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kM >> 4) << 24); }
 
 struct TcGemmArgs {
     const uint8_t *w = nullptr;       // tc layout: [rows / 128][K / 256][128 rows][144 B]
@@ -95,15 +95,23 @@ __host__ inline size_t partial_bytes(int num_sms) { return (size_t)num_sms * 2 *
 __device__ __forceinline__ uint64_t make_desc(uint32_t addr) {
     return (uint64_t)((addr & 0x3ffffu) >> 4) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(kSBO >> 4) << 32) | (1ull << 46);
 }
-__device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+__device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
     asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}"
-                 ::"r"(tmem_d), "l"(da), "l"(db), "r"(kIdesc), "r"(accumulate) : "memory");
+                 ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+template <int N> __device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t (&r)[N]);
+template <> __device__ __forceinline__ void tmem_ld<16>(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]),
                    "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
                  : "r"(taddr) : "memory");
+}
+template <> __device__ __forceinline__ void tmem_ld<8>(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr) : "memory");
+}
+template <> __device__ __forceinline__ void tmem_ld<4>(uint32_t taddr, uint32_t (&r)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
 }
 // The fold converts two integers and two fp32 scale products per (row, column, super-block) to double.  Integers go through the
 // 2^52 trick (one XOR + one DADD on the 64-lane double-precision pipe); the products use F2F.F64.F32 (16 lanes / clk / SM, measured
@@ -122,7 +130,11 @@ __device__ long long *g_tc_timeline;
 
 __device__ __forceinline__ void compute_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kComputeThreads) : "memory"); }
 
+// NC = live activation columns rounded up to 16 / 32 / 64: the MMA's N, the columns a thread folds (NC / 4) and the bytes of the
+// activation tile a step copies all scale with it, so a batch of 16 streams does not pay for 64
+template <int NC>
 __global__ void __launch_bounds__(kThreads, 1) tc_gemm_q4k_kernel(const TcGemmArgs a) {
+    constexpr int FC = NC / 4;                        // columns per compute thread
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     TC_STAMP(60, 0);
@@ -156,8 +168,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_q4k_kernel(const TcGemmAr
     auto issue_b = [&](int it) {
         const uint8_t *rec = a.img + (size_t)((g0 + it) % nsb) * kImgRec;
         const int b3 = it % 3;
-        mbar_expect_tx(bar_b + 8 * b3, kImgRec);
-        bulk_g2s(smem_u + kOffB + b3 * kImgX8, rec, kImgX8, bar_b + 8 * b3);
+        mbar_expect_tx(bar_b + 8 * b3, NC * 256 + kImgAux);
+        bulk_g2s(smem_u + kOffB + b3 * kImgX8, rec, NC * 256, bar_b + 8 * b3);          // columns [0, NC): NC / 8 groups of 2048 B
         bulk_g2s(smem_u + kOffAux + b3 * kImgAux, rec + kImgX8, kImgAux, bar_b + 8 * b3);
     };
     // expansion of step `it`: thread = (row, 64-weight group): nibbles x 3-bit halves of the two sub-block scales -> s8 operand tiles
@@ -200,8 +212,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_q4k_kernel(const TcGemmAr
 #pragma unroll
         for (int ks = 0; ks < 8; ks++) {
             const uint64_t db = make_desc(smem_u + kOffB + b3 * kImgX8 + ks * 256);
-            mma_i8(td, make_desc(smem_u + kOffAlo + buf * kOperandBytes + ks * 256), db, ks > 0 ? 1u : 0u);
-            mma_i8(td + kN, make_desc(smem_u + kOffAhi + buf * kOperandBytes + ks * 256), db, ks > 0 ? 1u : 0u);
+            mma_i8(td, make_desc(smem_u + kOffAlo + buf * kOperandBytes + ks * 256), db, idesc_for(NC), ks > 0 ? 1u : 0u);
+            mma_i8(td + kN, make_desc(smem_u + kOffAhi + buf * kOperandBytes + ks * 256), db, idesc_for(NC), ks > 0 ? 1u : 0u);
         }
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_mma + 8 * buf) : "memory");
     };
@@ -232,11 +244,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_q4k_kernel(const TcGemmAr
             if (it + 4 < total) issue_raw(it + 4);
         }
     } else if (is_compute) {
-        const int q = warp & 3, cg = warp >> 2;       // fold: TMEM lane quadrant, group of 16 columns
+        const int q = warp & 3, cg = warp >> 2;       // fold: TMEM lane quadrant, group of FC columns
         const int row = q * 32 + lane;
-        double acc[16];
+        double acc[FC];
 #pragma unroll
-        for (int c = 0; c < 16; c++) acc[c] = 0.0;
+        for (int c = 0; c < FC; c++) acc[c] = 0.0;
         // block terms in double (arithmetic of gemv.cuh compute_step) from accumulator set it & 1
         auto fold = [&](int it) {
             const int buf = it & 1, b3 = it % 3;
@@ -246,14 +258,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_q4k_kernel(const TcGemmAr
             const uint8_t *aux = smem + kOffAux + b3 * kImgAux;
             const int4 *bs_s = reinterpret_cast<const int4 *>(aux);
             const float *dx_s = reinterpret_cast<const float *>(aux + kN * 16);
-            uint32_t plo[16], phi[16];
-            const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + buf * 128 + cg * 16;
-            tmem_ld16(ta, plo);
-            tmem_ld16(ta + kN, phi);
+            uint32_t plo[FC], phi[FC];
+            const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + buf * 128 + cg * FC;
+            tmem_ld<FC>(ta, plo);
+            tmem_ld<FC>(ta + kN, phi);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-            for (int c = 0; c < 16; c++) {
-                const int col = cg * 16 + c;
+            for (int c = 0; c < FC; c++) {
+                const int col = cg * FC + c;
                 const int4 b4 = bs_s[col];
                 const float dxv = dx_s[col];
                 const int isum = (int)plo[c] + 8 * (int)phi[c];
@@ -271,46 +283,46 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_q4k_kernel(const TcGemmAr
         auto flush = [&](int tile) {
             const int c_first = owner((long long)tile * nsb), c_last = owner((long long)tile * nsb + nsb - 1);
             if (c_first != c_last) {
-                double *mine = a.partial + ((size_t)cta * 2 + (tile != g0 / nsb ? 1 : 0)) * (kN * kM) + (cg * 16) * kM + row;
+                double *mine = a.partial + ((size_t)cta * 2 + (tile != g0 / nsb ? 1 : 0)) * (kN * kM) + (cg * FC) * kM + row;
 #pragma unroll
-                for (int c = 0; c < 16; c++) __stcg(mine + c * kM, acc[c]);
+                for (int c = 0; c < FC; c++) __stcg(mine + c * kM, acc[c]);
                 compute_barrier();
                 if (tid == 0) { __threadfence(); *flag = atomicAdd(a.tickets + tile, 1u); }
                 compute_barrier();
                 if (*flag != (unsigned)(c_last - c_first)) return;           // another contributor finishes this tile
                 __threadfence();
 #pragma unroll
-                for (int c = 0; c < 16; c++) acc[c] = 0.0;
+                for (int c = 0; c < FC; c++) acc[c] = 0.0;
                 auto part_of = [&](int cc) {
-                    return a.partial + ((size_t)cc * 2 + (tile != (int)(S * cc / G) / nsb ? 1 : 0)) * (kN * kM) + (cg * 16) * kM + row;
+                    return a.partial + ((size_t)cc * 2 + (tile != (int)(S * cc / G) / nsb ? 1 : 0)) * (kN * kM) + (cg * FC) * kM + row;
                 };
                 for (int cc = c_first; cc <= c_last; cc += 2) {               // range order = super-block order; two ranges' loads in flight
                     const double *s0 = part_of(cc), *s1 = part_of(cc + 1 <= c_last ? cc + 1 : cc);
-                    double t0[16], t1[16];
+                    double t0[FC], t1[FC];
 #pragma unroll
-                    for (int c = 0; c < 16; c++) { t0[c] = __ldcg(s0 + c * kM); t1[c] = __ldcg(s1 + c * kM); }
+                    for (int c = 0; c < FC; c++) { t0[c] = __ldcg(s0 + c * kM); t1[c] = __ldcg(s1 + c * kM); }
                     const bool two = cc + 1 <= c_last;
 #pragma unroll
-                    for (int c = 0; c < 16; c++) { acc[c] += t0[c]; if (two) acc[c] += t1[c]; }
+                    for (int c = 0; c < FC; c++) { acc[c] += t0[c]; if (two) acc[c] += t1[c]; }
                 }
                 if (tid == 0) a.tickets[tile] = 0u;                            // ready for the next launch
             }
             const int grow = tile * kM + row;
             if (a.epi == EPI_GATE) {
-                // (gate, up) rows are adjacent lanes.  The even lane finishes columns 0..7 of the pair's row, the odd lane columns 8..15,
-                // so every lane evaluates 8 double-precision exponentials instead of 16 with half of the lanes idle
+                // (gate, up) rows are adjacent lanes.  The even lane finishes the first half of the pair's columns, the odd lane the
+                // second half, so every lane evaluates FC / 2 double-precision exponentials instead of FC with half of the lanes idle
 #pragma unroll
-                for (int c = 0; c < 8; c++) {
-                    const float lo = (float)acc[c], hi = (float)acc[c + 8];
+                for (int c = 0; c < FC / 2; c++) {
+                    const float lo = (float)acc[c], hi = (float)acc[c + FC / 2];
                     const float recv = __shfl_xor_sync(0xffffffffu, (lane & 1) ? lo : hi, 1);
                     const float gte = (lane & 1) ? recv : lo, up = (lane & 1) ? hi : recv;
-                    const int col = cg * 16 + c + ((lane & 1) ? 8 : 0);
+                    const int col = cg * FC + c + ((lane & 1) ? FC / 2 : 0);
                     if (col < a.nb) a.out[(size_t)col * a.ld + (grow >> 1)] = (gte / (1.0f + (float)exp((double)(-gte)))) * up;
                 }
             } else {
 #pragma unroll
-                for (int c = 0; c < 16; c++) {
-                    const int col = cg * 16 + c;
+                for (int c = 0; c < FC; c++) {
+                    const int col = cg * FC + c;
                     if (col < a.nb) {
                         float *o = a.out + (size_t)col * a.ld + grow;
                         const float v = (float)acc[c];
@@ -349,7 +361,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_q4k_kernel(const TcGemmAr
                 flush(g / nsb);
                 TC_STAMP(61 + (it == total - 1 ? 1 : 0), 1);
 #pragma unroll
-                for (int c = 0; c < 16; c++) acc[c] = 0.0;
+                for (int c = 0; c < FC; c++) acc[c] = 0.0;
             }
         }
     }
@@ -357,6 +369,46 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_q4k_kernel(const TcGemmAr
     __syncthreads();
     TC_STAMP(60, 2);
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols) : "memory");
+}
+
+// ---- the two epilogues of the batched decode step that the GEMM does not carry (wide batches only: 9 + dep_q launches per frame) ----
+// arg-max key of every live column's logits row (EPI_ARGMAX of gemv.cuh / mma_gemm.cuh: first maximum wins)
+__global__ void __launch_bounds__(256) argmax_rows_kernel(const float *logits, int ld, int n, Ctrl *ctrl, int key_index) {
+    griddep_launch();
+    griddep_wait();
+    const float *row = logits + (size_t)blockIdx.x * ld;
+    unsigned long long best = 0ull;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) { const unsigned long long k = argmax_key(__ldcg(row + i), i); best = k > best ? k : best; }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) { const unsigned long long x = __shfl_xor_sync(0xffffffffu, best, o); best = x > best ? x : best; }
+    __shared__ unsigned long long sb[8];
+    if ((threadIdx.x & 31) == 0) sb[threadIdx.x >> 5] = best;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; w++) best = sb[w] > best ? sb[w] : best;
+        Ctrl *c = ctrl + blockIdx.x;
+        atomicMax(key_index < 0 ? &c->text_key : &c->audio_key[key_index], best);
+    }
+}
+// depformer step input of every live column: x[col] += embedding of the column's previous token (EPI_ADD_EMB; lm.h:464-467, 494-516)
+__global__ void __launch_bounds__(256) dep_embed_add_cols_kernel(const Ctrl *ctrl, const EmbTable emb, int step, float *x, int ld, int n) {
+    griddep_launch();
+    griddep_wait();
+    const int token = depformer_prev_token(ctrl + blockIdx.y, step);
+    float *xc = x + (size_t)blockIdx.y * ld;
+    for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < n; row += gridDim.x * blockDim.x) {
+        float e;
+        if (step == 0) {
+            e = emb_element(emb, token < 0 ? 0 : token, row);
+            e = e * (token == -1 ? 0.f : 1.f);
+        } else e = emb_element(emb, token, row);
+        xc[row] = __ldcg(xc + row) + e;
+    }
+}
+
+__host__ inline int columns_for(int nb) { return nb <= 16 ? 16 : nb <= 32 ? 32 : 64; }
+__host__ inline const void *kernel_for(int nc) {
+    return nc == 16 ? (const void *)tc_gemm_q4k_kernel<16> : nc == 32 ? (const void *)tc_gemm_q4k_kernel<32> : (const void *)tc_gemm_q4k_kernel<64>;
 }
 
 // GGUF row-major Q4_K blocks -> tc layout.  One thread per 16-byte piece; perm_half > 0 interleaves rows for the gated MLP

@@ -460,10 +460,13 @@ def test_batched_prefill_vs_oracle(msx, orc, gguf_for, preset, T, quant):
         toks = np.concatenate([[t_ref], a_ref, rng.integers(0, cfg["card"], size=cfg["n_q"] - cfg["dep_q"])]).astype(np.int32)
 
 
-@pytest.mark.parametrize("preset,n,quant", [("tiny", 5, "q4_k"), ("tiny_pplex", 3, "q8_0"), ("moshi7b_l2", 8, "q4_k")])
+@pytest.mark.parametrize("preset,n,quant", [("tiny", 5, "q4_k"), ("tiny_pplex", 3, "q8_0"), ("moshi7b_l2", 8, "q4_k"),
+                                            ("moshi7b_l2", 13, "q4_k"), ("moshi7b_l2", 32, "q4_k"), ("moshi7b_l2", 64, "q4_k")])
 def test_batch_streams_vs_oracle(msx, orc, gguf_for, preset, n, quant):
     """Every stream of a lock-step batch (tensor-core dequant-GEMM, BASELINE.json config 5) against its own ORACLE state:
-    different inputs per stream, teacher-forced with the oracle's tokens, logits within tolerance and (almost always) bit-identical."""
+    different inputs per stream, teacher-forced with the oracle's tokens, logits within tolerance and (almost always) bit-identical.
+    Up to 8 streams run on mma.sync (mma_gemm.cuh); 9..64 streams on the tcgen05 kind::i8 GEMM with 16 / 32 / 64 columns
+    (tc_gemm.cuh; text head, depformer_in and the codebook heads included)."""
     path, cfg = gguf_for(preset, quant)
     gm = msx.Model(path, cfg); batch = msx.Batch(gm, n)
     om = orc.Model(path, cfg); states = [orc.State(om) for _ in range(n)]
@@ -545,7 +548,7 @@ def test_batched_gemm_vs_oracle(msx, orc, quant, k, rows, nb, rms):
 
 
 @pytest.mark.parametrize("preset,n,quant", [("tiny", 8, "q4_k"), ("tiny", 3, "q4_k"), ("tiny_pplex", 5, "q4_k"), ("moshi7b_l2", 8, "q4_k"),
-                                            ("tiny", 8, "q8_0"), ("moshi7b_l2", 5, "q8_0")])
+                                            ("tiny", 8, "q8_0"), ("moshi7b_l2", 5, "q8_0"), ("moshi7b_l2", 24, "q4_k")])
 def test_batch_equals_independent_streams(msx, gguf_for, preset, n, quant):
     """n streams stepped as one batch (different inputs, free running) produce the tokens and logits of n
     single msx_streams: the batched kernels share the single-stream arithmetic (double accumulation of exact
@@ -569,6 +572,22 @@ def test_batch_equals_independent_streams(msx, gguf_for, preset, n, quant):
             assert max_rel(btl, tl) < 2e-3 and max_rel(bal, al) < 2e-3, f"frame {f} stream {s}"
             assert out[s, 0] == t and np.array_equal(out[s, 1:], a), f"frame {f} stream {s}"
             assert_bitwise_mostly(btl, tl, f"text logits frame {f} stream {s}")
+
+
+def test_wide_batch_needs_tensor_core_layouts(msx, gguf_for):
+    """more than 8 streams: only models whose every linear has 128-row tiles and a 256-multiple inner dimension (tiny's
+    1000-row text head does not); 65 streams never"""
+    path, cfg = gguf_for("tiny", "q4_k")
+    gm = msx.Model(path, cfg)
+    with pytest.raises(Exception):
+        msx.Batch(gm, 16)
+    path, cfg = gguf_for("moshi7b_l2", "q4_k")
+    gm = msx.Model(path, cfg)
+    with pytest.raises(Exception):
+        msx.Batch(gm, 65)
+    path, cfg = gguf_for("moshi7b_l2", "q8_0")
+    with pytest.raises(Exception):
+        msx.Batch(msx.Model(path, cfg), 16)
 
 
 def test_batch_stream_restart_and_resident(msx, gguf_for):
