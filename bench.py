@@ -463,6 +463,34 @@ def main():
             "setup_s": t_b,
         }
         batch.close()
+        # ---- wider batches on the tcgen05 kind::i8 GEMM (tc_gemm.cuh): 16 / 32 / 64 streams per GPU, full-length KV rings ----
+        wide = []
+        if args.quant == "q4_k":
+            for nw in (16, 32, 64):
+                try:
+                    wb = msx.Batch(model, nw)
+                except Exception as e:                   # noqa: BLE001  (a model without tensor-core layouts, or no room for the rings)
+                    wide.append({"streams_per_gpu": nw, "error": str(e)[:160]})
+                    break
+                wfr = rngb.integers(0, cfg["card"], size=(nw, 64, cfg["n_q"] + 1)).astype(np.int32)
+                wfr[:, :, 0] = rngb.integers(0, cfg["text_card"], size=(nw, 64))
+                Kw = min(K, 60)
+                wb.run_resident(wfr, 5)
+                wkv0 = wb.kv_bytes_next()
+                barrier(); torch.cuda.synchronize(local_rank)
+                ms_w, _ = wb.run_resident(wfr, Kw)
+                torch.cuda.synchronize(local_rank); barrier()
+                wkv1 = wb.kv_bytes_next()
+                if dist is not None:
+                    t = torch.tensor([ms_w], device=f"cuda:{local_rank}", dtype=torch.float64)
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                    ms_w = float(t[0])
+                wide.append({"streams_per_gpu": nw, "value": world * nw * Kw / (ms_w * 1e-3), "unit": "frames/s (all streams, all GPUs)",
+                             "ms_per_step": ms_w / Kw, "per_stream_fps": Kw / (ms_w * 1e-3), "per_stream_realtime_factor": Kw / (ms_w * 1e-3) / FRAME_RATE,
+                             "launches_per_frame": wb.launches_per_frame, "steps": Kw, "kv_avg": 0.5 * (wkv0 + wkv1)})
+                wb.close()
+        batched["wide"] = {"kernel": "tc_gemm_q4k_kernel<16|32|64> (tcgen05.mma kind::i8, accumulators in tensor memory, exact Q4_K x Q8_K)",
+                           "what": "the same lock-step batch with more conversations per GPU; device-timed resident replay", "runs": wide}
 
     # ---- persistent step kernel (opt-in path), for the record --------------------------------------------------
     step_kernel = None

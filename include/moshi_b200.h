@@ -251,10 +251,12 @@ MSX_API int msx_stream_prefill(msx_stream *s, const int32_t *tokens, int n_frame
 MSX_API int msx_stream_prefill_profile(msx_stream *s, const int32_t *tokens, float *family_ms, int32_t *family_launches, int max_families);
 
 /* ---- lock-step batch of independent streams (BASELINE.json config 5) ------------------
- * n_streams (1..8) conversations share every weight read: one activation-quantisation launch and one
+ * n_streams conversations share every weight read: one activation-quantisation launch and one
  * tensor-core dequant-GEMM launch per linear layer serve all of them; KV rings, positions and delay state
  * stay private, so stream i of a batch computes exactly what a single msx_stream would.  q4_k and q8_0 models
- * (q8_0: K % 128 == 0); not the TTS-family layers. */
+ * (q8_0: K % 128 == 0); not the TTS-family layers.  1..8 streams: mma.sync GEMM; 9..64 streams: tcgen05 kind::i8
+ * GEMM with 16 / 32 / 64 columns (q4_k models whose every linear has rows % 128 == 0 and K % 256 == 0 — the 7B
+ * family does; MSX_ERR_ARG otherwise).  Each stream owns a full KV ring (7B, 3000 slots: 1.57 GB). */
 typedef struct msx_batch msx_batch;
 MSX_API int msx_batch_create(msx_model *model, int n_streams, int context_override, msx_batch **out);
 MSX_API void msx_batch_free(msx_batch *b);

@@ -21,7 +21,9 @@
 // super-block i and expand super-block i + 2 (pipeline at the shared-memory map below).  Descriptor encodings pinned by
 // scripts/tcgen05_probe.cu.
 #pragma once
+#include <algorithm>
 #include "common.cuh"
+#include "gemv.cuh"      // depformer_prev_token (the embedding-add follow-up kernel)
 
 namespace msx {
 namespace tc {

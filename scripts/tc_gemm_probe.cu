@@ -9,7 +9,7 @@
 using namespace msx;
 int main() {
     int sms = 0; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
-    cudaFuncSetAttribute(tc::tc_gemm_q4k_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes);
+    cudaFuncSetAttribute(tc::tc_gemm_q4k_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes);
     long long *tl; cudaMalloc(&tl, 64 * 4 * 8); cudaMemset(tl, 0, 64 * 4 * 8);
     cudaMemcpyToSymbol(tc::g_tc_timeline, &tl, sizeof(tl));
     struct Shape { const char *name; int rows, K, epi; } shapes[] = {
@@ -30,7 +30,7 @@ int main() {
         cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
         for (int rep = 0; rep < 3; rep++) {
             cudaEventRecord(e0);
-            for (int i = 0; i < 20; i++) { g.w = w + (size_t)(i & 3) * wbytes; tc::tc_gemm_q4k_kernel<<<grid, tc::kThreads, tc::kSmemBytes>>>(g); }
+            for (int i = 0; i < 20; i++) { g.w = w + (size_t)(i & 3) * wbytes; tc::tc_gemm_q4k_kernel<64><<<grid, tc::kThreads, tc::kSmemBytes>>>(g); }
             cudaEventRecord(e1); cudaEventSynchronize(e1);
         }
         float ms; cudaEventElapsedTime(&ms, e0, e1);
