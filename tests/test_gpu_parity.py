@@ -1066,6 +1066,53 @@ def test_batch_sampling_equals_independent_streams(msx, gguf_for):
     assert diff_from_greedy > 0, "sampling should not collapse to greedy"
 
 
+def test_wide_batch_sampling_and_generator(msx, gguf_for):
+    """20 conversations on the tcgen05 GEMM (32 columns, 12 of them dead) at 7B shapes: top-k sampling with per-stream host noise
+    == 20 single streams; then the batched generator (delay rings, one slot replaced mid-run) == 20 (stream, generator) pairs"""
+    path, cfg = gguf_for("moshi7b_l2", "q4_k")
+    gm = msx.Model(path, cfg)
+    n = 20
+    batch = msx.Batch(gm, n, 64); batch.set_sampling(0.7, 0.8, 25, 250)
+    singles = [msx.Stream(gm, context=64) for _ in range(n)]
+    for s in singles:
+        s.set_sampling(0.7, 0.8, 25, 250)
+    kt, ka = min(25, cfg["text_card"]), min(250, cfg["card"])
+    rng = np.random.default_rng(15)
+    toks = rng.integers(0, cfg["card"], size=(n, cfg["n_q"] + 1)).astype(np.int32)
+    toks[:, 0] = rng.integers(0, cfg["text_card"], size=n)
+    for f in range(3):
+        nt = rng.exponential(size=(n, kt)).astype(np.float32); na = rng.exponential(size=(n, cfg["dep_q"], ka)).astype(np.float32)
+        batch.set_noise(nt, na)
+        out = batch.step(toks)
+        for i in range(n):
+            singles[i].set_noise(nt[i], na[i])
+            t, _, _ = singles[i].step_temporal(toks[i])
+            a, _ = singles[i].step_depformer(t)
+            assert out[i, 0] == t and np.array_equal(out[i, 1:], a), f"sampled frame {f} stream {i}"
+        toks = np.concatenate([out, rng.integers(0, cfg["card"], size=(n, cfg["n_q"] - cfg["dep_q"]))], axis=1).astype(np.int32)
+    batch.close()
+    for s in singles:
+        s.close()
+    bg = msx.BatchGen(msx.Batch(gm, n, 64))
+    streams = [msx.Stream(gm, context=64) for _ in range(n)]
+    gens = [msx.Gen(s) for s in streams]
+    n_user = cfg["n_q"] - cfg["dep_q"]
+    emitted = 0
+    for f in range(8):
+        if f == 4:
+            bg.reset(7)
+            streams[7].reset(); gens[7] = msx.Gen(streams[7])
+        user = rng.integers(0, cfg["card"], size=(n, n_user)).astype(np.int32)
+        valid, text, audio = bg.step(user)
+        for i in range(n):
+            rc, t, a = gens[i].step(user[i])
+            assert valid[i] == rc, f"frame {f} stream {i}"
+            if rc:
+                emitted += 1
+                assert text[i] == t and np.array_equal(audio[i], a), f"frame {f} stream {i}"
+    assert emitted > n * 4 and bg.offset(7) == 4 and bg.offset(0) == 8
+
+
 @pytest.mark.parametrize("preset", ["tiny", "tiny_pplex"])
 def test_batched_generator_equals_independent_generators(msx, gguf_for, preset):
     """config 5 end to end: n conversations with their own delay rings on one batch == n (msx_stream + msx_gen) pairs,
