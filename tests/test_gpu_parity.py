@@ -394,6 +394,48 @@ def test_full_7b_q4k_250_frames_vs_oracle(msx, orc, gguf_for, step_kernel):
     print(f"moshi7b q4_k (step_kernel={step_kernel}): 250 free-running frames identical; teacher-forced worst max-rel text {wt:.2e} audio {wa:.2e}")
 
 
+def test_full_7b_q4k_tcgen05_prefill_and_wide_batch_vs_oracle(msx, orc, gguf_for):
+    """The tcgen05 paths at FULL size (32 layers, the GGUF bench.py times): (a) a 70-row prompt through msx_stream_prefill
+    (one 64-column pass + a 6-column tail on tc_gemm_q4k_kernel) against 70 serial oracle steps — KV rows bit-identical in the first
+    and last layer, next-frame logits within tolerance; (b) one frame of a 16-stream batch (tc_gemm_q4k_kernel<16>, all 32 layers +
+    depformer) against 16 oracle states."""
+    path, cfg = gguf_for("moshi7b", "q4_k")
+    gm = msx.Model(path, cfg); om = orc.Model(path, cfg)
+    rng = np.random.default_rng(77)
+    T = 70
+    gs = msx.Stream(gm, context=128); os_ = orc.State(om)
+    rows = rng.integers(0, cfg["card"], size=(T, cfg["n_q"] + 1)).astype(np.int32)
+    rows[:, 0] = rng.integers(0, cfg["text_card"], size=T)
+    gs.prefill(rows)
+    for f in range(T):
+        os_.step_temporal(rows[f])
+    for layer in (0, cfg["num_layers"] - 1):
+        for head in (0, cfg["num_heads"] - 1):
+            for slot in (0, 63, 64, T - 1):
+                kg, vg = gs.get_kv(layer, head, slot); ko, vo = os_.get_kv(layer, head, slot)
+                assert np.array_equal(kg, ko) and np.array_equal(vg, vo), f"KV row layer {layer} head {head} slot {slot}"
+    toks = rng.integers(0, cfg["card"], size=cfg["n_q"] + 1).astype(np.int32)
+    t_ref, lg_ref, _ = os_.step_temporal(toks); t_gpu, lg_gpu, _ = gs.step_temporal(toks)
+    assert max_rel(lg_gpu, lg_ref) < LOGIT_TOL
+    assert_bitwise_mostly(lg_gpu, lg_ref, "text logits after the 70-row prompt")
+    gs.close()
+    n = 16
+    batch = msx.Batch(gm, n, 64)
+    btoks = rng.integers(0, cfg["card"], size=(n, cfg["n_q"] + 1)).astype(np.int32)
+    btoks[:, 0] = rng.integers(0, cfg["text_card"], size=n)
+    out = batch.step(btoks)
+    for s in range(n):
+        st = orc.State(om)
+        t_ref, lg_ref, _ = st.step_temporal(btoks[s]); a_ref, al_ref = st.step_depformer(t_ref)
+        btl, bal = batch.logits(s)
+        assert max_rel(btl, lg_ref) < LOGIT_TOL and max_rel(bal, al_ref) < LOGIT_TOL, f"stream {s}: logits vs the oracle"
+        assert_bitwise_mostly(btl, lg_ref, f"text logits stream {s}")
+        if out[s, 0] == t_ref:
+            assert np.array_equal(out[s, 1:], a_ref), f"stream {s}: audio tokens"
+        else:
+            assert top2_margin(lg_ref) <= LOGIT_TOL * float(np.max(np.abs(lg_ref)))
+
+
 @pytest.mark.parametrize("step_kernel", [False, True])
 def test_long_ring_7b_shapes_q8_0_vs_oracle(msx, orc, gguf_for, step_kernel):
     """BASELINE.json config 4's operating point at 7B layer shapes: PersonaPlex (dep_q 16) q8_0, the ring filled past its
