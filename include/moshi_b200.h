@@ -243,8 +243,10 @@ MSX_API int msx_gen_max_delay(const msx_gen *g);
 /* Batched-T prompt prefill: T frames whose n_q+1 tokens are all given (PersonaPlex voice / system
  * prompt rows, lm.h:983-1134) are run 8 positions at a time as the 8 columns of the tensor-core GEMM.  Only the temporal
  * KV rings and the position advance — exactly what T "provided" steps leave behind (their logits, sampled tokens and
- * depformer output are discarded, lm.h:933-943).  tokens [T][n_q+1].  Up to the end of the ring's first lap 8 positions go
- * through each weight pass; positions beyond it (every insert overwrites a slot the previous position still sees) one per pass. */
+ * depformer output are discarded, lm.h:933-943).  tokens [T][n_q+1].  64 positions (q4_k models with tensor-core layouts; 8
+ * otherwise) go through each weight pass, anywhere on the ring: the K / V rows of a pass are inserted first and the old rows of
+ * the slots they overwrite are kept aside for the columns that still see them (the T > 1 window of torch.h:170-223 with
+ * serial-step semantics), so a prompt may be longer than the ring. */
 MSX_API int msx_stream_prefill(msx_stream *s, const int32_t *tokens, int n_frames);
 /* profiling tool: tokens [1 + pass][n_q+1] = one prompt row, then ONE full prefill pass launched eagerly with an event after every
  * launch -> per-family kernel time (family order of msx_family_name) */

@@ -42,10 +42,16 @@ struct AttnArgs {
     int64_t kv_bstride = 0;
     int32_t qkv_bstride = 0, ctx_bstride = 0;
     int32_t skip_insert = 0;        // the ring rows of this step were written by kv_insert_kernel (batched-T prefill)
+    // batched-T prefill past the ring's first lap: the pass's columns overwrite the `victim_n` oldest slots before anybody attends;
+    // kv_insert_kernel saves the old rows here ([H][kVictimRows][DH] bf16) and column c reads them in place of the rows of the
+    // columns after it (which hold positions it must not see) — the T > 1 window of torch.h:170-223 with serial-step semantics
+    uint16_t *victim_k = nullptr, *victim_v = nullptr;
+    int32_t victim_n = 0;
     long long *dbg = nullptr;       // optional timeline (scripts/attn_probe.cu): [CTA][8] globaltimer ns
 };
 
 constexpr int kAttnMaxSplit = 8;
+constexpr int kVictimRows = 64;       // columns of a prefill pass
 // K / V rows of the valid slots stream through a shared-memory ring of kAttnRing chunks of kAttnChunkRows rows, filled with
 // cp.async.bulk (TMA) + mbarrier completion: the rows of a (head, split) are contiguous in the ring cache [H][cap][DH], so a
 // chunk is ONE bulk copy.  The K chunks are followed by the V chunks of the same rows; the first kAttnRing chunks are
@@ -122,6 +128,11 @@ __global__ void __launch_bounds__(kThreads) attn_kernel(const AttnArgs a0) {
     const int pos = a.pos_const >= 0 ? a.pos_const : a.ctrl->offset;
     const int slot = pos % cap;
     const int n_valid = (pos >= cap - 1) ? cap : pos + 1;
+    // prefill pass: slot i was overwritten by column jv of this pass (slots of a pass are consecutive modulo cap); columns after
+    // mine hold future positions -> read the saved old row instead
+    const int vic_n = a.victim_n, my_col = (int)blockIdx.z;
+    const int vic_s0 = vic_n ? (((pos - my_col) % cap) + cap) % cap : 0;
+    auto victim_of = [&](int i) { const int jv = i - vic_s0 + (i < vic_s0 ? cap : 0); return (jv > my_col && jv < vic_n) ? jv : -1; };
     const int per = (cap + S - 1) / S + 1;
     // short context: the split is not worth three cluster barriers — rank 0 handles the head alone
     // (uniform decision across the cluster, so nobody waits at a barrier)
@@ -221,6 +232,7 @@ __global__ void __launch_bounds__(kThreads) attn_kernel(const AttnArgs a0) {
                 double d = 0.0;
                 if (i < hi) {
                     const uint16_t *rowp = (i == slot && !a.skip_insert) ? knew : ck + r * DH;
+                    if (vic_n) { const int jv = victim_of(i); if (jv >= 0) rowp = a.victim_k + ((size_t)h * kVictimRows + jv) * DH; }
                     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll
                     for (int u = 0; u < HP; u++) {
@@ -298,7 +310,8 @@ __global__ void __launch_bounds__(kThreads) attn_kernel(const AttnArgs a0) {
         for (int r = g; r < CH; r += NG) {
             const int i = lo + (j - n_ck) * CH + r;
             if (i < hi) {
-                const uint4 vv = (i == slot && !a.skip_insert) ? reinterpret_cast<const uint4 *>(vnew)[sl] : reinterpret_cast<const uint4 *>(ck + r * DH)[sl];
+                uint4 vv = (i == slot && !a.skip_insert) ? reinterpret_cast<const uint4 *>(vnew)[sl] : reinterpret_cast<const uint4 *>(ck + r * DH)[sl];
+                if (vic_n) { const int jv = victim_of(i); if (jv >= 0) vv = reinterpret_cast<const uint4 *>(a.victim_v + ((size_t)h * kVictimRows + jv) * DH)[sl]; }
                 const float p = sc_s[i - lo];
                 acc[0] += (double)(bf16_bits_to_f32(vv.x & 0xffff) * p); acc[1] += (double)(bf16_bits_to_f32(vv.x >> 16) * p);
                 acc[2] += (double)(bf16_bits_to_f32(vv.y & 0xffff) * p); acc[3] += (double)(bf16_bits_to_f32(vv.y >> 16) * p);
@@ -346,8 +359,14 @@ __global__ void __launch_bounds__(64) kv_insert_kernel(const AttnArgs a0) {
     rope_rows<DH>(a, h, pos, tid, q_s, knew, vnew);
     __syncthreads();
     const size_t o = ((size_t)h * a.cap + (pos % a.cap)) * DH;
-    if (tid < DH / 4) reinterpret_cast<uint2 *>(a.kc + o)[tid] = reinterpret_cast<const uint2 *>(knew)[tid];
-    else if (tid >= 32 && tid < 32 + DH / 4) reinterpret_cast<uint2 *>(a.vc + o)[tid - 32] = reinterpret_cast<const uint2 *>(vnew)[tid - 32];
+    const size_t vo = ((size_t)h * kVictimRows + b) * DH;                // old row of the slot -> victim row of this column
+    if (tid < DH / 4) {
+        if (a.victim_k) reinterpret_cast<uint2 *>(a.victim_k + vo)[tid] = reinterpret_cast<const uint2 *>(a.kc + o)[tid];
+        reinterpret_cast<uint2 *>(a.kc + o)[tid] = reinterpret_cast<const uint2 *>(knew)[tid];
+    } else if (tid >= 32 && tid < 32 + DH / 4) {
+        if (a.victim_v) reinterpret_cast<uint2 *>(a.victim_v + vo)[tid - 32] = reinterpret_cast<const uint2 *>(a.vc + o)[tid - 32];
+        reinterpret_cast<uint2 *>(a.vc + o)[tid - 32] = reinterpret_cast<const uint2 *>(vnew)[tid - 32];
+    }
 }
 
 }  // namespace msx

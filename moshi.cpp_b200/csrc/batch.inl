@@ -29,6 +29,7 @@ struct msx_batch {
     msx_stream *prefill_of = nullptr;
     int n_active = 0;
     bool tc = false;                      // prefill with 64 columns per pass on the tcgen05 GEMM (tc_gemm.cuh) instead of 8 on mma.sync
+    uint16_t *victim_k = nullptr, *victim_v = nullptr;             // prefill: old ring rows of the slots a pass overwrites [H][64][Dh]
     double *tc_partial = nullptr; int tc_max_tiles = 0;            // stream-K partial sums [cta][2][64][128]
     unsigned int *tc_tickets = nullptr;                            // [tiles] arrival counters (zero between launches)
     // sampling (sampling.h:46-64) per stream: temperature <= 0 = greedy; Exp(1) noise supplied by the host per frame
@@ -200,6 +201,7 @@ void enqueue_layer_b(BatchLauncher &B, const LayerW &lw, int w, bool temporal, i
         // columns = consecutive positions of one stream: insert all their K / V rows into ITS ring first, then attend
         a.kc = b->prefill_of->kc + (size_t)layer * lstride; a.vc = b->prefill_of->vc + (size_t)layer * lstride;
         a.kv_bstride = 0; a.skip_insert = 1;
+        a.victim_k = b->victim_k; a.victim_v = b->victim_v; a.victim_n = b->n_active;
         B.L.fam = FAM_ATTN; B.L.begin();
         if (dim / heads == 128) B.L.launch_pdl(kv_insert_kernel<128>, dim3(heads, b->n_active), dim3(64), 0, a);
         else B.L.launch_pdl(kv_insert_kernel<64>, dim3(heads, b->n_active), dim3(64), 0, a);
@@ -381,6 +383,11 @@ static int batch_create_impl(msx_model *m, int n_streams, int context_override, 
     if (int e = balloc(b.get(), (void **)&b->text_logits, n * c.text_card * 4)) return e;
     if (int e = balloc(b.get(), (void **)&b->rope_cs, n * (c.dim / c.num_heads) * 4)) return e;
     int maxK = std::max(c.dim, m->hidden);
+    if (prefill_of) {
+        const size_t vb = (size_t)c.num_heads * kVictimRows * (c.dim / c.num_heads) * 2;
+        if (int e = balloc(b.get(), (void **)&b->victim_k, vb)) return e;
+        if (int e = balloc(b.get(), (void **)&b->victim_v, vb)) return e;
+    }
     if (c.dep_q > 0 && !prefill_of) {
         const size_t dkv = (size_t)c.dep_layers * m->dep_cap * c.dep_dim;
         if (int e = balloc(b.get(), (void **)&b->dkc, dkv * 2 * n)) return e;
@@ -447,10 +454,9 @@ extern "C" int msx_stream_prefill(msx_stream *s, const int32_t *tokens, int T) {
     msx_batch *b = s->prefill;
     const int n_in = c.n_q + 1;
     for (int c0 = 0, nb = 0; c0 < T; c0 += nb) {
-        // all columns of a pass are inserted before any of them attends, so a pass must not overwrite a slot an earlier
-        // column still sees: up to the end of the ring's first lap b->n (64 or 8) positions per pass, beyond it one per pass
-        const int pos0 = s->host_offset + c0;
-        nb = pos0 >= s->cap ? 1 : std::min(std::min(b->n, T - c0), s->cap - pos0);
+        // all columns of a pass are inserted before any of them attends; the old rows of the slots they overwrite are kept aside
+        // (AttnArgs::victim_*) for the columns that still see them, so a pass is b->n (64 or 8) positions anywhere on the ring
+        nb = std::min(std::min(b->n, T - c0), s->cap);
         CU(cudaStreamSynchronize(b->st));            // the pinned staging buffers are reused per chunk
         for (int j = 0; j < b->n; j++) {
             Ctrl hdr; memset(&hdr, 0, sizeof(hdr));
@@ -485,7 +491,7 @@ extern "C" int msx_stream_prefill_profile(msx_stream *s, const int32_t *tokens, 
     if (!s || !tokens || !family_ms || !family_launches) return fail(MSX_ERR_ARG, "null argument");
     if (int e = msx_stream_prefill(s, tokens, 1)) return e;              // creates the prefill context
     msx_batch *b = s->prefill; msx_model *m = s->m; const msx_config &c = m->cfg;
-    if (s->host_offset + b->n > s->cap) return fail(MSX_ERR_STATE, "no room for a full pass in the ring's first lap");
+    if (b->n > s->cap) return fail(MSX_ERR_STATE, "ring shorter than a pass");
     const int n_in = c.n_q + 1;
     for (int i = 0; i < max_families; i++) { family_ms[i] = 0.f; family_launches[i] = 0; }
     CU(cudaStreamSynchronize(b->st));

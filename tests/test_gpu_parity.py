@@ -471,7 +471,7 @@ def test_long_ring_7b_shapes_q8_0_vs_oracle(msx, orc, gguf_for, step_kernel):
 
 
 @pytest.mark.parametrize("preset,T,quant", [("tiny", 19, "q4_k"), ("tiny_pplex", 13, "q8_0"), ("moshi7b_l2", 11, "q4_k"), ("moshi7b_l2", 139, "q4_k"),
-                                            ("moshi7b_l2", 70, "q8_0")])
+                                            ("moshi7b_l2", 70, "q8_0"), ("tiny", 61, "q4_k"), ("tiny_pplex", 45, "q8_0")])
 def test_batched_prefill_vs_oracle(msx, orc, gguf_for, preset, T, quant):
     """Prompt prefill against the ORACLE's T serial steps: KV rows bit-identical, logits of the frames that follow within tolerance
     (the prefill was only compared with the serial GPU path).  Q4_K models run 64 positions per weight pass on the
@@ -489,7 +489,7 @@ def test_batched_prefill_vs_oracle(msx, orc, gguf_for, preset, T, quant):
     assert gs.offset == os_.offset == T
     for layer in (0, cfg["num_layers"] - 1):
         for head in (0, cfg["num_heads"] - 1):
-            for slot in (0, T // 2, T - 1):
+            for slot in (0, (T // 2) % cfg["context"], (T - 1) % cfg["context"]):
                 kg, vg = gs.get_kv(layer, head, slot); ko, vo = os_.get_kv(layer, head, slot)
                 assert np.array_equal(kg, ko) and np.array_equal(vg, vo), f"KV row layer {layer} head {head} slot {slot}"
     toks = rng.integers(0, cfg["card"], size=cfg["n_q"] + 1).astype(np.int32)
@@ -500,6 +500,34 @@ def test_batched_prefill_vs_oracle(msx, orc, gguf_for, preset, T, quant):
         a_ref, al_ref = os_.step_depformer(t_ref); a_gpu, al_gpu = gs.step_depformer(t_ref, force=a_ref)
         assert max_rel(al_gpu, al_ref) < LOGIT_TOL
         toks = np.concatenate([[t_ref], a_ref, rng.integers(0, cfg["card"], size=cfg["n_q"] - cfg["dep_q"])]).astype(np.int32)
+
+
+def test_prefill_past_the_first_lap_7b_shapes(msx, orc, gguf_for):
+    """A prompt longer than the KV ring at 7B layer shapes (ring of 100 slots, 230 rows): 64-column passes on the tcgen05 GEMM that
+    start before / straddle / lie beyond the end of the first lap.  The columns of a pass overwrite the oldest slots before anybody
+    attends, and every column reads the saved old rows in place of the slots its successors took (T > 1 window, torch.h:170-223):
+    the whole ring and the logits that follow equal 230 serial oracle steps."""
+    path, cfg0 = gguf_for("moshi7b_l2", "q4_k")
+    cfg = dict(cfg0, context=100)
+    gm = msx.Model(path, cfg); gs = msx.Stream(gm)
+    om = orc.Model(path, cfg); os_ = orc.State(om)
+    rng = np.random.default_rng(5)
+    T = 230
+    rows = rng.integers(0, cfg["card"], size=(T, cfg["n_q"] + 1)).astype(np.int32)
+    rows[:, 0] = rng.integers(0, cfg["text_card"], size=T)
+    gs.prefill(rows[:150]); gs.prefill(rows[150:])
+    for f in range(T):
+        os_.step_temporal(rows[f])
+    assert gs.offset == os_.offset == T
+    for layer in range(cfg["num_layers"]):
+        for head in (0, 17, cfg["num_heads"] - 1):
+            for slot in range(0, 100, 7):
+                kg, vg = gs.get_kv(layer, head, slot); ko, vo = os_.get_kv(layer, head, slot)
+                assert np.array_equal(kg, ko) and np.array_equal(vg, vo), f"KV row layer {layer} head {head} slot {slot}"
+    toks = rng.integers(0, cfg["card"], size=cfg["n_q"] + 1).astype(np.int32)
+    t_ref, lg_ref, _ = os_.step_temporal(toks); t_gpu, lg_gpu, _ = gs.step_temporal(toks)
+    assert max_rel(lg_gpu, lg_ref) < LOGIT_TOL
+    assert_bitwise_mostly(lg_gpu, lg_ref, "text logits after a prompt of 2.3 ring lengths")
 
 
 @pytest.mark.parametrize("preset,n,quant", [("tiny", 5, "q4_k"), ("tiny_pplex", 3, "q8_0"), ("moshi7b_l2", 8, "q4_k"),
