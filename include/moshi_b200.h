@@ -308,6 +308,23 @@ MSX_API int msx_test_dequant_rows(int device, int type, const void *table, int64
 MSX_API int msx_test_quantize_rows(int device, int src_type, int dst_type, const void *x, int64_t k, int64_t rows, void *out);
 MSX_API int msx_test_dequant_repacked(int device, int type, const void *w, int64_t k, int64_t rows, float *out);
 
+/* ---- Mimi codec, first slice: the split residual vector quantiser (codes <-> latent) ---------------------------
+ * Replaces mimi_quantizer_encode / mimi_decode_latent (reference src/moshi/models/compression.h:93-99, 216-222) and the
+ * graphs under them (src/moshi/quantization/vq.h:18-117, core_vq.h:14-193; 1 x 1 convolutions torch.h:18-37).
+ * cb_first [n_sem][bins][D] f32, cb_rest [n_rest][bins][D] f32 (EuclideanCodebook embeddings); in_* [D][dim], out_* [dim][D]
+ * as F16 bit patterns (ggml_conv_1d kernels).  Codes are bit-exact against the CPU oracle (ggml's distance arithmetic and
+ * summation order).  The rest of Mimi (SEANet, codec transformers, resampling convolutions) is not built. */
+typedef struct msx_rvq msx_rvq;
+MSX_API int msx_rvq_create(int device, int n_sem, int n_rest, int bins, int D, int dim, const float *cb_first, const float *cb_rest,
+                           const uint16_t *in_first, const uint16_t *in_rest, const uint16_t *out_first, const uint16_t *out_rest, msx_rvq **out);
+MSX_API void msx_rvq_free(msx_rvq *q);
+/* x [T][dim] (host) -> codes [n_q][T] (host); n_q <= n_sem + n_rest */
+MSX_API int msx_rvq_encode(msx_rvq *q, const float *x, int T, int n_q, int32_t *codes);
+/* codes [K][T] (host, each in [0, bins)) -> latent [T][dim] (host) */
+MSX_API int msx_rvq_decode(msx_rvq *q, const int32_t *codes, int K, int T, float *y);
+/* device-timed repeats on resident buffers: milliseconds per encode / decode of T frames with n_q codebooks */
+MSX_API int msx_rvq_bench(msx_rvq *q, int T, int n_q, int reps, float *encode_ms, float *decode_ms);
+
 #ifdef __cplusplus
 }
 #endif

@@ -175,6 +175,11 @@ def lib():
     L.msx_batch_run_resident.argtypes = [vp, vp, C.c_int, C.c_int, vp, C.POINTER(C.c_float)]
     L.msx_batch_profile_frame.argtypes = [vp, vp, vp, vp, C.c_int]
     L.msx_stream_prefill_profile.argtypes = [vp, vp, vp, vp, C.c_int]
+    L.msx_rvq_create.argtypes = [C.c_int] * 6 + [vp] * 7
+    L.msx_rvq_free.argtypes = [vp]; L.msx_rvq_free.restype = None
+    L.msx_rvq_encode.argtypes = [vp, vp, C.c_int, C.c_int, vp]
+    L.msx_rvq_decode.argtypes = [vp, vp, C.c_int, C.c_int, vp]
+    L.msx_rvq_bench.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp]
     L.msx_test_gemm_batch.argtypes = [C.c_int, C.c_int, vp, C.c_int64, C.c_int64, vp, C.c_int, vp, vp]
     L.msx_bench_gemm_batch_ex.argtypes = [C.c_int, vp, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), vp]
     L.msx_bench_gemm_batch.argtypes = [C.c_int, vp, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]
@@ -671,3 +676,48 @@ def bench_gemm_batch_stamps(w_raw: np.ndarray, k: int, nb: int, n_mats: int, ite
     st = np.zeros((iters, 148, 8), dtype=np.int64)
     _check(lib().msx_bench_gemm_batch_ex(device, _p(w_raw), k, w_raw.shape[0], nb, n_mats, iters, epilogue, 1 if with_quant else 0, C.byref(us), _p(st)))
     return float(us.value), st
+
+
+class RVQ:
+    """Mimi split residual vector quantiser on the GPU (msx_rvq_*): codes <-> latent, reference quantization/vq.h:69-117.
+    cb_first [n_sem][bins][D] f32, cb_rest [n_rest][bins][D] f32; projections as F16 bit patterns: in_* [D][dim], out_* [dim][D]"""
+
+    def __init__(self, cb_first, cb_rest, in_first, in_rest, out_first, out_rest, device: int = 0):
+        cb_first = np.ascontiguousarray(cb_first, dtype=np.float32); cb_rest = np.ascontiguousarray(cb_rest, dtype=np.float32)
+        ws = [np.ascontiguousarray(w, dtype=np.uint16) for w in (in_first, in_rest, out_first, out_rest)]
+        self.n_sem, self.bins, self.D = cb_first.shape
+        self.n_rest = cb_rest.shape[0]
+        self.dim = ws[0].shape[1]
+        self.h = C.c_void_p()
+        _check(lib().msx_rvq_create(device, self.n_sem, self.n_rest, self.bins, self.D, self.dim, _p(cb_first), _p(cb_rest),
+                                    _p(ws[0]), _p(ws[1]), _p(ws[2]), _p(ws[3]), C.byref(self.h)))
+
+    def encode(self, x, n_q: int):
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        T = x.shape[0]
+        codes = np.zeros((n_q, T), dtype=np.int32)
+        _check(lib().msx_rvq_encode(self.h, _p(x), T, n_q, _p(codes)))
+        return codes
+
+    def decode(self, codes):
+        codes = np.ascontiguousarray(codes, dtype=np.int32)
+        K, T = codes.shape
+        y = np.zeros((T, self.dim), dtype=np.float32)
+        _check(lib().msx_rvq_decode(self.h, _p(codes), K, T, _p(y)))
+        return y
+
+    def bench(self, T: int, n_q: int, reps: int = 20):
+        """-> (encode_ms, decode_ms) per call, device-timed on resident buffers"""
+        e = C.c_float(0); d = C.c_float(0)
+        _check(lib().msx_rvq_bench(self.h, T, n_q, reps, C.byref(e), C.byref(d)))
+        return float(e.value), float(d.value)
+
+    def close(self):
+        if self.h:
+            lib().msx_rvq_free(self.h); self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

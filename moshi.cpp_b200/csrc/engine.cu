@@ -42,6 +42,7 @@
 #include "step_kernel.cuh"
 #include "tts_kernels.cuh"
 #include "tc_gemm.cuh"
+#include "mimi_rvq.cuh"
 
 using namespace msx;
 
@@ -110,5 +111,6 @@ extern "C" int msx_device_count(void) {
 #include "test_hooks.inl"
 #include "converters.inl"
 #include "batch.inl"
+#include "mimi_rvq.inl"
 
 static void free_prefill(struct msx_batch *b) { delete b; }

@@ -114,6 +114,16 @@ int orc_lmgen_step(orc_lmgen *g, const int32_t *in_tokens, int n_in, int depform
 orc_state *orc_lmgen_state(orc_lmgen *g);
 int orc_lmgen_offset(orc_lmgen *g);
 
+/* ---- Mimi split residual vector quantiser (mimi_rvq_ref.c; reference src/moshi/quantization/{core_vq,vq}.h) ---- */
+void orc_conv1d_k1_f16(const uint16_t *w, int n_in, int n_out, const float *x, int T, float *y);
+void orc_residual_vq_encode(const float *codebooks, int n_q, int bins, int D, float *x, int T, int32_t *codes);
+void orc_residual_vq_decode(const float *codebooks, int n_q, int bins, int D, const int32_t *codes, int T, float *out);
+void orc_split_rvq_encode(const float *cb_first, const float *cb_rest, const uint16_t *in_first, const uint16_t *in_rest, int n_sem, int n_q,
+                          int bins, int D, int dim, const float *x, int T, int32_t *codes);
+void orc_split_rvq_decode(const float *cb_first, const float *cb_rest, const uint16_t *out_first, const uint16_t *out_rest, int n_sem, int K,
+                          int bins, int D, int dim, const int32_t *codes, int T, float *y);
+
 #ifdef __cplusplus
 }
+
 #endif

@@ -29,7 +29,7 @@ class OrcConfig(C.Structure):
 
 
 def build(force: bool = False) -> str:
-    src = [os.path.join(_HERE, f) for f in ("ggml_ref.c", "ggml_ref.h", "Makefile")]
+    src = [os.path.join(_HERE, f) for f in ("ggml_ref.c", "mimi_rvq_ref.c", "ggml_ref.h", "Makefile")]
     stale = (not os.path.exists(_SO)) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in src)
     if force or stale:
         subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
@@ -177,6 +177,38 @@ def rms_norm(x: np.ndarray, alpha: np.ndarray | None, eps: float = 1e-8) -> np.n
     y = np.empty_like(x)
     lib().orc_rms_norm(_p(x), _p(alpha) if alpha is not None else None, eps, _p(y), x.size)
     return y
+
+
+# ---- Mimi split residual vector quantiser (mimi_rvq_ref.c) ----------------------------------------
+class SplitRVQ:
+    """codes <-> latent (reference quantization/vq.h:69-117).  cb_first [n_sem][bins][D] f32, cb_rest [n_rest][bins][D] f32,
+    projections f16 bit patterns: in_* [D][dim], out_* [dim][D]"""
+
+    def __init__(self, cb_first, cb_rest, in_first, in_rest, out_first, out_rest):
+        self.cb_first = np.ascontiguousarray(cb_first, dtype=np.float32); self.cb_rest = np.ascontiguousarray(cb_rest, dtype=np.float32)
+        self.in_first = np.ascontiguousarray(in_first, dtype=np.uint16); self.in_rest = np.ascontiguousarray(in_rest, dtype=np.uint16)
+        self.out_first = np.ascontiguousarray(out_first, dtype=np.uint16); self.out_rest = np.ascontiguousarray(out_rest, dtype=np.uint16)
+        self.n_sem, self.bins, self.D = self.cb_first.shape
+        self.n_rest = self.cb_rest.shape[0]
+        self.dim = self.in_first.shape[1]
+
+    def encode(self, x, n_q: int):
+        """x [T][dim] -> codes [n_q][T]"""
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        T = x.shape[0]
+        codes = np.zeros((n_q, T), dtype=np.int32)
+        lib().orc_split_rvq_encode(_p(self.cb_first), _p(self.cb_rest), _p(self.in_first), _p(self.in_rest), self.n_sem, n_q, self.bins, self.D,
+                                   self.dim, _p(x), T, _p(codes))
+        return codes
+
+    def decode(self, codes):
+        """codes [K][T] -> latent [T][dim]"""
+        codes = np.ascontiguousarray(codes, dtype=np.int32)
+        K, T = codes.shape
+        y = np.zeros((T, self.dim), dtype=np.float32)
+        lib().orc_split_rvq_decode(_p(self.cb_first), _p(self.cb_rest), _p(self.out_first), _p(self.out_rest), self.n_sem, K, self.bins, self.D,
+                                   self.dim, _p(codes), T, _p(y))
+        return y
 
 
 # ---- model ------------------------------------------------------------------------------------
