@@ -1,4 +1,7 @@
 // moshi_api.cpp — see moshi_api.h.  Mirrors src/moshi.cpp:600-953 (LM + generator) over the msx C ABI.
+// Two pieces below are integer host logic that has to match the reference token for token and therefore follows it statement by
+// statement (a restatement, not an independent design): moshi_tts_machine_t::process <- StateMachine::process (lm.h:104-193), and the
+// PersonaPlex PROMPT_TOKENS table <- lm.h:983-987.  Everything else (JSON reader, voice loader, prompt batching, handles) is original.
 #include "moshi_api.h"
 
 #include <algorithm>
