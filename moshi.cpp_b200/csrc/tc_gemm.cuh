@@ -1,9 +1,10 @@
 // tc_gemm.cuh — Q4_K x Q8_K dequant-GEMM on the 5th-generation tensor cores (tcgen05.mma kind::i8, accumulators in tensor
-// memory) for the dense contraction of the path: the batched-T prompt prefill, 64 prompt positions per weight pass.
+// memory) for the dense contractions of the path: the batched-T prompt prefill (64 prompt positions per weight pass) and lock-step
+// batches of 9..64 conversations (16 / 32 / 64 live columns).
 //
-// Replaces, for T columns at once, what the reference runs T times: ggml_mul_mat of a Q4_K matrix with one Q8_K-quantised
-// activation column (torch_nn_linear src/torch.h:79-87 -> ggml_vec_dot_q4_K_q8_K) inside moshi_lmgen_step_system_prompts /
-// _voice_prompt (src/moshi/models/lm.h:983-1134).
+// Replaces, for up to 64 columns at once, what the reference runs once per column: ggml_mul_mat of a Q4_K matrix with one
+// Q8_K-quantised activation column (torch_nn_linear src/torch.h:79-87 -> ggml_vec_dot_q4_K_q8_K), T times inside
+// moshi_lmgen_step_system_prompts / _voice_prompt (src/moshi/models/lm.h:983-1134), once per process and frame for concurrent streams.
 //
 // Exact arithmetic on tensor cores.  ggml's block dot is  sum_s sc_s * (sum_k q_k x_k)  with 6-bit sub-block scales sc_s: the
 // integer part cannot be one int8 MMA because q * sc needs 10 bits.  Split sc = sc_lo + 8 sc_hi (3 bits each): q * sc_lo and
@@ -12,14 +13,15 @@
 // and everything after that is the arithmetic of gemv.cuh: mins term with dp2a, the two block terms d * dx * isum and
 // dmin * dx * imin (fp32 scale products, exact in double) accumulated in double, one rounding at the end.
 //
-// One CTA = one tile of 128 weight rows x all 64 columns; per super-block: (a) the 128 raw GGUF blocks (18 KB, contiguous in the
-// "tc layout" built at load) and the 64 x 256 int8 activations go to shared memory by TMA, (b) every thread expands half a block into
-// the two s8 operand tiles in the canonical K-major no-swizzle layout (8-row x 16-byte core matrices), (c) one thread issues 16
-// tcgen05.mma (M 128, N 64, K 32) into two 64-column accumulators and commits to an mbarrier, (d) sixteen warps read the
-// accumulators back with tcgen05.ld (warp = 32 TMEM lanes x 16 columns) and fold them into 16 double accumulators per thread.
-// The accumulators are double-buffered in tensor memory, so the tensor cores work on super-block i + 1 while the CUDA cores fold
-// super-block i and expand super-block i + 2 (pipeline at the shared-memory map below).  Descriptor encodings pinned by
-// scripts/tcgen05_probe.cu.
+// A step = one tile of 128 weight rows x one super-block (256 weights) x all live columns: (a) the 128 raw GGUF blocks (18 KB,
+// contiguous in the "tc layout" built at load) and the columns' 256 int8 activations go to shared memory by TMA, (b) the compute
+// warps expand the blocks into the two s8 operand tiles in the canonical K-major no-swizzle layout (8-row x 16-byte core
+// matrices), (c) one thread issues 16 tcgen05.mma (M 128, N = columns, K 32) into two accumulators and commits to an mbarrier,
+// (d) sixteen warps read the accumulators back with tcgen05.ld (warp = 32 TMEM lanes x columns / 4) and fold them into their double
+// accumulators.  The accumulators are double-buffered in tensor memory, so the tensor cores work on step i + 1 while the CUDA
+// cores fold step i and expand step i + 2 (pipeline at the shared-memory map below).  The launch is persistent: one CTA per SM
+// walks a contiguous range of the matrix's step sequence (stream-K, see TcGemmArgs).  Descriptor encodings pinned by
+// scripts/tcgen05_probe.cu; measurements and the optimisation log in profiles/r2_tcgen05_prefill.md.
 #pragma once
 #include <algorithm>
 #include "common.cuh"
