@@ -405,6 +405,24 @@ def main():
                                  "how": "200 launches of the same kernel/shape in one CUDA graph over 8 rotating matrices (415 MB > L2)"},
                 "family_time_share": shares}
 
+    # ---- the two stacks inside the real pipelined run (graphs + PDL, one event between the two graphs of a frame) --------
+    stacks = None
+    if cfg["dep_q"] > 0 and not (cfg.get("cross_attention") or cfg.get("demux")):
+        Ks = min(K, 200)
+        kvs0 = stream.kv_bytes_next
+        t_ms, d_ms = stream.run_resident_split(frames, Ks)
+        kvs1 = stream.kv_bytes_next
+        lin_b = lambda rows, k: rows * synth.row_bytes(synth.linear_type(synth.TYPE_NAMES[args.quant], k), k)
+        d_, h_ = cfg["dim"], cfg["hidden"]
+        temporal_w = cfg["num_layers"] * (lin_b(3 * d_, d_) + lin_b(d_, d_) + lin_b(2 * h_, d_) + lin_b(d_, h_)) + lin_b(cfg["text_card"], d_)
+        dep_w = model.weight_bytes_per_frame - temporal_w
+        t_gbs = (temporal_w + 0.5 * (kvs0 + kvs1)) / (t_ms / Ks * 1e-3) / 1e9
+        d_gbs = dep_w / (d_ms / Ks * 1e-3) / 1e9
+        stacks = {"temporal_ms": t_ms / Ks, "depformer_ms": d_ms / Ks, "temporal_bytes": temporal_w + 0.5 * (kvs0 + kvs1), "depformer_bytes": dep_w,
+                  "temporal_gbs": t_gbs, "temporal_frac_of_peak": t_gbs / load_peaks()[0]["hbm_gbs"], "depformer_gbs": d_gbs,
+                  "depformer_frac_of_peak": d_gbs / load_peaks()[0]["hbm_gbs"], "steps": Ks,
+                  "how": "msx_run_resident_split: the timed graphs replayed with one CUDA event between the temporal and the depformer graph of every frame"}
+
     fps = world * K / (ms_res * 1e-3)
     fps_e2e = world * K / (ms_e2e * 1e-3)
     w_bytes = model.weight_bytes_per_frame
@@ -615,6 +633,7 @@ def main():
             "gpu_launches": stream.launches_per_frame * K,
             "launches_per_frame": stream.launches_per_frame,
             "clocks": clocks, "load_s": t_load,
+            "stacks": stacks,
             "batched_streams": batched,
             "parity_checked": parity["frames"] if parity else 0, "parity": parity,
             "step_kernel": step_kernel, "tensor_parallel": tensor_parallel, "other_configs": other,

@@ -184,6 +184,9 @@ MSX_API int msx_run_resident_async(msx_stream *s, const int32_t *frames, int n_f
 MSX_API int msx_stream_wait(msx_stream *s, float *elapsed_ms);
 /* kernels launched per fused frame (for bench.py "gpu_launches") */
 MSX_API int msx_stream_launches_per_frame(const msx_stream *s);
+/* the resident loop with one event between the two graphs of a frame: total device milliseconds of the temporal stack and of the
+ * depformer over n_steps frames of the real pipelined run */
+MSX_API int msx_run_resident_split(msx_stream *s, const int32_t *frames, int n_frames, int n_steps, float *temporal_ms, float *depformer_ms);
 /* Measurement aid: runs ONE fused frame eagerly (no CUDA graph) with a CUDA event recorded on the
  * launching stream after every kernel, and returns the summed device time and launch count per
  * kernel family (msx_family_name(i), i < msx_family_count()).  Results are identical to msx_step. */

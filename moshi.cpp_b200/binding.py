@@ -142,6 +142,7 @@ def lib():
     L.msx_run_resident_async.argtypes = [vp, vp, C.c_int, C.c_int]
     L.msx_stream_wait.argtypes = [vp, C.POINTER(C.c_float)]
     L.msx_profile_frame.argtypes = [vp, vp, vp, vp, vp, C.c_int]
+    L.msx_run_resident_split.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp]
     L.msx_step_timeline.argtypes = [vp, vp, vp, C.c_int, vp, vp]
     L.msx_family_count.restype = C.c_int
     L.msx_timer_start.argtypes = [vp]
@@ -381,6 +382,14 @@ class Stream:
         ms = C.c_float(0)
         _check(lib().msx_run_resident(self.h, _p(fr), fr.shape[0], n_steps, _p(out), C.byref(ms)))
         return float(ms.value), out
+
+    def run_resident_split(self, frames, n_steps: int):
+        """-> (temporal_ms, depformer_ms) summed over n_steps frames of the graph-replayed run (one event between the two graphs)"""
+        cfg = self.model.cfg
+        fr = np.ascontiguousarray(frames, dtype=np.int32).reshape(-1, cfg["n_q"] + 1)
+        t = C.c_float(0); d = C.c_float(0)
+        _check(lib().msx_run_resident_split(self.h, _p(fr), fr.shape[0], n_steps, C.byref(t), C.byref(d)))
+        return float(t.value), float(d.value)
 
     def profile_frame(self, tokens):
         """-> (out_tokens, {family: (ms, launches)}) for one eagerly-launched frame"""

@@ -34,6 +34,49 @@ extern "C" int msx_run_resident(msx_stream *s, const int32_t *frames, int n_fram
     return 0;
 }
 
+// The resident loop with one event between the two graphs of a frame: device time of the temporal stack and of the depformer
+// inside the REAL pipelined run (graphs, PDL) — unlike msx_profile_frame, which serialises every launch.
+extern "C" int msx_run_resident_split(msx_stream *s, const int32_t *frames, int n_frames, int n_steps, float *temporal_ms, float *depformer_ms) {
+    if (!s || !frames || n_frames <= 0 || n_steps <= 0 || n_steps > 4096) return fail(MSX_ERR_ARG, "bad argument");
+    const msx_config &c = s->m->cfg;
+    CU(cudaSetDevice(s->m->device));
+    const int n_in = c.n_q + 1;
+    if (int e = check_tokens(s->m, frames, n_frames, INT32_MIN, nullptr)) return e;
+    int32_t *d_feed = nullptr;
+    CU(cudaMalloc((void **)&d_feed, (size_t)n_frames * n_in * 4));
+    CU(cudaMemcpy(d_feed, frames, (size_t)n_frames * n_in * 4, cudaMemcpyHostToDevice));
+    if (int e = push_inputs(s, nullptr, INT32_MIN, nullptr)) return e;
+    Ctrl hdr;
+    memset(&hdr, 0, sizeof(hdr));
+    hdr.offset = s->host_offset; hdr.frame = 0; hdr.feed_n = n_frames; hdr.n_in = n_in; hdr.feed = d_feed; hdr.trace = nullptr;
+    CU(cudaMemcpyAsync(s->ctrl, &hdr, kCtrlInOffset, cudaMemcpyHostToDevice, s->st));
+    CU(cudaStreamSynchronize(s->st));
+    std::vector<cudaEvent_t> ev((size_t)2 * n_steps + 1);
+    for (cudaEvent_t &e : ev) CU(cudaEventCreate(&e));
+    CU(cudaEventRecord(ev[0], s->st));
+    for (int i = 0; i < n_steps; i++) {
+        CU(cudaGraphLaunch(s->g_temporal, s->st));
+        CU(cudaEventRecord(ev[2 * i + 1], s->st));
+        if (c.dep_q > 0) CU(cudaGraphLaunch(s->g_depformer, s->st));
+        CU(cudaEventRecord(ev[2 * i + 2], s->st));
+    }
+    CU(cudaStreamSynchronize(s->st));
+    s->host_offset += n_steps;
+    double t = 0.0, d = 0.0;
+    for (int i = 0; i < n_steps; i++) {
+        float a = 0.f, b = 0.f;
+        cudaEventElapsedTime(&a, ev[2 * i], ev[2 * i + 1]); cudaEventElapsedTime(&b, ev[2 * i + 1], ev[2 * i + 2]);
+        t += a; d += b;
+    }
+    for (cudaEvent_t e : ev) cudaEventDestroy(e);
+    if (temporal_ms) *temporal_ms = (float)t;
+    if (depformer_ms) *depformer_ms = (float)d;
+    int32_t zero2[2] = {0, 0};
+    CU(cudaMemcpy(&s->ctrl->frame, zero2, 8, cudaMemcpyHostToDevice));
+    cudaFree(d_feed);
+    return 0;
+}
+
 // Eager (non-graph) run of one fused frame with a CUDA event after every launch: per-family kernel time.
 extern "C" int msx_profile_frame(msx_stream *s, const int32_t *tokens, int32_t *out_tokens,
                                  float *family_ms, int32_t *family_launches, int max_families) {
