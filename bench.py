@@ -394,12 +394,12 @@ def main():
     replay_gbs = None
     if L.msx_bench_gemv(local_rank, gt, raw.ctypes.data, cfg["dim"], 2 * cfg["hidden"], 8, 200, 1, 2, C.byref(us)) == 0:
         replay_gbs = dom_bytes / (us.value * 1e-6) / 1e9
-    roofline = {"bound": "hbm", "kernel": "gemv_kernel<Q4_K,32> gating.linear_in (rms_norm + q8_K quant + dequant-GEMV + silu gate)",
+    roofline = {"bound": "hbm", "kernel": "dq_matvec_kernel<Q4_K,32> gating.linear_in (rms_norm + q8_K quant + dequant-GEMV + silu gate)",
                 "achieved": achieved, "peak": peaks["hbm_gbs"], "peak_source": f"{peak_src} copy bandwidth (MEASURED_PEAKS.json)",
                 "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
                 # dram__bytes_read.sum + dram__bytes_write.sum of this kernel and shape, from the committed ncu --set full capture
                 # (profiles/kernel_traffic.json); used only while the capture's stored-layout bytes equal this build's
-                "traffic": committed_traffic("gemv_kernel linear_in", args.quant, cfg["dim"], 2 * cfg["hidden"]),
+                "traffic": committed_traffic("dq_matvec_kernel linear_in", args.quant, cfg["dim"], 2 * cfg["hidden"]),
                 "bytes_per_launch": dom_bytes, "launch_us": dom_ms * 1e3, "launches_timed": fam_n[dom],
                 "graph_replay": {"launch_us": us.value, "achieved": replay_gbs, "frac": (replay_gbs or 0) / peaks["hbm_gbs"],
                                  "how": "200 launches of the same kernel/shape in one CUDA graph over 8 rotating matrices (415 MB > L2)"},
@@ -474,7 +474,7 @@ def main():
                     "timing": "wall clock around msx_bgen_step (per-stream delay rings on the host, one msx_batch_step, host sync inside every call)"},
             "step_bytes": {"weights_read_once": w_bytes, "kv_avg": 0.5 * (bkv0 + bkv1), "gbs": b_bytes / (ms_b / Kb * 1e-3) / 1e9},
             "launches_per_frame": batch.launches_per_frame, "steps": Kb,
-            "gemm": {"kernel": "gemm_q4k_kernel gating.linear_in (mma.sync m16n8k32 u8 x s8, TMA unit ring, silu gate)",
+            "gemm": {"kernel": "dq_matmul_q4k_kernel gating.linear_in (mma.sync m16n8k32 u8 x s8, TMA unit ring, silu gate)",
                      "launch_us": gemm_us, "achieved": dom_bytes / (gemm_us * 1e-6) / 1e9 if gemm_us else None,
                      "frac": dom_bytes / (gemm_us * 1e-6) / 1e9 / peaks["hbm_gbs"] if gemm_us else None,
                      "how": "200 launches in one CUDA graph over 8 rotating matrices, activations pre-quantised"},
@@ -521,7 +521,7 @@ def main():
                              "e2e": {"value": world * nw * Kw / (ms_we * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": 336 * nw,
                                      "d2h_bytes_per_step": 176 * nw, "timing": "wall clock around msx_bgen_step"}})
                 wb.close()
-        batched["wide"] = {"kernel": "tc_gemm_q4k_kernel<16|32|64> (tcgen05.mma kind::i8, accumulators in tensor memory, exact Q4_K x Q8_K)",
+        batched["wide"] = {"kernel": "tc_matmul_q4k_kernel<16|32|64> (tcgen05.mma kind::i8, accumulators in tensor memory, exact Q4_K x Q8_K)",
                            "what": "the same lock-step batch with more conversations per GPU; device-timed resident replay", "runs": wide}
 
     # ---- persistent step kernel (opt-in path), for the record --------------------------------------------------

@@ -132,7 +132,7 @@ struct BatchLauncher {
     void tc_gemm(const QLinear &w, float *out, int ld, int epi, int family, int key_index, const EmbTable *emb, int emb_step, const uint8_t *img) {
         auto it = b->m->wtc.find(w.qs);
         if (it == b->m->wtc.end()) { err = fail(MSX_ERR_STATE, "linear without a tensor-core layout in a wide batch"); return; }
-        tc::TcGemmArgs g;
+        tc::TcMatmulArgs g;
         g.w = it->second; g.K = w.K; g.rows = w.rows; g.img = img ? img : b->img; g.out = out; g.ld = ld; g.nb = b->n_active;
         g.epi = (epi == EPI_ARGMAX || epi == EPI_ADD_EMB) ? (int)EPI_STORE : epi;
         g.partial = b->tc_partial; g.tickets = b->tc_tickets;
@@ -140,9 +140,9 @@ struct BatchLauncher {
         const dim3 grid(tc::grid_for(w.rows / tc::kM, w.K >> 8, L.num_sms)), block(tc::kThreads);
         L.fam = family; L.begin();
         const int nc = tc::columns_for(b->n_active);
-        if (nc == 16) L.launch_pdl(tc::tc_gemm_q4k_kernel<16>, grid, block, (size_t)tc::kSmemBytes, g);
-        else if (nc == 32) L.launch_pdl(tc::tc_gemm_q4k_kernel<32>, grid, block, (size_t)tc::kSmemBytes, g);
-        else L.launch_pdl(tc::tc_gemm_q4k_kernel<64>, grid, block, (size_t)tc::kSmemBytes, g);
+        if (nc == 16) L.launch_pdl(tc::tc_matmul_q4k_kernel<16>, grid, block, (size_t)tc::kSmemBytes, g);
+        else if (nc == 32) L.launch_pdl(tc::tc_matmul_q4k_kernel<32>, grid, block, (size_t)tc::kSmemBytes, g);
+        else L.launch_pdl(tc::tc_matmul_q4k_kernel<64>, grid, block, (size_t)tc::kSmemBytes, g);
         L.check();
         if (epi == EPI_ARGMAX) {
             L.begin();
@@ -157,7 +157,7 @@ struct BatchLauncher {
     void gemm(const QLinear &w, float *out, int ld, int epi, int family, int key_index = -1, const EmbTable *emb = nullptr, int emb_step = 0,
               const uint8_t *img = nullptr, const float *xsrc = nullptr, int xld = 0, const float *alpha = nullptr) {
         if (b->tc) { tc_gemm(w, out, ld, epi, family, key_index, emb, emb_step, img); return; }
-        GemmArgs g;
+        MatmulArgs g;
         if (int e = tiles_of(b->m, w, &g.w)) { err = e; return; }
         g.xsrc = xsrc; g.xld = xld; g.alpha = alpha; g.eps = 1e-8f;
         g.img = img ? img : b->img; g.out = out; g.ld = ld; g.nb = b->n_active; g.epi = epi; g.ctrl = b->ctrl; g.key_index = key_index; g.emb_step = emb_step;
@@ -168,12 +168,12 @@ struct BatchLauncher {
         const size_t smem = (size_t)gemm_smem_bytes(w.K, g.stages, w.type);
         const bool lean = epi == EPI_STORE || epi == EPI_RESID || epi == EPI_GATE;
         if (w.type == T_Q4_K) {
-            if (lean && xsrc) L.launch_pdl(gemm_mma_kernel<12, 2>, grid, block, smem, g);
-            else if (lean) L.launch_pdl(gemm_mma_kernel<12, 1>, grid, block, smem, g);
-            else L.launch_pdl(gemm_mma_kernel<12, 0>, grid, block, smem, g);
+            if (lean && xsrc) L.launch_pdl(dq_matmul_mma_kernel<12, 2>, grid, block, smem, g);
+            else if (lean) L.launch_pdl(dq_matmul_mma_kernel<12, 1>, grid, block, smem, g);
+            else L.launch_pdl(dq_matmul_mma_kernel<12, 0>, grid, block, smem, g);
         } else {
-            if (lean) L.launch_pdl(gemm_mma_kernel<8, 1>, grid, block, smem, g);
-            else L.launch_pdl(gemm_mma_kernel<8, 0>, grid, block, smem, g);
+            if (lean) L.launch_pdl(dq_matmul_mma_kernel<8, 1>, grid, block, smem, g);
+            else L.launch_pdl(dq_matmul_mma_kernel<8, 0>, grid, block, smem, g);
         }
         L.check();
     }
@@ -345,15 +345,15 @@ static int batch_create_impl(msx_model *m, int n_streams, int context_override, 
         return fail(MSX_ERR_ARG, "batched streams do not cover the TTS-family layers (cross-attention, demux / low-rank embeddings)");
     CU(cudaSetDevice(m->device));
     if (int e = set_smem_attrs()) return e;
-    CU(cudaFuncSetAttribute(gemm_mma_kernel<12, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemMax));
-    CU(cudaFuncSetAttribute(gemm_mma_kernel<12, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemMax));
-    CU(cudaFuncSetAttribute(gemm_mma_kernel<12, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemMax));
-    CU(cudaFuncSetAttribute(gemm_mma_kernel<8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemMax));
-    CU(cudaFuncSetAttribute(gemm_mma_kernel<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemMax));
+    CU(cudaFuncSetAttribute(dq_matmul_mma_kernel<12, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemMax));
+    CU(cudaFuncSetAttribute(dq_matmul_mma_kernel<12, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemMax));
+    CU(cudaFuncSetAttribute(dq_matmul_mma_kernel<12, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemMax));
+    CU(cudaFuncSetAttribute(dq_matmul_mma_kernel<8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemMax));
+    CU(cudaFuncSetAttribute(dq_matmul_mma_kernel<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemMax));
     if (tc_mode) {
-        CU(cudaFuncSetAttribute(tc::tc_gemm_q4k_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes));
-        CU(cudaFuncSetAttribute(tc::tc_gemm_q4k_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes));
-        CU(cudaFuncSetAttribute(tc::tc_gemm_q4k_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes));
+        CU(cudaFuncSetAttribute(tc::tc_matmul_q4k_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes));
+        CU(cudaFuncSetAttribute(tc::tc_matmul_q4k_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes));
+        CU(cudaFuncSetAttribute(tc::tc_matmul_q4k_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes));
     }
     else if (int e = ensure_all_tiles(m)) return e;
     std::unique_ptr<msx_batch> b(new msx_batch);
@@ -693,18 +693,18 @@ extern "C" int msx_batch_profile_frame(msx_batch *b, const int32_t *tokens, floa
     return 0;
 }
 
-// test hook: y[nb][rows] = W x[nb][k] through quant_q8k_kernel + gemm_q4k_kernel (EPI_STORE)
+// test hook: y[nb][rows] = W x[nb][k] through quant_q8k_kernel + dq_matmul_q4k_kernel (EPI_STORE)
 extern "C" int msx_test_gemm_batch(int device, int type, const void *w, int64_t k, int64_t rows, const float *x, int nb, const float *alpha,
                                    float *y) {
     if (!w || !x || !y || nb < 1 || nb > kMmaCols) return fail(MSX_ERR_ARG, "bad argument");
     std::unique_ptr<msx_model> m;
     if (int e = device_setup(device, m)) return e;
-    CU(cudaFuncSetAttribute(gemm_q4k_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemMax));
+    CU(cudaFuncSetAttribute(dq_matmul_q4k_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemMax));
     QLinear ql;
     if (int e = upload_linear(m.get(), w, type, k, rows, 0, &ql)) return e;
     QTiles qt;
     if (int e = tiles_of(m.get(), ql, &qt)) return e;
-    CU(cudaFuncSetAttribute(gemm_q8_0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemMax));
+    CU(cudaFuncSetAttribute(dq_matmul_q8_0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemMax));
     if (gemm_stages_for((int)k, type) < 2) return fail(MSX_ERR_ARG, "k too large");
     float *dx = nullptr, *dy = nullptr, *da = nullptr; uint8_t *img = nullptr;
     if (int e = dev_alloc(m.get(), (void **)&dx, (size_t)nb * k * 4)) return e;
@@ -720,11 +720,11 @@ extern "C" int msx_test_gemm_batch(int device, int type, const void *w, int64_t 
     q.x = dx; q.ld = (int)k; q.alpha = da; q.eps = 1e-8f; q.img = img; q.K = (int)k;
     if (type == T_Q4_K) quant_q8k_kernel<<<dim3(nb, quant_parts_for((int)k)), kGemmThreads>>>(q);
     else quant_q8_0_kernel<<<dim3(nb, quant_parts_for((int)k)), kGemmThreads>>>(q);
-    GemmArgs g;
+    MatmulArgs g;
     g.w = qt; g.img = img; g.out = dy; g.ld = (int)rows; g.nb = nb; g.epi = EPI_STORE;
     g.stages = gemm_stages_for((int)k, type);
-    if (type == T_Q4_K) gemm_q4k_kernel<<<gemm_grid_for(qt.n_tiles, m->num_sms), kGemmThreads, gemm_smem_bytes((int)k, g.stages, 12)>>>(g);
-    else gemm_q8_0_kernel<<<gemm_grid_for(qt.n_tiles, m->num_sms), kGemmThreads, gemm_smem_bytes((int)k, g.stages, 8)>>>(g);
+    if (type == T_Q4_K) dq_matmul_q4k_kernel<<<gemm_grid_for(qt.n_tiles, m->num_sms), kGemmThreads, gemm_smem_bytes((int)k, g.stages, 12)>>>(g);
+    else dq_matmul_q8_0_kernel<<<gemm_grid_for(qt.n_tiles, m->num_sms), kGemmThreads, gemm_smem_bytes((int)k, g.stages, 8)>>>(g);
     CU(cudaGetLastError());
     CU(cudaDeviceSynchronize());
     CU(cudaMemcpy(y, dy, (size_t)nb * rows * 4, cudaMemcpyDeviceToHost));
@@ -743,7 +743,7 @@ extern "C" int msx_bench_gemm_batch_ex(int device, const void *w, int64_t k, int
     if (!w || !avg_us || n_mats < 1 || iters < 1 || nb < 1 || nb > kMmaCols) return fail(MSX_ERR_ARG, "bad argument");
     std::unique_ptr<msx_model> m;
     if (int e = device_setup(device, m)) return e;
-    CU(cudaFuncSetAttribute(gemm_q4k_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemMax));
+    CU(cudaFuncSetAttribute(dq_matmul_q4k_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemMax));
     std::vector<QTiles> mats(n_mats);
     for (int i = 0; i < n_mats; i++) {
         QLinear ql;
@@ -775,11 +775,11 @@ extern "C" int msx_bench_gemm_batch_ex(int device, const void *w, int64_t k, int
         QuantArgs q;
         q.x = dx; q.ld = (int)k; q.eps = 1e-8f; q.img = img; q.K = (int)k;
         if (with_quant || i == 0) L.launch_pdl(quant_q8k_kernel, dim3(nb, quant_parts_for((int)k)), dim3(kGemmThreads), 0, q);
-        GemmArgs g;
+        MatmulArgs g;
         g.w = mats[i % n_mats]; g.img = img; g.out = dy; g.ld = (int)(epilogue == EPI_GATE ? rows / 2 : rows); g.nb = nb; g.epi = epilogue; g.ctrl = ctrl;
         if (d_stamps) g.stamps = d_stamps + (size_t)i * 148 * 8;
         g.stages = gemm_stages_for((int)k);
-        L.launch_pdl(gemm_q4k_kernel, dim3(gemm_grid_for(g.w.n_tiles, m->num_sms)), dim3(kGemmThreads), (size_t)gemm_smem_bytes((int)k, g.stages), g);
+        L.launch_pdl(dq_matmul_q4k_kernel, dim3(gemm_grid_for(g.w.n_tiles, m->num_sms)), dim3(kGemmThreads), (size_t)gemm_smem_bytes((int)k, g.stages), g);
     }
     CU(cudaStreamEndCapture(st, &graph));
     if (L.err != cudaSuccess) return fail(MSX_ERR_CUDA, std::string("gemm launch: ") + cudaGetErrorString(L.err));

@@ -100,7 +100,7 @@ __device__ __forceinline__ uint32_t tp_seq(const TpCtx *tp, int idx) {
     return *reinterpret_cast<const volatile uint32_t *>(tp->frame_ctr) * (uint32_t)tp->reduces_per_frame + (uint32_t)idx + 1u;
 }
 
-struct GemvArgs {
+struct MatvecArgs {
     QLinear w;
     const float *x = nullptr;       // [K] activations (f32)
     const double *xparts = nullptr; // alternative input: x = sum of nparts double vectors (split-KV attention partials)

@@ -25,7 +25,7 @@ extern "C" int msx_stream_set_condition(msx_stream *s, const float *cond_sum, co
         for (int l = 0; l < c.num_layers; l++) {
             const QLinear kvw = linear_rows(m->layers[l].cross_in, dim, 2 * dim);
             for (int i = 0; i < tc; i++) {
-                GemvArgs g;
+                MatvecArgs g;
                 g.ctrl = s->ctrl; g.w = kvw; g.x = d_cross + (size_t)i * dim; g.out = s->kv_cross + ((size_t)l * tc + i) * 2 * dim;
                 L.gemv(g, PRO_PLAIN, EPI_STORE);
             }
@@ -123,7 +123,7 @@ extern "C" int msx_vad(msx_stream *s, float *vad) {
     const QLinear &w = m->extra_heads[2];
     if (w.rows > 64) return fail(MSX_ERR_ARG, "extra head wider than 64");
     Launcher L{s->st, m->num_sms};
-    GemvArgs g;
+    MatvecArgs g;
     g.ctrl = s->ctrl; g.w = w; g.x = s->tout; g.out = s->vad_logits;
     L.gemv(g, PRO_PLAIN, EPI_STORE);
     if (L.err != cudaSuccess) return fail(MSX_ERR_CUDA, cudaGetErrorString(L.err));

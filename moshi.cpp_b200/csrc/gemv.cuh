@@ -73,7 +73,7 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 // 8 consecutive activations starting at e0: plain f32 vector, or the sum of `nparts` double partial vectors
 // (attention context written by the split-KV phase of the persistent kernel)
 template <bool LEAN = false>
-__device__ __forceinline__ void load_x8(const GemvArgs &a, const float *xin, int e0, float (&v)[8]) {
+__device__ __forceinline__ void load_x8(const MatvecArgs &a, const float *xin, int e0, float (&v)[8]) {
     if (!LEAN && a.xparts) {
         double s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         for (int c = 0; c < a.nparts; c++) {
@@ -88,7 +88,7 @@ __device__ __forceinline__ void load_x8(const GemvArgs &a, const float *xin, int
     const float4 p0 = ld_act4(xin + e0), p1 = ld_act4(xin + e0 + 4);
     v[0] = p0.x; v[1] = p0.y; v[2] = p0.z; v[3] = p0.w; v[4] = p1.x; v[5] = p1.y; v[6] = p1.z; v[7] = p1.w;
 }
-__device__ __forceinline__ void load_alpha8(const GemvArgs &a, int e0, float (&al)[8]) {
+__device__ __forceinline__ void load_alpha8(const MatvecArgs &a, int e0, float (&al)[8]) {
     const float4 a0 = *reinterpret_cast<const float4 *>(a.alpha + e0), a1 = *reinterpret_cast<const float4 *>(a.alpha + e0 + 4);
     al[0] = a0.x; al[1] = a0.y; al[2] = a0.z; al[3] = a0.w; al[4] = a1.x; al[5] = a1.y; al[6] = a1.z; al[7] = a1.w;
 }
@@ -159,7 +159,7 @@ __device__ __forceinline__ void quantize_block_q8_0(int b, int lane, const float
 constexpr int kChunk = 3;
 
 template <int WT, int LAYOUT = 0, bool LEAN = false>
-__device__ __forceinline__ void gemv_prologue(const GemvArgs &a, const float *xin, const bool norm_out_cta, const int PRO, int K, int8_t *x8,
+__device__ __forceinline__ void gemv_prologue(const MatvecArgs &a, const float *xin, const bool norm_out_cta, const int PRO, int K, int8_t *x8,
                                               int *bs, float *dx, double *red, const BlockGeom &bg) {
     const int lane = threadIdx.x & 31, warp = uniform_warp_id();
     const int nblk = (K + 255) >> 8;
@@ -233,7 +233,7 @@ __device__ __forceinline__ void gemv_prologue(const GemvArgs &a, const float *xi
 
 // ---- epilogue ------------------------------------------------------------------------------------
 template <int R>
-__device__ __forceinline__ void gemv_epilogue(const GemvArgs &a, const int EPI, int r0, const float (&acc)[R], int emb_token,
+__device__ __forceinline__ void gemv_epilogue(const MatvecArgs &a, const int EPI, int r0, const float (&acc)[R], int emb_token,
                                               unsigned long long &best) {
 #pragma unroll
     for (int r = 0; r < R; r++) {
@@ -399,7 +399,7 @@ struct NoMid { __device__ __forceinline__ void operator()() const {} };
 // `mid` runs after the first weight steps have been requested and before the activation prologue: the PDL wait of the
 // standalone kernels, or wait + local attention of the fused kernel (its weights stream in under the attention)
 template <int WT, int LANES, bool PDL = false, bool TPPUSH = false, bool LEAN = false, typename Mid = NoMid>
-__device__ __forceinline__ void gemv_body(const GemvArgs &a, const float *x_over, const bool norm_out_cta, const int PRO, const int EPI,
+__device__ __forceinline__ void gemv_body(const MatvecArgs &a, const float *x_over, const bool norm_out_cta, const int PRO, const int EPI,
                                           uint8_t *smem, const int cta, const int n_cta, const BlockGeom bg,
                                           Mid mid = Mid()) {
     const float *xin = x_over ? x_over : a.x;
@@ -540,7 +540,7 @@ __device__ __forceinline__ void gemv_body(const GemvArgs &a, const float *x_over
 // warps to spread its 256-element blocks over (K = 11264: 3 block iterations per warp instead of 6)
 constexpr int kGemvThreads = 512;
 template <int WT, int LANES, bool TPPUSH = false, bool LEAN = false>
-__global__ void __launch_bounds__(kGemvThreads, 1) gemv_kernel(const GemvArgs a, const int pro, const int epi) {
+__global__ void __launch_bounds__(kGemvThreads, 1) dq_matvec_kernel(const MatvecArgs a, const int pro, const int epi) {
     extern __shared__ __align__(16) uint8_t smem[];
     griddep_launch();      // the next kernel may start launching: it prefetches its weights and then waits for us
     gemv_body<WT, LANES, true, TPPUSH, LEAN>(a, nullptr, blockIdx.x == 0, pro, epi, smem, blockIdx.x, gridDim.x, BlockGeom{kGemvThreads, kGemvThreads / 32});
@@ -549,7 +549,7 @@ __global__ void __launch_bounds__(kGemvThreads, 1) gemv_kernel(const GemvArgs a,
 // Several GEMVs of one shape over the SAME input in one launch (the depformer_in[k] . t_out of all codebook steps, which
 // do not depend on the serial chain): CTA blockIdx.x works on matrix blockIdx.x / per as CTA blockIdx.x % per of `per`.
 constexpr int kGemvMultiMax = 40;
-struct GemvMulti {
+struct MatvecMulti {
     const uint8_t *qs[kGemvMultiMax];
     const uint32_t *sc[kGemvMultiMax];
     const void *dd[kGemvMultiMax];
@@ -557,11 +557,11 @@ struct GemvMulti {
     int32_t per = 1;
 };
 template <int WT, int LANES>
-__global__ void __launch_bounds__(kGemvThreads, 1) gemv_multi_kernel(const GemvArgs a, const __grid_constant__ GemvMulti m, const int pro, const int epi) {
+__global__ void __launch_bounds__(kGemvThreads, 1) dq_matvec_multi_kernel(const MatvecArgs a, const __grid_constant__ MatvecMulti m, const int pro, const int epi) {
     extern __shared__ __align__(16) uint8_t smem[];
     griddep_launch();
     const int mat = blockIdx.x / m.per, cta = blockIdx.x - mat * m.per;
-    GemvArgs b = a;
+    MatvecArgs b = a;
     b.w.qs = m.qs[mat]; b.w.sc = m.sc[mat]; b.w.dd = m.dd[mat]; b.out = m.out[mat];
     gemv_body<WT, LANES, true, false, true>(b, nullptr, false, pro, epi, smem, cta, m.per, BlockGeom{kGemvThreads, kGemvThreads / 32});
 }

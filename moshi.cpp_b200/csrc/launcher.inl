@@ -59,7 +59,7 @@ struct Launcher {
     }
     bool pdl = true;
 
-    void gemv(const GemvArgs &a, int pro, int epi, int family = 0) {
+    void gemv(const MatvecArgs &a, int pro, int epi, int family = 0) {
         fam = family; begin();
         const int tr = tile_rows(a.w.gs);
         const int n_tiles = (a.w.rows + tr - 1) / tr;
@@ -67,42 +67,42 @@ struct Launcher {
         const int smem = gemv_smem_bytes(a.w.type, a.w.K);
         if (a.tp) {          // tensor-parallel partial sums pushed to the peers: separate instantiations
             if (a.w.type == T_Q4_K) {
-                if (a.w.gs == 32) launch_pdl(gemv_kernel<12, 32, true>, dim3(grid), dim3(kGemvThreads), smem, a, pro, epi);
-                else launch_pdl(gemv_kernel<12, 16, true>, dim3(grid), dim3(kGemvThreads), smem, a, pro, epi);
+                if (a.w.gs == 32) launch_pdl(dq_matvec_kernel<12, 32, true>, dim3(grid), dim3(kGemvThreads), smem, a, pro, epi);
+                else launch_pdl(dq_matvec_kernel<12, 16, true>, dim3(grid), dim3(kGemvThreads), smem, a, pro, epi);
             } else {
-                if (a.w.gs == 32) launch_pdl(gemv_kernel<8, 32, true>, dim3(grid), dim3(kGemvThreads), smem, a, pro, epi);
-                else launch_pdl(gemv_kernel<8, 16, true>, dim3(grid), dim3(kGemvThreads), smem, a, pro, epi);
+                if (a.w.gs == 32) launch_pdl(dq_matvec_kernel<8, 32, true>, dim3(grid), dim3(kGemvThreads), smem, a, pro, epi);
+                else launch_pdl(dq_matvec_kernel<8, 16, true>, dim3(grid), dim3(kGemvThreads), smem, a, pro, epi);
             }
         } else if ((epi == EPI_STORE || epi == EPI_RESID || epi == EPI_GATE) && !a.xparts && !a.norm_out) {
             // the lean kernels: store / residual / gate epilogues only (4 of every 5 launches of a frame)
             if (a.w.type == T_Q4_K) {
-                if (a.w.gs == 32) launch_pdl(gemv_kernel<12, 32, false, true>, dim3(grid), dim3(kGemvThreads), smem, a, pro, epi);
-                else launch_pdl(gemv_kernel<12, 16, false, true>, dim3(grid), dim3(kGemvThreads), smem, a, pro, epi);
+                if (a.w.gs == 32) launch_pdl(dq_matvec_kernel<12, 32, false, true>, dim3(grid), dim3(kGemvThreads), smem, a, pro, epi);
+                else launch_pdl(dq_matvec_kernel<12, 16, false, true>, dim3(grid), dim3(kGemvThreads), smem, a, pro, epi);
             } else {
-                if (a.w.gs == 32) launch_pdl(gemv_kernel<8, 32, false, true>, dim3(grid), dim3(kGemvThreads), smem, a, pro, epi);
-                else launch_pdl(gemv_kernel<8, 16, false, true>, dim3(grid), dim3(kGemvThreads), smem, a, pro, epi);
+                if (a.w.gs == 32) launch_pdl(dq_matvec_kernel<8, 32, false, true>, dim3(grid), dim3(kGemvThreads), smem, a, pro, epi);
+                else launch_pdl(dq_matvec_kernel<8, 16, false, true>, dim3(grid), dim3(kGemvThreads), smem, a, pro, epi);
             }
         } else if (a.w.type == T_Q4_K) {
-            if (a.w.gs == 32) launch_pdl(gemv_kernel<12, 32>, dim3(grid), dim3(kGemvThreads), smem, a, pro, epi);
-            else launch_pdl(gemv_kernel<12, 16>, dim3(grid), dim3(kGemvThreads), smem, a, pro, epi);
+            if (a.w.gs == 32) launch_pdl(dq_matvec_kernel<12, 32>, dim3(grid), dim3(kGemvThreads), smem, a, pro, epi);
+            else launch_pdl(dq_matvec_kernel<12, 16>, dim3(grid), dim3(kGemvThreads), smem, a, pro, epi);
         } else {
-            if (a.w.gs == 32) launch_pdl(gemv_kernel<8, 32>, dim3(grid), dim3(kGemvThreads), smem, a, pro, epi);
-            else launch_pdl(gemv_kernel<8, 16>, dim3(grid), dim3(kGemvThreads), smem, a, pro, epi);
+            if (a.w.gs == 32) launch_pdl(dq_matvec_kernel<8, 32>, dim3(grid), dim3(kGemvThreads), smem, a, pro, epi);
+            else launch_pdl(dq_matvec_kernel<8, 16>, dim3(grid), dim3(kGemvThreads), smem, a, pro, epi);
         }
         check();
     }
 
     // n GEMVs of one shape over the same input in one launch (lean store epilogue)
-    void gemv_multi(const GemvArgs &a, const GemvMulti &mm, int n, int family) {
+    void gemv_multi(const MatvecArgs &a, const MatvecMulti &mm, int n, int family) {
         fam = family; begin();
         const int smem = gemv_smem_bytes(a.w.type, a.w.K);
         const dim3 grid(n * mm.per), block(kGemvThreads);
         if (a.w.type == T_Q4_K) {
-            if (a.w.gs == 32) launch_pdl(gemv_multi_kernel<12, 32>, grid, block, smem, a, mm, (int)PRO_PLAIN, (int)EPI_STORE);
-            else launch_pdl(gemv_multi_kernel<12, 16>, grid, block, smem, a, mm, (int)PRO_PLAIN, (int)EPI_STORE);
+            if (a.w.gs == 32) launch_pdl(dq_matvec_multi_kernel<12, 32>, grid, block, smem, a, mm, (int)PRO_PLAIN, (int)EPI_STORE);
+            else launch_pdl(dq_matvec_multi_kernel<12, 16>, grid, block, smem, a, mm, (int)PRO_PLAIN, (int)EPI_STORE);
         } else {
-            if (a.w.gs == 32) launch_pdl(gemv_multi_kernel<8, 32>, grid, block, smem, a, mm, (int)PRO_PLAIN, (int)EPI_STORE);
-            else launch_pdl(gemv_multi_kernel<8, 16>, grid, block, smem, a, mm, (int)PRO_PLAIN, (int)EPI_STORE);
+            if (a.w.gs == 32) launch_pdl(dq_matvec_multi_kernel<8, 32>, grid, block, smem, a, mm, (int)PRO_PLAIN, (int)EPI_STORE);
+            else launch_pdl(dq_matvec_multi_kernel<8, 16>, grid, block, smem, a, mm, (int)PRO_PLAIN, (int)EPI_STORE);
         }
         check();
     }
@@ -112,14 +112,14 @@ struct Launcher {
     }
 
     // fused local attention + out_proj (tiny rings)
-    void gemv_local_attn(const GemvArgs &g, const AttnArgs &a, int heads, int dh, int pro, int epi, int family = 0) {
+    void gemv_local_attn(const MatvecArgs &g, const AttnArgs &a, int heads, int dh, int pro, int epi, int family = 0) {
         fam = family; begin();
         const int tr = tile_rows(g.w.gs);
         const int n_tiles = (g.w.rows + tr - 1) / tr;
         const int grid = std::max(1, std::min(num_sms, (n_tiles + kTilesPerCta - 1) / kTilesPerCta));
         const int region = (gemv_smem_bytes(g.w.type, g.w.K) + 15) / 16 * 16;
         const int smem = local_attn_smem_bytes(region, a.dim, dh);
-#define MSX_LA(WT, LN, DH) launch_pdl(gemv_local_attn_kernel<WT, LN, DH>, dim3(grid), dim3(kGemvThreads), smem, g, a, heads, pro, epi, region)
+#define MSX_LA(WT, LN, DH) launch_pdl(dq_matvec_local_attn_kernel<WT, LN, DH>, dim3(grid), dim3(kGemvThreads), smem, g, a, heads, pro, epi, region)
         if (g.w.type == T_Q4_K) {
             if (g.w.gs == 32) { if (dh == 64) MSX_LA(12, 32, 64); else MSX_LA(12, 32, 128); }
             else { if (dh == 64) MSX_LA(12, 16, 64); else MSX_LA(12, 16, 128); }

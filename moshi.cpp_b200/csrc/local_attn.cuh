@@ -147,7 +147,7 @@ __device__ __forceinline__ void attn_local(const AttnArgs &a, int heads, float *
 // Used by the PDL-chained path for transformers whose ring is tiny (depformer: <= 64 slots): one launch
 // instead of attention + out_proj.  smem: [gemv region][ctx_s dim floats][attn scratch]
 template <int WT, int LANES, int DH>
-__global__ void __launch_bounds__(kGemvThreads, 1) gemv_local_attn_kernel(const GemvArgs g, const AttnArgs a, const int heads, const int pro,
+__global__ void __launch_bounds__(kGemvThreads, 1) dq_matvec_local_attn_kernel(const MatvecArgs g, const AttnArgs a, const int heads, const int pro,
                                                                           const int epi, const int gemv_region) {
     extern __shared__ __align__(16) uint8_t smem[];
     griddep_launch();

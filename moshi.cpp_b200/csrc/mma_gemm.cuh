@@ -344,7 +344,7 @@ __global__ void __launch_bounds__(kGemmThreads) quant_q8_0_kernel(const QuantArg
 }
 
 // ---- the GEMM -----------------------------------------------------------------------------------------
-struct GemmArgs {
+struct MatmulArgs {
     QTiles w;
     const uint8_t *img = nullptr;     // activation image of this input (act_image_bytes(K))
     float *out = nullptr; int32_t ld = 0;   // out[col * ld + row]
@@ -446,7 +446,7 @@ __device__ __forceinline__ void unit_compute(const uint8_t *slot, const uint8_t 
 }
 
 // fused prologue: (column, block) pairs p = warp, warp + 16, ... ; same arithmetic and image layout as quant_q8k_kernel
-__device__ __forceinline__ void fused_quant_columns(const GemmArgs &a, uint8_t *img, double *sscratch, int warp, int lane) {
+__device__ __forceinline__ void fused_quant_columns(const MatmulArgs &a, uint8_t *img, double *sscratch, int warp, int lane) {
     const int K = a.w.K, nblk = K >> 8, npairs = a.nb * nblk;
     const bool norm = a.alpha != nullptr;
     float v[kFusedMaxPairs][8], al[kFusedMaxPairs][8];
@@ -553,7 +553,7 @@ __device__ __forceinline__ void round_next(WarpRound &w, int warp, int nsb) {
 // kernel), 2 = lean with the fused short-K activation prologue.  One small body per kernel: consecutive launches of a frame
 // alternate between variants, and kernel size costs instruction-cache misses (see gemv.cuh).
 template <int WT, int VAR = 0>
-__global__ void __launch_bounds__(kGemmThreads, 1) gemm_mma_kernel(const GemmArgs a) {
+__global__ void __launch_bounds__(kGemmThreads, 1) dq_matmul_mma_kernel(const MatmulArgs a) {
     constexpr bool LEAN = VAR != 0, FUSED = VAR == 2 || (VAR == 0 && WT == 12);
     constexpr int kUB = unit_bytes_of(WT);
     extern __shared__ __align__(16) uint8_t smem[];
@@ -716,8 +716,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_mma_kernel(const GemmArg
     }
 }
 
-#define gemm_q4k_kernel gemm_mma_kernel<12, 0>
-#define gemm_q8_0_kernel gemm_mma_kernel<8, 0>
+#define dq_matmul_q4k_kernel dq_matmul_mma_kernel<12, 0>
+#define dq_matmul_q8_0_kernel dq_matmul_mma_kernel<8, 0>
 __host__ inline int gemm_grid_for(int n_tiles, int num_sms) { return n_tiles < num_sms ? n_tiles : num_sms; }
 
 }  // namespace msx

@@ -106,7 +106,7 @@ void enqueue_layer(Launcher &L, const msx_stream *s, const LayerW &lw, int w, bo
     const int cap = temporal ? s->cap : m->dep_cap;
     float *x = temporal ? s->x : s->dx, *qkv = temporal ? s->qkv : s->dqkv, *ctx = temporal ? s->ctx : s->dctx, *gate = temporal ? s->gate : s->dgate;
     // out[dim] += W_shard . in : partial sums in double -> NCCL all-reduce (sum) -> rounded once into the residual stream
-    auto reduce_into_x = [&](GemvArgs &gg, int family) {
+    auto reduce_into_x = [&](MatvecArgs &gg, int family) {
         if (s->tp_p2p) {
             // GEMV pushes its partial sums into every rank's inbox over NVLink; the consumer waits for the flags
             const int idx = 2 * layer + (family == FAM_LIN_OUT ? 1 : 0);
@@ -128,7 +128,7 @@ void enqueue_layer(Launcher &L, const msx_stream *s, const LayerW &lw, int w, bo
         L.launch_pdl(tp_apply_kernel, dim3((dim + 255) / 256), dim3(256), 0, x, (const double *)s->tp_partial, dim);
         L.check();
     };
-    GemvArgs g;
+    MatvecArgs g;
     g.ctrl = s->ctrl; g.eps = 1e-8f;
     // x -> rms_norm1 -> in_proj -> qkv
     g.w = lw.in_proj[w]; g.x = x; g.alpha = lw.norm1; g.out = qkv;
@@ -186,7 +186,7 @@ void enqueue_temporal(Launcher &L, const msx_stream *s) {
         L.fam = FAM_EMBED; L.begin();
         L.launch_pdl(demux_rows_kernel, dim3((c.dim + 255) / 256), dim3(256), 0, dr);
         L.check();
-        GemvArgs g1;
+        MatvecArgs g1;
         g1.ctrl = s->ctrl; g1.w = m->text_out1; g1.x = s->demux_l; g1.out = s->demux_y1;
         L.gemv(g1, PRO_PLAIN, EPI_STORE, FAM_EMBED);
         g1.w = m->text_out2; g1.x = s->demux_r; g1.out = s->demux_y2;
@@ -200,7 +200,7 @@ void enqueue_temporal(Launcher &L, const msx_stream *s) {
     L.check();
     for (int l = 0; l < c.num_layers; l++) enqueue_layer(L, s, m->layers[l], 0, true, l, -1);
     // out_norm -> transformer_out (kept for depformer / VAD) -> text_linear -> greedy token (lm.h:671-674, 864-868)
-    GemvArgs g;
+    MatvecArgs g;
     g.ctrl = s->ctrl; g.eps = 1e-8f;
     g.w = m->text_linear; g.x = s->x; g.alpha = m->out_norm; g.norm_out = s->tout; g.out = s->text_logits;
     g.key = &s->ctrl->text_key;
@@ -225,12 +225,12 @@ void enqueue_depformer(Launcher &L, const msx_stream *s) {
     // (same kernel body, same arithmetic); the steps then only add the previous token's embedding (lm.h:464-467, 494-516)
     const bool hoist = c.dep_q <= kGemvMultiMax;
     if (hoist) {
-        GemvMulti mm;
+        MatvecMulti mm;
         for (int k = 0; k < c.dep_q; k++) {
             const QLinear &w = m->dep_in[weights_of(k)];
             mm.qs[k] = w.qs; mm.sc[k] = w.sc; mm.dd[k] = w.dd; mm.out[k] = s->dep_d + (size_t)k * c.dep_dim;
         }
-        GemvArgs g;
+        MatvecArgs g;
         g.ctrl = s->ctrl; g.eps = 1e-8f; g.w = m->dep_in[weights_of(0)]; g.x = s->tout; g.out = s->dep_d;
         mm.per = L.gemv_ctas(g.w);
         L.gemv_multi(g, mm, c.dep_q, FAM_DEP_IN);
@@ -238,7 +238,7 @@ void enqueue_depformer(Launcher &L, const msx_stream *s) {
     for (int k = 0; k < c.dep_q; k++) {
         const int w = weights_of(k);
         const float *dk = s->dep_d + (size_t)k * c.dep_dim;
-        GemvArgs g;
+        MatvecArgs g;
         g.ctrl = s->ctrl; g.eps = 1e-8f;
         g.w = m->dep_in[w]; g.x = s->tout; g.out = s->dx;
         if (m->dep_small) {
@@ -274,7 +274,7 @@ void enqueue_depformer(Launcher &L, const msx_stream *s) {
         }
         for (int l = 0; l < c.dep_layers; l++) enqueue_layer(L, s, m->dep_layers[l], w, false, l, k);
         // linears[k] -> logits -> greedy token (no final norm, lm.h:472)
-        GemvArgs h;
+        MatvecArgs h;
         h.ctrl = s->ctrl;
         h.w = m->linears[k]; h.x = s->dx; h.out = s->audio_logits + (size_t)k * c.card; h.key = &s->ctrl->audio_key[k];
         L.gemv(h, PRO_PLAIN, EPI_ARGMAX, FAM_DEP_HEAD);
@@ -312,30 +312,30 @@ int capture(msx_stream *s, F &&body, cudaGraphExec_t *exec, int *launches) {
 
 int set_smem_attrs() {
     const int big = 220 * 1024;   // dynamic part; the kernels also have a little static shared memory
-    CU(cudaFuncSetAttribute(gemv_kernel<12, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    CU(cudaFuncSetAttribute(gemv_multi_kernel<12, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    CU(cudaFuncSetAttribute(gemv_multi_kernel<12, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    CU(cudaFuncSetAttribute(gemv_multi_kernel<8, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    CU(cudaFuncSetAttribute(gemv_multi_kernel<8, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    CU(cudaFuncSetAttribute(gemv_kernel<12, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    CU(cudaFuncSetAttribute(gemv_kernel<8, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    CU(cudaFuncSetAttribute(gemv_kernel<8, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    CU(cudaFuncSetAttribute(gemv_kernel<12, 32, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    CU(cudaFuncSetAttribute(gemv_kernel<12, 16, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    CU(cudaFuncSetAttribute(gemv_kernel<8, 32, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    CU(cudaFuncSetAttribute(gemv_kernel<8, 16, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    CU(cudaFuncSetAttribute(gemv_kernel<12, 32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    CU(cudaFuncSetAttribute(gemv_kernel<12, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    CU(cudaFuncSetAttribute(gemv_kernel<8, 32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    CU(cudaFuncSetAttribute(gemv_kernel<8, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    CU(cudaFuncSetAttribute(gemv_local_attn_kernel<12, 32, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    CU(cudaFuncSetAttribute(gemv_local_attn_kernel<12, 32, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    CU(cudaFuncSetAttribute(gemv_local_attn_kernel<12, 16, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    CU(cudaFuncSetAttribute(gemv_local_attn_kernel<12, 16, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    CU(cudaFuncSetAttribute(gemv_local_attn_kernel<8, 32, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    CU(cudaFuncSetAttribute(gemv_local_attn_kernel<8, 32, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    CU(cudaFuncSetAttribute(gemv_local_attn_kernel<8, 16, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    CU(cudaFuncSetAttribute(gemv_local_attn_kernel<8, 16, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU(cudaFuncSetAttribute(dq_matvec_kernel<12, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU(cudaFuncSetAttribute(dq_matvec_multi_kernel<12, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU(cudaFuncSetAttribute(dq_matvec_multi_kernel<12, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU(cudaFuncSetAttribute(dq_matvec_multi_kernel<8, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU(cudaFuncSetAttribute(dq_matvec_multi_kernel<8, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU(cudaFuncSetAttribute(dq_matvec_kernel<12, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU(cudaFuncSetAttribute(dq_matvec_kernel<8, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU(cudaFuncSetAttribute(dq_matvec_kernel<8, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU(cudaFuncSetAttribute(dq_matvec_kernel<12, 32, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU(cudaFuncSetAttribute(dq_matvec_kernel<12, 16, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU(cudaFuncSetAttribute(dq_matvec_kernel<8, 32, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU(cudaFuncSetAttribute(dq_matvec_kernel<8, 16, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU(cudaFuncSetAttribute(dq_matvec_kernel<12, 32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU(cudaFuncSetAttribute(dq_matvec_kernel<12, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU(cudaFuncSetAttribute(dq_matvec_kernel<8, 32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU(cudaFuncSetAttribute(dq_matvec_kernel<8, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU(cudaFuncSetAttribute(dq_matvec_local_attn_kernel<12, 32, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU(cudaFuncSetAttribute(dq_matvec_local_attn_kernel<12, 32, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU(cudaFuncSetAttribute(dq_matvec_local_attn_kernel<12, 16, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU(cudaFuncSetAttribute(dq_matvec_local_attn_kernel<12, 16, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU(cudaFuncSetAttribute(dq_matvec_local_attn_kernel<8, 32, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU(cudaFuncSetAttribute(dq_matvec_local_attn_kernel<8, 32, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU(cudaFuncSetAttribute(dq_matvec_local_attn_kernel<8, 16, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    CU(cudaFuncSetAttribute(dq_matvec_local_attn_kernel<8, 16, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     CU(cudaFuncSetAttribute(sk::step_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, sk::kSmemBytes));
     CU(cudaFuncSetAttribute(sk::step_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, sk::kSmemBytes));
     // all kernels stay below the 48 KB default except long-context attention with split 1

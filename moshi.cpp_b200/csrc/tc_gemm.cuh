@@ -20,7 +20,7 @@
 // (d) sixteen warps read the accumulators back with tcgen05.ld (warp = 32 TMEM lanes x columns / 4) and fold them into their double
 // accumulators.  The accumulators are double-buffered in tensor memory, so the tensor cores work on step i + 1 while the CUDA
 // cores fold step i and expand step i + 2 (pipeline at the shared-memory map below).  The launch is persistent: one CTA per SM
-// walks a contiguous range of the matrix's step sequence (stream-K, see TcGemmArgs).  Descriptor encodings pinned by
+// walks a contiguous range of the matrix's step sequence (stream-K, see TcMatmulArgs).  Descriptor encodings pinned by
 // scripts/tcgen05_probe.cu; measurements and the optimisation log in profiles/r2_tcgen05_prefill.md.
 #pragma once
 #include <algorithm>
@@ -64,7 +64,7 @@ constexpr int kTmemCols = 256;                         // set s at 128 s: [0, 64
 // instruction descriptor, kind::i8 (cute/arch/mma_sm100_desc.hpp): D = S32, A = B = signed 8 bit, both K-major, N >> 3, M >> 4
 __host__ __device__ constexpr uint32_t idesc_for(int n) { return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kM >> 4) << 24); }
 
-struct TcGemmArgs {
+struct TcMatmulArgs {
     const uint8_t *w = nullptr;       // tc layout: [rows / 128][K / 256][128 rows][144 B]
     int32_t K = 0, rows = 0;          // stored rows (gate / up interleaved for EPI_GATE)
     const uint8_t *img = nullptr;     // activation image (see image_bytes)
@@ -137,7 +137,7 @@ __device__ __forceinline__ void compute_barrier() { asm volatile("bar.sync 1, %0
 // NC = live activation columns rounded up to 16 / 32 / 64: the MMA's N, the columns a thread folds (NC / 4) and the bytes of the
 // activation tile a step copies all scale with it, so a batch of 16 streams does not pay for 64
 template <int NC>
-__global__ void __launch_bounds__(kThreads, 1) tc_gemm_q4k_kernel(const TcGemmArgs a) {
+__global__ void __launch_bounds__(kThreads, 1) tc_matmul_q4k_kernel(const TcMatmulArgs a) {
     constexpr int FC = NC / 4;                        // columns per compute thread
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -412,7 +412,7 @@ __global__ void __launch_bounds__(256) dep_embed_add_cols_kernel(const Ctrl *ctr
 
 __host__ inline int columns_for(int nb) { return nb <= 16 ? 16 : nb <= 32 ? 32 : 64; }
 __host__ inline const void *kernel_for(int nc) {
-    return nc == 16 ? (const void *)tc_gemm_q4k_kernel<16> : nc == 32 ? (const void *)tc_gemm_q4k_kernel<32> : (const void *)tc_gemm_q4k_kernel<64>;
+    return nc == 16 ? (const void *)tc_matmul_q4k_kernel<16> : nc == 32 ? (const void *)tc_matmul_q4k_kernel<32> : (const void *)tc_matmul_q4k_kernel<64>;
 }
 
 // GGUF row-major Q4_K blocks -> tc layout.  One thread per 16-byte piece; perm_half > 0 interleaves rows for the gated MLP

@@ -35,7 +35,7 @@ extern "C" int msx_test_gemv(int device, int type, const void *w, int64_t k, int
         CU(cudaMemcpy(da, alpha, (size_t)k * 4, cudaMemcpyHostToDevice));
     }
     Launcher L{nullptr, m->num_sms};
-    GemvArgs g;
+    MatvecArgs g;
     g.w = ql; g.x = dx; g.alpha = da; g.eps = 1e-8f; g.out = dy;
     L.gemv(g, prologue == PRO_RMS ? PRO_RMS : PRO_PLAIN, EPI_STORE);
     if (L.err != cudaSuccess) return fail(MSX_ERR_CUDA, std::string("gemv launch: ") + cudaGetErrorString(L.err));
@@ -76,7 +76,7 @@ extern "C" int msx_bench_gemv(int device, int type, const void *w, int64_t k, in
     cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
     CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
     for (int i = 0; i < iters; i++) {
-        GemvArgs g;
+        MatvecArgs g;
         g.w = mats[i % n_mats]; g.x = dx; g.alpha = da; g.eps = 1e-8f; g.out = dy; g.key = dkey;
         L.gemv(g, prologue, epilogue);
     }

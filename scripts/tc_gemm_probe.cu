@@ -9,7 +9,7 @@
 using namespace msx;
 int main() {
     int sms = 0; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
-    cudaFuncSetAttribute(tc::tc_gemm_q4k_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes);
+    cudaFuncSetAttribute(tc::tc_matmul_q4k_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes);
     long long *tl; cudaMalloc(&tl, 64 * 4 * 8); cudaMemset(tl, 0, 64 * 4 * 8);
     cudaMemcpyToSymbol(tc::g_tc_timeline, &tl, sizeof(tl));
     struct Shape { const char *name; int rows, K, epi; } shapes[] = {
@@ -23,14 +23,14 @@ int main() {
         cudaMalloc(&img, tc::image_bytes(sh.K)); cudaMemset(img, 0x01, tc::image_bytes(sh.K));
         cudaMalloc(&out, (size_t)64 * sh.rows * 4); cudaMemset(out, 0, (size_t)64 * sh.rows * 4);
         cudaMalloc(&partial, tc::partial_bytes(sms)); cudaMalloc(&tickets, tiles * 4); cudaMemset(tickets, 0, tiles * 4);
-        tc::TcGemmArgs g;
+        tc::TcMatmulArgs g;
         g.K = sh.K; g.rows = sh.rows; g.img = img; g.out = out; g.ld = sh.epi == EPI_GATE ? sh.rows / 2 : sh.rows; g.nb = 64; g.epi = sh.epi;
         g.partial = partial; g.tickets = tickets;
         const int grid = tc::grid_for(tiles, nsb, sms);
         cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
         for (int rep = 0; rep < 3; rep++) {
             cudaEventRecord(e0);
-            for (int i = 0; i < 20; i++) { g.w = w + (size_t)(i & 3) * wbytes; tc::tc_gemm_q4k_kernel<64><<<grid, tc::kThreads, tc::kSmemBytes>>>(g); }
+            for (int i = 0; i < 20; i++) { g.w = w + (size_t)(i & 3) * wbytes; tc::tc_matmul_q4k_kernel<64><<<grid, tc::kThreads, tc::kSmemBytes>>>(g); }
             cudaEventRecord(e1); cudaEventSynchronize(e1);
         }
         float ms; cudaEventElapsedTime(&ms, e0, e1);

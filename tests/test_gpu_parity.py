@@ -396,8 +396,8 @@ def test_full_7b_q4k_250_frames_vs_oracle(msx, orc, gguf_for, step_kernel):
 
 def test_full_7b_q4k_tcgen05_prefill_and_wide_batch_vs_oracle(msx, orc, gguf_for):
     """The tcgen05 paths at FULL size (32 layers, the GGUF bench.py times): (a) a 70-row prompt through msx_stream_prefill
-    (one 64-column pass + a 6-column tail on tc_gemm_q4k_kernel) against 70 serial oracle steps — KV rows bit-identical in the first
-    and last layer, next-frame logits within tolerance; (b) one frame of a 16-stream batch (tc_gemm_q4k_kernel<16>, all 32 layers +
+    (one 64-column pass + a 6-column tail on tc_matmul_q4k_kernel) against 70 serial oracle steps — KV rows bit-identical in the first
+    and last layer, next-frame logits within tolerance; (b) one frame of a 16-stream batch (tc_matmul_q4k_kernel<16>, all 32 layers +
     depformer) against 16 oracle states."""
     path, cfg = gguf_for("moshi7b", "q4_k")
     gm = msx.Model(path, cfg); om = orc.Model(path, cfg)
