@@ -521,6 +521,47 @@ def main():
                              "e2e": {"value": world * nw * Kw / (ms_we * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": 336 * nw,
                                      "d2h_bytes_per_step": 176 * nw, "timing": "wall clock around msx_bgen_step"}})
                 wb.close()
+        # ---- several batches at once: each msx_batch owns a CUDA stream, so the latency-bound launch chains of independent batches
+        #      fill each other's gaps when they are stepped from their own host threads ----
+        concurrent = []
+        if args.quant == "q4_k" and wide and "error" not in wide[-1]:
+            import threading
+            for n_b, n_s, ctx_c in [(2, 8, 0), (2, 64, 1024)]:
+                try:
+                    cbs = [msx.Batch(model, n_s, ctx_c) for _ in range(n_b)]
+                except Exception as e:                   # noqa: BLE001
+                    concurrent.append({"batches": n_b, "streams_per_batch": n_s, "error": str(e)[:160]})
+                    continue
+                cfr = [rngb.integers(0, cfg["card"], size=(n_s, 64, cfg["n_q"] + 1)).astype(np.int32) for _ in range(n_b)]
+                for f in cfr:
+                    f[:, :, 0] = rngb.integers(0, cfg["text_card"], size=(n_s, 64))
+                for cb, f in zip(cbs, cfr):
+                    cb.run_resident(f, 5)
+                Kc = min(K, 60)
+                dev_ms = [0.0] * n_b
+
+                def _work(i):
+                    dev_ms[i], _ = cbs[i].run_resident(cfr[i], Kc)
+                ths = [threading.Thread(target=_work, args=(i,)) for i in range(n_b)]
+                barrier(); torch.cuda.synchronize(local_rank)
+                t0 = time.perf_counter()
+                for t_ in ths:
+                    t_.start()
+                for t_ in ths:
+                    t_.join()
+                wall_c = (time.perf_counter() - t0) * 1e3
+                torch.cuda.synchronize(local_rank); barrier()
+                if dist is not None:
+                    t = torch.tensor([wall_c], device=f"cuda:{local_rank}", dtype=torch.float64)
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                    wall_c = float(t[0])
+                concurrent.append({"batches": n_b, "streams_per_batch": n_s, "streams_per_gpu": n_b * n_s, "context": ctx_c or cfg["context"],
+                                   "value": world * n_b * n_s * Kc / (wall_c * 1e-3), "unit": "frames/s (all streams, all GPUs)",
+                                   "ms_per_step_all_batches": wall_c / Kc, "device_ms_per_step_slowest_batch": max(dev_ms) / Kc, "steps": Kc,
+                                   "timing": "wall clock around the host threads (one msx_batch_run_resident each); device time of the slowest batch beside it"})
+                for cb in cbs:
+                    cb.close()
+        batched["concurrent_batches"] = concurrent
         batched["wide"] = {"kernel": "tc_matmul_q4k_kernel<16|32|64> (tcgen05.mma kind::i8, accumulators in tensor memory, exact Q4_K x Q8_K)",
                            "what": "the same lock-step batch with more conversations per GPU; device-timed resident replay", "runs": wide}
 
