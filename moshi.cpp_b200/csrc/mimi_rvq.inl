@@ -74,7 +74,7 @@ extern "C" void msx_rvq_free(msx_rvq *q) { delete q; }
 
 // mimi_quantizer_encode: x [T][dim] host -> codes [n_q][T] host
 extern "C" int msx_rvq_encode(msx_rvq *q, const float *x, int T, int n_q, int32_t *codes) {
-    if (!q || !x || !codes || T < 1 || n_q < 1 || n_q > q->n_sem + q->n_rest) return fail(MSX_ERR_ARG, "bad argument");
+    if (!q || !x || !codes || T < 1 || T > 65535 || n_q < 1 || n_q > q->n_sem + q->n_rest) return fail(MSX_ERR_ARG, "bad argument (1 <= T <= 65535 frames per call)");
     CU(cudaSetDevice(q->device));
     if (int e = rvq_reserve(q, T)) return e;
     CU(cudaMemcpyAsync(q->x, x, (size_t)T * q->dim * 4, cudaMemcpyHostToDevice, q->st));
@@ -96,7 +96,7 @@ extern "C" int msx_rvq_encode(msx_rvq *q, const float *x, int T, int n_q, int32_
 }
 // mimi_decode_latent: codes [K][T] host -> latent [T][dim] host
 extern "C" int msx_rvq_decode(msx_rvq *q, const int32_t *codes, int K, int T, float *y) {
-    if (!q || !codes || !y || T < 1 || K < 1 || K > q->n_sem + q->n_rest) return fail(MSX_ERR_ARG, "bad argument");
+    if (!q || !codes || !y || T < 1 || T > 65535 || K < 1 || K > q->n_sem + q->n_rest) return fail(MSX_ERR_ARG, "bad argument (1 <= T <= 65535 frames per call)");
     for (size_t i = 0; i < (size_t)K * T; i++)
         if (codes[i] < 0 || codes[i] >= q->bins) return fail(MSX_ERR_ARG, "code out of range");
     CU(cudaSetDevice(q->device));
@@ -119,7 +119,7 @@ extern "C" int msx_rvq_decode(msx_rvq *q, const int32_t *codes, int K, int T, fl
 }
 // device-timed repeat of encode / decode on resident buffers (bench hook): ms per call
 extern "C" int msx_rvq_bench(msx_rvq *q, int T, int n_q, int reps, float *encode_ms, float *decode_ms) {
-    if (!q || T < 1 || n_q < 1 || n_q > q->n_sem + q->n_rest || reps < 1) return fail(MSX_ERR_ARG, "bad argument");
+    if (!q || T < 1 || T > 65535 || n_q < 1 || n_q > q->n_sem + q->n_rest || reps < 1) return fail(MSX_ERR_ARG, "bad argument");
     CU(cudaSetDevice(q->device));
     if (int e = rvq_reserve(q, T)) return e;
     cudaEvent_t e0, e1;
