@@ -105,6 +105,32 @@ def test_oracle_ties_take_the_first_centroid_and_codes_of_centroids_round_trip()
     assert np.all(np.isfinite(errs))
 
 
+def _golden():
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_rvq.npz"))
+    return [g[k] for k in ("cb_first", "cb_rest", "in_first", "in_rest", "out_first", "out_rest")], g["x"], g["codes"], g["y"]
+
+
+def test_oracle_matches_committed_golden_vectors():
+    """tests/golden/golden_rvq.npz (written by make_golden_rvq.py from the numpy restatement): the C oracle reproduces it bit for bit"""
+    qz, x, codes, y = _golden()
+    o = oracle.SplitRVQ(*qz)
+    assert np.array_equal(o.encode(x, codes.shape[0]), codes)
+    assert np.array_equal(o.encode(x, 1), codes[:1])
+    assert np.array_equal(o.decode(codes).view(np.uint32), y.view(np.uint32))
+
+
+@pytest.mark.gpu
+def test_gpu_matches_committed_golden_vectors():
+    from moshi_cpp_b200 import binding as msx
+    qz, x, codes, y = _golden()
+    g = msx.RVQ(*qz)
+    assert np.array_equal(g.encode(x, codes.shape[0]), codes)
+    got = g.decode(codes)
+    assert np.max(np.abs(got - y)) <= 1e-6 * np.max(np.abs(y)) and np.mean(got.view(np.uint32) == y.view(np.uint32)) > 0.99
+    g.close()
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("T,n_q", [(1, 8), (33, 8), (7, 32), (375, 16)])
 def test_gpu_split_rvq_matches_oracle_at_mimi_sizes(T, n_q):
